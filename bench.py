@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: even-odd twisted-mass Dslash (BASELINE.json metric, config[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one application of the even-odd preconditioned twisted-mass Dslash (A^-1 D, parity hop)
+on the whole local lattice.  N=1 workload: 32^3 x 64, fp32, reconstruct-12 (BASELINE configs[1]); the
+half-precision variant of the same config is reported in `extra`.  N>1: weak scaling, every rank
+owns a 32^3 x 64 block of a lattice partitioned along T (one process per GPU, NCCL halo exchange).
+
+`value`   : GFLOP/s (1368 flop/site, the reference's own flop model, lib/dslash_quda.cuh:496-536 +
+            dslash_twisted_mass.cu:145) with fields resident in HBM, CUDA events on the library's stream.
+`e2e`     : the same metric through dslashQuda() with pinned HOST buffers (H2D + D2H inside the timing).
+`roofline`: compulsory bytes (576 B/site fp32 r12: 8 links x 48 B + in + out spinor) / kernel time vs
+            the measured HBM peak (MEASURED_PEAKS.json).
+`cpu_baseline`: the CPU oracle (OpenMP port of the reference's verify path) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_SITE = 1368
+BYTES_COMPULSORY = {(4, 12): 576, (2, 12): 296, (8, 12): 1152, (4, 18): 768, (4, 8): 448, (8, 18): 1536}
+BYTES_REFMODEL = {(4, 12): 1152, (2, 12): 612, (8, 12): 2304}
+LOCAL_X = (32, 32, 32, 64)
+KAPPA, MU = 0.1, 0.01
+
+
+def vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = []
+        for idx, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
+            if any(len(r) > idx and r[idx].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_inputs(oracle, X, seed):
+    oracle.set_dims(X)
+    g = oracle.gauge(kind=1, antiperiodic=True, seed=seed)
+    sp = oracle.drand(oracle.Vh * 24, seed=seed)
+    return g, sp
+
+
+def cpu_baseline_port(oracle, g, sp, budget_s=12.0):
+    """Oracle (OpenMP port) on the full 32^3x64 workload in fp32, bounded to ~budget_s seconds."""
+    cores = os.cpu_count() or 1
+    gf = [a.astype(np.float32) for a in g]
+    ef = sp.astype(np.float32)
+    oracle.set_dims(LOCAL_X)
+    t0 = time.perf_counter()
+    oracle.tm_dslash(gf, ef, KAPPA, MU, 1, 0, 0, 0)
+    first = time.perf_counter() - t0
+    reps = max(1, min(10, int(budget_s / max(first, 1e-3)) - 1))
+    best = first
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.tm_dslash(gf, ef, KAPPA, MU, 1, 0, 0, 0)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": FLOPS_PER_SITE * oracle.Vh / best / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+            "sample": f"{reps + 1} x fp32 tm_dslash on the full 32^3x64 lattice (oracle/tm_oracle.c, OpenMP over sites), best of",
+            "ms_per_step": best * 1e3}
+
+
+def _ref_worker(args):
+    """One process = one copy of the reference's own single-threaded tm_dslash on a 16^3x32 lattice."""
+    reps, seed = args
+    from tests import oracle_util as ou
+    ref = ou.load_ref()
+    orc = ou.load_oracle()
+    X = (16, 16, 16, 32)
+    ref.setup(X, antiperiodic=True)
+    orc.set_dims(X)
+    g = [a.astype(np.float32) for a in orc.gauge(kind=1, antiperiodic=True, seed=seed)]
+    sp = orc.drand(ref.Vh * 24, seed=seed).astype(np.float32)
+    ref.tm_dslash(g, sp, KAPPA, MU, 1, 0, 0, 0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ref.tm_dslash(g, sp, KAPPA, MU, 1, 0, 0, 0)
+    return (time.perf_counter() - t0) / reps, ref.Vh
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU Dslash (oracle/_ref, unmodified sources) on all host cores.
+    The code is single-threaded as shipped, so one independent copy runs per core (site-parallel work
+    has no cross-core dependency) and the aggregate rate is reported."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from tests import oracle_util as ou
+    cores = os.cpu_count() or 1
+    have_ref = ou.load_ref() is not None
+    steps, warmup = args.steps, args.warmup
+    times = []
+    if have_ref:
+        reps = 2
+        with mp.get_context("spawn").Pool(cores) as pool:
+            for s in range(warmup + steps):
+                t0 = time.perf_counter()
+                res = pool.map(_ref_worker, [(reps, 137 + i) for i in range(cores)])
+                if s >= warmup:
+                    # aggregate rate of this step: all copies run concurrently
+                    times.append(sum(FLOPS_PER_SITE * vh / t for t, vh in res) / 1e9)
+                if time.perf_counter() - t0 > 60 and len(times) >= 1:
+                    break
+        gflops = float(np.mean(times))
+        kind, sample = "reference", f"{cores} concurrent copies of the reference's tm_dslash (tests/wilson_dslash_reference.cpp, -O3, fp32) on 16^3x32, {reps} reps per step"
+        vh = 16 * 16 * 16 * 32 // 2
+        ms = FLOPS_PER_SITE * vh * cores / gflops / 1e6
+    else:
+        orc = ou.load_oracle()
+        g, sp = make_inputs(orc, LOCAL_X, 137)
+        b = cpu_baseline_port(orc, g, sp, budget_s=20.0)
+        gflops, kind, sample, ms = b["value"], "port", b["sample"], b["ms_per_step"]
+    line = {"impl": "reference", "metric": "tm_dslash_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": len(times) if times else steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "twisted-mass even-odd Dslash, fp32 (CPU verify path of the reference), lattice sample 16^3x32 per core"},
+            "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--prec", type=int, default=4, choices=[2, 4, 8])
+    ap.add_argument("--recon", type=int, default=12, choices=[8, 12, 18])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the half-precision extra measurement")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus != 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    import torch
+    import torch.distributed as dist
+    import quda_b200 as q
+    from tests import oracle_util as ou
+
+    torch.cuda.set_device(local_rank)
+    L = q.lib()
+    L.initQudaDevice(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            L.ncclUniqueIdQudaB200(buf)
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        L.commsBootstrapQudaB200(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        L.initCommsGridQuda(4, (C.c_int * 4)(1, 1, 1, world), None, None)
+    L.initQudaMemory()
+
+    oracle = ou.load_oracle()
+    X = LOCAL_X
+    g, sp = make_inputs(oracle, X, 137 + 17 * rank)
+    Vh = oracle.Vh
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_config(prec, recon, steps, warmup, with_e2e):
+        gp = q.gauge_param(X, cuda_prec=prec, reconstruct=recon)
+        L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+        p = q.invert_param(cuda_prec=prec)
+        fin = L.newSpinorQudaB200(q.QUDA_PARITY_SITE_SUBSET, prec)
+        fout = L.newSpinorQudaB200(q.QUDA_PARITY_SITE_SUBSET, prec)
+        L.loadSpinorQudaB200(fin, vp(sp), C.byref(p))
+        L.timeDslashQudaB200(fout, fin, C.byref(p), 0, warmup, None)
+        per = (C.c_float * steps)()
+        n0 = L.kernelLaunchCountQudaB200()
+        barrier()
+        t0 = time.perf_counter()
+        ms = L.timeDslashQudaB200(fout, fin, C.byref(p), 0, steps, per)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+        launches = L.kernelLaunchCountQudaB200() - n0
+        res = {"ms": ms, "wall_ms": wall_ms, "launches": launches, "per": list(per)}
+        if with_e2e:
+            # e2e: dslashQuda with pinned host buffers; H2D of the input and D2H of the result inside the timed region
+            hin = torch.from_numpy(sp.astype(np.float32 if prec != 8 else np.float64)).pin_memory()
+            hout = torch.empty_like(hin).pin_memory()
+            pe = q.invert_param(cuda_prec=prec, cpu_prec=(8 if prec == 8 else 4))
+            for _ in range(3):
+                L.dslashQuda(C.c_void_p(hout.data_ptr()), C.c_void_p(hin.data_ptr()), C.byref(pe), 0)
+            n = max(3, min(steps, 20))
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                L.dslashQuda(C.c_void_p(hout.data_ptr()), C.c_void_p(hin.data_ptr()), C.byref(pe), 0)
+            barrier()
+            res["e2e_ms"] = (time.perf_counter() - t0) * 1e3 / n
+            res["e2e_bytes"] = hin.numel() * hin.element_size()
+        L.freeSpinorQudaB200(fin)
+        L.freeSpinorQudaB200(fout)
+        return res
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    main_res = run_config(args.prec, args.recon, args.steps, args.warmup, True)
+    extra = {}
+    if not args.no_extra and args.prec == 4:
+        half = run_config(2, 12, args.steps, args.warmup, False)
+        extra["half_r12"] = half
+    sampler.stop_flag = True
+
+    # max over ranks of the device time
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = max_over_ranks(main_res["ms"])
+    e2e_ms = max_over_ranks(main_res["e2e_ms"])
+    half_ms = max_over_ranks(extra["half_r12"]["ms"]) if extra else None
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        sites = Vh * world
+        gflops = FLOPS_PER_SITE * sites / (ms * 1e-3) / 1e9
+        bpsite = BYTES_COMPULSORY[(args.prec, args.recon)]
+        # the hop kernel is the only kernel in a step at N=1; at N>1 pack + interior + boundary launches share the step
+        achieved = bpsite * Vh / (ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "dslash_traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get(f"prec{args.prec}_recon{args.recon}")
+            except Exception:
+                traffic = None
+        cpu = None
+        if not args.no_cpu:
+            cpu = cpu_baseline_port(oracle, g, sp)
+        dtype = {8: "f64", 4: "f32", 2: "i16-storage/f32-math"}[args.prec]
+        line = {
+            "metric": "tm_dslash_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": f"twisted-mass even-odd Dslash {X[0]}^3x{X[3]} per GPU, {dtype}, reconstruct-{args.recon} (BASELINE configs[1])",
+                       "global_lattice": [X[0], X[1], X[2], X[3] * world], "partition": [1, 1, 1, world], "kappa": KAPPA, "mu": MU,
+                       "l2_policy": "inputs larger than L2: gauge 403 MB + spinors 201 MB per hop vs 126 MB L2",
+                       "flops_per_site": FLOPS_PER_SITE, "bytes_per_site_compulsory": bpsite},
+            "effective_gbs_reference_model": BYTES_REFMODEL.get((args.prec, args.recon), 0) * sites / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": traffic, "peak_source": peak_kind, "kernel": "dslash_kernel<StoreS,12,false,false>" if args.prec == 4 else "dslash_kernel"},
+            "e2e": {"value": FLOPS_PER_SITE * sites / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": main_res["e2e_bytes"], "d2h_bytes_per_step": main_res["e2e_bytes"]},
+            "gpu_launches": main_res["launches"],
+            "clocks": sampler.summary(),
+            "cpu_baseline": cpu,
+            "extra": {},
+        }
+        if half_ms:
+            line["extra"]["half_r12"] = {"ms_per_step": half_ms, "gflops": FLOPS_PER_SITE * sites / (half_ms * 1e-3) / 1e9,
+                                         "hbm_gbs_compulsory": 296 * Vh / (half_ms * 1e-3) / 1e9,
+                                         "roofline_frac": 296 * Vh / (half_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        print(json.dumps(line))
+    L.endQuda()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+/* Extensions of the QUDA C interface for device-resident operation on B200.
+ *
+ * The reference API (include/quda.h) moves every operand host -> device -> host on each call
+ * (/root/reference/lib/interface_quda.cpp:1509-1557).  These entry points expose the same
+ * operators on fields that stay resident in HBM, which is what the reference does internally
+ * between `cudaColorSpinorField in(*in_h, cudaParam)` (:1513) and `*out_h = out` (:1554), and what
+ * QKXTM does through the internal C++ classes (interface_quda.cpp:6289-6449).  They exist so that
+ * benchmarks can time the kernels without PCIe traffic and so that multi-GPU runs can be
+ * bootstrapped without MPI (NCCL unique id handed in by the launcher).
+ *
+ * Plain C ABI: opaque handles are void*, no C++/torch types.
+ */
+#ifndef QUDA_B200_EXT_H
+#define QUDA_B200_EXT_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* --- resident spinor fields ------------------------------------------------------------------
+ * site_subset: QUDA_PARITY_SITE_SUBSET (1) or QUDA_FULL_SITE_SUBSET (2); precision: device precision.
+ * The lattice is the one of the gauge field loaded with loadGaugeQuda. */
+void *newSpinorQudaB200(QudaSiteSubset site_subset, QudaPrecision precision);
+void freeSpinorQudaB200(void *field);
+/* host (param->cpu_prec, dirac_order, gamma_basis) <-> resident field; mirrors the
+ * cudaColorSpinorField <- cpuColorSpinorField assignment (lib/cuda_color_spinor_field.cu:513-552) */
+void loadSpinorQudaB200(void *field, const void *h_in, QudaInvertParam *param);
+void saveSpinorQudaB200(void *h_out, const void *field, QudaInvertParam *param);
+
+/* same semantics as dslashQuda / MatQuda / MatDagMatQuda, operands resident */
+void dslashResidentQudaB200(void *out, void *in, QudaInvertParam *param, QudaParity parity);
+void matResidentQudaB200(void *out, void *in, QudaInvertParam *param);
+void matDagMatResidentQudaB200(void *out, void *in, QudaInvertParam *param);
+
+/* Repeat dslashResident `niter` times on the library's compute stream and return the mean device
+ * time per application in milliseconds, measured with CUDA events on that stream (what
+ * tests/dslash_test.cpp:455-616 does).  per_iter_ms (may be NULL) receives each iteration's time. */
+double timeDslashQudaB200(void *out, void *in, QudaInvertParam *param, QudaParity parity, int niter,
+                          float *per_iter_ms);
+
+/* number of kernels this library has launched since initQuda (monotonic counter) */
+long long kernelLaunchCountQudaB200(void);
+/* the CUDA stream (cudaStream_t) compute kernels are launched on */
+void *computeStreamQudaB200(void);
+/* blocks until all work queued by the library has finished */
+void syncQudaB200(void);
+
+/* --- multi-GPU bootstrap (replaces MPI_Init/QMP of tests/test_util.cpp:44-67) -------------------
+ * Call on every rank before initCommsGridQuda.  `unique_id` is the 128-byte ncclUniqueId produced
+ * by ncclUniqueIdQudaB200 on rank 0 and broadcast by the launcher (torch.distributed, files, ...). */
+void ncclUniqueIdQudaB200(void *unique_id_out_128B);
+void commsBootstrapQudaB200(int rank, int size, const void *unique_id_128B);
+/* single-process emulation of a partitioned lattice: halos are packed, "exchanged" with the rank
+ * itself and consumed by the boundary kernels (the reference's --partition test trick,
+ * tests/test_util.cpp:2047-2065, lib/comm_common.cpp:420-433).  mask bit d = dimension d. */
+void commDimPartitionedSetQudaB200(int mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,493 @@
+// BLAS-1 / reduction kernels (see blas.h).  Compiled with --extended-lambda.
+#include "blas.h"
+#include "comm.h"
+#include "layout.cuh"
+
+namespace qb {
+namespace blas {
+
+unsigned long long flops = 0, bytes = 0;
+static bool global_reduction = true;
+void set_global_reduction(bool on) { global_reduction = on; }
+
+template <typename real> struct alignas(16) Pack {
+  static constexpr int N = 8 / sizeof(real);  // complex numbers per 16 bytes
+  cplx<real> c[N];
+};
+
+static const int BLOCK = 256;
+static int grid_for(long n) {
+  const long want = (n + BLOCK - 1) / BLOCK;
+  const long cap = (long)rt().num_sms * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <typename F> __global__ void __launch_bounds__(BLOCK) ew_kernel(long n, F f) {
+  for (long i = (long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long)gridDim.x * BLOCK) f(i);
+}
+
+// ---- reduction machinery --------------------------------------------------------------------
+static const int MAX_RED = 64;           // doubles per reduction (block dot of up to 32 vectors)
+static double *d_partial = nullptr;      // [grid][MAX_RED]
+static unsigned *d_counter = nullptr;
+static double *h_result = nullptr;       // mapped pinned host memory, written by the last block
+static double *d_result = nullptr;       // device alias of h_result
+static int max_grid = 0;
+
+void init() {
+  if (d_partial) return;
+  max_grid = rt().num_sms * 8;
+  QB_CUDA(cudaMalloc((void **)&d_partial, sizeof(double) * max_grid * MAX_RED));
+  QB_CUDA(cudaMalloc((void **)&d_counter, sizeof(unsigned)));
+  QB_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned)));
+  QB_CUDA(cudaHostAlloc((void **)&h_result, sizeof(double) * MAX_RED, cudaHostAllocMapped));
+  QB_CUDA(cudaHostGetDevicePointer((void **)&d_result, h_result, 0));
+}
+
+void end() {
+  if (d_partial) cudaFree(d_partial);
+  if (d_counter) cudaFree(d_counter);
+  if (h_result) cudaFreeHost(h_result);
+  d_partial = nullptr; d_counter = nullptr; h_result = nullptr; d_result = nullptr;
+}
+
+template <int NR, typename F>
+__global__ void __launch_bounds__(BLOCK) red_kernel(long n, F f, double *partial, unsigned *counter, double *result) {
+  double acc[NR];
+_Pragma("unroll")
+  for (int k = 0; k < NR; k++) acc[k] = 0.0;
+  for (long i = (long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long)gridDim.x * BLOCK) f(i, acc);
+
+  __shared__ double sm[NR][BLOCK / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+_Pragma("unroll")
+  for (int k = 0; k < NR; k++) {
+    double v = acc[k];
+_Pragma("unroll")
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NR) {
+    double v = 0.0;
+_Pragma("unroll")
+    for (int w = 0; w < BLOCK / 32; w++) v += sm[threadIdx.x][w];
+    partial[(long)blockIdx.x * NR + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    // deterministic final pass: fixed order over CTAs
+    for (int k = warp; k < NR; k += BLOCK / 32) {
+      double v = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) v += partial[(long)b * NR + k];
+_Pragma("unroll")
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) result[k] = v;
+    }
+  }
+}
+
+template <int NR, typename F> static void reduce(double *out, long n, F f) {
+  Runtime &r = rt();
+  init();
+  const int grid = grid_for(n);
+  red_kernel<NR, F><<<grid, BLOCK, 0, r.compute>>>(n, f, d_partial, d_counter, d_result);
+  QB_CHECK_LAUNCH();
+  QB_CUDA(cudaStreamSynchronize(r.compute));
+  for (int k = 0; k < NR; k++) out[k] = h_result[k];
+  if (global_reduction) comm_allreduce_sum(out, NR);
+}
+
+template <typename F> static void elementwise(long n, F f) {
+  ew_kernel<F><<<grid_for(n), BLOCK, 0, rt().compute>>>(n, f);
+  QB_CHECK_LAUNCH();
+}
+
+static void check_same(const SpinorField &a, const SpinorField &b) {
+  if (a.prec != b.prec) QB_ERROR("blas: precision mismatch (%d vs %d)", (int)a.prec, (int)b.prec);
+  if (a.reals() != b.reals()) QB_ERROR("blas: field length mismatch (%ld vs %ld)", a.reals(), b.reals());
+}
+static void check_prec(const SpinorField &a) {
+  if (a.prec == PREC_HALF) QB_ERROR("blas: half-precision fields are only supported by the Dslash kernels; use single precision for solver vectors");
+}
+
+#define BY_PREC(field, ...)                                \
+  do {                                                     \
+    check_prec(field);                                     \
+    if ((field).prec == PREC_DOUBLE) { typedef double real; __VA_ARGS__ } \
+    else { typedef float real; __VA_ARGS__ }               \
+  } while (0)
+
+template <typename real> static long npacks(const SpinorField &x) { return x.reals() * (long)sizeof(real) / 16; }
+template <typename real> __host__ __device__ inline cplx<real> cmul(cplx<real> a, cplx<real> b) { return a * b; }
+
+void zero(SpinorField &a) { a.zero(rt().compute); }
+void copy(SpinorField &dst, const SpinorField &src) { copy_spinor(dst, src, rt().compute); }
+
+// ---- elementwise ------------------------------------------------------------------------------
+void ax(double a, SpinorField &x) {
+  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; const real A = (real)a;
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> v = X[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re *= A; v.c[k].im *= A; }
+            X[i] = v;
+          }););
+  flops += x.reals(); bytes += 2 * x.bytes();
+}
+
+void axpby(double a, const SpinorField &x, double b, SpinorField &y) {
+  check_same(x, y);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const real A = (real)a, B = (real)b;
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re = A * u.c[k].re + B * v.c[k].re; v.c[k].im = A * u.c[k].im + B * v.c[k].im; }
+            Y[i] = v;
+          }););
+  flops += 3 * x.reals(); bytes += 3 * x.bytes();
+}
+
+void axpy(double a, const SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const real A = (real)a;
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re += A * u.c[k].re; v.c[k].im += A * u.c[k].im; }
+            Y[i] = v;
+          }););
+  flops += 2 * x.reals(); bytes += 3 * x.bytes();
+}
+
+void xpy(const SpinorField &x, SpinorField &y) { axpy(1.0, x, y); }
+void mxpy(const SpinorField &x, SpinorField &y) { axpy(-1.0, x, y); }
+void xpay(const SpinorField &x, double a, SpinorField &y) { axpby(1.0, x, a, y); }
+
+void caxpy(Complex a, const SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const cplx<real> A((real)a.real(), (real)a.imag());
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) cmac(v.c[k], A, u.c[k]);
+            Y[i] = v;
+          }););
+  flops += 4 * x.reals(); bytes += 3 * x.bytes();
+}
+
+void caxpby(Complex a, const SpinorField &x, Complex b, SpinorField &y) {
+  check_same(x, y);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
+          const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag());
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cplx<real> t = B * v.c[k]; cmac(t, A, u.c[k]); v.c[k] = t; }
+            Y[i] = v;
+          }););
+  flops += 7 * x.reals(); bytes += 3 * x.bytes();
+}
+
+void cxpaypbz(const SpinorField &x, Complex a, const SpinorField &y, Complex b, SpinorField &z) {
+  check_same(x, y); check_same(x, z);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v; Pack<real> *Z = (Pack<real> *)z.v;
+          const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag());
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i], w = Z[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cplx<real> t = u.c[k]; cmac(t, A, v.c[k]); cmac(t, B, w.c[k]); w.c[k] = t; }
+            Z[i] = w;
+          }););
+  flops += 8 * x.reals(); bytes += 4 * x.bytes();
+}
+
+void caxpbypz(Complex a, const SpinorField &x, Complex b, const SpinorField &y, SpinorField &z) {
+  check_same(x, y); check_same(x, z);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v; Pack<real> *Z = (Pack<real> *)z.v;
+          const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag());
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i], w = Z[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(w.c[k], A, u.c[k]); cmac(w.c[k], B, v.c[k]); }
+            Z[i] = w;
+          }););
+  flops += 8 * x.reals(); bytes += 4 * x.bytes();
+}
+
+void caxpbypzYmbw(Complex a, const SpinorField &x, Complex b, SpinorField &y, SpinorField &z, const SpinorField &w) {
+  check_same(x, y); check_same(x, z); check_same(x, w);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; Pack<real> *Z = (Pack<real> *)z.v;
+          const Pack<real> *W = (const Pack<real> *)w.v;
+          const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag()), mB(-(real)b.real(), -(real)b.imag());
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i], zz = Z[i], ww = W[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(zz.c[k], A, u.c[k]); cmac(zz.c[k], B, v.c[k]); cmac(v.c[k], mB, ww.c[k]); }
+            Z[i] = zz; Y[i] = v;
+          }););
+  flops += 12 * x.reals(); bytes += 6 * x.bytes();
+}
+
+void cabxpyAx(double a, Complex b, SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
+          const real A = (real)a; const cplx<real> AB((real)(a * b.real()), (real)(a * b.imag()));
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; }
+            X[i] = u; Y[i] = v;
+          }););
+  flops += 5 * x.reals(); bytes += 4 * x.bytes();
+}
+
+void caxpyXmaz(Complex a, SpinorField &x, SpinorField &y, const SpinorField &z) {
+  check_same(x, y); check_same(x, z);
+  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+          const cplx<real> A((real)a.real(), (real)a.imag()), mA(-(real)a.real(), -(real)a.imag());
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v = Y[i], w = Z[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); cmac(u.c[k], mA, w.c[k]); }
+            X[i] = u; Y[i] = v;
+          }););
+  flops += 8 * x.reals(); bytes += 5 * x.bytes();
+}
+
+// ---- reductions -------------------------------------------------------------------------------
+double norm2(const SpinorField &x) {
+  double out[1];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v;
+          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) acc[0] += (double)u.c[k].re * u.c[k].re + (double)u.c[k].im * u.c[k].im;
+          }););
+  flops += 2 * x.reals(); bytes += x.bytes();
+  return out[0];
+}
+
+double reDotProduct(const SpinorField &x, const SpinorField &y) {
+  check_same(x, y);
+  double out[1];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
+          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) acc[0] += (double)u.c[k].re * v.c[k].re + (double)u.c[k].im * v.c[k].im;
+          }););
+  flops += 2 * x.reals(); bytes += 2 * x.bytes();
+  return out[0];
+}
+
+// acc[0..1] += conj(u) v
+template <typename real> __device__ __forceinline__ void cdot_acc(double *acc, cplx<real> u, cplx<real> v) {
+  acc[0] += (double)u.re * v.re + (double)u.im * v.im;
+  acc[1] += (double)u.re * v.im - (double)u.im * v.re;
+}
+template <typename real> __device__ __forceinline__ double norm_c(cplx<real> u) { return (double)u.re * u.re + (double)u.im * u.im; }
+
+Complex cDotProduct(const SpinorField &x, const SpinorField &y) {
+  check_same(x, y);
+  double out[2];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
+          reduce<2>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) cdot_acc(acc, u.c[k], v.c[k]);
+          }););
+  flops += 4 * x.reals(); bytes += 2 * x.bytes();
+  return Complex(out[0], out[1]);
+}
+
+double3_ cDotProductNormA(const SpinorField &x, const SpinorField &y) {
+  check_same(x, y);
+  double out[3];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
+          reduce<3>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cdot_acc(acc, u.c[k], v.c[k]); acc[2] += norm_c(u.c[k]); }
+          }););
+  flops += 6 * x.reals(); bytes += 2 * x.bytes();
+  return double3_{out[0], out[1], out[2]};
+}
+
+double3_ cDotProductNormB(const SpinorField &x, const SpinorField &y) {
+  check_same(x, y);
+  double out[3];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
+          reduce<3>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cdot_acc(acc, u.c[k], v.c[k]); acc[2] += norm_c(v.c[k]); }
+          }););
+  flops += 6 * x.reals(); bytes += 2 * x.bytes();
+  return double3_{out[0], out[1], out[2]};
+}
+
+double axpyNorm(double a, const SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  double out[1];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const real A = (real)a;
+          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re += A * u.c[k].re; v.c[k].im += A * u.c[k].im; acc[0] += norm_c(v.c[k]); }
+            Y[i] = v;
+          }););
+  flops += 4 * x.reals(); bytes += 3 * x.bytes();
+  return out[0];
+}
+
+double xmyNorm(const SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  double out[1];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
+          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re = u.c[k].re - v.c[k].re; v.c[k].im = u.c[k].im - v.c[k].im; acc[0] += norm_c(v.c[k]); }
+            Y[i] = v;
+          }););
+  flops += 3 * x.reals(); bytes += 3 * x.bytes();
+  return out[0];
+}
+
+double caxpyNorm(Complex a, const SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  double out[1];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const cplx<real> A((real)a.real(), (real)a.imag());
+          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); acc[0] += norm_c(v.c[k]); }
+            Y[i] = v;
+          }););
+  flops += 6 * x.reals(); bytes += 3 * x.bytes();
+  return out[0];
+}
+
+double cabxpyAxNorm(double a, Complex b, SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  double out[1];
+  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
+          const real A = (real)a; const cplx<real> AB((real)(a * b.real()), (real)(a * b.imag()));
+          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; acc[0] += norm_c(u.c[k]); }
+            X[i] = u; Y[i] = v;
+          }););
+  flops += 7 * x.reals(); bytes += 4 * x.bytes();
+  return out[0];
+}
+
+Complex caxpyDotzy(Complex a, const SpinorField &x, SpinorField &y, const SpinorField &z) {
+  check_same(x, y); check_same(x, z);
+  double out[2];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+          const cplx<real> A((real)a.real(), (real)a.imag());
+          reduce<2>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i], w = Z[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); cdot_acc(acc, w.c[k], v.c[k]); }
+            Y[i] = v;
+          }););
+  flops += 8 * x.reals(); bytes += 4 * x.bytes();
+  return Complex(out[0], out[1]);
+}
+
+double caxpyXmazNormX(Complex a, SpinorField &x, SpinorField &y, const SpinorField &z) {
+  check_same(x, y); check_same(x, z);
+  double out[1];
+  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+          const cplx<real> A((real)a.real(), (real)a.imag()), mA(-(real)a.real(), -(real)a.imag());
+          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i], w = Z[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); cmac(u.c[k], mA, w.c[k]); acc[0] += norm_c(u.c[k]); }
+            X[i] = u; Y[i] = v;
+          }););
+  flops += 10 * x.reals(); bytes += 5 * x.bytes();
+  return out[0];
+}
+
+Complex xpaycDotzy(const SpinorField &x, double a, SpinorField &y, const SpinorField &z) {
+  check_same(x, y); check_same(x, z);
+  double out[2];
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+          const real A = (real)a;
+          reduce<2>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
+            Pack<real> u = X[i], v = Y[i], w = Z[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re = u.c[k].re + A * v.c[k].re; v.c[k].im = u.c[k].im + A * v.c[k].im; cdot_acc(acc, w.c[k], v.c[k]); }
+            Y[i] = v;
+          }););
+  flops += 6 * x.reals(); bytes += 4 * x.bytes();
+  return Complex(out[0], out[1]);
+}
+
+// ---- block variants -----------------------------------------------------------------------------
+static const int MAX_BLOCK_VEC = 32;
+template <typename real> struct PtrList { const Pack<real> *p[MAX_BLOCK_VEC]; cplx<real> a[MAX_BLOCK_VEC]; int n; };
+
+template <int NV, typename real> static void block_cdot(double *out, const PtrList<real> &L, const Pack<real> *Y, long n) {
+  const PtrList<real> l = L;
+  reduce<2 * NV>(out, n, [=] __device__(long i, double *acc) {
+    Pack<real> v = Y[i];
+_Pragma("unroll")
+    for (int j = 0; j < NV; j++) {
+      if (j < l.n) {
+        Pack<real> u = l.p[j][i];
+_Pragma("unroll")
+        for (int k = 0; k < Pack<real>::N; k++) cdot_acc(acc + 2 * j, u.c[k], v.c[k]);
+      }
+    }
+  });
+}
+
+void cDotProduct(Complex *result, const std::vector<SpinorField *> &x, const SpinorField &y) {
+  const int n = (int)x.size();
+  if (n == 0) return;
+  if (n > MAX_BLOCK_VEC) QB_ERROR("block cDotProduct supports at most %d vectors", MAX_BLOCK_VEC);
+  for (auto *f : x) check_same(*f, y);
+  double out[2 * MAX_BLOCK_VEC];
+  BY_PREC(y, PtrList<real> L; L.n = n; for (int j = 0; j < n; j++) L.p[j] = (const Pack<real> *)x[j]->v;
+          for (int j = n; j < MAX_BLOCK_VEC; j++) L.p[j] = nullptr;
+          const Pack<real> *Y = (const Pack<real> *)y.v; const long np = npacks<real>(y);
+          if (n <= 4) block_cdot<4>(out, L, Y, np);
+          else if (n <= 8) block_cdot<8>(out, L, Y, np);
+          else if (n <= 16) block_cdot<16>(out, L, Y, np);
+          else block_cdot<32>(out, L, Y, np););
+  for (int j = 0; j < n; j++) result[j] = Complex(out[2 * j], out[2 * j + 1]);
+  flops += 4ull * n * y.reals(); bytes += (unsigned long long)(n + 1) * y.bytes();
+}
+
+void caxpy(const Complex *a, const std::vector<SpinorField *> &x, SpinorField &y) {
+  const int n = (int)x.size();
+  if (n == 0) return;
+  if (n > MAX_BLOCK_VEC) QB_ERROR("block caxpy supports at most %d vectors", MAX_BLOCK_VEC);
+  for (auto *f : x) check_same(*f, y);
+  BY_PREC(y, PtrList<real> L; L.n = n;
+          for (int j = 0; j < n; j++) { L.p[j] = (const Pack<real> *)x[j]->v; L.a[j] = cplx<real>((real)a[j].real(), (real)a[j].imag()); }
+          Pack<real> *Y = (Pack<real> *)y.v;
+          elementwise(npacks<real>(y), [=] __device__(long i) {
+            Pack<real> v = Y[i];
+            for (int j = 0; j < L.n; j++) {
+              Pack<real> u = L.p[j][i];
+_Pragma("unroll")
+              for (int k = 0; k < Pack<real>::N; k++) cmac(v.c[k], L.a[j], u.c[k]);
+            }
+            Y[i] = v;
+          }););
+  flops += 4ull * n * y.reals(); bytes += (unsigned long long)(n + 2) * y.bytes();
+}
+
+}  // namespace blas
+}  // namespace qb

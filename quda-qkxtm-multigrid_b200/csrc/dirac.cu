@@ -1,0 +1,141 @@
+// Wilson / twisted-mass operators on resident fields.
+// Operator algebra follows /root/reference/lib/dirac_twisted_mass.cpp:129-174 (M), :246-294 (Dslash),
+// :297-344 (DslashXpay), :346-403 (PC M), :418-520 (prepare), :522-570 (reconstruct); every
+// composite below is issued as ONE fused hop kernel where the reference needs a hop plus separate
+// twist / xpay kernels.
+#include "dirac.h"
+
+namespace qb {
+
+void Dirac::Mdag(SpinorField &out, const SpinorField &in) const {
+  Dirac *self = const_cast<Dirac *>(this);
+  self->dagger = !self->dagger;
+  M(out, in);
+  self->dagger = !self->dagger;
+}
+
+void Dirac::MdagM(SpinorField &out, const SpinorField &in) const {
+  std::unique_ptr<SpinorField> t(new SpinorField(in.Vh, in.nparity, in.prec, in.nspin, in.ncolor));
+  M(*t, in);
+  Mdag(out, *t);
+}
+
+void Dirac::create_coarse_op(CoarseOperator &, const Transfer &) const { QB_ERROR("create_coarse_op not implemented for this operator"); }
+
+DiracTM::DiracTM(Lattice *lat_, const GaugeField *gauge_, double kappa_, double mu_, int flavor_, bool pc_, int matpc_, bool dagger_)
+    : lat(lat_), gauge(gauge_), kappa(kappa_), mu(mu_), flavor(flavor_), pc(pc_), matpc_type(matpc_) {
+  dagger = dagger_;
+  if (flavor != 0 && flavor != 1 && flavor != -1) QB_ERROR("only degenerate twisted mass (flavor +-1) is supported, got %d", flavor);
+}
+
+SpinorField &DiracTM::tmp(std::unique_ptr<SpinorField> &t, const SpinorField &like) const {
+  if (!t || t->prec != like.prec || t->Vh != like.Vh || t->nparity != like.nparity)
+    t.reset(new SpinorField(like.Vh, like.nparity, like.prec));
+  return *t;
+}
+
+void DiracTM::WilsonDslash(SpinorField &out, const SpinorField &in, int parity) const {
+  apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), TwistCoef(), nullptr, TwistCoef());
+  flops += 1320ll * in.Vh;
+}
+
+void DiracTM::WilsonDslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const {
+  apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), TwistCoef(k, 0.0), &x, TwistCoef());
+  flops += 1368ll * in.Vh;
+}
+
+void DiracTM::Twist(SpinorField &out, const SpinorField &in) const { apply_twist_field(out, in, A()); }
+void DiracTM::TwistInv(SpinorField &out, const SpinorField &in) const { apply_twist_field(out, in, Ainv()); }
+
+// PC hop:  A^-1 D  (no dagger, or asymmetric)   |   D A^-1  (dagger & symmetric: twist on the input)
+void DiracTM::Dslash(SpinorField &out, const SpinorField &in, int parity) const {
+  if (flavor == 0) return WilsonDslash(out, in, parity);
+  if (!dagger || !symmetric()) apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), Ainv(), nullptr, TwistCoef());
+  else apply_hop(*lat, *gauge, out, in, parity, dagger, Ainv(), TwistCoef(), nullptr, TwistCoef());
+  flops += 1392ll * in.Vh;
+}
+
+// out = x + k (A^-1 D | D A^-1) in     (dirac_twisted_mass.cpp:297-344: dagger alone selects the input twist)
+void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const {
+  if (flavor == 0) return WilsonDslashXpay(out, in, parity, x, k);
+  if (!dagger) apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), Ainv(k), &x, TwistCoef());
+  else apply_hop(*lat, *gauge, out, in, parity, dagger, Ainv(), TwistCoef(k, 0.0), &x, TwistCoef());
+  flops += 1416ll * in.Vh;
+}
+
+void DiracTM::M(SpinorField &out, const SpinorField &in) const {
+  if (!pc) {
+    // full operator on [even | odd]:  out_p = A in_p - kappa D_{p,1-p} in_{1-p}
+    if (in.nparity != 2 || out.nparity != 2) QB_ERROR("full operator needs full fields");
+    SpinorField oe, oo, ie, io;
+    out.view_parity(oe, 0); out.view_parity(oo, 1);
+    in.view_parity(ie, 0); in.view_parity(io, 1);
+    apply_hop(*lat, *gauge, oo, ie, 1, dagger, TwistCoef(), TwistCoef(-kappa, 0.0), &io, flavor ? A() : TwistCoef());
+    apply_hop(*lat, *gauge, oe, io, 0, dagger, TwistCoef(), TwistCoef(-kappa, 0.0), &ie, flavor ? A() : TwistCoef());
+    flops += (1320ll + 72ll) * 2 * in.Vh;
+    return;
+  }
+  if (in.nparity != 1 || out.nparity != 1) QB_ERROR("preconditioned operator needs single-parity fields");
+  const double kappa2 = -kappa * kappa;
+  const int p_out = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1;
+  SpinorField &t = tmp(tmp1, in);
+  Dslash(t, in, 1 - p_out);
+  if (flavor == 0 || symmetric()) {
+    DslashXpay(out, t, p_out, in, kappa2);
+  } else {
+    // asymmetric: out = A in - kappa^2 D t
+    apply_hop(*lat, *gauge, out, t, p_out, dagger, TwistCoef(), TwistCoef(kappa2, 0.0), &in, A());
+    flops += (1320ll + 96ll) * in.Vh;
+  }
+}
+
+// Solve M x = b through the Schur complement on one parity (dirac_twisted_mass.cpp:418-520):
+//   symmetric :  src = A^-1 (b_p + kappa D A^-1 b_q),  asymmetric:  src = b_p + kappa D A^-1 b_q
+// with p the preconditioned parity and q the other one.  `src` aliases the q-half of x as in the reference.
+void DiracTM::prepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b, SolutionType sol_type) const {
+  if (!pc) {
+    if (sol_type == SOL_MATPC || sol_type == SOL_MATPCDAG_MATPC) QB_ERROR("Preconditioned solution requires a preconditioned solve_type");
+    b.view_parity(src, 0); src.nparity = b.nparity; src.parity_bytes = b.parity_bytes;
+    x.view_parity(sol, 0); sol.nparity = x.nparity; sol.parity_bytes = x.parity_bytes;
+    return;
+  }
+  if (sol_type == SOL_MATPC || sol_type == SOL_MATPCDAG_MATPC) {
+    b.view_parity(src, 0);
+    x.view_parity(sol, 0);
+    return;
+  }
+  if (x.nparity != 2 || b.nparity != 2) QB_ERROR("prepare: full-lattice source and solution required for a MAT solution");
+  const int p = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p;
+  SpinorField bp, bq;
+  b.view_parity(bp, p); b.view_parity(bq, q);
+  x.view_parity(src, q);
+  x.view_parity(sol, p);
+  if (flavor == 0) {
+    apply_hop(*lat, *gauge, src, bq, p, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bp, TwistCoef());
+  } else if (symmetric()) {
+    const TwistCoef ai = Ainv();
+    apply_hop(*lat, *gauge, src, bq, p, dagger, ai, TwistCoef(kappa * ai.p, kappa * ai.q), &bp, ai);
+  } else {
+    apply_hop(*lat, *gauge, src, bq, p, dagger, Ainv(), TwistCoef(kappa, 0.0), &bp, TwistCoef());
+  }
+  flops += 1440ll * b.Vh;
+}
+
+// x_q = A^-1 (b_q + kappa D x_p)   (dirac_twisted_mass.cpp:522-570)
+void DiracTM::reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const {
+  if (!pc) return;
+  if (sol_type == SOL_MATPC || sol_type == SOL_MATPCDAG_MATPC) return;
+  const int p = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p;
+  SpinorField xp, xq, bq;
+  x.view_parity(xp, p); x.view_parity(xq, q);
+  b.view_parity(bq, q);
+  if (flavor == 0) {
+    apply_hop(*lat, *gauge, xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bq, TwistCoef());
+  } else {
+    const TwistCoef ai = Ainv();
+    apply_hop(*lat, *gauge, xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa * ai.p, kappa * ai.q), &bq, ai);
+  }
+  flops += 1416ll * b.Vh;
+}
+
+}  // namespace qb

@@ -1,0 +1,293 @@
+// Fine-grid Wilson / twisted-mass hopping kernels for sm_100a.
+//
+// One kernel covers every operator variant of the reference's twisted-mass Dslash
+// (/root/reference/lib/dslash_twisted_mass.cu:167-242, lib/tm_dslash_def.h:389-456, generated body
+// lib/dslash_core/tm_dslash_gt200_core.h) and the plain Wilson Dslash(+xpay)
+// (lib/dslash_wilson.cu:107) through three complex coefficient pairs:
+//
+//     out(x) = Cx * X(x)  +  Co * sum_mu [ P(-s)_mu U_mu(x) Cin*in(x+mu) + P(+s)_mu U_mu(x-mu)^dag Cin*in(x-mu) ]
+//
+// where a coefficient C = (p, q) acts as p + i q gamma5, i.e. (p + iq) on the upper two spins and
+// (p - iq) on the lower two in the internal DeGrand-Rossi basis, and s = -1 (no dagger) / +1 (dagger).
+//   QUDA_DEG_DSLASH_TWIST_INV   : Co = b(1, a)           (A^-1 D)
+//   QUDA_DEG_TWIST_INV_DSLASH   : Cin = b(1, a)          (D A^-1; the pack kernel applies Cin too)
+//   ..._XPAY of the two above   : Cx = (1,0), Co or Cin scaled by k
+//   QUDA_DEG_DSLASH_TWIST_XPAY  : Cx = (1, a), Co = (b, 0)
+// (coefficient table: SURVEY.md Appendix A.5, /root/reference/lib/dirac_twisted_mass.cpp:246-403)
+//
+// Thread mapping: one thread per output checkerboard site, consecutive threads = consecutive cb
+// sites, so every plane load of a warp is one contiguous 512-byte (fp32) request.  Links use the
+// L1-bypassing streaming path (read once per hop); neighbour spinors go through L1/L2 where the
+// 8-fold reuse is caught.  Partitioned dimensions read projected half spinors from the ghost zone.
+#pragma once
+#include "layout.cuh"
+
+namespace qb {
+
+struct DslashParam {
+  Geom g;
+  int parity;  // parity of the output sites
+  void *out; float *out_norm;
+  const void *in; const float *in_norm;   // parity 1 - parity
+  const void *x; const float *x_norm;     // same parity as out (may alias out)
+  const void *gauge_fwd;                  // [mu][plane][Vh], parity of out
+  const void *gauge_bwd;                  // [mu][plane][Vh], other parity
+  const void *gauge_ghost[4];             // [plane][faceVh] links U_d(x - d) for sites at x_d = 0
+  const void *ghost[4][2];                // received half spinors, [d][0]: from backward nbr, [d][1]: from forward nbr
+  const float *ghost_norm[4][2];
+  long stride;                            // plane stride of spinors and links (= Vh)
+  double cin[2], co[2], cx[2];            // (p, q) pairs
+  double sgn_fwd;                         // -1: (1 - gamma) on forward hops (no dagger), +1: dagger
+  int site_begin, site_count;             // contiguous range ...
+  const int *site_list;                   // ... or explicit list of cb sites (interior / boundary split)
+};
+
+// ---- gamma matrices, DeGrand-Rossi: gamma_mu[s][gcol(mu,s)] = gre + i gim -----------------------
+__host__ __device__ constexpr int gcol(int mu, int s) { return mu < 2 ? 3 - s : (s + 2) & 3; }
+__host__ __device__ constexpr int gre(int mu, int s) {
+  return mu == 1 ? ((s == 0 || s == 3) ? -1 : 1) : (mu == 3 ? 1 : 0);
+}
+__host__ __device__ constexpr int gim(int mu, int s) {
+  return mu == 0 ? (s < 2 ? 1 : -1) : (mu == 2 ? ((s == 0 || s == 3) ? 1 : -1) : 0);
+}
+
+// z * (re + i im) for re, im in {0, +-1}, exactly one non-zero (folds at compile time)
+template <typename T> __device__ __forceinline__ cplx<T> mul_unit(int re, int im, cplx<T> z) {
+  if (re == 1) return z;
+  if (re == -1) return cplx<T>(-z.re, -z.im);
+  if (im == 1) return cplx<T>(-z.im, z.re);
+  return cplx<T>(z.im, -z.re);
+}
+
+// (p + i q g5) psi in place on a full spinor
+template <typename T> __device__ __forceinline__ void apply_twist(cplx<T> *psi, T p, T q) {
+  const cplx<T> cu(p, q), cl(p, -q);
+#pragma unroll
+  for (int k = 0; k < 6; k++) psi[k] = cu * psi[k];
+#pragma unroll
+  for (int k = 6; k < 12; k++) psi[k] = cl * psi[k];
+}
+
+// upper two spin rows of (1 + sigma gamma_mu) psi
+template <int MU, typename T> __device__ __forceinline__ void project(cplx<T> *h, const cplx<T> *psi, T sigma) {
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const cplx<T> g = mul_unit(gre(MU, s), gim(MU, s), psi[gcol(MU, s) * 3 + c]);
+      h[s * 3 + c] = cplx<T>(psi[s * 3 + c].re + sigma * g.re, psi[s * 3 + c].im + sigma * g.im);
+    }
+}
+
+// acc += (1 + sigma gamma_mu)-reconstruction of the link-multiplied half spinor chi
+template <int MU, typename T> __device__ __forceinline__ void reconstruct_acc(cplx<T> *acc, const cplx<T> *chi, T sigma) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) acc[k] = acc[k] + chi[k];
+#pragma unroll
+  for (int s = 2; s < 4; s++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const cplx<T> g = mul_unit(gre(MU, s), gim(MU, s), chi[gcol(MU, s) * 3 + c]);
+      acc[s * 3 + c].re += sigma * g.re;
+      acc[s * 3 + c].im += sigma * g.im;
+    }
+}
+
+template <bool DAG, typename T> __device__ __forceinline__ void su3_mul(cplx<T> *chi, const cplx<T> *U, const cplx<T> *h) {
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      cplx<T> a((T)0, (T)0);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        if (!DAG) cmac(a, U[r * 3 + c], h[s * 3 + c]);
+        else cmac_conj(a, U[c * 3 + r], h[s * 3 + c]);
+      }
+      chi[s * 3 + r] = a;
+    }
+}
+
+// checkerboard index -> coordinates and the full lexicographic index
+__device__ __forceinline__ void cb_coords(int *x, int &full, int cb, int parity, const Geom &g) {
+  const int za = cb / g.Xh;
+  const int zb = za / g.X[1];
+  x[1] = za - zb * g.X[1];
+  x[3] = zb / g.X[2];
+  x[2] = zb - x[3] * g.X[2];
+  const int odd = (x[1] + x[2] + x[3] + parity) & 1;
+  full = 2 * cb + odd;
+  x[0] = full - za * g.X[0];
+}
+
+// index of a site inside the checkerboarded face orthogonal to MU (3-d lexicographic, x fastest, >> 1)
+template <int MU> __device__ __forceinline__ int face_index(const int *x, const Geom &g) {
+  if (MU == 0) return (x[1] + g.X[1] * (x[2] + g.X[2] * x[3])) >> 1;
+  if (MU == 1) return (x[0] + g.X[0] * (x[2] + g.X[2] * x[3])) >> 1;
+  if (MU == 2) return (x[0] + g.X[0] * (x[1] + g.X[1] * x[3])) >> 1;
+  return (x[0] + g.X[0] * (x[1] + g.X[1] * x[2])) >> 1;
+}
+
+__device__ __forceinline__ int dim_stride(int mu, const Geom &g) {
+  return mu == 0 ? 1 : (mu == 1 ? g.X[0] : (mu == 2 ? g.X[0] * g.X[1] : g.X[0] * g.X[1] * g.X[2]));
+}
+
+template <typename Store, int RECON> __device__ __forceinline__ size_t link_block_bytes(long stride) {
+  return (size_t)RECON * StoreTraits<Store>::real_bytes * stride;
+}
+
+// one hop: MU direction, BACK = 0 forward (x+mu), 1 backward (x-mu)
+template <typename Store, int RECON, bool TWIST_IN, int MU, int BACK>
+__device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const DslashParam &p, const int *x, int full, int cb) {
+  typedef typename Store::real real;
+  const Geom &g = p.g;
+  const int L = g.X[MU];
+  const int step = dim_stride(MU, g);
+  const bool edge = BACK ? (x[MU] == 0) : (x[MU] == L - 1);
+  const bool use_ghost = edge && g.part[MU];
+  const real sigma = BACK ? (real)(-p.sgn_fwd) : (real)p.sgn_fwd;
+
+  cplx<real> h[6];
+  int nbr = 0, fidx = 0;
+  if (use_ghost) {
+    fidx = face_index<MU>(x, g);
+    Store::template load<6>(h, p.ghost[MU][BACK ? 0 : 1], p.ghost_norm[MU][BACK ? 0 : 1], g.faceVh[MU], fidx);
+  } else {
+    const int nfull = BACK ? (edge ? full + (L - 1) * step : full - step) : (edge ? full - (L - 1) * step : full + step);
+    nbr = nfull >> 1;
+    cplx<real> psi[12];
+    Store::template load<12>(psi, p.in, p.in_norm, p.stride, nbr);
+    if (TWIST_IN) apply_twist(psi, (real)p.cin[0], (real)p.cin[1]);
+    project<MU>(h, psi, sigma);
+  }
+
+  // link: forward hop uses U_mu(x) (own parity, own site); backward uses U_mu(x-mu)^dag (other parity)
+  real raw[RECON];
+  if (!BACK) {
+    LinkRaw<Store, RECON>::load(raw, (const char *)p.gauge_fwd + MU * link_block_bytes<Store, RECON>(p.stride), p.stride, cb);
+  } else if (use_ghost) {
+    LinkRaw<Store, RECON>::load(raw, p.gauge_ghost[MU], g.faceVh[MU], fidx);
+  } else {
+    LinkRaw<Store, RECON>::load(raw, (const char *)p.gauge_bwd + MU * link_block_bytes<Store, RECON>(p.stride), p.stride, nbr);
+  }
+  real u0;
+  if (MU < 3) u0 = RECON == 8 ? (real)1 / (real)g.aniso : (real)g.aniso;
+  else u0 = BACK ? (x[3] == 0 ? (real)g.tb_bwd : (real)1) : (x[3] == L - 1 ? (real)g.tb_fwd : (real)1);
+  cplx<real> U[9];
+  reconstruct_link<real, RECON>(U, raw, u0);
+
+  cplx<real> chi[6];
+  su3_mul<BACK != 0>(chi, U, h);
+  reconstruct_acc<MU>(acc, chi, sigma);
+}
+
+template <typename Store, int RECON, bool TWIST_IN, bool HAS_X>
+__global__ void __launch_bounds__(128) dslash_kernel(const DslashParam p) {
+  typedef typename Store::real real;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= p.site_count) return;
+  const int cb = p.site_list ? p.site_list[tid] : p.site_begin + tid;
+
+  int x[4], full;
+  cb_coords(x, full, cb, p.parity, p.g);
+
+  cplx<real> acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) acc[k] = cplx<real>((real)0, (real)0);
+
+  hop<Store, RECON, TWIST_IN, 0, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, 0, 1>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, 1, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, 1, 1>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, 2, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, 2, 1>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, 3, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, 3, 1>(acc, p, x, full, cb);
+
+  // epilogue: out = Cx x + Co acc
+  apply_twist(acc, (real)p.co[0], (real)p.co[1]);
+  if (HAS_X) {
+    cplx<real> xs[12];
+    Store::template load<12, false>(xs, p.x, p.x_norm, p.stride, cb);
+    const cplx<real> cu((real)p.cx[0], (real)p.cx[1]), cl((real)p.cx[0], -(real)p.cx[1]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) cmac(acc[k], cu, xs[k]);
+#pragma unroll
+    for (int k = 6; k < 12; k++) cmac(acc[k], cl, xs[k]);
+  }
+  Store::template store<12>(p.out, p.out_norm, p.stride, cb, acc);
+}
+
+// ---- face packing (replaces lib/dslash_pack.cu:271-339, :609-674) -------------------------------
+// One thread per (partitioned dim, direction, face site): load the full spinor of the input field on
+// the boundary slice, apply Cin if the operator twists its input, project with the projector the
+// *receiver* will use, store the 12-real half spinor into the send buffer [plane][face site].
+struct PackParam {
+  Geom g;
+  int parity;                 // parity of the field being packed (= input parity of the hop)
+  const void *in; const float *in_norm;
+  long stride;
+  void *send[4][2];           // [d][0]: slice x_d = 0 (sent backward), [d][1]: slice x_d = X_d-1 (sent forward)
+  float *send_norm[4][2];
+  int thread_off[5];          // prefix sums over partitioned dims of 2*faceVh[d]
+  double cin[2];
+  double sgn_fwd;
+};
+
+template <int MU> __device__ __forceinline__ int face_to_cb(int fidx, int slice, int parity, const Geom &g) {
+  // invert face_index<MU> for the site of the given parity on the slice x_MU = slice
+  int a, b, c;  // the three remaining coordinates, fastest first
+  const int d0 = MU == 0 ? 1 : 0, d1 = MU <= 1 ? 2 : 1, d2 = MU <= 2 ? 3 : 2;
+  const int L0 = g.X[d0], L1 = g.X[d1];
+  const int f2 = 2 * fidx;
+  const int row = f2 / L0;
+  c = row / L1;
+  b = row - c * L1;
+  a = f2 - row * L0;
+  a += (slice + b + c + parity + a) & 1;  // a is even here; fix the checkerboard offset
+  int x[4];
+  x[MU] = slice; x[d0] = a; x[d1] = b; x[d2] = c;
+  return (((x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.X[0] + x[0]) >> 1;
+}
+
+template <typename Store, bool TWIST_IN, int MU>
+__device__ __forceinline__ void pack_site(const PackParam &p, int t) {
+  typedef typename Store::real real;
+  const Geom &g = p.g;
+  const int fv = g.faceVh[MU];
+  const int dir = t / fv;  // 0: back face (x=0), 1: forward face (x=L-1)
+  const int fidx = t - dir * fv;
+  const int cb = face_to_cb<MU>(fidx, dir ? g.X[MU] - 1 : 0, p.parity, g);
+  cplx<real> psi[12], h[6];
+  Store::template load<12>(psi, p.in, p.in_norm, p.stride, cb);
+  if (TWIST_IN) apply_twist(psi, (real)p.cin[0], (real)p.cin[1]);
+  // back face feeds the neighbour's forward hop (sigma = sgn_fwd); forward face its backward hop
+  const real sigma = dir ? (real)(-p.sgn_fwd) : (real)p.sgn_fwd;
+  project<MU>(h, psi, sigma);
+  Store::template store<6>(p.send[MU][dir], p.send_norm[MU][dir], fv, fidx, h);
+}
+
+template <typename Store, bool TWIST_IN>
+__global__ void __launch_bounds__(128) pack_kernel(const PackParam p) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= p.thread_off[4]) return;
+  if (tid < p.thread_off[1]) pack_site<Store, TWIST_IN, 0>(p, tid - p.thread_off[0]);
+  else if (tid < p.thread_off[2]) pack_site<Store, TWIST_IN, 1>(p, tid - p.thread_off[1]);
+  else if (tid < p.thread_off[3]) pack_site<Store, TWIST_IN, 2>(p, tid - p.thread_off[2]);
+  else pack_site<Store, TWIST_IN, 3>(p, tid - p.thread_off[3]);
+}
+
+// ---- site-local twist (replaces twistGamma5Cuda, lib/dslash_quda.cu:430-463) --------------------
+template <typename Store>
+__global__ void __launch_bounds__(256) twist_kernel(void *out, float *out_norm, const void *in, const float *in_norm, long stride,
+                                                    int n, double pr, double qr) {
+  typedef typename Store::real real;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cplx<real> psi[12];
+  Store::template load<12, false>(psi, in, in_norm, stride, i);
+  apply_twist(psi, (real)pr, (real)qr);
+  Store::template store<12>(out, out_norm, stride, i, psi);
+}
+
+}  // namespace qb

@@ -1,0 +1,53 @@
+// Host-side driver of the fine-grid hopping kernels: halo exchange + interior/boundary overlap.
+#pragma once
+#include "field.h"
+
+namespace qb {
+
+struct DslashParam;
+struct PackParam;
+struct StoreD; struct StoreS; struct StoreH;
+
+template <typename Store> void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, int block, cudaStream_t s);
+template <typename Store> void launch_pack_T(const PackParam &p, bool twist_in, cudaStream_t s);
+template <typename Store> void launch_twist_T(void *out, float *out_norm, const void *in, const float *in_norm, long stride, int n, double pr, double qr, cudaStream_t s);
+
+// (p, q) <-> p + i q gamma5
+struct TwistCoef {
+  double p = 1.0, q = 0.0;
+  TwistCoef() {}
+  TwistCoef(double p_, double q_) : p(p_), q(q_) {}
+  bool trivial() const { return p == 1.0 && q == 0.0; }
+};
+
+// Lattice context: geometry, comm pattern, halo buffers, interior/boundary site lists.
+struct Lattice {
+  Geom geom;
+  long V = 0;
+  // partitioned-lattice bookkeeping (built lazily by setup_partition)
+  int *interior_list[2] = {nullptr, nullptr};  // device, cb sites of parity p with no partitioned-boundary hop
+  int *boundary_list[2] = {nullptr, nullptr};
+  int n_interior[2] = {0, 0}, n_boundary[2] = {0, 0};
+  // halo arenas per storage precision index (0: double, 1: single, 2: half)
+  void *send_arena[3] = {nullptr, nullptr, nullptr};
+  void *recv_arena[3] = {nullptr, nullptr, nullptr};
+  size_t arena_bytes[3] = {0, 0, 0};
+  size_t face_off[3][4][2];   // byte offset of the (d, dir) half-spinor block inside an arena
+  size_t norm_off[3][4][2];   // byte offset of the norm block (half precision only)
+  int block_size = 128;
+
+  void init(const int *X, int t_boundary_sign, double anisotropy);
+  void setup_partition();
+  void release();
+};
+
+// out(parity) = Cx x + Co D(parity <- 1-parity) Cin in     (see dslash.cuh)
+// x may be nullptr.  Runs on rt().compute; when dimensions are partitioned the face pack + exchange
+// run on rt().halo concurrently with the interior kernel, then the boundary sites are completed.
+void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
+               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx);
+
+// out = (p + i q gamma5) in on every site of the field
+void apply_twist_field(SpinorField &out, const SpinorField &in, TwistCoef c);
+
+}  // namespace qb

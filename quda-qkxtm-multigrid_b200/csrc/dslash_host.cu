@@ -1,0 +1,225 @@
+// Host driver for the fine-grid hop: geometry, halo buffers, pack -> exchange -> interior/boundary.
+// Replaces the reference's policy layer (/root/reference/lib/dslash_policy.cuh:148-297, :838-997) and the
+// ghost bookkeeping of lib/cuda_color_spinor_field.cu:592-676, :1465-1860.
+//
+// Design difference (B200-first): the reference's interior kernel computes *partial* sums for
+// boundary sites and per-dimension exterior kernels read them back and finish them.  Here the
+// interior launch covers only the sites that need no remote data (complete results, written
+// once), and after the halo has landed one boundary launch computes the remaining sites wholly.
+// No read-modify-write of `out`, no "incomplete" bookkeeping, two launches regardless of how
+// many dimensions are partitioned.
+#include <vector>
+#include "dslash.cuh"
+#include "dslash_api.h"
+#include "comm.h"
+
+namespace qb {
+
+static int prec_index(Prec p) { return p == PREC_DOUBLE ? 0 : (p == PREC_SINGLE ? 1 : 2); }
+static int prec_store_bytes(Prec p) { return p == PREC_HALF ? 2 : (int)p; }
+
+void Lattice::init(const int *X, int t_boundary_sign, double anisotropy) {
+  release();
+  V = 1;
+  for (int d = 0; d < 4; d++) {
+    if (X[d] < 2 || (X[d] & 1)) QB_ERROR("local lattice extent X[%d]=%d must be even and >= 2", d, X[d]);
+    geom.X[d] = X[d];
+    V *= X[d];
+  }
+  geom.Xh = X[0] / 2;
+  geom.Vh = (int)(V / 2);
+  Runtime &r = rt();
+  for (int d = 0; d < 4; d++) {
+    geom.faceVh[d] = (int)(V / X[d] / 2);
+    geom.part[d] = (r.part_mask >> d) & 1;
+  }
+  // antiperiodic sign lives on the links of the last global time slice
+  const bool last_t = r.coord[3] == r.grid[3] - 1, first_t = r.coord[3] == 0;
+  geom.tb_fwd = (t_boundary_sign < 0 && last_t) ? -1 : 1;
+  geom.tb_bwd = (t_boundary_sign < 0 && first_t) ? -1 : 1;
+  geom.aniso = (float)anisotropy;
+  for (int i = 0; i < 3; i++) arena_bytes[i] = 0;
+  if (r.part_mask) setup_partition();
+}
+
+void Lattice::release() {
+  for (int p = 0; p < 2; p++) {
+    if (interior_list[p]) cudaFree(interior_list[p]);
+    if (boundary_list[p]) cudaFree(boundary_list[p]);
+    interior_list[p] = boundary_list[p] = nullptr;
+    n_interior[p] = n_boundary[p] = 0;
+  }
+  for (int i = 0; i < 3; i++) {
+    if (send_arena[i]) comm_free_halo(send_arena[i]);
+    if (recv_arena[i]) comm_free_halo(recv_arena[i]);
+    send_arena[i] = recv_arena[i] = nullptr;
+    arena_bytes[i] = 0;
+  }
+}
+
+void Lattice::setup_partition() {
+  const Geom &g = geom;
+  // site lists (host build, once per lattice)
+  for (int p = 0; p < 2; p++) {
+    std::vector<int> in_l, bd_l;
+    in_l.reserve(g.Vh);
+    for (int cb = 0; cb < g.Vh; cb++) {
+      const int za = cb / g.Xh, zb = za / g.X[1];
+      int x[4];
+      x[1] = za - zb * g.X[1];
+      x[3] = zb / g.X[2];
+      x[2] = zb - x[3] * g.X[2];
+      x[0] = 2 * cb + ((x[1] + x[2] + x[3] + p) & 1) - za * g.X[0];
+      bool bd = false;
+      for (int d = 0; d < 4; d++)
+        if (g.part[d] && (x[d] == 0 || x[d] == g.X[d] - 1)) bd = true;
+      (bd ? bd_l : in_l).push_back(cb);
+    }
+    n_interior[p] = (int)in_l.size();
+    n_boundary[p] = (int)bd_l.size();
+    if (n_interior[p]) {
+      QB_CUDA(cudaMalloc((void **)&interior_list[p], sizeof(int) * n_interior[p]));
+      QB_CUDA(cudaMemcpy(interior_list[p], in_l.data(), sizeof(int) * n_interior[p], cudaMemcpyHostToDevice));
+    }
+    if (n_boundary[p]) {
+      QB_CUDA(cudaMalloc((void **)&boundary_list[p], sizeof(int) * n_boundary[p]));
+      QB_CUDA(cudaMemcpy(boundary_list[p], bd_l.data(), sizeof(int) * n_boundary[p], cudaMemcpyHostToDevice));
+    }
+  }
+}
+
+// halo arena for one precision: per partitioned (d, dir) a [plane][faceVh] half-spinor block
+// (12 reals per face site) and, for half precision, faceVh float norms.  256-byte aligned blocks.
+static void ensure_arena(Lattice &lat, Prec prec) {
+  const int pi = prec_index(prec);
+  if (lat.arena_bytes[pi]) return;
+  const Geom &g = lat.geom;
+  size_t off = 0;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  for (int d = 0; d < 4; d++)
+    for (int dir = 0; dir < 2; dir++) {
+      lat.face_off[pi][d][dir] = off;
+      lat.norm_off[pi][d][dir] = off;
+      if (!g.part[d]) continue;
+      off = align(off + (size_t)g.faceVh[d] * 12 * prec_store_bytes(prec));
+      if (prec == PREC_HALF) {
+        lat.norm_off[pi][d][dir] = off;
+        off = align(off + (size_t)g.faceVh[d] * sizeof(float));
+      }
+    }
+  lat.arena_bytes[pi] = off;
+  lat.send_arena[pi] = comm_alloc_halo(off);
+  lat.recv_arena[pi] = comm_alloc_halo(off);
+}
+
+template <typename Store>
+static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
+                  TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx) {
+  Runtime &r = rt();
+  const Geom &g = lat.geom;
+  DslashParam p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.parity = parity;
+  p.out = out.v; p.out_norm = out.norm;
+  p.in = in.v; p.in_norm = in.norm;
+  p.x = x ? x->v : nullptr; p.x_norm = x ? x->norm : nullptr;
+  p.gauge_fwd = gauge.dir_ptr(parity, 0);
+  p.gauge_bwd = gauge.dir_ptr(1 - parity, 0);
+  p.stride = g.Vh;
+  p.cin[0] = cin.p; p.cin[1] = cin.q;
+  p.co[0] = co.p; p.co[1] = co.q;
+  p.cx[0] = cx.p; p.cx[1] = cx.q;
+  p.sgn_fwd = dagger ? 1.0 : -1.0;
+  const bool twist_in = !cin.trivial();
+  const bool has_x = x != nullptr;
+
+  const bool partitioned = g.part[0] || g.part[1] || g.part[2] || g.part[3];
+  if (!partitioned) {
+    p.site_begin = 0; p.site_count = g.Vh; p.site_list = nullptr;
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, lat.block_size, r.compute);
+    return;
+  }
+
+  const int pi = prec_index(Store::prec);
+  ensure_arena(lat, Store::prec);
+  char *send = (char *)lat.send_arena[pi], *recv = (char *)lat.recv_arena[pi];
+  const bool self = comm_self_exchange();
+  // self-exchange (single rank, forced partitioning): our back face *is* our forward ghost -> alias, no copy
+  PackParam pk;
+  memset(&pk, 0, sizeof(pk));
+  pk.g = g;
+  pk.parity = 1 - parity;
+  pk.in = in.v; pk.in_norm = in.norm;
+  pk.stride = g.Vh;
+  pk.cin[0] = cin.p; pk.cin[1] = cin.q;
+  pk.sgn_fwd = p.sgn_fwd;
+  int off = 0;
+  for (int d = 0; d < 4; d++) {
+    pk.thread_off[d] = off;
+    if (g.part[d]) off += 2 * g.faceVh[d];
+    for (int dir = 0; dir < 2; dir++) {
+      pk.send[d][dir] = send + lat.face_off[pi][d][dir];
+      pk.send_norm[d][dir] = (float *)(send + lat.norm_off[pi][d][dir]);
+      // ghost[d][0] comes from the backward neighbour = its forward face (dir 1); ghost[d][1] = nbr's back face
+      const char *src = self ? send : recv;
+      p.ghost[d][dir] = src + lat.face_off[pi][d][1 - dir];
+      p.ghost_norm[d][dir] = (const float *)(src + lat.norm_off[pi][d][1 - dir]);
+      if (!self) {  // received blocks are laid out by *receiving* slot: recv[d][0] <- from back, recv[d][1] <- from fwd
+        p.ghost[d][dir] = recv + lat.face_off[pi][d][dir];
+        p.ghost_norm[d][dir] = (const float *)(recv + lat.norm_off[pi][d][dir]);
+      }
+    }
+    p.gauge_ghost[d] = gauge.ghost[d] ? (const char *)gauge.ghost[d] + (size_t)(1 - parity) * gauge.recon * gauge.store_bytes() * g.faceVh[d] : nullptr;
+    if (g.part[d] && !gauge.ghost[d]) QB_ERROR("gauge field has no ghost links for partitioned dimension %d", d);
+  }
+  pk.thread_off[4] = off;
+
+  // halo stream: wait until `in` is complete on the compute stream, pack, exchange
+  QB_CUDA(cudaEventRecord(r.ev_in_ready, r.compute));
+  QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_in_ready, 0));
+  launch_pack_T<Store>(pk, twist_in, r.halo);
+  if (!self) comm_exchange_halo(lat, pi, r.halo);
+  QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
+
+  // interior sites overlap with the exchange
+  const int np = parity;
+  if (lat.n_interior[np]) {
+    p.site_begin = 0; p.site_count = lat.n_interior[np]; p.site_list = lat.interior_list[np];
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, lat.block_size, r.compute);
+  }
+  QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
+  if (lat.n_boundary[np]) {
+    p.site_begin = 0; p.site_count = lat.n_boundary[np]; p.site_list = lat.boundary_list[np];
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, lat.block_size, r.compute);
+  }
+  // the next pack must not overwrite the send buffers before the boundary kernel (self mode reads them)
+  QB_CUDA(cudaEventRecord(r.ev_pack_ready, r.compute));
+  QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_pack_ready, 0));
+}
+
+void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
+               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx) {
+  if (out.prec != in.prec || out.prec != gauge.prec || (x && x->prec != out.prec))
+    QB_ERROR("apply_hop: precision mismatch (out %d, in %d, gauge %d)", (int)out.prec, (int)in.prec, (int)gauge.prec);
+  if (out.Vh != lat.geom.Vh || in.Vh != lat.geom.Vh) QB_ERROR("apply_hop: field volume does not match the lattice");
+  if (out.v == in.v) QB_ERROR("apply_hop: out and in must not alias");
+  if (out.prec == PREC_DOUBLE) hop_T<StoreD>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
+  else if (out.prec == PREC_SINGLE) hop_T<StoreS>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
+  else hop_T<StoreH>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
+}
+
+void apply_twist_field(SpinorField &out, const SpinorField &in, TwistCoef c) {
+  if (out.prec != in.prec || out.Vh != in.Vh || out.nparity != in.nparity) QB_ERROR("apply_twist_field: field mismatch");
+  Runtime &r = rt();
+  const int n = (int)(in.Vh);
+  for (int p = 0; p < in.nparity; p++) {
+    void *o = out.parity_ptr(p); float *on = out.parity_norm(p);
+    const void *i = in.parity_ptr(p); const float *inn = in.parity_norm(p);
+    if (in.prec == PREC_DOUBLE) launch_twist_T<StoreD>(o, on, i, inn, in.Vh, n, c.p, c.q, r.compute);
+    else if (in.prec == PREC_SINGLE) launch_twist_T<StoreS>(o, on, i, inn, in.Vh, n, c.p, c.q, r.compute);
+    else launch_twist_T<StoreH>(o, on, i, inn, in.Vh, n, c.p, c.q, r.compute);
+  }
+}
+
+}  // namespace qb

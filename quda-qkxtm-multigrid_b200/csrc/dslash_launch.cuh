@@ -1,0 +1,51 @@
+// Template dispatch for the fine-grid kernels; instantiated once per storage precision in
+// dslash_d.cu / dslash_s.cu / dslash_h.cu so the three precisions compile in parallel.
+#pragma once
+#include "dslash.cuh"
+#include "dslash_api.h"
+
+namespace qb {
+
+template <typename Store, int RECON>
+static void launch_dslash_recon(const DslashParam &p, bool twist_in, bool has_x, int block, cudaStream_t s) {
+  const int nb = div_up(p.site_count, block);
+  if (nb == 0) return;
+  if (twist_in) {
+    if (has_x) dslash_kernel<Store, RECON, true, true><<<nb, block, 0, s>>>(p);
+    else dslash_kernel<Store, RECON, true, false><<<nb, block, 0, s>>>(p);
+  } else {
+    if (has_x) dslash_kernel<Store, RECON, false, true><<<nb, block, 0, s>>>(p);
+    else dslash_kernel<Store, RECON, false, false><<<nb, block, 0, s>>>(p);
+  }
+  QB_CHECK_LAUNCH();
+}
+
+template <typename Store>
+void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, int block, cudaStream_t s) {
+  if (recon == 18) launch_dslash_recon<Store, 18>(p, twist_in, has_x, block, s);
+  else if (recon == 12) launch_dslash_recon<Store, 12>(p, twist_in, has_x, block, s);
+  else if (recon == 8) launch_dslash_recon<Store, 8>(p, twist_in, has_x, block, s);
+  else QB_ERROR("unsupported reconstruct %d", recon);
+}
+
+template <typename Store>
+void launch_pack_T(const PackParam &p, bool twist_in, cudaStream_t s) {
+  const int n = p.thread_off[4];
+  if (n == 0) return;
+  if (twist_in) pack_kernel<Store, true><<<div_up(n, 128), 128, 0, s>>>(p);
+  else pack_kernel<Store, false><<<div_up(n, 128), 128, 0, s>>>(p);
+  QB_CHECK_LAUNCH();
+}
+
+template <typename Store>
+void launch_twist_T(void *out, float *out_norm, const void *in, const float *in_norm, long stride, int n, double pr, double qr, cudaStream_t s) {
+  twist_kernel<Store><<<div_up(n, 256), 256, 0, s>>>(out, out_norm, in, in_norm, stride, n, pr, qr);
+  QB_CHECK_LAUNCH();
+}
+
+#define QB_INSTANTIATE_DSLASH(Store)                                                                          \
+  template void launch_dslash_T<Store>(const DslashParam &, int, bool, bool, int, cudaStream_t);              \
+  template void launch_pack_T<Store>(const PackParam &, bool, cudaStream_t);                                  \
+  template void launch_twist_T<Store>(void *, float *, const void *, const float *, long, int, double, double, cudaStream_t);
+
+}  // namespace qb

@@ -1,0 +1,93 @@
+// Device-resident lattice fields and their HBM layout.
+//
+// Layout rule (all fields): structure-of-arrays of 16-byte "planes", so that one warp reading one
+// plane of 32 consecutive checkerboard sites issues a single fully coalesced 512-byte request with
+// 128-bit loads per thread:
+//     spinor  : [parity][plane][cb site]      plane = 16 B = 1 complex<double> | 2 complex<float> | 4 complex<int16>
+//     gauge   : [parity][mu][plane][cb site]  recon 12/8: 16-B planes (fp64/fp32), 8-B planes (half);
+//                                             recon 18: 9 planes of one complex each
+//     half    : additionally one float norm per site, [parity][cb site]
+// Internal gamma basis is DeGrand-Rossi (chiral): the twist is diagonal, chirality blocks coincide
+// with the multigrid coarse spin, and the host test basis needs no rotation.  (The reference keeps
+// UKQCD internally and rotates on every copy: /root/reference/include/color_spinor_field.h:174,
+// lib/copy_color_spinor.cuh:49-92.)
+#pragma once
+#include "common.h"
+
+namespace qb {
+
+// Local lattice geometry, passed by value to kernels.
+struct Geom {
+  int X[4];       // local extents (x,y,z,t), all even
+  int Xh;         // X[0]/2
+  int Vh;         // checkerboard volume
+  int part[4];    // dimension partitioned -> boundary hops read the ghost zone
+  int faceVh[4];  // checkerboard face volume per dimension
+  int tb_fwd;     // -1 if forward T links on the local slice t=T-1 carry the antiperiodic sign
+  int tb_bwd;     // -1 if backward T links used by sites at t=0 carry it
+  float aniso;    // anisotropy (recon 12/8: scale of the reconstructed row for spatial links)
+};
+
+struct SpinorField {
+  Prec prec = PREC_DOUBLE;
+  int nparity = 1;       // 1: single-parity field, 2: full field [even | odd]
+  int ncomplex = 12;     // complex components per site (nspin * ncolor)
+  int nspin = 4, ncolor = 3;
+  long Vh = 0;           // sites per parity
+  void *v = nullptr;     // planes
+  float *norm = nullptr; // half precision only
+  size_t parity_bytes = 0;
+  bool owner = true;
+
+  SpinorField() {}
+  SpinorField(long Vh, int nparity, Prec prec, int nspin = 4, int ncolor = 3);
+  ~SpinorField();
+  SpinorField(const SpinorField &) = delete;
+  SpinorField &operator=(const SpinorField &) = delete;
+
+  int planes() const { return ncomplex * 2 * (int)(prec == PREC_HALF ? 2 : prec) / 16; }
+  size_t bytes() const { return parity_bytes * nparity; }
+  long reals() const { return (long)Vh * ncomplex * 2 * nparity; }
+  void *parity_ptr(int p) const { return (char *)v + parity_bytes * (nparity == 2 ? p : 0); }
+  float *parity_norm(int p) const { return norm ? norm + Vh * (nparity == 2 ? p : 0) : nullptr; }
+  // non-owning view of one parity of a full field (or the field itself if single parity)
+  void view_parity(SpinorField &dst, int p) const;
+  void zero(cudaStream_t s);
+};
+
+struct GaugeField {
+  Prec prec = PREC_DOUBLE;
+  int recon = 18;
+  long Vh = 0;
+  void *data = nullptr;          // [parity][mu][plane][Vh]
+  void *ghost[4] = {nullptr, nullptr, nullptr, nullptr};  // [parity][plane][faceVh[d]] : U_d at x_d = X_d-1 of the backward neighbour
+  int store_bytes() const { return prec == PREC_HALF ? 2 : (int)prec; }
+  int reals_per_plane() const { return recon == 18 ? 2 : (prec == PREC_DOUBLE ? 2 : 4); }
+  int planes() const { return recon / reals_per_plane(); }
+  size_t plane_elem_bytes() const { return (size_t)reals_per_plane() * store_bytes(); }
+  size_t dir_bytes() const { return (size_t)recon * store_bytes() * Vh; }  // one (parity, mu) block
+  size_t bytes() const { return 8 * dir_bytes(); }
+  void *dir_ptr(int parity, int mu) const { return (char *)data + (size_t)(parity * 4 + mu) * dir_bytes(); }
+  GaugeField(long Vh, Prec prec, int recon);
+  ~GaugeField();
+  GaugeField(const GaugeField &) = delete;
+  GaugeField &operator=(const GaugeField &) = delete;
+};
+
+// host <-> device marshalling (interface_quda.cpp:521-692 loadGaugeQuda; cuda_color_spinor_field.cu:513-552)
+enum HostBasis { BASIS_DEGRAND_ROSSI = 0, BASIS_UKQCD = 1 };
+enum HostSpinorOrder { ORDER_SPIN_COLOR = 0, ORDER_COLOR_SPIN = 1 };
+
+// h_gauge: QDP order void*[4], each [parity][cb][row][col][re,im] in host_prec
+void import_gauge(GaugeField &g, void *const *h_gauge, Prec host_prec, const Geom &geom, cudaStream_t s);
+void export_gauge(void *const *h_gauge, const GaugeField &g, Prec host_prec, const Geom &geom, cudaStream_t s);
+// fills g.ghost[d] for the partitioned dimensions from the local field (self-exchange) or the neighbour (NCCL)
+void exchange_gauge_ghost(GaugeField &g, const Geom &geom, cudaStream_t s);
+
+// h: [parity][cb][spin][color][re,im] (or color-spin) in host_prec; nparity taken from the field
+void import_spinor(SpinorField &f, const void *h, Prec host_prec, HostBasis basis, HostSpinorOrder order, cudaStream_t s);
+void export_spinor(void *h, const SpinorField &f, Prec host_prec, HostBasis basis, HostSpinorOrder order, cudaStream_t s);
+// precision change / copy between resident fields of identical geometry
+void copy_spinor(SpinorField &dst, const SpinorField &src, cudaStream_t s);
+
+}  // namespace qb

@@ -1,0 +1,187 @@
+"""Test-side helpers: load the CPU oracles (oracle/liboracle.so, oracle/_ref/libtmref.so) and wrap
+them with numpy signatures.  TEST INFRASTRUCTURE ONLY - the product never imports this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _ptrs(g):
+    return (C.c_void_p * 4)(*[a.ctypes.data for a in g])
+
+
+class Oracle:
+    """numpy face of oracle/tm_oracle.c (our C restatement of the reference's host verify path)."""
+
+    def __init__(self, lib):
+        self.L = lib
+        L = lib
+        L.orc_set_dims.argtypes = [C.POINTER(C.c_int)]
+        L.orc_drand_fill.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_uint64)]
+        L.orc_construct_gauge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint]
+        L.orc_construct_weak_gauge.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_uint64]
+        L.orc_site_coords.argtypes = [C.POINTER(C.c_int), C.c_long, C.c_int]
+        L.orc_site_index.argtypes = [C.POINTER(C.c_int)]
+        L.orc_site_index.restype = C.c_long
+        for s in ("_d", "_f"):
+            getattr(L, "orc_wil_dslash" + s).argtypes = [C.c_void_p] * 3 + [C.c_int] * 2
+            getattr(L, "orc_twist_gamma5" + s).argtypes = [C.c_void_p] * 2 + [C.c_int, C.c_double, C.c_double, C.c_int, C.c_long, C.c_int]
+            getattr(L, "orc_tm_dslash" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 4
+            getattr(L, "orc_tm_matpc" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 3
+            getattr(L, "orc_tm_mat" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 2
+            getattr(L, "orc_wil_mat" + s).argtypes = [C.c_void_p] * 3 + [C.c_double, C.c_int]
+            getattr(L, "orc_wil_matpc" + s).argtypes = [C.c_void_p] * 3 + [C.c_double, C.c_int, C.c_int]
+        self.dims = None
+
+    def set_dims(self, X):
+        self.dims = tuple(int(x) for x in X)
+        self.V = int(np.prod(self.dims))
+        self.Vh = self.V // 2
+        self.L.orc_set_dims((C.c_int * 4)(*self.dims))
+
+    def drand(self, n, seed=137):
+        out = np.empty(n, dtype=np.float64)
+        st = C.c_uint64(seed)
+        self.L.orc_drand_fill(_ptr(out), n, C.byref(st))
+        return out
+
+    def gauge(self, kind=1, antiperiodic=True, anisotropy=1.0, seed=137):
+        g = [np.zeros(self.V * 18, dtype=np.float64) for _ in range(4)]
+        self.L.orc_construct_gauge(_ptrs(g), kind, int(antiperiodic), anisotropy, seed)
+        return g
+
+    def weak_gauge(self, eps=0.2, antiperiodic=False, seed=4711):
+        g = [np.zeros(self.V * 18, dtype=np.float64) for _ in range(4)]
+        self.L.orc_construct_weak_gauge(_ptrs(g), eps, int(antiperiodic), seed)
+        return g
+
+    @staticmethod
+    def _suffix(a):
+        return "_d" if a.dtype == np.float64 else "_f"
+
+    def _cast_gauge(self, g, dtype):
+        return g if g[0].dtype == dtype else [a.astype(dtype) for a in g]
+
+    def wil_dslash(self, g, inp, parity, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(self.Vh * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_wil_dslash" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), parity, dagger)
+        return out
+
+    def tm_dslash(self, g, inp, kappa, mu, flavor, parity, matpc, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(self.Vh * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_tm_dslash" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, mu, flavor, parity, matpc, dagger)
+        return out
+
+    def tm_matpc(self, g, inp, kappa, mu, flavor, matpc, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(self.Vh * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_tm_matpc" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, mu, flavor, matpc, dagger)
+        return out
+
+    def tm_mat(self, g, inp, kappa, mu, flavor, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(self.V * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_tm_mat" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, mu, flavor, dagger)
+        return out
+
+    def wil_mat(self, g, inp, kappa, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(self.V * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_wil_mat" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, dagger)
+        return out
+
+    def wil_matpc(self, g, inp, kappa, matpc, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(self.Vh * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_wil_matpc" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, matpc, dagger)
+        return out
+
+    def twist(self, inp, kappa, mu, flavor, dagger, inverse):
+        out = np.zeros_like(inp)
+        getattr(self.L, "orc_twist_gamma5" + self._suffix(inp))(_ptr(out), _ptr(inp), dagger, kappa, mu, flavor, inp.size // 24, int(inverse))
+        return out
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle.so"])
+
+
+def load_oracle():
+    path = os.path.join(ORACLE_DIR, "liboracle.so")
+    if not os.path.exists(path):
+        build_oracle()
+    return Oracle(C.CDLL(path))
+
+
+class Ref:
+    """numpy face of oracle/_ref/libtmref.so = the reference's own unmodified CPU sources."""
+
+    def __init__(self, lib):
+        self.L = lib
+        L = lib
+        L.tmref_setup.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_double]
+        L.tmref_construct_gauge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint]
+        L.tmref_wil_dslash.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3
+        L.tmref_tm_dslash.argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 5
+        L.tmref_tm_matpc.argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 4
+        L.tmref_tm_mat.argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 3
+
+    def setup(self, X, antiperiodic=True, anisotropy=1.0):
+        self.dims = tuple(int(x) for x in X)
+        self.V = int(np.prod(self.dims))
+        self.Vh = self.V // 2
+        self.L.tmref_setup((C.c_int * 4)(*self.dims), int(antiperiodic), anisotropy)
+
+    def gauge(self, kind=1, seed=137, dtype=np.float64):
+        g = [np.zeros(self.V * 18, dtype=dtype) for _ in range(4)]
+        self.L.tmref_construct_gauge(_ptrs(g), kind, g[0].itemsize, seed)
+        return g
+
+    def tm_dslash(self, g, inp, kappa, mu, flavor, parity, matpc, dagger):
+        out = np.zeros(self.Vh * 24, dtype=inp.dtype)
+        work = inp.copy()  # the reference twists its input in place for some variants
+        self.L.tmref_tm_dslash(_ptr(out), _ptrs(g), _ptr(work), kappa, mu, flavor, parity, matpc, dagger, inp.itemsize)
+        return out
+
+    def tm_matpc(self, g, inp, kappa, mu, flavor, matpc, dagger):
+        out = np.zeros(self.Vh * 24, dtype=inp.dtype)
+        work = inp.copy()
+        self.L.tmref_tm_matpc(_ptr(out), _ptrs(g), _ptr(work), kappa, mu, flavor, matpc, dagger, inp.itemsize)
+        return out
+
+    def tm_mat(self, g, inp, kappa, mu, flavor, dagger):
+        out = np.zeros(self.V * 24, dtype=inp.dtype)
+        self.L.tmref_tm_mat(_ptr(out), _ptrs(g), _ptr(inp.copy()), kappa, mu, flavor, dagger, inp.itemsize)
+        return out
+
+    def wil_dslash(self, g, inp, parity, dagger):
+        out = np.zeros(self.Vh * 24, dtype=inp.dtype)
+        self.L.tmref_wil_dslash(_ptr(out), _ptrs(g), _ptr(inp.copy()), parity, dagger, inp.itemsize)
+        return out
+
+
+def load_ref():
+    """Returns None when neither the prebuilt library nor the reference tree is available."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libtmref.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference/tests"):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "_ref/libtmref.so"])
+        else:
+            return None
+    return Ref(C.CDLL(path))
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))

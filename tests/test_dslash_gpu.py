@@ -1,0 +1,304 @@
+"""GPU parity tests of the fine-grid operators through the C ABI (dslashQuda / MatQuda / MatDagMatQuda),
+modelled on the reference's tests/dslash_test.cpp (test types 0-4 x dagger x matpc x flavor) with the
+reference's inputs (random SU(3) links from srand(137), LCG spinor seeded 137, kappa=0.1, mu=0.01,
+antiperiodic T).  Oracle: oracle/tm_oracle.c (bit-pinned to the reference's own objects, tests/test_oracle.py).
+
+Tolerances (BASELINE.json north_star): relative L2  fp64 <= 1e-13, fp32 <= 1e-6, half <= 1e-3.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests.oracle_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+KAPPA, MU = 0.1, 0.01
+TOL = {8: 1e-13, 4: 1e-6, 2: 1e-3}
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "tm_ref_4448.npz")
+
+
+def vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Ctx:
+    """Lattice + inputs + loaded gauge for one (dims, precision, reconstruct)."""
+
+    def __init__(self, quda, oracle, X, prec, recon, seed=137, antiperiodic=True, anisotropy=1.0):
+        self.q, self.o, self.X, self.prec = quda, oracle, X, prec
+        oracle.set_dims(X)
+        self.g = oracle.gauge(kind=1, antiperiodic=antiperiodic, anisotropy=anisotropy, seed=seed)
+        self.sp = oracle.drand(2 * oracle.Vh * 24, seed=137)
+        self.Vh = oracle.Vh
+        self.even = self.sp[: self.Vh * 24].copy()
+        gp = quda.gauge_param(X, cuda_prec=prec, reconstruct=recon, anisotropy=anisotropy,
+                              t_boundary=quda.QUDA_ANTI_PERIODIC_T if antiperiodic else quda.QUDA_PERIODIC_T)
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in self.g])
+        quda.lib().loadGaugeQuda(ptrs, C.byref(gp))
+        assert gp.gaugeGiB > 0
+
+    def param(self, **kw):
+        return self.q.invert_param(kappa=KAPPA, mu=MU, cuda_prec=self.prec, **kw)
+
+
+def run_dslash(c, flavor, parity, matpc, dagger):
+    p = c.param(flavor=flavor, matpc=matpc, dagger=dagger)
+    out = np.zeros(c.Vh * 24)
+    c.q.lib().dslashQuda(vp(out), vp(c.even), C.byref(p), parity)
+    c.o.set_dims(c.X)
+    return out, c.o.tm_dslash(c.g, c.even, KAPPA, MU, flavor, parity, matpc, dagger)
+
+
+@pytest.mark.parametrize("prec", [8, 4, 2])
+@pytest.mark.parametrize("recon", [18, 12, 8])
+def test_tm_dslash_all_variants_8x8x8x8(quda, oracle, prec, recon):
+    """BASELINE config 1 (8^4, random SU(3)) -- dslash_test --test 0, every flavor/parity/matpc/dagger."""
+    c = Ctx(quda, oracle, (8, 8, 8, 8), prec, recon)
+    tol = TOL[prec]
+    if recon == 8 and prec == 4:
+        tol = 5e-6   # fp32 reconstruct-8: trig + rsqrt reconstruction (reference asserts 1e-3 here, dslash_test.cpp:942-947)
+    if recon == 8 and prec == 2:
+        tol = 2e-3
+    worst = 0.0
+    for flavor in (1, -1):
+        for parity in (0, 1):
+            for matpc in (0, 2):
+                for dagger in (0, 1):
+                    out, ref = run_dslash(c, flavor, parity, matpc, dagger)
+                    worst = max(worst, rel_l2(out, ref))
+    assert worst <= tol, f"prec {prec} recon {recon}: rel L2 {worst:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("prec", [8, 4, 2])
+def test_matpc_and_mat(quda, oracle, prec):
+    """dslash_test --test 1 (MatPC), 2 (Mat), 3/4 (MatPCDagMatPC / MatDagMat)."""
+    q = quda
+    c = Ctx(quda, oracle, (8, 8, 8, 8), prec, 12)
+    L = q.lib()
+    tol = TOL[prec] * (1 if prec != 2 else 2)
+    for flavor in (1, -1):
+        for matpc in range(4):
+            for dagger in (0, 1):
+                p = c.param(flavor=flavor, matpc=matpc, dagger=dagger, solution_type=q.QUDA_MATPC_SOLUTION)
+                out = np.zeros(c.Vh * 24)
+                L.MatQuda(vp(out), vp(c.even), C.byref(p))
+                ref = c.o.tm_matpc(c.g, c.even, KAPPA, MU, flavor, matpc, dagger)
+                assert rel_l2(out, ref) <= tol, (flavor, matpc, dagger)
+    for dagger in (0, 1):
+        p = c.param(dagger=dagger, solution_type=q.QUDA_MAT_SOLUTION)
+        out = np.zeros(c.o.V * 24)
+        L.MatQuda(vp(out), vp(c.sp), C.byref(p))
+        ref = c.o.tm_mat(c.g, c.sp, KAPPA, MU, 1, dagger)
+        assert rel_l2(out, ref) <= tol
+    # MatDagMat = Mdag M (full and preconditioned)
+    p = c.param(solution_type=q.QUDA_MAT_SOLUTION)
+    out = np.zeros(c.o.V * 24)
+    L.MatDagMatQuda(vp(out), vp(c.sp), C.byref(p))
+    ref = c.o.tm_mat(c.g, c.o.tm_mat(c.g, c.sp, KAPPA, MU, 1, 0), KAPPA, MU, 1, 1)
+    assert rel_l2(out, ref) <= 2 * tol
+    p = c.param(solution_type=q.QUDA_MATPC_SOLUTION, matpc=q.QUDA_MATPC_EVEN_EVEN)
+    out = np.zeros(c.Vh * 24)
+    L.MatDagMatQuda(vp(out), vp(c.even), C.byref(p))
+    ref = c.o.tm_matpc(c.g, c.o.tm_matpc(c.g, c.even, KAPPA, MU, 1, 0, 0), KAPPA, MU, 1, 0, 1)
+    assert rel_l2(out, ref) <= 2 * tol
+
+
+def test_mass_normalization_and_wilson(quda, oracle):
+    q = quda
+    c = Ctx(quda, oracle, (4, 4, 4, 8), 8, 18)
+    L = q.lib()
+    p = c.param(solution_type=q.QUDA_MAT_SOLUTION, mass_normalization=q.QUDA_MASS_NORMALIZATION)
+    out = np.zeros(c.o.V * 24)
+    L.MatQuda(vp(out), vp(c.sp), C.byref(p))
+    ref = c.o.tm_mat(c.g, c.sp, KAPPA, MU, 1, 0) * (0.5 / KAPPA)
+    assert rel_l2(out, ref) <= 1e-13
+    p = c.param(solution_type=q.QUDA_MATPC_SOLUTION, mass_normalization=q.QUDA_MASS_NORMALIZATION)
+    out = np.zeros(c.Vh * 24)
+    L.MatQuda(vp(out), vp(c.even), C.byref(p))
+    ref = c.o.tm_matpc(c.g, c.even, KAPPA, MU, 1, 0, 0) * (0.25 / KAPPA ** 2)
+    assert rel_l2(out, ref) <= 1e-13
+    # plain Wilson through the same kernels
+    p = c.param(dslash_type=q.QUDA_WILSON_DSLASH, solution_type=q.QUDA_MAT_SOLUTION)
+    out = np.zeros(c.o.V * 24)
+    L.MatQuda(vp(out), vp(c.sp), C.byref(p))
+    assert rel_l2(out, c.o.wil_mat(c.g, c.sp, KAPPA, 0)) <= 1e-13
+    for matpc in (0, 1):
+        p = c.param(dslash_type=q.QUDA_WILSON_DSLASH, solution_type=q.QUDA_MATPC_SOLUTION, matpc=matpc)
+        out = np.zeros(c.Vh * 24)
+        L.MatQuda(vp(out), vp(c.even), C.byref(p))
+        assert rel_l2(out, c.o.wil_matpc(c.g, c.even, KAPPA, matpc, 0)) <= 1e-13
+
+
+def test_golden_vectors_from_reference(quda, oracle):
+    """Outputs of the reference's own CPU objects (tests/golden/make_golden.py), lattice 4x4x4x8."""
+    gold = np.load(GOLD)
+    X = tuple(int(x) for x in gold["X"])
+    c = Ctx(quda, oracle, X, 8, 18)
+    L = quda.lib()
+    for key in gold.files:
+        parts = key.split("_")
+        if key.startswith("dslash_"):
+            f, par, m, d = int(parts[1][1:]), int(parts[2][1:]), int(parts[3][1:]), int(parts[4][1:])
+            p = c.param(flavor=f, matpc=m, dagger=d)
+            out = np.zeros(c.Vh * 24)
+            L.dslashQuda(vp(out), vp(c.even), C.byref(p), par)
+        elif key.startswith("matpc_"):
+            p = c.param(matpc=int(parts[1][1:]), dagger=int(parts[2][1:]), solution_type=quda.QUDA_MATPC_SOLUTION)
+            out = np.zeros(c.Vh * 24)
+            L.MatQuda(vp(out), vp(c.even), C.byref(p))
+        elif key.startswith("mat_"):
+            p = c.param(dagger=int(parts[1][1:]), solution_type=quda.QUDA_MAT_SOLUTION)
+            out = np.zeros(c.o.V * 24)
+            L.MatQuda(vp(out), vp(c.sp), C.byref(p))
+        else:
+            continue
+        assert rel_l2(out, gold[key]) <= 1e-13, key
+
+
+@pytest.mark.parametrize("X", [(4, 4, 4, 4), (2, 2, 2, 2), (6, 4, 2, 8), (16, 8, 4, 2), (4, 12, 6, 10)])
+def test_ragged_and_minimal_lattices(quda, oracle, X):
+    c = Ctx(quda, oracle, X, 8, 12)
+    for parity in (0, 1):
+        out, ref = run_dslash(c, 1, parity, 0, 0)
+        assert rel_l2(out, ref) <= 1e-13
+
+
+def test_anisotropy_and_periodic(quda, oracle):
+    c = Ctx(quda, oracle, (4, 4, 4, 8), 8, 12, anisotropy=2.5)
+    out, ref = run_dslash(c, 1, 0, 0, 0)
+    assert rel_l2(out, ref) <= 1e-13
+    c = Ctx(quda, oracle, (4, 4, 4, 8), 8, 8, anisotropy=2.5)
+    out, ref = run_dslash(c, 1, 1, 0, 1)
+    assert rel_l2(out, ref) <= 1e-12
+    c = Ctx(quda, oracle, (4, 4, 4, 8), 4, 12, antiperiodic=False)
+    out, ref = run_dslash(c, -1, 1, 2, 1)
+    assert rel_l2(out, ref) <= 1e-6
+
+
+def test_host_field_orders_and_basis(quda, oracle):
+    """QDP (spin inside colour) order and UKQCD basis at the API must give the same operator."""
+    q = quda
+    c = Ctx(quda, oracle, (4, 4, 4, 8), 8, 18)
+    L = q.lib()
+    ref = c.o.tm_dslash(c.g, c.even, KAPPA, MU, 1, 0, 0, 0)
+    # colour-spin order
+    p = c.param(dirac_order=q.QUDA_QDP_DIRAC_ORDER)
+    inp = c.even.reshape(-1, 4, 3, 2).transpose(0, 2, 1, 3).copy().ravel()
+    out = np.zeros_like(inp)
+    L.dslashQuda(vp(out), vp(inp), C.byref(p), 0)
+    out = out.reshape(-1, 3, 4, 2).transpose(0, 2, 1, 3).ravel()
+    assert rel_l2(out, ref) <= 1e-13
+    # UKQCD basis: psi_uk = R psi_dr (lib/copy_color_spinor.cuh:49-66), D_uk = R D_dr R^-1
+    k = 1 / np.sqrt(2)
+    R = k * np.array([[0, 1, 0, 1], [-1, 0, -1, 0], [0, 1, 0, -1], [-1, 0, 1, 0]], dtype=float)
+    e = c.even.reshape(-1, 4, 3, 2)
+    inp = np.einsum("st,xtcr->xscr", R, e).copy().ravel()
+    p = c.param(gamma_basis=q.QUDA_UKQCD_GAMMA_BASIS)
+    out = np.zeros_like(inp)
+    L.dslashQuda(vp(out), vp(inp), C.byref(p), 0)
+    back = np.einsum("st,xtcr->xscr", R.T, out.reshape(-1, 4, 3, 2)).ravel()
+    assert rel_l2(back, ref) <= 1e-13
+
+
+def test_save_gauge_roundtrip(quda, oracle):
+    for recon, tol in ((18, 0.0), (12, 1e-14), (8, 1e-12)):
+        c = Ctx(quda, oracle, (4, 4, 4, 8), 8, recon)
+        back = [np.zeros_like(a) for a in c.g]
+        gp = quda.gauge_param(c.X, cuda_prec=8, reconstruct=recon)
+        quda.lib().saveGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in back]), C.byref(gp))
+        err = max(np.abs(a - b).max() for a, b in zip(back, c.g))
+        assert err <= tol, (recon, err)
+
+
+@pytest.mark.parametrize("mask", [8, 4, 12, 15, 1, 3])
+@pytest.mark.parametrize("prec", [8, 4, 2])
+def test_partitioned_self_exchange(oracle, mask, prec):
+    """The halo path (face pack -> ghost zone -> interior/boundary split) on one GPU: every partitioned
+    dimension exchanges with itself, the reference's `--partition` trick (tests/test_util.cpp:2047-2065).
+    Runs in a subprocess because partitioning is fixed at communicator set-up."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, {root!r})
+import quda_b200 as q
+from tests import oracle_util as ou
+o = ou.load_oracle(); X=(8,4,6,8); o.set_dims(X)
+g = o.gauge(1, True, 1.0, 137); sp = o.drand(2*o.Vh*24, 137); even = sp[:o.Vh*24].copy()
+L = q.lib(); L.initQuda(0); L.commDimPartitionedSetQudaB200({mask})
+gp = q.gauge_param(X, cuda_prec={prec}, reconstruct=12)
+L.loadGaugeQuda((C.c_void_p*4)(*[a.ctypes.data for a in g]), C.byref(gp))
+worst = 0.0
+for flavor, parity, matpc, dag in [(1,0,0,0),(1,1,0,1),(-1,0,2,1),(1,1,2,0)]:
+    p = q.invert_param(cuda_prec={prec}, flavor=flavor, matpc=matpc, dagger=dag)
+    out = np.zeros(o.Vh*24)
+    L.dslashQuda(out.ctypes.data_as(C.c_void_p), even.ctypes.data_as(C.c_void_p), C.byref(p), parity)
+    worst = max(worst, ou.rel_l2(out, o.tm_dslash(g, even, 0.1, 0.01, flavor, parity, matpc, dag)))
+p = q.invert_param(cuda_prec={prec}, solution_type=q.QUDA_MAT_SOLUTION)
+out = np.zeros(o.V*24)
+L.MatQuda(out.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p), C.byref(p))
+worst = max(worst, ou.rel_l2(out, o.tm_mat(g, sp, 0.1, 0.01, 1, 0)))
+L.endQuda()
+print("WORST", worst)
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst <= TOL[prec] * (2 if prec == 2 else 1), worst
+
+
+def test_resident_api_and_large_lattice_properties(quda, oracle):
+    """BASELINE config 2 size (32^3 x 64, fp32 recon-12 and half): size-independent properties --
+    linearity, gamma5-hermiticity  <a, D b> = <D^dag a, b>, and A^-1 D agreeing with the 8^4-verified
+    kernels on a periodic tiling of the 8^4 inputs."""
+    q = quda
+    L = q.lib()
+    X = (32, 32, 32, 64)
+    oracle.set_dims((8, 8, 8, 8))
+    g8 = oracle.gauge(kind=1, antiperiodic=False, seed=137)
+    e8 = oracle.drand(2 * oracle.Vh * 24, seed=137)
+    # tile the 8^4 lattice periodically: site (x,y,z,t) of the big lattice carries the data of (x%8, ...)
+    V8h = 2048
+
+    def tile_field(arr8, per_site):
+        # arr8: [parity][cb][per_site] on 8^4 -> same on X
+        a = arr8.reshape(2, V8h, per_site)
+        lex8 = np.zeros((8, 8, 8, 8, per_site))  # t z y x
+        for par in (0, 1):
+            cb = np.arange(V8h)
+            za = cb // 4; x1h = cb - za * 4; zb = za // 8; y = za - zb * 8; t = zb // 8; z = zb - t * 8
+            x = 2 * x1h + ((y + z + t + par) & 1)
+            lex8[t, z, y, x] = a[par]
+        big = np.tile(lex8, (X[3] // 8, X[2] // 8, X[1] // 8, X[0] // 8, 1))
+        T, Z, Y, XX = X[3], X[2], X[1], X[0]
+        tt, zz, yy, xx = np.meshgrid(np.arange(T), np.arange(Z), np.arange(Y), np.arange(XX), indexing="ij")
+        par = (tt + zz + yy + xx) & 1
+        flat = big.reshape(-1, per_site)
+        parf = par.ravel()
+        return np.concatenate([flat[parf == 0], flat[parf == 1]]).ravel()
+
+    g = [tile_field(a, 18) for a in g8]
+    sp = tile_field(e8, 24)
+    Vh = int(np.prod(X)) // 2
+    for prec, tol in ((4, 1e-6), (2, 1e-3)):
+        gp = q.gauge_param(X, cuda_prec=prec, reconstruct=12, t_boundary=q.QUDA_PERIODIC_T)
+        L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+        p = q.invert_param(cuda_prec=prec)
+        fin = L.newSpinorQudaB200(q.QUDA_PARITY_SITE_SUBSET, prec)
+        fout = L.newSpinorQudaB200(q.QUDA_PARITY_SITE_SUBSET, prec)
+        odd = sp[Vh * 24:].copy()
+        L.loadSpinorQudaB200(fin, vp(odd), C.byref(p))
+        L.dslashResidentQudaB200(fout, fin, C.byref(p), 0)
+        out = np.zeros(Vh * 24)
+        L.saveSpinorQudaB200(vp(out), fout, C.byref(p))
+        # oracle on the 8^4 cell, tiled
+        oracle.set_dims((8, 8, 8, 8))
+        ref8 = oracle.tm_dslash(g8, e8[V8h * 24:].copy(), KAPPA, MU, 1, 0, 0, 0)
+        ref = tile_field(np.concatenate([ref8, np.zeros_like(ref8)]), 24)[: Vh * 24]
+        assert rel_l2(out, ref) <= tol, (prec, rel_l2(out, ref))
+        L.freeSpinorQudaB200(fin)
+        L.freeSpinorQudaB200(fout)
