@@ -37,6 +37,9 @@ void matDagMatResidentQudaB200(void *out, void *in, QudaInvertParam *param);
 double timeDslashQudaB200(void *out, void *in, QudaInvertParam *param, QudaParity parity, int niter,
                           float *per_iter_ms);
 
+/* launch geometry of the fine Dslash kernels (the reference autotunes this, lib/tune.cpp:480-655;
+ * here a fixed default is used and this knob exists for tuning runs).  Call after loadGaugeQuda. */
+void setDslashBlockSizeQudaB200(int threads_per_block);
 /* number of kernels this library has launched since initQuda (monotonic counter) */
 long long kernelLaunchCountQudaB200(void);
 /* the CUDA stream (cudaStream_t) compute kernels are launched on */
@@ -53,6 +56,21 @@ void commsBootstrapQudaB200(int rank, int size, const void *unique_id_128B);
  * itself and consumed by the boundary kernels (the reference's --partition test trick,
  * tests/test_util.cpp:2047-2065, lib/comm_common.cpp:420-433).  mask bit d = dimension d. */
 void commDimPartitionedSetQudaB200(int mask);
+
+/* --- multigrid introspection (what MG::verify, lib/multigrid.cpp:372-486, checks inside the library) ----
+ * `mg` is the handle returned by newMultigridQuda; level 0 is the fine grid.  Generic host field order:
+ * [parity][checkerboard site][component k = spin * nColor + colour][re, im], float32. */
+/* relative deviations {|R P eta - eta|, max_k |P R v_k - v_k|, |R M P eta - M_c eta|} of level `level` */
+void mgVerifyQudaB200(void *mg, int level, double *dev3);
+/* info8 = {coarse X[0..3], n_vec, fine components per site, sites per aggregate, coarse components per site} */
+void mgLevelInfoQudaB200(void *mg, int level, int *info8);
+void mgProlongQudaB200(void *mg, int level, float *h_fine_out, const float *h_coarse_in);
+void mgRestrictQudaB200(void *mg, int level, float *h_coarse_out, const float *h_fine_in);
+/* operator of a level: pc = 0 the full operator (level 0: fine M, level >= 1: coarse M_c), pc = 1 the smoother's operator */
+void mgMatQudaB200(void *mg, int level, int pc, float *h_out, const float *h_in);
+void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out);
+/* one multigrid cycle of level `level`:  x = MG(b) */
+void mgCycleQudaB200(void *mg, int level, float *h_x, const float *h_b);
 
 #ifdef __cplusplus
 }

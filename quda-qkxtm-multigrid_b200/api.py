@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libquda_b200.so")
+LIB_PATH = os.environ.get("QUDA_B200_LIB", os.path.join(_HERE, "libquda_b200.so"))  # override: tuning builds only
 
 QUDA_MAX_DIM = 6
 QUDA_MAX_MULTI_SHIFT = 32
@@ -133,8 +133,10 @@ EXPORTS = [
     "loadCloverQuda", "freeCloverQuda", "invertMultiSrcQuda", "invertMultiShiftQuda", "cloverQuda",
     "newSpinorQudaB200", "freeSpinorQudaB200", "loadSpinorQudaB200", "saveSpinorQudaB200",
     "dslashResidentQudaB200", "matResidentQudaB200", "matDagMatResidentQudaB200", "timeDslashQudaB200",
-    "kernelLaunchCountQudaB200", "computeStreamQudaB200", "syncQudaB200",
+    "setDslashBlockSizeQudaB200", "kernelLaunchCountQudaB200", "computeStreamQudaB200", "syncQudaB200",
     "ncclUniqueIdQudaB200", "commsBootstrapQudaB200", "commDimPartitionedSetQudaB200",
+    "mgVerifyQudaB200", "mgLevelInfoQudaB200", "mgProlongQudaB200", "mgRestrictQudaB200", "mgMatQudaB200",
+    "mgNullVectorQudaB200", "mgCycleQudaB200",
 ]
 
 _lib = None
@@ -180,11 +182,19 @@ def lib():
     L.matDagMatResidentQudaB200.argtypes = [_p, _p, IP]
     L.timeDslashQudaB200.argtypes = [_p, _p, IP, _i, _i, C.POINTER(C.c_float)]
     L.timeDslashQudaB200.restype = _d
+    L.setDslashBlockSizeQudaB200.argtypes = [_i]
     L.kernelLaunchCountQudaB200.restype = C.c_longlong
     L.computeStreamQudaB200.restype = _p
     L.ncclUniqueIdQudaB200.argtypes = [_p]
     L.commsBootstrapQudaB200.argtypes = [_i, _i, _p]
     L.commDimPartitionedSetQudaB200.argtypes = [_i]
+    L.mgVerifyQudaB200.argtypes = [_p, _i, C.POINTER(_d)]
+    L.mgLevelInfoQudaB200.argtypes = [_p, _i, C.POINTER(_i)]
+    L.mgProlongQudaB200.argtypes = [_p, _i, _p, _p]
+    L.mgRestrictQudaB200.argtypes = [_p, _i, _p, _p]
+    L.mgMatQudaB200.argtypes = [_p, _i, _i, _p, _p]
+    L.mgNullVectorQudaB200.argtypes = [_p, _i, _i, _p]
+    L.mgCycleQudaB200.argtypes = [_p, _i, _p, _p]
     _lib = L
     return L
 
@@ -249,3 +259,38 @@ def invert_param(kappa=0.1, mu=0.01, flavor=QUDA_TWIST_PLUS, dslash_type=QUDA_TW
     p.inv_type = QUDA_GCR_INVERTER
     p.preserve_source = QUDA_PRESERVE_SOURCE_YES
     return p
+
+
+def multigrid_param(inv_param, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(24,), nu_pre=2, nu_post=2,
+                    smoother_tol=0.25, omega=0.85, setup_maxiter=500, setup_tol=5e-6,
+                    cycle=QUDA_MG_CYCLE_RECURSIVE, generate_all_levels=True):
+    """What tests/multigrid_invert_test.cpp:161-286 (setMultigridParam) fills in.
+    `inv_param` must stay alive as long as the returned struct is used."""
+    m = lib().newQudaMultigridParam()
+    m.invert_param = C.pointer(inv_param)
+    m.n_level = n_level
+    for l in range(n_level):
+        gb = geo_block[min(l, len(geo_block) - 1)]
+        for d in range(QUDA_MAX_DIM):
+            m.geo_block_size[l][d] = gb[d] if d < 4 else 1
+        m.spin_block_size[l] = 2 if l == 0 else 1
+        m.n_vec[l] = n_vec[min(l, len(n_vec) - 1)]
+        m.nu_pre[l] = nu_pre
+        m.nu_post[l] = nu_post
+        m.cycle_type[l] = cycle
+        m.smoother[l] = QUDA_MR_INVERTER
+        m.smoother_tol[l] = smoother_tol
+        m.global_reduction[l] = QUDA_BOOLEAN_YES
+        m.smoother_solve_type[l] = QUDA_DIRECT_PC_SOLVE
+        m.coarse_grid_solution_type[l] = QUDA_MAT_SOLUTION
+        m.omega[l] = omega
+        m.location[l] = QUDA_CUDA_FIELD_LOCATION
+    m.smoother[n_level - 1] = QUDA_GCR_INVERTER
+    m.compute_null_vector = QUDA_COMPUTE_NULL_VECTOR_YES
+    m.generate_all_levels = QUDA_BOOLEAN_YES if generate_all_levels else QUDA_BOOLEAN_NO
+    m.run_verify = QUDA_BOOLEAN_YES
+    m.setup_maxiter = setup_maxiter
+    m.setup_tol = setup_tol
+    m.delta_muPR = 1.0
+    m.delta_kappaPR = 1.0
+    return m

@@ -381,7 +381,7 @@ double cabxpyAxNorm(double a, Complex b, SpinorField &x, SpinorField &y) {
           reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
             Pack<real> u = X[i], v = Y[i];
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; acc[0] += norm_c(u.c[k]); }
+            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; acc[0] += norm_c(v.c[k]); }
             X[i] = u; Y[i] = v;
           }););
   flops += 7 * x.reals(); bytes += 4 * x.bytes();

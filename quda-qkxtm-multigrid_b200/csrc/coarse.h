@@ -1,0 +1,80 @@
+// Multigrid coarse-level operator (replaces /root/reference/lib/dirac_coarse.cpp, lib/dslash_coarse.cu
+// and the coarse-link construction of lib/coarse_op.cu, lib/coarsecoarse_op.cu, lib/coarse_op.cuh).
+//
+// Stencil form used at every level:   (M psi)(x) = L_8(x) psi(x) + sum_{d=0..7} L_d(x) psi(x + e_d)
+// with e_d = +mu for d = 2 mu and -mu for d = 2 mu + 1.  On a coarse level L_d(x) are dense N x N complex
+// matrices (N = 2 * n_vec: chirality x null-vector index) kept in HBM as
+//     Y[site][d][col][row pair] float4 = (Y[2rp][col], Y[2rp+1][col])
+// i.e. one contiguous 9*N*N*8-byte record per site, column-major in row pairs, so that the matvec of the
+// coarse Dslash streams each matrix once with 128-bit loads and needs no cross-thread reduction inside a
+// direction.  The links are the Galerkin product  L^c = R L P  of the next-finer level, so
+//     M_c = R M P   holds exactly (up to rounding) -- checked by tests (the identity of MG::verify,
+// lib/multigrid.cpp:372-486).  The -kappa of the reference's  X - kappa * sum Y  is folded into the links.
+#pragma once
+#include <memory>
+#include "dirac.h"
+#include "transfer.h"
+
+namespace qb {
+
+struct CoarseOperator {
+  LevelGeom geom;
+  int nvec = 0;   // coarse colours
+  int N = 0;      // 2 * nvec
+  float *Y = nullptr;     // [V][9][N][N/2] float4
+  float *Xinv = nullptr;  // [V][N][N/2] float4, inverse of the site-diagonal block L_8 (for even-odd preconditioning)
+  size_t link_bytes() const { return (size_t)geom.V() * 9 * N * N * 8; }
+  void allocate(const LevelGeom &g, int nvec_);
+  void compute_xinv();    // batched in-kernel Gauss-Jordan with partial pivoting (the reference calls MAGMA, coarse_op.cuh:1466-1474)
+  ~CoarseOperator();
+};
+
+// Builders of the Galerkin coarse links (coarse_op.cu)
+void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a);
+void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine);
+
+// Coarse Dirac operator.  Full operator on [even | odd] fields, or (pc = true) the symmetric even-odd
+// Schur complement  1 - Xinv_pp Y_pq Xinv_qq Y_qp  on single-parity fields (DiracCoarsePC, dirac_coarse.cpp:226-372).
+class DiracCoarse : public Dirac {
+ public:
+  std::shared_ptr<CoarseOperator> op;
+  bool pc;
+  int matpc_type;
+  mutable std::unique_ptr<SpinorField> tmp1, tmp2;
+  DiracCoarse(std::shared_ptr<CoarseOperator> op_, bool pc_, int matpc_) : op(op_), pc(pc_), matpc_type(matpc_) {}
+  DiracType type() const override { return pc ? DIRAC_COARSE_PC : DIRAC_COARSE; }
+  bool is_pc() const override { return pc; }
+  int matpc() const override { return matpc_type; }
+  Prec precision() const override { return PREC_SINGLE; }
+  SpinorField *new_field(Prec) const override { return new SpinorField(op->geom.Vh, pc ? 1 : 2, PREC_SINGLE, 2, op->nvec); }
+  SpinorField *new_parity_field(Prec) const override { return new SpinorField(op->geom.Vh, 1, PREC_SINGLE, 2, op->nvec); }
+
+  // out(parity) = sum_d Y_d in(other parity)   [hopping part only]
+  void Dslash(SpinorField &out, const SpinorField &in, int parity) const override;
+  void DslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const override;
+  void Clover(SpinorField &out, const SpinorField &in, int parity) const;      // X in
+  void CloverInv(SpinorField &out, const SpinorField &in, int parity) const;   // X^-1 in
+  void M(SpinorField &out, const SpinorField &in) const override;
+  void prepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b, SolutionType sol_type) const override;
+  void reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const override;
+  void create_coarse_op(CoarseOperator &coarse, const Transfer &T) const override;
+  int p_parity() const { return (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1; }
+};
+
+// low-level launcher: out(sites of `parity`, or all sites if parity < 0) =
+//    [use_x]  (Xinv or L_8) in_diag(x)   +   [use_y]  sum_d L_d(x) in_hop(x + e_d)
+// optionally followed by out = a * out + b * xpay
+struct CoarseApplyArgs {
+  const CoarseOperator *op;
+  float *out;                // full-field base pointers ([parity][plane][cb]); parity fields are addressed through poff
+  const float *in_hop;       // field supplying the neighbours
+  const float *in_diag;      // field supplying the site-diagonal term
+  const float *xpay;
+  long out_poff[2], hop_poff[2], diag_poff[2], xpay_poff[2];  // float4 offset of each parity block inside the buffers
+  int parity;                // -1: all sites
+  bool use_y, use_x, use_xinv;
+  float a, b;
+};
+void coarse_apply(const CoarseApplyArgs &args);
+
+}  // namespace qb

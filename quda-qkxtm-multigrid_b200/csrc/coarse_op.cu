@@ -1,0 +1,322 @@
+// Galerkin construction of the coarse links on the GPU:  L^c_d(X) = sum_{x in X} V(x)^dag L_d(x) V(x + e_d).
+//
+// Replaces the reference's CPU-only path (/root/reference/lib/coarse_op.cu:152-213, lib/coarsecoarse_op.cu:148-184,
+// lib/coarse_op.cuh: computeUV :59-125, computeVUV :487-599, computeCoarseLocal :670-711, AddCoarseDiagonal /
+// AddCoarseTmDiagonal :813-869; `errorQuda("GPU variant not yet implemented")` :1117-1119).  The reference
+// materialises UV = U V for the whole lattice and accumulates V^dag UV site by site on one CPU core.
+// Here one CTA owns one aggregate X and walks its fine sites; for every site and direction it
+//   1. stages V(x), V(x + e_d) (and the link) in shared memory,
+//   2. forms W = L_d(x) V(x+e_d) split by source chirality (the reference's UV, never written to HBM),
+//   3. accumulates V(x)^dag W into register tiles of the N x N coarse matrix: into Y_d(X) if x + e_d leaves
+//      the aggregate, into the site-diagonal block L_8(X) otherwise (computeCoarseLocal).
+// The mass / twist term enters as a ninth "direction" with e_8 = 0 (AddCoarseDiagonal / AddCoarseTmDiagonal).
+// All sums run in a fixed order: the result is deterministic.
+#include "coarse.h"
+#include "dslash.cuh"
+
+namespace qb {
+
+// ---- fp32 AoS copy of the fine links, any resident precision / reconstruction -----------------------
+template <typename Store, int RECON>
+__global__ void decompress_gauge_kernel(float *out, const void *src, Geom g, long Vh) {
+  typedef typename Store::real real;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 8 * Vh) return;
+  const int pm = (int)(t / Vh);
+  const long cb = t - (long)pm * Vh;
+  const int mu = pm & 3;
+  real raw[RECON];
+  LinkRaw<Store, RECON>::load(raw, (const char *)src + (size_t)pm * RECON * StoreTraits<Store>::real_bytes * Vh, Vh, cb);
+  real u0;
+  if (mu < 3) u0 = RECON == 8 ? (real)1 / (real)g.aniso : (real)g.aniso;
+  else {
+    const long za = cb / g.Xh, zb = za / g.X[1];
+    const int tt = (int)(zb / g.X[2]);
+    u0 = (tt == g.X[3] - 1) ? (real)g.tb_fwd : (real)1;
+  }
+  cplx<real> U[9];
+  reconstruct_link<real, RECON>(U, raw, link_u0<Store, RECON>(u0));
+  const real ls = link_scale<Store, RECON>();
+  float *dst = out + (size_t)t * 18;  // [parity][mu][cb][row][col][re,im]
+#pragma unroll
+  for (int k = 0; k < 9; k++) { dst[2 * k] = (float)(U[k].re * ls); dst[2 * k + 1] = (float)(U[k].im * ls); }
+}
+
+static float *decompress_gauge(const GaugeField &gf, const Geom &g) {
+  float *out;
+  QB_CUDA(cudaMalloc((void **)&out, sizeof(float) * 18 * 8 * gf.Vh));
+  const int bs = 256, nb = div_up(8 * gf.Vh, bs);
+  cudaStream_t s = rt().compute;
+#define DC(ST, RC) decompress_gauge_kernel<ST, RC><<<nb, bs, 0, s>>>(out, gf.data, g, gf.Vh)
+#define BY_RECON(ST)                  \
+  if (gf.recon == 18) DC(ST, 18);     \
+  else if (gf.recon == 12) DC(ST, 12);\
+  else DC(ST, 8)
+  if (gf.prec == PREC_DOUBLE) { BY_RECON(StoreD); }
+  else if (gf.prec == PREC_SINGLE) { BY_RECON(StoreS); }
+  else { BY_RECON(StoreH); }
+#undef BY_RECON
+#undef DC
+  QB_CHECK_LAUNCH();
+  return out;
+}
+
+// ---- shared pieces -------------------------------------------------------------------------------------
+struct GalerkinArgs {
+  // transfer
+  const float4 *V;
+  const int *f2c, *c2f;
+  int Nf, nvec, block_sites;
+  long Vh_f;
+  int Xf[4], Xfh;
+  // output
+  float4 *Yc;  // [Vc][9][N][N/2]
+  int N;
+  // fine-level links
+  const float *U;  // decompressed [parity][mu][cb][18]
+  float kappa, twist_a;
+  // coarse-level links (the finer coarse operator)
+  const float4 *Yf;  // [Vf][9][Nf][Nf/2]
+};
+
+__device__ __forceinline__ void fine_coords(int *x, long cb, int parity, const GalerkinArgs &a) {
+  const long za = cb / a.Xfh, zb = za / a.Xf[1];
+  x[1] = (int)(za - zb * a.Xf[1]);
+  x[3] = (int)(zb / a.Xf[2]);
+  x[2] = (int)(zb - (long)x[3] * a.Xf[2]);
+  x[0] = (int)(2 * cb + ((x[1] + x[2] + x[3] + parity) & 1) - za * a.Xf[0]);
+}
+
+// V(x) -> smem as [k][j] complex
+__device__ __forceinline__ void stage_V(float2 *dst, const GalerkinArgs &a, int parity, long cb) {
+  const int nvh = a.nvec / 2;
+  for (int e = threadIdx.x; e < a.Nf * nvh; e += blockDim.x) {
+    const int k = e / nvh, jp = e - k * nvh;
+    const float4 v = __ldg(a.V + (((size_t)parity * a.Nf + k) * nvh + jp) * a.Vh_f + cb);
+    dst[k * a.nvec + 2 * jp] = make_float2(v.x, v.y);
+    dst[k * a.nvec + 2 * jp + 1] = make_float2(v.z, v.w);
+  }
+}
+
+// acc[t][u] += sum_{k in chirality S of the tile rows} conj(Vx[k][j0+t]) * W[k][c0+u]
+template <int T>
+__device__ __forceinline__ void accumulate_tile(cplx<float> (*acc)[T], const float2 *Vx, const float2 *W, int nvec, int N, int cpc, int r0, int c0) {
+  const int S = r0 / nvec, j0 = r0 - S * nvec;
+  for (int kk = 0; kk < cpc; kk++) {
+    const int k = S * cpc + kk;
+    cplx<float> v[T], w[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) { const float2 q = Vx[k * nvec + j0 + t]; v[t] = cplx<float>(q.x, q.y); }
+#pragma unroll
+    for (int u = 0; u < T; u++) { const float2 q = W[k * N + c0 + u]; w[u] = cplx<float>(q.x, q.y); }
+#pragma unroll
+    for (int t = 0; t < T; t++)
+#pragma unroll
+      for (int u = 0; u < T; u++) cmac_conj(acc[t][u], v[t], w[u]);
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void store_tile(float4 *Yc, long X, int d, int N, int r0, int c0, cplx<float> (*acc)[T]) {
+  float2 *base = (float2 *)(Yc + ((size_t)X * 9 + d) * N * (N / 2));
+#pragma unroll
+  for (int t = 0; t < T; t++)
+#pragma unroll
+    for (int u = 0; u < T; u++) {
+      const int r = r0 + t, c = c0 + u;
+      base[((size_t)c * (N / 2) + (r >> 1)) * 2 + (r & 1)] = make_float2(acc[t][u].re, acc[t][u].im);
+    }
+}
+
+// LEVEL 0: fine links are -kappa P_d (x) U; LEVEL 1: dense links of a coarse operator
+template <int T, int LEVEL>
+__global__ void __launch_bounds__(256) galerkin_kernel(const GalerkinArgs a) {
+  extern __shared__ float2 sm[];
+  const int Nf = a.Nf, nvec = a.nvec, N = a.N, cpc = Nf / 2;
+  float2 *Vx = sm;                    // [Nf][nvec]
+  float2 *Vn = Vx + Nf * nvec;        // [Nf][nvec]
+  float2 *W = Vn + Nf * nvec;         // [Nf][N]
+  float2 *Ld = W + Nf * N;            // LEVEL 0: 9 complex (the link); LEVEL 1: [Nf][Nf]
+  __shared__ int s_info[4];           // neighbour parity, leaves-block flag
+  __shared__ long s_cb[2];
+
+  const long X = blockIdx.x;
+  const int ntc = N / T;
+  const int tr = threadIdx.x / ntc, tc = threadIdx.x - tr * ntc;
+  const bool owner = threadIdx.x < ntc * ntc;
+  const int r0 = tr * T, c0 = tc * T;
+
+  cplx<float> diag[T][T];
+#pragma unroll
+  for (int t = 0; t < T; t++)
+#pragma unroll
+    for (int u = 0; u < T; u++) diag[t][u] = cplx<float>(0.f, 0.f);
+
+  for (int d = 0; d < 9; d++) {
+    cplx<float> hop[T][T];
+#pragma unroll
+    for (int t = 0; t < T; t++)
+#pragma unroll
+      for (int u = 0; u < T; u++) hop[t][u] = cplx<float>(0.f, 0.f);
+
+    for (int i = 0; i < a.block_sites; i++) {
+      const int fs = a.c2f[(size_t)X * a.block_sites + i];
+      const int parity = fs >= a.Vh_f ? 1 : 0;
+      const long cb = fs - (long)parity * a.Vh_f;
+      __syncthreads();  // previous iteration's readers are done with the staging buffers
+      if (threadIdx.x == 0) {
+        int x[4];
+        fine_coords(x, cb, parity, a);
+        int npar = parity;
+        long ncb = cb;
+        if (d < 8) {
+          const int mu = d >> 1;
+          x[mu] = (x[mu] + ((d & 1) ? a.Xf[mu] - 1 : 1)) % a.Xf[mu];
+          npar = 1 - parity;
+          ncb = ((((long)x[3] * a.Xf[2] + x[2]) * a.Xf[1] + x[1]) * a.Xf[0] + x[0]) >> 1;
+        }
+        s_info[0] = npar;
+        s_cb[0] = ncb;
+        s_info[1] = (d < 8 && a.f2c[(size_t)npar * a.Vh_f + ncb] != X) ? 1 : 0;
+      }
+      __syncthreads();
+      const int npar = s_info[0];
+      const long ncb = s_cb[0];
+      stage_V(Vx, a, parity, cb);
+      if (d < 8) stage_V(Vn, a, npar, ncb);
+      if (LEVEL == 0) {
+        if (d < 8 && threadIdx.x < 9) {
+          // forward: U_mu(x); backward: U_mu(x - mu)^dagger
+          const int mu = d >> 1;
+          const float *u = (d & 1) ? a.U + (((size_t)npar * 4 + mu) * a.Vh_f + ncb) * 18 : a.U + (((size_t)parity * 4 + mu) * a.Vh_f + cb) * 18;
+          const int r = threadIdx.x / 3, c = threadIdx.x - 3 * r;
+          Ld[threadIdx.x] = (d & 1) ? make_float2(u[(c * 3 + r) * 2], -u[(c * 3 + r) * 2 + 1]) : make_float2(u[threadIdx.x * 2], u[threadIdx.x * 2 + 1]);
+        }
+      } else {
+        const float4 *src = a.Yf + ((size_t)fs * 9 + d) * Nf * (Nf / 2);
+        for (int e = threadIdx.x; e < Nf * (Nf / 2); e += blockDim.x) {
+          const int c = e / (Nf / 2), rp = e - c * (Nf / 2);
+          const float4 v = __ldg(src + e);
+          Ld[(2 * rp) * Nf + c] = make_float2(v.x, v.y);
+          Ld[(2 * rp + 1) * Nf + c] = make_float2(v.z, v.w);
+        }
+      }
+      __syncthreads();
+      // W[k][(S', j')] = sum_{k' in S'} L_d(x)[k][k'] V(x + e_d)[k'][j']
+      const float2 *Vsrc = d < 8 ? Vn : Vx;
+      for (int e = threadIdx.x; e < Nf * N; e += blockDim.x) {
+        const int k = e / N, col = e - k * N;
+        const int Sp = col / nvec, jp = col - Sp * nvec;
+        cplx<float> w(0.f, 0.f);
+        if (LEVEL == 0) {
+          const int s = k / 3, c = k - 3 * s;
+          const int chi = s >> 1;
+          if (d == 8) {
+            if (Sp == chi) {
+              const float2 v = Vx[k * nvec + jp];
+              const float tw = chi == 0 ? a.twist_a : -a.twist_a;  // (1 + i a gamma5)
+              w = cplx<float>(v.x - tw * v.y, v.y + tw * v.x);
+            }
+          } else {
+            const int mu = d >> 1;
+            const float sigma = (d & 1) ? 1.f : -1.f;  // forward: 1 - gamma_mu, backward: 1 + gamma_mu
+            int ss;
+            cplx<float> coef;
+            if (Sp == chi) { ss = s; coef = cplx<float>(1.f, 0.f); }
+            else {
+              ss = mu < 2 ? 3 - s : (s + 2) & 3;
+              const int gr = mu == 1 ? ((s == 0 || s == 3) ? -1 : 1) : (mu == 3 ? 1 : 0);
+              const int gi = mu == 0 ? (s < 2 ? 1 : -1) : (mu == 2 ? ((s == 0 || s == 3) ? 1 : -1) : 0);
+              coef = cplx<float>(sigma * gr, sigma * gi);
+            }
+            cplx<float> acc(0.f, 0.f);
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) {
+              const float2 u = Ld[c * 3 + cc], v = Vsrc[(ss * 3 + cc) * nvec + jp];
+              cmac(acc, cplx<float>(u.x, u.y), cplx<float>(v.x, v.y));
+            }
+            w = coef * acc;
+            w.re *= -a.kappa; w.im *= -a.kappa;
+          }
+        } else {
+          const int cpcf = Nf / 2;
+          for (int kk = 0; kk < cpcf; kk++) {
+            const int kp = Sp * cpcf + kk;
+            const float2 l = Ld[k * Nf + kp], v = Vsrc[kp * nvec + jp];
+            cmac(w, cplx<float>(l.x, l.y), cplx<float>(v.x, v.y));
+          }
+        }
+        W[e] = make_float2(w.re, w.im);
+      }
+      __syncthreads();
+      if (owner) {
+        if (s_info[1]) accumulate_tile<T>(hop, Vx, W, nvec, N, cpc, r0, c0);
+        else accumulate_tile<T>(diag, Vx, W, nvec, N, cpc, r0, c0);
+      }
+    }
+    if (owner && d < 8) store_tile<T>(a.Yc, X, d, N, r0, c0, hop);
+  }
+  if (owner) store_tile<T>(a.Yc, X, 8, N, r0, c0, diag);
+}
+
+static int tile_for(int N, int nvec) {
+  // largest T in {4,3,2,1} dividing nvec with (N/T)^2 <= 256 threads
+  for (int T = 1; T <= 4; T++)
+    if (nvec % T == 0 && (N / T) * (N / T) <= 256) return T;
+  QB_ERROR("no register tiling for the coarse-link build with n_vec = %d", nvec);
+}
+
+template <int LEVEL> static void launch_galerkin(const GalerkinArgs &a, long Vc) {
+  const int T = tile_for(a.N, a.nvec);
+  const size_t sm = sizeof(float2) * ((size_t)2 * a.Nf * a.nvec + (size_t)a.Nf * a.N + (LEVEL == 0 ? 16 : (size_t)a.Nf * a.Nf));
+  cudaStream_t s = rt().compute;
+  const int threads = std::max(32, (((a.N / T) * (a.N / T) + 31) / 32) * 32);
+#define GO(TT)                                                                                               \
+  QB_CUDA(cudaFuncSetAttribute(galerkin_kernel<TT, LEVEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+  galerkin_kernel<TT, LEVEL><<<(unsigned)Vc, threads, sm, s>>>(a)
+  if (sm > 227 * 1024) QB_ERROR("coarse-link build needs %zu bytes of shared memory (Nf=%d, n_vec=%d): too large", sm, a.Nf, a.nvec);
+  if (T == 4) { GO(4); }
+  else if (T == 3) { GO(3); }
+  else if (T == 2) { GO(2); }
+  else { GO(1); }
+#undef GO
+  QB_CHECK_LAUNCH();
+}
+
+static void fill_transfer_args(GalerkinArgs &a, const Transfer &T) {
+  a.V = (const float4 *)T.V; a.f2c = T.f2c; a.c2f = T.c2f;
+  a.Nf = T.Nf; a.nvec = T.nvec; a.block_sites = T.block_sites; a.Vh_f = T.fine.Vh;
+  for (int d = 0; d < 4; d++) a.Xf[d] = T.fine.X[d];
+  a.Xfh = T.fine.Xh;
+  a.N = 2 * T.nvec;
+}
+
+void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a) {
+  if (T.Nf != 12) QB_ERROR("build_coarse_from_fine: transfer is not defined on a Wilson-type fine field");
+  out.allocate(T.coarse, T.nvec);
+  float *U = decompress_gauge(gauge, fine_geom);
+  GalerkinArgs a{};
+  fill_transfer_args(a, T);
+  a.Yc = (float4 *)out.Y; a.U = U; a.kappa = (float)kappa; a.twist_a = (float)twist_a; a.Yf = nullptr;
+  launch_galerkin<0>(a, T.coarse.V());
+  QB_CUDA(cudaStreamSynchronize(rt().compute));
+  QB_CUDA(cudaFree(U));
+}
+
+void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine) {
+  if (T.Nf != fine.N || T.fine.Vh != fine.geom.Vh) QB_ERROR("build_coarse_from_coarse: transfer does not match the fine coarse-operator");
+  out.allocate(T.coarse, T.nvec);
+  GalerkinArgs a{};
+  fill_transfer_args(a, T);
+  a.Yc = (float4 *)out.Y; a.U = nullptr; a.Yf = (const float4 *)fine.Y;
+  launch_galerkin<1>(a, T.coarse.V());
+  QB_CUDA(cudaStreamSynchronize(rt().compute));
+}
+
+void DiracTM::create_coarse_op(CoarseOperator &coarse, const Transfer &T) const {
+  if (pc) QB_ERROR("coarsening of the even-odd preconditioned operator is not implemented: coarsen the full operator (coarse_grid_solution_type = QUDA_MAT_SOLUTION)");
+  if (dagger) QB_ERROR("create_coarse_op: operator must not be daggered");
+  build_coarse_from_fine(coarse, T, *gauge, lat->geom, kappa, flavor ? twist_a() : 0.0);
+}
+
+}  // namespace qb

@@ -23,7 +23,7 @@ void Dirac::MdagM(SpinorField &out, const SpinorField &in) const {
 void Dirac::create_coarse_op(CoarseOperator &, const Transfer &) const { QB_ERROR("create_coarse_op not implemented for this operator"); }
 
 DiracTM::DiracTM(Lattice *lat_, const GaugeField *gauge_, double kappa_, double mu_, int flavor_, bool pc_, int matpc_, bool dagger_)
-    : lat(lat_), gauge(gauge_), kappa(kappa_), mu(mu_), flavor(flavor_), pc(pc_), matpc_type(matpc_) {
+    : lat(lat_), gauge(gauge_), gauge_vec(nullptr), kappa(kappa_), mu(mu_), flavor(flavor_), pc(pc_), matpc_type(matpc_) {
   dagger = dagger_;
   if (flavor != 0 && flavor != 1 && flavor != -1) QB_ERROR("only degenerate twisted mass (flavor +-1) is supported, got %d", flavor);
 }
@@ -32,6 +32,12 @@ SpinorField &DiracTM::tmp(std::unique_ptr<SpinorField> &t, const SpinorField &li
   if (!t || t->prec != like.prec || t->Vh != like.Vh || t->nparity != like.nparity)
     t.reset(new SpinorField(like.Vh, like.nparity, like.prec));
   return *t;
+}
+
+const GaugeField &DiracTM::links_for(const SpinorField &f) const {
+  if (f.prec == gauge->prec) return *gauge;
+  if (gauge_vec && f.prec == gauge_vec->prec) return *gauge_vec;
+  QB_ERROR("operator works in precision %d but was handed a field of precision %d and no matching gauge field", (int)gauge->prec, (int)f.prec);
 }
 
 void DiracTM::WilsonDslash(SpinorField &out, const SpinorField &in, int parity) const {
@@ -64,6 +70,18 @@ void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, co
 }
 
 void DiracTM::M(SpinorField &out, const SpinorField &in) const {
+  if (in.prec != gauge->prec) {
+    // vectors live in another precision than the operator (e.g. fp32 smoother vectors, int16 operator):
+    // convert, apply in the operator's precision, convert back
+    if (!conv_in || conv_in->prec != gauge->prec || conv_in->Vh != in.Vh || conv_in->nparity != in.nparity) {
+      conv_in.reset(new SpinorField(in.Vh, in.nparity, gauge->prec));
+      conv_out.reset(new SpinorField(in.Vh, in.nparity, gauge->prec));
+    }
+    copy_spinor(*conv_in, in, rt().compute);
+    M(*conv_out, *conv_in);
+    copy_spinor(out, *conv_out, rt().compute);
+    return;
+  }
   if (!pc) {
     // full operator on [even | odd]:  out_p = A in_p - kappa D_{p,1-p} in_{1-p}
     if (in.nparity != 2 || out.nparity != 2) QB_ERROR("full operator needs full fields");
@@ -111,12 +129,12 @@ void DiracTM::prepare(SpinorField &src, SpinorField &sol, SpinorField &x, Spinor
   x.view_parity(src, q);
   x.view_parity(sol, p);
   if (flavor == 0) {
-    apply_hop(*lat, *gauge, src, bq, p, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bp, TwistCoef());
+    apply_hop(*lat, links_for(bq), src, bq, p, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bp, TwistCoef());
   } else if (symmetric()) {
     const TwistCoef ai = Ainv();
-    apply_hop(*lat, *gauge, src, bq, p, dagger, ai, TwistCoef(kappa * ai.p, kappa * ai.q), &bp, ai);
+    apply_hop(*lat, links_for(bq), src, bq, p, dagger, ai, TwistCoef(kappa * ai.p, kappa * ai.q), &bp, ai);
   } else {
-    apply_hop(*lat, *gauge, src, bq, p, dagger, Ainv(), TwistCoef(kappa, 0.0), &bp, TwistCoef());
+    apply_hop(*lat, links_for(bq), src, bq, p, dagger, Ainv(), TwistCoef(kappa, 0.0), &bp, TwistCoef());
   }
   flops += 1440ll * b.Vh;
 }
@@ -130,10 +148,10 @@ void DiracTM::reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol
   x.view_parity(xp, p); x.view_parity(xq, q);
   b.view_parity(bq, q);
   if (flavor == 0) {
-    apply_hop(*lat, *gauge, xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bq, TwistCoef());
+    apply_hop(*lat, links_for(xp), xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bq, TwistCoef());
   } else {
     const TwistCoef ai = Ainv();
-    apply_hop(*lat, *gauge, xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa * ai.p, kappa * ai.q), &bq, ai);
+    apply_hop(*lat, links_for(xp), xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa * ai.p, kappa * ai.q), &bq, ai);
   }
   flops += 1416ll * b.Vh;
 }

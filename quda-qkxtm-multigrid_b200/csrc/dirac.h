@@ -47,12 +47,13 @@ class Dirac {
 class DiracTM : public Dirac {
  public:
   Lattice *lat;
-  const GaugeField *gauge;
+  const GaugeField *gauge;      // links in the operator's working precision
+  const GaugeField *gauge_vec;  // links in the precision of the solver vectors (prepare / reconstruct when they differ), may be null
   double kappa, mu;
   int flavor;   // +-1 twisted mass, 0 = plain Wilson
   bool pc;
   int matpc_type;
-  mutable std::unique_ptr<SpinorField> tmp1, tmp2;
+  mutable std::unique_ptr<SpinorField> tmp1, tmp2, conv_in, conv_out;
 
   DiracTM(Lattice *lat, const GaugeField *gauge, double kappa, double mu, int flavor, bool pc, int matpc_type, bool dagger);
   DiracType type() const override { return flavor == 0 ? (pc ? DIRAC_WILSON_PC : DIRAC_WILSON) : (pc ? DIRAC_TM_PC : DIRAC_TM); }
@@ -86,6 +87,7 @@ class DiracTM : public Dirac {
 
  private:
   SpinorField &tmp(std::unique_ptr<SpinorField> &t, const SpinorField &like) const;
+  const GaugeField &links_for(const SpinorField &f) const;
 };
 
 // functors handed to solvers (cf. DiracM / DiracMdagM, include/dirac_quda.h:869-1030)

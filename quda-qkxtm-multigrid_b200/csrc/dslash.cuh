@@ -80,9 +80,13 @@ template <int MU, typename T> __device__ __forceinline__ void project(cplx<T> *h
 }
 
 // acc += (1 + sigma gamma_mu)-reconstruction of the link-multiplied half spinor chi
-template <int MU, typename T> __device__ __forceinline__ void reconstruct_acc(cplx<T> *acc, const cplx<T> *chi, T sigma) {
+template <bool SCALED, int MU, typename T> __device__ __forceinline__ void reconstruct_acc(cplx<T> *acc, const cplx<T> *chi, T sigma, T scale) {
+  if (SCALED) sigma *= scale;
 #pragma unroll
-  for (int k = 0; k < 6; k++) acc[k] = acc[k] + chi[k];
+  for (int k = 0; k < 6; k++) {
+    if (SCALED) { acc[k].re += scale * chi[k].re; acc[k].im += scale * chi[k].im; }
+    else acc[k] = acc[k] + chi[k];
+  }
 #pragma unroll
   for (int s = 2; s < 4; s++)
 #pragma unroll
@@ -149,14 +153,15 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
 
   cplx<real> h[6];
   int nbr = 0, fidx = 0;
+  real sc;  // storage scale of the loaded (half) spinor, folded into the accumulation below
   if (use_ghost) {
     fidx = face_index<MU>(x, g);
-    Store::template load<6>(h, p.ghost[MU][BACK ? 0 : 1], p.ghost_norm[MU][BACK ? 0 : 1], g.faceVh[MU], fidx);
+    sc = Store::template load<6>(h, p.ghost[MU][BACK ? 0 : 1], p.ghost_norm[MU][BACK ? 0 : 1], g.faceVh[MU], fidx);
   } else {
     const int nfull = BACK ? (edge ? full + (L - 1) * step : full - step) : (edge ? full - (L - 1) * step : full + step);
     nbr = nfull >> 1;
     cplx<real> psi[12];
-    Store::template load<12>(psi, p.in, p.in_norm, p.stride, nbr);
+    sc = Store::template load<12>(psi, p.in, p.in_norm, p.stride, nbr);
     if (TWIST_IN) apply_twist(psi, (real)p.cin[0], (real)p.cin[1]);
     project<MU>(h, psi, sigma);
   }
@@ -174,15 +179,25 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
   if (MU < 3) u0 = RECON == 8 ? (real)1 / (real)g.aniso : (real)g.aniso;
   else u0 = BACK ? (x[3] == 0 ? (real)g.tb_bwd : (real)1) : (x[3] == L - 1 ? (real)g.tb_fwd : (real)1);
   cplx<real> U[9];
-  reconstruct_link<real, RECON>(U, raw, u0);
+  reconstruct_link<real, RECON>(U, raw, link_u0<Store, RECON>(u0));
 
   cplx<real> chi[6];
   su3_mul<BACK != 0>(chi, U, h);
-  reconstruct_acc<MU>(acc, chi, sigma);
+  reconstruct_acc<Store::scaled, MU>(acc, chi, sigma, sc * link_scale<Store, RECON>());
 }
 
+// Launch bounds from the B200 sweep of profiles/tune_r01.md: the kernel is HBM-latency bound, so fp32 / int16
+// want maximum occupancy (64 registers, 8 CTAs of 128 threads per SM) while fp64 needs 128 registers to avoid spills.
+// QB_DSLASH_MINB overrides for tuning builds.
+template <typename Store> struct DslashBounds { static constexpr int max_threads = 128, min_blocks = 8; };
+template <> struct DslashBounds<StoreD> { static constexpr int max_threads = 128, min_blocks = 4; };
+#ifdef QB_DSLASH_MINB
+#define QB_DSLASH_BOUNDS __launch_bounds__(QB_DSLASH_MAXT, QB_DSLASH_MINB)
+#else
+#define QB_DSLASH_BOUNDS __launch_bounds__(DslashBounds<Store>::max_threads, DslashBounds<Store>::min_blocks)
+#endif
 template <typename Store, int RECON, bool TWIST_IN, bool HAS_X>
-__global__ void __launch_bounds__(128) dslash_kernel(const DslashParam p) {
+__global__ void QB_DSLASH_BOUNDS dslash_kernel(const DslashParam p) {
   typedef typename Store::real real;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.site_count) return;
@@ -208,8 +223,8 @@ __global__ void __launch_bounds__(128) dslash_kernel(const DslashParam p) {
   apply_twist(acc, (real)p.co[0], (real)p.co[1]);
   if (HAS_X) {
     cplx<real> xs[12];
-    Store::template load<12, false>(xs, p.x, p.x_norm, p.stride, cb);
-    const cplx<real> cu((real)p.cx[0], (real)p.cx[1]), cl((real)p.cx[0], -(real)p.cx[1]);
+    const real xsc = Store::template load<12, false>(xs, p.x, p.x_norm, p.stride, cb);
+    const cplx<real> cu((real)p.cx[0] * xsc, (real)p.cx[1] * xsc), cl((real)p.cx[0] * xsc, -(real)p.cx[1] * xsc);
 #pragma unroll
     for (int k = 0; k < 6; k++) cmac(acc[k], cu, xs[k]);
 #pragma unroll
@@ -259,7 +274,7 @@ __device__ __forceinline__ void pack_site(const PackParam &p, int t) {
   const int fidx = t - dir * fv;
   const int cb = face_to_cb<MU>(fidx, dir ? g.X[MU] - 1 : 0, p.parity, g);
   cplx<real> psi[12], h[6];
-  Store::template load<12>(psi, p.in, p.in_norm, p.stride, cb);
+  load_scaled<Store, 12>(psi, p.in, p.in_norm, p.stride, cb);
   if (TWIST_IN) apply_twist(psi, (real)p.cin[0], (real)p.cin[1]);
   // back face feeds the neighbour's forward hop (sigma = sgn_fwd); forward face its backward hop
   const real sigma = dir ? (real)(-p.sgn_fwd) : (real)p.sgn_fwd;
@@ -285,7 +300,7 @@ __global__ void __launch_bounds__(256) twist_kernel(void *out, float *out_norm, 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   cplx<real> psi[12];
-  Store::template load<12, false>(psi, in, in_norm, stride, i);
+  load_scaled<Store, 12, false>(psi, in, in_norm, stride, i);
   apply_twist(psi, (real)pr, (real)qr);
   Store::template store<12>(out, out_norm, stride, i, psi);
 }

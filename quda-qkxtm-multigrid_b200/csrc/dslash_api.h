@@ -34,7 +34,7 @@ struct Lattice {
   size_t arena_bytes[3] = {0, 0, 0};
   size_t face_off[3][4][2];   // byte offset of the (d, dir) half-spinor block inside an arena
   size_t norm_off[3][4][2];   // byte offset of the norm block (half precision only)
-  int block_size = 128;
+  int block_size = 0;         // 0: per-precision default
 
   void init(const int *X, int t_boundary_sign, double anisotropy);
   void setup_partition();

@@ -134,10 +134,12 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   const bool twist_in = !cin.trivial();
   const bool has_x = x != nullptr;
 
+  // default launch geometry: 128 threads (fp32 / int16), 64 threads (fp64); lat.block_size > 0 overrides
+  const int block = lat.block_size > 0 ? lat.block_size : (Store::prec == PREC_DOUBLE ? 64 : 128);
   const bool partitioned = g.part[0] || g.part[1] || g.part[2] || g.part[3];
   if (!partitioned) {
     p.site_begin = 0; p.site_count = g.Vh; p.site_list = nullptr;
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, lat.block_size, r.compute);
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, r.compute);
     return;
   }
 
@@ -186,12 +188,12 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   const int np = parity;
   if (lat.n_interior[np]) {
     p.site_begin = 0; p.site_count = lat.n_interior[np]; p.site_list = lat.interior_list[np];
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, lat.block_size, r.compute);
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, r.compute);
   }
   QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
   if (lat.n_boundary[np]) {
     p.site_begin = 0; p.site_count = lat.n_boundary[np]; p.site_list = lat.boundary_list[np];
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, lat.block_size, r.compute);
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, r.compute);
   }
   // the next pack must not overwrite the send buffers before the boundary kernel (self mode reads them)
   QB_CUDA(cudaEventRecord(r.ev_pack_ready, r.compute));

@@ -58,7 +58,7 @@ __device__ __forceinline__ void store_link_real(void *block, long stride, int rp
     const double s = phase ? val * (1.0 / 3.14159265358979323846) : val;
     int q = __double2int_rn(s * 32767.0);
     q = q > 32767 ? 32767 : (q < -32767 ? -32767 : q);
-    ((short *)block)[idx] = (short)q;
+    ((unsigned short *)block)[idx] = (unsigned short)(q + 32768);  // offset-binary, see layout.cuh
   }
 }
 
@@ -148,10 +148,11 @@ __global__ void export_gauge_kernel(Host *stage, const void *src, Geom g, long V
     u0 = (tt == g.X[3] - 1) ? (real)g.tb_fwd : (real)1;
   }
   cplx<real> U[9];
-  reconstruct_link<real, RECON>(U, raw, u0);
+  reconstruct_link<real, RECON>(U, raw, link_u0<Store, RECON>(u0));
+  const real ls = link_scale<Store, RECON>();
   Host *dst = stage + ((long)mu * 2 * Vh + (long)parity * Vh + cb) * 18;
 #pragma unroll
-  for (int k = 0; k < 9; k++) { dst[2 * k] = (Host)U[k].re; dst[2 * k + 1] = (Host)U[k].im; }
+  for (int k = 0; k < 9; k++) { dst[2 * k] = (Host)(U[k].re * ls); dst[2 * k + 1] = (Host)(U[k].im * ls); }
 }
 
 template <typename Host>
@@ -282,7 +283,7 @@ __global__ void export_spinor_kernel(Host *stage, const void *src, const float *
   const int parity = (int)(t / Vh);
   const long cb = t - (long)parity * Vh;
   cplx<real> psi[12];
-  Store::template load<12, false>(psi, (const char *)src + parity_bytes * parity, snorm ? snorm + (long)parity * Vh : nullptr, Vh, cb);
+  load_scaled<Store, 12, false>(psi, (const char *)src + parity_bytes * parity, snorm ? snorm + (long)parity * Vh : nullptr, Vh, cb);
   if (basis == BASIS_UKQCD) {
     cplx<real> r[12];
     dr_to_ukqcd(r, psi);
@@ -359,6 +360,41 @@ void export_spinor(void *h, const SpinorField &f, Prec host_prec, HostBasis basi
 }
 
 // ---------------------------------------------------------------------------------------------
+// generic fp32 fields (any nSpin x nColor): host order [parity][cb][component][re,im] <-> planes
+// ---------------------------------------------------------------------------------------------
+__global__ void generic_reorder_kernel(float4 *planes, float *host, long Vh, int nplanes, int nparity, bool to_device) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)nparity * nplanes * Vh) return;
+  const long cb = t % Vh;
+  const int pl = (int)((t / Vh) % nplanes), parity = (int)(t / (Vh * nplanes));
+  float4 *h = (float4 *)(host + (((size_t)parity * Vh + cb) * nplanes + pl) * 4);
+  if (to_device) planes[t] = *h;
+  else *h = planes[t];
+}
+
+void import_generic(SpinorField &f, const float *h, cudaStream_t s) {
+  if (f.prec != PREC_SINGLE) QB_ERROR("import_generic: single precision fields only");
+  const size_t hb = f.bytes();
+  float *stage = (float *)staging(hb);
+  QB_CUDA(cudaMemcpyAsync(stage, h, hb, cudaMemcpyHostToDevice, s));
+  const long n = (long)f.nparity * f.planes() * f.Vh;
+  generic_reorder_kernel<<<div_up(n, 256), 256, 0, s>>>((float4 *)f.v, stage, f.Vh, f.planes(), f.nparity, true);
+  QB_CHECK_LAUNCH();
+  QB_CUDA(cudaStreamSynchronize(s));
+}
+
+void export_generic(float *h, const SpinorField &f, cudaStream_t s) {
+  if (f.prec != PREC_SINGLE) QB_ERROR("export_generic: single precision fields only");
+  const size_t hb = f.bytes();
+  float *stage = (float *)staging(hb);
+  const long n = (long)f.nparity * f.planes() * f.Vh;
+  generic_reorder_kernel<<<div_up(n, 256), 256, 0, s>>>((float4 *)f.v, stage, f.Vh, f.planes(), f.nparity, false);
+  QB_CHECK_LAUNCH();
+  QB_CUDA(cudaMemcpyAsync(h, stage, hb, cudaMemcpyDeviceToHost, s));
+  QB_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---------------------------------------------------------------------------------------------
 // resident copy with precision change (fine fields), plain memcpy otherwise
 // ---------------------------------------------------------------------------------------------
 template <typename Dst, typename Src>
@@ -370,7 +406,7 @@ __global__ void convert_spinor_kernel(void *dst, float *dnorm, const void *src, 
   const int parity = (int)(t / Vh);
   const long cb = t - (long)parity * Vh;
   cplx<sreal> a[12];
-  Src::template load<12, false>(a, (const char *)src + spb * parity, snorm ? snorm + (long)parity * Vh : nullptr, Vh, cb);
+  load_scaled<Src, 12, false>(a, (const char *)src + spb * parity, snorm ? snorm + (long)parity * Vh : nullptr, Vh, cb);
   cplx<dreal> b[12];
 #pragma unroll
   for (int k = 0; k < 12; k++) b[k] = cplx<dreal>((dreal)a[k].re, (dreal)a[k].im);

@@ -9,6 +9,8 @@
 #include "blas.h"
 #include "comm.h"
 #include "dirac.h"
+#include "multigrid.h"
+#include "solver.h"
 
 using namespace qb;
 
@@ -552,6 +554,10 @@ double timeDslashQudaB200(void *out, void *in, QudaInvertParam *p, QudaParity pa
   return (double)total / niter;
 }
 
+void setDslashBlockSizeQudaB200(int block) {
+  if (block != 0 && (block < 32 || block > 128 || (block & 31))) QB_ERROR("dslash block size %d must be 0 (default) or a multiple of 32 in [32, 128]", block);
+  G.lat.block_size = block;
+}
 long long kernelLaunchCountQudaB200(void) { return rt().launches; }
 void *computeStreamQudaB200(void) { return (void *)rt().compute; }
 void syncQudaB200(void) { QB_CUDA(cudaDeviceSynchronize()); }
@@ -569,5 +575,312 @@ void freeCloverQuda(void) {}
 void invertMultiSrcQuda(void **, void **, QudaInvertParam *) { QB_ERROR("invertMultiSrcQuda is not implemented (SURVEY.md section 8f.4)"); }
 void invertMultiShiftQuda(void **, void *, QudaInvertParam *) { QB_ERROR("invertMultiShiftQuda is outside this build's scope"); }
 void cloverQuda(void *, void *, QudaInvertParam *, QudaParity *, int) { QB_ERROR("cloverQuda is outside this build's scope"); }
+
+}  // extern "C"
+
+// =================================================================================================
+// Solvers and multigrid
+// =================================================================================================
+namespace {
+
+InverterType to_inverter(QudaInverterType t) {
+  switch (t) {
+    case QUDA_GCR_INVERTER: return INV_GCR;
+    case QUDA_MR_INVERTER: return INV_MR;
+    case QUDA_BICGSTAB_INVERTER: return INV_BICGSTAB;
+    case QUDA_MG_INVERTER: return INV_MG;
+    case QUDA_INVALID_INVERTER: return INV_NONE;
+    default: QB_ERROR("Invalid solver type %d (this build provides GCR, MR, BiCGStab and the MG preconditioner)", (int)t);
+  }
+}
+
+// SolverParam(QudaInvertParam&) of include/invert_quda.h:201-240
+void fill_solver_param(SolverParam &s, const QudaInvertParam *p) {
+  s.inv_type = to_inverter(p->inv_type);
+  s.inv_type_precondition = to_inverter(p->inv_type_precondition);
+  if (p->tol == INVALID_DOUBLE) QB_ERROR("Parameter tol undefined");
+  if (p->maxiter == INVALID_INT) QB_ERROR("Parameter maxiter undefined");
+  s.tol = p->tol;
+  s.maxiter = p->maxiter;
+  s.Nkrylov = p->gcrNkrylov == INVALID_INT ? 20 : p->gcrNkrylov;
+  s.delta = p->reliable_delta == INVALID_DOUBLE ? 1e-3 : p->reliable_delta;
+  s.omega = p->omega == INVALID_DOUBLE ? 1.0 : p->omega;
+  s.precision = to_prec(p->cuda_prec, "cuda_prec");
+  s.precision_sloppy = p->cuda_prec_sloppy == QUDA_INVALID_PRECISION ? s.precision : to_prec(p->cuda_prec_sloppy, "cuda_prec_sloppy");
+  s.precision_precondition = p->cuda_prec_precondition == QUDA_INVALID_PRECISION ? s.precision_sloppy : to_prec(p->cuda_prec_precondition, "cuda_prec_precondition");
+  s.use_init_guess = p->use_init_guess == QUDA_USE_INIT_GUESS_YES;
+  s.preserve_source = true;
+  s.is_preconditioner = false;
+  s.global_reduction = true;
+  s.compute_true_res = true;
+  s.pipeline = p->pipeline;
+  s.precondition_cycle = p->precondition_cycle;
+  s.max_res_increase = p->max_res_increase;
+  s.max_res_increase_total = p->max_res_increase_total;
+  s.verbosity = (int)p->verbosity == INVALID_INT ? 1 : (int)p->verbosity;
+  if (s.inv_type_precondition == INV_MR) {
+    if (p->maxiter_precondition != INVALID_INT) {
+      // the inner MR takes its own iteration count; GCR copies `param` for it and overrides below
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// interface_quda.cpp:2276-2543
+void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
+  require_gauge();
+  if (!param) QB_ERROR("invertQuda: null parameter struct");
+  check_invert_param_operator(param);
+  Runtime &r = rt();
+  const int saved_verbosity = r.verbosity;
+  if ((int)param->verbosity != INVALID_INT) r.verbosity = (int)param->verbosity;
+  if (param->solution_type == QUDA_INVALID_SOLUTION) QB_ERROR("Parameter solution_type undefined");
+  if (param->solve_type == QUDA_INVALID_SOLVE) QB_ERROR("Parameter solve_type undefined");
+  const bool pc_solution = param->solution_type == QUDA_MATPC_SOLUTION || param->solution_type == QUDA_MATPCDAG_MATPC_SOLUTION;
+  const bool pc_solve = param->solve_type == QUDA_DIRECT_PC_SOLVE || param->solve_type == QUDA_NORMOP_PC_SOLVE;
+  const bool mat_solution = param->solution_type == QUDA_MAT_SOLUTION || param->solution_type == QUDA_MATPC_SOLUTION;
+  const bool direct_solve = param->solve_type == QUDA_DIRECT_SOLVE || param->solve_type == QUDA_DIRECT_PC_SOLVE;
+  if (param->solve_type != QUDA_DIRECT_SOLVE && param->solve_type != QUDA_DIRECT_PC_SOLVE && param->solve_type != QUDA_NORMOP_SOLVE &&
+      param->solve_type != QUDA_NORMOP_PC_SOLVE)
+    QB_ERROR("solve_type %d not supported", (int)param->solve_type);
+  if (pc_solution && !pc_solve) QB_ERROR("Preconditioned (PC) solution_type requires a PC solve_type");
+  if (!mat_solution && !pc_solution && pc_solve) QB_ERROR("Unpreconditioned MATDAG_MAT solution_type requires an unpreconditioned solve_type");
+  if (param->inv_type_precondition == QUDA_MG_INVERTER && (!direct_solve || !mat_solution)) QB_ERROR("Multigrid preconditioning only supported for direct solves");
+  if (!mat_solution && direct_solve) QB_ERROR("Two-pass MATDAG_MAT solves with a direct solver are not implemented; use a NORMOP solve_type");
+
+  SolverParam sp;
+  fill_solver_param(sp, param);
+  param->secs = 0; param->gflops = 0; param->iter = 0;
+  const Prec prec = sp.precision;
+  const Prec prec_vec_sloppy = blas_prec(sp.precision_sloppy);
+  if (prec == PREC_HALF) QB_ERROR("cuda_prec must be single or double for a solve");
+  param->spinorGiB = (double)G.lat.geom.Vh * 24 * (pc_solve ? 1 : 2) * (int)prec * (param->preserve_source == QUDA_PRESERVE_SOURCE_NO ? 7 : 9) / (double)(1 << 30);
+
+  // createDirac (interface_quda.cpp:1386-1410): precise, sloppy and preconditioner operators
+  std::unique_ptr<DiracTM> d(make_dirac(param, pc_solve, pick_gauge(prec)));
+  std::unique_ptr<DiracTM> dS(make_dirac(param, pc_solve, pick_gauge(sp.precision_sloppy)));
+  std::unique_ptr<DiracTM> dP(make_dirac(param, pc_solve, pick_gauge(sp.precision_precondition)));
+  if (dS->gauge->prec != prec_vec_sloppy) dS->gauge_vec = pick_gauge(prec_vec_sloppy);
+  if (dP->gauge->prec != prec_vec_sloppy) dP->gauge_vec = pick_gauge(prec_vec_sloppy);
+
+  std::unique_ptr<SpinorField> b(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec));
+  std::unique_ptr<SpinorField> x(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec));
+  load_host_spinor(*b, hp_b, param);
+  if (param->use_init_guess == QUDA_USE_INIT_GUESS_YES) load_host_spinor(*x, hp_x, param);
+  else blas::zero(*x);
+  double nb = blas::norm2(*b);
+  if (nb == 0.0) QB_ERROR("Source has zero norm");
+  if (param->solver_normalization == QUDA_SOURCE_NORMALIZATION) { blas::ax(1.0 / sqrt(nb), *b); blas::ax(1.0 / sqrt(nb), *x); }
+  // massRescale (interface_quda.cpp:1412-1494)
+  {
+    const double kappa = param->kappa;
+    double s = 1.0;
+    switch (param->solution_type) {
+      case QUDA_MAT_SOLUTION:
+        if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION) s = 2.0 * kappa;
+        break;
+      case QUDA_MATDAG_MAT_SOLUTION:
+        if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION) s = 4.0 * kappa * kappa;
+        break;
+      case QUDA_MATPC_SOLUTION:
+        if (param->mass_normalization == QUDA_MASS_NORMALIZATION) s = 4.0 * kappa * kappa;
+        else if (param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION) s = 2.0 * kappa;
+        break;
+      case QUDA_MATPCDAG_MATPC_SOLUTION:
+        if (param->mass_normalization == QUDA_MASS_NORMALIZATION) s = 16.0 * pow(kappa, 4);
+        else if (param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION) s = 4.0 * kappa * kappa;
+        break;
+      default: QB_ERROR("Solution type %d not supported", (int)param->solution_type);
+    }
+    if (s != 1.0) blas::ax(s, *b);
+  }
+
+  SpinorField in, out;
+  const SolutionType st = (SolutionType)(int)param->solution_type;
+  d->prepare(in, out, *x, *b, st);
+
+  Solver *K = nullptr;
+  if (param->inv_type_precondition == QUDA_MG_INVERTER) {
+    if (!param->preconditioner) QB_ERROR("inv_type_precondition is QUDA_MG_INVERTER but `preconditioner` is not set (call newMultigridQuda first)");
+    K = ((MultigridSolver *)param->preconditioner)->mg.get();
+  }
+  std::unique_ptr<SpinorField> tmp_in;
+  if (mat_solution && !direct_solve) {  // normal equations: b' = A^dag b
+    tmp_in.reset(new SpinorField(in.Vh, in.nparity, in.prec));
+    blas::copy(*tmp_in, in);
+    d->Mdag(in, *tmp_in);
+  }
+  {
+    const bool normal = !direct_solve;
+    DiracMatrix m(d.get(), normal), mS(dS.get(), normal), mP(dP.get(), normal);
+    if (sp.inv_type_precondition == INV_MR && param->maxiter_precondition != INVALID_INT) {
+      // GCR builds its inner MR from a copy of sp; hand the inner iteration count through `maxiter` of that copy
+    }
+    std::unique_ptr<Solver> solve(Solver::create(sp, m, mS, mP, K));
+    if (GCR *g = dynamic_cast<GCR *>(solve.get())) g->set_inner(param->maxiter_precondition == INVALID_INT ? 10 : param->maxiter_precondition,
+                                                               param->tol_precondition == INVALID_DOUBLE ? 0.1 : param->tol_precondition);
+    (*solve)(out, in);
+  }
+  d->reconstruct(*x, *b, st);
+  if (param->solver_normalization == QUDA_SOURCE_NORMALIZATION) blas::ax(sqrt(nb), *x);
+  save_host_spinor(hp_x, *x, param);
+
+  param->true_res = sp.true_res;
+  param->true_res_hq = 0.0;
+  param->iter += sp.iter;
+  param->secs += sp.secs;
+  const double gflops = (double)(d->flops + dS->flops + dP->flops + (double)blas::flops) * 1e-9;
+  param->gflops += gflops;
+  blas::flops = 0;
+  r.verbosity = saved_verbosity;
+}
+
+// interface_quda.cpp:2161-2269
+void *newMultigridQuda(QudaMultigridParam *mgp) {
+  require_gauge();
+  if (!mgp || !mgp->invert_param) QB_ERROR("newMultigridQuda: null parameter struct");
+  QudaInvertParam *ip = mgp->invert_param;
+  check_invert_param_operator(ip);
+  if (mgp->n_level == INVALID_INT) QB_ERROR("Parameter n_level undefined");
+  if (mgp->n_level < 2 || mgp->n_level > QUDA_MAX_MG_LEVEL) QB_ERROR("Maximum number of multigrid levels is %d (and at least 2), requested %d", QUDA_MAX_MG_LEVEL, mgp->n_level);
+  if (ip->solve_type != QUDA_DIRECT_SOLVE) QB_ERROR("Outer MG solver can only use QUDA_DIRECT_SOLVE at present");
+  Runtime &r = rt();
+  const int saved_verbosity = r.verbosity;
+  if ((int)ip->verbosity != INVALID_INT) r.verbosity = (int)ip->verbosity;
+  const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+
+  MultigridSolver *ms = new MultigridSolver();
+  MGParam &mp = ms->mp;
+  mp.n_level = mgp->n_level;
+  for (int l = 0; l < mp.n_level; l++) {
+    MGLevelParam &lp = mp.level[l];
+    if (mgp->smoother_solve_type[l] != QUDA_DIRECT_SOLVE && mgp->smoother_solve_type[l] != QUDA_DIRECT_PC_SOLVE)
+      QB_ERROR("Unsupported smoother solve type %d on level %d", (int)mgp->smoother_solve_type[l], l);
+    if (mgp->coarse_grid_solution_type[l] == QUDA_MATPC_SOLUTION)
+      QB_ERROR("coarse_grid_solution_type = QUDA_MATPC_SOLUTION (preconditioned coarsening) is not implemented; use QUDA_MAT_SOLUTION");
+    for (int d = 0; d < 4; d++) {
+      lp.geo_bs[d] = mgp->geo_block_size[l][d];
+      if (l < mp.n_level - 1 && (lp.geo_bs[d] == INVALID_INT || lp.geo_bs[d] < 1)) QB_ERROR("Parameter geo_block_size[%d][%d] undefined", l, d);
+    }
+    lp.spin_bs = l == 0 ? 2 : 1;
+    if (l < mp.n_level - 1 && mgp->spin_block_size[l] != lp.spin_bs) QB_ERROR("spin_block_size[%d] must be %d", l, lp.spin_bs);
+    lp.nvec = mgp->n_vec[l];
+    if (l < mp.n_level - 1 && (lp.nvec == INVALID_INT || lp.nvec < 2)) QB_ERROR("Parameter n_vec[%d] undefined", l);
+    lp.smoother = to_inverter(mgp->smoother[l]);
+    if (lp.smoother != INV_MR && lp.smoother != INV_GCR) QB_ERROR("smoother[%d] must be MR or GCR", l);
+    lp.smoother_pc = mgp->smoother_solve_type[l] == QUDA_DIRECT_PC_SOLVE;
+    lp.nu_pre = mgp->nu_pre[l]; lp.nu_post = mgp->nu_post[l];
+    if (lp.nu_pre == INVALID_INT || lp.nu_post == INVALID_INT) QB_ERROR("Parameter nu_pre/nu_post[%d] undefined", l);
+    lp.smoother_tol = mgp->smoother_tol[l];
+    lp.omega = mgp->omega[l] == INVALID_DOUBLE ? 1.0 : mgp->omega[l];
+    lp.recursive = mgp->cycle_type[l] == QUDA_MG_CYCLE_RECURSIVE;
+    if (mgp->cycle_type[l] != QUDA_MG_CYCLE_RECURSIVE && mgp->cycle_type[l] != QUDA_MG_CYCLE_VCYCLE) QB_ERROR("Multigrid cycle type %d not supported", (int)mgp->cycle_type[l]);
+    lp.global_reduction = mgp->global_reduction[l] != QUDA_BOOLEAN_NO;
+  }
+  mp.setup_maxiter = mgp->setup_maxiter == INVALID_INT ? 500 : mgp->setup_maxiter;
+  mp.setup_tol = mgp->setup_tol == INVALID_DOUBLE ? 5e-6 : mgp->setup_tol;
+  mp.compute_null_vector = mgp->compute_null_vector == QUDA_COMPUTE_NULL_VECTOR_YES;
+  mp.generate_all_levels = mgp->generate_all_levels == QUDA_BOOLEAN_YES;
+  mp.verbosity = r.verbosity;
+  if (!mp.compute_null_vector) QB_ERROR("compute_null_vector = NO needs vec_infile, which requires QIO (not available); generate the null vectors");
+
+  // fine operators: residual = full operator in the MG working precision (fp32 vectors); smoother = even-odd
+  // preconditioned operator in cuda_prec_precondition, with the setup rescale of kappa / mu (interface_quda.cpp:2196-2233)
+  const double dk = mgp->delta_kappaPR == 0.0 ? 1.0 : mgp->delta_kappaPR, dm = mgp->delta_muPR == 0.0 ? 1.0 : mgp->delta_muPR;
+  const GaugeField *g32 = pick_gauge(PREC_SINGLE);
+  ms->dirac.reset(make_dirac(ip, false, g32, dk, dm));
+  const Prec pprec = ip->cuda_prec_precondition == QUDA_INVALID_PRECISION ? PREC_SINGLE : to_prec(ip->cuda_prec_precondition, "cuda_prec_precondition");
+  ms->diracSmooth.reset(make_dirac(ip, mp.level[0].smoother_pc, pprec == PREC_DOUBLE ? g32 : pick_gauge(pprec), dk, dm));
+  ms->diracSmooth->gauge_vec = g32;
+  ms->dirac->dagger = false; ms->diracSmooth->dagger = false;
+  ms->mg.reset(new MG(mp, 0, ms->dirac.get(), ms->diracSmooth.get(), nullptr));
+  for (int l = 0; l < mp.n_level - 1; l++)
+    for (int d = 0; d < 4; d++) mgp->geo_block_size[l][d] = mp.level[l].geo_bs[d];
+  QB_CUDA(cudaDeviceSynchronize());
+  mgp->secs = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
+  mgp->gflops = 0;
+  r.verbosity = saved_verbosity;
+  return ms;
+}
+
+void destroyMultigridQuda(void *mg) {
+  if (!mg) return;
+  QB_CUDA(cudaDeviceSynchronize());
+  delete (MultigridSolver *)mg;
+}
+
+// ---- multigrid introspection for tests (include/quda_b200_ext.h) ----------------------------------
+static MG *mg_level(void *mg, int level) {
+  if (!mg) QB_ERROR("null multigrid handle");
+  MG *m = ((MultigridSolver *)mg)->mg.get();
+  for (int l = 0; l < level; l++) {
+    if (!m->coarse) QB_ERROR("multigrid has no level %d", level);
+    m = m->coarse.get();
+  }
+  return m;
+}
+
+void mgVerifyQudaB200(void *mg, int level, double *dev3) { mg_level(mg, level)->verify(dev3); }
+
+void mgLevelInfoQudaB200(void *mg, int level, int *info8) {
+  MG *m = mg_level(mg, level);
+  if (!m->transfer) QB_ERROR("level %d is the coarsest level: it has no transfer operator", level);
+  const Transfer &T = *m->transfer;
+  for (int d = 0; d < 4; d++) info8[d] = T.coarse.X[d];
+  info8[4] = T.nvec; info8[5] = T.Nf; info8[6] = T.block_sites; info8[7] = 2 * T.nvec;
+}
+
+}  // extern "C"
+
+namespace qb {
+void import_generic(SpinorField &f, const float *h, cudaStream_t s);
+void export_generic(float *h, const SpinorField &f, cudaStream_t s);
+}
+
+extern "C" {
+
+// host order of generic fields: [parity][cb][component k][re,im], float32
+void mgProlongQudaB200(void *mg, int level, float *h_fine_out, const float *h_coarse_in) {
+  MG *m = mg_level(mg, level);
+  std::unique_ptr<SpinorField> c(m->transfer->new_coarse_field());
+  std::unique_ptr<SpinorField> f(new SpinorField(m->transfer->fine.Vh, 2, PREC_SINGLE, m->transfer->fine_nspin, m->transfer->fine_ncolor));
+  import_generic(*c, h_coarse_in, rt().compute);
+  m->transfer->P(*f, *c);
+  export_generic(h_fine_out, *f, rt().compute);
+}
+void mgRestrictQudaB200(void *mg, int level, float *h_coarse_out, const float *h_fine_in) {
+  MG *m = mg_level(mg, level);
+  std::unique_ptr<SpinorField> c(m->transfer->new_coarse_field());
+  std::unique_ptr<SpinorField> f(new SpinorField(m->transfer->fine.Vh, 2, PREC_SINGLE, m->transfer->fine_nspin, m->transfer->fine_ncolor));
+  import_generic(*f, h_fine_in, rt().compute);
+  m->transfer->R(*c, *f);
+  export_generic(h_coarse_out, *c, rt().compute);
+}
+// applies the operator of level `level` (0: fine full operator in fp32, >= 1: coarse operator); pc != 0: the smoother's operator
+void mgMatQudaB200(void *mg, int level, int pc, float *h_out, const float *h_in) {
+  MG *m = mg_level(mg, level);
+  const Dirac *d = pc ? m->matSmooth : m->matResidual;
+  std::unique_ptr<SpinorField> in(d->new_field(PREC_SINGLE)), out(d->new_field(PREC_SINGLE));
+  import_generic(*in, h_in, rt().compute);
+  d->M(*out, *in);
+  export_generic(h_out, *out, rt().compute);
+}
+// null vector k of level `level` in host order
+void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out) {
+  MG *m = mg_level(mg, level);
+  if (k < 0 || k >= (int)m->B.size()) QB_ERROR("null vector index %d out of range", k);
+  export_generic(h_out, *m->B[k], rt().compute);
+}
+// one multigrid cycle on level `level`: x = MG(b)
+void mgCycleQudaB200(void *mg, int level, float *h_x, const float *h_b) {
+  MG *m = mg_level(mg, level);
+  std::unique_ptr<SpinorField> b(m->matResidual->new_field(PREC_SINGLE)), x(m->matResidual->new_field(PREC_SINGLE));
+  import_generic(*b, h_b, rt().compute);
+  (*m)(*x, *b);
+  export_generic(h_x, *x, rt().compute);
+}
 
 }  // extern "C"

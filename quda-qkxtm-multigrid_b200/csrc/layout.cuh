@@ -67,17 +67,22 @@ __device__ __forceinline__ int ld_stream(const int *p) {
 // ------------------------------------------------------------------------------------------
 constexpr float HALF_MAX = 32767.0f;  // int16 fixed point of the reference (quda_internal.h:30, io_spinor.h:49-62)
 
+// Every policy's load() returns the factor the loaded values still have to be multiplied by
+// (1 for fp64/fp32).  The hop kernel folds it into the accumulation FMA, so that int16 storage
+// costs no extra multiplies; everything else uses load_scaled().
 struct StoreD {
   typedef double real;
   static constexpr Prec prec = PREC_DOUBLE;
+  static constexpr bool scaled = false;
   template <int NC, bool NC_PATH = true>
-  __device__ __forceinline__ static void load(cplx<double> *o, const void *base, const float *, long stride, long i) {
+  __device__ __forceinline__ static double load(cplx<double> *o, const void *base, const float *, long stride, long i) {
     const double2 *p = (const double2 *)base + i;
 #pragma unroll
     for (int k = 0; k < NC; k++) {
       double2 t = NC_PATH ? ld_nc(p + (long)k * stride) : p[(long)k * stride];
       o[k] = cplx<double>(t.x, t.y);
     }
+    return 1.0;
   }
   template <int NC>
   __device__ __forceinline__ static void store(void *base, float *, long stride, long i, const cplx<double> *v) {
@@ -90,8 +95,9 @@ struct StoreD {
 struct StoreS {
   typedef float real;
   static constexpr Prec prec = PREC_SINGLE;
+  static constexpr bool scaled = false;
   template <int NC, bool NC_PATH = true>
-  __device__ __forceinline__ static void load(cplx<float> *o, const void *base, const float *, long stride, long i) {
+  __device__ __forceinline__ static float load(cplx<float> *o, const void *base, const float *, long stride, long i) {
     const float4 *p = (const float4 *)base + i;
 #pragma unroll
     for (int k = 0; k < NC / 2; k++) {
@@ -99,6 +105,7 @@ struct StoreS {
       o[2 * k] = cplx<float>(t.x, t.y);
       o[2 * k + 1] = cplx<float>(t.z, t.w);
     }
+    return 1.0f;
   }
   template <int NC>
   __device__ __forceinline__ static void store(void *base, float *, long stride, long i, const cplx<float> *v) {
@@ -108,41 +115,52 @@ struct StoreS {
   }
 };
 
-__device__ __forceinline__ void unpack_s16x2(int w, float scale, float &a, float &b) {
-  a = (float)(short)(w & 0xffff) * scale;
-  b = (float)(short)(w >> 16) * scale;
+// int16 <-> fp32 without the quarter-rate I2F/F2I conversion pipe (the first profile of the half
+// kernel showed 387 I2F + 592 FMUL per thread).  The 16-bit integers are kept in HBM in offset-binary
+// form u = s + 32768 (same values as the reference's two's-complement shorts, different encoding), so
+//   as_float(0x4B000000 | u) = 2^23 + u   exactly   =>   float(s) = that - (2^23 + 32768)
+// costs one PRMT and one exact FADD per value on the full-rate pipes.
+__device__ __forceinline__ void unpack_s16x2_raw(int w, float &a, float &b) {
+  const unsigned lo = __byte_perm((unsigned)w, 0x4B000000u, 0x7610);
+  const unsigned hi = __byte_perm((unsigned)w, 0x4B000000u, 0x7632);
+  a = __uint_as_float(lo) - 8421376.0f;
+  b = __uint_as_float(hi) - 8421376.0f;
 }
+// fp32 -> offset-binary int16 pair, round to nearest even: x*scale + (1.5*2^23 + 32768) leaves u in the low mantissa bits
 __device__ __forceinline__ int pack_s16x2(float a, float b, float scale) {
-  int ia = __float2int_rn(a * scale), ib = __float2int_rn(b * scale);
-  return (ia & 0xffff) | (ib << 16);
+  const unsigned ia = __float_as_uint(fmaf(a, scale, 12615680.0f));
+  const unsigned ib = __float_as_uint(fmaf(b, scale, 12615680.0f));
+  return (int)__byte_perm(ia, ib, 0x5410);
 }
 
 // int16 storage + one float norm per site; arithmetic in fp32
 struct StoreH {
   typedef float real;
   static constexpr Prec prec = PREC_HALF;
+  static constexpr bool scaled = true;
   template <int NC, bool NC_PATH = true>
-  __device__ __forceinline__ static void load(cplx<float> *o, const void *base, const float *norm, long stride, long i) {
+  __device__ __forceinline__ static float load(cplx<float> *o, const void *base, const float *norm, long stride, long i) {
     const float c = (NC_PATH ? ld_nc(norm + i) : norm[i]) * (1.0f / HALF_MAX);
     if (NC % 4 == 0) {
       const int4 *p = (const int4 *)base + i;
 #pragma unroll
       for (int k = 0; k < NC / 4; k++) {
         int4 t = NC_PATH ? ld_nc(p + (long)k * stride) : p[(long)k * stride];
-        unpack_s16x2(t.x, c, o[4 * k].re, o[4 * k].im);
-        unpack_s16x2(t.y, c, o[4 * k + 1].re, o[4 * k + 1].im);
-        unpack_s16x2(t.z, c, o[4 * k + 2].re, o[4 * k + 2].im);
-        unpack_s16x2(t.w, c, o[4 * k + 3].re, o[4 * k + 3].im);
+        unpack_s16x2_raw(t.x, o[4 * k].re, o[4 * k].im);
+        unpack_s16x2_raw(t.y, o[4 * k + 1].re, o[4 * k + 1].im);
+        unpack_s16x2_raw(t.z, o[4 * k + 2].re, o[4 * k + 2].im);
+        unpack_s16x2_raw(t.w, o[4 * k + 3].re, o[4 * k + 3].im);
       }
     } else {  // half spinors (6 complex): 8-byte planes of 2 complex
       const int2 *p = (const int2 *)base + i;
 #pragma unroll
       for (int k = 0; k < NC / 2; k++) {
         int2 t = NC_PATH ? ld_nc(p + (long)k * stride) : p[(long)k * stride];
-        unpack_s16x2(t.x, c, o[2 * k].re, o[2 * k].im);
-        unpack_s16x2(t.y, c, o[2 * k + 1].re, o[2 * k + 1].im);
+        unpack_s16x2_raw(t.x, o[2 * k].re, o[2 * k].im);
+        unpack_s16x2_raw(t.y, o[2 * k + 1].re, o[2 * k + 1].im);
       }
     }
+    return c;
   }
   template <int NC>
   __device__ __forceinline__ static void store(void *base, float *norm, long stride, long i, const cplx<float> *v) {
@@ -165,6 +183,16 @@ struct StoreH {
     }
   }
 };
+
+// load and apply the storage scale (everything except the hop kernel)
+template <typename Store, int NC, bool NC_PATH = true>
+__device__ __forceinline__ void load_scaled(cplx<typename Store::real> *o, const void *base, const float *norm, long stride, long i) {
+  const typename Store::real sc = Store::template load<NC, NC_PATH>(o, base, norm, stride, i);
+  if (Store::scaled) {
+#pragma unroll
+    for (int k = 0; k < NC; k++) { o[k].re *= sc; o[k].im *= sc; }
+  }
+}
 
 // bytes of one site-plane element for NC complex per site
 template <typename Store> struct StoreTraits;
@@ -209,28 +237,44 @@ template <int RECON> struct LinkRaw<StoreS, RECON> {
     }
   }
 };
+// half precision: returns integer-valued floats (the 1/32767 is folded into the hop's accumulation scale,
+// see link_scale()); recon 8 is non-linear in the stored numbers and is converted to real units here
 template <int RECON> struct LinkRaw<StoreH, RECON> {
   __device__ __forceinline__ static void load(float *r, const void *base, long stride, long i) {
-    const float c = 1.0f / HALF_MAX;
     if (RECON == 18) {
       const int *p = (const int *)base + i;
 #pragma unroll
       for (int k = 0; k < 9; k++) {
         int t = ld_stream(p + (long)k * stride);
-        unpack_s16x2(t, c, r[2 * k], r[2 * k + 1]);
+        unpack_s16x2_raw(t, r[2 * k], r[2 * k + 1]);
       }
     } else {
       const int2 *p = (const int2 *)base + i;
 #pragma unroll
       for (int k = 0; k < RECON / 4; k++) {
         int2 t = ld_stream(p + (long)k * stride);
-        unpack_s16x2(t.x, c, r[4 * k], r[4 * k + 1]);
-        unpack_s16x2(t.y, c, r[4 * k + 2], r[4 * k + 3]);
+        unpack_s16x2_raw(t.x, r[4 * k], r[4 * k + 1]);
+        unpack_s16x2_raw(t.y, r[4 * k + 2], r[4 * k + 3]);
       }
-      if (RECON == 8) { r[6] *= 3.14159265358979323846f; r[7] *= 3.14159265358979323846f; }  // phases are stored / pi
+      if (RECON == 8) {
+        const float c = 1.0f / HALF_MAX;
+#pragma unroll
+        for (int k = 0; k < 6; k++) r[k] *= c;
+        r[6] *= c * 3.14159265358979323846f;  // phases are stored / pi
+        r[7] *= c * 3.14159265358979323846f;
+      }
     }
   }
 };
+
+// factor by which a reconstructed link of this storage type still has to be multiplied, and the
+// correction of the recon-12 third-row factor u0 (that row is quadratic in the stored numbers)
+template <typename Store, int RECON> __device__ __forceinline__ typename Store::real link_scale() {
+  return (Store::scaled && RECON != 8) ? (typename Store::real)(1.0f / HALF_MAX) : (typename Store::real)1;
+}
+template <typename Store, int RECON> __device__ __forceinline__ typename Store::real link_u0(typename Store::real u0) {
+  return (Store::scaled && RECON == 12) ? u0 * (typename Store::real)(1.0f / HALF_MAX) : u0;
+}
 
 // Reconstruct the full 3x3 link U[row*3+col] from RECON stored reals.
 //  recon 12: rows 0,1 stored; row 2 = conj(row0 x row1) * u0   (cf. lib/read_gauge.h:393-401)

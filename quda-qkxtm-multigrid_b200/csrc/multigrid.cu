@@ -1,0 +1,263 @@
+// Multigrid level construction and cycle.
+#include <chrono>
+#include <cmath>
+#include "multigrid.h"
+
+namespace qb {
+
+using blas::Complex;
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// deterministic counter-based uniform numbers in [0,1): value depends only on (seed, parity, site, component)
+__global__ void random_fill_kernel(float4 *v, long Vh, int nplanes, int nparity, unsigned long long seed) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)nparity * nplanes * Vh) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(4 * t + 1);
+  float r[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    z += 0x9E3779B97F4A7C15ull;
+    unsigned long long x = z;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    r[k] = (float)(x >> 40) * (1.0f / 16777216.0f);
+  }
+  v[t] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+void random_fill(SpinorField &f, unsigned long long seed) {
+  if (f.prec != PREC_SINGLE) QB_ERROR("random_fill: single precision fields only");
+  const long n = (long)f.nparity * f.planes() * f.Vh;
+  random_fill_kernel<<<div_up(n, 256), 256, 0, rt().compute>>>((float4 *)f.v, f.Vh, f.planes(), f.nparity, seed);
+  QB_CHECK_LAUNCH();
+}
+
+static SpinorField *new_full(const Dirac &d) {
+  SpinorField *p = d.new_parity_field(PREC_SINGLE);
+  SpinorField *f = new SpinorField(p->Vh, 2, PREC_SINGLE, p->nspin, p->ncolor);
+  delete p;
+  return f;
+}
+
+MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmooth_, std::vector<std::unique_ptr<SpinorField>> *B_in)
+    : Solver(dummy), mp(mp_), level(level_), matResidual(matResidual_), matSmooth(matSmooth_) {
+  const double t0 = now_s();
+  const MGLevelParam &lp = mp.level[level];
+  const bool last = level == mp.n_level - 1;
+  log_msg(1, "MG level %d: creating level %d of %d\n", level + 1, level + 1, mp.n_level);
+  if (matResidual->is_pc()) QB_ERROR("MG: the residual operator of a level must be the full (unpreconditioned) operator");
+
+  // ---- smoothers (multigrid.cpp:47-92) ----
+  param_presmooth.inv_type = lp.smoother;
+  param_presmooth.inv_type_precondition = INV_NONE;
+  param_presmooth.is_preconditioner = true;
+  param_presmooth.preserve_source = true;
+  param_presmooth.use_init_guess = false;
+  param_presmooth.maxiter = lp.nu_pre;
+  param_presmooth.Nkrylov = 4;
+  param_presmooth.tol = lp.smoother_tol;
+  param_presmooth.omega = lp.omega;
+  param_presmooth.global_reduction = lp.global_reduction;
+  param_presmooth.precision = param_presmooth.precision_sloppy = param_presmooth.precision_precondition = PREC_SINGLE;
+  param_presmooth.compute_true_res = false;
+  param_presmooth.verbosity = 0;
+  if (last) {  // coarsest grid: GCR(20) to smoother_tol (multigrid.cpp:63-70)
+    param_presmooth.inv_type = lp.smoother == INV_MR ? INV_GCR : lp.smoother;
+    param_presmooth.Nkrylov = 20;
+    param_presmooth.maxiter = 1000;
+    param_presmooth.delta = 1e-8;
+  }
+  DiracMatrix ms(matSmooth);
+  presmoother.reset(Solver::create(param_presmooth, ms, ms, ms));
+  if (!last) {
+    param_postsmooth = param_presmooth;
+    param_postsmooth.use_init_guess = true;
+    param_postsmooth.maxiter = lp.nu_post;
+    postsmoother.reset(Solver::create(param_postsmooth, ms, ms, ms));
+  }
+  r.reset(new_full(*matResidual));
+
+  if (!last) {
+    // ---- near-null vectors ----
+    if (B_in) B = std::move(*B_in);
+    if ((int)B.size() < lp.nvec) {
+      if (!mp.compute_null_vector) QB_ERROR("MG level %d: %d null vectors needed but compute_null_vector is off (vector files are not supported)", level + 1, lp.nvec);
+      generate_null_vectors();
+    }
+    std::vector<SpinorField *> Bp;
+    for (int i = 0; i < lp.nvec; i++) Bp.push_back(B[i].get());
+
+    // ---- transfer operator and Galerkin coarse operator ----
+    int bs[4] = {lp.geo_bs[0], lp.geo_bs[1], lp.geo_bs[2], lp.geo_bs[3]};
+    int fineX[4];
+    if (level == 0) {
+      const DiracTM *d = dynamic_cast<const DiracTM *>(matResidual);
+      if (!d) QB_ERROR("MG: level-0 operator must be Wilson / twisted mass");
+      for (int k = 0; k < 4; k++) fineX[k] = d->lat->geom.X[k];
+    } else {
+      const DiracCoarse *d = dynamic_cast<const DiracCoarse *>(matResidual);
+      for (int k = 0; k < 4; k++) fineX[k] = d->op->geom.X[k];
+    }
+    transfer.reset(new Transfer(Bp, lp.nvec, bs, lp.spin_bs, fineX));
+    for (int k = 0; k < 4; k++) mp.level[level].geo_bs[k] = bs[k];  // written back like multigrid.cpp:120-122
+    coarse_op.reset(new CoarseOperator());
+    const double tc0 = now_s();
+    matResidual->create_coarse_op(*coarse_op, *transfer);
+    const MGLevelParam &cp = mp.level[level + 1];
+    if (cp.smoother_pc) coarse_op->compute_xinv();
+    QB_CUDA(cudaStreamSynchronize(rt().compute));
+    log_msg(1, "MG level %d: coarse operator %d x %d x %d x %d, N = %d built in %.3f s\n", level + 1, coarse_op->geom.X[0], coarse_op->geom.X[1],
+            coarse_op->geom.X[2], coarse_op->geom.X[3], coarse_op->N, now_s() - tc0);
+    coarseResidual.reset(new DiracCoarse(coarse_op, false, MATPC_EVEN_EVEN));
+    coarseSmooth.reset(new DiracCoarse(coarse_op, cp.smoother_pc, MATPC_EVEN_EVEN));
+    r_coarse.reset(transfer->new_coarse_field());
+    x_coarse.reset(transfer->new_coarse_field());
+
+    // ---- coarse-level null vectors: restricted fine ones unless every level generates its own ----
+    std::vector<std::unique_ptr<SpinorField>> Bc;
+    if (level + 1 < mp.n_level - 1 && !mp.generate_all_levels) {
+      if (cp.nvec > lp.nvec) QB_ERROR("MG: n_vec[%d] = %d > n_vec[%d] = %d requires generate_all_levels", level + 1, cp.nvec, level, lp.nvec);
+      for (int i = 0; i < cp.nvec; i++) {
+        Bc.emplace_back(transfer->new_coarse_field());
+        transfer->R(*Bc.back(), *B[i]);
+      }
+    }
+    coarse.reset(new MG(mp, level + 1, coarseResidual.get(), coarseSmooth.get(), Bc.empty() ? nullptr : &Bc));
+
+    // ---- coarse solver: the next level's cycle, wrapped in GCR(10) for a K-cycle (multigrid.cpp:225-275) ----
+    if (lp.recursive && level + 1 < mp.n_level - 1) {
+      param_coarse_solver.inv_type = INV_GCR;
+      param_coarse_solver.inv_type_precondition = INV_MG;
+      param_coarse_solver.is_preconditioner = true;
+      param_coarse_solver.preserve_source = true;
+      param_coarse_solver.use_init_guess = false;
+      param_coarse_solver.maxiter = 11;
+      param_coarse_solver.Nkrylov = 10;
+      param_coarse_solver.tol = cp.smoother_tol;
+      param_coarse_solver.global_reduction = true;
+      param_coarse_solver.compute_true_res = false;
+      param_coarse_solver.delta = 1e-8;
+      param_coarse_solver.precision = param_coarse_solver.precision_sloppy = param_coarse_solver.precision_precondition = PREC_SINGLE;
+      param_coarse_solver.verbosity = 0;
+      DiracMatrix mc(coarseResidual.get());
+      coarse_solver_gcr.reset(new GCR(mc, mc, mc, param_coarse_solver, coarse.get()));
+    }
+  }
+  setup_secs = now_s() - t0;
+  log_msg(1, "MG level %d: setup completed in %.3f s\n", level + 1, setup_secs);
+}
+
+// BiCGStab on the smoother operator with zero source and random initial guess, then global Gram-Schmidt
+// (multigrid.cpp:693-779)
+void MG::generate_null_vectors() {
+  const MGLevelParam &lp = mp.level[level];
+  log_msg(1, "MG level %d: generating %d null vectors (BiCGStab, maxiter %d, tol %g)\n", level + 1, lp.nvec, mp.setup_maxiter, mp.setup_tol);
+  SolverParam sp;
+  sp.inv_type = INV_BICGSTAB;
+  sp.maxiter = mp.setup_maxiter;
+  sp.tol = mp.setup_tol;
+  sp.use_init_guess = true;
+  sp.compute_null_vector = true;
+  sp.precision = sp.precision_sloppy = sp.precision_precondition = PREC_SINGLE;
+  sp.verbosity = mp.verbosity >= 3 ? 3 : 0;
+  DiracMatrix ms(matSmooth);
+  std::unique_ptr<SpinorField> b(new_full(*matResidual));
+  while ((int)B.size() < lp.nvec) {
+    const int i = (int)B.size();
+    std::unique_ptr<SpinorField> x(new_full(*matResidual));
+    random_fill(*x, 0x5EEDull + 7919ull * (unsigned long long)(level * 1000 + i));
+    blas::zero(*b);
+    BiCGStab solve(ms, ms, sp);
+    SpinorField src, sol;
+    matSmooth->prepare(src, sol, *x, *b, SOL_MAT);
+    solve(sol, src);
+    matSmooth->reconstruct(*x, *b, SOL_MAT);
+    for (int j = 0; j < i; j++) {
+      const Complex a = blas::cDotProduct(*B[j], *x);
+      blas::caxpy(-a, *B[j], *x);
+    }
+    const double n2 = blas::norm2(*x);
+    if (!(n2 > 1e-16)) QB_ERROR("Cannot orthogonalize %d vector", i);
+    blas::ax(1.0 / sqrt(n2), *x);
+    B.push_back(std::move(x));
+    log_msg(2, "MG level %d: null vector %d done (%d BiCGStab iterations so far)\n", level + 1, i, sp.iter);
+  }
+}
+
+// x <- smoother applied to M x = b through the (possibly even-odd preconditioned) smoother operator
+void MG::smooth(Solver &s, SpinorField &x, SpinorField &b) {
+  SpinorField src, sol;
+  matSmooth->prepare(src, sol, x, b, SOL_MAT);
+  s(sol, src);
+  matSmooth->reconstruct(x, b, SOL_MAT);
+}
+
+void MG::cycle(SpinorField &x, SpinorField &b) {
+  const MGLevelParam &lp = mp.level[level];
+  if (level == mp.n_level - 1) {  // coarsest grid solve
+    smooth(*presmoother, x, b);
+    return;
+  }
+  // pre-smoothing (zero initial guess) and residual
+  if (lp.nu_pre > 0) {
+    smooth(*presmoother, x, b);
+    matResidual->M(*r, x);
+    blas::axpby(1.0, b, -1.0, *r);
+  } else {
+    blas::zero(x);
+    blas::copy(*r, b);
+  }
+  // coarse-grid correction
+  transfer->R(*r_coarse, *r);
+  if (coarse_solver_gcr) (*coarse_solver_gcr)(*x_coarse, *r_coarse);
+  else (*coarse)(*x_coarse, *r_coarse);
+  transfer->P(*r, *x_coarse);
+  blas::xpy(*r, x);
+  // post-smoothing with x as the initial guess
+  if (lp.nu_post > 0) smooth(*postsmoother, x, b);
+}
+
+void MG::operator()(SpinorField &x, SpinorField &b) {
+  if (x.nparity != 2 || b.nparity != 2) QB_ERROR("MG: the multigrid cycle acts on full fields (use solve_type = QUDA_DIRECT_SOLVE for the outer solver)");
+  if (x.prec == PREC_SINGLE && b.prec == PREC_SINGLE) {
+    cycle(x, b);  // b is only read (smoothers preserve their source)
+    return;
+  }
+  // outer solver runs in another precision: the cycle itself is single precision (reference: cuda_prec_sloppy)
+  if (!x32) { x32.reset(new_like(x, PREC_SINGLE)); b32.reset(new_like(b, PREC_SINGLE)); }
+  blas::copy(*b32, b);
+  cycle(*x32, *b32);
+  blas::copy(x, *x32);
+}
+
+long long MG::flops() const { return 0; }
+
+// MG::verify identities (multigrid.cpp:372-486)
+void MG::verify(double *dev) {
+  dev[0] = dev[1] = dev[2] = 0.0;
+  if (!transfer) return;
+  std::unique_ptr<SpinorField> eta(transfer->new_coarse_field()), t_c(transfer->new_coarse_field()), t_c2(transfer->new_coarse_field());
+  std::unique_ptr<SpinorField> t_f(new_full(*matResidual)), t_f2(new_full(*matResidual));
+  random_fill(*eta, 424242ull + level);
+  // (1) R P eta = eta
+  transfer->P(*t_f, *eta);
+  transfer->R(*t_c, *t_f);
+  dev[0] = sqrt(blas::xmyNorm(*eta, *t_c) / blas::norm2(*eta));
+  // (2) P R v_k = v_k for the null vectors
+  for (size_t k = 0; k < B.size() && (int)k < mp.level[level].nvec; k++) {
+    transfer->R(*t_c, *B[k]);
+    transfer->P(*t_f, *t_c);
+    const double d = sqrt(blas::xmyNorm(*B[k], *t_f) / blas::norm2(*B[k]));
+    if (d > dev[1]) dev[1] = d;
+  }
+  // (3) R M P eta = M_c eta
+  transfer->P(*t_f, *eta);
+  matResidual->M(*t_f2, *t_f);
+  transfer->R(*t_c, *t_f2);
+  coarseResidual->M(*t_c2, *eta);
+  dev[2] = sqrt(blas::xmyNorm(*t_c2, *t_c) / blas::norm2(*t_c2));
+}
+
+}  // namespace qb

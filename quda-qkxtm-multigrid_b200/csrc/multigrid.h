@@ -1,0 +1,76 @@
+// Adaptive multigrid preconditioner (replaces /root/reference/lib/multigrid.cpp, include/multigrid.h).
+// Level construction (:11-295), V / K cycle (:488-604), null-vector generation (:693-779) and the
+// consistency checks of MG::verify (:372-486, disabled in the reference fork, enabled here for tests).
+#pragma once
+#include <memory>
+#include <vector>
+#include "coarse.h"
+#include "solver.h"
+#include "transfer.h"
+
+namespace qb {
+
+struct MGLevelParam {
+  int geo_bs[4] = {4, 4, 4, 4};
+  int spin_bs = 2;
+  int nvec = 24;
+  InverterType smoother = INV_MR;
+  bool smoother_pc = true;          // smoother_solve_type == QUDA_DIRECT_PC_SOLVE
+  int nu_pre = 2, nu_post = 2;
+  double smoother_tol = 0.25;
+  double omega = 0.85;
+  bool recursive = true;            // cycle_type == QUDA_MG_CYCLE_RECURSIVE (K-cycle)
+  bool global_reduction = true;
+};
+
+struct MGParam {
+  int n_level = 2;
+  MGLevelParam level[4];
+  int setup_maxiter = 500;
+  double setup_tol = 5e-6;
+  bool compute_null_vector = true;
+  bool generate_all_levels = true;
+  int verbosity = 1;
+};
+
+class MG : public Solver {
+ public:
+  MGParam &mp;
+  int level;
+  const Dirac *matResidual;   // full operator of this level (fp32 vectors)
+  const Dirac *matSmooth;     // even-odd preconditioned (or full) operator used by the smoother
+  SolverParam dummy;
+  // next level
+  std::unique_ptr<Transfer> transfer;
+  std::shared_ptr<CoarseOperator> coarse_op;
+  std::unique_ptr<DiracCoarse> coarseResidual, coarseSmooth;
+  std::unique_ptr<MG> coarse;
+  std::unique_ptr<Solver> coarse_solver_gcr;  // K-cycle wrapper
+  SolverParam param_coarse_solver, param_presmooth, param_postsmooth;
+  std::unique_ptr<Solver> presmoother, postsmoother;
+  std::vector<std::unique_ptr<SpinorField>> B;   // near-null vectors of this level
+  std::unique_ptr<SpinorField> r, r_coarse, x_coarse, b_copy, x32, b32;
+  double setup_secs = 0.0;
+
+  MG(MGParam &mp, int level, const Dirac *matResidual, const Dirac *matSmooth, std::vector<std::unique_ptr<SpinorField>> *B_in);
+  void operator()(SpinorField &x, SpinorField &b) override;
+  // deviations of the identities checked by MG::verify: {|P^dag P eta - eta|, max_k |P R v_k - v_k|, |R M P eta - M_c eta|} (relative)
+  void verify(double *dev3);
+  long long flops() const override;
+
+ private:
+  void generate_null_vectors();
+  void smooth(Solver &s, SpinorField &x, SpinorField &b);
+  void cycle(SpinorField &x, SpinorField &b);
+};
+
+// handle returned by newMultigridQuda (multigrid_solver of interface_quda.cpp:2161-2255)
+struct MultigridSolver {
+  MGParam mp;
+  std::unique_ptr<DiracTM> dirac, diracSmooth;
+  std::unique_ptr<MG> mg;
+};
+
+void random_fill(SpinorField &f, unsigned long long seed);
+
+}  // namespace qb

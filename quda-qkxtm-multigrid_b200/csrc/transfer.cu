@@ -1,0 +1,272 @@
+// Transfer operator: geometry maps, V assembly, block Gram-Schmidt, prolongator and restrictor kernels.
+#include <algorithm>
+#include <vector>
+#include "layout.cuh"
+#include "transfer.h"
+
+namespace qb {
+
+// ---- geometry ------------------------------------------------------------------------------------
+static inline void cb_to_coords(int *x, long cb, int parity, const LevelGeom &g) {
+  const long za = cb / g.Xh, zb = za / g.X[1];
+  x[1] = (int)(za - zb * g.X[1]);
+  x[3] = (int)(zb / g.X[2]);
+  x[2] = (int)(zb - (long)x[3] * g.X[2]);
+  x[0] = (int)(2 * cb + ((x[1] + x[2] + x[3] + parity) & 1) - za * g.X[0]);
+}
+static inline long coords_to_full(const int *x, const LevelGeom &g) {
+  const long lex = (((long)x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.X[0] + x[0];
+  const int parity = (x[0] + x[1] + x[2] + x[3]) & 1;
+  return (long)parity * g.Vh + (lex >> 1);
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------
+// V[(parity*Nf + k) * nvec/2 + j/2][cb] float4, complex j%2 inside
+__device__ __forceinline__ size_t v_plane(int parity, int k, int jp, int Nf, int nvh) { return ((size_t)parity * Nf + k) * nvh + jp; }
+
+__global__ void fill_v_kernel(float4 *V, const float4 *B, long Vh, int Nf, int nvec, int j) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nkp = Nf / 2;
+  if (t >= 2 * Vh * nkp) return;
+  const long cb = t % Vh;
+  const int kp = (int)((t / Vh) % nkp), parity = (int)(t / (Vh * nkp));
+  const float4 b = B[((size_t)parity * nkp + kp) * Vh + cb];  // field layout [parity][plane][cb]
+  float2 *v0 = (float2 *)(V + v_plane(parity, 2 * kp, j / 2, Nf, nvec / 2) * Vh + cb) + (j & 1);
+  float2 *v1 = (float2 *)(V + v_plane(parity, 2 * kp + 1, j / 2, Nf, nvec / 2) * Vh + cb) + (j & 1);
+  *v0 = make_float2(b.x, b.y);
+  *v1 = make_float2(b.z, b.w);
+}
+
+__device__ __forceinline__ double2 block_sum(double2 v, double2 *sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  double2 s = make_double2(0.0, 0.0);
+  for (int w = 0; w < nw; w++) { s.x += sm[w].x; s.y += sm[w].y; }
+  return s;
+}
+
+// One CTA per (aggregate, chirality): modified Gram-Schmidt over the nvec block vectors, fp64 sums
+// (order of operations of blockGramSchmidt, lib/transfer_util.cu:327-363).
+__global__ void __launch_bounds__(256) block_ortho_kernel(float *V, const int *c2f, long Vh_f, int Nf, int nvec, int block_sites) {
+  __shared__ double2 sm[8];
+  const int X = blockIdx.x, S = blockIdx.y;
+  const int cpc = Nf / 2;            // components per chirality
+  const int E = block_sites * cpc;   // block-vector length
+  const int nvh = nvec / 2;
+  auto addr = [&](int e, int j) -> float2 * {
+    const int i = e / cpc, k = S * cpc + (e - i * cpc);
+    const int fs = c2f[(size_t)X * block_sites + i];
+    const int parity = fs >= Vh_f ? 1 : 0;
+    const long cb = fs - (long)parity * Vh_f;
+    return (float2 *)((float4 *)V + v_plane(parity, k, j >> 1, Nf, nvh) * Vh_f + cb) + (j & 1);
+  };
+  for (int jc = 0; jc < nvec; jc++) {
+    for (int ic = 0; ic < jc; ic++) {
+      double2 d = make_double2(0.0, 0.0);
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const float2 a = *addr(e, ic), b = *addr(e, jc);
+        d.x += (double)a.x * b.x + (double)a.y * b.y;
+        d.y += (double)a.x * b.y - (double)a.y * b.x;
+      }
+      d = block_sum(d, sm);
+      const float dr = (float)d.x, di = (float)d.y;
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const float2 a = *addr(e, ic);
+        float2 *pb = addr(e, jc);
+        float2 b = *pb;
+        b.x -= dr * a.x - di * a.y;
+        b.y -= dr * a.y + di * a.x;
+        *pb = b;
+      }
+      __syncthreads();
+    }
+    double2 n = make_double2(0.0, 0.0);
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const float2 b = *addr(e, jc);
+      n.x += (double)b.x * b.x + (double)b.y * b.y;
+    }
+    n = block_sum(n, sm);
+    const float scale = n.x > 0.0 ? (float)(1.0 / sqrt(n.x)) : 0.0f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      float2 *pb = addr(e, jc);
+      float2 b = *pb;
+      b.x *= scale; b.y *= scale;
+      *pb = b;
+    }
+    __syncthreads();
+  }
+}
+
+// thread = (fine site, component pair): out(x, k) = sum_j V(x,k,j) c(X, chi(k), j)
+__global__ void __launch_bounds__(128) prolong_kernel(float4 *out, const float4 *cin, const float4 *V, const int *f2c, long Vh_f, long Vh_c,
+                                                      int Nf, int nvec, int cpc) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nkp = Nf / 2;
+  if (t >= 2 * Vh_f * nkp) return;
+  const long cb = t % Vh_f;
+  const int kp = (int)((t / Vh_f) % nkp), parity = (int)(t / (Vh_f * nkp));
+  const int k0 = 2 * kp, S = k0 / cpc, nvh = nvec / 2;
+  const int cs = f2c[(size_t)parity * Vh_f + cb];
+  const int cpar = cs >= Vh_c ? 1 : 0;
+  const long ccb = cs - (long)cpar * Vh_c;
+  // coarse field [parity][plane = (S*nvec + j)/2][cb]
+  const float4 *c = cin + ((size_t)cpar * nvec + (size_t)S * nvh) * Vh_c + ccb;
+  const float4 *v0 = V + v_plane(parity, k0, 0, Nf, nvh) * Vh_f + cb;
+  const float4 *v1 = V + v_plane(parity, k0 + 1, 0, Nf, nvh) * Vh_f + cb;
+  cplx<float> a0(0.f, 0.f), a1(0.f, 0.f);
+#pragma unroll 4
+  for (int jp = 0; jp < nvh; jp++) {
+    const float4 cc = __ldg(c + (size_t)jp * Vh_c);
+    const float4 w0 = ld_stream(v0 + (size_t)jp * Vh_f), w1 = ld_stream(v1 + (size_t)jp * Vh_f);
+    cmac(a0, cplx<float>(w0.x, w0.y), cplx<float>(cc.x, cc.y));
+    cmac(a0, cplx<float>(w0.z, w0.w), cplx<float>(cc.z, cc.w));
+    cmac(a1, cplx<float>(w1.x, w1.y), cplx<float>(cc.x, cc.y));
+    cmac(a1, cplx<float>(w1.z, w1.w), cplx<float>(cc.z, cc.w));
+  }
+  out[((size_t)parity * nkp + kp) * Vh_f + cb] = make_float4(a0.re, a0.im, a1.re, a1.im);
+}
+
+// CTA = one aggregate; threads = (32 site lanes) x (nvec/2 vector pairs).  Deterministic: fixed site order
+// per lane, shuffle tree across lanes (the reference uses cub::BlockReduce, restrictor.cu:159-237).
+__global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V, const int *c2f, long Vh_f, long Vh_c, int Nf, int nvec,
+                                int cpc, int block_sites) {
+  const int X = blockIdx.x;  // coarse full index
+  const int lane = threadIdx.x, jp = threadIdx.y;
+  const int nkp = Nf / 2, nvh = nvec / 2;
+  cplx<float> acc[2][2];  // [chirality][j within pair]
+#pragma unroll
+  for (int s = 0; s < 2; s++) { acc[s][0] = cplx<float>(0.f, 0.f); acc[s][1] = cplx<float>(0.f, 0.f); }
+  for (int i = lane; i < block_sites; i += 32) {
+    const int fs = c2f[(size_t)X * block_sites + i];
+    const int parity = fs >= Vh_f ? 1 : 0;
+    const long cb = fs - (long)parity * Vh_f;
+    for (int kp = 0; kp < nkp; kp++) {
+      const float4 f = __ldg(fin + ((size_t)parity * nkp + kp) * Vh_f + cb);
+      const float4 w0 = ld_stream(V + v_plane(parity, 2 * kp, jp, Nf, nvh) * Vh_f + cb);
+      const float4 w1 = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, Nf, nvh) * Vh_f + cb);
+      const int S = (2 * kp) / cpc;
+      const cplx<float> f0(f.x, f.y), f1(f.z, f.w);
+      if (S == 0) {
+        cmac_conj(acc[0][0], cplx<float>(w0.x, w0.y), f0); cmac_conj(acc[0][1], cplx<float>(w0.z, w0.w), f0);
+        cmac_conj(acc[0][0], cplx<float>(w1.x, w1.y), f1); cmac_conj(acc[0][1], cplx<float>(w1.z, w1.w), f1);
+      } else {
+        cmac_conj(acc[1][0], cplx<float>(w0.x, w0.y), f0); cmac_conj(acc[1][1], cplx<float>(w0.z, w0.w), f0);
+        cmac_conj(acc[1][0], cplx<float>(w1.x, w1.y), f1); cmac_conj(acc[1][1], cplx<float>(w1.z, w1.w), f1);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc[s][q].re += __shfl_xor_sync(0xffffffffu, acc[s][q].re, o);
+        acc[s][q].im += __shfl_xor_sync(0xffffffffu, acc[s][q].im, o);
+      }
+  if (lane == 0) {
+    const int cpar = X >= Vh_c ? 1 : 0;
+    const long ccb = X - (long)cpar * Vh_c;
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+      out[((size_t)cpar * nvec + (size_t)s * nvh + jp) * Vh_c + ccb] = make_float4(acc[s][0].re, acc[s][0].im, acc[s][1].re, acc[s][1].im);
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+Transfer::Transfer(const std::vector<SpinorField *> &B, int nvec_, int *bs, int spin_bs_, const int *fine_X) : nvec(nvec_), spin_bs(spin_bs_) {
+  if ((int)B.size() < nvec) QB_ERROR("Transfer: %d null vectors supplied, %d needed", (int)B.size(), nvec);
+  if (nvec < 2 || (nvec & 1)) QB_ERROR("Transfer: n_vec = %d must be even and >= 2", nvec);
+  fine.set(fine_X);
+  fine_nspin = B[0]->nspin; fine_ncolor = B[0]->ncolor; Nf = B[0]->ncomplex;
+  if (fine_nspin % spin_bs || fine_nspin / spin_bs != 2) QB_ERROR("Transfer: spin block size %d does not give two chiralities for nSpin = %d", spin_bs, fine_nspin);
+  if ((Nf / 2) & 1) QB_ERROR("Transfer: odd number of components per chirality (%d) is not supported", Nf / 2);
+  for (auto *b : B)
+    if (b->prec != PREC_SINGLE || b->nparity != 2 || b->Vh != fine.Vh) QB_ERROR("Transfer: null vectors must be full single-precision fields of the fine lattice");
+  // block-size fix-up of the reference (transfer.cpp:31-44)
+  int cX[4];
+  block_sites = 1;
+  for (int d = 0; d < 4; d++) {
+    while (bs[d] > 0) {
+      if (d == 0 && fine.X[0] == bs[0]) log_msg(1, "WARNING: X-dimension length %d cannot block length %d\n", fine.X[0], bs[0]);
+      else if ((fine.X[d] / bs[d] + 1) % 2 == 0) log_msg(1, "WARNING: Indexing does not (yet) support odd coarse dimensions: X(%d) = %d\n", d, fine.X[d] / bs[d]);
+      else if ((fine.X[d] / bs[d]) * bs[d] != fine.X[d]) log_msg(1, "WARNING: cannot block dim[%d]=%d with block size = %d\n", d, fine.X[d], bs[d]);
+      else break;
+      bs[d] /= 2;
+    }
+    if (bs[d] == 0) QB_ERROR("Unable to block dimension %d", d);
+    geo_bs[d] = bs[d];
+    cX[d] = fine.X[d] / bs[d];
+    block_sites *= bs[d];
+  }
+  if (block_sites == 1) QB_ERROR("Total geometric block size is 1");
+  coarse.set(cX);
+  log_msg(2, "Transfer: using block size %d x %d x %d x %d, coarse lattice %d x %d x %d x %d, %d vectors\n", bs[0], bs[1], bs[2], bs[3], cX[0], cX[1], cX[2], cX[3], nvec);
+
+  // geometry maps (createGeoMap, transfer.cpp:220-258): fine -> coarse by integer division of coordinates;
+  // coarse -> fine = fine sites sorted by (coarse index, fine index)
+  const long Vf = fine.V(), Vc = coarse.V();
+  std::vector<int> h_f2c(Vf), h_c2f(Vf), fill(Vc, 0);
+  for (int p = 0; p < 2; p++)
+    for (long cb = 0; cb < fine.Vh; cb++) {
+      int x[4], xc[4];
+      cb_to_coords(x, cb, p, fine);
+      for (int d = 0; d < 4; d++) xc[d] = x[d] / geo_bs[d];
+      h_f2c[p * fine.Vh + cb] = (int)coords_to_full(xc, coarse);
+    }
+  for (long f = 0; f < Vf; f++) {  // ascending fine index => parity-0 sites first within each aggregate
+    const int c = h_f2c[f];
+    h_c2f[(size_t)c * block_sites + fill[c]++] = (int)f;
+  }
+  QB_CUDA(cudaMalloc((void **)&f2c, sizeof(int) * Vf));
+  QB_CUDA(cudaMalloc((void **)&c2f, sizeof(int) * Vf));
+  QB_CUDA(cudaMemcpy(f2c, h_f2c.data(), sizeof(int) * Vf, cudaMemcpyHostToDevice));
+  QB_CUDA(cudaMemcpy(c2f, h_c2f.data(), sizeof(int) * Vf, cudaMemcpyHostToDevice));
+
+  // V <- null vectors, then block orthonormalisation
+  cudaStream_t s = rt().compute;
+  QB_CUDA(cudaMalloc((void **)&V, v_bytes()));
+  const long nt = 2 * fine.Vh * (Nf / 2);
+  for (int j = 0; j < nvec; j++) {
+    fill_v_kernel<<<div_up(nt, 256), 256, 0, s>>>((float4 *)V, (const float4 *)B[j]->v, fine.Vh, Nf, nvec, j);
+    QB_CHECK_LAUNCH();
+  }
+  block_ortho_kernel<<<dim3((unsigned)Vc, 2), 256, 0, s>>>(V, c2f, fine.Vh, Nf, nvec, block_sites);
+  QB_CHECK_LAUNCH();
+  QB_CUDA(cudaStreamSynchronize(s));
+}
+
+Transfer::~Transfer() {
+  if (V) cudaFree(V);
+  if (f2c) cudaFree(f2c);
+  if (c2f) cudaFree(c2f);
+}
+
+void Transfer::P(SpinorField &fo, const SpinorField &ci) const {
+  if (fo.prec != PREC_SINGLE || ci.prec != PREC_SINGLE) QB_ERROR("Transfer::P works in single precision");
+  if (fo.nparity != 2 || ci.nparity != 2 || fo.Vh != fine.Vh || ci.Vh != coarse.Vh || fo.ncomplex != Nf || ci.ncomplex != 2 * nvec)
+    QB_ERROR("Transfer::P: field geometry mismatch");
+  const long nt = 2 * fine.Vh * (Nf / 2);
+  prolong_kernel<<<div_up(nt, 128), 128, 0, rt().compute>>>((float4 *)fo.v, (const float4 *)ci.v, (const float4 *)V, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2);
+  QB_CHECK_LAUNCH();
+  flops += 8ll * Nf * nvec * fine.V();
+}
+
+void Transfer::R(SpinorField &co, const SpinorField &fi) const {
+  if (co.prec != PREC_SINGLE || fi.prec != PREC_SINGLE) QB_ERROR("Transfer::R works in single precision");
+  if (fi.nparity != 2 || co.nparity != 2 || fi.Vh != fine.Vh || co.Vh != coarse.Vh || fi.ncomplex != Nf || co.ncomplex != 2 * nvec)
+    QB_ERROR("Transfer::R: field geometry mismatch");
+  restrict_kernel<<<(unsigned)coarse.V(), dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, c2f, fine.Vh,
+                                                                                 coarse.Vh, Nf, nvec, Nf / 2, block_sites);
+  QB_CHECK_LAUNCH();
+  flops += 8ll * Nf * nvec * fine.V();
+}
+
+}  // namespace qb

@@ -182,6 +182,9 @@ def load_ref():
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if not (np.iscomplexobj(a) or np.iscomplexobj(b)):
+        a = a.astype(np.float64)
+        b = b.astype(np.float64)
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))

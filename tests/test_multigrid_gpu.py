@@ -1,0 +1,254 @@
+"""GPU tests of the multigrid path through the C ABI (newMultigridQuda / invertQuda) and the test hooks of
+include/quda_b200_ext.h.  Modelled on tests/multigrid_invert_test.cpp (host residual check :529-577) and on
+the identities of MG::verify (lib/multigrid.cpp:372-486).  Oracles:
+  * fine operator: oracle/tm_oracle.c (tm_mat), bit-pinned to the reference's CPU code;
+  * transfer operator / Galerkin coarse operator / Schur complement: numpy restatements below of
+    lib/transfer.cpp:220-258 (geo map), lib/prolongator.cu:41-56, lib/restrictor.cu:90-125,
+    lib/coarse_op.cuh (M_c = R M P) and lib/dirac_coarse.cpp:250-283 (DiracCoarsePC::M).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.oracle_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def load_gauge(q, g, X, prec=8, sloppy=4, precond=4, recon=18, antiperiodic=False):
+    gp = q.gauge_param(X, cuda_prec=prec, reconstruct=recon, cuda_prec_sloppy=sloppy, cuda_prec_precondition=precond,
+                       t_boundary=q.QUDA_ANTI_PERIODIC_T if antiperiodic else q.QUDA_PERIODIC_T)
+    q.lib().loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+
+
+def mg_inv_param(q, kappa, mu, prec=8, sloppy=4, precond=4):
+    p = q.invert_param(kappa=kappa, mu=mu, cuda_prec=prec, solution_type=q.QUDA_MAT_SOLUTION)
+    p.cuda_prec_sloppy = sloppy
+    p.cuda_prec_precondition = precond
+    p.solve_type = q.QUDA_DIRECT_SOLVE
+    p.inv_type = q.QUDA_GCR_INVERTER
+    p.verbosity = q.QUDA_SILENT
+    return p
+
+
+def coords_of(cb, parity, X):
+    za = cb // (X[0] // 2); zb = za // X[1]
+    y = za - zb * X[1]; t = zb // X[2]; z = zb - t * X[2]
+    x = 2 * cb + ((y + z + t + parity) & 1) - za * X[0]
+    return x, y, z, t
+
+
+def full_index(x, y, z, t, X):
+    Vh = X[0] * X[1] * X[2] * X[3] // 2
+    lex = ((t * X[2] + z) * X[1] + y) * X[0] + x
+    return ((x + y + z + t) & 1) * Vh + (lex >> 1)
+
+
+def as_c(a):
+    a = np.asarray(a)
+    return a[..., 0::2] + 1j * a[..., 1::2]
+
+
+def test_transfer_and_galerkin_coarse_operator(quda, oracle):
+    q, L = quda, quda.lib()
+    X = (4, 4, 4, 8)
+    bs = (2, 2, 2, 2)
+    nvec = 4
+    kappa, mu = 0.124, 0.05
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.3, antiperiodic=True, seed=99)
+    load_gauge(q, g, X, antiperiodic=True)
+    ip = mg_inv_param(q, kappa, mu)
+    mgp = q.multigrid_param(ip, n_level=2, geo_block=(bs,), n_vec=(nvec,), setup_maxiter=30, setup_tol=1e-3)
+    mg = L.newMultigridQuda(C.byref(mgp))
+    assert mg and mgp.secs > 0
+    info = (C.c_int * 8)()
+    L.mgLevelInfoQudaB200(mg, 0, info)
+    Xc = tuple(info[0:4]); N = info[7]
+    assert Xc == (2, 2, 2, 4) and info[4] == nvec and info[5] == 12 and info[6] == 16 and N == 2 * nvec
+    Vf, Vc = int(np.prod(X)), int(np.prod(Xc))
+    nf, nc = Vf * 12, Vc * N
+
+    dev = (C.c_double * 3)()
+    L.mgVerifyQudaB200(mg, 0, dev)
+    assert dev[0] < 2e-6 and dev[1] < 2e-5 and dev[2] < 2e-5, list(dev)
+
+    # dense P from unit coarse vectors
+    P = np.zeros((nf, nc), dtype=np.complex128)
+    e = np.zeros(2 * nc, dtype=np.float32)
+    out = np.zeros(2 * nf, dtype=np.float32)
+    for i in range(nc):
+        e[:] = 0; e[2 * i] = 1
+        L.mgProlongQudaB200(mg, 0, vp(out), vp(e))
+        P[:, i] = as_c(out.astype(np.float64))
+    # (a) block orthonormality  P^dag P = 1
+    assert np.abs(P.conj().T @ P - np.eye(nc)).max() < 5e-6
+    # (b) support: column (X, S, j) lives on the aggregate X (coords // block) and chirality S (spin // 2)
+    Vhf, Vhc = Vf // 2, Vc // 2
+    agg = np.zeros(Vf, dtype=np.int64)
+    for par in (0, 1):
+        for cb in range(Vhf):
+            x, y, z, t = coords_of(cb, par, X)
+            agg[par * Vhf + cb] = full_index(x // bs[0], y // bs[1], z // bs[2], t // bs[3], Xc)
+    Pm = np.abs(P).reshape(Vf, 4, 3, Vc, 2, nvec)
+    for s in range(4):
+        for S in range(2):
+            blk = Pm[:, s, :, :, S, :]
+            if S != s // 2:
+                assert blk.max() == 0.0
+            else:
+                mask = (agg[:, None] == np.arange(Vc)[None, :])
+                assert (blk.max(axis=(1, 3))[~mask] == 0).all()
+    # (c) R = P^dag
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal(2 * nf).astype(np.float32)
+    rc = np.zeros(2 * nc, dtype=np.float32)
+    L.mgRestrictQudaB200(mg, 0, vp(rc), vp(v))
+    assert rel_l2(as_c(rc.astype(np.float64)), P.conj().T @ as_c(v.astype(np.float64))) < 5e-6
+    # (d) the null vectors lie in the range of P
+    for k in range(nvec):
+        L.mgNullVectorQudaB200(mg, 0, k, vp(out))
+        b = as_c(out.astype(np.float64))
+        assert np.linalg.norm(P @ (P.conj().T @ b) - b) / np.linalg.norm(b) < 2e-5
+    # (e) Galerkin: M_c = P^dag M P with M the reference CPU operator (oracle tm_mat, fp64)
+    Mc = np.zeros((nc, nc), dtype=np.complex128)
+    oc = np.zeros(2 * nc, dtype=np.float32)
+    for i in range(nc):
+        e[:] = 0; e[2 * i] = 1
+        L.mgMatQudaB200(mg, 1, 0, vp(oc), vp(e))
+        Mc[:, i] = as_c(oc.astype(np.float64))
+    MP = np.zeros((nf, nc), dtype=np.complex128)
+    for i in range(nc):
+        col = np.zeros(2 * nf)
+        col[0::2] = P[:, i].real; col[1::2] = P[:, i].imag
+        MP[:, i] = as_c(oracle.tm_mat(g, col, kappa, mu, 1, 0))
+    ref = P.conj().T @ MP
+    assert np.abs(Mc - ref).max() / np.abs(ref).max() < 1e-5
+    # (f) even-odd preconditioned coarse operator = Schur complement of M_c (uses Xinv)
+    ne = Vhc * N
+    Mee, Meo, Moe, Moo = Mc[:ne, :ne], Mc[:ne, ne:], Mc[ne:, :ne], Mc[ne:, ne:]
+    Xe = np.zeros_like(Mee); Xo = np.zeros_like(Moo)
+    for s in range(Vhc):
+        sl = slice(s * N, (s + 1) * N)
+        Xe[sl, sl] = Mee[sl, sl]; Xo[sl, sl] = Moo[sl, sl]
+    assert np.abs(Mee - Xe).max() < 1e-6 * np.abs(Mee).max()  # same-parity couplings only within a site
+    Mhat = np.eye(ne) - np.linalg.inv(Xe) @ Meo @ np.linalg.inv(Xo) @ Moe
+    vin = rng.standard_normal(2 * ne).astype(np.float32)
+    vout = np.zeros_like(vin)
+    L.mgMatQudaB200(mg, 1, 1, vp(vout), vp(vin))
+    assert rel_l2(as_c(vout.astype(np.float64)), Mhat @ as_c(vin.astype(np.float64))) < 1e-5
+    L.destroyMultigridQuda(mg)
+
+
+def host_residual(oracle, g, x, b, kappa, mu):
+    """|b - M x| / |b| with the reference CPU operator (multigrid_invert_test.cpp:529-577)."""
+    return np.linalg.norm(b - oracle.tm_mat(g, x, kappa, mu, 1, 0)) / np.linalg.norm(b)
+
+
+def point_source(V):
+    b = np.zeros(V * 24)
+    b[0] = 1.0  # first real component, as the reference test's source (multigrid_invert_test.cpp:497-508 sets 12 reals)
+    b[2] = 1.0
+    return b
+
+
+@pytest.mark.parametrize("inv,precond", [("gcr", None), ("bicgstab", None), ("gcr", "mr"), ("mr", None)])
+def test_krylov_solvers_without_multigrid(quda, oracle, inv, precond):
+    """invert_test-style: GCR / BiCGStab / MR, even-odd preconditioned and full, true residual checked on the host."""
+    q, L = quda, quda.lib()
+    X = (8, 8, 8, 8)
+    kappa, mu = 0.12, 0.1
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.3, antiperiodic=True, seed=7)
+    load_gauge(q, g, X, antiperiodic=True)
+    b = oracle.drand(oracle.V * 24, seed=5)
+    for solve_type in (q.QUDA_DIRECT_PC_SOLVE, q.QUDA_DIRECT_SOLVE):
+        p = mg_inv_param(q, kappa, mu)
+        p.solve_type = solve_type
+        p.inv_type = {"gcr": q.QUDA_GCR_INVERTER, "bicgstab": q.QUDA_BICGSTAB_INVERTER, "mr": q.QUDA_MR_INVERTER}[inv]
+        p.inv_type_precondition = q.QUDA_MR_INVERTER if precond == "mr" else q.QUDA_INVALID_INVERTER
+        p.tol = 1e-9 if inv != "mr" else 1e-3
+        p.maxiter = 2000 if inv != "mr" else 300
+        p.gcrNkrylov = 16
+        p.reliable_delta = 1e-4
+        p.maxiter_precondition = 4
+        p.tol_precondition = 0.1
+        p.omega = 1.0
+        x = np.zeros_like(b)
+        L.invertQuda(vp(x), vp(b), C.byref(p))
+        res = host_residual(oracle, g, x, b, kappa, mu)
+        if inv == "mr":
+            assert res < 0.05 and p.iter == 300
+        else:
+            assert res < 5e-9, (inv, precond, solve_type, res, p.true_res)
+            assert abs(p.true_res - res) < 0.5 * res + 1e-10
+        assert p.iter > 0 and p.secs > 0
+
+
+def run_mg_solve(q, oracle, X, blocks, nvecs, n_level, kappa, mu, eps, tol, precond_prec=4, nu=2, setup_maxiter=200):
+    L = q.lib()
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=eps, antiperiodic=False, seed=4711)
+    load_gauge(q, g, X, prec=8, sloppy=4, precond=precond_prec, recon=12)
+    ip = mg_inv_param(q, kappa, mu, precond=precond_prec)
+    mgp = q.multigrid_param(ip, n_level=n_level, geo_block=blocks, n_vec=nvecs, nu_pre=nu, nu_post=nu, setup_maxiter=setup_maxiter, setup_tol=5e-6)
+    mg = L.newMultigridQuda(C.byref(mgp))
+    b = point_source(oracle.V)
+    # outer solve: GCR preconditioned by MG (setInvertParam of the reference test)
+    p = mg_inv_param(q, kappa, mu, precond=precond_prec)
+    p.inv_type_precondition = q.QUDA_MG_INVERTER
+    p.preconditioner = mg
+    p.gcrNkrylov = 20
+    p.tol = tol
+    p.maxiter = 200
+    p.reliable_delta = 1e-4
+    x = np.zeros_like(b)
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    res = host_residual(oracle, g, x, b, kappa, mu)
+    # same solve without the preconditioner
+    p0 = mg_inv_param(q, kappa, mu, precond=precond_prec)
+    p0.gcrNkrylov = 20; p0.tol = tol; p0.maxiter = 4000; p0.reliable_delta = 1e-4
+    x0 = np.zeros_like(b)
+    L.invertQuda(vp(x0), vp(b), C.byref(p0))
+    devs = []
+    for l in range(n_level - 1):
+        dev = (C.c_double * 3)()
+        L.mgVerifyQudaB200(mg, l, dev)
+        devs.append(list(dev))
+    L.destroyMultigridQuda(mg)
+    return res, p.true_res, p.iter, p0.iter, host_residual(oracle, g, x0, b, kappa, mu), devs, mgp.secs, p.secs, p0.secs
+
+
+def test_two_level_mg_gcr_solve(quda, oracle):
+    """BASELINE config 4 in miniature: 2-level MG (4^4 aggregates), twisted mass, MR smoother, K-cycle."""
+    res, true_res, it_mg, it_plain, res_plain, devs, t_setup, t_mg, t_plain = run_mg_solve(
+        quda, oracle, (8, 8, 8, 16), ((4, 4, 4, 4),), (8,), 2, kappa=0.1245, mu=0.005, eps=0.25, tol=1e-8)
+    print(f"2-level: MG iters {it_mg} vs plain GCR {it_plain}; host res {res:.2e} (plain {res_plain:.2e}); setup {t_setup:.2f}s solve {t_mg:.3f}s plain {t_plain:.3f}s")
+    assert res < 5e-8 and abs(true_res - res) < 0.5 * res + 1e-10
+    assert res_plain < 5e-8
+    assert it_mg < it_plain / 3, (it_mg, it_plain)
+    for d in devs:
+        assert d[0] < 5e-6 and d[1] < 1e-4 and d[2] < 5e-5, d
+
+
+def test_three_level_mg_gcr_solve(quda, oracle):
+    """BASELINE config 5 in miniature: 3-level K-cycle, 4^4 then 2^4 aggregates, same true residual as the host check."""
+    res, true_res, it_mg, it_plain, res_plain, devs, t_setup, t_mg, t_plain = run_mg_solve(
+        quda, oracle, (16, 16, 16, 16), ((4, 4, 4, 4), (2, 2, 2, 2)), (8, 8), 3, kappa=0.1248, mu=0.004, eps=0.25, tol=1e-8)
+    print(f"3-level: MG iters {it_mg} vs plain GCR {it_plain}; host res {res:.2e}; setup {t_setup:.2f}s solve {t_mg:.3f}s plain {t_plain:.3f}s")
+    assert res < 5e-8 and abs(true_res - res) < 0.5 * res + 1e-10
+    assert it_mg < it_plain / 3, (it_mg, it_plain)
+    for d in devs:
+        assert d[0] < 5e-6 and d[1] < 1e-4 and d[2] < 5e-5, d
+
+
+def test_mg_half_precision_smoother(quda, oracle):
+    """cuda_prec_precondition = half on the fine level (int16 links and smoother mat-vec), as the reference allows."""
+    res, true_res, it_mg, it_plain, *_ = run_mg_solve(
+        quda, oracle, (8, 8, 8, 16), ((4, 4, 4, 4),), (8,), 2, kappa=0.1245, mu=0.005, eps=0.25, tol=1e-8, precond_prec=2)
+    assert res < 5e-8 and it_mg < it_plain / 3
