@@ -52,6 +52,12 @@ void syncQudaB200(void);
  * by ncclUniqueIdQudaB200 on rank 0 and broadcast by the launcher (torch.distributed, files, ...). */
 void ncclUniqueIdQudaB200(void *unique_id_out_128B);
 void commsBootstrapQudaB200(int rank, int size, const void *unique_id_128B);
+/* info10 = {rank, size, coords[4], grid[4]} after initCommsGridQuda (rank <-> coordinate map is
+ * lexicographic with t fastest, lib/interface_quda.cpp:261-274) */
+void commRankInfoQudaB200(int *info10);
+/* checkerboard index of every site of face `face_num` (0: x_dim = 0, 1: x_dim = X_dim - 1) of the given
+ * parity in face-index order, as used by the pack kernel (cf. indexFromFaceIndex, lib/dslash_index.cuh:13-96) */
+void faceIndexMapQudaB200(int dim, int face_num, int parity, int *h_cb_out);
 /* single-process emulation of a partitioned lattice: halos are packed, "exchanged" with the rank
  * itself and consumed by the boundary kernels (the reference's --partition test trick,
  * tests/test_util.cpp:2047-2065, lib/comm_common.cpp:420-433).  mask bit d = dimension d. */

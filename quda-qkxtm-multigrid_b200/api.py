@@ -135,6 +135,7 @@ EXPORTS = [
     "dslashResidentQudaB200", "matResidentQudaB200", "matDagMatResidentQudaB200", "timeDslashQudaB200",
     "setDslashBlockSizeQudaB200", "kernelLaunchCountQudaB200", "computeStreamQudaB200", "syncQudaB200",
     "ncclUniqueIdQudaB200", "commsBootstrapQudaB200", "commDimPartitionedSetQudaB200",
+    "commRankInfoQudaB200", "faceIndexMapQudaB200",
     "mgVerifyQudaB200", "mgLevelInfoQudaB200", "mgProlongQudaB200", "mgRestrictQudaB200", "mgMatQudaB200",
     "mgNullVectorQudaB200", "mgCycleQudaB200",
 ]
@@ -188,6 +189,8 @@ def lib():
     L.ncclUniqueIdQudaB200.argtypes = [_p]
     L.commsBootstrapQudaB200.argtypes = [_i, _i, _p]
     L.commDimPartitionedSetQudaB200.argtypes = [_i]
+    L.commRankInfoQudaB200.argtypes = [C.POINTER(_i)]
+    L.faceIndexMapQudaB200.argtypes = [_i, _i, _i, C.POINTER(_i)]
     L.mgVerifyQudaB200.argtypes = [_p, _i, C.POINTER(_d)]
     L.mgLevelInfoQudaB200.argtypes = [_p, _i, C.POINTER(_i)]
     L.mgProlongQudaB200.argtypes = [_p, _i, _p, _p]

@@ -73,6 +73,7 @@ void comm_bootstrap(int rank, int size, const void *unique_id128) {
   r.rank = rank;
   r.size = size;
   if (size == 1) return;
+  if (!unique_id128) return;  // bookkeeping only (CPU tests of the rank grid): any exchange will fail loudly
   if (!r.device_ready) QB_ERROR("call initQudaDevice before commsBootstrapQudaB200 (the NCCL communicator binds to the current device)");
   load_nccl();
   ncclUniqueId id;
@@ -153,6 +154,7 @@ void comm_sendrecv(const void *sendbuf, int to_rank, void *recvbuf, int from_ran
 void comm_exchange_halo(Lattice &lat, int pi, cudaStream_t s) {
   Runtime &r = rt();
   if (r.size == 1) return;
+  if (!comm) QB_ERROR("halo exchange requested but the NCCL communicator was not created (commsBootstrapQudaB200 without a unique id)");
   const Geom &g = lat.geom;
   char *send = (char *)lat.send_arena[pi], *recv = (char *)lat.recv_arena[pi];
   QB_NCCL(nccl.GroupStart());

@@ -28,6 +28,8 @@ struct Lattice {
   int *interior_list[2] = {nullptr, nullptr};  // device, cb sites of parity p with no partitioned-boundary hop
   int *boundary_list[2] = {nullptr, nullptr};
   int n_interior[2] = {0, 0}, n_boundary[2] = {0, 0};
+  bool interior_contiguous[2] = {false, false};
+  int interior_begin[2] = {0, 0};
   // halo arenas per storage precision index (0: double, 1: single, 2: half)
   void *send_arena[3] = {nullptr, nullptr, nullptr};
   void *recv_arena[3] = {nullptr, nullptr, nullptr};
@@ -46,6 +48,8 @@ struct Lattice {
 // run on rt().halo concurrently with the interior kernel, then the boundary sites are completed.
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
                TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx);
+
+void face_index_map(const Lattice &lat, int mu, int face_num, int parity, int *h_out);
 
 // out = (p + i q gamma5) in on every site of the field
 void apply_twist_field(SpinorField &out, const SpinorField &in, TwistCoef c);

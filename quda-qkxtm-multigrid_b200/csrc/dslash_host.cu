@@ -77,6 +77,9 @@ void Lattice::setup_partition() {
     }
     n_interior[p] = (int)in_l.size();
     n_boundary[p] = (int)bd_l.size();
+    // a T-only (or any slowest-dimension-only) split leaves the interior as one contiguous cb range: no index list needed
+    interior_contiguous[p] = !in_l.empty() && in_l.back() - in_l.front() + 1 == (int)in_l.size();
+    interior_begin[p] = in_l.empty() ? 0 : in_l.front();
     if (n_interior[p]) {
       QB_CUDA(cudaMalloc((void **)&interior_list[p], sizeof(int) * n_interior[p]));
       QB_CUDA(cudaMemcpy(interior_list[p], in_l.data(), sizeof(int) * n_interior[p], cudaMemcpyHostToDevice));
@@ -177,27 +180,31 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   }
   pk.thread_off[4] = off;
 
-  // halo stream: wait until `in` is complete on the compute stream, pack, exchange
+  // halo stream (high priority): wait until `in` is complete on the compute stream, pack, exchange, and then
+  // compute the boundary sites right there -- they are few (2 faces of X*Y*Z/2 sites for a T split), so
+  // the launch is latency-bound and hides completely under the interior kernel running on the compute stream.
+  // Interior and boundary launches write disjoint sites of `out`.
   QB_CUDA(cudaEventRecord(r.ev_in_ready, r.compute));
   QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_in_ready, 0));
   launch_pack_T<Store>(pk, twist_in, r.halo);
   if (!self) comm_exchange_halo(lat, pi, r.halo);
+
+  const int np = parity;
+  DslashParam pb = p;
+  if (lat.n_boundary[np]) {
+    pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
+    launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, block, r.halo);
+  }
   QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
 
-  // interior sites overlap with the exchange
-  const int np = parity;
+  // interior sites: everything that needs no remote data, overlapping with pack + exchange + boundary
   if (lat.n_interior[np]) {
-    p.site_begin = 0; p.site_count = lat.n_interior[np]; p.site_list = lat.interior_list[np];
+    p.site_count = lat.n_interior[np];
+    if (lat.interior_contiguous[np]) { p.site_begin = lat.interior_begin[np]; p.site_list = nullptr; }
+    else { p.site_begin = 0; p.site_list = lat.interior_list[np]; }
     launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, r.compute);
   }
   QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
-  if (lat.n_boundary[np]) {
-    p.site_begin = 0; p.site_count = lat.n_boundary[np]; p.site_list = lat.boundary_list[np];
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, r.compute);
-  }
-  // the next pack must not overwrite the send buffers before the boundary kernel (self mode reads them)
-  QB_CUDA(cudaEventRecord(r.ev_pack_ready, r.compute));
-  QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_pack_ready, 0));
 }
 
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
@@ -209,6 +216,30 @@ void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const Sp
   if (out.prec == PREC_DOUBLE) hop_T<StoreD>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
   else if (out.prec == PREC_SINGLE) hop_T<StoreS>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
   else hop_T<StoreH>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
+}
+
+// face index -> checkerboard index table of the pack kernel (for the index-parity tests)
+__global__ void face_map_kernel(int *out, Geom g, int mu, int face_num, int parity) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.faceVh[mu]) return;
+  const int slice = face_num ? g.X[mu] - 1 : 0;
+  int cb;
+  if (mu == 0) cb = face_to_cb<0>(f, slice, parity, g);
+  else if (mu == 1) cb = face_to_cb<1>(f, slice, parity, g);
+  else if (mu == 2) cb = face_to_cb<2>(f, slice, parity, g);
+  else cb = face_to_cb<3>(f, slice, parity, g);
+  out[f] = cb;
+}
+
+void face_index_map(const Lattice &lat, int mu, int face_num, int parity, int *h_out) {
+  const int n = lat.geom.faceVh[mu];
+  int *d;
+  QB_CUDA(cudaMalloc((void **)&d, sizeof(int) * n));
+  face_map_kernel<<<div_up(n, 128), 128, 0, rt().compute>>>(d, lat.geom, mu, face_num, parity);
+  QB_CHECK_LAUNCH();
+  QB_CUDA(cudaMemcpyAsync(h_out, d, sizeof(int) * n, cudaMemcpyDeviceToHost, rt().compute));
+  QB_CUDA(cudaStreamSynchronize(rt().compute));
+  QB_CUDA(cudaFree(d));
 }
 
 void apply_twist_field(SpinorField &out, const SpinorField &in, TwistCoef c) {

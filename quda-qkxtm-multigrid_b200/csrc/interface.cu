@@ -562,6 +562,16 @@ long long kernelLaunchCountQudaB200(void) { return rt().launches; }
 void *computeStreamQudaB200(void) { return (void *)rt().compute; }
 void syncQudaB200(void) { QB_CUDA(cudaDeviceSynchronize()); }
 
+void faceIndexMapQudaB200(int dim, int face_num, int parity, int *h_cb_out) {
+  require_gauge();
+  if (dim < 0 || dim > 3 || (face_num != 0 && face_num != 1) || (parity != 0 && parity != 1)) QB_ERROR("faceIndexMapQudaB200: bad arguments");
+  face_index_map(G.lat, dim, face_num, parity, h_cb_out);
+}
+void commRankInfoQudaB200(int *info10) {
+  Runtime &r = rt();
+  info10[0] = r.rank; info10[1] = r.size;
+  for (int d = 0; d < 4; d++) { info10[2 + d] = r.coord[d]; info10[6 + d] = r.grid[d]; }
+}
 void ncclUniqueIdQudaB200(void *out) { comm_unique_id(out); }
 void commsBootstrapQudaB200(int rank, int size, const void *id) { comm_bootstrap(rank, size, id); }
 void commDimPartitionedSetQudaB200(int mask) {
