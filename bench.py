@@ -90,6 +90,71 @@ def make_inputs(oracle, X, seed):
     return g, sp
 
 
+def run_mg_leg(q, L, oracle, X):
+    """Second half of the BASELINE metric: 3-level MG-GCR twisted-mass solve (seconds), plus the coarse-operator
+    kernels against their HBM roofline.  32^3x64, 4^4 then 2^4 aggregates, 24 vectors per level, MR(2,2) smoother,
+    K-cycle, fp64 outer GCR(20) / fp32 MG / int16 level-0 smoother, weak-field SU(3) gauge (periodic)."""
+    kappa, mu = 0.1248, 0.004
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711)
+    gp = q.gauge_param(X, cuda_prec=8, reconstruct=12, cuda_prec_sloppy=4, cuda_prec_precondition=2, t_boundary=q.QUDA_PERIODIC_T)
+    L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+
+    def inv_param():
+        p = q.invert_param(kappa=kappa, mu=mu, cuda_prec=8, solution_type=q.QUDA_MAT_SOLUTION)
+        p.cuda_prec_sloppy = 4
+        p.cuda_prec_precondition = 2
+        p.solve_type = q.QUDA_DIRECT_SOLVE
+        p.inv_type = q.QUDA_GCR_INVERTER
+        p.gcrNkrylov = 20
+        p.tol = 1e-9
+        p.maxiter = 5000
+        p.reliable_delta = 1e-4
+        return p
+
+    ip = inv_param()
+    mgp = q.multigrid_param(ip, n_level=3, geo_block=((4, 4, 4, 4), (2, 2, 2, 2)), n_vec=(24, 24), nu_pre=2, nu_post=2,
+                            setup_maxiter=500, setup_tol=5e-6, run_verify=False)
+    t0 = time.perf_counter()
+    mg = L.newMultigridQuda(C.byref(mgp))
+    setup_s = time.perf_counter() - t0
+    V = oracle.V
+    b = np.zeros(V * 24)
+    b[0:24:2] = 1.0  # point source on the first site (multigrid_invert_test.cpp:497-508)
+    x = np.zeros_like(b)
+    p = inv_param()
+    p.inv_type_precondition = q.QUDA_MG_INVERTER
+    p.preconditioner = mg
+    L.invertQuda(vp(x), vp(b), C.byref(p))  # warm-up (allocations)
+    p.iter = 0
+    t0 = time.perf_counter()
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    wall_s = time.perf_counter() - t0
+    p0 = inv_param()
+    x0 = np.zeros_like(b)
+    L.invertQuda(vp(x0), vp(b), C.byref(p0))
+    res = {"lattice": list(X), "levels": 3, "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
+           "setup_seconds": setup_s, "solve_seconds": p.secs, "solve_wall_seconds_incl_h2d_d2h": wall_s, "iterations": p.iter,
+           "true_res": p.true_res, "tol": 1e-9, "plain_gcr_seconds": p0.secs, "plain_gcr_iterations": p0.iter, "plain_gcr_true_res": p0.true_res}
+    peaks, _ = measured_peaks()
+    for lvl in (1, 2):
+        info = (C.c_int * 8)()
+        L.mgLevelInfoQudaB200(mg, lvl - 1, info)
+        sites = int(np.prod(info[0:4]))
+        N = info[7]
+        ms = L.mgTimeQudaB200(mg, lvl, 0, 50)
+        byts = sites * (9 * N * N * 8 + 10 * N * 8)
+        flops = sites * ((8 + 1) * 8 * N * N - 2 * N)
+        res[f"coarse_dslash_level{lvl}"] = {"sites": sites, "N": N, "ms": ms, "gflops": flops / ms / 1e6, "hbm_gbs": byts / ms / 1e6,
+                                            "roofline_frac": byts / ms / 1e6 / peaks["hbm_gbs"], "bytes": byts}
+    for what, name in ((2, "prolong"), (3, "restrict")):
+        ms = L.mgTimeQudaB200(mg, 0, what, 50)
+        byts = V * (8 * 12 * 24 + 96)
+        res[f"{name}_level0"] = {"ms": ms, "hbm_gbs": byts / ms / 1e6, "roofline_frac": byts / ms / 1e6 / peaks["hbm_gbs"]}
+    L.destroyMultigridQuda(mg)
+    return res
+
+
 def cpu_baseline_port(oracle, g, sp, budget_s=12.0):
     """Oracle (OpenMP port) on the full 32^3x64 workload in fp32, bounded to ~budget_s seconds."""
     cores = os.cpu_count() or 1
@@ -181,6 +246,7 @@ def main():
     ap.add_argument("--recon", type=int, default=12, choices=[8, 12, 18])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the half-precision extra measurement")
+    ap.add_argument("--no-mg", action="store_true", help="skip the 3-level MG-GCR solve leg (N=1 only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -268,6 +334,9 @@ def main():
     if not args.no_extra and args.prec == 4:
         half = run_config(2, 12, args.steps, args.warmup, False)
         extra["half_r12"] = half
+    mg_res = None
+    if world == 1 and not args.no_mg and not args.no_extra:
+        mg_res = run_mg_leg(q, L, oracle, X)
     sampler.stop_flag = True
 
     # max over ranks of the device time
@@ -317,6 +386,8 @@ def main():
             "cpu_baseline": cpu,
             "extra": {},
         }
+        if mg_res:
+            line["extra"]["mg_gcr_3level"] = mg_res
         if half_ms:
             line["extra"]["half_r12"] = {"ms_per_step": half_ms, "gflops": FLOPS_PER_SITE * sites / (half_ms * 1e-3) / 1e9,
                                          "hbm_gbs_compulsory": 296 * Vh / (half_ms * 1e-3) / 1e9,

@@ -63,6 +63,12 @@ void faceIndexMapQudaB200(int dim, int face_num, int parity, int *h_cb_out);
  * tests/test_util.cpp:2047-2065, lib/comm_common.cpp:420-433).  mask bit d = dimension d. */
 void commDimPartitionedSetQudaB200(int mask);
 
+/* --- BLAS-1 / reduction test hook (the reference drives these through tests/blas_test.cu) -------------
+ * name = a function of quda::blas (include/blas_quda.h:33-144): "axpy", "caxpy", "cDotProductNormA", ...;
+ * x, y, z, w: host arrays of n complex numbers of `prec` bytes per real (updated in place), coef = {a_re, a_im,
+ * b_re, b_im}.  Returns how many doubles were written to result. */
+int blasQudaB200(const char *name, long n, int prec, const double *coef, void *x, void *y, void *z, void *w, double *result);
+
 /* --- multigrid introspection (what MG::verify, lib/multigrid.cpp:372-486, checks inside the library) ----
  * `mg` is the handle returned by newMultigridQuda; level 0 is the fine grid.  Generic host field order:
  * [parity][checkerboard site][component k = spin * nColor + colour][re, im], float32. */
@@ -75,6 +81,9 @@ void mgRestrictQudaB200(void *mg, int level, float *h_coarse_out, const float *h
 /* operator of a level: pc = 0 the full operator (level 0: fine M, level >= 1: coarse M_c), pc = 1 the smoother's operator */
 void mgMatQudaB200(void *mg, int level, int pc, float *h_out, const float *h_in);
 void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out);
+/* mean device time in ms (CUDA events on the compute stream) of `niter` applications on level `level` of
+ * what = 0: full operator, 1: smoother operator, 2: prolongator, 3: restrictor */
+double mgTimeQudaB200(void *mg, int level, int what, int niter);
 /* one multigrid cycle of level `level`:  x = MG(b) */
 void mgCycleQudaB200(void *mg, int level, float *h_x, const float *h_b);
 

@@ -136,8 +136,8 @@ EXPORTS = [
     "setDslashBlockSizeQudaB200", "kernelLaunchCountQudaB200", "computeStreamQudaB200", "syncQudaB200",
     "ncclUniqueIdQudaB200", "commsBootstrapQudaB200", "commDimPartitionedSetQudaB200",
     "commRankInfoQudaB200", "faceIndexMapQudaB200",
-    "mgVerifyQudaB200", "mgLevelInfoQudaB200", "mgProlongQudaB200", "mgRestrictQudaB200", "mgMatQudaB200",
-    "mgNullVectorQudaB200", "mgCycleQudaB200",
+    "blasQudaB200", "mgVerifyQudaB200", "mgLevelInfoQudaB200", "mgProlongQudaB200", "mgRestrictQudaB200", "mgMatQudaB200",
+    "mgNullVectorQudaB200", "mgCycleQudaB200", "mgTimeQudaB200",
 ]
 
 _lib = None
@@ -191,6 +191,7 @@ def lib():
     L.commDimPartitionedSetQudaB200.argtypes = [_i]
     L.commRankInfoQudaB200.argtypes = [C.POINTER(_i)]
     L.faceIndexMapQudaB200.argtypes = [_i, _i, _i, C.POINTER(_i)]
+    L.blasQudaB200.argtypes = [C.c_char_p, C.c_long, _i, C.POINTER(_d), _p, _p, _p, _p, C.POINTER(_d)]
     L.mgVerifyQudaB200.argtypes = [_p, _i, C.POINTER(_d)]
     L.mgLevelInfoQudaB200.argtypes = [_p, _i, C.POINTER(_i)]
     L.mgProlongQudaB200.argtypes = [_p, _i, _p, _p]
@@ -198,6 +199,8 @@ def lib():
     L.mgMatQudaB200.argtypes = [_p, _i, _i, _p, _p]
     L.mgNullVectorQudaB200.argtypes = [_p, _i, _i, _p]
     L.mgCycleQudaB200.argtypes = [_p, _i, _p, _p]
+    L.mgTimeQudaB200.argtypes = [_p, _i, _i, _i]
+    L.mgTimeQudaB200.restype = _d
     _lib = L
     return L
 
@@ -266,7 +269,7 @@ def invert_param(kappa=0.1, mu=0.01, flavor=QUDA_TWIST_PLUS, dslash_type=QUDA_TW
 
 def multigrid_param(inv_param, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(24,), nu_pre=2, nu_post=2,
                     smoother_tol=0.25, omega=0.85, setup_maxiter=500, setup_tol=5e-6,
-                    cycle=QUDA_MG_CYCLE_RECURSIVE, generate_all_levels=True):
+                    cycle=QUDA_MG_CYCLE_RECURSIVE, generate_all_levels=True, run_verify=True):
     """What tests/multigrid_invert_test.cpp:161-286 (setMultigridParam) fills in.
     `inv_param` must stay alive as long as the returned struct is used."""
     m = lib().newQudaMultigridParam()
@@ -291,7 +294,7 @@ def multigrid_param(inv_param, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(24,)
     m.smoother[n_level - 1] = QUDA_GCR_INVERTER
     m.compute_null_vector = QUDA_COMPUTE_NULL_VECTOR_YES
     m.generate_all_levels = QUDA_BOOLEAN_YES if generate_all_levels else QUDA_BOOLEAN_NO
-    m.run_verify = QUDA_BOOLEAN_YES
+    m.run_verify = QUDA_BOOLEAN_YES if run_verify else QUDA_BOOLEAN_NO
     m.setup_maxiter = setup_maxiter
     m.setup_tol = setup_tol
     m.delta_muPR = 1.0

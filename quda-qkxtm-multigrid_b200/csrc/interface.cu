@@ -4,6 +4,7 @@
 #include <climits>
 #include <chrono>
 #include <map>
+#include <string>
 #include <vector>
 #include "../../include/quda.h"
 #include "blas.h"
@@ -795,6 +796,7 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   mp.compute_null_vector = mgp->compute_null_vector == QUDA_COMPUTE_NULL_VECTOR_YES;
   mp.generate_all_levels = mgp->generate_all_levels == QUDA_BOOLEAN_YES;
   mp.verbosity = r.verbosity;
+  mp.keep_null_vectors = mgp->run_verify == QUDA_BOOLEAN_YES;  // needed by mgVerifyQudaB200 / mgNullVectorQudaB200 only
   if (!mp.compute_null_vector) QB_ERROR("compute_null_vector = NO needs vec_infile, which requires QIO (not available); generate the null vectors");
 
   // fine operators: residual = full operator in the MG working precision (fp32 vectors); smoother = even-odd
@@ -884,6 +886,36 @@ void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out) {
   if (k < 0 || k >= (int)m->B.size()) QB_ERROR("null vector index %d out of range", k);
   export_generic(h_out, *m->B[k], rt().compute);
 }
+// mean device time (ms, CUDA events on the compute stream) of `niter` applications of a level's operator / transfer:
+// what = 0: full operator M, 1: smoother operator, 2: prolongator, 3: restrictor (of the transfer *from* this level)
+double mgTimeQudaB200(void *mg, int level, int what, int niter) {
+  MG *m = mg_level(mg, level);
+  Runtime &r = rt();
+  const Dirac *d = what == 1 ? m->matSmooth : m->matResidual;
+  std::unique_ptr<SpinorField> in(d->new_field(PREC_SINGLE)), out(d->new_field(PREC_SINGLE)), c;
+  random_fill(*in, 99);
+  if (what >= 2) {
+    if (!m->transfer) QB_ERROR("level %d has no transfer operator", level);
+    c.reset(m->transfer->new_coarse_field());
+    random_fill(*c, 98);
+  }
+  auto apply = [&]() {
+    if (what <= 1) d->M(*out, *in);
+    else if (what == 2) m->transfer->P(*out, *c);
+    else m->transfer->R(*c, *in);
+  };
+  for (int i = 0; i < 3; i++) apply();
+  cudaEvent_t e0, e1;
+  QB_CUDA(cudaEventCreate(&e0)); QB_CUDA(cudaEventCreate(&e1));
+  QB_CUDA(cudaEventRecord(e0, r.compute));
+  for (int i = 0; i < niter; i++) apply();
+  QB_CUDA(cudaEventRecord(e1, r.compute));
+  QB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  QB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return (double)ms / niter;
+}
 // one multigrid cycle on level `level`: x = MG(b)
 void mgCycleQudaB200(void *mg, int level, float *h_x, const float *h_b) {
   MG *m = mg_level(mg, level);
@@ -894,3 +926,66 @@ void mgCycleQudaB200(void *mg, int level, float *h_x, const float *h_b) {
 }
 
 }  // extern "C"
+
+// ---- BLAS / reduction test hook (what tests/blas_test.cu drives inside the reference) ------------------------
+// Operands are flat arrays of n complex numbers in precision `prec` (4 or 8 bytes per real), n % 12 == 0.
+// coef = {a_re, a_im, b_re, b_im}; result receives up to 3 doubles.  Returns the number of result doubles.
+extern "C" int blasQudaB200(const char *name, long n, int prec, const double *coef, void *x, void *y, void *z, void *w, double *result) {
+  require_init();
+  using namespace qb::blas;
+  if (n <= 0 || n % 12) QB_ERROR("blasQudaB200: n must be a positive multiple of 12");
+  const Prec pr = to_prec((QudaPrecision)prec, "prec");
+  if (pr == PREC_HALF) QB_ERROR("blasQudaB200: single or double precision only");
+  const long Vh = n / 12;
+  const size_t bytes = (size_t)n * 2 * (int)pr;
+  SpinorField fx(Vh, 1, pr), fy(Vh, 1, pr), fz(Vh, 1, pr), fw(Vh, 1, pr);
+  cudaStream_t s = rt().compute;
+  void *hp[4] = {x, y, z, w};
+  SpinorField *fp[4] = {&fx, &fy, &fz, &fw};
+  for (int i = 0; i < 4; i++)
+    if (hp[i]) QB_CUDA(cudaMemcpyAsync(fp[i]->v, hp[i], bytes, cudaMemcpyHostToDevice, s));
+  const double a = coef[0];
+  const Complex ca(coef[0], coef[1]), cb(coef[2], coef[3]);
+  const std::string nm(name);
+  int nres = 0;
+  if (nm == "ax") ax(a, fx);
+  else if (nm == "axpy") axpy(a, fx, fy);
+  else if (nm == "xpy") xpy(fx, fy);
+  else if (nm == "xpay") xpay(fx, a, fy);
+  else if (nm == "mxpy") mxpy(fx, fy);
+  else if (nm == "axpby") axpby(a, fx, coef[2], fy);
+  else if (nm == "caxpy") caxpy(ca, fx, fy);
+  else if (nm == "caxpby") caxpby(ca, fx, cb, fy);
+  else if (nm == "cxpaypbz") cxpaypbz(fx, ca, fy, cb, fz);
+  else if (nm == "caxpbypz") caxpbypz(ca, fx, cb, fy, fz);
+  else if (nm == "caxpbypzYmbw") caxpbypzYmbw(ca, fx, cb, fy, fz, fw);
+  else if (nm == "cabxpyAx") cabxpyAx(a, cb, fx, fy);
+  else if (nm == "caxpyXmaz") caxpyXmaz(ca, fx, fy, fz);
+  else if (nm == "norm2") { result[0] = norm2(fx); nres = 1; }
+  else if (nm == "reDotProduct") { result[0] = reDotProduct(fx, fy); nres = 1; }
+  else if (nm == "cDotProduct") { Complex c = cDotProduct(fx, fy); result[0] = c.real(); result[1] = c.imag(); nres = 2; }
+  else if (nm == "cDotProductNormA") { double3_ d = cDotProductNormA(fx, fy); result[0] = d.x; result[1] = d.y; result[2] = d.z; nres = 3; }
+  else if (nm == "cDotProductNormB") { double3_ d = cDotProductNormB(fx, fy); result[0] = d.x; result[1] = d.y; result[2] = d.z; nres = 3; }
+  else if (nm == "axpyNorm") { result[0] = axpyNorm(a, fx, fy); nres = 1; }
+  else if (nm == "xmyNorm") { result[0] = xmyNorm(fx, fy); nres = 1; }
+  else if (nm == "caxpyNorm") { result[0] = caxpyNorm(ca, fx, fy); nres = 1; }
+  else if (nm == "cabxpyAxNorm") { result[0] = cabxpyAxNorm(a, cb, fx, fy); nres = 1; }
+  else if (nm == "caxpyDotzy") { Complex c = caxpyDotzy(ca, fx, fy, fz); result[0] = c.real(); result[1] = c.imag(); nres = 2; }
+  else if (nm == "caxpyXmazNormX") { result[0] = caxpyXmazNormX(ca, fx, fy, fz); nres = 1; }
+  else if (nm == "xpaycDotzy") { Complex c = xpaycDotzy(fx, a, fy, fz); result[0] = c.real(); result[1] = c.imag(); nres = 2; }
+  else if (nm == "block_cDotProduct") {  // (x,w), (y,w), (z,w)
+    std::vector<SpinorField *> v{&fx, &fy, &fz};
+    Complex r3[3];
+    cDotProduct(r3, v, fw);
+    for (int i = 0; i < 3; i++) { result[2 * i] = r3[i].real(); result[2 * i + 1] = r3[i].imag(); }
+    nres = 6;
+  } else if (nm == "block_caxpy") {  // w += a x + b y + conj(a) z
+    std::vector<SpinorField *> v{&fx, &fy, &fz};
+    Complex c3[3] = {ca, cb, std::conj(ca)};
+    caxpy(c3, v, fw);
+  } else QB_ERROR("blasQudaB200: unknown operation %s", name);
+  for (int i = 0; i < 4; i++)
+    if (hp[i]) QB_CUDA(cudaMemcpyAsync(hp[i], fp[i]->v, bytes, cudaMemcpyDeviceToHost, s));
+  QB_CUDA(cudaStreamSynchronize(s));
+  return nres;
+}

@@ -124,6 +124,7 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
         transfer->R(*Bc.back(), *B[i]);
       }
     }
+    if (!mp.keep_null_vectors) B.clear();
     coarse.reset(new MG(mp, level + 1, coarseResidual.get(), coarseSmooth.get(), Bc.empty() ? nullptr : &Bc));
 
     // ---- coarse solver: the next level's cycle, wrapped in GCR(10) for a K-cycle (multigrid.cpp:225-275) ----
@@ -246,6 +247,7 @@ void MG::verify(double *dev) {
   transfer->R(*t_c, *t_f);
   dev[0] = sqrt(blas::xmyNorm(*eta, *t_c) / blas::norm2(*eta));
   // (2) P R v_k = v_k for the null vectors
+  if (B.empty()) dev[1] = -1.0;  // null vectors were released (run_verify off)
   for (size_t k = 0; k < B.size() && (int)k < mp.level[level].nvec; k++) {
     transfer->R(*t_c, *B[k]);
     transfer->P(*t_f, *t_c);

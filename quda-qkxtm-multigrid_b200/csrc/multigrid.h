@@ -31,6 +31,7 @@ struct MGParam {
   bool compute_null_vector = true;
   bool generate_all_levels = true;
   int verbosity = 1;
+  bool keep_null_vectors = true;  // false: free the near-null vectors of a level once V and the coarse vectors exist (24 x 96 B/site)
 };
 
 class MG : public Solver {

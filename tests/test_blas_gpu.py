@@ -1,0 +1,100 @@
+"""GPU parity tests of the BLAS-1 / reduction kernels used by GCR / MR / BiCGStab, in the style of the reference's
+tests/blas_test.cu (same operation on the host, relative error of norms <= 1e-11 double / 1e-5 single,
+blas_test.cu:453, :952-962).  Oracle: numpy complex128 restatement of the functor bodies of
+lib/blas_quda.cu:109-692 and lib/reduce_quda.cu:166-849."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+A, B = 0.37 - 1.21j, -0.58 + 0.44j
+
+
+def run(L, name, prec, x, y, z, w):
+    dt = np.float64 if prec == 8 else np.float32
+    arrs = []
+    for v in (x, y, z, w):
+        f = np.empty(2 * v.size, dtype=dt)
+        f[0::2] = v.real; f[1::2] = v.imag
+        arrs.append(f)
+    coef = (C.c_double * 4)(A.real, A.imag, B.real, B.imag)
+    res = (C.c_double * 8)()
+    n = L.blasQudaB200(name.encode(), x.size, prec, coef, *[a.ctypes.data_as(C.c_void_p) for a in arrs], res)
+    back = [a[0::2].astype(np.float64) + 1j * a[1::2].astype(np.float64) for a in arrs]
+    return back, list(res)[:n]
+
+
+def host(name, x, y, z, w):
+    a, b, ar, br = A, B, A.real, B.real
+    r = None
+    if name == "ax": x = ar * x
+    elif name == "axpy": y = y + ar * x
+    elif name == "xpy": y = y + x
+    elif name == "xpay": y = x + ar * y
+    elif name == "mxpy": y = y - x
+    elif name == "axpby": y = ar * x + br * y
+    elif name == "caxpy": y = y + a * x
+    elif name == "caxpby": y = a * x + b * y
+    elif name == "cxpaypbz": z = x + a * y + b * z
+    elif name == "caxpbypz": z = z + a * x + b * y
+    elif name == "caxpbypzYmbw": z = z + a * x + b * y; y = y - b * w
+    elif name == "cabxpyAx": y = y + ar * b * x; x = ar * x
+    elif name == "caxpyXmaz": y = y + a * x; x = x - a * z
+    elif name == "norm2": r = [np.vdot(x, x).real]
+    elif name == "reDotProduct": r = [np.vdot(x, y).real]
+    elif name == "cDotProduct": d = np.vdot(x, y); r = [d.real, d.imag]
+    elif name == "cDotProductNormA": d = np.vdot(x, y); r = [d.real, d.imag, np.vdot(x, x).real]
+    elif name == "cDotProductNormB": d = np.vdot(x, y); r = [d.real, d.imag, np.vdot(y, y).real]
+    elif name == "axpyNorm": y = y + ar * x; r = [np.vdot(y, y).real]
+    elif name == "xmyNorm": y = x - y; r = [np.vdot(y, y).real]
+    elif name == "caxpyNorm": y = y + a * x; r = [np.vdot(y, y).real]
+    elif name == "cabxpyAxNorm": y = y + ar * b * x; x = ar * x; r = [np.vdot(y, y).real]
+    elif name == "caxpyDotzy": y = y + a * x; d = np.vdot(z, y); r = [d.real, d.imag]
+    elif name == "caxpyXmazNormX": y = y + a * x; x = x - a * z; r = [np.vdot(x, x).real]
+    elif name == "xpaycDotzy": y = x + ar * y; d = np.vdot(z, y); r = [d.real, d.imag]
+    elif name == "block_cDotProduct":
+        r = []
+        for v in (x, y, z):
+            d = np.vdot(v, w); r += [d.real, d.imag]
+    elif name == "block_caxpy": w = w + a * x + b * y + np.conj(a) * z
+    else: raise KeyError(name)
+    return [x, y, z, w], r
+
+
+OPS = ["ax", "axpy", "xpy", "xpay", "mxpy", "axpby", "caxpy", "caxpby", "cxpaypbz", "caxpbypz", "caxpbypzYmbw", "cabxpyAx",
+       "caxpyXmaz", "norm2", "reDotProduct", "cDotProduct", "cDotProductNormA", "cDotProductNormB", "axpyNorm", "xmyNorm",
+       "caxpyNorm", "cabxpyAxNorm", "caxpyDotzy", "caxpyXmazNormX", "xpaycDotzy", "block_cDotProduct", "block_caxpy"]
+
+
+@pytest.mark.parametrize("prec", [8, 4])
+@pytest.mark.parametrize("n", [12, 12 * 1000, 12 * 70001])
+def test_blas_against_host(quda, prec, n):
+    L = quda.lib()
+    rng = np.random.default_rng(n + prec)
+    vecs = [rng.standard_normal(n) + 1j * rng.standard_normal(n) for _ in range(4)]
+    if prec == 4:
+        vecs = [v.astype(np.complex64).astype(np.complex128) for v in vecs]
+    tol = 1e-11 if prec == 8 else 1e-5
+    for name in OPS:
+        got, res = run(L, name, prec, *vecs)
+        want, wres = host(name, *vecs)
+        for g, h in zip(got, want):
+            assert abs(np.linalg.norm(g) - np.linalg.norm(h)) <= tol * np.linalg.norm(h), name
+            assert np.linalg.norm(g - h) <= 10 * tol * np.linalg.norm(h), name
+        if wres is not None:
+            scale = np.linalg.norm(vecs[0]) * np.linalg.norm(vecs[1]) if n > 12 else 50.0
+            assert len(res) == len(wres), name
+            for a, b in zip(res, wres):
+                assert abs(a - b) <= tol * max(abs(b), scale), (name, a, b)
+
+
+def test_reductions_are_deterministic(quda):
+    L = quda.lib()
+    rng = np.random.default_rng(3)
+    n = 12 * 50000
+    vecs = [rng.standard_normal(n) + 1j * rng.standard_normal(n) for _ in range(4)]
+    first = run(L, "cDotProductNormA", 4, *vecs)[1]
+    for _ in range(5):
+        assert run(L, "cDotProductNormA", 4, *vecs)[1] == first
