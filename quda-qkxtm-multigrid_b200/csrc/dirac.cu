@@ -61,6 +61,13 @@ void DiracTM::Dslash(SpinorField &out, const SpinorField &in, int parity) const 
   flops += 1392ll * in.Vh;
 }
 
+void DiracTM::DslashRange(SpinorField &out, const SpinorField &in, int parity, int begin, int count, cudaStream_t s) const {
+  if (flavor == 0) apply_hop_range(*lat, *gauge, out, in, parity, dagger, TwistCoef(), TwistCoef(), nullptr, TwistCoef(), begin, count, s);
+  else if (!dagger || !symmetric()) apply_hop_range(*lat, *gauge, out, in, parity, dagger, TwistCoef(), Ainv(), nullptr, TwistCoef(), begin, count, s);
+  else apply_hop_range(*lat, *gauge, out, in, parity, dagger, Ainv(), TwistCoef(), nullptr, TwistCoef(), begin, count, s);
+  flops += 1392ll * count;
+}
+
 // out = x + k (A^-1 D | D A^-1) in     (dirac_twisted_mass.cpp:297-344: dagger alone selects the input twist)
 void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const {
   if (flavor == 0) return WilsonDslashXpay(out, in, parity, x, k);

@@ -79,6 +79,8 @@ class DiracTM : public Dirac {
   void TwistInv(SpinorField &out, const SpinorField &in) const;   // A^-1 in
 
   void Dslash(SpinorField &out, const SpinorField &in, int parity) const override;
+  // Dslash restricted to the checkerboard range [begin, begin+count) of the output, on stream s (unpartitioned lattice)
+  void DslashRange(SpinorField &out, const SpinorField &in, int parity, int begin, int count, cudaStream_t s) const;
   void DslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const override;
   void M(SpinorField &out, const SpinorField &in) const override;
   void prepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b, SolutionType sol_type) const override;

@@ -49,6 +49,11 @@ struct Lattice {
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
                TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx);
 
+// same on the contiguous checkerboard range [site_begin, site_begin + site_count) only, on stream s (unpartitioned lattices;
+// used by the pipelined host path of dslashQuda)
+void apply_hop_range(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
+                     TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, int site_begin, int site_count, cudaStream_t s);
+
 void face_index_map(const Lattice &lat, int mu, int face_num, int parity, int *h_out);
 
 // out = (p + i q gamma5) in on every site of the field

@@ -117,7 +117,8 @@ static void ensure_arena(Lattice &lat, Prec prec) {
 
 template <typename Store>
 static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
-                  TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx) {
+                  TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, int range_begin = 0, int range_count = -1,
+                  cudaStream_t range_stream = nullptr) {
   Runtime &r = rt();
   const Geom &g = lat.geom;
   DslashParam p;
@@ -141,10 +142,11 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   const int block = lat.block_size > 0 ? lat.block_size : (Store::prec == PREC_DOUBLE ? 64 : 128);
   const bool partitioned = g.part[0] || g.part[1] || g.part[2] || g.part[3];
   if (!partitioned) {
-    p.site_begin = 0; p.site_count = g.Vh; p.site_list = nullptr;
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, r.compute);
+    p.site_begin = range_begin; p.site_count = range_count < 0 ? g.Vh : range_count; p.site_list = nullptr;
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, range_stream ? range_stream : r.compute);
     return;
   }
+  if (range_count >= 0) QB_ERROR("apply_hop_range is only available on unpartitioned lattices");
 
   const int pi = prec_index(Store::prec);
   ensure_arena(lat, Store::prec);
@@ -229,6 +231,14 @@ __global__ void face_map_kernel(int *out, Geom g, int mu, int face_num, int pari
   else if (mu == 2) cb = face_to_cb<2>(f, slice, parity, g);
   else cb = face_to_cb<3>(f, slice, parity, g);
   out[f] = cb;
+}
+
+void apply_hop_range(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
+                     TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, int site_begin, int site_count, cudaStream_t s) {
+  if (out.prec != in.prec || out.prec != gauge.prec) QB_ERROR("apply_hop_range: precision mismatch");
+  if (out.prec == PREC_DOUBLE) hop_T<StoreD>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, site_begin, site_count, s);
+  else if (out.prec == PREC_SINGLE) hop_T<StoreS>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, site_begin, site_count, s);
+  else hop_T<StoreH>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, site_begin, site_count, s);
 }
 
 void face_index_map(const Lattice &lat, int mu, int face_num, int parity, int *h_out) {

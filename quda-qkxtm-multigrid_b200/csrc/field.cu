@@ -251,10 +251,11 @@ template <typename T> __device__ __forceinline__ void dr_to_ukqcd(cplx<T> *o, co
 }
 
 template <typename Store, typename Host>
-__global__ void import_spinor_kernel(void *dst, float *dnorm, const Host *stage, long Vh, long nsites, size_t parity_bytes, int basis, int order) {
+__global__ void import_spinor_kernel(void *dst, float *dnorm, const Host *stage, long Vh, long nsites, size_t parity_bytes, int basis, int order, long site_begin = 0) {
   typedef typename Store::real real;
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nsites) return;
+  t += site_begin;
   const int parity = (int)(t / Vh);
   const long cb = t - (long)parity * Vh;
   const Host *src = stage + t * 24;
@@ -276,10 +277,11 @@ __global__ void import_spinor_kernel(void *dst, float *dnorm, const Host *stage,
 }
 
 template <typename Store, typename Host>
-__global__ void export_spinor_kernel(Host *stage, const void *src, const float *snorm, long Vh, long nsites, size_t parity_bytes, int basis, int order) {
+__global__ void export_spinor_kernel(Host *stage, const void *src, const float *snorm, long Vh, long nsites, size_t parity_bytes, int basis, int order, long site_begin = 0) {
   typedef typename Store::real real;
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nsites) return;
+  t += site_begin;
   const int parity = (int)(t / Vh);
   const long cb = t - (long)parity * Vh;
   cplx<real> psi[12];
@@ -356,6 +358,37 @@ static void export_spinor_host(void *h, const SpinorField &f, HostBasis basis, H
 void export_spinor(void *h, const SpinorField &f, Prec host_prec, HostBasis basis, HostSpinorOrder order, cudaStream_t s) {
   if (host_prec == PREC_DOUBLE) export_spinor_host<double>(h, f, basis, order, s);
   else if (host_prec == PREC_SINGLE) export_spinor_host<float>(h, f, basis, order, s);
+  else QB_ERROR("host spinor precision %d not supported", (int)host_prec);
+}
+
+// range variants for the pipelined host path: `stage` is the device copy of the WHOLE host array, only
+// sites [begin, begin + count) are converted
+template <typename Host>
+static void import_range_T(SpinorField &f, const void *stage, HostBasis basis, HostSpinorOrder order, long begin, long count, cudaStream_t s) {
+  const int bs = 128, nb = div_up(count, bs);
+  const Host *st = (const Host *)stage;
+  if (f.prec == PREC_DOUBLE) import_spinor_kernel<StoreD, Host><<<nb, bs, 0, s>>>(f.v, f.norm, st, f.Vh, count, f.parity_bytes, basis, order, begin);
+  else if (f.prec == PREC_SINGLE) import_spinor_kernel<StoreS, Host><<<nb, bs, 0, s>>>(f.v, f.norm, st, f.Vh, count, f.parity_bytes, basis, order, begin);
+  else import_spinor_kernel<StoreH, Host><<<nb, bs, 0, s>>>(f.v, f.norm, st, f.Vh, count, f.parity_bytes, basis, order, begin);
+  QB_CHECK_LAUNCH();
+}
+template <typename Host>
+static void export_range_T(void *stage, const SpinorField &f, HostBasis basis, HostSpinorOrder order, long begin, long count, cudaStream_t s) {
+  const int bs = 128, nb = div_up(count, bs);
+  Host *st = (Host *)stage;
+  if (f.prec == PREC_DOUBLE) export_spinor_kernel<StoreD, Host><<<nb, bs, 0, s>>>(st, f.v, f.norm, f.Vh, count, f.parity_bytes, basis, order, begin);
+  else if (f.prec == PREC_SINGLE) export_spinor_kernel<StoreS, Host><<<nb, bs, 0, s>>>(st, f.v, f.norm, f.Vh, count, f.parity_bytes, basis, order, begin);
+  else export_spinor_kernel<StoreH, Host><<<nb, bs, 0, s>>>(st, f.v, f.norm, f.Vh, count, f.parity_bytes, basis, order, begin);
+  QB_CHECK_LAUNCH();
+}
+void import_spinor_range(SpinorField &f, const void *stage, Prec host_prec, HostBasis basis, HostSpinorOrder order, long begin, long count, cudaStream_t s) {
+  if (host_prec == PREC_DOUBLE) import_range_T<double>(f, stage, basis, order, begin, count, s);
+  else if (host_prec == PREC_SINGLE) import_range_T<float>(f, stage, basis, order, begin, count, s);
+  else QB_ERROR("host spinor precision %d not supported", (int)host_prec);
+}
+void export_spinor_range(void *stage, const SpinorField &f, Prec host_prec, HostBasis basis, HostSpinorOrder order, long begin, long count, cudaStream_t s) {
+  if (host_prec == PREC_DOUBLE) export_range_T<double>(stage, f, basis, order, begin, count, s);
+  else if (host_prec == PREC_SINGLE) export_range_T<float>(stage, f, basis, order, begin, count, s);
   else QB_ERROR("host spinor precision %d not supported", (int)host_prec);
 }
 

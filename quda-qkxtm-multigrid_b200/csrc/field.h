@@ -87,6 +87,9 @@ void exchange_gauge_ghost(GaugeField &g, const Geom &geom, cudaStream_t s);
 // h: [parity][cb][spin][color][re,im] (or color-spin) in host_prec; nparity taken from the field
 void import_spinor(SpinorField &f, const void *h, Prec host_prec, HostBasis basis, HostSpinorOrder order, cudaStream_t s);
 void export_spinor(void *h, const SpinorField &f, Prec host_prec, HostBasis basis, HostSpinorOrder order, cudaStream_t s);
+void import_spinor_range(SpinorField &f, const void *stage_dev, Prec host_prec, HostBasis basis, HostSpinorOrder order, long begin, long count, cudaStream_t s);
+void export_spinor_range(void *stage_dev, const SpinorField &f, Prec host_prec, HostBasis basis, HostSpinorOrder order, long begin, long count, cudaStream_t s);
+void *staging(size_t bytes);
 // precision change / copy between resident fields of identical geometry
 void copy_spinor(SpinorField &dst, const SpinorField &src, cudaStream_t s);
 

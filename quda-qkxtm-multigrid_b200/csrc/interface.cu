@@ -175,6 +175,7 @@ void initQuda(int dev) {
 
 void freeGaugeQuda(void);
 void free_staging_buffers();
+void pipe_cleanup_c();
 
 void endQuda(void) {
   Runtime &r = rt();
@@ -183,6 +184,7 @@ void endQuda(void) {
     QB_CUDA(cudaDeviceSynchronize());
     freeGaugeQuda();
     blas::end();
+    pipe_cleanup_c();
     free_staging_buffers();
     comm_finalize();
     cudaEventDestroy(r.ev_pack_ready); cudaEventDestroy(r.ev_halo_done); cudaEventDestroy(r.ev_in_ready);
@@ -468,11 +470,90 @@ static void mat_fields(SpinorField &out, SpinorField &in, QudaInvertParam *p, bo
   mass_rescale_out(out, p, pc, normal);
 }
 
+// Pipelined host path of dslashQuda: the parity field is cut into T-slabs; slab c is converted and multiplied as soon
+// as slabs c-1, c, c+1 have landed, and its result starts its way back while later slabs are still arriving, so that
+// H2D, the hop and D2H overlap on the two copy engines (the reference moves the whole field in, computes, moves it out:
+// interface_quda.cpp:1509-1557).  Unpartitioned lattices only.
+struct PipeState {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_out;
+  cudaEvent_t ev_done = nullptr;
+};
+static PipeState pipe_state;
+
+void pipe_cleanup_c() {
+  if (pipe_state.h2d) { cudaStreamDestroy(pipe_state.h2d); cudaStreamDestroy(pipe_state.d2h); cudaEventDestroy(pipe_state.ev_done); }
+  for (auto e : pipe_state.ev_in) cudaEventDestroy(e);
+  for (auto e : pipe_state.ev_out) cudaEventDestroy(e);
+  pipe_state.h2d = pipe_state.d2h = nullptr; pipe_state.ev_done = nullptr; pipe_state.ev_in.clear(); pipe_state.ev_out.clear();
+}
+
+static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaParity parity, SpinorField &in, SpinorField &out) {
+  const Geom &g = G.lat.geom;
+  if (g.part[0] || g.part[1] || g.part[2] || g.part[3]) return false;
+  if (p->input_location != QUDA_CPU_FIELD_LOCATION || p->output_location != QUDA_CPU_FIELD_LOCATION) return false;
+  const int T = g.X[3];
+  int nchunk = 0;
+  for (int c : {16, 8, 4}) if (T % c == 0 && T / c >= 2) { nchunk = c; break; }
+  if (!nchunk || (long)g.Vh * 24 * 4 < (4l << 20)) return false;  // small fields: latency dominates, keep it simple
+  Runtime &r = rt();
+  if (!pipe_state.h2d) {
+    QB_CUDA(cudaStreamCreateWithFlags(&pipe_state.h2d, cudaStreamNonBlocking));
+    QB_CUDA(cudaStreamCreateWithFlags(&pipe_state.d2h, cudaStreamNonBlocking));
+    QB_CUDA(cudaEventCreateWithFlags(&pipe_state.ev_done, cudaEventDisableTiming));
+  }
+  while ((int)pipe_state.ev_in.size() < nchunk) {
+    cudaEvent_t a, b;
+    QB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    QB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    pipe_state.ev_in.push_back(a); pipe_state.ev_out.push_back(b);
+  }
+  const Prec hp = to_prec(p->cpu_prec, "cpu_prec");
+  const HostBasis basis = to_basis(p->gamma_basis);
+  const HostSpinorOrder order = to_order(p->dirac_order);
+  const size_t site_bytes = 24 * (size_t)hp;
+  const size_t hb = site_bytes * g.Vh;
+  char *stage_in = (char *)staging(2 * hb), *stage_out = stage_in + hb;
+  const long csites = g.Vh / nchunk;
+  std::unique_ptr<DiracTM> d(make_dirac(p, true, pick_gauge(in.prec)));
+  // everything previously queued on the compute stream must be done before the staging buffers are reused
+  QB_CUDA(cudaEventRecord(pipe_state.ev_done, r.compute));
+  QB_CUDA(cudaStreamWaitEvent(pipe_state.h2d, pipe_state.ev_done, 0));
+  for (int c = 0; c < nchunk; c++) {
+    QB_CUDA(cudaMemcpyAsync(stage_in + c * csites * site_bytes, (const char *)h_in + c * csites * site_bytes, csites * site_bytes, cudaMemcpyHostToDevice, pipe_state.h2d));
+    import_spinor_range(in, stage_in, hp, basis, order, c * csites, csites, pipe_state.h2d);
+    QB_CUDA(cudaEventRecord(pipe_state.ev_in[c], pipe_state.h2d));
+  }
+  // slab c needs its t-neighbours c-1 and c+1 (periodic): process 1 .. nchunk-2 as they arrive, then nchunk-1 and 0
+  std::vector<int> order_c;
+  for (int c = 1; c < nchunk - 1; c++) order_c.push_back(c);
+  order_c.push_back(nchunk - 1);
+  order_c.push_back(0);
+  for (int c : order_c) {
+    QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[(c + 1) % nchunk], 0));
+    QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[c], 0));
+    QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[(c + nchunk - 1) % nchunk], 0));
+    d->DslashRange(out, in, (int)parity, (int)(c * csites), (int)csites, r.compute);
+    export_spinor_range(stage_out, out, hp, basis, order, c * csites, csites, r.compute);
+    QB_CUDA(cudaEventRecord(pipe_state.ev_out[c], r.compute));
+    QB_CUDA(cudaStreamWaitEvent(pipe_state.d2h, pipe_state.ev_out[c], 0));
+    QB_CUDA(cudaMemcpyAsync((char *)h_out + c * csites * site_bytes, stage_out + c * csites * site_bytes, csites * site_bytes, cudaMemcpyDeviceToHost, pipe_state.d2h));
+  }
+  QB_CUDA(cudaStreamSynchronize(pipe_state.d2h));
+  QB_CUDA(cudaStreamSynchronize(r.compute));
+  return true;
+}
+
 // interface_quda.cpp:1496-1569
 void dslashQuda(void *h_out, void *h_in, QudaInvertParam *p, QudaParity parity) {
   require_gauge();
   const Prec prec = to_prec(p->cuda_prec, "cuda_prec");
   SpinorField *in = pool_get(1, prec), *out = pool_get(1, prec);
+  if (parity != QUDA_EVEN_PARITY && parity != QUDA_ODD_PARITY) QB_ERROR("invalid parity %d", (int)parity);
+  if (dslash_pipelined(h_out, h_in, p, parity, *in, *out)) {
+    pool_put(in); pool_put(out);
+    return;
+  }
   load_host_spinor(*in, h_in, p);
   dslash_fields(*out, *in, p, parity);
   save_host_spinor(h_out, *out, p);
@@ -735,6 +816,7 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
                                                                param->tol_precondition == INVALID_DOUBLE ? 0.1 : param->tol_precondition);
     (*solve)(out, in);
   }
+  if (K) ((MultigridSolver *)param->preconditioner)->mg->print_profile();
   d->reconstruct(*x, *b, st);
   if (param->solver_normalization == QUDA_SOURCE_NORMALIZATION) blas::ax(sqrt(nb), *x);
   save_host_spinor(hp_x, *x, param);

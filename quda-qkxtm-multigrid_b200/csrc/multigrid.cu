@@ -195,15 +195,30 @@ void MG::smooth(Solver &s, SpinorField &x, SpinorField &b) {
   matSmooth->reconstruct(x, b, SOL_MAT);
 }
 
+// optional wall-clock profile of the cycle (QUDA_B200_MG_PROFILE=1): sections are bracketed by stream syncs
+static bool mg_profile_on() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("QUDA_B200_MG_PROFILE"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+struct Section {
+  double *acc; double t0; bool on;
+  Section(double *a) : acc(a), on(mg_profile_on()) { if (on) { cudaStreamSynchronize(rt().compute); t0 = now_s(); } }
+  ~Section() { if (on) { cudaStreamSynchronize(rt().compute); *acc += now_s() - t0; } }
+};
+
 void MG::cycle(SpinorField &x, SpinorField &b) {
   const MGLevelParam &lp = mp.level[level];
+  ncycle++;
   if (level == mp.n_level - 1) {  // coarsest grid solve
+    Section s(&t_prof[0]);
     smooth(*presmoother, x, b);
     return;
   }
   // pre-smoothing (zero initial guess) and residual
   if (lp.nu_pre > 0) {
-    smooth(*presmoother, x, b);
+    { Section s(&t_prof[0]); smooth(*presmoother, x, b); }
+    Section s(&t_prof[1]);
     matResidual->M(*r, x);
     blas::axpby(1.0, b, -1.0, *r);
   } else {
@@ -211,13 +226,24 @@ void MG::cycle(SpinorField &x, SpinorField &b) {
     blas::copy(*r, b);
   }
   // coarse-grid correction
-  transfer->R(*r_coarse, *r);
-  if (coarse_solver_gcr) (*coarse_solver_gcr)(*x_coarse, *r_coarse);
-  else (*coarse)(*x_coarse, *r_coarse);
-  transfer->P(*r, *x_coarse);
-  blas::xpy(*r, x);
+  { Section s(&t_prof[2]); transfer->R(*r_coarse, *r); }
+  {
+    Section s(&t_prof[3]);
+    if (coarse_solver_gcr) (*coarse_solver_gcr)(*x_coarse, *r_coarse);
+    else (*coarse)(*x_coarse, *r_coarse);
+  }
+  { Section s(&t_prof[4]); transfer->P(*r, *x_coarse); blas::xpy(*r, x); }
   // post-smoothing with x as the initial guess
-  if (lp.nu_post > 0) smooth(*postsmoother, x, b);
+  if (lp.nu_post > 0) { Section s(&t_prof[5]); smooth(*postsmoother, x, b); }
+}
+
+void MG::print_profile() {
+  if (!mg_profile_on()) return;
+  log_msg(0, "MG level %d profile: %ld cycles, smooth-pre %.4f s, residual %.4f s, restrict %.4f s, coarse-solve %.4f s, prolong %.4f s, smooth-post %.4f s\n",
+          level + 1, ncycle, t_prof[0], t_prof[1], t_prof[2], t_prof[3], t_prof[4], t_prof[5]);
+  for (double &t : t_prof) t = 0;
+  ncycle = 0;
+  if (coarse) coarse->print_profile();
 }
 
 void MG::operator()(SpinorField &x, SpinorField &b) {

@@ -52,6 +52,9 @@ class MG : public Solver {
   std::vector<std::unique_ptr<SpinorField>> B;   // near-null vectors of this level
   std::unique_ptr<SpinorField> r, r_coarse, x_coarse, b_copy, x32, b32;
   double setup_secs = 0.0;
+  double t_prof[6] = {0, 0, 0, 0, 0, 0};
+  long ncycle = 0;
+  void print_profile();
 
   MG(MGParam &mp, int level, const Dirac *matResidual, const Dirac *matSmooth, std::vector<std::unique_ptr<SpinorField>> *B_in);
   void operator()(SpinorField &x, SpinorField &b) override;

@@ -166,6 +166,20 @@ def test_ragged_and_minimal_lattices(quda, oracle, X):
         assert rel_l2(out, ref) <= 1e-13
 
 
+@pytest.mark.parametrize("prec,cpu_prec", [(4, 8), (8, 8), (2, 4), (4, 4)])
+def test_pipelined_host_path(quda, oracle, prec, cpu_prec):
+    """dslashQuda on fields >= 4 MB takes the slab-pipelined H2D / hop / D2H path: same numbers as the plain path."""
+    c = Ctx(quda, oracle, (16, 16, 16, 32), prec, 12)
+    dt = np.float64 if cpu_prec == 8 else np.float32
+    for flavor, parity, matpc, dagger in ((1, 0, 0, 0), (-1, 1, 0, 1), (1, 1, 2, 1)):
+        p = c.param(flavor=flavor, matpc=matpc, dagger=dagger, cpu_prec=cpu_prec)
+        inp = c.even.astype(dt)
+        out = np.zeros(c.Vh * 24, dtype=dt)
+        c.q.lib().dslashQuda(vp(out), vp(inp), C.byref(p), parity)
+        ref = c.o.tm_dslash(c.g, c.even, KAPPA, MU, flavor, parity, matpc, dagger)
+        assert rel_l2(out, ref) <= max(TOL[prec], 2e-7 if cpu_prec == 4 else 0), (prec, cpu_prec, flavor, parity)
+
+
 def test_anisotropy_and_periodic(quda, oracle):
     c = Ctx(quda, oracle, (4, 4, 4, 8), 8, 12, anisotropy=2.5)
     out, ref = run_dslash(c, 1, 0, 0, 0)
