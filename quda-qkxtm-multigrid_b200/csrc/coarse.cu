@@ -1,6 +1,7 @@
 // Coarse-level operator: storage, the coarse Dslash kernel, batched site-block inversion, DiracCoarse.
 #include "blas.h"
 #include "coarse.h"
+#include "comm.h"
 #include "layout.cuh"
 
 namespace qb {
@@ -12,11 +13,93 @@ void CoarseOperator::allocate(const LevelGeom &g, int nvec_) {
   if (Y) cudaFree(Y);
   QB_CUDA(cudaMalloc((void **)&Y, link_bytes()));
   QB_CUDA(cudaMemsetAsync(Y, 0, link_bytes(), rt().compute));
+  for (int d = 0; d < 4; d++) {
+    if (!geom.part[d]) continue;
+    const size_t bytes = (size_t)2 * (N / 2) * geom.faceVh[d] * sizeof(float4);
+    for (int k = 0; k < 2; k++) {
+      QB_CUDA(cudaMalloc((void **)&send[d][k], bytes));
+      if (comm_self_exchange()) recv[d][1 - k] = send[d][k];  // my back face is my own forward ghost and vice versa
+      else QB_CUDA(cudaMalloc((void **)&recv[d][k], bytes));
+    }
+  }
 }
 
 CoarseOperator::~CoarseOperator() {
   if (Y) cudaFree(Y);
   if (Xinv) cudaFree(Xinv);
+  for (int d = 0; d < 4; d++)
+    for (int k = 0; k < 2; k++) {
+      if (recv[d][k] && !comm_self_exchange()) cudaFree(recv[d][k]);
+      if (send[d][k]) cudaFree(send[d][k]);
+    }
+}
+
+// ---- coarse halo: plain copies of the boundary slices (no spin projection on coarse levels,
+// cf. GenericPackGhostKernel, lib/color_spinor_pack.cu) ------------------------------------------------
+struct CoarsePackArgs {
+  float4 *send[4][2];
+  const float4 *field;
+  long poff[2];
+  int X[4];
+  long Vh;
+  int faceVh[4], part[4];
+  int nplanes, parity_mask;
+  long off[5];  // prefix sums of 2 * 2 * nplanes * faceVh[d] over partitioned dims
+};
+
+__device__ __forceinline__ long coarse_face_to_cb(int mu, int fidx, int slice, int parity, const int *X) {
+  const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
+  const int L0 = X[d0], L1 = X[d1];
+  const int f2 = 2 * fidx;
+  const int row = f2 / L0;
+  const int c = row / L1, b = row - c * L1;
+  int a = f2 - row * L0;
+  a += (slice + b + c + parity + a) & 1;
+  int x[4];
+  x[mu] = slice; x[d0] = a; x[d1] = b; x[d2] = c;
+  return ((((long)x[3] * X[2] + x[2]) * X[1] + x[1]) * X[0] + x[0]) >> 1;
+}
+
+__global__ void coarse_pack_kernel(const CoarsePackArgs a) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.off[4]) return;
+  int d = 0;
+  while (d < 3 && t >= a.off[d + 1]) d++;
+  long r = t - a.off[d];
+  const int fv = a.faceVh[d];
+  const int fidx = (int)(r % fv); r /= fv;
+  const int pl = (int)(r % a.nplanes); r /= a.nplanes;
+  const int parity = (int)(r & 1), dir = (int)(r >> 1);
+  if (!((a.parity_mask >> parity) & 1)) return;
+  const long cb = coarse_face_to_cb(d, fidx, dir ? a.X[d] - 1 : 0, parity, a.X);
+  a.send[d][dir][((size_t)parity * a.nplanes + pl) * fv + fidx] = a.field[a.poff[parity] + (size_t)pl * a.Vh + cb];
+}
+
+void CoarseOperator::exchange_ghost(const float *field, const long *poff, int parity_mask) const {
+  if (!geom.partitioned()) return;
+  Runtime &r = rt();
+  CoarsePackArgs a;
+  a.field = (const float4 *)field;
+  a.poff[0] = poff[0]; a.poff[1] = poff[1];
+  a.Vh = geom.Vh; a.nplanes = N / 2; a.parity_mask = parity_mask;
+  long off = 0;
+  for (int d = 0; d < 4; d++) {
+    a.X[d] = geom.X[d]; a.faceVh[d] = geom.faceVh[d]; a.part[d] = geom.part[d];
+    a.send[d][0] = (float4 *)send[d][0]; a.send[d][1] = (float4 *)send[d][1];
+    a.off[d] = off;
+    if (geom.part[d]) off += 2L * 2 * a.nplanes * geom.faceVh[d];
+  }
+  a.off[4] = off;
+  coarse_pack_kernel<<<div_up(off, 256), 256, 0, r.compute>>>(a);
+  QB_CHECK_LAUNCH();
+  if (comm_self_exchange()) return;
+  for (int d = 0; d < 4; d++) {
+    if (!geom.part[d]) continue;
+    const size_t bytes = (size_t)2 * a.nplanes * geom.faceVh[d] * sizeof(float4);
+    // my back face -> backward neighbour's "from forward" ghost; my forward face -> forward neighbour's "from backward" ghost
+    comm_sendrecv(send[d][0], comm_neighbor_rank(d, 0), recv[d][1], comm_neighbor_rank(d, 1), bytes, r.compute);
+    comm_sendrecv(send[d][1], comm_neighbor_rank(d, 1), recv[d][0], comm_neighbor_rank(d, 0), bytes, r.compute);
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------
@@ -38,6 +121,8 @@ struct CoarseKernelArgs {
   int parity;      // -1: all sites (blockIdx.x = full index), else cb index of that parity
   int use_y, use_x, use_xinv;
   float a, b;
+  int part[4], faceVh[4];
+  const float4 *ghost[4][2];  // [d][0]: from the backward, [d][1]: from the forward neighbour; [parity][plane][faceVh]
 };
 
 template <int N>
@@ -46,6 +131,7 @@ __global__ void __launch_bounds__(((9 * (N / 2) + 31) / 32) * 32) coarse_dslash_
   __shared__ float2 xin[9][N + 1];
   __shared__ float4 red[9][NRP];
   __shared__ int nbr_par[9];
+  __shared__ int nbr_ghost[9];
   __shared__ long nbr_cb[9];
 
   const long Vh = p.Vh;
@@ -65,12 +151,23 @@ __global__ void __launch_bounds__(((9 * (N / 2) + 31) / 32) * 32) coarse_dslash_
     x[3] = (int)(zb / p.X[2]);
     x[2] = (int)(zb - (long)x[3] * p.X[2]);
     x[0] = (int)(2 * cb + ((x[1] + x[2] + x[3] + parity) & 1) - za * p.X[0]);
+    nbr_ghost[t] = 0;
     if (t < 8) {
       const int mu = t >> 1;
-      x[mu] = (x[mu] + ((t & 1) ? p.X[mu] - 1 : 1)) % p.X[mu];
+      const bool edge = (t & 1) ? (x[mu] == 0) : (x[mu] == p.X[mu] - 1);
       nbr_par[t] = 1 - parity;
-    } else nbr_par[t] = parity;
-    nbr_cb[t] = ((((long)x[3] * p.X[2] + x[2]) * p.X[1] + x[1]) * p.X[0] + x[0]) >> 1;
+      if (edge && p.part[mu]) {
+        nbr_ghost[t] = 1;
+        const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
+        nbr_cb[t] = (x[d0] + p.X[d0] * (x[d1] + (long)p.X[d1] * x[d2])) >> 1;
+      } else {
+        x[mu] = (x[mu] + ((t & 1) ? p.X[mu] - 1 : 1)) % p.X[mu];
+        nbr_cb[t] = ((((long)x[3] * p.X[2] + x[2]) * p.X[1] + x[1]) * p.X[0] + x[0]) >> 1;
+      }
+    } else {
+      nbr_par[t] = parity;
+      nbr_cb[t] = cb;
+    }
   }
   __syncthreads();
 
@@ -79,8 +176,14 @@ __global__ void __launch_bounds__(((9 * (N / 2) + 31) / 32) * 32) coarse_dslash_
     const bool diag = d == 8;
     const bool need = diag ? (p.use_x || p.use_xinv) : p.use_y;
     if (need) {
-      const float4 *src = diag ? p.in_diag + p.diag_poff[nbr_par[8]] : p.in_hop + p.hop_poff[nbr_par[d]];
-      const float4 v = __ldg(src + (size_t)rp * Vh + nbr_cb[d]);
+      float4 v;
+      if (!diag && nbr_ghost[d]) {
+        const int mu = d >> 1;
+        v = __ldg(p.ghost[mu][(d & 1) ? 0 : 1] + ((size_t)nbr_par[d] * NRP + rp) * p.faceVh[mu] + nbr_cb[d]);
+      } else {
+        const float4 *src = diag ? p.in_diag + p.diag_poff[nbr_par[8]] : p.in_hop + p.hop_poff[nbr_par[d]];
+        v = __ldg(src + (size_t)rp * Vh + nbr_cb[d]);
+      }
       xin[d][2 * rp] = make_float2(v.x, v.y);
       xin[d][2 * rp + 1] = make_float2(v.z, v.w);
     }
@@ -134,6 +237,14 @@ void coarse_apply(const CoarseApplyArgs &a) {
   for (int d = 0; d < 4; d++) k.X[d] = op.geom.X[d];
   k.Xh = op.geom.Xh; k.Vh = op.geom.Vh;
   k.parity = a.parity; k.use_y = a.use_y; k.use_x = a.use_x; k.use_xinv = a.use_xinv; k.a = a.a; k.b = a.b;
+  for (int d = 0; d < 4; d++) {
+    k.part[d] = op.geom.part[d]; k.faceVh[d] = op.geom.faceVh[d];
+    k.ghost[d][0] = (const float4 *)op.recv[d][0]; k.ghost[d][1] = (const float4 *)op.recv[d][1];
+  }
+  if (a.use_y && op.geom.partitioned()) {
+    // halo of the hop input: the parities the output sites read from (both for a full-lattice apply)
+    op.exchange_ghost(a.in_hop, a.hop_poff, a.parity < 0 ? 3 : (1 << (1 - a.parity)));
+  }
   if (a.use_xinv && !op.Xinv) QB_ERROR("coarse_apply: Xinv has not been computed");
   const long nsites = a.parity < 0 ? op.geom.V() : op.geom.Vh;
   switch (op.N) {

@@ -23,8 +23,15 @@ struct CoarseOperator {
   int N = 0;      // 2 * nvec
   float *Y = nullptr;     // [V][9][N][N/2] float4
   float *Xinv = nullptr;  // [V][N][N/2] float4, inverse of the site-diagonal block L_8 (for even-odd preconditioning)
+  // halo buffers of coarse spinors for partitioned dimensions: [d][dir] -> [parity][plane N/2][faceVh] float4
+  // send[d][0] = my slice x_d = 0 (goes backward), send[d][1] = my slice x_d = X_d - 1 (goes forward);
+  // recv[d][0] = from the backward neighbour, recv[d][1] = from the forward neighbour (alias of send in self-exchange mode)
+  float *send[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  float *recv[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   size_t link_bytes() const { return (size_t)geom.V() * 9 * N * N * 8; }
   void allocate(const LevelGeom &g, int nvec_);
+  // pack the boundary slices of the parities in `parity_mask` of a coarse field and exchange them with the neighbours
+  void exchange_ghost(const float *field, const long *poff, int parity_mask) const;
   void compute_xinv();    // batched in-kernel Gauss-Jordan with partial pivoting (the reference calls MAGMA, coarse_op.cuh:1466-1474)
   ~CoarseOperator();
 };

@@ -61,6 +61,47 @@ static float *decompress_gauge(const GaugeField &gf, const Geom &g) {
   return out;
 }
 
+// ghost links (compressed [parity][plane][faceVh]) -> [parity][faceVh][18]; they sit on the backward neighbour's last slice
+template <typename Store, int RECON>
+__global__ void decompress_ghost_kernel(float *out, const void *src, Geom g, int mu, int faceVh) {
+  typedef typename Store::real real;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2L * faceVh) return;
+  const int parity = (int)(t / faceVh);
+  const long f = t - (long)parity * faceVh;
+  real raw[RECON];
+  LinkRaw<Store, RECON>::load(raw, (const char *)src + (size_t)parity * RECON * StoreTraits<Store>::real_bytes * faceVh, faceVh, f);
+  real u0;
+  if (mu < 3) u0 = RECON == 8 ? (real)1 / (real)g.aniso : (real)g.aniso;
+  else u0 = (real)g.tb_bwd;  // links used by the backward hop of sites at t = 0
+  cplx<real> U[9];
+  reconstruct_link<real, RECON>(U, raw, link_u0<Store, RECON>(u0));
+  const real ls = link_scale<Store, RECON>();
+  float *dst = out + (size_t)t * 18;
+#pragma unroll
+  for (int k = 0; k < 9; k++) { dst[2 * k] = (float)(U[k].re * ls); dst[2 * k + 1] = (float)(U[k].im * ls); }
+}
+
+static float *decompress_ghost(const GaugeField &gf, const Geom &g, int mu) {
+  float *out;
+  const int fv = g.faceVh[mu];
+  QB_CUDA(cudaMalloc((void **)&out, sizeof(float) * 18 * 2 * fv));
+  const int bs = 256, nb = div_up(2L * fv, bs);
+  cudaStream_t s = rt().compute;
+#define DG(ST, RC) decompress_ghost_kernel<ST, RC><<<nb, bs, 0, s>>>(out, gf.ghost[mu], g, mu, fv)
+#define BY_RECON(ST)                  \
+  if (gf.recon == 18) DG(ST, 18);     \
+  else if (gf.recon == 12) DG(ST, 12);\
+  else DG(ST, 8)
+  if (gf.prec == PREC_DOUBLE) { BY_RECON(StoreD); }
+  else if (gf.prec == PREC_SINGLE) { BY_RECON(StoreS); }
+  else { BY_RECON(StoreH); }
+#undef BY_RECON
+#undef DG
+  QB_CHECK_LAUNCH();
+  return out;
+}
+
 // ---- shared pieces -------------------------------------------------------------------------------------
 struct GalerkinArgs {
   // transfer
@@ -77,6 +118,10 @@ struct GalerkinArgs {
   float kappa, twist_a;
   // coarse-level links (the finer coarse operator)
   const float4 *Yf;  // [Vf][9][Nf][Nf/2]
+  // partitioned dimensions: V (and, on the fine level, backward links) of the neighbours' boundary slices
+  int part[4], faceVh[4];
+  const float4 *Vghost[4][2];  // [d][0] from the backward, [d][1] from the forward neighbour: [parity][k][nvec/2][faceVh]
+  const float *Ughost[4];      // decompressed U_d at x_d = X_d - 1 of the backward neighbour: [parity][faceVh][18]
 };
 
 __device__ __forceinline__ void fine_coords(int *x, long cb, int parity, const GalerkinArgs &a) {
@@ -87,12 +132,12 @@ __device__ __forceinline__ void fine_coords(int *x, long cb, int parity, const G
   x[0] = (int)(2 * cb + ((x[1] + x[2] + x[3] + parity) & 1) - za * a.Xf[0]);
 }
 
-// V(x) -> smem as [k][j] complex
-__device__ __forceinline__ void stage_V(float2 *dst, const GalerkinArgs &a, int parity, long cb) {
+// V(x) -> smem as [k][j] complex; base/stride select the local field or a ghost slice
+__device__ __forceinline__ void stage_V(float2 *dst, const GalerkinArgs &a, const float4 *base, long stride, int parity, long idx) {
   const int nvh = a.nvec / 2;
   for (int e = threadIdx.x; e < a.Nf * nvh; e += blockDim.x) {
     const int k = e / nvh, jp = e - k * nvh;
-    const float4 v = __ldg(a.V + (((size_t)parity * a.Nf + k) * nvh + jp) * a.Vh_f + cb);
+    const float4 v = __ldg(base + (((size_t)parity * a.Nf + k) * nvh + jp) * stride + idx);
     dst[k * a.nvec + 2 * jp] = make_float2(v.x, v.y);
     dst[k * a.nvec + 2 * jp + 1] = make_float2(v.z, v.w);
   }
@@ -137,7 +182,7 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const GalerkinArgs a) {
   float2 *Vn = Vx + Nf * nvec;        // [Nf][nvec]
   float2 *W = Vn + Nf * nvec;         // [Nf][N]
   float2 *Ld = W + Nf * N;            // LEVEL 0: 9 complex (the link); LEVEL 1: [Nf][Nf]
-  __shared__ int s_info[4];           // neighbour parity, leaves-block flag
+  __shared__ int s_info[4];           // neighbour parity, leaves-block flag, ghost flag
   __shared__ long s_cb[2];
 
   const long X = blockIdx.x;
@@ -167,28 +212,42 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const GalerkinArgs a) {
       if (threadIdx.x == 0) {
         int x[4];
         fine_coords(x, cb, parity, a);
-        int npar = parity;
+        int npar = parity, ghost = 0;
         long ncb = cb;
         if (d < 8) {
           const int mu = d >> 1;
-          x[mu] = (x[mu] + ((d & 1) ? a.Xf[mu] - 1 : 1)) % a.Xf[mu];
+          const bool edge = (d & 1) ? (x[mu] == 0) : (x[mu] == a.Xf[mu] - 1);
           npar = 1 - parity;
-          ncb = ((((long)x[3] * a.Xf[2] + x[2]) * a.Xf[1] + x[1]) * a.Xf[0] + x[0]) >> 1;
+          if (edge && a.part[mu]) {
+            // neighbour lives on another rank: index of the site inside the face (3-d lexicographic >> 1)
+            ghost = 1;
+            const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
+            ncb = (x[d0] + a.Xf[d0] * (x[d1] + (long)a.Xf[d1] * x[d2])) >> 1;
+          } else {
+            x[mu] = (x[mu] + ((d & 1) ? a.Xf[mu] - 1 : 1)) % a.Xf[mu];
+            ncb = ((((long)x[3] * a.Xf[2] + x[2]) * a.Xf[1] + x[1]) * a.Xf[0] + x[0]) >> 1;
+          }
         }
         s_info[0] = npar;
         s_cb[0] = ncb;
-        s_info[1] = (d < 8 && a.f2c[(size_t)npar * a.Vh_f + ncb] != X) ? 1 : 0;
+        s_info[2] = ghost;
+        s_info[1] = (d < 8 && (ghost || a.f2c[(size_t)npar * a.Vh_f + ncb] != X)) ? 1 : 0;
       }
       __syncthreads();
       const int npar = s_info[0];
       const long ncb = s_cb[0];
-      stage_V(Vx, a, parity, cb);
-      if (d < 8) stage_V(Vn, a, npar, ncb);
+      const bool ghost = s_info[2] != 0;
+      stage_V(Vx, a, a.V, a.Vh_f, parity, cb);
+      if (d < 8) {
+        if (ghost) stage_V(Vn, a, a.Vghost[d >> 1][(d & 1) ? 0 : 1], a.faceVh[d >> 1], npar, ncb);
+        else stage_V(Vn, a, a.V, a.Vh_f, npar, ncb);
+      }
       if (LEVEL == 0) {
         if (d < 8 && threadIdx.x < 9) {
           // forward: U_mu(x); backward: U_mu(x - mu)^dagger
           const int mu = d >> 1;
-          const float *u = (d & 1) ? a.U + (((size_t)npar * 4 + mu) * a.Vh_f + ncb) * 18 : a.U + (((size_t)parity * 4 + mu) * a.Vh_f + cb) * 18;
+          const float *u = (d & 1) ? (ghost ? a.Ughost[mu] + ((size_t)npar * a.faceVh[mu] + ncb) * 18 : a.U + (((size_t)npar * 4 + mu) * a.Vh_f + ncb) * 18)
+                                   : a.U + (((size_t)parity * 4 + mu) * a.Vh_f + cb) * 18;
           const int r = threadIdx.x / 3, c = threadIdx.x - 3 * r;
           Ld[threadIdx.x] = (d & 1) ? make_float2(u[(c * 3 + r) * 2], -u[(c * 3 + r) * 2 + 1]) : make_float2(u[threadIdx.x * 2], u[threadIdx.x * 2 + 1]);
         }
@@ -284,6 +343,12 @@ template <int LEVEL> static void launch_galerkin(const GalerkinArgs &a, long Vc)
 }
 
 static void fill_transfer_args(GalerkinArgs &a, const Transfer &T) {
+  for (int d = 0; d < 4; d++) {
+    a.part[d] = T.fine.part[d]; a.faceVh[d] = T.fine.faceVh[d];
+    a.Vghost[d][0] = (const float4 *)T.Vghost[d][0]; a.Vghost[d][1] = (const float4 *)T.Vghost[d][1];
+    a.Ughost[d] = nullptr;
+    if (a.part[d] && (!T.Vghost[d][0] || !T.Vghost[d][1])) QB_ERROR("transfer operator has no ghost V for partitioned dimension %d", d);
+  }
   a.V = (const float4 *)T.V; a.f2c = T.f2c; a.c2f = T.c2f;
   a.Nf = T.Nf; a.nvec = T.nvec; a.block_sites = T.block_sites; a.Vh_f = T.fine.Vh;
   for (int d = 0; d < 4; d++) a.Xf[d] = T.fine.X[d];
@@ -298,9 +363,18 @@ void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeF
   GalerkinArgs a{};
   fill_transfer_args(a, T);
   a.Yc = (float4 *)out.Y; a.U = U; a.kappa = (float)kappa; a.twist_a = (float)twist_a; a.Yf = nullptr;
+  float *ug[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int d = 0; d < 4; d++)
+    if (fine_geom.part[d]) {
+      if (!gauge.ghost[d]) QB_ERROR("gauge field has no ghost links for partitioned dimension %d", d);
+      ug[d] = decompress_ghost(gauge, fine_geom, d);
+      a.Ughost[d] = ug[d];
+    }
   launch_galerkin<0>(a, T.coarse.V());
   QB_CUDA(cudaStreamSynchronize(rt().compute));
   QB_CUDA(cudaFree(U));
+  for (int d = 0; d < 4; d++)
+    if (ug[d]) QB_CUDA(cudaFree(ug[d]));
 }
 
 void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine) {

@@ -168,7 +168,7 @@ void MG::generate_null_vectors() {
   while ((int)B.size() < lp.nvec) {
     const int i = (int)B.size();
     std::unique_ptr<SpinorField> x(new_full(*matResidual));
-    random_fill(*x, 0x5EEDull + 7919ull * (unsigned long long)(level * 1000 + i));
+    random_fill(*x, 0x5EEDull + 7919ull * (unsigned long long)(level * 1000 + i) + 104729ull * (unsigned long long)rt().rank);
     blas::zero(*b);
     BiCGStab solve(ms, ms, sp);
     SpinorField src, sol;
@@ -267,7 +267,7 @@ void MG::verify(double *dev) {
   if (!transfer) return;
   std::unique_ptr<SpinorField> eta(transfer->new_coarse_field()), t_c(transfer->new_coarse_field()), t_c2(transfer->new_coarse_field());
   std::unique_ptr<SpinorField> t_f(new_full(*matResidual)), t_f2(new_full(*matResidual));
-  random_fill(*eta, 424242ull + level);
+  random_fill(*eta, 424242ull + level + 104729ull * (unsigned long long)rt().rank);
   // (1) R P eta = eta
   transfer->P(*t_f, *eta);
   transfer->R(*t_c, *t_f);

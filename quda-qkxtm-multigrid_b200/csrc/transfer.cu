@@ -3,6 +3,7 @@
 #include <vector>
 #include "layout.cuh"
 #include "transfer.h"
+#include "comm.h"
 
 namespace qb {
 
@@ -180,7 +181,71 @@ __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V,
   }
 }
 
+// face site (3-d lexicographic >> 1 of the remaining coordinates, as in the fine Dslash) -> cb index on slice x_mu = slice
+__device__ __forceinline__ long level_face_to_cb(int mu, int fidx, int slice, int parity, const int *X) {
+  const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
+  const int L0 = X[d0], L1 = X[d1];
+  const int f2 = 2 * fidx;
+  const int row = f2 / L0;
+  const int c = row / L1, b = row - c * L1;
+  int a = f2 - row * L0;
+  a += (slice + b + c + parity + a) & 1;
+  int x[4];
+  x[mu] = slice; x[d0] = a; x[d1] = b; x[d2] = c;
+  return ((((long)x[3] * X[2] + x[2]) * X[1] + x[1]) * X[0] + x[0]) >> 1;
+}
+
+struct LevelDims { int X[4]; };
+
+// gathers nplanes float4 planes per parity of the slice x_mu = slice into [parity][plane][faceVh]
+__global__ void gather_slice_kernel(float4 *dst, const float4 *src, LevelDims dims, long Vh, int faceVh, int nplanes, int mu, int slice) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2L * nplanes * faceVh) return;
+  const int fidx = (int)(t % faceVh);
+  const int pl = (int)((t / faceVh) % nplanes), parity = (int)(t / ((long)faceVh * nplanes));
+  const long cb = level_face_to_cb(mu, fidx, slice, parity, dims.X);
+  dst[t] = src[((size_t)parity * nplanes + pl) * Vh + cb];
+}
+
+void gather_slice(float4 *dst, const float4 *src, const LevelGeom &g, int nplanes, int mu, int slice, cudaStream_t s) {
+  LevelDims d;
+  for (int k = 0; k < 4; k++) d.X[k] = g.X[k];
+  const long n = 2L * nplanes * g.faceVh[mu];
+  gather_slice_kernel<<<div_up(n, 256), 256, 0, s>>>(dst, src, d, g.Vh, g.faceVh[mu], nplanes, mu, slice);
+  QB_CHECK_LAUNCH();
+}
+
 // ---- host ------------------------------------------------------------------------------------------
+void Transfer::exchange_v_ghost() {
+  if (!fine.partitioned()) return;
+  Runtime &r = rt();
+  const int nplanes = Nf * nvec / 2;
+  for (int d = 0; d < 4; d++) {
+    if (!fine.part[d]) continue;
+    const size_t bytes = (size_t)2 * nplanes * fine.faceVh[d] * sizeof(float4);
+    float4 *lo, *hi;  // my x_d = 0 and x_d = X_d - 1 slices
+    QB_CUDA(cudaMalloc((void **)&lo, bytes));
+    QB_CUDA(cudaMalloc((void **)&hi, bytes));
+    gather_slice(lo, (const float4 *)V, fine, nplanes, d, 0, r.compute);
+    gather_slice(hi, (const float4 *)V, fine, nplanes, d, fine.X[d] - 1, r.compute);
+    if (comm_self_exchange()) {
+      Vghost[d][0] = (float *)hi;  // backward neighbour (= myself) last slice
+      Vghost[d][1] = (float *)lo;  // forward neighbour first slice
+    } else {
+      QB_CUDA(cudaMalloc((void **)&Vghost[d][0], bytes));
+      QB_CUDA(cudaMalloc((void **)&Vghost[d][1], bytes));
+      // my last slice -> forward neighbour's "from backward" ghost; my first slice -> backward neighbour's "from forward" ghost
+      comm_sendrecv(hi, comm_neighbor_rank(d, 1), Vghost[d][0], comm_neighbor_rank(d, 0), bytes, r.compute);
+      comm_sendrecv(lo, comm_neighbor_rank(d, 0), Vghost[d][1], comm_neighbor_rank(d, 1), bytes, r.compute);
+      QB_CUDA(cudaStreamSynchronize(r.compute));
+      QB_CUDA(cudaFree(lo));
+      QB_CUDA(cudaFree(hi));
+    }
+  }
+  QB_CUDA(cudaStreamSynchronize(r.compute));
+}
+
+
 Transfer::Transfer(const std::vector<SpinorField *> &B, int nvec_, int *bs, int spin_bs_, const int *fine_X) : nvec(nvec_), spin_bs(spin_bs_) {
   if ((int)B.size() < nvec) QB_ERROR("Transfer: %d null vectors supplied, %d needed", (int)B.size(), nvec);
   if (nvec < 2 || (nvec & 1)) QB_ERROR("Transfer: n_vec = %d must be even and >= 2", nvec);
@@ -241,12 +306,16 @@ Transfer::Transfer(const std::vector<SpinorField *> &B, int nvec_, int *bs, int 
   block_ortho_kernel<<<dim3((unsigned)Vc, 2), 256, 0, s>>>(V, c2f, fine.Vh, Nf, nvec, block_sites);
   QB_CHECK_LAUNCH();
   QB_CUDA(cudaStreamSynchronize(s));
+  exchange_v_ghost();
 }
 
 Transfer::~Transfer() {
   if (V) cudaFree(V);
   if (f2c) cudaFree(f2c);
   if (c2f) cudaFree(c2f);
+  for (int d = 0; d < 4; d++)
+    for (int k = 0; k < 2; k++)
+      if (Vghost[d][k]) cudaFree(Vghost[d][k]);
 }
 
 void Transfer::P(SpinorField &fo, const SpinorField &ci) const {

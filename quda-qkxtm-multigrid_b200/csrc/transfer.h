@@ -16,15 +16,22 @@
 namespace qb {
 
 struct LevelGeom {
-  int X[4];
+  int X[4];        // local extents of this level
   int Xh;
   long Vh;
+  int part[4];     // dimension partitioned over ranks (or forced self-exchange): neighbours across it live in ghost buffers
+  int faceVh[4];   // checkerboard face volume per dimension
   long V() const { return 2 * Vh; }
   void set(const int *x) {
     for (int d = 0; d < 4; d++) X[d] = x[d];
     Xh = x[0] / 2;
     Vh = (long)x[0] * x[1] * x[2] * x[3] / 2;
+    for (int d = 0; d < 4; d++) {
+      part[d] = (rt().part_mask >> d) & 1;
+      faceVh[d] = (int)(Vh / x[d]);
+    }
   }
+  bool partitioned() const { return part[0] || part[1] || part[2] || part[3]; }
 };
 
 class Transfer {
@@ -38,6 +45,9 @@ class Transfer {
   float *V = nullptr;   // [parity][k][nvec/2][Vh_f] float4
   int *f2c = nullptr;   // [parity*Vh_f + cb]      -> coarse full index (parity_c*Vh_c + cb_c)
   int *c2f = nullptr;   // [coarse full index][block_sites] -> fine full index
+  // ghost copies of V on the neighbours' boundary slices, [d][0]: backward neighbour's x_d = X_d-1 slice, [d][1]: forward
+  // neighbour's x_d = 0 slice; layout [parity][k][nvec/2][faceVh] float4.  Needed by the coarse-link build only.
+  float *Vghost[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   mutable long long flops = 0;
 
   // B: nvec near-null vectors (full fine fields, fp32).  geo_bs is adjusted in place exactly as the
@@ -50,6 +60,8 @@ class Transfer {
   void P(SpinorField &fine_out, const SpinorField &coarse_in) const;
   void R(SpinorField &coarse_out, const SpinorField &fine_in) const;
   size_t v_bytes() const { return (size_t)2 * fine.Vh * Nf * nvec * 8; }
+ private:
+  void exchange_v_ghost();
 };
 
 }  // namespace qb

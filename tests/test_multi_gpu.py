@@ -148,3 +148,16 @@ def test_nccl_halo_exchange_vs_global_oracle(nranks, grid, local):
            "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_dslash.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTIGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks,grid", [(2, "1,1,1,2"), (2, "1,1,2,1"), (4, "1,1,2,2")])
+def test_distributed_multigrid_solve(nranks, grid):
+    import torch
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
+           "--master-port", "29633", os.path.join(ROOT, "tests", "multi_gpu_mg.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTIGPU_MG_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
