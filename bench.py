@@ -90,20 +90,20 @@ def make_inputs(oracle, X, seed):
     return g, sp
 
 
-def run_mg_leg(q, L, oracle, X):
+def run_mg_leg(q, L, oracle, X, precond=2):
     """Second half of the BASELINE metric: 3-level MG-GCR twisted-mass solve (seconds), plus the coarse-operator
     kernels against their HBM roofline.  32^3x64, 4^4 then 2^4 aggregates, 24 vectors per level, MR(2,2) smoother,
     K-cycle, fp64 outer GCR(20) / fp32 MG / int16 level-0 smoother, weak-field SU(3) gauge (periodic)."""
     kappa, mu = 0.1248, 0.004
     oracle.set_dims(X)
     g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711)
-    gp = q.gauge_param(X, cuda_prec=8, reconstruct=12, cuda_prec_sloppy=4, cuda_prec_precondition=2, t_boundary=q.QUDA_PERIODIC_T)
+    gp = q.gauge_param(X, cuda_prec=8, reconstruct=12, cuda_prec_sloppy=4, cuda_prec_precondition=precond, t_boundary=q.QUDA_PERIODIC_T)
     L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
 
     def inv_param():
         p = q.invert_param(kappa=kappa, mu=mu, cuda_prec=8, solution_type=q.QUDA_MAT_SOLUTION)
         p.cuda_prec_sloppy = 4
-        p.cuda_prec_precondition = 2
+        p.cuda_prec_precondition = precond
         p.solve_type = q.QUDA_DIRECT_SOLVE
         p.inv_type = q.QUDA_GCR_INVERTER
         p.gcrNkrylov = 20
@@ -133,7 +133,7 @@ def run_mg_leg(q, L, oracle, X):
     p0 = inv_param()
     x0 = np.zeros_like(b)
     L.invertQuda(vp(x0), vp(b), C.byref(p0))
-    res = {"lattice": list(X), "levels": 3, "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
+    res = {"lattice": list(X), "levels": 3, "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond], "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
            "setup_seconds": setup_s, "solve_seconds": p.secs, "solve_wall_seconds_incl_h2d_d2h": wall_s, "iterations": p.iter,
            "true_res": p.true_res, "tol": 1e-9, "plain_gcr_seconds": p0.secs, "plain_gcr_iterations": p0.iter, "plain_gcr_true_res": p0.true_res}
     peaks, _ = measured_peaks()
@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the half-precision extra measurement")
     ap.add_argument("--no-mg", action="store_true", help="skip the 3-level MG-GCR solve leg (N=1 only)")
+    ap.add_argument("--mg-precond", type=int, default=4, choices=[2, 4], help="precision of the level-0 smoother operator (2 = int16, 4 = fp32)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -336,7 +337,7 @@ def main():
         extra["half_r12"] = half
     mg_res = None
     if world == 1 and not args.no_mg and not args.no_extra:
-        mg_res = run_mg_leg(q, L, oracle, X)
+        mg_res = run_mg_leg(q, L, oracle, X, args.mg_precond)
     sampler.stop_flag = True
 
     # max over ranks of the device time

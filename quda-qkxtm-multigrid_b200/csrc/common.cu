@@ -1,5 +1,8 @@
 // Runtime singleton, logging and the error path.
 #include "common.h"
+#include <map>
+#include <unordered_map>
+#include <vector>
 
 namespace qb {
 
@@ -32,6 +35,46 @@ void log_msg(int level, const char *fmt, ...) {
   vfprintf(o, fmt, ap);
   va_end(ap);
   fflush(o);
+}
+
+static std::multimap<size_t, void *> pool_cache;          // free blocks by size
+static std::unordered_map<void *, size_t> pool_live;       // blocks handed out
+
+void *pool_malloc(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  auto it = pool_cache.find(bytes);
+  void *p = nullptr;
+  if (it != pool_cache.end()) {
+    p = it->second;
+    pool_cache.erase(it);
+  } else {
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      for (auto &kv : pool_cache) cudaFree(kv.second);
+      pool_cache.clear();
+      e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) QB_ERROR("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+  }
+  pool_live[p] = bytes;
+  return p;
+}
+
+void pool_free(void *ptr) {
+  if (!ptr) return;
+  auto it = pool_live.find(ptr);
+  if (it == pool_live.end()) { cudaFree(ptr); return; }
+  // the block may still be in use by kernels queued on the library's streams; a later user only ever touches it
+  // through the same in-order compute stream (or after an event wait on it), so reuse is stream-ordered
+  pool_cache.emplace(it->second, ptr);
+  pool_live.erase(it);
+}
+
+void pool_release_all() {
+  for (auto &kv : pool_cache) cudaFree(kv.second);
+  pool_cache.clear();
 }
 
 }  // namespace qb

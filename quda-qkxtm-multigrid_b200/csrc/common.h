@@ -51,6 +51,13 @@ struct Runtime {
 };
 Runtime &rt();
 
+// Size-bucketed caching allocator for field storage: cudaMalloc / cudaFree synchronise the device and cost
+// milliseconds at field sizes, and solvers create and drop work vectors constantly (the reference has the same
+// design: lib/malloc.cpp + the pinned/device pools of later QUDA).  Freed blocks are kept and reused by exact size.
+void *pool_malloc(size_t bytes);
+void pool_free(void *ptr);
+void pool_release_all();   // return everything cached to the driver (freeGaugeQuda / endQuda)
+
 inline int div_up(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace qb

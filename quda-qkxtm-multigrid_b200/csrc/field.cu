@@ -9,15 +9,15 @@ SpinorField::SpinorField(long Vh_, int nparity_, Prec prec_, int nspin_, int nco
   const int sb = prec == PREC_HALF ? 2 : (int)prec;
   if ((ncomplex * 2 * sb) % 16) QB_ERROR("site size %d B is not a multiple of the 16-B plane", ncomplex * 2 * sb);
   parity_bytes = (size_t)Vh * ncomplex * 2 * sb;
-  QB_CUDA(cudaMalloc(&v, parity_bytes * nparity));
-  if (prec == PREC_HALF) QB_CUDA(cudaMalloc((void **)&norm, sizeof(float) * Vh * nparity));
+  v = pool_malloc(parity_bytes * nparity);
+  if (prec == PREC_HALF) norm = (float *)pool_malloc(sizeof(float) * Vh * nparity);
   owner = true;
 }
 
 SpinorField::~SpinorField() {
   if (owner) {
-    if (v) cudaFree(v);
-    if (norm) cudaFree(norm);
+    if (v) pool_free(v);
+    if (norm) pool_free(norm);
   }
 }
 

@@ -186,6 +186,7 @@ void endQuda(void) {
     blas::end();
     pipe_cleanup_c();
     free_staging_buffers();
+    pool_release_all();
     comm_finalize();
     cudaEventDestroy(r.ev_pack_ready); cudaEventDestroy(r.ev_halo_done); cudaEventDestroy(r.ev_in_ready);
     cudaStreamDestroy(r.compute); cudaStreamDestroy(r.halo);
@@ -437,6 +438,7 @@ void freeGaugeQuda(void) {
   pool_clear();
   G.precise.reset(); G.sloppy.reset(); G.precondition.reset();
   G.lat.release();
+  pool_release_all();
   G.loaded = false;
 }
 

@@ -102,18 +102,7 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
     }
     transfer.reset(new Transfer(Bp, lp.nvec, bs, lp.spin_bs, fineX));
     for (int k = 0; k < 4; k++) mp.level[level].geo_bs[k] = bs[k];  // written back like multigrid.cpp:120-122
-    coarse_op.reset(new CoarseOperator());
-    const double tc0 = now_s();
-    matResidual->create_coarse_op(*coarse_op, *transfer);
     const MGLevelParam &cp = mp.level[level + 1];
-    if (cp.smoother_pc) coarse_op->compute_xinv();
-    QB_CUDA(cudaStreamSynchronize(rt().compute));
-    log_msg(1, "MG level %d: coarse operator %d x %d x %d x %d, N = %d built in %.3f s\n", level + 1, coarse_op->geom.X[0], coarse_op->geom.X[1],
-            coarse_op->geom.X[2], coarse_op->geom.X[3], coarse_op->N, now_s() - tc0);
-    coarseResidual.reset(new DiracCoarse(coarse_op, false, MATPC_EVEN_EVEN));
-    coarseSmooth.reset(new DiracCoarse(coarse_op, cp.smoother_pc, MATPC_EVEN_EVEN));
-    r_coarse.reset(transfer->new_coarse_field());
-    x_coarse.reset(transfer->new_coarse_field());
 
     // ---- coarse-level null vectors: restricted fine ones unless every level generates its own ----
     std::vector<std::unique_ptr<SpinorField>> Bc;
@@ -124,7 +113,20 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
         transfer->R(*Bc.back(), *B[i]);
       }
     }
+    // V holds everything the cycle needs; the near-null vectors (n_vec x 96 B/site on the fine grid) are only kept for verify()
     if (!mp.keep_null_vectors) B.clear();
+
+    coarse_op.reset(new CoarseOperator());
+    const double tc0 = now_s();
+    matResidual->create_coarse_op(*coarse_op, *transfer);
+    if (cp.smoother_pc) coarse_op->compute_xinv();
+    QB_CUDA(cudaStreamSynchronize(rt().compute));
+    log_msg(1, "MG level %d: coarse operator %d x %d x %d x %d, N = %d built in %.3f s\n", level + 1, coarse_op->geom.X[0], coarse_op->geom.X[1],
+            coarse_op->geom.X[2], coarse_op->geom.X[3], coarse_op->N, now_s() - tc0);
+    coarseResidual.reset(new DiracCoarse(coarse_op, false, MATPC_EVEN_EVEN));
+    coarseSmooth.reset(new DiracCoarse(coarse_op, cp.smoother_pc, MATPC_EVEN_EVEN));
+    r_coarse.reset(transfer->new_coarse_field());
+    x_coarse.reset(transfer->new_coarse_field());
     coarse.reset(new MG(mp, level + 1, coarseResidual.get(), coarseSmooth.get(), Bc.empty() ? nullptr : &Bc));
 
     // ---- coarse solver: the next level's cycle, wrapped in GCR(10) for a K-cycle (multigrid.cpp:225-275) ----

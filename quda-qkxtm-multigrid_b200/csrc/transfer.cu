@@ -136,11 +136,12 @@ __global__ void __launch_bounds__(128) prolong_kernel(float4 *out, const float4 
 
 // CTA = one aggregate; threads = (32 site lanes) x (nvec/2 vector pairs).  Deterministic: fixed site order
 // per lane, shuffle tree across lanes (the reference uses cub::BlockReduce, restrictor.cu:159-237).
+template <int NKP>  // NKP = Nf/2 known at compile time (full unrolling => all V loads of a site in flight), 0 = generic
 __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V, const int *c2f, long Vh_f, long Vh_c, int Nf, int nvec,
                                 int cpc, int block_sites) {
   const int X = blockIdx.x;  // coarse full index
   const int lane = threadIdx.x, jp = threadIdx.y;
-  const int nkp = Nf / 2, nvh = nvec / 2;
+  const int nkp = NKP ? NKP : Nf / 2, nvh = nvec / 2;
   cplx<float> acc[2][2];  // [chirality][j within pair]
 #pragma unroll
   for (int s = 0; s < 2; s++) { acc[s][0] = cplx<float>(0.f, 0.f); acc[s][1] = cplx<float>(0.f, 0.f); }
@@ -148,6 +149,24 @@ __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V,
     const int fs = c2f[(size_t)X * block_sites + i];
     const int parity = fs >= Vh_f ? 1 : 0;
     const long cb = fs - (long)parity * Vh_f;
+    if (NKP > 0) {
+      // issue every load of this site before the first use: 3 * NKP independent 128-bit requests in flight per thread
+      float4 f[NKP ? NKP : 1], w0[NKP ? NKP : 1], w1[NKP ? NKP : 1];
+#pragma unroll
+      for (int kp = 0; kp < NKP; kp++) {
+        f[kp] = __ldg(fin + ((size_t)parity * NKP + kp) * Vh_f + cb);
+        w0[kp] = ld_stream(V + v_plane(parity, 2 * kp, jp, Nf, nvh) * Vh_f + cb);
+        w1[kp] = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, Nf, nvh) * Vh_f + cb);
+      }
+#pragma unroll
+      for (int kp = 0; kp < NKP; kp++) {
+        const int S = (2 * kp) / cpc;
+        const cplx<float> f0(f[kp].x, f[kp].y), f1(f[kp].z, f[kp].w);
+        cmac_conj(acc[S][0], cplx<float>(w0[kp].x, w0[kp].y), f0); cmac_conj(acc[S][1], cplx<float>(w0[kp].z, w0[kp].w), f0);
+        cmac_conj(acc[S][0], cplx<float>(w1[kp].x, w1[kp].y), f1); cmac_conj(acc[S][1], cplx<float>(w1[kp].z, w1[kp].w), f1);
+      }
+      continue;
+    }
     for (int kp = 0; kp < nkp; kp++) {
       const float4 f = __ldg(fin + ((size_t)parity * nkp + kp) * Vh_f + cb);
       const float4 w0 = ld_stream(V + v_plane(parity, 2 * kp, jp, Nf, nvh) * Vh_f + cb);
@@ -332,8 +351,11 @@ void Transfer::R(SpinorField &co, const SpinorField &fi) const {
   if (co.prec != PREC_SINGLE || fi.prec != PREC_SINGLE) QB_ERROR("Transfer::R works in single precision");
   if (fi.nparity != 2 || co.nparity != 2 || fi.Vh != fine.Vh || co.Vh != coarse.Vh || fi.ncomplex != Nf || co.ncomplex != 2 * nvec)
     QB_ERROR("Transfer::R: field geometry mismatch");
-  restrict_kernel<<<(unsigned)coarse.V(), dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, c2f, fine.Vh,
-                                                                                 coarse.Vh, Nf, nvec, Nf / 2, block_sites);
+#define RK(NKP) restrict_kernel<NKP><<<(unsigned)coarse.V(), dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, c2f, \
+                                                                                      fine.Vh, coarse.Vh, Nf, nvec, Nf / 2, block_sites)
+  if (Nf == 12) RK(6);
+  else RK(0);
+#undef RK
   QB_CHECK_LAUNCH();
   flops += 8ll * Nf * nvec * fine.V();
 }

@@ -10,6 +10,6 @@ import bench
 o = ou.load_oracle()
 L = q.lib(); L.initQuda(0)
 L.setVerbosityQuda(q.QUDA_SUMMARIZE, b"", None)
-res = bench.run_mg_leg(q, L, o, (32, 32, 32, 64))
+res = bench.run_mg_leg(q, L, o, (32, 32, 32, 64), int(os.environ.get('QB_PRECOND', '4')))
 print({k: v for k, v in res.items() if not isinstance(v, dict)})
 L.endQuda()
