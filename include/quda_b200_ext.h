@@ -84,6 +84,16 @@ void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out);
 /* mean device time in ms (CUDA events on the compute stream) of `niter` applications on level `level` of
  * what = 0: full operator, 1: smoother operator, 2: prolongator, 3: restrictor */
 double mgTimeQudaB200(void *mg, int level, int what, int niter);
+/* Multi-right-hand-side coarse operator on the tensor cores (tcgen05, tf32) of coarse level `level` >= 1, applied to `nrhs`
+ * vectors at once (h_in / h_out = [rhs][generic host field]); the link matrices of a site are read once for all of them.
+ * what = 0: full operator M_c; 1: hopping term into the even sites; 2: Xinv on the odd sites.
+ * mode = 1: one tf32 pass (11 significant bits per operand); 3: split tf32, fp32-accurate (hi/lo operands, all four products).
+ * Reference: one right-hand side per call, lib/dslash_coarse.cu:293-333; the multi-RHS coarse grid is BASELINE config 5. */
+void mgMatMrhsQudaB200(void *mg, int level, int what, int nrhs, int mode, float *h_out, const float *h_in);
+/* largest nrhs one call accepts on that level (bounded by the 128-row MMA tile and by shared memory) */
+int mgMrhsMaxRhsQudaB200(void *mg, int level, int mode);
+/* mean device time in ms of `niter` applications of the operator above on resident block fields */
+double mgTimeMrhsQudaB200(void *mg, int level, int what, int nrhs, int mode, int niter);
 /* one multigrid cycle of level `level`:  x = MG(b) */
 void mgCycleQudaB200(void *mg, int level, float *h_x, const float *h_b);
 

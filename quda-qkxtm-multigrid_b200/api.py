@@ -137,7 +137,7 @@ EXPORTS = [
     "ncclUniqueIdQudaB200", "commsBootstrapQudaB200", "commDimPartitionedSetQudaB200",
     "commRankInfoQudaB200", "faceIndexMapQudaB200",
     "blasQudaB200", "mgVerifyQudaB200", "mgLevelInfoQudaB200", "mgProlongQudaB200", "mgRestrictQudaB200", "mgMatQudaB200",
-    "mgNullVectorQudaB200", "mgCycleQudaB200", "mgTimeQudaB200",
+    "mgNullVectorQudaB200", "mgCycleQudaB200", "mgTimeQudaB200", "mgMatMrhsQudaB200", "mgTimeMrhsQudaB200", "mgMrhsMaxRhsQudaB200",
 ]
 
 _lib = None
@@ -201,6 +201,10 @@ def lib():
     L.mgCycleQudaB200.argtypes = [_p, _i, _p, _p]
     L.mgTimeQudaB200.argtypes = [_p, _i, _i, _i]
     L.mgTimeQudaB200.restype = _d
+    L.mgMatMrhsQudaB200.argtypes = [_p, _i, _i, _i, _i, _p, _p]
+    L.mgTimeMrhsQudaB200.argtypes = [_p, _i, _i, _i, _i, _i]
+    L.mgTimeMrhsQudaB200.restype = _d
+    L.mgMrhsMaxRhsQudaB200.argtypes = [_p, _i, _i]
     _lib = L
     return L
 

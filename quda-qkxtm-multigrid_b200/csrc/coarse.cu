@@ -27,6 +27,9 @@ void CoarseOperator::allocate(const LevelGeom &g, int nvec_) {
 CoarseOperator::~CoarseOperator() {
   if (Y) cudaFree(Y);
   if (Xinv) cudaFree(Xinv);
+  if (Ymma) cudaFree(Ymma);
+  if (Xinv_mma) cudaFree(Xinv_mma);
+  if (nbr) cudaFree(nbr);
   for (int d = 0; d < 4; d++)
     for (int k = 0; k < 2; k++) {
       if (recv[d][k] && !comm_self_exchange()) cudaFree(recv[d][k]);

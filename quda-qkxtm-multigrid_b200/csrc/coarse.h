@@ -33,6 +33,11 @@ struct CoarseOperator {
   // pack the boundary slices of the parities in `parity_mask` of a coarse field and exchange them with the neighbours
   void exchange_ghost(const float *field, const long *poff, int parity_mask) const;
   void compute_xinv();    // batched in-kernel Gauss-Jordan with partial pivoting (the reference calls MAGMA, coarse_op.cuh:1466-1474)
+  // ---- tensor-core (multi-RHS) view of the same links, coarse_mrhs.cu ----
+  float *Ymma = nullptr;      // [V][9][N/2][N] float4: K-major UMMA operand image of every link matrix
+  float *Xinv_mma = nullptr;  // [V][N/2][N] float4
+  int *nbr = nullptr;         // [V][8] full-site index of x + e_d
+  void prepare_mrhs();        // (re)build the three arrays above from Y / Xinv
   ~CoarseOperator();
 };
 
@@ -83,5 +88,35 @@ struct CoarseApplyArgs {
   float a, b;
 };
 void coarse_apply(const CoarseApplyArgs &args);
+
+// R coarse vectors side by side: [parity][cb][kc = N/2][r] float4 = components 2kc, 2kc+1 of vector r.  All vectors of a
+// site are one contiguous block, which is what the multi-RHS kernel stages as its MMA operand.
+struct CoarseBlockField {
+  long Vh;
+  int nparity, N, R;
+  float *v = nullptr;
+  void **ptrs = nullptr;  // device scratch: member field pointers for pack / unpack
+  CoarseBlockField(long Vh, int nparity, int N, int R);
+  ~CoarseBlockField();
+  CoarseBlockField(const CoarseBlockField &) = delete;
+  size_t parity_float4() const { return (size_t)Vh * (N / 2) * R; }
+  size_t bytes() const { return parity_float4() * 16 * nparity; }
+  void pack(SpinorField *const *fields);          // R single fields -> block
+  void unpack(SpinorField *const *fields) const;  // block -> R single fields
+};
+
+// Same contract as CoarseApplyArgs on block fields; mode = 1: one tf32 pass (11-bit operands), 3: split tf32 (fp32-accurate)
+struct CoarseMrhsArgs {
+  const CoarseOperator *op;
+  float *out;
+  const float *in_hop, *in_diag, *xpay;
+  long out_poff[2], hop_poff[2], diag_poff[2], xpay_poff[2];  // float4 offsets of the parity blocks
+  int parity;
+  bool use_y, use_x, use_xinv;
+  float a, b;
+  int R, mode;
+};
+void coarse_apply_mrhs(const CoarseMrhsArgs &args);
+int coarse_mrhs_max_rhs(int N, int mode);
 
 }  // namespace qb

@@ -1000,6 +1000,81 @@ double mgTimeQudaB200(void *mg, int level, int what, int niter) {
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return (double)ms / niter;
 }
+// Multi-RHS tensor-core coarse operator on `nrhs` host vectors of a coarse level (level >= 1), h_in / h_out = [rhs][generic field].
+//   what = 0: full operator M_c;  1: hopping term into the even sites (reads the odd sites);  2: Xinv on the odd sites
+//   mode = 1: tf32, 3: split tf32 (fp32-accurate)
+static DiracCoarse *coarse_dirac_of(MG *m, int level) {
+  if (level < 1) QB_ERROR("the multi-RHS tensor-core operator exists on coarse levels only (level >= 1)");
+  DiracCoarse *d = dynamic_cast<DiracCoarse *>(const_cast<Dirac *>(m->matResidual));
+  if (!d) QB_ERROR("level %d has no coarse operator", level);
+  return d;
+}
+static void mrhs_args(CoarseMrhsArgs &a, const CoarseOperator &op, CoarseBlockField &out, const CoarseBlockField &in, int what, int nrhs, int mode) {
+  a = CoarseMrhsArgs{};
+  a.op = &op; a.out = out.v; a.in_hop = in.v; a.in_diag = in.v; a.xpay = nullptr;
+  const long pb = (long)in.parity_float4();
+  for (int p = 0; p < 2; p++) a.out_poff[p] = a.hop_poff[p] = a.diag_poff[p] = a.xpay_poff[p] = p * pb;
+  a.a = 1.f; a.b = 0.f; a.R = nrhs; a.mode = mode;
+  if (what == 0) { a.parity = -1; a.use_y = true; a.use_x = true; }
+  else if (what == 1) { a.parity = 0; a.use_y = true; }
+  else if (what == 2) { a.parity = 1; a.use_xinv = true; }
+  else QB_ERROR("mgMatMrhs: unknown operator %d", what);
+}
+void mgMatMrhsQudaB200(void *mg, int level, int what, int nrhs, int mode, float *h_out, const float *h_in) {
+  MG *m = mg_level(mg, level);
+  DiracCoarse *d = coarse_dirac_of(m, level);
+  CoarseOperator &op = *d->op;
+  if (what == 2 && !op.Xinv) op.compute_xinv();
+  op.prepare_mrhs();
+  std::vector<std::unique_ptr<SpinorField>> in(nrhs), out(nrhs);
+  std::vector<SpinorField *> pin(nrhs), pout(nrhs);
+  const size_t reals = (size_t)op.geom.V() * op.N * 2;
+  for (int r = 0; r < nrhs; r++) {
+    in[r].reset(new SpinorField(op.geom.Vh, 2, PREC_SINGLE, 2, op.nvec));
+    out[r].reset(new SpinorField(op.geom.Vh, 2, PREC_SINGLE, 2, op.nvec));
+    import_generic(*in[r], h_in + r * reals, rt().compute);
+    out[r]->zero(rt().compute);
+    pin[r] = in[r].get(); pout[r] = out[r].get();
+  }
+  CoarseBlockField bin(op.geom.Vh, 2, op.N, nrhs), bout(op.geom.Vh, 2, op.N, nrhs);
+  bin.pack(pin.data());
+  bout.pack(pout.data());
+  CoarseMrhsArgs a;
+  mrhs_args(a, op, bout, bin, what, nrhs, mode);
+  coarse_apply_mrhs(a);
+  bout.unpack(pout.data());
+  for (int r = 0; r < nrhs; r++) export_generic(h_out + r * reals, *out[r], rt().compute);
+}
+int mgMrhsMaxRhsQudaB200(void *mg, int level, int mode) { return coarse_mrhs_max_rhs(coarse_dirac_of(mg_level(mg, level), level)->op->N, mode); }
+// mean device time (ms) of `niter` applications of the multi-RHS operator (what as above) on resident random block fields
+double mgTimeMrhsQudaB200(void *mg, int level, int what, int nrhs, int mode, int niter) {
+  MG *m = mg_level(mg, level);
+  DiracCoarse *d = coarse_dirac_of(m, level);
+  CoarseOperator &op = *d->op;
+  if (what == 2 && !op.Xinv) op.compute_xinv();
+  op.prepare_mrhs();
+  Runtime &r = rt();
+  CoarseBlockField bin(op.geom.Vh, 2, op.N, nrhs), bout(op.geom.Vh, 2, op.N, nrhs);
+  {
+    SpinorField view;  // random numbers through the generic generator: treat the block as one long single-parity field
+    view.prec = PREC_SINGLE; view.nparity = 1; view.ncomplex = 2; view.nspin = 1; view.ncolor = 2;
+    view.Vh = (long)(bin.bytes() / 16); view.v = bin.v; view.parity_bytes = bin.bytes(); view.owner = false;
+    random_fill(view, 4242);
+  }
+  CoarseMrhsArgs a;
+  mrhs_args(a, op, bout, bin, what, nrhs, mode);
+  for (int i = 0; i < 3; i++) coarse_apply_mrhs(a);
+  cudaEvent_t e0, e1;
+  QB_CUDA(cudaEventCreate(&e0)); QB_CUDA(cudaEventCreate(&e1));
+  QB_CUDA(cudaEventRecord(e0, r.compute));
+  for (int i = 0; i < niter; i++) coarse_apply_mrhs(a);
+  QB_CUDA(cudaEventRecord(e1, r.compute));
+  QB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  QB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return (double)ms / niter;
+}
 // one multigrid cycle on level `level`: x = MG(b)
 void mgCycleQudaB200(void *mg, int level, float *h_x, const float *h_b) {
   MG *m = mg_level(mg, level);

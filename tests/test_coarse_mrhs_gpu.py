@@ -1,0 +1,126 @@
+"""GPU parity tests of the multi-RHS tensor-core coarse operator (csrc/coarse_mrhs.cu: tcgen05.mma kind::tf32, TMEM
+accumulators, bulk-copy staged link matrices) against the single-RHS fp32 coarse Dslash, which test_multigrid_gpu.py pins to
+the numpy restatement  M_c = P^dag M_oracle P  (reference: lib/dslash_coarse.cu:49-333, one right-hand side per call).
+
+Tolerances (relative L2 per right-hand side, written here as the task demands):
+  mode 3 (split tf32: hi/lo operands, all four partial products, fp32 accumulation)   <= 2e-6   -- the fp32 bar of the coarse operator
+  mode 1 (single tf32 pass, 11 significant bits per operand)                          <= 2e-3   -- preconditioner use only
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.oracle_util import rel_l2
+from tests.test_multigrid_gpu import as_c, load_gauge, mg_inv_param, vp
+
+pytestmark = pytest.mark.gpu
+
+TOL = {1: 2e-3, 3: 2e-6}
+
+
+@pytest.fixture(scope="module", params=[24, 8, 16, 32])
+def coarse_level(request, quda, oracle):
+    """2-level hierarchy on 8^3x16 with 4^4 aggregates -> 2x2x2x4 coarse lattice with N = 2 n_vec coarse components.
+    A short setup is enough: the test is about the operator, not the quality of the null space."""
+    q, L = quda, quda.lib()
+    nvec = request.param
+    X = (8, 8, 8, 16)
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.3, antiperiodic=False, seed=5)
+    load_gauge(q, g, X)
+    ip = mg_inv_param(q, 0.124, 0.02)
+    mgp = q.multigrid_param(ip, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(nvec,), setup_maxiter=10, setup_tol=1e-2, run_verify=False)
+    mg = L.newMultigridQuda(C.byref(mgp))
+    info = (C.c_int * 8)()
+    L.mgLevelInfoQudaB200(mg, 0, info)
+    Vc, N = int(np.prod(info[0:4])), info[7]
+    assert N == 2 * nvec
+    # dense coarse operator in fp64 from unit vectors through the single-RHS kernel: a unit vector picks out one column
+    # of the links with no arithmetic, so Mc holds the exact fp32 link values and Mc @ v is the exact answer
+    n = Vc * N
+    Mc = np.zeros((n, n), dtype=np.complex128)
+    e = np.zeros(2 * n, dtype=np.float32)
+    o = np.zeros(2 * n, dtype=np.float32)
+    for i in range(n):
+        e[:] = 0; e[2 * i] = 1
+        L.mgMatQudaB200(mg, 1, 0, vp(o), vp(e))
+        Mc[:, i] = as_c(o.astype(np.float64))
+    yield q, L, mg, Vc, N, Mc
+    L.destroyMultigridQuda(mg)
+
+
+def single_rhs(L, mg, vin):
+    out = np.zeros_like(vin)
+    for r in range(vin.shape[0]):
+        L.mgMatQudaB200(mg, 1, 0, vp(out[r]), vp(vin[r]))
+    return out
+
+
+def exact(Mc, vin):
+    """Mc @ v in fp64, returned in the interleaved (re, im) host order."""
+    w = (Mc @ as_c(vin.astype(np.float64)).T).T
+    out = np.empty(vin.shape, dtype=np.float64)
+    out[:, 0::2] = w.real; out[:, 1::2] = w.imag
+    return out
+
+
+@pytest.mark.parametrize("mode", [3, 1])
+@pytest.mark.parametrize("nrhs", [1, 5, 12, 16, 24, 32, 64])
+def test_full_coarse_operator_mrhs(coarse_level, nrhs, mode):
+    q, L, mg, Vc, N, Mc = coarse_level
+    if nrhs > L.mgMrhsMaxRhsQudaB200(mg, 1, mode):
+        pytest.skip("does not fit one launch (128-row MMA tile / shared memory)")
+    rng = np.random.default_rng(100 + nrhs)
+    vin = rng.standard_normal((nrhs, 2 * Vc * N)).astype(np.float32)
+    ref = exact(Mc, vin)
+    out = np.full_like(vin, np.nan)
+    L.mgMatMrhsQudaB200(mg, 1, 0, nrhs, mode, vp(out), vp(vin))
+    errs = [rel_l2(out[r].astype(np.float64), ref[r]) for r in range(nrhs)]
+    e1 = max(rel_l2(o.astype(np.float64), ref[r]) for r, o in enumerate(single_rhs(L, mg, vin[:2])))
+    print(f"N={N} nrhs={nrhs} mode={mode}: max rel-L2 vs fp64 {max(errs):.2e} (single-RHS fp32 kernel: {e1:.2e})")
+    assert max(errs) <= TOL[mode], errs
+
+
+@pytest.mark.parametrize("mode", [3, 1])
+def test_hop_and_xinv_pieces_mrhs(coarse_level, mode):
+    """The even-odd pieces used by the preconditioned coarse operator: hopping term into one parity, Xinv on the other."""
+    q, L, mg, Vc, N, Mc = coarse_level
+    nrhs = 7
+    half = Vc * N  # reals per parity = Vc/2 * N * 2
+    rng = np.random.default_rng(7)
+    vin = rng.standard_normal((nrhs, 2 * Vc * N)).astype(np.float32)
+    # (1) hop into the even sites == M applied to the odd part only, read on the even sites
+    odd_only = vin.copy(); odd_only[:, :half] = 0
+    ref = exact(Mc, odd_only)[:, :half]
+    out = np.zeros_like(vin)
+    L.mgMatMrhsQudaB200(mg, 1, 1, nrhs, mode, vp(out), vp(vin))
+    err = max(rel_l2(out[r, :half].astype(np.float64), ref[r]) for r in range(nrhs))
+    print(f"hop into even sites, N={N} mode={mode}: {err:.2e}")
+    assert err <= TOL[mode]
+    assert not out[:, half:].any()
+    # (2) w = Xinv v on the odd sites;  X w = v with X = the odd-odd block of Mc
+    w = np.zeros_like(vin)
+    L.mgMatMrhsQudaB200(mg, 1, 2, nrhs, mode, vp(w), vp(vin))
+    assert not w[:, :half].any()
+    back = exact(Mc, w)[:, half:]
+    err = max(rel_l2(back[r], vin[r, half:].astype(np.float64)) for r in range(nrhs))
+    print(f"X Xinv v = v on the odd sites, N={N} mode={mode}: {err:.2e}")
+    assert err <= 20 * TOL[mode]  # two operators (Xinv itself is an fp32 Gauss-Jordan inverse) and the conditioning of X
+
+
+def test_mrhs_linearity_and_timing_hook(coarse_level):
+    """Size-independent property: the operator is linear over the right-hand sides (column r of the block depends on
+    column r of the input only), and the timing hook runs."""
+    q, L, mg, Vc, N, Mc = coarse_level
+    nrhs = 8
+    rng = np.random.default_rng(3)
+    vin = rng.standard_normal((nrhs, 2 * Vc * N)).astype(np.float32)
+    out = np.zeros_like(vin)
+    L.mgMatMrhsQudaB200(mg, 1, 0, nrhs, 3, vp(out), vp(vin))
+    perm = rng.permutation(nrhs)
+    out2 = np.zeros_like(vin)
+    L.mgMatMrhsQudaB200(mg, 1, 0, nrhs, 3, vp(out2), vp(np.ascontiguousarray(vin[perm])))
+    assert np.array_equal(out2, out[perm])  # bit-identical: every column sees the same arithmetic
+    ms = L.mgTimeMrhsQudaB200(mg, 1, 0, nrhs, 3, 5)
+    assert ms > 0
