@@ -110,6 +110,7 @@ def run_mg_leg(q, L, oracle, X, precond=2):
         p.tol = 1e-9
         p.maxiter = 5000
         p.reliable_delta = 1e-4
+        p.verbosity = int(os.environ.get("QB_VERBOSITY", q.QUDA_SILENT))
         return p
 
     ip = inv_param()
@@ -147,6 +148,23 @@ def run_mg_leg(q, L, oracle, X, precond=2):
         flops = sites * ((8 + 1) * 8 * N * N - 2 * N)
         res[f"coarse_dslash_level{lvl}"] = {"sites": sites, "N": N, "ms": ms, "gflops": flops / ms / 1e6, "hbm_gbs": byts / ms / 1e6,
                                             "roofline_frac": byts / ms / 1e6 / peaks["hbm_gbs"], "bytes": byts}
+    # multi-RHS coarse Dslash of level 1 on the tensor cores (tcgen05 tf32, csrc/coarse_mrhs.cu): the links of a site are read
+    # once for all right-hand sides; compulsory bytes = links + every vector read once and written once
+    info = (C.c_int * 8)()
+    L.mgLevelInfoQudaB200(mg, 0, info)
+    sites, N = int(np.prod(info[0:4])), info[7]
+    single_ms = res["coarse_dslash_level1"]["ms"]
+    mrhs = {}
+    for mode, name in ((1, "tf32"), (3, "split_tf32_fp32_accurate")):
+        for nrhs in (12, 16, 32):
+            if nrhs > L.mgMrhsMaxRhsQudaB200(mg, 1, mode):
+                continue
+            ms = L.mgTimeMrhsQudaB200(mg, 1, 0, nrhs, mode, 50)
+            byts = sites * (9 * N * N * 8 + 2 * nrhs * N * 8)
+            flops = sites * nrhs * ((8 + 1) * 8 * N * N - 2 * N)
+            mrhs[f"{name}_nrhs{nrhs}"] = {"ms": ms, "ms_per_rhs": ms / nrhs, "speedup_per_rhs_vs_single": single_ms * nrhs / ms, "tflops": flops / ms / 1e9,
+                                          "hbm_gbs": byts / ms / 1e6, "roofline_frac": byts / ms / 1e6 / peaks["hbm_gbs"]}
+    res["coarse_dslash_level1_multi_rhs_tensor_core"] = mrhs
     for what, name in ((2, "prolong"), (3, "restrict")):
         ms = L.mgTimeQudaB200(mg, 0, what, 50)
         byts = V * (8 * 12 * 24 + 96)

@@ -460,6 +460,8 @@ template <int N, int M, int MODE> static void launch_mrhs(MrhsKernelArgs &k) {
   // with a third / fourth work slot when the link ring is already deep
   int W = 2, S = 3;
   if (C::smem_bytes(S, W, k.R) > (size_t)max_smem) QB_ERROR("multi-RHS coarse kernel: %d right-hand sides do not fit shared memory", k.R);
+  // MODE 3: the builders do the hi / lo split of the link tile and need a third work slot more than a deep link ring
+  if (MODE == 3 && C::smem_bytes(4, 3, k.R) <= (size_t)max_smem) { W = 3; S = 4; }
   while (S < MRHS_MAX_STAGES && C::smem_bytes(S + 1, W, k.R) <= (size_t)max_smem) S++;
   while (W < MRHS_MAX_WORK && S > 6 && C::smem_bytes(S - 1, W + 1, k.R) <= (size_t)max_smem) { W++; S--; }
   while (W < MRHS_MAX_WORK && C::smem_bytes(S, W + 1, k.R) <= (size_t)max_smem) W++;
