@@ -385,7 +385,7 @@ def main():
             except Exception:
                 traffic = None
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # reported on rank 0 at N = 1 only (torchrun also pins OMP_NUM_THREADS=1)
             cpu = cpu_baseline_port(oracle, g, sp)
         dtype = {8: "f64", 4: "f32", 2: "i16-storage/f32-math"}[args.prec]
         line = {

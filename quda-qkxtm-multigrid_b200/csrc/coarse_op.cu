@@ -42,9 +42,9 @@ __global__ void decompress_gauge_kernel(float *out, const void *src, Geom g, lon
   for (int k = 0; k < 9; k++) { dst[2 * k] = (float)(U[k].re * ls); dst[2 * k + 1] = (float)(U[k].im * ls); }
 }
 
-static float *decompress_gauge(const GaugeField &gf, const Geom &g) {
+float *decompress_gauge(const GaugeField &gf, const Geom &g) {
   float *out;
-  QB_CUDA(cudaMalloc((void **)&out, sizeof(float) * 18 * 8 * gf.Vh));
+  out = (float *)pool_malloc(sizeof(float) * 18 * 8 * gf.Vh);
   const int bs = 256, nb = div_up(8 * gf.Vh, bs);
   cudaStream_t s = rt().compute;
 #define DC(ST, RC) decompress_gauge_kernel<ST, RC><<<nb, bs, 0, s>>>(out, gf.data, g, gf.Vh)
@@ -359,6 +359,10 @@ static void fill_transfer_args(GalerkinArgs &a, const Transfer &T) {
 void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a) {
   if (T.Nf != 12) QB_ERROR("build_coarse_from_fine: transfer is not defined on a Wilson-type fine field");
   out.allocate(T.coarse, T.nvec);
+  if (galerkin_mma_supported(T)) {  // tensor-core build (coarse_op_mma.cu)
+    build_coarse_from_fine_mma(out, T, gauge, fine_geom, kappa, twist_a);
+    return;
+  }
   float *U = decompress_gauge(gauge, fine_geom);
   GalerkinArgs a{};
   fill_transfer_args(a, T);
@@ -372,7 +376,7 @@ void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeF
     }
   launch_galerkin<0>(a, T.coarse.V());
   QB_CUDA(cudaStreamSynchronize(rt().compute));
-  QB_CUDA(cudaFree(U));
+  pool_free(U);
   for (int d = 0; d < 4; d++)
     if (ug[d]) QB_CUDA(cudaFree(ug[d]));
 }

@@ -896,6 +896,7 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   for (int l = 0; l < mp.n_level - 1; l++)
     for (int d = 0; d < 4; d++) mgp->geo_block_size[l][d] = mp.level[l].geo_bs[d];
   QB_CUDA(cudaDeviceSynchronize());
+  pool_release_all();  // the setup's multi-GB scratch (site-major V, decompressed links) goes back to the driver
   mgp->secs = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
   mgp->gflops = 0;
   r.verbosity = saved_verbosity;

@@ -124,3 +124,42 @@ def test_mrhs_linearity_and_timing_hook(coarse_level):
     assert np.array_equal(out2, out[perm])  # bit-identical: every column sees the same arithmetic
     ms = L.mgTimeMrhsQudaB200(mg, 1, 0, nrhs, 3, 5)
     assert ms > 0
+
+
+@pytest.mark.parametrize("nvec", [24, 16, 8])
+def test_tensor_core_coarse_link_build_matches_cuda_core_build(quda, oracle, nvec):
+    """The Galerkin coarse-link build on the tensor cores (csrc/coarse_op_mma.cu: split-tf32 tcgen05 MMAs, accumulators flushed
+    into fp32 every 32 sites) against the fp32 CUDA-core build (csrc/coarse_op.cu, pinned to P^dag M_oracle P in
+    test_multigrid_gpu.py): same V (the setup is deterministic), coarse operators compared through M_c applied to random vectors.
+    Tolerance 3e-6 relative L2: both builds carry fp32 rounding of a 9 x 256-term sum."""
+    import os
+    q, L = quda, quda.lib()
+    X = (8, 8, 8, 16)
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.3, antiperiodic=True, seed=11)
+    load_gauge(q, g, X, antiperiodic=True)
+    outs = {}
+    rng = np.random.default_rng(5)
+    vin = None
+    for use_mma in (0, 1):
+        os.environ["QB_GALERKIN_MMA"] = str(use_mma)
+        ip = mg_inv_param(q, 0.124, 0.02)
+        mgp = q.multigrid_param(ip, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(nvec,), setup_maxiter=10, setup_tol=1e-2, run_verify=False)
+        mg = L.newMultigridQuda(C.byref(mgp))
+        info = (C.c_int * 8)()
+        L.mgLevelInfoQudaB200(mg, 0, info)
+        Vc, N = int(np.prod(info[0:4])), info[7]
+        if vin is None:
+            vin = rng.standard_normal((4, 2 * Vc * N)).astype(np.float32)
+        outs[use_mma] = single_rhs(L, mg, vin)
+        dev = (C.c_double * 3)()
+        L.mgVerifyQudaB200(mg, 0, dev)
+        print(f"n_vec={nvec} mma={use_mma}: verify deviations {list(dev)}")
+        devs = outs.setdefault("dev", {}); devs[use_mma] = dev[2]  # |R M P eta - M_c eta| / |.|: the Galerkin identity, checked inside the library
+        L.destroyMultigridQuda(mg)
+    os.environ.pop("QB_GALERKIN_MMA")
+    err = max(rel_l2(outs[1][r].astype(np.float64), outs[0][r].astype(np.float64)) for r in range(4))
+    print(f"n_vec={nvec}: tensor-core vs CUDA-core coarse operator, rel-L2 {err:.2e}")
+    assert err < 3e-6
+    # the Galerkin identity holds as well with the tensor-core links as with the CUDA-core ones (fp32 noise of R M P itself)
+    assert outs["dev"][1] < max(3e-5, 1.5 * outs["dev"][0]), outs["dev"]

@@ -54,11 +54,12 @@ def as_c(a):
     return a[..., 0::2] + 1j * a[..., 1::2]
 
 
-def test_transfer_and_galerkin_coarse_operator(quda, oracle):
+@pytest.mark.parametrize("nvec", [4, 8])
+def test_transfer_and_galerkin_coarse_operator(quda, oracle, nvec):
+    """n_vec = 4: CUDA-core coarse-link build (coarse_op.cu); n_vec = 8: tensor-core build (coarse_op_mma.cu, tcgen05 split tf32)."""
     q, L = quda, quda.lib()
     X = (4, 4, 4, 8)
     bs = (2, 2, 2, 2)
-    nvec = 4
     kappa, mu = 0.124, 0.05
     oracle.set_dims(X)
     g = oracle.weak_gauge(eps=0.3, antiperiodic=True, seed=99)
