@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <vector>
 #include "layout.cuh"
+#include <cstdlib>
 #include "transfer.h"
 #include "comm.h"
 
@@ -200,6 +201,75 @@ __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V,
   }
 }
 
+// Row-major variant of the restrictor for fine lattices with Xh % 8 == 0 (every fine level of practical size).
+// The aggregate-major kernel above gathers V in runs of bs_x / 2 sites (32 bytes for 4^4 blocks) scattered over the 144
+// planes of V: every access opens another DRAM page, ~52 % of the HBM roofline.  Here a CTA owns the aggregates of one
+// (by, bz, bt) block row over XL = min(Xh, 32) consecutive checkerboard x positions, and a warp reads RS = 32 / XL
+// consecutive y rows at a time: when XL = Xh these are adjacent in memory, i.e. one contiguous 512-byte run per V plane,
+// the access pattern of the prolongator.  lane <-> x position <-> aggregate, so each lane accumulates for one aggregate
+// over all rows of the block; the final reduction is a fixed shuffle tree over the row lanes and the bs_x / 2 lanes of
+// the aggregate (deterministic).
+template <int NKP>
+__global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const float4 *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
+                                     long Vh_c, int nvec, int cpc, int XL) {
+  const int lane = threadIdx.x, jp = threadIdx.y, nvh = nvec / 2;
+  const int RS = 32 / XL;
+  const int xl = lane % XL, rs = lane / XL;
+  const long Vh_f = fg.Vh;
+  const int ng = fg.Xh / XL, nby = fg.X[1] / b1, nbz = fg.X[2] / b2;
+  int bid = blockIdx.x;
+  const int g = bid % ng; bid /= ng;
+  const int by = bid % nby; bid /= nby;
+  const int bz = bid % nbz;
+  const int bt = bid / nbz;
+  const int nyg = b1 / RS;                 // groups of RS consecutive y rows inside the block
+  const int niter = 2 * nyg * b2 * b3;     // (parity, y group, z, t)
+  cplx<float> acc[2][2];  // [chirality][j within pair]
+#pragma unroll
+  for (int s = 0; s < 2; s++) { acc[s][0] = cplx<float>(0.f, 0.f); acc[s][1] = cplx<float>(0.f, 0.f); }
+  long first_fs = -1;
+  for (int it = 0; it < niter; it++) {
+    const int parity = it & 1;
+    int r = it >> 1;
+    const int yg = r % nyg; r /= nyg;
+    const int y = by * b1 + yg * RS + rs, z = bz * b2 + r % b2, t = bt * b3 + r / b2;
+    const long cb = (((long)t * fg.X[2] + z) * fg.X[1] + y) * fg.Xh + XL * g + xl;
+    if (first_fs < 0) first_fs = (long)parity * Vh_f + cb;
+    float4 f[NKP], w0[NKP], w1[NKP];
+#pragma unroll
+    for (int kp = 0; kp < NKP; kp++) {
+      f[kp] = __ldg(fin + ((size_t)parity * NKP + kp) * Vh_f + cb);
+      w0[kp] = ld_stream(V + v_plane(parity, 2 * kp, jp, 2 * NKP, nvh) * Vh_f + cb);
+      w1[kp] = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, 2 * NKP, nvh) * Vh_f + cb);
+    }
+#pragma unroll
+    for (int kp = 0; kp < NKP; kp++) {
+      const int S = (2 * kp) / cpc;
+      const cplx<float> f0(f[kp].x, f[kp].y), f1(f[kp].z, f[kp].w);
+      cmac_conj(acc[S][0], cplx<float>(w0[kp].x, w0[kp].y), f0); cmac_conj(acc[S][1], cplx<float>(w0[kp].z, w0[kp].w), f0);
+      cmac_conj(acc[S][0], cplx<float>(w1[kp].x, w1[kp].y), f1); cmac_conj(acc[S][1], cplx<float>(w1[kp].z, w1[kp].w), f1);
+    }
+  }
+  const int spa = b0 / 2;  // lanes (cb x positions) per aggregate
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int qq = 0; qq < 2; qq++) {
+      float re = acc[s][qq].re, im = acc[s][qq].im;
+      for (int o = 16; o >= XL; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+      for (int o = 1; o < spa; o <<= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+      acc[s][qq] = cplx<float>(re, im);
+    }
+  if (rs == 0 && (xl % spa) == 0) {
+    const int X = f2c[first_fs];
+    const int cpar = X >= Vh_c ? 1 : 0;
+    const long ccb = X - (long)cpar * Vh_c;
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+      out[((size_t)cpar * nvec + (size_t)s * nvh + jp) * Vh_c + ccb] = make_float4(acc[s][0].re, acc[s][0].im, acc[s][1].re, acc[s][1].im);
+  }
+}
+
 // face site (3-d lexicographic >> 1 of the remaining coordinates, as in the fine Dslash) -> cb index on slice x_mu = slice
 __device__ __forceinline__ long level_face_to_cb(int mu, int fidx, int slice, int parity, const int *X) {
   const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
@@ -353,7 +423,16 @@ void Transfer::R(SpinorField &co, const SpinorField &fi) const {
     QB_ERROR("Transfer::R: field geometry mismatch");
 #define RK(NKP) restrict_kernel<NKP><<<(unsigned)coarse.V(), dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, c2f, \
                                                                                       fine.Vh, coarse.Vh, Nf, nvec, Nf / 2, block_sites)
-  if (Nf == 12) RK(6);
+  const int b0 = geo_bs[0];
+  // lanes per row: the whole row if it fits a warp (contiguous runs over consecutive y rows), else pieces of 8
+  int XL = 0;
+  if (fine.Xh == 8 || fine.Xh == 16 || fine.Xh % 32 == 0) XL = fine.Xh < 32 ? fine.Xh : 32;
+  else if (fine.Xh % 8 == 0) XL = 8;
+  if (Nf == 12 && XL && (b0 == 2 || b0 == 4 || b0 == 8) && geo_bs[1] % (32 / XL) == 0 && !getenv("QB_RESTRICT_OLD")) {
+    const unsigned nblk = (unsigned)((fine.Xh / XL) * (fine.X[1] / geo_bs[1]) * (fine.X[2] / geo_bs[2]) * (fine.X[3] / geo_bs[3]));
+    restrict_rows_kernel<6><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, f2c, fine, b0, geo_bs[1],
+                                                                            geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL);
+  } else if (Nf == 12) RK(6);
   else RK(0);
 #undef RK
   QB_CHECK_LAUNCH();

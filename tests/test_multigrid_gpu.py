@@ -295,3 +295,36 @@ print("RESULT", res, p.iter)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     res, it = r.stdout.strip().split("RESULT")[-1].split()
     assert float(res) < 5e-8 and int(it) < 60, r.stdout[-1000:]
+
+
+@pytest.mark.parametrize("X,bs", [((16, 8, 8, 8), (4, 4, 4, 4)), ((32, 4, 4, 8), (8, 2, 2, 4)), ((16, 4, 4, 4), (2, 2, 2, 2))])
+def test_restrictor_is_adjoint_of_prolongator_row_major_kernel(quda, oracle, X, bs):
+    """Lattices with X/2 a multiple of 8 take the row-major restrictor (restrict_rows_kernel): <R f, c> = <f, P c> for random
+    f, c (R = P^dag, lib/restrictor.cu:90-125 vs lib/prolongator.cu:41-56), and R agrees with the aggregate-major kernel."""
+    import os
+    q, L = quda, quda.lib()
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.3, antiperiodic=False, seed=3)
+    load_gauge(q, g, X)
+    ip = mg_inv_param(q, 0.124, 0.02)
+    nvec = 8
+    mgp = q.multigrid_param(ip, n_level=2, geo_block=(bs,), n_vec=(nvec,), setup_maxiter=5, setup_tol=1e-1, run_verify=False)
+    mg = L.newMultigridQuda(C.byref(mgp))
+    info = (C.c_int * 8)()
+    L.mgLevelInfoQudaB200(mg, 0, info)
+    Vf, Vc, N = int(np.prod(X)), int(np.prod(info[0:4])), info[7]
+    rng = np.random.default_rng(2)
+    f = rng.standard_normal(2 * Vf * 12).astype(np.float32)
+    c = rng.standard_normal(2 * Vc * N).astype(np.float32)
+    Rf = np.zeros_like(c); Pc = np.zeros_like(f)
+    L.mgRestrictQudaB200(mg, 0, vp(Rf), vp(f))
+    L.mgProlongQudaB200(mg, 0, vp(Pc), vp(c))
+    lhs = np.vdot(as_c(Rf.astype(np.float64)), as_c(c.astype(np.float64)))
+    rhs = np.vdot(as_c(f.astype(np.float64)), as_c(Pc.astype(np.float64)))
+    assert abs(lhs - rhs) <= 2e-6 * np.linalg.norm(f) * np.linalg.norm(Pc)
+    os.environ["QB_RESTRICT_OLD"] = "1"
+    Rf_old = np.zeros_like(c)
+    L.mgRestrictQudaB200(mg, 0, vp(Rf_old), vp(f))
+    os.environ.pop("QB_RESTRICT_OLD")
+    assert rel_l2(Rf.astype(np.float64), Rf_old.astype(np.float64)) < 1e-6
+    L.destroyMultigridQuda(mg)
