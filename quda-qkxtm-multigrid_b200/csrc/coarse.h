@@ -106,6 +106,9 @@ struct CoarseBlockField {
   size_t bytes() const { return parity_float4() * 16 * nparity; }
   void pack(SpinorField *const *fields);          // R single fields -> block
   void unpack(SpinorField *const *fields) const;  // block -> R single fields
+  // the same with raw device pointers to [plane][cb] float4 blocks of matching parity count (e.g. one parity of full fields)
+  void pack_ptrs(const void *const *ptrs);
+  void unpack_ptrs(const void *const *ptrs) const;
 };
 
 // Same contract as CoarseApplyArgs on block fields; mode = 1: one tf32 pass (11-bit operands), 3: split tf32 (fp32-accurate)

@@ -130,6 +130,16 @@ static void block_copy(CoarseBlockField &b, SpinorField *const *f, int to_block)
   block_pack_kernel<<<div_up(n, 256), 256, 0, s>>>((float4 *)b.v, (const float4 *const *)b.ptrs, b.R, b.N / 2, b.Vh, b.nparity, to_block);
   QB_CHECK_LAUNCH();
 }
+static void block_copy_ptrs(CoarseBlockField &b, const void *const *src, int to_block) {
+  cudaStream_t s = rt().compute;
+  QB_CUDA(cudaMemcpyAsync(b.ptrs, src, sizeof(void *) * b.R, cudaMemcpyHostToDevice, s));
+  QB_CUDA(cudaStreamSynchronize(s));
+  const long n = (long)b.nparity * b.Vh * (b.N / 2) * b.R;
+  block_pack_kernel<<<div_up(n, 256), 256, 0, s>>>((float4 *)b.v, (const float4 *const *)b.ptrs, b.R, b.N / 2, b.Vh, b.nparity, to_block);
+  QB_CHECK_LAUNCH();
+}
+void CoarseBlockField::pack_ptrs(const void *const *p) { block_copy_ptrs(*this, p, 1); }
+void CoarseBlockField::unpack_ptrs(const void *const *p) const { block_copy_ptrs(const_cast<CoarseBlockField &>(*this), p, 0); }
 void CoarseBlockField::pack(SpinorField *const *f) { block_copy(*this, f, 1); }
 void CoarseBlockField::unpack(SpinorField *const *f) const { block_copy(const_cast<CoarseBlockField &>(*this), f, 0); }
 

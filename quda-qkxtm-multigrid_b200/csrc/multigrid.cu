@@ -167,10 +167,36 @@ void MG::generate_null_vectors() {
   sp.verbosity = mp.verbosity >= 3 ? 3 : 0;
   DiracMatrix ms(matSmooth);
   std::unique_ptr<SpinorField> b(new_full(*matResidual));
+  auto seed_of = [&](int i) { return 0x5EEDull + 7919ull * (unsigned long long)(level * 1000 + i) + 104729ull * (unsigned long long)rt().rank; };
+  auto orthonormalise_and_keep = [&](std::unique_ptr<SpinorField> &x) {
+    const int i = (int)B.size();
+    for (int j = 0; j < i; j++) {
+      const Complex a = blas::cDotProduct(*B[j], *x);
+      blas::caxpy(-a, *B[j], *x);
+    }
+    const double n2 = blas::norm2(*x);
+    if (!(n2 > 1e-16)) QB_ERROR("Cannot orthogonalize %d vector", i);
+    blas::ax(1.0 / sqrt(n2), *x);
+    B.push_back(std::move(x));
+  };
+  if (level >= 1 && B.empty() && block_null_vectors_supported(matSmooth, lp.nvec)) {
+    // coarse level: all solves advance together on block fields, the operator runs on the tensor cores (block_solver.cu)
+    std::vector<std::unique_ptr<SpinorField>> xs(lp.nvec);
+    std::vector<SpinorField *> px(lp.nvec);
+    for (int i = 0; i < lp.nvec; i++) {
+      xs[i].reset(new_full(*matResidual));
+      random_fill(*xs[i], seed_of(i));
+      px[i] = xs[i].get();
+    }
+    const int it = block_null_vectors(matSmooth, px, mp.setup_maxiter, mp.setup_tol);
+    log_msg(1, "MG level %d: %d null vectors from one batched BiCGStab on the multi-RHS tensor-core operator (%d iterations)\n", level + 1, lp.nvec, it);
+    for (int i = 0; i < lp.nvec; i++) orthonormalise_and_keep(xs[i]);
+    return;
+  }
   while ((int)B.size() < lp.nvec) {
     const int i = (int)B.size();
     std::unique_ptr<SpinorField> x(new_full(*matResidual));
-    random_fill(*x, 0x5EEDull + 7919ull * (unsigned long long)(level * 1000 + i) + 104729ull * (unsigned long long)rt().rank);
+    random_fill(*x, seed_of(i));
     blas::zero(*b);
     BiCGStab solve(ms, ms, sp);
     SpinorField src, sol;
