@@ -87,6 +87,26 @@ void tmref_wil_mat(void *out, void **gauge, void *in, double kappa, int dagger, 
 void tmref_wil_matpc(void *out, void **gauge, void *in, double kappa, int matpc, int dagger, int prec_bytes)
 { wil_matpc(out, gauge, in, kappa, (QudaMatPCType)matpc, dagger, (QudaPrecision)prec_bytes, gparam_); }
 
+// twisted-clover host path of the reference (tests/clover_reference.cpp) and its clover generator (tests/test_util.cpp:1116)
+void tmref_construct_clover(void *clover, double norm, double diag, int prec_bytes, unsigned seed)
+{ srand(seed); construct_clover_field(clover, norm, diag, (QudaPrecision)prec_bytes); }
+
+void tmref_apply_clover(void *out, void *clover, void *in, int parity, int prec_bytes)
+{ apply_clover(out, clover, in, parity, (QudaPrecision)prec_bytes); }
+
+void tmref_tmc_dslash(void *out, void **gauge, void *in, void *clover, void *cinv, double kappa, double mu, int flavor,
+                      int parity, int matpc, int dagger, int prec_bytes)
+{ tmc_dslash(out, gauge, in, clover, cinv, kappa, mu, (QudaTwistFlavorType)flavor, parity, (QudaMatPCType)matpc, dagger,
+             (QudaPrecision)prec_bytes, gparam_); }
+
+void tmref_tmc_mat(void *out, void **gauge, void *clover, void *in, double kappa, double mu, int flavor, int dagger, int prec_bytes)
+{ tmc_mat(out, gauge, clover, in, kappa, mu, (QudaTwistFlavorType)flavor, dagger, (QudaPrecision)prec_bytes, gparam_); }
+
+void tmref_tmc_matpc(void *out, void **gauge, void *in, void *clover, void *cinv, double kappa, double mu, int flavor,
+                     int matpc, int dagger, int prec_bytes)
+{ tmc_matpc(out, gauge, in, clover, cinv, kappa, mu, (QudaTwistFlavorType)flavor, (QudaMatPCType)matpc, dagger,
+            (QudaPrecision)prec_bytes, gparam_); }
+
 int tmref_volume(void) { return V; }
 
 } // extern "C"

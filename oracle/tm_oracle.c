@@ -217,6 +217,18 @@ void orc_construct_weak_gauge(double *const *gauge, double eps, int antiperiodic
   }
 }
 
+/* random clover term of the reference's tests (tests/test_util.cpp:1100-1114 constructCloverField): uniform entries in
+ * (-norm, norm) from glibc rand(), `diag` added to the 2 x 6 diagonal entries; 72 reals per site, even sites first */
+void orc_construct_clover(double *res, double norm, double diag, unsigned seed)
+{
+  const double c = 2.0 * norm / RAND_MAX;
+  srand(seed);
+  for (long i = 0; i < orc_lat.V; i++) {
+    for (int j = 0; j < 72; j++) res[i * 72 + j] = c * rand() - norm;
+    for (int j = 0; j < 6; j++) { res[i * 72 + j] += diag; res[i * 72 + j + 36] += diag; }
+  }
+}
+
 #define REAL double
 #define SUF _d
 #include "tm_oracle_impl.h"

@@ -202,6 +202,152 @@ void FN(orc_tm_matpc)(REAL *out, REAL *const *gauge, const REAL *in, double kapp
   free(tmp);
 }
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Twisted-clover (and Wilson-clover) host path: /root/reference/tests/clover_reference.cpp
+ *   apply_clover / cloverReference   :19-79   packed clover: per site and chirality 6 real diagonal
+ *                                             entries, then the 15 complex strictly-lower-triangular
+ *                                             entries column by column (QUDA_PACKED_CLOVER_ORDER)
+ *   applyTwist                       :160-192 out = tmpH + i a gamma5 in
+ *   twistCloverGamma5                :203-232 direct: C + i a g5;  inverse: cInv (C - i a0 g5), cInv = (C^2 + a0^2)^-1
+ *   tmc_dslash :234-255, tmc_mat :257-282, tmc_matpc :284-341
+ * Same operation order as the reference (fp64 agrees to the bit); inputs are never modified.
+ * ------------------------------------------------------------------------------------------- */
+void FN(orc_apply_clover)(REAL *out, const REAL *clover, const REAL *in, int parity)
+{
+  const long Vh = orc_lat.Vh;
+  const int N = 6, chiralBlock = 36;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < Vh; i++) {
+    const REAL *In = in + i * 24;
+    REAL *Out = out + i * 24;
+    for (int chi = 0; chi < 2; chi++) {
+      const REAL *D = clover + ((parity * Vh + i) * 2 + chi) * chiralBlock;
+      const REAL *L = D + N;
+      for (int col = 0; col < N; col++) {
+        const int Col = chi * N + col;
+        REAL re = 0, im = 0;
+        for (int row = 0; row < N; row++) {
+          const int Row = chi * N + row;
+          const REAL br = In[2 * Row], bi = In[2 * Row + 1];
+          if (row == col) {
+            re += D[row] * br; im += D[row] * bi;
+          } else if (col < row) {
+            const int k = N * (N - 1) / 2 - (N - col) * (N - col - 1) / 2 + row - col - 1;
+            const REAL ar = L[2 * k], ai = -L[2 * k + 1];  /* conj(L[k]) */
+            re += ar * br - ai * bi; im += ar * bi + ai * br;
+          } else {
+            const int k = N * (N - 1) / 2 - (N - row) * (N - row - 1) / 2 + col - row - 1;
+            const REAL ar = L[2 * k], ai = L[2 * k + 1];
+            re += ar * br - ai * bi; im += ar * bi + ai * br;
+          }
+        }
+        Out[2 * Col] = re; Out[2 * Col + 1] = im;
+      }
+    }
+  }
+}
+
+static void FN(apply_twist_)(REAL *out, const REAL *in, const REAL *tmpH, double a)
+{
+  const long Vh = orc_lat.Vh;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < Vh; i++)
+    for (int s = 0; s < 4; s++) {
+      const REAL a5 = (REAL)(((s / 2) ? -1.0 : +1.0) * a);
+      for (int c = 0; c < 3; c++) {
+        const long o = i * 24 + s * 6 + c * 2;
+        const REAL xr = in[o], xi = in[o + 1];
+        out[o] = tmpH[o] - a5 * xi;
+        out[o + 1] = tmpH[o + 1] + a5 * xr;
+      }
+    }
+}
+
+void FN(orc_twist_clover_gamma5)(REAL *out, const REAL *in, const REAL *clover, const REAL *cinv, int dagger, double kappa, double mu,
+                                 int flavor, int parity, int inverse)
+{
+  const long Vh = orc_lat.Vh;
+  REAL *tmp1 = (REAL *)malloc(sizeof(REAL) * Vh * 24), *tmp2 = (REAL *)malloc(sizeof(REAL) * Vh * 24);
+  if (!inverse) {
+    double a = 2.0 * kappa * mu * flavor;
+    if (dagger) a *= -1.0;
+    FN(orc_apply_clover)(tmp1, clover, in, parity);
+    FN(apply_twist_)(tmp2, in, tmp1, a);
+    memcpy(out, tmp2, sizeof(REAL) * Vh * 24);
+  } else {
+    double a = -2.0 * kappa * mu * flavor;
+    if (dagger) a *= -1.0;
+    FN(orc_apply_clover)(tmp1, clover, in, parity);
+    FN(apply_twist_)(tmp2, in, tmp1, a);
+    FN(orc_apply_clover)(tmp1, cinv, tmp2, parity);
+    memcpy(out, tmp1, sizeof(REAL) * Vh * 24);
+  }
+  free(tmp1); free(tmp2);
+}
+
+void FN(orc_tmc_dslash)(REAL *out, REAL *const *gauge, const REAL *in, const REAL *clover, const REAL *cinv, double kappa, double mu, int flavor,
+                        int parity, int matpc, int dagger)
+{
+  const long Vh = orc_lat.Vh;
+  REAL *tmp1 = (REAL *)malloc(sizeof(REAL) * Vh * 24), *tmp2 = (REAL *)malloc(sizeof(REAL) * Vh * 24);
+  if (dagger) {
+    FN(orc_twist_clover_gamma5)(tmp1, in, clover, cinv, dagger, kappa, mu, flavor, 1 - parity, 1);
+    if (!FN(symmetric_)(matpc)) {
+      FN(orc_wil_dslash)(tmp2, gauge, tmp1, parity, dagger);
+      FN(orc_twist_clover_gamma5)(out, tmp2, clover, cinv, dagger, kappa, mu, flavor, parity, 1);
+    } else {
+      FN(orc_wil_dslash)(out, gauge, tmp1, parity, dagger);
+    }
+  } else {
+    FN(orc_wil_dslash)(tmp1, gauge, in, parity, dagger);
+    FN(orc_twist_clover_gamma5)(out, tmp1, clover, cinv, dagger, kappa, mu, flavor, parity, 1);
+  }
+  free(tmp1); free(tmp2);
+}
+
+void FN(orc_tmc_mat)(REAL *out, REAL *const *gauge, const REAL *clover, const REAL *in, double kappa, double mu, int flavor, int dagger)
+{
+  const long Vh = orc_lat.Vh, V = 2 * Vh;
+  REAL *tmp = (REAL *)malloc(sizeof(REAL) * V * 24);
+  FN(orc_wil_dslash)(out + Vh * 24, gauge, in, 1, dagger);
+  FN(orc_twist_clover_gamma5)(tmp + Vh * 24, in + Vh * 24, clover, NULL, dagger, kappa, mu, flavor, 1, 0);
+  FN(orc_wil_dslash)(out, gauge, in + Vh * 24, 0, dagger);
+  FN(orc_twist_clover_gamma5)(tmp, in, clover, NULL, dagger, kappa, mu, flavor, 0, 0);
+  FN(xpay_)(tmp, (REAL)-kappa, out, V * 24);
+  free(tmp);
+}
+
+void FN(orc_tmc_matpc)(REAL *out, REAL *const *gauge, const REAL *in, const REAL *clover, const REAL *cinv, double kappa, double mu, int flavor,
+                       int matpc, int dagger)
+{
+  const long Vh = orc_lat.Vh;
+  const double kappa2 = -kappa * kappa;
+  const int p = (matpc == ORC_MATPC_EVEN_EVEN || matpc == ORC_MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p;
+  REAL *tmp1 = (REAL *)malloc(sizeof(REAL) * Vh * 24), *tmp2 = (REAL *)malloc(sizeof(REAL) * Vh * 24);
+  if (FN(symmetric_)(matpc)) {
+    if (!dagger) {
+      FN(orc_wil_dslash)(out, gauge, in, q, dagger);
+      FN(orc_twist_clover_gamma5)(tmp1, out, clover, cinv, dagger, kappa, mu, flavor, q, 1);
+      FN(orc_wil_dslash)(tmp2, gauge, tmp1, p, dagger);
+      FN(orc_twist_clover_gamma5)(out, tmp2, clover, cinv, dagger, kappa, mu, flavor, p, 1);
+    } else {
+      FN(orc_twist_clover_gamma5)(out, in, clover, cinv, dagger, kappa, mu, flavor, p, 1);
+      FN(orc_wil_dslash)(tmp1, gauge, out, q, dagger);
+      FN(orc_twist_clover_gamma5)(tmp2, tmp1, clover, cinv, dagger, kappa, mu, flavor, q, 1);
+      FN(orc_wil_dslash)(out, gauge, tmp2, p, dagger);
+    }
+    FN(xpay_)(in, (REAL)kappa2, out, Vh * 24);
+  } else {
+    FN(orc_wil_dslash)(tmp1, gauge, in, q, dagger);
+    FN(orc_twist_clover_gamma5)(tmp2, tmp1, clover, cinv, dagger, kappa, mu, flavor, q, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp2, p, dagger);
+    FN(orc_twist_clover_gamma5)(tmp2, in, clover, cinv, dagger, kappa, mu, flavor, p, 0);
+    FN(xpay_)(tmp2, (REAL)kappa2, out, Vh * 24);
+  }
+  free(tmp1); free(tmp2);
+}
+
 #undef FN
 #undef CAT
 #undef CAT_
