@@ -28,6 +28,7 @@ QUDA_RECONSTRUCT_NO, QUDA_RECONSTRUCT_12, QUDA_RECONSTRUCT_8 = 18, 12, 8
 QUDA_GAUGE_FIXED_NO, QUDA_GAUGE_FIXED_YES = 0, 1
 QUDA_WILSON_DSLASH, QUDA_CLOVER_WILSON_DSLASH = 0, 1
 QUDA_TWISTED_MASS_DSLASH, QUDA_TWISTED_CLOVER_DSLASH = 7, 8
+QUDA_FLOAT_CLOVER_ORDER, QUDA_FLOAT2_CLOVER_ORDER, QUDA_FLOAT4_CLOVER_ORDER, QUDA_PACKED_CLOVER_ORDER = 1, 2, 4, 5
 QUDA_CG_INVERTER, QUDA_BICGSTAB_INVERTER, QUDA_GCR_INVERTER, QUDA_MR_INVERTER = 0, 1, 2, 3
 QUDA_MG_INVERTER = 15
 QUDA_INVALID_INVERTER = QUDA_INVALID_ENUM
@@ -173,6 +174,7 @@ def lib():
     L.dslashQuda.argtypes = [_p, _p, IP, _i]
     L.MatQuda.argtypes = [_p, _p, IP]
     L.MatDagMatQuda.argtypes = [_p, _p, IP]
+    L.loadCloverQuda.argtypes = [_p, _p, IP]
     L.newSpinorQudaB200.argtypes = [_i, _i]
     L.newSpinorQudaB200.restype = _p
     L.freeSpinorQudaB200.argtypes = [_p]

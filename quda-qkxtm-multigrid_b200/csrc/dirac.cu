@@ -50,11 +50,26 @@ void DiracTM::WilsonDslashXpay(SpinorField &out, const SpinorField &in, int pari
   flops += 1368ll * in.Vh;
 }
 
+void DiracTM::CloverTwist(SpinorField &out, const SpinorField &in, int parity, bool inverse, const SpinorField *x, double k) const {
+  const double a0 = twist_a();
+  const CloverField &cl = clover->get(in.prec, a0);
+  if (!inverse) clover_apply(out, in, cl, parity, CLOVER_DIRECT, dagger ? -a0 : a0, x, k);
+  else clover_apply(out, in, cl, parity, dagger ? CLOVER_INVERSE_ADJ : CLOVER_INVERSE, a0, x, k);
+  flops += (inverse ? 576ll : 552ll) * in.Vh;
+}
+
 void DiracTM::Twist(SpinorField &out, const SpinorField &in) const { apply_twist_field(out, in, A()); }
 void DiracTM::TwistInv(SpinorField &out, const SpinorField &in) const { apply_twist_field(out, in, Ainv()); }
 
 // PC hop:  A^-1 D  (no dagger, or asymmetric)   |   D A^-1  (dagger & symmetric: twist on the input)
 void DiracTM::Dslash(SpinorField &out, const SpinorField &in, int parity) const {
+  if (clover) {
+    // A^-1 D  |  D A^-1 (dagger & symmetric)   with A = C + i a gamma5   (dirac_twisted_clover.cpp:191-227, clover_reference.cpp:234-255)
+    SpinorField &t = tmp(tmp2, in);
+    if (!dagger || !symmetric()) { WilsonDslash(t, in, parity); CloverTwist(out, t, parity, true); }
+    else { CloverTwist(t, in, 1 - parity, true); WilsonDslash(out, t, parity); }
+    return;
+  }
   if (flavor == 0) return WilsonDslash(out, in, parity);
   if (!dagger || !symmetric()) apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), Ainv(), nullptr, TwistCoef());
   else apply_hop(*lat, *gauge, out, in, parity, dagger, Ainv(), TwistCoef(), nullptr, TwistCoef());
@@ -70,6 +85,12 @@ void DiracTM::DslashRange(SpinorField &out, const SpinorField &in, int parity, i
 
 // out = x + k (A^-1 D | D A^-1) in     (dirac_twisted_mass.cpp:297-344: dagger alone selects the input twist)
 void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const {
+  if (clover) {
+    SpinorField &t = tmp(tmp2, in);
+    if (!dagger) { WilsonDslash(t, in, parity); CloverTwist(out, t, parity, true, &x, k); }
+    else { CloverTwist(t, in, 1 - parity, true); WilsonDslashXpay(out, t, parity, x, k); }
+    return;
+  }
   if (flavor == 0) return WilsonDslashXpay(out, in, parity, x, k);
   if (!dagger) apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), Ainv(k), &x, TwistCoef());
   else apply_hop(*lat, *gauge, out, in, parity, dagger, Ainv(), TwistCoef(k, 0.0), &x, TwistCoef());
@@ -95,6 +116,16 @@ void DiracTM::M(SpinorField &out, const SpinorField &in) const {
     SpinorField oe, oo, ie, io;
     out.view_parity(oe, 0); out.view_parity(oo, 1);
     in.view_parity(ie, 0); in.view_parity(io, 1);
+    if (clover) {
+      // out_p = (C + i a g5) in_p - kappa D in_q   (dirac_twisted_clover.cpp M, clover_reference.cpp:257-282)
+      SpinorField &t = tmp(tmp2, ie);
+      CloverTwist(t, io, 1, false);
+      apply_hop(*lat, *gauge, oo, ie, 1, dagger, TwistCoef(), TwistCoef(-kappa, 0.0), &t, TwistCoef());
+      CloverTwist(t, ie, 0, false);
+      apply_hop(*lat, *gauge, oe, io, 0, dagger, TwistCoef(), TwistCoef(-kappa, 0.0), &t, TwistCoef());
+      flops += 1368ll * 2 * in.Vh;
+      return;
+    }
     apply_hop(*lat, *gauge, oo, ie, 1, dagger, TwistCoef(), TwistCoef(-kappa, 0.0), &io, flavor ? A() : TwistCoef());
     apply_hop(*lat, *gauge, oe, io, 0, dagger, TwistCoef(), TwistCoef(-kappa, 0.0), &ie, flavor ? A() : TwistCoef());
     flops += (1320ll + 72ll) * 2 * in.Vh;
@@ -104,6 +135,26 @@ void DiracTM::M(SpinorField &out, const SpinorField &in) const {
   const double kappa2 = -kappa * kappa;
   const int p_out = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1;
   SpinorField &t = tmp(tmp1, in);
+  if (clover) {
+    if (symmetric()) {
+      if (!dagger) {
+        Dslash(t, in, 1 - p_out);                 // A^-1 D in
+        DslashXpay(out, t, p_out, in, kappa2);    // in - kappa^2 A^-1 D t
+      } else {
+        // in - kappa^2 D A^-1 D A^-1 in
+        Dslash(t, in, 1 - p_out);                 // D A^-1 in
+        DslashXpay(out, t, p_out, in, kappa2);    // in + kappa2 D A^-1 t
+      }
+    } else {
+      // (C + i a g5) in - kappa^2 D A^-1 D in, both daggers
+      SpinorField &u = tmp(tmp3, in);
+      WilsonDslash(u, in, 1 - p_out);
+      CloverTwist(t, u, 1 - p_out, true);
+      CloverTwist(u, in, p_out, false);
+      WilsonDslashXpay(out, t, p_out, u, kappa2);
+    }
+    return;
+  }
   Dslash(t, in, 1 - p_out);
   if (flavor == 0 || symmetric()) {
     DslashXpay(out, t, p_out, in, kappa2);
@@ -135,6 +186,20 @@ void DiracTM::prepare(SpinorField &src, SpinorField &sol, SpinorField &x, Spinor
   b.view_parity(bp, p); b.view_parity(bq, q);
   x.view_parity(src, q);
   x.view_parity(sol, p);
+  if (clover) {
+    // symmetric: src = A_p^-1 (b_p + kappa D A_q^-1 b_q);  asymmetric: src = b_p + kappa D A_q^-1 b_q   (dirac_twisted_clover.cpp prepare)
+    if (links_for(bq).prec != gauge->prec) QB_ERROR("clover operators need the solver vectors in the operator's precision");
+    SpinorField &t = tmp(tmp1, bq);
+    CloverTwist(t, bq, q, true);
+    if (symmetric()) {
+      SpinorField &u = tmp(tmp3, bq);
+      WilsonDslashXpay(u, t, p, bp, kappa);
+      CloverTwist(src, u, p, true);
+    } else {
+      WilsonDslashXpay(src, t, p, bp, kappa);
+    }
+    return;
+  }
   if (flavor == 0) {
     apply_hop(*lat, links_for(bq), src, bq, p, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bp, TwistCoef());
   } else if (symmetric()) {
@@ -154,6 +219,13 @@ void DiracTM::reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol
   SpinorField xp, xq, bq;
   x.view_parity(xp, p); x.view_parity(xq, q);
   b.view_parity(bq, q);
+  if (clover) {
+    // x_q = A_q^-1 (b_q + kappa D x_p)
+    SpinorField &t = tmp(tmp1, xp);
+    WilsonDslashXpay(t, xp, q, bq, kappa);
+    CloverTwist(xq, t, q, true);
+    return;
+  }
   if (flavor == 0) {
     apply_hop(*lat, links_for(xp), xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa, 0.0), &bq, TwistCoef());
   } else {

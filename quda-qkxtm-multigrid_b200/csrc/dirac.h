@@ -5,6 +5,7 @@
 // and, in coarse.h, the multigrid coarse operator.
 #pragma once
 #include <memory>
+#include "clover.h"
 #include "dslash_api.h"
 
 namespace qb {
@@ -51,9 +52,10 @@ class DiracTM : public Dirac {
   const GaugeField *gauge_vec;  // links in the precision of the solver vectors (prepare / reconstruct when they differ), may be null
   double kappa, mu;
   int flavor;   // +-1 twisted mass, 0 = plain Wilson
+  CloverSet *clover = nullptr;  // set: Wilson-clover / twisted-clover, the site-local term is C + i a gamma5 (clover.h)
   bool pc;
   int matpc_type;
-  mutable std::unique_ptr<SpinorField> tmp1, tmp2, conv_in, conv_out;
+  mutable std::unique_ptr<SpinorField> tmp1, tmp2, tmp3, conv_in, conv_out;
 
   DiracTM(Lattice *lat, const GaugeField *gauge, double kappa, double mu, int flavor, bool pc, int matpc_type, bool dagger);
   DiracType type() const override { return flavor == 0 ? (pc ? DIRAC_WILSON_PC : DIRAC_WILSON) : (pc ? DIRAC_TM_PC : DIRAC_TM); }
@@ -77,6 +79,8 @@ class DiracTM : public Dirac {
   void WilsonDslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const;
   void Twist(SpinorField &out, const SpinorField &in) const;      // A in
   void TwistInv(SpinorField &out, const SpinorField &in) const;   // A^-1 in
+  // clover operators: out(parity) = [x +] k (C + i a g5) in  /  [x +] k (C + i a g5)^-1 in, daggered as the operator is
+  void CloverTwist(SpinorField &out, const SpinorField &in, int parity, bool inverse, const SpinorField *x = nullptr, double k = 1.0) const;
 
   void Dslash(SpinorField &out, const SpinorField &in, int parity) const override;
   // Dslash restricted to the checkerboard range [begin, begin+count) of the output, on stream s (unpartitioned lattice)

@@ -25,6 +25,7 @@ struct GaugeSet {
   QudaGaugeParam param;
   std::shared_ptr<GaugeField> precise, sloppy, precondition;
   bool loaded = false;
+  CloverSet clover;  // loadCloverQuda (process-global like the gauge field, interface_quda.cpp:723-900)
 } G;
 
 void require_init() {
@@ -54,10 +55,13 @@ HostSpinorOrder to_order(QudaDiracFieldOrder o) {
 }
 
 void check_invert_param_operator(const QudaInvertParam *p) {
-  if (p->dslash_type != QUDA_TWISTED_MASS_DSLASH && p->dslash_type != QUDA_WILSON_DSLASH)
-    QB_ERROR("Unsupported dslash_type %d (this build covers Wilson and degenerate twisted mass)", (int)p->dslash_type);
+  if (p->dslash_type != QUDA_TWISTED_MASS_DSLASH && p->dslash_type != QUDA_WILSON_DSLASH && p->dslash_type != QUDA_TWISTED_CLOVER_DSLASH &&
+      p->dslash_type != QUDA_CLOVER_WILSON_DSLASH)
+    QB_ERROR("Unsupported dslash_type %d (this build covers Wilson, Wilson-clover, degenerate twisted mass and twisted clover)", (int)p->dslash_type);
   if (p->kappa == INVALID_DOUBLE) QB_ERROR("Parameter kappa undefined");
-  if (p->dslash_type == QUDA_TWISTED_MASS_DSLASH) {
+  if ((p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH) && !G.clover.loaded)
+    QB_ERROR("Clover field not allocated (call loadCloverQuda)");
+  if (p->dslash_type == QUDA_TWISTED_MASS_DSLASH || p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH) {
     if (p->mu == INVALID_DOUBLE) QB_ERROR("Parameter mu undefined");
     if (p->twist_flavor != QUDA_TWIST_PLUS && p->twist_flavor != QUDA_TWIST_MINUS)
       QB_ERROR("Twist flavor not set %d (only the degenerate +-1 flavours are supported)", (int)p->twist_flavor);
@@ -76,9 +80,12 @@ const GaugeField *pick_gauge(Prec prec) {
 // setDiracParam + Dirac::create (interface_quda.cpp:1265-1340, :1386-1410)
 DiracTM *make_dirac(const QudaInvertParam *p, bool pc, const GaugeField *gauge, double kappa_scale = 1.0, double mu_scale = 1.0) {
   check_invert_param_operator(p);
-  const int flavor = p->dslash_type == QUDA_TWISTED_MASS_DSLASH ? (int)p->twist_flavor : 0;
-  const double mu = p->dslash_type == QUDA_TWISTED_MASS_DSLASH ? p->mu * mu_scale : 0.0;
-  return new DiracTM(&G.lat, gauge, p->kappa * kappa_scale, mu, flavor, pc, (int)p->matpc_type, p->dagger == QUDA_DAG_YES);
+  const bool twisted = p->dslash_type == QUDA_TWISTED_MASS_DSLASH || p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH;
+  const int flavor = twisted ? (int)p->twist_flavor : 0;
+  const double mu = twisted ? p->mu * mu_scale : 0.0;
+  DiracTM *d = new DiracTM(&G.lat, gauge, p->kappa * kappa_scale, mu, flavor, pc, (int)p->matpc_type, p->dagger == QUDA_DAG_YES);
+  if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH) d->clover = &G.clover;
+  return d;
 }
 
 // small pool of resident work fields so that dslashQuda / MatQuda do not cudaMalloc per call
@@ -436,6 +443,7 @@ void freeGaugeQuda(void) {
   if (!G.loaded) return;
   QB_CUDA(cudaDeviceSynchronize());
   pool_clear();
+  G.clover.release();
   G.precise.reset(); G.sloppy.reset(); G.precondition.reset();
   G.lat.release();
   pool_release_all();
@@ -493,6 +501,7 @@ void pipe_cleanup_c() {
 static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaParity parity, SpinorField &in, SpinorField &out) {
   const Geom &g = G.lat.geom;
   if (g.part[0] || g.part[1] || g.part[2] || g.part[3]) return false;
+  if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH) return false;  // two kernels per hop: plain path
   if (p->input_location != QUDA_CPU_FIELD_LOCATION || p->output_location != QUDA_CPU_FIELD_LOCATION) return false;
   const int T = g.X[3];
   int nchunk = 0;
@@ -664,8 +673,23 @@ void commDimPartitionedSetQudaB200(int mask) {
 }
 
 // ---- outside the hot path: exported for link compatibility ------------------------------------
-void loadCloverQuda(void *, void *, QudaInvertParam *) { QB_ERROR("loadCloverQuda: clover operators are outside this build's scope (SURVEY.md section 8f.1)"); }
-void freeCloverQuda(void) {}
+// interface_quda.cpp:723-900.  The clover term itself must come from the host (QUDA_PACKED_CLOVER_ORDER); its inverses are
+// always computed on the device.  For a twisted-clover operator return_clover_inverse hands back (C^2 + (2 kappa mu)^2)^-1,
+// the field the reference's host verification code expects (tests/dslash_test.cpp:339-349, lib/clover_invert.cu:56-90).
+void loadCloverQuda(void *h_clover, void *h_clovinv, QudaInvertParam *p) {
+  require_gauge();
+  if (!h_clover || p->compute_clover) QB_ERROR("loadCloverQuda: computing the clover term from the gauge field is not implemented, pass h_clover");
+  if (p->clover_order != QUDA_PACKED_CLOVER_ORDER) QB_ERROR("loadCloverQuda: only QUDA_PACKED_CLOVER_ORDER is supported (got %d)", (int)p->clover_order);
+  const Prec hp = to_prec(p->clover_cpu_prec, "clover_cpu_prec");
+  G.clover.load(h_clover, hp, G.lat.geom.Vh);
+  if (h_clovinv && p->return_clover_inverse) {
+    const bool twisted = p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH;
+    const double a = twisted ? 2.0 * p->kappa * p->mu : 0.0;
+    if (twisted) G.clover.inverse_to_host(h_clovinv, hp, a * a);
+    else QB_ERROR("loadCloverQuda: return_clover_inverse is implemented for twisted clover only");
+  }
+}
+void freeCloverQuda(void) { G.clover.release(); }
 void invertMultiSrcQuda(void **, void **, QudaInvertParam *) { QB_ERROR("invertMultiSrcQuda is not implemented (SURVEY.md section 8f.4)"); }
 void invertMultiShiftQuda(void **, void *, QudaInvertParam *) { QB_ERROR("invertMultiShiftQuda is outside this build's scope"); }
 void cloverQuda(void *, void *, QudaInvertParam *, QudaParity *, int) { QB_ERROR("cloverQuda is outside this build's scope"); }
