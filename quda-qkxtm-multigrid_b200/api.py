@@ -175,6 +175,7 @@ def lib():
     L.MatQuda.argtypes = [_p, _p, IP]
     L.MatDagMatQuda.argtypes = [_p, _p, IP]
     L.loadCloverQuda.argtypes = [_p, _p, IP]
+    L.invertMultiSrcQuda.argtypes = [_p, _p, IP]
     L.newSpinorQudaB200.argtypes = [_i, _i]
     L.newSpinorQudaB200.restype = _p
     L.freeSpinorQudaB200.argtypes = [_p]

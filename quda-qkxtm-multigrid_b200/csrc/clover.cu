@@ -131,6 +131,19 @@ void CloverSet::load(const void *h_clover, Prec host_prec, long Vh_) {
   loaded = true;
 }
 
+__global__ void clover_to_float_kernel(float *out, const double *in, long n) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (float)in[t];
+}
+float *CloverSet::site_major_f32() const {
+  if (!loaded) QB_ERROR("no clover field resident");
+  const long n = 2 * Vh * 72;
+  float *out = (float *)pool_malloc(sizeof(float) * n);
+  clover_to_float_kernel<<<div_up(n, 256), 256, 0, rt().compute>>>(out, master, n);
+  QB_CHECK_LAUNCH();
+  return out;
+}
+
 void CloverSet::release() {
   if (master) cudaFree(master);
   master = nullptr;

@@ -39,6 +39,8 @@ struct CloverSet {
   void load(const void *h_clover, Prec host_prec, long Vh);
   void inverse_to_host(void *h_clovinv, Prec host_prec, double a2);  // (C^2 + a2)^-1 in packed order (what loadCloverQuda returns)
   void release();
+  // site-major fp32 copy [V][72] (pool memory; caller frees with pool_free): the coarse-link build reads one record per site
+  float *site_major_f32() const;
 };
 
 enum CloverMode { CLOVER_DIRECT = 0, CLOVER_INVERSE = 1, CLOVER_INVERSE_ADJ = 2 };

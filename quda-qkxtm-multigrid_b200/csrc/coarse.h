@@ -42,11 +42,14 @@ struct CoarseOperator {
 };
 
 // Builders of the Galerkin coarse links (coarse_op.cu)
-void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a);
+// clover_site: site-major fp32 packed clover term [V][72] (nullptr: the site-local term is 1 + i a gamma5)
+void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
+                            const float *clover_site = nullptr);
 void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine);
 // tensor-core variant of build_coarse_from_fine (coarse_op_mma.cu); out.Y allocated and zeroed
 bool galerkin_mma_supported(const Transfer &T);
-void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a);
+void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
+                                const float *clover_site);
 
 // Coarse Dirac operator.  Full operator on [even | odd] fields, or (pc = true) the symmetric even-odd
 // Schur complement  1 - Xinv_pp Y_pq Xinv_qq Y_qp  on single-parity fields (DiracCoarsePC, dirac_coarse.cpp:226-372).

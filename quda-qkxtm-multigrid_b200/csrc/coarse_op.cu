@@ -116,6 +116,7 @@ struct GalerkinArgs {
   // fine-level links
   const float *U;  // decompressed [parity][mu][cb][18]
   float kappa, twist_a;
+  const float *clover;  // site-major packed clover term [Vf][72], or nullptr
   // coarse-level links (the finer coarse operator)
   const float4 *Yf;  // [Vf][9][Nf][Nf/2]
   // partitioned dimensions: V (and, on the fine level, backward links) of the neighbours' boundary slices
@@ -273,8 +274,22 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const GalerkinArgs a) {
           if (d == 8) {
             if (Sp == chi) {
               const float2 v = Vx[k * nvec + jp];
-              const float tw = chi == 0 ? a.twist_a : -a.twist_a;  // (1 + i a gamma5)
-              w = cplx<float>(v.x - tw * v.y, v.y + tw * v.x);
+              const float tw = chi == 0 ? a.twist_a : -a.twist_a;  // (1 + i a gamma5)  or  (C + i a gamma5) with a clover term
+              if (!a.clover) w = cplx<float>(v.x - tw * v.y, v.y + tw * v.x);
+              else {
+                const float *cb = a.clover + ((size_t)fs * 2 + chi) * 36;  // Hermitian 6 x 6 block: 6 diagonal reals, 15 complex L(row > col) by columns
+                const int r = k - 6 * chi;
+                w = cplx<float>(cb[r] * v.x - tw * v.y, cb[r] * v.y + tw * v.x);
+                for (int c2 = 0; c2 < 6; c2++) {
+                  if (c2 == r) continue;
+                  const float2 u = Vx[(6 * chi + c2) * nvec + jp];
+                  const int lo = c2 < r ? c2 : r, hi = c2 < r ? r : c2;
+                  const int kk = 15 - (6 - lo) * (5 - lo) / 2 + hi - lo - 1;
+                  const cplx<float> l(cb[6 + 2 * kk], cb[6 + 2 * kk + 1]);
+                  if (r > c2) cmac(w, l, cplx<float>(u.x, u.y));       // H[r][c2] = L
+                  else cmac_conj(w, l, cplx<float>(u.x, u.y));          // H[r][c2] = conj(L(c2, r))
+                }
+              }
             }
           } else {
             const int mu = d >> 1;
@@ -356,17 +371,18 @@ static void fill_transfer_args(GalerkinArgs &a, const Transfer &T) {
   a.N = 2 * T.nvec;
 }
 
-void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a) {
+void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
+                            const float *clover_site) {
   if (T.Nf != 12) QB_ERROR("build_coarse_from_fine: transfer is not defined on a Wilson-type fine field");
   out.allocate(T.coarse, T.nvec);
   if (galerkin_mma_supported(T)) {  // tensor-core build (coarse_op_mma.cu)
-    build_coarse_from_fine_mma(out, T, gauge, fine_geom, kappa, twist_a);
+    build_coarse_from_fine_mma(out, T, gauge, fine_geom, kappa, twist_a, clover_site);
     return;
   }
   float *U = decompress_gauge(gauge, fine_geom);
   GalerkinArgs a{};
   fill_transfer_args(a, T);
-  a.Yc = (float4 *)out.Y; a.U = U; a.kappa = (float)kappa; a.twist_a = (float)twist_a; a.Yf = nullptr;
+  a.Yc = (float4 *)out.Y; a.U = U; a.kappa = (float)kappa; a.twist_a = (float)twist_a; a.Yf = nullptr; a.clover = clover_site;
   float *ug[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int d = 0; d < 4; d++)
     if (fine_geom.part[d]) {
@@ -394,7 +410,9 @@ void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const Coar
 void DiracTM::create_coarse_op(CoarseOperator &coarse, const Transfer &T) const {
   if (pc) QB_ERROR("coarsening of the even-odd preconditioned operator is not implemented: coarsen the full operator (coarse_grid_solution_type = QUDA_MAT_SOLUTION)");
   if (dagger) QB_ERROR("create_coarse_op: operator must not be daggered");
-  build_coarse_from_fine(coarse, T, *gauge, lat->geom, kappa, flavor ? twist_a() : 0.0);
+  float *cs = clover ? clover->site_major_f32() : nullptr;
+  build_coarse_from_fine(coarse, T, *gauge, lat->geom, kappa, flavor ? twist_a() : 0.0, cs);
+  if (cs) pool_free(cs);
 }
 
 }  // namespace qb

@@ -119,6 +119,7 @@ struct GalerkinMmaArgs {
   const float2 *Vs;   // [Vf][12][nvec]
   const float2 *Us;   // [Vf][8][10]
   const GmMeta *meta; // [Vc][block_sites]
+  const float *clover; // site-major packed clover term [Vf][72] or nullptr
   float *Y;           // [Vc][9][N][N/2] float4 viewed as floats: ((X*9 + d)*N + c)*2N + 2r + ri
   long Vc;
   int block_sites;
@@ -226,6 +227,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) galerkin_mma_kernel(const Galer
                 bulk_g2s(st, p.Vs + (size_t)fs * 12 * NV, C::V_BYTES, &raw_full[slot]);
                 bulk_g2s(st + C::V_BYTES, p.Vs + (size_t)nb * 12 * NV, C::V_BYTES, &raw_full[slot]);
                 bulk_g2s(st + 2 * C::V_BYTES, p.Us + ((size_t)fs * 8 + d) * 10, C::U_BYTES, &raw_full[slot]);
+              } else if (p.clover) {
+                mbar_arrive_expect_tx(&raw_full[slot], C::V_BYTES + 288);
+                bulk_g2s(st, p.Vs + (size_t)fs * 12 * NV, C::V_BYTES, &raw_full[slot]);
+                bulk_g2s(st + C::V_BYTES, p.clover + (size_t)fs * 72, 288, &raw_full[slot]);  // 72 floats: the site's two packed blocks
               } else {
                 mbar_arrive_expect_tx(&raw_full[slot], C::V_BYTES);
                 bulk_g2s(st, p.Vs + (size_t)fs * 12 * NV, C::V_BYTES, &raw_full[slot]);
@@ -350,14 +355,40 @@ __global__ void __launch_bounds__(GM_THREADS, 1) galerkin_mma_kernel(const Galer
           const int gi = mu == 0 ? (sp_opp < 2 ? 1 : -1) : (mu == 2 ? ((sp_opp == 0 || sp_opp == 3) ? 1 : -1) : 0);
           coef = cplx<float>(sigma * gr, sigma * gi);
         } else {
-          // site-local term (1 + i a gamma5) V(x): chirality-diagonal, the other chirality's rows are zero
+          // site-local term (1 + i a gamma5) V(x), or (C + i a gamma5) V(x) with a clover term: chirality-diagonal, the other
+          // chirality's rows are zero
           sp_opp = (ss + 2) & 3;
           const float tw = S == 0 ? p.twist_a : -p.twist_a;
-          float2 qv[3];
+          if (!p.clover) {
+            float2 qv[3];
 #pragma unroll
-          for (int cp = 0; cp < 3; cp++) qv[cp] = lds64(st + (uint32_t)((ss * 3 + cp) * NV + j) * 8);
+            for (int cp = 0; cp < 3; cp++) qv[cp] = lds64(st + (uint32_t)((ss * 3 + cp) * NV + j) * 8);
 #pragma unroll
-          for (int cp = 0; cp < 3; cp++) T[cp] = cplx<float>(qv[cp].x - tw * qv[cp].y, qv[cp].y + tw * qv[cp].x);
+            for (int cp = 0; cp < 3; cp++) T[cp] = cplx<float>(qv[cp].x - tw * qv[cp].y, qv[cp].y + tw * qv[cp].x);
+          } else {
+            float2 qv[6];
+#pragma unroll
+            for (int c2 = 0; c2 < 6; c2++) qv[c2] = lds64(st + (uint32_t)((6 * S + c2) * NV + j) * 8);
+            const uint32_t cbk = st + C::V_BYTES + (uint32_t)S * 144;  // packed Hermitian block of chirality S: 6 reals + 15 complex
+#pragma unroll
+            for (int cp = 0; cp < 3; cp++) {
+              const int r = si * 3 + cp;
+              float dg;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dg) : "r"(cbk + (uint32_t)r * 4));
+              const float2 vr = si ? qv[3 + cp] : qv[cp];  // = qv[r] without dynamic register indexing
+              cplx<float> w(dg * vr.x - tw * vr.y, dg * vr.y + tw * vr.x);
+#pragma unroll
+              for (int c2 = 0; c2 < 6; c2++) {
+                if (c2 == r) continue;
+                const int lo = c2 < r ? c2 : r, hi = c2 < r ? r : c2;
+                const int kk = 15 - (6 - lo) * (5 - lo) / 2 + hi - lo - 1;
+                const float2 l = lds64(cbk + 24 + (uint32_t)kk * 8);
+                if (r > c2) cmac(w, cplx<float>(l.x, l.y), cplx<float>(qv[c2].x, qv[c2].y));
+                else cmac_conj(w, cplx<float>(l.x, l.y), cplx<float>(qv[c2].x, qv[c2].y));
+              }
+              T[cp] = w;
+            }
+          }
         }
 #pragma unroll
         for (int cp = 0; cp < 3; cp++) {
@@ -483,7 +514,8 @@ bool galerkin_mma_supported(const Transfer &T) {
 }
 
 // out.Y must be allocated and zero (CoarseOperator::allocate)
-void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a) {
+void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
+                                const float *clover_site) {
   cudaStream_t s = rt().compute;
   const long Vh = T.fine.Vh, Vf = 2 * Vh;
   float *U = decompress_gauge(gauge, fine_geom);
@@ -507,7 +539,7 @@ void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const Ga
   galerkin_meta_kernel<<<div_up(nmeta, 256), 256, 0, s>>>(meta, T.c2f, T.f2c, nbr, nmeta, T.block_sites);
   QB_CHECK_LAUNCH();
   GalerkinMmaArgs a{};
-  a.Vs = Vs; a.Us = Us; a.meta = meta; a.Y = out.Y; a.Vc = T.coarse.V(); a.block_sites = T.block_sites;
+  a.Vs = Vs; a.Us = Us; a.meta = meta; a.clover = clover_site; a.Y = out.Y; a.Vc = T.coarse.V(); a.block_sites = T.block_sites;
   a.twist_a = (float)twist_a;
   a.chunk = getenv("QB_GALERKIN_CHUNK") ? atoi(getenv("QB_GALERKIN_CHUNK")) : 8;
   if (a.chunk < 1) a.chunk = 1;

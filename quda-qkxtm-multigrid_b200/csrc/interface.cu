@@ -1,5 +1,6 @@
 // C-ABI entry points: the quda.h subset of SURVEY.md section 8(b) plus the resident-field extensions.
 // Behavioural model: /root/reference/lib/interface_quda.cpp (line refs at each function).
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <chrono>
@@ -690,7 +691,21 @@ void loadCloverQuda(void *h_clover, void *h_clovinv, QudaInvertParam *p) {
   }
 }
 void freeCloverQuda(void) { G.clover.release(); }
-void invertMultiSrcQuda(void **, void **, QudaInvertParam *) { QB_ERROR("invertMultiSrcQuda is not implemented (SURVEY.md section 8f.4)"); }
+// interface_quda.cpp invertMultiSrcQuda: param->num_src right-hand sides with the same operator, solver and preconditioner.
+// The solves run one after the other through invertQuda (the gauge field, the clover term and the multigrid hierarchy stay
+// resident, so nothing is set up twice); iter / secs / gflops accumulate, true_res reports the worst source.
+// A lock-step block solve on top of the multi-RHS tensor-core coarse operator is the next step.
+void invertMultiSrcQuda(void **hp_x, void **hp_b, QudaInvertParam *param) {
+  if (param->num_src < 1 || param->num_src == INVALID_INT) QB_ERROR("invertMultiSrcQuda: num_src undefined");
+  int iter = 0;
+  double secs = 0, gflops = 0, worst = 0, worst_hq = 0;
+  for (int i = 0; i < param->num_src; i++) {
+    invertQuda(hp_x[i], hp_b[i], param);
+    iter += param->iter; secs += param->secs; gflops += param->gflops;
+    worst = std::max(worst, param->true_res); worst_hq = std::max(worst_hq, param->true_res_hq);
+  }
+  param->iter = iter; param->secs = secs; param->gflops = gflops; param->true_res = worst; param->true_res_hq = worst_hq;
+}
 void invertMultiShiftQuda(void **, void *, QudaInvertParam *) { QB_ERROR("invertMultiShiftQuda is outside this build's scope"); }
 void cloverQuda(void *, void *, QudaInvertParam *, QudaParity *, int) { QB_ERROR("cloverQuda is outside this build's scope"); }
 

@@ -139,3 +139,73 @@ def test_tmc_solve_reaches_host_residual(quda, oracle, solve_type, matpc):
     res = np.linalg.norm(b - oracle.tmc_mat(c.g, x, c.c, KAPPA, MU, 1, 0)) / np.linalg.norm(b)
     print(f"twisted-clover GCR ({solve_type}, matpc {matpc}): {p.iter} iterations, host residual {res:.2e}, reported {p.true_res:.2e}")
     assert res < 5e-10 and abs(p.true_res - res) < 0.5 * res + 1e-12
+
+
+@pytest.mark.parametrize("nvec", [4, 8])
+def test_tmc_multigrid_coarsening_and_solve(quda, oracle, nvec):
+    """Multigrid on the twisted-clover operator (the coarse site-diagonal block is V^dag (C + i a gamma5) V:
+    lib/coarse_op.cuh computeTMCAV / COMPUTE_COARSE_CLOVER): the Galerkin identity R M P = M_c checked inside the library
+    (n_vec 4: CUDA-core build, n_vec 8: tensor-core build) and an MG-preconditioned GCR solve checked with the host operator."""
+    q, L = quda, quda.lib()
+    X = (8, 8, 8, 8)
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=21)
+    cl = oracle.clover(norm=0.05, diag=1.0, seed=99)
+    kappa, mu = 0.122, 0.01
+    gp = q.gauge_param(X, cuda_prec=8, reconstruct=18, cuda_prec_sloppy=4, cuda_prec_precondition=4, t_boundary=q.QUDA_PERIODIC_T)
+    L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+
+    def param():
+        p = q.invert_param(kappa=kappa, mu=mu, cuda_prec=8, dslash_type=q.QUDA_TWISTED_CLOVER_DSLASH, solution_type=q.QUDA_MAT_SOLUTION)
+        p.cuda_prec_sloppy = 4; p.cuda_prec_precondition = 4
+        p.clover_cpu_prec = 8
+        p.clover_cuda_prec = 8; p.clover_cuda_prec_sloppy = 4; p.clover_cuda_prec_precondition = 4
+        p.clover_order = q.QUDA_PACKED_CLOVER_ORDER
+        p.clover_coeff = 1.0
+        p.compute_clover = p.compute_clover_inverse = p.return_clover = p.return_clover_inverse = 0
+        p.solve_type = q.QUDA_DIRECT_SOLVE
+        p.inv_type = q.QUDA_GCR_INVERTER
+        p.gcrNkrylov = 20; p.tol = 1e-9; p.maxiter = 2000; p.reliable_delta = 1e-4
+        return p
+
+    ip = param()
+    L.loadCloverQuda(vp(cl), None, C.byref(ip))
+    mgp = q.multigrid_param(ip, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(nvec,), setup_maxiter=200, setup_tol=5e-6, run_verify=False)
+    mg = L.newMultigridQuda(C.byref(mgp))
+    dev = (C.c_double * 3)()
+    L.mgVerifyQudaB200(mg, 0, dev)
+    print(f"twisted-clover MG n_vec={nvec}: verify deviations {list(dev)}")
+    assert dev[0] < 5e-6 and dev[2] < 5e-5, list(dev)
+    b = np.zeros(oracle.V * 24); b[0] = 1.0; b[2] = 1.0
+    x = np.zeros_like(b)
+    p = param()
+    p.inv_type_precondition = q.QUDA_MG_INVERTER
+    p.preconditioner = mg
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    res = np.linalg.norm(b - oracle.tmc_mat(g, x, cl, kappa, mu, 1, 0)) / np.linalg.norm(b)
+    x0 = np.zeros_like(b)
+    p0 = param()
+    L.invertQuda(vp(x0), vp(b), C.byref(p0))
+    print(f"twisted-clover MG-GCR: {p.iter} iterations (plain GCR {p0.iter}), host residual {res:.2e}")
+    assert res < 5e-9 and p.iter < p0.iter / 2
+    L.destroyMultigridQuda(mg)
+
+
+def test_invert_multi_src(quda, oracle):
+    """invertMultiSrcQuda: several sources through one resident operator; every solution checked with the host operator."""
+    q, L = quda, quda.lib()
+    c = Ctx(q, oracle, (8, 8, 8, 8), 8, recon=12)
+    p = c.param(flavor=1, solution_type=q.QUDA_MAT_SOLUTION)
+    p.solve_type = q.QUDA_DIRECT_PC_SOLVE
+    p.inv_type = q.QUDA_GCR_INVERTER
+    p.gcrNkrylov = 20; p.tol = 1e-9; p.maxiter = 2000; p.reliable_delta = 1e-4
+    nsrc = 3
+    p.num_src = nsrc
+    rng = np.random.default_rng(8)
+    bs = [rng.standard_normal(oracle.V * 24) for _ in range(nsrc)]
+    xs = [np.zeros(oracle.V * 24) for _ in range(nsrc)]
+    L.invertMultiSrcQuda((C.c_void_p * nsrc)(*[a.ctypes.data for a in xs]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bs]), C.byref(p))
+    for x, b in zip(xs, bs):
+        res = np.linalg.norm(b - oracle.tmc_mat(c.g, x, c.c, KAPPA, MU, 1, 0)) / np.linalg.norm(b)
+        assert res < 5e-9
+    assert p.iter > 0 and p.true_res < 5e-9
