@@ -397,7 +397,7 @@ def main():
                        "flops_per_site": FLOPS_PER_SITE, "bytes_per_site_compulsory": bpsite},
             "effective_gbs_reference_model": BYTES_REFMODEL.get((args.prec, args.recon), 0) * sites / (ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": traffic, "peak_source": peak_kind, "kernel": "dslash_kernel<StoreS,12,false,false>" if args.prec == 4 else "dslash_kernel"},
+                         "traffic": traffic, "peak_source": peak_kind, "kernel": "dslash_kernel<StoreS,12,TWIST_IN=false,HAS_X=false,GHOST=false>" if args.prec == 4 else "dslash_kernel"},
             "e2e": {"value": FLOPS_PER_SITE * sites / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": main_res["e2e_bytes"], "d2h_bytes_per_step": main_res["e2e_bytes"]},
             "gpu_launches": main_res["launches"],

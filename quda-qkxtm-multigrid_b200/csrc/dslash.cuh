@@ -112,6 +112,80 @@ template <bool DAG, typename T> __device__ __forceinline__ void su3_mul(cplx<T> 
     }
 }
 
+#ifndef QB_NO_F32X2
+// ---- fp32 math on packed pairs (f32x2.cuh): same formulas as the generic templates above, one complex number per
+// register pair, a complex multiply-accumulate in two FFMA2.  Used by the storage types with Store::packed_math
+// (B200 sweep, profiles/README_r01.md: int16 storage 111 -> 101 us per hop; fp32 storage is latency-bound and does not gain).
+__device__ __forceinline__ f2 cpk(const cplx<float> &z) { return pk2(z.re, z.im); }
+__device__ __forceinline__ f2 cpk_swap(const cplx<float> &z) { return pk2(z.im, z.re); }
+__device__ __forceinline__ cplx<float> cunpk(f2 v) { cplx<float> z; unpk2(v, z.re, z.im); return z; }
+
+// a + sigma * (re + i im) * b   for the unit (re, im)
+__device__ __forceinline__ f2 axpy_unit(int re, int im, float sigma, f2 a, const cplx<float> &b) {
+  if (re == 1) return fma2(bc2(sigma), cpk(b), a);
+  if (re == -1) return fma2(bc2(-sigma), cpk(b), a);
+  if (im == 1) return fma2(pk2(-sigma, sigma), cpk_swap(b), a);  // i b = (-b.im, b.re)
+  return fma2(pk2(sigma, -sigma), cpk_swap(b), a);
+}
+
+__device__ __forceinline__ void apply_twist_pk(cplx<float> *psi, float p, float q) {
+  const f2 pp = bc2(p), qu = pk2(-q, q), ql = pk2(q, -q);
+#pragma unroll
+  for (int k = 0; k < 12; k++) psi[k] = cunpk(fma2(k < 6 ? qu : ql, cpk_swap(psi[k]), mul2(pp, cpk(psi[k]))));
+}
+
+template <int MU> __device__ __forceinline__ void project_pk(cplx<float> *h, const cplx<float> *psi, float sigma) {
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      h[s * 3 + c] = cunpk(axpy_unit(gre(MU, s), gim(MU, s), sigma, cpk(psi[s * 3 + c]), psi[gcol(MU, s) * 3 + c]));
+}
+
+template <bool SCALED, int MU> __device__ __forceinline__ void reconstruct_acc_pk(cplx<float> *acc, const cplx<float> *chi, float sigma, float scale) {
+  if (SCALED) sigma *= scale;
+#pragma unroll
+  for (int k = 0; k < 6; k++) acc[k] = cunpk(SCALED ? fma2(bc2(scale), cpk(chi[k]), cpk(acc[k])) : add2(cpk(acc[k]), cpk(chi[k])));
+#pragma unroll
+  for (int s = 2; s < 4; s++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      acc[s * 3 + c] = cunpk(axpy_unit(gre(MU, s), gim(MU, s), sigma, cpk(acc[s * 3 + c]), chi[gcol(MU, s) * 3 + c]));
+}
+
+template <bool DAG> __device__ __forceinline__ void su3_mul_pk(cplx<float> *chi, const cplx<float> *U, const cplx<float> *h) {
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    f2 hp[3], hs[3];  // h and i*h (no dagger) / -i*h (dagger: conj(u) h = u.re h + u.im (-i h))
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      hp[c] = cpk(h[s * 3 + c]);
+      hs[c] = mul2(cpk_swap(h[s * 3 + c]), DAG ? pk2(1.0f, -1.0f) : pk2(-1.0f, 1.0f));  // one packed op, no scalar negation + pair rebuild
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      f2 a = mul2(bc2(U[DAG ? r : r * 3].re), hp[0]);
+#pragma unroll
+      for (int c = 1; c < 3; c++) a = fma2(bc2(U[DAG ? c * 3 + r : r * 3 + c].re), hp[c], a);
+#pragma unroll
+      for (int c = 0; c < 3; c++) a = fma2(bc2(U[DAG ? c * 3 + r : r * 3 + c].im), hs[c], a);
+      chi[s * 3 + r] = cunpk(a);
+    }
+  }
+}
+
+// a += b * c
+__device__ __forceinline__ void cmac_pk(cplx<float> &a, const cplx<float> &b, const cplx<float> &c) {
+  a = cunpk(fma2(pk2(-b.im, b.im), cpk_swap(c), fma2(bc2(b.re), cpk(c), cpk(a))));
+}
+#endif
+// double precision has no packed form: the *_pk names fall through to the generic templates
+__device__ __forceinline__ void apply_twist_pk(cplx<double> *psi, double p, double q) { apply_twist(psi, p, q); }
+template <int MU> __device__ __forceinline__ void project_pk(cplx<double> *h, const cplx<double> *psi, double s) { project<MU>(h, psi, s); }
+template <bool SCALED, int MU> __device__ __forceinline__ void reconstruct_acc_pk(cplx<double> *a, const cplx<double> *c, double s, double sc) { reconstruct_acc<SCALED, MU>(a, c, s, sc); }
+template <bool DAG> __device__ __forceinline__ void su3_mul_pk(cplx<double> *chi, const cplx<double> *U, const cplx<double> *h) { su3_mul<DAG>(chi, U, h); }
+__device__ __forceinline__ void cmac_pk(cplx<double> &a, const cplx<double> &b, const cplx<double> &c) { cmac(a, b, c); }
+
 // checkerboard index -> coordinates and the full lexicographic index
 __device__ __forceinline__ void cb_coords(int *x, int &full, int cb, int parity, const Geom &g) {
   const int za = cb / g.Xh;
@@ -140,15 +214,26 @@ template <typename Store, int RECON> __device__ __forceinline__ size_t link_bloc
   return (size_t)RECON * StoreTraits<Store>::real_bytes * stride;
 }
 
-// one hop: MU direction, BACK = 0 forward (x+mu), 1 backward (x-mu)
-template <typename Store, int RECON, bool TWIST_IN, int MU, int BACK>
+// packed-pair math for this storage type?  (QB_PACKED_S / QB_NO_F32X2: tuning builds)
+template <typename Store> __host__ __device__ constexpr bool use_packed() {
+#ifdef QB_NO_F32X2
+  return false;
+#else
+  return Store::packed_math;
+#endif
+}
+
+// one hop: MU direction, BACK = 0 forward (x+mu), 1 backward (x-mu); GHOST = false compiles the ghost-zone branches away
+// (unpartitioned lattices and the interior launch of partitioned ones: straight-line code, loads hoisted across hops)
+template <typename Store, int RECON, bool TWIST_IN, bool GHOST, int MU, int BACK>
 __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const DslashParam &p, const int *x, int full, int cb) {
   typedef typename Store::real real;
   const Geom &g = p.g;
   const int L = g.X[MU];
   const int step = dim_stride(MU, g);
   const bool edge = BACK ? (x[MU] == 0) : (x[MU] == L - 1);
-  const bool use_ghost = edge && g.part[MU];
+  constexpr bool PK = use_packed<Store>();
+  const bool use_ghost = GHOST && edge && g.part[MU];
   const real sigma = BACK ? (real)(-p.sgn_fwd) : (real)p.sgn_fwd;
 
   cplx<real> h[6];
@@ -162,8 +247,8 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
     nbr = nfull >> 1;
     cplx<real> psi[12];
     sc = Store::template load<12>(psi, p.in, p.in_norm, p.stride, nbr);
-    if (TWIST_IN) apply_twist(psi, (real)p.cin[0], (real)p.cin[1]);
-    project<MU>(h, psi, sigma);
+    if (TWIST_IN) { if constexpr (PK) apply_twist_pk(psi, (real)p.cin[0], (real)p.cin[1]); else apply_twist(psi, (real)p.cin[0], (real)p.cin[1]); }
+    if constexpr (PK) project_pk<MU>(h, psi, sigma); else project<MU>(h, psi, sigma);
   }
 
   // link: forward hop uses U_mu(x) (own parity, own site); backward uses U_mu(x-mu)^dag (other parity)
@@ -179,24 +264,31 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
   if (MU < 3) u0 = RECON == 8 ? (real)1 / (real)g.aniso : (real)g.aniso;
   else u0 = BACK ? (x[3] == 0 ? (real)g.tb_bwd : (real)1) : (x[3] == L - 1 ? (real)g.tb_fwd : (real)1);
   cplx<real> U[9];
-  reconstruct_link<real, RECON>(U, raw, link_u0<Store, RECON>(u0));
+  reconstruct_link<real, RECON, PK>(U, raw, link_u0<Store, RECON>(u0));
 
   cplx<real> chi[6];
-  su3_mul<BACK != 0>(chi, U, h);
-  reconstruct_acc<Store::scaled, MU>(acc, chi, sigma, sc * link_scale<Store, RECON>());
+  if constexpr (PK) {
+    su3_mul_pk<BACK != 0>(chi, U, h);
+    reconstruct_acc_pk<Store::scaled, MU>(acc, chi, sigma, sc * link_scale<Store, RECON>());
+  } else {
+    su3_mul<BACK != 0>(chi, U, h);
+    reconstruct_acc<Store::scaled, MU>(acc, chi, sigma, sc * link_scale<Store, RECON>());
+  }
 }
 
-// Launch bounds from the B200 sweep of profiles/tune_r01.md: the kernel is HBM-latency bound, so fp32 / int16
-// want maximum occupancy (64 registers, 8 CTAs of 128 threads per SM) while fp64 needs 128 registers to avoid spills.
+// Launch bounds from the B200 sweeps of profiles/README_r01.md: the kernel is HBM-latency bound; with the ghost-zone
+// branches compiled away fp32 / int16 run best at 72 registers (7 CTAs of 128 threads per SM: the extra registers let
+// the compiler keep the next hop's loads in flight), fp64 needs 128 registers to avoid spills.
 // QB_DSLASH_MINB overrides for tuning builds.
-template <typename Store> struct DslashBounds { static constexpr int max_threads = 128, min_blocks = 8; };
-template <> struct DslashBounds<StoreD> { static constexpr int max_threads = 128, min_blocks = 4; };
+template <typename Store> struct DslashBounds { static constexpr int max_threads = 128, min_blocks = 7; static constexpr bool prefetch_links = false; };
+template <> struct DslashBounds<StoreS> { static constexpr int max_threads = 128, min_blocks = 7; static constexpr bool prefetch_links = true; };
+template <> struct DslashBounds<StoreD> { static constexpr int max_threads = 128, min_blocks = 4; static constexpr bool prefetch_links = false; };
 #ifdef QB_DSLASH_MINB
 #define QB_DSLASH_BOUNDS __launch_bounds__(QB_DSLASH_MAXT, QB_DSLASH_MINB)
 #else
 #define QB_DSLASH_BOUNDS __launch_bounds__(DslashBounds<Store>::max_threads, DslashBounds<Store>::min_blocks)
 #endif
-template <typename Store, int RECON, bool TWIST_IN, bool HAS_X>
+template <typename Store, int RECON, bool TWIST_IN, bool HAS_X, bool GHOST>
 __global__ void QB_DSLASH_BOUNDS dslash_kernel(const DslashParam p) {
   typedef typename Store::real real;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,25 +302,38 @@ __global__ void QB_DSLASH_BOUNDS dslash_kernel(const DslashParam p) {
 #pragma unroll
   for (int k = 0; k < 12; k++) acc[k] = cplx<real>((real)0, (real)0);
 
-  hop<Store, RECON, TWIST_IN, 0, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, 0, 1>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, 1, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, 1, 1>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, 2, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, 2, 1>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, 3, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, 3, 1>(acc, p, x, full, cb);
+  // forward links of this site are pure DRAM streams: pull the y/z/t ones towards L2 before their hops need them
+  // (fp32 storage only: 102.7 -> 100.8 us on B200; int16 unchanged, fp64 slower -- profiles/README_r01.md)
+  if (DslashBounds<Store>::prefetch_links && RECON != 18) {
+    const size_t eb = 4 * StoreTraits<Store>::real_bytes;
+#pragma unroll
+    for (int mu = 1; mu < 4; mu++)
+#pragma unroll
+      for (int k = 0; k < RECON / 4; k++) {
+        const char *a = (const char *)p.gauge_fwd + mu * link_block_bytes<Store, RECON>(p.stride) + ((size_t)k * p.stride + cb) * eb;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      }
+  }
+  hop<Store, RECON, TWIST_IN, GHOST, 0, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, 0, 1>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, 1, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, 1, 1>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, 2, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, 2, 1>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, 3, 0>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, 3, 1>(acc, p, x, full, cb);
 
   // epilogue: out = Cx x + Co acc
-  apply_twist(acc, (real)p.co[0], (real)p.co[1]);
+  constexpr bool PK = use_packed<Store>();
+  if constexpr (PK) apply_twist_pk(acc, (real)p.co[0], (real)p.co[1]); else apply_twist(acc, (real)p.co[0], (real)p.co[1]);
   if (HAS_X) {
     cplx<real> xs[12];
     const real xsc = Store::template load<12, false>(xs, p.x, p.x_norm, p.stride, cb);
     const cplx<real> cu((real)p.cx[0] * xsc, (real)p.cx[1] * xsc), cl((real)p.cx[0] * xsc, -(real)p.cx[1] * xsc);
 #pragma unroll
-    for (int k = 0; k < 6; k++) cmac(acc[k], cu, xs[k]);
+    for (int k = 0; k < 6; k++) { if constexpr (PK) cmac_pk(acc[k], cu, xs[k]); else cmac(acc[k], cu, xs[k]); }
 #pragma unroll
-    for (int k = 6; k < 12; k++) cmac(acc[k], cl, xs[k]);
+    for (int k = 6; k < 12; k++) { if constexpr (PK) cmac_pk(acc[k], cl, xs[k]); else cmac(acc[k], cl, xs[k]); }
   }
   Store::template store<12>(p.out, p.out_norm, p.stride, cb, acc);
 }

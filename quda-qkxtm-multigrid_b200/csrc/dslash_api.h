@@ -8,7 +8,7 @@ struct DslashParam;
 struct PackParam;
 struct StoreD; struct StoreS; struct StoreH;
 
-template <typename Store> void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, int block, cudaStream_t s);
+template <typename Store> void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, bool ghost, int block, cudaStream_t s);
 template <typename Store> void launch_pack_T(const PackParam &p, bool twist_in, cudaStream_t s);
 template <typename Store> void launch_twist_T(void *out, float *out_norm, const void *in, const float *in_norm, long stride, int n, double pr, double qr, cudaStream_t s);
 

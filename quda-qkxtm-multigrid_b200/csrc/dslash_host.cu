@@ -143,7 +143,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   const bool partitioned = g.part[0] || g.part[1] || g.part[2] || g.part[3];
   if (!partitioned) {
     p.site_begin = range_begin; p.site_count = range_count < 0 ? g.Vh : range_count; p.site_list = nullptr;
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, range_stream ? range_stream : r.compute);
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, range_stream ? range_stream : r.compute);
     return;
   }
   if (range_count >= 0) QB_ERROR("apply_hop_range is only available on unpartitioned lattices");
@@ -195,7 +195,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   DslashParam pb = p;
   if (lat.n_boundary[np]) {
     pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
-    launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, block, r.halo);
+    launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, r.halo);
   }
   QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
 
@@ -204,7 +204,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     p.site_count = lat.n_interior[np];
     if (lat.interior_contiguous[np]) { p.site_begin = lat.interior_begin[np]; p.site_list = nullptr; }
     else { p.site_begin = 0; p.site_list = lat.interior_list[np]; }
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, block, r.compute);
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, r.compute);
   }
   QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
 }

@@ -6,26 +6,34 @@
 
 namespace qb {
 
-template <typename Store, int RECON>
+template <typename Store, int RECON, bool GHOST>
 static void launch_dslash_recon(const DslashParam &p, bool twist_in, bool has_x, int block, cudaStream_t s) {
   const int nb = div_up(p.site_count, block);
   if (nb == 0) return;
   if (twist_in) {
-    if (has_x) dslash_kernel<Store, RECON, true, true><<<nb, block, 0, s>>>(p);
-    else dslash_kernel<Store, RECON, true, false><<<nb, block, 0, s>>>(p);
+    if (has_x) dslash_kernel<Store, RECON, true, true, GHOST><<<nb, block, 0, s>>>(p);
+    else dslash_kernel<Store, RECON, true, false, GHOST><<<nb, block, 0, s>>>(p);
   } else {
-    if (has_x) dslash_kernel<Store, RECON, false, true><<<nb, block, 0, s>>>(p);
-    else dslash_kernel<Store, RECON, false, false><<<nb, block, 0, s>>>(p);
+    if (has_x) dslash_kernel<Store, RECON, false, true, GHOST><<<nb, block, 0, s>>>(p);
+    else dslash_kernel<Store, RECON, false, false, GHOST><<<nb, block, 0, s>>>(p);
   }
   QB_CHECK_LAUNCH();
 }
 
 template <typename Store>
-void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, int block, cudaStream_t s) {
-  if (recon == 18) launch_dslash_recon<Store, 18>(p, twist_in, has_x, block, s);
-  else if (recon == 12) launch_dslash_recon<Store, 12>(p, twist_in, has_x, block, s);
-  else if (recon == 8) launch_dslash_recon<Store, 8>(p, twist_in, has_x, block, s);
-  else QB_ERROR("unsupported reconstruct %d", recon);
+void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, bool ghost, int block, cudaStream_t s) {
+  // ghost = false: no site of this launch has a neighbour in a ghost zone (unpartitioned lattice, interior launch)
+  if (ghost) {
+    if (recon == 18) launch_dslash_recon<Store, 18, true>(p, twist_in, has_x, block, s);
+    else if (recon == 12) launch_dslash_recon<Store, 12, true>(p, twist_in, has_x, block, s);
+    else if (recon == 8) launch_dslash_recon<Store, 8, true>(p, twist_in, has_x, block, s);
+    else QB_ERROR("unsupported reconstruct %d", recon);
+  } else {
+    if (recon == 18) launch_dslash_recon<Store, 18, false>(p, twist_in, has_x, block, s);
+    else if (recon == 12) launch_dslash_recon<Store, 12, false>(p, twist_in, has_x, block, s);
+    else if (recon == 8) launch_dslash_recon<Store, 8, false>(p, twist_in, has_x, block, s);
+    else QB_ERROR("unsupported reconstruct %d", recon);
+  }
 }
 
 template <typename Store>
@@ -44,7 +52,7 @@ void launch_twist_T(void *out, float *out_norm, const void *in, const float *in_
 }
 
 #define QB_INSTANTIATE_DSLASH(Store)                                                                          \
-  template void launch_dslash_T<Store>(const DslashParam &, int, bool, bool, int, cudaStream_t);              \
+  template void launch_dslash_T<Store>(const DslashParam &, int, bool, bool, bool, int, cudaStream_t);              \
   template void launch_pack_T<Store>(const PackParam &, bool, cudaStream_t);                                  \
   template void launch_twist_T<Store>(void *, float *, const void *, const float *, long, int, double, double, cudaStream_t);
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "field.h"
+#include "f32x2.cuh"
 
 namespace qb {
 
@@ -74,6 +75,7 @@ struct StoreD {
   typedef double real;
   static constexpr Prec prec = PREC_DOUBLE;
   static constexpr bool scaled = false;
+  static constexpr bool packed_math = false;
   template <int NC, bool NC_PATH = true>
   __device__ __forceinline__ static double load(cplx<double> *o, const void *base, const float *, long stride, long i) {
     const double2 *p = (const double2 *)base + i;
@@ -96,6 +98,11 @@ struct StoreS {
   typedef float real;
   static constexpr Prec prec = PREC_SINGLE;
   static constexpr bool scaled = false;
+#ifdef QB_SCALAR_S
+  static constexpr bool packed_math = false;
+#else
+  static constexpr bool packed_math = true;  // f32x2.cuh
+#endif
   template <int NC, bool NC_PATH = true>
   __device__ __forceinline__ static float load(cplx<float> *o, const void *base, const float *, long stride, long i) {
     const float4 *p = (const float4 *)base + i;
@@ -123,13 +130,23 @@ struct StoreS {
 __device__ __forceinline__ void unpack_s16x2_raw(int w, float &a, float &b) {
   const unsigned lo = __byte_perm((unsigned)w, 0x4B000000u, 0x7610);
   const unsigned hi = __byte_perm((unsigned)w, 0x4B000000u, 0x7632);
+#ifndef QB_NO_F32X2
+  unpk2(add2(pk2(__uint_as_float(lo), __uint_as_float(hi)), bc2(-8421376.0f)), a, b);
+#else
   a = __uint_as_float(lo) - 8421376.0f;
   b = __uint_as_float(hi) - 8421376.0f;
+#endif
 }
 // fp32 -> offset-binary int16 pair, round to nearest even: x*scale + (1.5*2^23 + 32768) leaves u in the low mantissa bits
 __device__ __forceinline__ int pack_s16x2(float a, float b, float scale) {
+#ifndef QB_NO_F32X2
+  float fa, fb;
+  unpk2(fma2(pk2(a, b), bc2(scale), bc2(12615680.0f)), fa, fb);
+  const unsigned ia = __float_as_uint(fa), ib = __float_as_uint(fb);
+#else
   const unsigned ia = __float_as_uint(fmaf(a, scale, 12615680.0f));
   const unsigned ib = __float_as_uint(fmaf(b, scale, 12615680.0f));
+#endif
   return (int)__byte_perm(ia, ib, 0x5410);
 }
 
@@ -138,6 +155,7 @@ struct StoreH {
   typedef float real;
   static constexpr Prec prec = PREC_HALF;
   static constexpr bool scaled = true;
+  static constexpr bool packed_math = true;  // f32x2.cuh
   template <int NC, bool NC_PATH = true>
   __device__ __forceinline__ static float load(cplx<float> *o, const void *base, const float *norm, long stride, long i) {
     const float c = (NC_PATH ? ld_nc(norm + i) : norm[i]) * (1.0f / HALF_MAX);
@@ -281,7 +299,7 @@ template <typename Store, int RECON> __device__ __forceinline__ typename Store::
 //  recon  8: a2,a3,b1 + phases of a1 and c1 (Bunk/Sommer, cf. lib/read_gauge.h:403-483)
 // u0: recon 12 -> factor of the reconstructed row (anisotropy for spatial, boundary sign for temporal links);
 //     recon  8 -> factor of the whole link (1/anisotropy resp. boundary sign).
-template <typename real, int RECON>
+template <typename real, int RECON, bool PK = false>
 __device__ __forceinline__ void reconstruct_link(cplx<real> *U, const real *r, real u0) {
   if (RECON == 18) {
 #pragma unroll
@@ -289,6 +307,26 @@ __device__ __forceinline__ void reconstruct_link(cplx<real> *U, const real *r, r
   } else if (RECON == 12) {
 #pragma unroll
     for (int k = 0; k < 6; k++) U[k] = cplx<real>(r[2 * k], r[2 * k + 1]);
+#ifndef QB_NO_F32X2
+    if constexpr (PK && sizeof(real) == 4) {
+      // conj(a b) = a.re (b.re, -b.im) + (-a.im) (b.im, b.re): a from row 0 as broadcast scalars, b from row 1 as pairs
+      f2 cb[3], sb[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { cb[k] = mul2(pk2(U[3 + k].re, U[3 + k].im), pk2(1.0f, -1.0f)); sb[k] = pk2(U[3 + k].im, U[3 + k].re); }
+      const f2 u02 = bc2(u0);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int i = (k + 1) % 3, j = (k + 2) % 3;  // row2[k] = conj(U[i] U[3+j] - U[j] U[3+i]) u0
+        f2 t = mul2(bc2(U[i].re), cb[j]);
+        t = fma2(bc2(-U[i].im), sb[j], t);
+        t = fma2(bc2(-U[j].re), cb[i], t);
+        t = fma2(bc2(U[j].im), sb[i], t);
+        t = mul2(t, u02);
+        unpk2(t, U[6 + k].re, U[6 + k].im);
+      }
+      return;
+    }
+#endif
     U[6] = conj(U[1] * U[5] - U[2] * U[4]);
     U[7] = conj(U[2] * U[3] - U[0] * U[5]);
     U[8] = conj(U[0] * U[4] - U[1] * U[3]);

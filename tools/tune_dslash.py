@@ -15,16 +15,16 @@ from tests import oracle_util as ou
 o = ou.load_oracle(); X=(32,32,32,64); o.set_dims(X)
 g = o.gauge(1, True, 1.0, 137); sp = o.drand(o.Vh*24, 137)
 L = q.lib(); L.initQuda(0)
-for prec, recon in ((4,12),(2,12),(8,12),(4,18),(4,8)):
+for prec, recon in eval(os.environ.get('QB_TUNE_CASES', '((2,12),(4,12),(2,18),(4,18),(8,12),(4,8))')):
     gp = q.gauge_param(X, cuda_prec=prec, reconstruct=recon)
     L.loadGaugeQuda((C.c_void_p*4)(*[a.ctypes.data for a in g]), C.byref(gp))
     p = q.invert_param(cuda_prec=prec)
     fi = L.newSpinorQudaB200(1, prec); fo = L.newSpinorQudaB200(1, prec)
     L.loadSpinorQudaB200(fi, sp.ctypes.data_as(C.c_void_p), C.byref(p))
-    for bs in (64, 96, 128, 192, 256):
+    for bs in (64, 128):
         L.setDslashBlockSizeQudaB200(bs)
         L.timeDslashQudaB200(fo, fi, C.byref(p), 0, 10, None)
-        ms = L.timeDslashQudaB200(fo, fi, C.byref(p), 0, 100, None)
+        ms = L.timeDslashQudaB200(fo, fi, C.byref(p), 0, int(os.environ.get('QB_TUNE_ITER', '100')), None)
         print("TUNE lib=%%s prec=%%d recon=%%d block=%%d us=%%.2f" %% (os.path.basename(q.LIB_PATH), prec, recon, bs, ms*1e3), flush=True)
     L.freeSpinorQudaB200(fi); L.freeSpinorQudaB200(fo)
 L.endQuda()
