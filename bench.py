@@ -134,9 +134,38 @@ def run_mg_leg(q, L, oracle, X, precond=2):
     p0 = inv_param()
     x0 = np.zeros_like(b)
     L.invertQuda(vp(x0), vp(b), C.byref(p0))
+    # 12 spin-colour point sources of one propagator: invertMultiSrcQuda on the block path (all sources through the K-cycle in
+    # lock-step, coarse levels on the multi-RHS tensor-core operator) against the same call with the block path switched off
+    multi = None
+    if os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
+        nsrc = int(os.environ.get("QB_BENCH_NSRC", "12"))
+        bs = []
+        for k in range(nsrc):
+            bk = np.zeros(V * 24); bk[2 * k] = 1.0
+            bs.append(bk)
+        xs = [np.zeros(V * 24) for _ in range(nsrc)]
+        multi = {"sources": nsrc}
+        for name, env in (("block", "1"), ("sequential", "0")):
+            os.environ["QB_BLOCK_MG"] = env
+            pm = inv_param()
+            pm.inv_type_precondition = q.QUDA_MG_INVERTER
+            pm.preconditioner = mg
+            pm.num_src = nsrc
+            ptr_x, ptr_b = (C.c_void_p * nsrc)(*[a.ctypes.data for a in xs]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bs])
+            if name == "block":
+                L.invertMultiSrcQuda(ptr_x, ptr_b, C.byref(pm))  # warm-up (allocations), as for the single solve above
+            t0 = time.perf_counter()
+            L.invertMultiSrcQuda(ptr_x, ptr_b, C.byref(pm))
+            wall = time.perf_counter() - t0
+            multi[name] = {"solve_seconds": pm.secs, "seconds_per_source": pm.secs / nsrc, "wall_seconds_incl_h2d_d2h": wall, "iterations": pm.iter, "worst_true_res": pm.true_res}
+        os.environ.pop("QB_BLOCK_MG", None)
+        multi["speedup_per_source"] = multi["sequential"]["solve_seconds"] / multi["block"]["solve_seconds"]
+        del bs, xs
     res = {"lattice": list(X), "levels": 3, "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond], "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
            "setup_seconds": setup_s, "solve_seconds": p.secs, "solve_wall_seconds_incl_h2d_d2h": wall_s, "iterations": p.iter,
            "true_res": p.true_res, "tol": 1e-9, "plain_gcr_seconds": p0.secs, "plain_gcr_iterations": p0.iter, "plain_gcr_true_res": p0.true_res}
+    if multi:
+        res["multi_src_12_point_sources"] = multi
     peaks, _ = measured_peaks()
     for lvl in (1, 2):
         info = (C.c_int * 8)()

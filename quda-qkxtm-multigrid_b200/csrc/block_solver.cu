@@ -7,8 +7,10 @@
 // kernel (coarse_mrhs.cu) and its links are read once per iteration for all right-hand sides.  Each right-hand side keeps
 // its own Krylov scalars and its own convergence test; a converged column is frozen (its coefficients become zero).
 // The arithmetic per column is that of BiCGStab::operator() in solver.cu.
+#include <chrono>
 #include <cmath>
 #include <complex>
+#include <functional>
 #include <cstdlib>
 #include <vector>
 #include "coarse.h"
@@ -231,6 +233,491 @@ int block_null_vectors(const Dirac *matSmooth, std::vector<SpinorField *> &x, in
     QB_CUDA(cudaStreamSynchronize(s));
   }
   return longest;
+}
+
+
+// =====================================================================================================================
+// Block multigrid: R right-hand sides through the K-cycle together (reference: invertMultiSrcQuda
+// include/quda.h:647 + the composite ColorSpinorField).  On the coarse levels the R vectors live side by side in block
+// fields, every operator application is ONE launch of the tensor-core multi-RHS kernel (links read once for all R), and
+// the Krylov scalars are kept per column; a converged column gets zero coefficients.  The fine level keeps one field per
+// right-hand side and runs the single-RHS kernels column by column (the fine hop is HBM-bound on its own vectors).
+// The per-column arithmetic is that of MR::operator() / GCR::operator() in solver.cu.
+// =====================================================================================================================
+namespace {
+
+typedef std::complex<double> Cx;
+typedef std::vector<char> Mask;
+
+// optional wall-clock profile of the block cycle (QUDA_B200_MG_PROFILE=1): sections bracketed by stream syncs
+static double bnow_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool block_profile_on() { static int on = -1; if (on < 0) on = (getenv("QUDA_B200_MG_PROFILE") && atoi(getenv("QUDA_B200_MG_PROFILE"))) ? 1 : 0; return on == 1; }
+struct BSection {
+  double *acc; double t0; bool on;
+  explicit BSection(double *a) : acc(a), on(block_profile_on()) { if (on) { cudaStreamSynchronize(rt().compute); t0 = bnow_s(); } }
+  ~BSection() { if (on) { cudaStreamSynchronize(rt().compute); *acc += bnow_s() - t0; } }
+};
+
+static bool any_active(const Mask &m) { for (char c : m) if (c) return true; return false; }
+
+// ---- vector-set policies -------------------------------------------------------------------------------------------
+// R coarse vectors in one block buffer of n4 float4 (one parity or a full field)
+struct BlockOps {
+  typedef float *Vec;
+  int R; long n4; BlockBlas blas_;
+  std::vector<Cx> none;
+  BlockOps(long n4_, int R_) : R(R_), n4(n4_), blas_(n4_, R_) {}
+  Vec make() { Vec v = (Vec)pool_malloc((size_t)n4 * 16); QB_CUDA(cudaMemsetAsync(v, 0, (size_t)n4 * 16, rt().compute)); return v; }
+  void release(Vec v) { pool_free(v); }
+  void copy(Vec d, Vec s_, const Mask &) { QB_CUDA(cudaMemcpyAsync(d, s_, (size_t)n4 * 16, cudaMemcpyDeviceToDevice, rt().compute)); }
+  void zero(Vec d, const Mask &) { QB_CUDA(cudaMemsetAsync(d, 0, (size_t)n4 * 16, rt().compute)); }
+  void cdot(Vec x, Vec y, std::vector<Cx> &dot, std::vector<double> &nx, const Mask &) { blas_.cdot(x, y, dot, nx); }
+  void axpy(const std::vector<Cx> &a, Vec x, Vec y, const Mask &) { blas_.axpy<0>(a, none, x, nullptr, y); }   // y += a x
+  void scale(const std::vector<double> &a, Vec x, const Mask &) {
+    std::vector<Cx> c(R);
+    for (int r = 0; r < R; r++) c[r] = Cx(a[r], 0.0);
+    blas_.axpy<3>(c, none, x, nullptr, x);
+  }
+  // beta[i][c] = <v_i, y>_c for i < k, then y -= sum_i beta_i v_i   (one vector at a time: modified Gram-Schmidt)
+  void ortho(const std::vector<Vec> &v, int k, Vec y, std::vector<std::vector<Cx>> &beta, const Mask &live) {
+    std::vector<Cx> dot, coef(R);
+    std::vector<double> nx;
+    beta.assign(k, std::vector<Cx>(R));
+    for (int i = 0; i < k; i++) {
+      blas_.cdot(v[i], y, dot, nx);
+      for (int c = 0; c < R; c++) { beta[i][c] = live[c] ? dot[c] : Cx(0, 0); coef[c] = -beta[i][c]; }
+      axpy(coef, v[i], y, live);
+    }
+  }
+  // y += sum_i a[i][c] v_i
+  void multi_axpy(const std::vector<std::vector<Cx>> &a, const std::vector<Vec> &v, int k, Vec y, const Mask &m) {
+    for (int i = 0; i < k; i++) axpy(a[i], v[i], y, m);
+  }
+};
+
+// R separate fine-grid fields (single precision, full); inactive columns are skipped altogether
+struct FieldOps {
+  typedef std::vector<SpinorField *> *Vec;
+  int R; long Vh; int nparity;
+  std::vector<std::unique_ptr<std::vector<SpinorField *>>> owned;
+  FieldOps(int R_, long Vh_, int nparity_) : R(R_), Vh(Vh_), nparity(nparity_) {}
+  ~FieldOps() { for (auto &v : owned) for (SpinorField *f : *v) delete f; }
+  Vec make() {
+    owned.emplace_back(new std::vector<SpinorField *>(R));
+    for (int r = 0; r < R; r++) { (*owned.back())[r] = new SpinorField(Vh, nparity, PREC_SINGLE); blas::zero(*(*owned.back())[r]); }
+    return owned.back().get();
+  }
+  void release(Vec) {}
+  void copy(Vec d, Vec s_, const Mask &m) { for (int r = 0; r < R; r++) if (m[r]) blas::copy(*(*d)[r], *(*s_)[r]); }
+  void zero(Vec d, const Mask &m) { for (int r = 0; r < R; r++) if (m[r]) blas::zero(*(*d)[r]); }
+  void cdot(Vec x, Vec y, std::vector<Cx> &dot, std::vector<double> &nx, const Mask &m) {
+    dot.assign(R, Cx(0, 0)); nx.assign(R, 0.0);
+    for (int r = 0; r < R; r++) if (m[r]) { const blas::double3_ d = blas::cDotProductNormA(*(*x)[r], *(*y)[r]); dot[r] = Cx(d.x, d.y); nx[r] = d.z; }
+  }
+  void axpy(const std::vector<Cx> &a, Vec x, Vec y, const Mask &m) { for (int r = 0; r < R; r++) if (m[r] && a[r] != Cx(0, 0)) blas::caxpy(a[r], *(*x)[r], *(*y)[r]); }
+  void scale(const std::vector<double> &a, Vec x, const Mask &m) { for (int r = 0; r < R; r++) if (m[r] && a[r] != 1.0) blas::ax(a[r], *(*x)[r]); }
+  // per column the fused multi-vector kernels of blas.cu (y is read once for all k dot products / updated once for all k terms)
+  void ortho(const std::vector<Vec> &v, int k, Vec y, std::vector<std::vector<Cx>> &beta, const Mask &live) {
+    beta.assign(k, std::vector<Cx>(R, Cx(0, 0)));
+    if (k == 0) return;
+    std::vector<SpinorField *> prev(k);
+    std::vector<Cx> bt(k);
+    for (int c = 0; c < R; c++) {
+      if (!live[c]) continue;
+      for (int i = 0; i < k; i++) prev[i] = (*v[i])[c];
+      blas::cDotProduct(bt.data(), prev, *(*y)[c]);
+      for (int i = 0; i < k; i++) { beta[i][c] = bt[i]; bt[i] = -bt[i]; }
+      blas::caxpy(bt.data(), prev, *(*y)[c]);
+    }
+  }
+  void multi_axpy(const std::vector<std::vector<Cx>> &a, const std::vector<Vec> &v, int k, Vec y, const Mask &m) {
+    if (k == 0) return;
+    std::vector<SpinorField *> vs(k);
+    std::vector<Cx> co(k);
+    for (int c = 0; c < R; c++) {
+      if (!m[c]) continue;
+      for (int i = 0; i < k; i++) { vs[i] = (*v[i])[c]; co[i] = a[i][c]; }
+      blas::caxpy(co.data(), vs, *(*y)[c]);
+    }
+  }
+};
+
+// ---- lock-step Krylov methods ----------------------------------------------------------------------------------------
+template <class Ops> struct BlockKrylov {
+  typedef typename Ops::Vec Vec;
+  typedef std::function<void(Vec, Vec, const Mask &)> Op;
+  Ops &ops;
+  std::vector<Vec> p, Ap;
+  Vec r = Vec(), y = Vec(), Ar = Vec();
+  explicit BlockKrylov(Ops &o) : ops(o) {}
+  ~BlockKrylov() {
+    for (Vec v : p) ops.release(v);
+    for (Vec v : Ap) ops.release(v);
+    if (r) ops.release(r);
+    if (y) ops.release(y);
+    if (Ar) ops.release(Ar);
+  }
+
+  // MR::operator() of solver.cu on every active column: niter steps with relaxation omega
+  void mr(const Op &A, Vec x, Vec b, int niter, double omega, bool use_init_guess, const Mask &active) {
+    const int R = ops.R;
+    if (!r) r = ops.make();
+    if (!y) y = ops.make();
+    if (!Ar) Ar = ops.make();
+    std::vector<Cx> dot, a(R);
+    std::vector<double> nx, c2, sc(R);
+    if (use_init_guess) {
+      A(Ar, x, active);
+      ops.copy(r, b, active);
+      for (int c = 0; c < R; c++) a[c] = Cx(-1, 0);
+      ops.axpy(a, Ar, r, active);
+    } else {
+      ops.copy(r, b, active);
+      ops.zero(x, active);
+    }
+    ops.cdot(r, r, dot, c2, active);
+    for (int c = 0; c < R; c++) sc[c] = (active[c] && c2[c] > 0.0) ? 1.0 / sqrt(c2[c]) : 1.0;
+    ops.scale(sc, r, active);
+    ops.zero(y, active);
+    for (int k = 0; k < niter; k++) {
+      A(Ar, r, active);
+      ops.cdot(Ar, r, dot, nx, active);
+      for (int c = 0; c < R; c++) a[c] = (active[c] && c2[c] > 0.0 && nx[c] > 0.0) ? omega * dot[c] / nx[c] : Cx(0, 0);
+      ops.axpy(a, r, y, active);                       // y += omega alpha r
+      for (int c = 0; c < R; c++) a[c] = -a[c];
+      ops.axpy(a, Ar, r, active);                      // r -= omega alpha A r
+    }
+    for (int c = 0; c < R; c++) a[c] = (active[c] && c2[c] > 0.0) ? Cx(sqrt(c2[c]), 0) : Cx(0, 0);
+    ops.axpy(a, y, x, active);
+  }
+
+  // GCR::operator() of solver.cu on every active column, zero initial guess.  stop2[c]: target <r,r> of column c.
+  // Restarts after nK iterations with the residual recomputed from A (unless the iteration budget is used up).
+  // r2 returns the last (recursive, or after a restart true) <r,r>.  Returns the number of iterations of the longest column.
+  // delta > 0: hand back to the caller (who recomputes the true residual) as soon as a running column has dropped by that
+  // factor since the start of the cycle -- the reliable update of GCR::operator() (reliable_delta).
+  int gcr(const Op &A, const Op *K, Vec x, Vec b, const std::vector<double> &stop2, int nK, int maxiter, const Mask &active, std::vector<double> &r2,
+          double delta = 0.0) {
+    const int R = ops.R;
+    if (!r) r = ops.make();
+    Mask live = active;
+    std::vector<Cx> dot, coef(R);
+    std::vector<double> nx, sc(R);
+    std::vector<std::vector<Cx>> alpha(nK, std::vector<Cx>(R)), beta((size_t)nK * nK, std::vector<Cx>(R));
+    std::vector<std::vector<double>> gamma(nK, std::vector<double>(R));
+    ops.copy(r, b, active);
+    ops.zero(x, active);
+    ops.cdot(r, r, dot, r2, active);
+    for (int c = 0; c < R; c++) if (live[c] && !(r2[c] > stop2[c])) live[c] = 0;
+    const std::vector<double> r2_start = r2;
+    bool reliable = false;
+    int total = 0;
+    while (any_active(live) && total < maxiter) {
+      int k = 0;
+      while (k < nK && total < maxiter && any_active(live) && !reliable) {
+        while ((int)p.size() <= k) { p.push_back(ops.make()); Ap.push_back(ops.make()); }
+        if (K) (*K)(p[k], r, live);
+        else ops.copy(p[k], r, live);
+        A(Ap[k], p[k], live);
+        {
+          std::vector<std::vector<Cx>> bk;
+          ops.ortho(Ap, k, Ap[k], bk, live);
+          for (int i = 0; i < k; i++) beta[(size_t)i * nK + k] = bk[i];
+        }
+        ops.cdot(Ap[k], r, dot, nx, live);
+        for (int c = 0; c < R; c++) {
+          if (live[c] && nx[c] > 0.0) { gamma[k][c] = sqrt(nx[c]); alpha[k][c] = dot[c] / gamma[k][c]; sc[c] = 1.0 / gamma[k][c]; }
+          else { gamma[k][c] = 1.0; alpha[k][c] = Cx(0, 0); sc[c] = 1.0; }
+          coef[c] = -alpha[k][c];
+        }
+        ops.scale(sc, Ap[k], live);
+        ops.axpy(coef, Ap[k], r, live);
+        ops.cdot(r, r, dot, nx, live);
+        k++; total++;
+        for (int c = 0; c < R; c++) if (live[c]) {
+          r2[c] = nx[c];
+          if (!(r2[c] > stop2[c])) live[c] = 0;
+          else if (delta > 0.0 && sqrt(r2[c] / r2_start[c]) < delta) reliable = true;
+        }
+      }
+      // x += sum_i delta_i p_i   (back substitution per column; columns that stopped early have alpha = beta = 0 from then on)
+      std::vector<std::vector<Cx>> delta(k, std::vector<Cx>(R));
+      for (int c = 0; c < R; c++)
+        for (int i = k - 1; i >= 0; i--) {
+          Cx d = alpha[i][c];
+          for (int j = i + 1; j < k; j++) d -= beta[(size_t)i * nK + j][c] * delta[j][c];
+          delta[i][c] = d / gamma[i][c];
+        }
+      ops.multi_axpy(delta, p, k, x, active);
+      if (!any_active(live) || total >= maxiter || reliable) break;
+      // restart from the true residual of the columns still running
+      A(Ap[0], x, live);
+      ops.copy(r, b, live);
+      for (int c = 0; c < R; c++) coef[c] = Cx(-1, 0);
+      ops.axpy(coef, Ap[0], r, live);
+      ops.cdot(r, r, dot, nx, live);
+      for (int c = 0; c < R; c++) if (live[c]) { r2[c] = nx[c]; if (!(r2[c] > stop2[c])) live[c] = 0; }
+      for (auto &a_ : alpha) a_.assign(R, Cx(0, 0));
+      for (auto &b_ : beta) b_.assign(R, Cx(0, 0));
+    }
+    return total;
+  }
+};
+
+}  // namespace
+
+// One coarse level (l >= 1) of the block cycle
+struct BlockMGLevel {
+  MG *mg;
+  const DiracCoarse *dres;
+  CoarseOperator *op;
+  int R, mode, p, q;
+  long Vh; int N; size_t pf4;    // float4 per parity block
+  std::unique_ptr<CoarseBlockField> x, b, r, t;
+  std::unique_ptr<BlockOps> ops_full, ops_par;
+  std::unique_ptr<BlockKrylov<BlockOps>> smoother, kcycle_gcr;
+  std::unique_ptr<BlockMhat> mhat;
+  float *s1 = nullptr, *s2 = nullptr, *src = nullptr;   // parity scratch
+  std::vector<std::unique_ptr<SpinorField>> fx, fb;     // R single fields of this level (transfers to / from the neighbours)
+  double t_prof[6] = {0, 0, 0, 0, 0, 0};                // smooth-pre, residual, restrict, coarse solve, prolong, smooth-post
+
+  BlockMGLevel(MG *mg_, int R_, int mode_) : mg(mg_), R(R_), mode(mode_) {
+    dres = dynamic_cast<const DiracCoarse *>(mg->matResidual);
+    const DiracCoarse *ds = dynamic_cast<const DiracCoarse *>(mg->matSmooth);
+    op = dres->op.get();
+    if (!op->Xinv) op->compute_xinv();
+    op->prepare_mrhs();
+    p = ds->p_parity(); q = 1 - p;
+    Vh = op->geom.Vh; N = op->N; pf4 = (size_t)Vh * (N / 2) * R;
+    x.reset(new CoarseBlockField(Vh, 2, N, R)); b.reset(new CoarseBlockField(Vh, 2, N, R));
+    r.reset(new CoarseBlockField(Vh, 2, N, R)); t.reset(new CoarseBlockField(Vh, 2, N, R));
+    for (CoarseBlockField *f : {x.get(), b.get(), r.get(), t.get()}) QB_CUDA(cudaMemsetAsync(f->v, 0, f->bytes(), rt().compute));
+    ops_full.reset(new BlockOps((long)(2 * pf4), R));
+    ops_par.reset(new BlockOps((long)pf4, R));
+    smoother.reset(new BlockKrylov<BlockOps>(*ops_par));
+    kcycle_gcr.reset(new BlockKrylov<BlockOps>(*ops_full));
+    mhat.reset(new BlockMhat(*op, p, R, mode));
+    s1 = ops_par->make(); s2 = ops_par->make(); src = ops_par->make();
+    for (int c = 0; c < R; c++) {
+      fx.emplace_back(new SpinorField(Vh, 2, PREC_SINGLE, 2, op->nvec));
+      fb.emplace_back(new SpinorField(Vh, 2, PREC_SINGLE, 2, op->nvec));
+      blas::zero(*fx.back()); blas::zero(*fb.back());
+    }
+  }
+  ~BlockMGLevel() { pool_free(s1); pool_free(s2); pool_free(src); }
+  float *par(CoarseBlockField &f, int parity) const { return f.v + (size_t)parity * pf4 * 4; }
+
+  // out = M in on full block fields
+  void full_M(float *out, const float *in) const {
+    CoarseMrhsArgs k{};
+    k.op = op; k.out = out; k.in_hop = in; k.in_diag = in; k.xpay = nullptr;
+    for (int pp = 0; pp < 2; pp++) k.out_poff[pp] = k.hop_poff[pp] = k.diag_poff[pp] = k.xpay_poff[pp] = (long)(pp * pf4);
+    k.parity = -1; k.use_y = true; k.use_x = true; k.use_xinv = false; k.a = 1.f; k.b = 0.f; k.R = R; k.mode = mode;
+    coarse_apply_mrhs(k);
+  }
+  // x <- smoother / coarsest solver on M x = b through the even-odd preconditioned system (MG::smooth + DiracCoarse::prepare / reconstruct)
+  void smooth(CoarseBlockField &xx, CoarseBlockField &bb, bool coarsest, int niter, bool init_guess, const Mask &active) {
+    const MGLevelParam &lp = mg->mp.level[mg->level];
+    float *xp = par(xx, p), *xq = par(xx, q), *bp = par(bb, p), *bq = par(bb, q);
+    mhat->launch(s1, nullptr, bq, nullptr, q, false, true, 1.f, 0.f);      // Xinv_q b_q
+    mhat->launch(s2, s1, nullptr, bp, p, true, false, -1.f, 1.f);          // b_p - Y_pq .
+    mhat->launch(src, nullptr, s2, nullptr, p, false, true, 1.f, 0.f);     // Xinv_p .
+    BlockKrylov<BlockOps>::Op A = [this](float *o, float *i, const Mask &) { (*mhat)(o, i); };
+    if (coarsest) {
+      std::vector<Cx> dot; std::vector<double> n2, stop(R), r2;
+      ops_par->cdot(src, src, dot, n2, active);
+      for (int c = 0; c < R; c++) stop[c] = lp.smoother_tol * lp.smoother_tol * n2[c];
+      smoother->gcr(A, nullptr, xp, src, stop, 20, 1000, active, r2);
+    } else {
+      smoother->mr(A, xp, src, niter, lp.omega, init_guess, active);
+    }
+    mhat->launch(s1, xp, nullptr, bq, q, true, false, -1.f, 1.f);          // b_q - Y_qp x_p
+    mhat->launch(xq, nullptr, s1, nullptr, q, false, true, 1.f, 0.f);      // x_q = Xinv_q .
+  }
+};
+
+class BlockMG {
+ public:
+  MG &top;
+  int R, mode;
+  std::vector<std::unique_ptr<BlockMGLevel>> lv;   // lv[l - 1] <-> level l
+  std::vector<std::unique_ptr<SpinorField>> rres;      // R fine residuals (input of the multi-vector restrictor)
+  BlockMG(MG &top_, int R_, int mode_) : top(top_), R(R_), mode(mode_) {
+    for (MG *m = top.coarse.get(); m; m = m->coarse.get()) lv.emplace_back(new BlockMGLevel(m, R, mode));
+  }
+
+  // block cycle on coarse level l (MG::cycle)
+  void cycle(int l, CoarseBlockField &x, CoarseBlockField &b, const Mask &active) {
+    BlockMGLevel &L = *lv[l - 1];
+    MG &m = *L.mg;
+    const MGLevelParam &lp = m.mp.level[m.level];
+    if (!m.coarse) { BSection s_(&L.t_prof[0]); L.smooth(x, b, true, 0, false, active); return; }
+    BlockMGLevel &C = *lv[l];
+    if (lp.nu_pre > 0) {
+      { BSection s_(&L.t_prof[0]); L.smooth(x, b, false, lp.nu_pre, false, active); }
+      BSection s_(&L.t_prof[1]);
+      L.full_M(L.r->v, x.v);
+      std::vector<Cx> a(R, Cx(-1, 0)), one(R, Cx(1, 0)), none;
+      L.ops_full->blas_.axpy<3>(a, none, L.r->v, nullptr, L.r->v);   // r = -M x
+      L.ops_full->axpy(one, b.v, L.r->v, active);                    // r += b
+    } else {
+      L.ops_full->zero(x.v, active);
+      L.ops_full->copy(L.r->v, b.v, active);
+    }
+    { BSection s_(&L.t_prof[2]); restrict_to(l, *L.r, *C.b, active); }
+    { BSection s_(&L.t_prof[3]); coarse_solve(l + 1, *C.x, *C.b, active); }
+    { BSection s_(&L.t_prof[4]); prolong_add(l, *C.x, x, active); }
+    if (lp.nu_post > 0) { BSection s_(&L.t_prof[5]); L.smooth(x, b, false, lp.nu_post, true, active); }
+  }
+
+  // solve on level l as seen from level l - 1: the level's cycle, wrapped in GCR(10) when the parent runs a K-cycle
+  void coarse_solve(int l, CoarseBlockField &x, CoarseBlockField &b, const Mask &active) {
+    BlockMGLevel &L = *lv[l - 1];
+    MG *parent = l == 1 ? &top : lv[l - 2]->mg;
+    if (!parent->coarse_solver_gcr) { cycle(l, x, b, active); return; }
+    const SolverParam &sp = parent->param_coarse_solver;
+    BlockKrylov<BlockOps>::Op A = [&L](float *o, float *i, const Mask &) { L.full_M(o, i); };
+    // preconditioner of the K-cycle: this level's cycle on the GCR's own vectors (the cycle only reads its source)
+    BlockKrylov<BlockOps>::Op K = [this, l](float *o, float *i, const Mask &m) { cycle_raw(l, o, i, m); };
+    std::vector<Cx> dot; std::vector<double> n2, stop(R), r2;
+    L.ops_full->cdot(b.v, b.v, dot, n2, active);
+    for (int c = 0; c < R; c++) stop[c] = sp.tol * sp.tol * n2[c];
+    L.kcycle_gcr->gcr(A, &K, x.v, b.v, stop, sp.Nkrylov, sp.maxiter, active, r2);
+  }
+
+  // cycle() on raw full-field buffers of level l (used as the K-cycle preconditioner): borrows the level's x / b objects' storage
+  void cycle_raw(int l, float *x, float *b, const Mask &active) {
+    BlockMGLevel &L = *lv[l - 1];
+    float *sx = L.x->v, *sb = L.b->v;
+    L.x->v = x; L.b->v = b;
+    cycle(l, *L.x, *L.b, active);
+    L.x->v = sx; L.b->v = sb;
+  }
+
+  // level l (coarse) -> level l + 1 through the single-vector transfer kernels
+  void restrict_to(int l, CoarseBlockField &fine, CoarseBlockField &coarse, const Mask &active) {
+    BlockMGLevel &L = *lv[l - 1], &C = *lv[l];
+    std::vector<SpinorField *> pf(R), pc(R);
+    for (int c = 0; c < R; c++) { pf[c] = L.fb[c].get(); pc[c] = C.fb[c].get(); }
+    fine.unpack(pf.data());
+    for (int c = 0; c < R; c++) if (active[c]) L.mg->transfer->R(*pc[c], *pf[c]);
+    coarse.pack(pc.data());
+  }
+  void prolong_add(int l, CoarseBlockField &coarse, CoarseBlockField &fine, const Mask &active) {
+    BlockMGLevel &L = *lv[l - 1], &C = *lv[l];
+    std::vector<SpinorField *> pf(R), pc(R);
+    for (int c = 0; c < R; c++) { pf[c] = L.fx[c].get(); pc[c] = C.fx[c].get(); }
+    coarse.unpack(pc.data());
+    for (int c = 0; c < R; c++) if (active[c]) L.mg->transfer->P(*pf[c], *pc[c]);
+    L.t->pack(pf.data());
+    std::vector<Cx> one(R, Cx(1, 0));
+    L.ops_full->axpy(one, L.t->v, fine.v, active);
+  }
+
+  // level-0 cycle for R fine right-hand sides (single precision, full fields)
+  void apply(std::vector<SpinorField *> &x, std::vector<SpinorField *> &b, const Mask &active) {
+    const MGLevelParam &lp = top.mp.level[0];
+    BlockMGLevel &L1 = *lv[0];
+    std::vector<SpinorField *> pb(R), px(R);
+    for (int c = 0; c < R; c++) { pb[c] = L1.fb[c].get(); px[c] = L1.fx[c].get(); }
+    std::vector<SpinorField *> act_res, act_pb, act_px, act_x;
+    while ((int)rres.size() < R) rres.emplace_back(new SpinorField(top.r->Vh, 2, PREC_SINGLE));
+    for (int c = 0; c < R; c++) {
+      if (!active[c]) continue;
+      if (lp.nu_pre > 0) {
+        { BSection s_(&t_prof[0]); top.smooth(*top.presmoother, *x[c], *b[c]); }
+        BSection s_(&t_prof[1]);
+        top.matResidual->M(*rres[c], *x[c]);
+        blas::axpby(1.0, *b[c], -1.0, *rres[c]);
+      } else {
+        blas::zero(*x[c]);
+        blas::copy(*rres[c], *b[c]);
+      }
+      act_res.push_back(rres[c].get()); act_pb.push_back(pb[c]); act_px.push_back(px[c]); act_x.push_back(x[c]);
+    }
+    { BSection s_(&t_prof[2]); top.transfer->R_multi(act_pb.data(), act_res.data(), (int)act_res.size()); }
+    {
+      BSection s_(&t_prof[3]);
+      L1.b->pack(pb.data());
+      coarse_solve(1, *L1.x, *L1.b, active);
+      L1.x->unpack(px.data());
+    }
+    { BSection s_(&t_prof[4]); top.transfer->P_multi(act_x.data(), act_px.data(), (int)act_x.size(), true); }
+    if (lp.nu_post > 0)
+      for (int c = 0; c < R; c++) if (active[c]) { BSection s_(&t_prof[5]); top.smooth(*top.postsmoother, *x[c], *b[c]); }
+    ncycle++;
+  }
+  double t_prof[6] = {0, 0, 0, 0, 0, 0};
+  long ncycle = 0;
+  void print_profile() {
+    if (!block_profile_on()) return;
+    auto line = [&](int level, const double *t) {
+      log_msg(0, "block MG level %d profile (%d rhs, %ld cycles): smooth-pre %.4f s, residual %.4f s, restrict %.4f s, coarse-solve %.4f s, prolong %.4f s, smooth-post %.4f s\n",
+              level, R, ncycle, t[0], t[1], t[2], t[3], t[4], t[5]);
+    };
+    line(1, t_prof);
+    for (size_t i = 0; i < lv.size(); i++) line((int)i + 2, lv[i]->t_prof);
+  }
+};
+
+bool block_mg_supported(const MG &mg, int R, int mode) {
+  if (getenv("QB_BLOCK_MG") && atoi(getenv("QB_BLOCK_MG")) == 0) return false;
+  if (R < 2 || R > MAXR || !mg.coarse) return false;
+  for (const MG *m = mg.coarse.get(); m; m = m->coarse.get()) {
+    const DiracCoarse *dr = dynamic_cast<const DiracCoarse *>(m->matResidual), *ds = dynamic_cast<const DiracCoarse *>(m->matSmooth);
+    if (!dr || !ds || !ds->pc || dr->op->geom.partitioned()) return false;
+    const InverterType sm = m->mp.level[m->level].smoother;
+    if (m->coarse ? sm != INV_MR : (sm != INV_MR && sm != INV_GCR)) return false;   // the coarsest level solves with GCR(20) either way
+    const int N = dr->op->N;
+    if (N != 16 && N != 32 && N != 48 && N != 64) return false;
+    if (coarse_mrhs_max_rhs(N, mode) < R) return false;
+  }
+  return true;
+}
+
+// R solves of M x = b by flexible GCR preconditioned with the block multigrid cycle, all columns in lock-step.
+// x, b: full fields in the outer precision.  The Krylov space is single precision (the reference's cuda_prec_sloppy); the true
+// residual is recomputed in the outer precision at every restart (defect correction), exactly where GCR::operator() does its
+// reliable update.  Returns the iteration count of the longest column; true_res[c] = |b - M x| / |b|.
+int block_mg_gcr_solve(MG &mg, const DiracMatrix &mat, const DiracMatrix &matSloppy, std::vector<SpinorField *> &x, std::vector<SpinorField *> &b,
+                       const SolverParam &sp, int mode, std::vector<double> &true_res) {
+  const int R = (int)x.size();
+  BlockMG bmg(mg, R, mode);
+  FieldOps ops(R, x[0]->Vh, x[0]->nparity);
+  BlockKrylov<FieldOps> kry(ops);
+  typedef BlockKrylov<FieldOps>::Op Op;
+  Op A = [&](FieldOps::Vec o, FieldOps::Vec i, const Mask &m) { for (int c = 0; c < R; c++) if (m[c]) matSloppy(*(*o)[c], *(*i)[c]); };
+  Op K = [&](FieldOps::Vec o, FieldOps::Vec i, const Mask &m) { bmg.apply(*o, *i, m); };
+  FieldOps::Vec rS = ops.make(), e = ops.make();
+  std::vector<std::unique_ptr<SpinorField>> r(R), tmp(R);
+  std::vector<double> b2(R), r2(R), stop(R), stop_inner(R), r2_inner;
+  Mask live(R, 1);
+  true_res.assign(R, 0.0);
+  for (int c = 0; c < R; c++) {
+    r[c].reset(new_like(*b[c], b[c]->prec)); tmp[c].reset(new_like(*b[c], b[c]->prec));
+    blas::copy(*r[c], *b[c]);
+    blas::zero(*x[c]);
+    b2[c] = r2[c] = blas::norm2(*b[c]);
+    stop[c] = sp.tol * sp.tol * b2[c];
+    if (!(b2[c] > 0.0)) live[c] = 0;
+  }
+  int total = 0;
+  while (any_active(live) && total < sp.maxiter) {
+    for (int c = 0; c < R; c++) if (live[c]) { blas::copy(*(*rS)[c], *r[c]); stop_inner[c] = stop[c]; }
+    const int budget = std::min(sp.Nkrylov, sp.maxiter - total);
+    total += kry.gcr(A, &K, e, rS, stop_inner, sp.Nkrylov, budget, live, r2_inner, sp.delta);
+    for (int c = 0; c < R; c++) {
+      if (!live[c]) continue;
+      blas::copy(*tmp[c], *(*e)[c]);          // to the outer precision
+      blas::xpy(*tmp[c], *x[c]);
+      mat(*r[c], *x[c]);
+      r2[c] = blas::xmyNorm(*b[c], *r[c]);    // r = b - M x
+      if (!(r2[c] > stop[c])) live[c] = 0;
+    }
+  }
+  for (int c = 0; c < R; c++) true_res[c] = b2[c] > 0.0 ? sqrt(r2[c] / b2[c]) : 0.0;
+  bmg.print_profile();
+  return total;
 }
 
 }  // namespace qb

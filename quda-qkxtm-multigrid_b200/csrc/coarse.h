@@ -37,6 +37,7 @@ struct CoarseOperator {
   float *Ymma = nullptr;      // [V][9][N/2][N] float4: K-major UMMA operand image of every link matrix
   float *Xinv_mma = nullptr;  // [V][N/2][N] float4
   int *nbr = nullptr;         // [V][8] full-site index of x + e_d
+  bool mrhs_ready = false;
   void prepare_mrhs();        // (re)build the three arrays above from Y / Xinv
   ~CoarseOperator();
 };

@@ -74,6 +74,8 @@ void CoarseOperator::prepare_mrhs() {
   if (geom.partitioned()) QB_ERROR("multi-RHS coarse operator: partitioned coarse lattices are not supported yet");
   cudaStream_t s = rt().compute;
   const long V = geom.V();
+  if (mrhs_ready && Ymma && nbr && (!Xinv || Xinv_mma)) return;   // links are immutable once the level is set up
+  mrhs_ready = true;
   if (!Ymma) QB_CUDA(cudaMalloc((void **)&Ymma, link_bytes()));
   {
     const long n = V * 9 * N * (N / 2);

@@ -72,6 +72,12 @@ void pool_free(void *ptr) {
   pool_live.erase(it);
 }
 
+size_t pool_cached_bytes() {
+  size_t n = 0;
+  for (auto &kv : pool_cache) n += kv.first;
+  return n;
+}
+
 void pool_release_all() {
   for (auto &kv : pool_cache) cudaFree(kv.second);
   pool_cache.clear();

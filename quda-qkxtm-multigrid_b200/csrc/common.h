@@ -56,6 +56,7 @@ Runtime &rt();
 // design: lib/malloc.cpp + the pinned/device pools of later QUDA).  Freed blocks are kept and reused by exact size.
 void *pool_malloc(size_t bytes);
 void pool_free(void *ptr);
+size_t pool_cached_bytes();  // bytes sitting in the cache (reusable without a driver call)
 void pool_release_all();   // return everything cached to the driver (freeGaugeQuda / endQuda)
 
 inline int div_up(long a, long b) { return (int)((a + b - 1) / b); }

@@ -62,9 +62,10 @@ class MG : public Solver {
   void verify(double *dev3);
   long long flops() const override;
 
+  void smooth(Solver &s, SpinorField &x, SpinorField &b);
+
  private:
   void generate_null_vectors();
-  void smooth(Solver &s, SpinorField &x, SpinorField &b);
   void cycle(SpinorField &x, SpinorField &b);
 };
 
@@ -79,5 +80,9 @@ void random_fill(SpinorField &f, unsigned long long seed);
 // batched null-vector generation on coarse levels through the multi-RHS tensor-core operator (block_solver.cu)
 bool block_null_vectors_supported(const Dirac *matSmooth, int nvec);
 int block_null_vectors(const Dirac *matSmooth, std::vector<SpinorField *> &x, int maxiter, double tol);
+// block multigrid (block_solver.cu): R right-hand sides through the K-cycle in lock-step, coarse levels on the multi-RHS tensor-core operator
+bool block_mg_supported(const MG &mg, int R, int mode);
+int block_mg_gcr_solve(MG &mg, const DiracMatrix &mat, const DiracMatrix &matSloppy, std::vector<SpinorField *> &x, std::vector<SpinorField *> &b,
+                       const SolverParam &sp, int mode, std::vector<double> &true_res);
 
 }  // namespace qb

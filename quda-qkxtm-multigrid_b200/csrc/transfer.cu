@@ -270,6 +270,117 @@ __global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const float
   }
 }
 
+// ---- multi-right-hand-side variants (block multigrid, block_solver.cu): V is streamed once for NR vectors ------------
+constexpr int TRANSFER_MAX_NR = 6;
+struct MultiPtrs { const float4 *in[TRANSFER_MAX_NR]; float4 *out[TRANSFER_MAX_NR]; };
+
+// prolong_kernel for NR coarse vectors at once; ACC: out += P c (the coarse-grid correction is added in place)
+template <int NR, bool ACC>
+__global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const float4 *V, const int *f2c, long Vh_f, long Vh_c, int Nf, int nvec, int cpc) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nkp = Nf / 2;
+  if (t >= 2 * Vh_f * nkp) return;
+  const long cb = t % Vh_f;
+  const int kp = (int)((t / Vh_f) % nkp), parity = (int)(t / (Vh_f * nkp));
+  const int k0 = 2 * kp, S = k0 / cpc, nvh = nvec / 2;
+  const int cs = f2c[(size_t)parity * Vh_f + cb];
+  const int cpar = cs >= Vh_c ? 1 : 0;
+  const long ccb = cs - (long)cpar * Vh_c;
+  const size_t coff = ((size_t)cpar * nvec + (size_t)S * nvh) * Vh_c + ccb;
+  const float4 *v0 = V + v_plane(parity, k0, 0, Nf, nvh) * Vh_f + cb;
+  const float4 *v1 = V + v_plane(parity, k0 + 1, 0, Nf, nvh) * Vh_f + cb;
+  cplx<float> a0[NR], a1[NR];
+#pragma unroll
+  for (int r = 0; r < NR; r++) { a0[r] = cplx<float>(0.f, 0.f); a1[r] = cplx<float>(0.f, 0.f); }
+#pragma unroll 4
+  for (int jp = 0; jp < nvh; jp++) {
+    const float4 w0 = ld_stream(v0 + (size_t)jp * Vh_f), w1 = ld_stream(v1 + (size_t)jp * Vh_f);
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const float4 cc = __ldg(p.in[r] + coff + (size_t)jp * Vh_c);
+      cmac(a0[r], cplx<float>(w0.x, w0.y), cplx<float>(cc.x, cc.y));
+      cmac(a0[r], cplx<float>(w0.z, w0.w), cplx<float>(cc.z, cc.w));
+      cmac(a1[r], cplx<float>(w1.x, w1.y), cplx<float>(cc.x, cc.y));
+      cmac(a1[r], cplx<float>(w1.z, w1.w), cplx<float>(cc.z, cc.w));
+    }
+  }
+  const size_t o = ((size_t)parity * nkp + kp) * Vh_f + cb;
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    float4 v = make_float4(a0[r].re, a0[r].im, a1[r].re, a1[r].im);
+    if (ACC) { const float4 old = p.out[r][o]; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+    p.out[r][o] = v;
+  }
+}
+
+// restrict_rows_kernel for NR fine vectors at once (same thread mapping and reduction tree: deterministic)
+template <int NKP, int NR>
+__global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p, const float4 *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
+                                           long Vh_c, int nvec, int cpc, int XL) {
+  const int lane = threadIdx.x, jp = threadIdx.y, nvh = nvec / 2;
+  const int RS = 32 / XL;
+  const int xl = lane % XL, rs = lane / XL;
+  const long Vh_f = fg.Vh;
+  const int ng = fg.Xh / XL, nby = fg.X[1] / b1, nbz = fg.X[2] / b2;
+  int bid = blockIdx.x;
+  const int g = bid % ng; bid /= ng;
+  const int by = bid % nby; bid /= nby;
+  const int bz = bid % nbz;
+  const int bt = bid / nbz;
+  const int nyg = b1 / RS;
+  const int niter = 2 * nyg * b2 * b3;
+  cplx<float> acc[NR][2][2];
+#pragma unroll
+  for (int r = 0; r < NR; r++)
+#pragma unroll
+    for (int s = 0; s < 2; s++) { acc[r][s][0] = cplx<float>(0.f, 0.f); acc[r][s][1] = cplx<float>(0.f, 0.f); }
+  long first_fs = -1;
+  for (int it = 0; it < niter; it++) {
+    const int parity = it & 1;
+    int rr = it >> 1;
+    const int yg = rr % nyg; rr /= nyg;
+    const int y = by * b1 + yg * RS + rs, z = bz * b2 + rr % b2, t = bt * b3 + rr / b2;
+    const long cb = (((long)t * fg.X[2] + z) * fg.X[1] + y) * fg.Xh + XL * g + xl;
+    if (first_fs < 0) first_fs = (long)parity * Vh_f + cb;
+    float4 w0[NKP], w1[NKP];
+#pragma unroll
+    for (int kp = 0; kp < NKP; kp++) {
+      w0[kp] = ld_stream(V + v_plane(parity, 2 * kp, jp, 2 * NKP, nvh) * Vh_f + cb);
+      w1[kp] = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, 2 * NKP, nvh) * Vh_f + cb);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+#pragma unroll
+      for (int kp = 0; kp < NKP; kp++) {
+        const float4 f = __ldg(p.in[r] + ((size_t)parity * NKP + kp) * Vh_f + cb);
+        constexpr int CPC = NKP;            // components per chirality = Nf / 2 (two coarse spins): compile-time, keeps acc in registers
+        const int S = (2 * kp) / CPC;
+        const cplx<float> f0(f.x, f.y), f1(f.z, f.w);
+        cmac_conj(acc[r][S][0], cplx<float>(w0[kp].x, w0[kp].y), f0); cmac_conj(acc[r][S][1], cplx<float>(w0[kp].z, w0[kp].w), f0);
+        cmac_conj(acc[r][S][0], cplx<float>(w1[kp].x, w1[kp].y), f1); cmac_conj(acc[r][S][1], cplx<float>(w1[kp].z, w1[kp].w), f1);
+      }
+    }
+  }
+  const int spa = b0 / 2;
+  const bool writer = rs == 0 && (xl % spa) == 0;
+  int X = 0;
+  if (writer) X = f2c[first_fs];
+  const int cpar = X >= Vh_c ? 1 : 0;
+  const long ccb = X - (long)cpar * Vh_c;
+#pragma unroll
+  for (int r = 0; r < NR; r++)
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      float v[4] = {acc[r][s][0].re, acc[r][s][0].im, acc[r][s][1].re, acc[r][s][1].im};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        for (int o = 16; o >= XL; o >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+        for (int o = 1; o < spa; o <<= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+      }
+      if (writer) p.out[r][((size_t)cpar * nvec + (size_t)s * nvh + jp) * Vh_c + ccb] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 // face site (3-d lexicographic >> 1 of the remaining coordinates, as in the fine Dslash) -> cb index on slice x_mu = slice
 __device__ __forceinline__ long level_face_to_cb(int mu, int fidx, int slice, int parity, const int *X) {
   const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
@@ -437,6 +548,73 @@ void Transfer::R(SpinorField &co, const SpinorField &fi) const {
 #undef RK
   QB_CHECK_LAUNCH();
   flops += 8ll * Nf * nvec * fine.V();
+}
+
+// n fine fields fo[i] (+)= P ci[i]: V is streamed once per group of up to TRANSFER_MAX_NR vectors
+void Transfer::P_multi(SpinorField *const *fo, const SpinorField *const *ci, int n, bool accumulate) const {
+  const long nt = 2 * fine.Vh * (Nf / 2);
+  for (int first = 0; first < n; first += TRANSFER_MAX_NR) {
+    const int nr = std::min(TRANSFER_MAX_NR, n - first);
+    MultiPtrs p{};
+    for (int r = 0; r < nr; r++) {
+      SpinorField &f = *fo[first + r];
+      const SpinorField &c = *ci[first + r];
+      if (f.prec != PREC_SINGLE || c.prec != PREC_SINGLE || f.nparity != 2 || c.nparity != 2 || f.Vh != fine.Vh || c.Vh != coarse.Vh || f.ncomplex != Nf || c.ncomplex != 2 * nvec)
+        QB_ERROR("Transfer::P_multi: field geometry mismatch");
+      p.out[r] = (float4 *)f.v; p.in[r] = (const float4 *)c.v;
+    }
+#define PM(NR_) \
+    if (accumulate) prolong_multi_kernel<NR_, true><<<div_up(nt, 128), 128, 0, rt().compute>>>(p, (const float4 *)V, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2); \
+    else prolong_multi_kernel<NR_, false><<<div_up(nt, 128), 128, 0, rt().compute>>>(p, (const float4 *)V, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2)
+    switch (nr) {
+      case 1: PM(1); break;
+      case 2: PM(2); break;
+      case 3: PM(3); break;
+      case 4: PM(4); break;
+      case 5: PM(5); break;
+      default: PM(6); break;
+    }
+#undef PM
+    QB_CHECK_LAUNCH();
+    flops += 8ll * Nf * nvec * fine.V() * nr;
+  }
+}
+
+// n coarse fields co[i] = R fi[i]
+void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int n) const {
+  const int b0 = geo_bs[0];
+  int XL = 0;
+  if (fine.Xh == 8 || fine.Xh == 16 || fine.Xh % 32 == 0) XL = fine.Xh < 32 ? fine.Xh : 32;
+  else if (fine.Xh % 8 == 0) XL = 8;
+  const bool rows = Nf == 12 && XL && (b0 == 2 || b0 == 4 || b0 == 8) && geo_bs[1] % (32 / XL) == 0 && 32 * (nvec / 2) <= 384;
+  if (!rows) {  // geometries the row-major kernel does not take: one vector at a time
+    for (int i = 0; i < n; i++) R(*co[i], *fi[i]);
+    return;
+  }
+  const unsigned nblk = (unsigned)((fine.Xh / XL) * (fine.X[1] / geo_bs[1]) * (fine.X[2] / geo_bs[2]) * (fine.X[3] / geo_bs[3]));
+  for (int first = 0; first < n; first += TRANSFER_MAX_NR) {
+    const int nr = std::min(TRANSFER_MAX_NR, n - first);
+    MultiPtrs p{};
+    for (int r = 0; r < nr; r++) {
+      SpinorField &c = *co[first + r];
+      const SpinorField &f = *fi[first + r];
+      if (f.prec != PREC_SINGLE || c.prec != PREC_SINGLE || f.nparity != 2 || c.nparity != 2 || f.Vh != fine.Vh || c.Vh != coarse.Vh || f.ncomplex != Nf || c.ncomplex != 2 * nvec)
+        QB_ERROR("Transfer::R_multi: field geometry mismatch");
+      p.out[r] = (float4 *)c.v; p.in[r] = (const float4 *)f.v;
+    }
+#define RM(NR_) restrict_rows_multi_kernel<6, NR_><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const float4 *)V, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL)
+    switch (nr) {
+      case 1: RM(1); break;
+      case 2: RM(2); break;
+      case 3: RM(3); break;
+      case 4: RM(4); break;
+      case 5: RM(5); break;
+      default: RM(6); break;
+    }
+#undef RM
+    QB_CHECK_LAUNCH();
+    flops += 8ll * Nf * nvec * fine.V() * nr;
+  }
 }
 
 }  // namespace qb

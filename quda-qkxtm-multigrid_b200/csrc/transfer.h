@@ -59,6 +59,9 @@ class Transfer {
   SpinorField *new_coarse_field() const { return new SpinorField(coarse.Vh, 2, PREC_SINGLE, 2, nvec); }
   void P(SpinorField &fine_out, const SpinorField &coarse_in) const;
   void R(SpinorField &coarse_out, const SpinorField &fine_in) const;
+  // several vectors per pass over V (block multigrid); accumulate: fine_out += P coarse_in
+  void P_multi(SpinorField *const *fine_out, const SpinorField *const *coarse_in, int n, bool accumulate) const;
+  void R_multi(SpinorField *const *coarse_out, const SpinorField *const *fine_in, int n) const;
   size_t v_bytes() const { return (size_t)2 * fine.Vh * Nf * nvec * 8; }
  private:
   void exchange_v_ghost();

@@ -248,6 +248,49 @@ def test_three_level_mg_gcr_solve(quda, oracle):
         assert d[0] < 5e-6 and d[1] < 1e-4 and d[2] < 5e-5, d
 
 
+@pytest.mark.parametrize("n_level,X,blocks,nvecs", [(2, (8, 8, 8, 16), ((4, 4, 4, 4),), (8,)),
+                                                    (3, (16, 16, 16, 16), ((4, 4, 4, 4), (2, 2, 2, 2)), (8, 8))])
+@pytest.mark.parametrize("mode", [3, 1])
+def test_block_mg_multi_src_solve(quda, oracle, n_level, X, blocks, nvecs, mode, monkeypatch):
+    """invertMultiSrcQuda on the block path: all sources through the K-cycle in lock-step, coarse levels on
+    the multi-RHS tensor-core operator.  Every solution is checked with the host operator of the oracle and against the
+    one-source-at-a-time path (same tolerance, comparable iteration count)."""
+    q, L = quda, quda.lib()
+    kappa, mu, tol = 0.1248, 0.004, 1e-8
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711)
+    load_gauge(q, g, X, prec=8, sloppy=4, precond=4, recon=12)
+    ip = mg_inv_param(q, kappa, mu)
+    mgp = q.multigrid_param(ip, n_level=n_level, geo_block=blocks, n_vec=nvecs, nu_pre=2, nu_post=2, setup_maxiter=200, setup_tol=5e-6)
+    mg = L.newMultigridQuda(C.byref(mgp))
+    nsrc = 5
+    rng = np.random.default_rng(11)
+    bs = [point_source(oracle.V)] + [rng.standard_normal(oracle.V * 24) for _ in range(nsrc - 1)]
+
+    def solve(block):
+        monkeypatch.setenv("QB_BLOCK_MG", "1" if block else "0")
+        monkeypatch.setenv("QB_BLOCK_MG_MODE", str(mode))
+        p = mg_inv_param(q, kappa, mu)
+        p.inv_type_precondition = q.QUDA_MG_INVERTER
+        p.preconditioner = mg
+        p.gcrNkrylov = 20; p.tol = tol; p.maxiter = 200; p.reliable_delta = 1e-4
+        p.num_src = nsrc
+        xs = [np.zeros(oracle.V * 24) for _ in range(nsrc)]
+        L.invertMultiSrcQuda((C.c_void_p * nsrc)(*[a.ctypes.data for a in xs]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bs]), C.byref(p))
+        return xs, p.iter, p.true_res, p.secs
+
+    xb, it_b, tr_b, t_b = solve(True)
+    xs, it_s, tr_s, t_s = solve(False)
+    L.destroyMultigridQuda(mg)
+    worst = max(host_residual(oracle, g, x, b, kappa, mu) for x, b in zip(xb, bs))
+    print(f"block MG ({n_level} levels, mode {mode}): {it_b} lock-step iterations in {t_b:.3f} s, sequential {it_s} iterations (sum over {nsrc}) in {t_s:.3f} s; "
+          f"worst host residual {worst:.2e}, reported {tr_b:.2e}")
+    assert worst < 5e-8 and tr_b < 5e-8 and tr_s < 5e-8
+    assert it_b <= 1.5 * it_s / nsrc + 3, (it_b, it_s)    # lock-step count = that of the slowest source
+    for a, b_ in zip(xb, xs):
+        assert np.linalg.norm(a - b_) / np.linalg.norm(b_) < 1e-6
+
+
 def test_mg_half_precision_smoother(quda, oracle):
     """cuda_prec_precondition = half on the fine level (int16 links and smoother mat-vec), as the reference allows."""
     res, true_res, it_mg, it_plain, *_ = run_mg_solve(
