@@ -93,4 +93,8 @@ void *staging(size_t bytes);
 // precision change / copy between resident fields of identical geometry
 void copy_spinor(SpinorField &dst, const SpinorField &src, cudaStream_t s);
 
+// host <-> device in the generic order [parity][x_cb][component][re, im] (fp32, any number of components)
+void import_generic(SpinorField &f, const float *h, cudaStream_t s);
+void export_generic(float *h, const SpinorField &f, cudaStream_t s);
+
 }  // namespace qb

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <climits>
+#include <cstring>
 #include <chrono>
 #include <map>
 #include <string>
@@ -996,7 +997,9 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   mp.generate_all_levels = mgp->generate_all_levels == QUDA_BOOLEAN_YES;
   mp.verbosity = r.verbosity;
   mp.keep_null_vectors = mgp->run_verify == QUDA_BOOLEAN_YES;  // needed by mgVerifyQudaB200 / mgNullVectorQudaB200 only
-  if (!mp.compute_null_vector) QB_ERROR("compute_null_vector = NO needs vec_infile, which requires QIO (not available); generate the null vectors");
+  mp.vec_infile = std::string(mgp->vec_infile, strnlen(mgp->vec_infile, sizeof(mgp->vec_infile)));
+  mp.vec_outfile = std::string(mgp->vec_outfile, strnlen(mgp->vec_outfile, sizeof(mgp->vec_outfile)));
+  if (!mp.compute_null_vector && mp.vec_infile.empty()) QB_ERROR("compute_null_vector = NO needs vec_infile (written by an earlier newMultigridQuda with vec_outfile set)");
 
   // fine operators: residual = full operator in the MG working precision (fp32 vectors); smoother = even-odd
   // preconditioned operator in cuda_prec_precondition, with the setup rescale of kappa / mu (interface_quda.cpp:2196-2233)

@@ -1,6 +1,8 @@
 // Multigrid level construction and cycle.
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstring>
 #include "multigrid.h"
 
 namespace qb {
@@ -83,8 +85,15 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
     // ---- near-null vectors ----
     if (B_in) B = std::move(*B_in);
     if ((int)B.size() < lp.nvec) {
-      if (!mp.compute_null_vector) QB_ERROR("MG level %d: %d null vectors needed but compute_null_vector is off (vector files are not supported)", level + 1, lp.nvec);
-      generate_null_vectors();
+      // multigrid.cpp:29-38: compute, or load from vec_infile_level_<l>; multigrid.cpp:776: save after computing
+      if (mp.compute_null_vector) {
+        generate_null_vectors();
+        if (!mp.vec_outfile.empty()) save_vectors();
+      } else if (!mp.vec_infile.empty()) {
+        load_vectors();
+      } else {
+        QB_ERROR("MG level %d: %d null vectors needed but compute_null_vector is off and vec_infile is empty", level + 1, lp.nvec);
+      }
     }
     std::vector<SpinorField *> Bp;
     for (int i = 0; i < lp.nvec; i++) Bp.push_back(B[i].get());
@@ -213,6 +222,71 @@ void MG::generate_null_vectors() {
     B.push_back(std::move(x));
     log_msg(2, "MG level %d: null vector %d done (%d BiCGStab iterations so far)\n", level + 1, i, sp.iter);
   }
+}
+
+// Near-null vector files (multigrid.cpp:607-691 uses QIO's read/write_spinor_field; QIO / LIME are not available here, so the
+// container is a plain binary one): <name>_level_<l>[_rank_<r>] =  header, then n_vec vectors of this rank's sub-lattice in the
+// order [parity][x_cb][spin][colour][re, im], fp32.
+namespace {
+struct VecFileHeader {
+  char magic[8];          // "QB200VEC"
+  int version, level, nvec, nspin, ncolor, X[4], rank, nranks, prec;
+};
+std::string vec_file_name(const std::string &base, int level) {
+  std::string n = base + "_level_" + std::to_string(level);
+  if (rt().size > 1) n += "_rank_" + std::to_string(rt().rank);
+  return n;
+}
+void level_dims(const Dirac *m, int *X) {
+  if (const DiracTM *d = dynamic_cast<const DiracTM *>(m)) for (int k = 0; k < 4; k++) X[k] = d->lat->geom.X[k];
+  else if (const DiracCoarse *c = dynamic_cast<const DiracCoarse *>(m)) for (int k = 0; k < 4; k++) X[k] = c->op->geom.X[k];
+  else QB_ERROR("MG: unknown operator type");
+}
+}  // namespace
+
+void MG::save_vectors() {
+  const std::string name = vec_file_name(mp.vec_outfile, level);
+  log_msg(1, "MG level %d: saving %d vectors to %s\n", level + 1, (int)B.size(), name.c_str());
+  FILE *f = fopen(name.c_str(), "wb");
+  if (!f) QB_ERROR("cannot open %s for writing", name.c_str());
+  VecFileHeader h{};
+  memcpy(h.magic, "QB200VEC", 8);
+  h.version = 1; h.level = level; h.nvec = (int)B.size(); h.nspin = B[0]->nspin; h.ncolor = B[0]->ncolor;
+  level_dims(matResidual, h.X);
+  h.rank = rt().rank; h.nranks = rt().size; h.prec = 4;
+  if (fwrite(&h, sizeof(h), 1, f) != 1) QB_ERROR("write error on %s", name.c_str());
+  std::vector<float> host(B[0]->bytes() / sizeof(float));
+  for (auto &v : B) {
+    export_generic(host.data(), *v, rt().compute);
+    if (fwrite(host.data(), sizeof(float), host.size(), f) != host.size()) QB_ERROR("write error on %s", name.c_str());
+  }
+  fclose(f);
+}
+
+void MG::load_vectors() {
+  const MGLevelParam &lp = mp.level[level];
+  const std::string name = vec_file_name(mp.vec_infile, level);
+  log_msg(1, "MG level %d: loading %d vectors from %s\n", level + 1, lp.nvec, name.c_str());
+  FILE *f = fopen(name.c_str(), "rb");
+  if (!f) QB_ERROR("cannot open %s for reading", name.c_str());
+  VecFileHeader h{};
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "QB200VEC", 8) != 0 || h.version != 1) QB_ERROR("%s is not a null-vector file of this library", name.c_str());
+  std::unique_ptr<SpinorField> like(new_full(*matResidual));
+  int X[4];
+  level_dims(matResidual, X);
+  if (h.level != level || h.nvec < lp.nvec || h.nspin != like->nspin || h.ncolor != like->ncolor || h.nranks != rt().size || h.rank != rt().rank ||
+      h.X[0] != X[0] || h.X[1] != X[1] || h.X[2] != X[2] || h.X[3] != X[3])
+    QB_ERROR("%s does not match this level (file: level %d, %d vectors, %d x %d components, %d x %d x %d x %d, rank %d of %d)", name.c_str(), h.level, h.nvec,
+             h.nspin, h.ncolor, h.X[0], h.X[1], h.X[2], h.X[3], h.rank, h.nranks);
+  std::vector<float> host(like->bytes() / sizeof(float));
+  B.clear();
+  for (int i = 0; i < lp.nvec; i++) {
+    if (fread(host.data(), sizeof(float), host.size(), f) != host.size()) QB_ERROR("%s is truncated", name.c_str());
+    std::unique_ptr<SpinorField> v(new_full(*matResidual));
+    import_generic(*v, host.data(), rt().compute);
+    B.push_back(std::move(v));
+  }
+  fclose(f);
 }
 
 // x <- smoother applied to M x = b through the (possibly even-odd preconditioned) smoother operator

@@ -3,6 +3,7 @@
 // consistency checks of MG::verify (:372-486, disabled in the reference fork, enabled here for tests).
 #pragma once
 #include <memory>
+#include <string>
 #include <vector>
 #include "coarse.h"
 #include "solver.h"
@@ -31,6 +32,7 @@ struct MGParam {
   bool compute_null_vector = true;
   bool generate_all_levels = true;
   int verbosity = 1;
+  std::string vec_infile, vec_outfile;   // near-null vector files (QudaMultigridParam::vec_infile / vec_outfile), "" = none
   bool keep_null_vectors = true;  // false: free the near-null vectors of a level once V and the coarse vectors exist (24 x 96 B/site)
 };
 
@@ -66,6 +68,8 @@ class MG : public Solver {
 
  private:
   void generate_null_vectors();
+  void load_vectors();
+  void save_vectors();
   void cycle(SpinorField &x, SpinorField &b);
 };
 

@@ -291,6 +291,50 @@ def test_block_mg_multi_src_solve(quda, oracle, n_level, X, blocks, nvecs, mode,
         assert np.linalg.norm(a - b_) / np.linalg.norm(b_) < 1e-6
 
 
+def test_null_vector_files_round_trip(quda, oracle, tmp_path):
+    """vec_outfile / vec_infile (multigrid.cpp:607-691; SURVEY 8f.2: QIO-free container): a hierarchy rebuilt from the saved
+    near-null vectors (compute_null_vector = NO) has the same vectors, skips the setup solves and solves in the same iterations."""
+    q, L = quda, quda.lib()
+    X, kappa, mu = (8, 8, 8, 16), 0.1245, 0.005
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711)
+    load_gauge(q, g, X, prec=8, sloppy=4, precond=4, recon=12)
+    base = str(tmp_path / "nullvec").encode()
+
+    def build(compute):
+        ip = mg_inv_param(q, kappa, mu)
+        mgp = q.multigrid_param(ip, n_level=3, geo_block=((2, 2, 2, 4), (2, 2, 2, 2)), n_vec=(8, 8), setup_maxiter=100, setup_tol=5e-6)
+        if compute:
+            mgp.vec_outfile = base
+        else:
+            mgp.compute_null_vector = q.QUDA_COMPUTE_NULL_VECTOR_NO
+            mgp.vec_infile = base
+        mg = L.newMultigridQuda(C.byref(mgp))
+        vecs = []
+        info = (C.c_int * 8)()
+        L.mgLevelInfoQudaB200(mg, 0, info)   # geometry of level 1 (the coarse side of the level-0 transfer)
+        for lvl, n in ((0, oracle.V * 24), (1, int(np.prod(info[0:4])) * info[7] * 2)):
+            v = np.zeros(n, dtype=np.float32)
+            L.mgNullVectorQudaB200(mg, lvl, 3, v.ctypes.data)
+            vecs.append(v)
+        b = point_source(oracle.V); x = np.zeros_like(b)
+        p = mg_inv_param(q, kappa, mu); p.inv_type_precondition = q.QUDA_MG_INVERTER; p.preconditioner = mg
+        p.gcrNkrylov = 20; p.tol = 1e-8; p.maxiter = 200; p.reliable_delta = 1e-4
+        L.invertQuda(vp(x), vp(b), C.byref(p))
+        res = host_residual(oracle, g, x, b, kappa, mu)
+        L.destroyMultigridQuda(mg)
+        return vecs, p.iter, res, mgp.secs
+
+    v1, it1, res1, t1 = build(True)
+    import os
+    assert os.path.exists(base.decode() + "_level_0") and os.path.exists(base.decode() + "_level_1")
+    v2, it2, res2, t2 = build(False)
+    print(f"null-vector files: setup {t1:.2f} s computing, {t2:.2f} s loading; MG-GCR {it1} / {it2} iterations, residuals {res1:.2e} / {res2:.2e}")
+    for a, b_ in zip(v1, v2):
+        assert np.array_equal(a, b_)
+    assert it1 == it2 and res2 < 5e-8
+
+
 def test_mg_half_precision_smoother(quda, oracle):
     """cuda_prec_precondition = half on the fine level (int16 links and smoother mat-vec), as the reference allows."""
     res, true_res, it_mg, it_plain, *_ = run_mg_solve(
