@@ -1267,3 +1267,26 @@ extern "C" int blasQudaB200(const char *name, long n, int prec, const double *co
   QB_CUDA(cudaStreamSynchronize(s));
   return nres;
 }
+
+// ---- bridges for the C++ facade (quda_cpp.cu) ------------------------------------------------------------------------------
+namespace qb {
+DiracTM *facade_make_dirac(const QudaInvertParam *p, bool pc, Prec gauge_prec) {
+  require_gauge();
+  DiracTM *d = make_dirac(p, pc, pick_gauge(gauge_prec));
+  if (gauge_prec == PREC_HALF) d->gauge_vec = pick_gauge(PREC_SINGLE);   // int16 links, fp32 solver vectors
+  return d;
+}
+void facade_load_spinor(SpinorField &f, const void *h, const QudaInvertParam *p) {
+  import_spinor(f, h, to_prec(p->cpu_prec, "cpu_prec"), to_basis(p->gamma_basis), to_order(p->dirac_order), rt().compute);
+  QB_CUDA(cudaStreamSynchronize(rt().compute));
+}
+void facade_save_spinor(void *h, const SpinorField &f, const QudaInvertParam *p) {
+  export_spinor(h, f, to_prec(p->cpu_prec, "cpu_prec"), to_basis(p->gamma_basis), to_order(p->dirac_order), rt().compute);
+  QB_CUDA(cudaStreamSynchronize(rt().compute));
+}
+void facade_fill_solver_param(SolverParam &s, const QudaInvertParam *p) { fill_solver_param(s, p); }
+void facade_lattice(int *X4) {
+  require_gauge();
+  for (int d = 0; d < 4; d++) X4[d] = G.lat.geom.X[d];
+}
+}  // namespace qb
