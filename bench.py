@@ -90,7 +90,7 @@ def make_inputs(oracle, X, seed):
     return g, sp
 
 
-def run_mg_leg(q, L, oracle, X, precond=2):
+def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True):
     """Second half of the BASELINE metric: 3-level MG-GCR twisted-mass solve (seconds), plus the coarse-operator
     kernels against their HBM roofline.  32^3x64, 4^4 then 2^4 aggregates, 24 vectors per level, MR(2,2) smoother,
     K-cycle, fp64 outer GCR(20) / fp32 MG / int16 level-0 smoother, weak-field SU(3) gauge (periodic)."""
@@ -116,9 +116,13 @@ def run_mg_leg(q, L, oracle, X, precond=2):
     ip = inv_param()
     mgp = q.multigrid_param(ip, n_level=3, geo_block=((4, 4, 4, 4), (2, 2, 2, 2)), n_vec=(24, 24), nu_pre=2, nu_post=2,
                             setup_maxiter=500, setup_tol=5e-6, run_verify=False)
+    # storage precision of the preconditioner's data (V of the transfer operators, coarse links of the single-RHS kernel): fp32, or
+    # fp16 with fp32 arithmetic (what cuda_prec_precondition = half selects; here chosen independently of the level-0 smoother)
+    os.environ["QB_MG_HALF_STORAGE"] = "1" if half_storage else "0"
     t0 = time.perf_counter()
     mg = L.newMultigridQuda(C.byref(mgp))
     setup_s = time.perf_counter() - t0
+    os.environ.pop("QB_MG_HALF_STORAGE", None)
     V = oracle.V
     b = np.zeros(V * 24)
     b[0:24:2] = 1.0  # point source on the first site (multigrid_invert_test.cpp:497-508)
@@ -137,7 +141,7 @@ def run_mg_leg(q, L, oracle, X, precond=2):
     # 12 spin-colour point sources of one propagator: invertMultiSrcQuda on the block path (all sources through the K-cycle in
     # lock-step, coarse levels on the multi-RHS tensor-core operator) against the same call with the block path switched off
     multi = None
-    if os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
+    if full and os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
         nsrc = int(os.environ.get("QB_BENCH_NSRC", "12"))
         bs = []
         for k in range(nsrc):
@@ -161,11 +165,15 @@ def run_mg_leg(q, L, oracle, X, precond=2):
         os.environ.pop("QB_BLOCK_MG", None)
         multi["speedup_per_source"] = multi["sequential"]["solve_seconds"] / multi["block"]["solve_seconds"]
         del bs, xs
-    res = {"lattice": list(X), "levels": 3, "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond], "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
+    res = {"lattice": list(X), "levels": 3, "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond],
+           "preconditioner_storage": "fp16 V and coarse links, fp32 arithmetic" if half_storage else "fp32", "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
            "setup_seconds": setup_s, "solve_seconds": p.secs, "solve_wall_seconds_incl_h2d_d2h": wall_s, "iterations": p.iter,
            "true_res": p.true_res, "tol": 1e-9, "plain_gcr_seconds": p0.secs, "plain_gcr_iterations": p0.iter, "plain_gcr_true_res": p0.true_res}
     if multi:
         res["multi_src_12_point_sources"] = multi
+    if not full:
+        L.destroyMultigridQuda(mg)
+        return res
     peaks, _ = measured_peaks()
     for lvl in (1, 2):
         info = (C.c_int * 8)()
@@ -385,6 +393,7 @@ def main():
     mg_res = None
     if world == 1 and not args.no_mg and not args.no_extra:
         mg_res = run_mg_leg(q, L, oracle, X, args.mg_precond)
+        mg_res_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False)
     sampler.stop_flag = True
 
     # max over ranks of the device time
@@ -436,6 +445,7 @@ def main():
         }
         if mg_res:
             line["extra"]["mg_gcr_3level"] = mg_res
+            line["extra"]["mg_gcr_3level_fp16_preconditioner_storage"] = mg_res_h16
         if half_ms:
             line["extra"]["half_r12"] = {"ms_per_step": half_ms, "gflops": FLOPS_PER_SITE * sites / (half_ms * 1e-3) / 1e9,
                                          "hbm_gbs_compulsory": 296 * Vh / (half_ms * 1e-3) / 1e9,

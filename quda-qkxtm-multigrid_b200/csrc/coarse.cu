@@ -1,5 +1,6 @@
 // Coarse-level operator: storage, the coarse Dslash kernel, batched site-block inversion, DiracCoarse.
 #include "blas.h"
+#include <cuda_fp16.h>
 #include "coarse.h"
 #include "comm.h"
 #include "layout.cuh"
@@ -27,6 +28,8 @@ void CoarseOperator::allocate(const LevelGeom &g, int nvec_) {
 CoarseOperator::~CoarseOperator() {
   if (Y) cudaFree(Y);
   if (Xinv) cudaFree(Xinv);
+  if (Y16) cudaFree(Y16);
+  if (Xinv16) cudaFree(Xinv16);
   if (Ymma) cudaFree(Ymma);
   if (Xinv_mma) cudaFree(Xinv_mma);
   if (nbr) cudaFree(nbr);
@@ -115,6 +118,7 @@ void CoarseOperator::exchange_ghost(const float *field, const long *poff, int pa
 struct CoarseKernelArgs {
   const float4 *Y;
   const float4 *Xinv;
+  const uint2 *Y16, *Xinv16;   // the same matrices as 4 x fp16 per element pair (CoarseOperator::enable_half_links)
   float4 *out;
   const float4 *in_hop, *in_diag, *xpay;
   long out_poff[2], hop_poff[2], diag_poff[2], xpay_poff[2];
@@ -128,7 +132,7 @@ struct CoarseKernelArgs {
   const float4 *ghost[4][2];  // [d][0]: from the backward, [d][1]: from the forward neighbour; [parity][plane][faceVh]
 };
 
-template <int N>
+template <int N, bool H16>
 __global__ void __launch_bounds__(((9 * (N / 2) + 31) / 32) * 32) coarse_dslash_kernel(const CoarseKernelArgs p) {
   constexpr int NRP = N / 2;
   __shared__ float2 xin[9][N + 1];
@@ -199,10 +203,19 @@ __global__ void __launch_bounds__(((9 * (N / 2) + 31) / 32) * 32) coarse_dslash_
     const bool need = diag ? (p.use_x || p.use_xinv) : p.use_y;
     if (need) {
       const long site = (long)parity * Vh + cb;
-      const float4 *M = (diag && p.use_xinv) ? p.Xinv + (size_t)site * N * NRP + rp : p.Y + ((size_t)site * 9 + d) * N * NRP + rp;
+      const size_t moff = (diag && p.use_xinv) ? (size_t)site * N * NRP + rp : ((size_t)site * 9 + d) * N * NRP + rp;
+      const float4 *M = ((diag && p.use_xinv) ? p.Xinv : p.Y) + moff;
+      const uint2 *M16 = ((diag && p.use_xinv) ? p.Xinv16 : p.Y16) + moff;
 #pragma unroll 8
       for (int c = 0; c < N; c++) {
-        const float4 y = ld_stream(M + (size_t)c * NRP);
+        float4 y;
+        if (H16) {
+          const int2 h = ld_stream((const int2 *)(M16 + (size_t)c * NRP));
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2 *>(&h.y));
+          y = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          y = ld_stream(M + (size_t)c * NRP);
+        }
         const float2 xv = xin[d][c];
         const cplx<float> xc(xv.x, xv.y);
         cmac(a0, cplx<float>(y.x, y.y), xc);
@@ -227,7 +240,28 @@ __global__ void __launch_bounds__(((9 * (N / 2) + 31) / 32) * 32) coarse_dslash_
 
 template <int N> static void launch_coarse(const CoarseKernelArgs &k, long nsites) {
   constexpr int threads = ((9 * (N / 2) + 31) / 32) * 32;
-  coarse_dslash_kernel<N><<<(unsigned)nsites, threads, 0, rt().compute>>>(k);
+  if (k.Y16) coarse_dslash_kernel<N, true><<<(unsigned)nsites, threads, 0, rt().compute>>>(k);
+  else coarse_dslash_kernel<N, false><<<(unsigned)nsites, threads, 0, rt().compute>>>(k);
+  QB_CHECK_LAUNCH();
+}
+
+// fp16 copies of the link matrices for the single-RHS kernel (preconditioner storage precision, as later QUDA versions do for the
+// coarse links): the kernel is bound by streaming Y, so halving its bytes halves its time; arithmetic stays fp32
+__global__ void links_to_half_kernel(uint2 *dst, const float4 *src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = src[i];
+  const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+  dst[i] = make_uint2(*reinterpret_cast<const unsigned *>(&lo), *reinterpret_cast<const unsigned *>(&hi));
+}
+void CoarseOperator::enable_half_links() {
+  const size_t ny = (size_t)geom.V() * 9 * N * (N / 2), nx = (size_t)geom.V() * N * (N / 2);
+  if (!Y16) QB_CUDA(cudaMalloc((void **)&Y16, ny * sizeof(uint2)));
+  links_to_half_kernel<<<(unsigned)div_up((long)ny, 256), 256, 0, rt().compute>>>((uint2 *)Y16, (const float4 *)Y, ny);
+  if (Xinv) {
+    if (!Xinv16) QB_CUDA(cudaMalloc((void **)&Xinv16, nx * sizeof(uint2)));
+    links_to_half_kernel<<<(unsigned)div_up((long)nx, 256), 256, 0, rt().compute>>>((uint2 *)Xinv16, (const float4 *)Xinv, nx);
+  }
   QB_CHECK_LAUNCH();
 }
 
@@ -235,6 +269,8 @@ void coarse_apply(const CoarseApplyArgs &a) {
   const CoarseOperator &op = *a.op;
   CoarseKernelArgs k;
   k.Y = (const float4 *)op.Y; k.Xinv = (const float4 *)op.Xinv;
+  const bool h16 = op.Y16 && (!a.use_xinv || op.Xinv16) && !a.force_fp32;
+  k.Y16 = h16 ? (const uint2 *)op.Y16 : nullptr; k.Xinv16 = h16 ? (const uint2 *)op.Xinv16 : nullptr;
   k.out = (float4 *)a.out; k.in_hop = (const float4 *)a.in_hop; k.in_diag = (const float4 *)a.in_diag; k.xpay = (const float4 *)a.xpay;
   for (int p = 0; p < 2; p++) { k.out_poff[p] = a.out_poff[p]; k.hop_poff[p] = a.hop_poff[p]; k.diag_poff[p] = a.diag_poff[p]; k.xpay_poff[p] = a.xpay_poff[p]; }
   for (int d = 0; d < 4; d++) k.X[d] = op.geom.X[d];

@@ -23,6 +23,8 @@ struct CoarseOperator {
   int N = 0;      // 2 * nvec
   float *Y = nullptr;     // [V][9][N][N/2] float4
   float *Xinv = nullptr;  // [V][N][N/2] float4, inverse of the site-diagonal block L_8 (for even-odd preconditioning)
+  void *Y16 = nullptr, *Xinv16 = nullptr;   // optional fp16 copies used by the single-RHS kernel (enable_half_links)
+  void enable_half_links();
   // halo buffers of coarse spinors for partitioned dimensions: [d][dir] -> [parity][plane N/2][faceVh] float4
   // send[d][0] = my slice x_d = 0 (goes backward), send[d][1] = my slice x_d = X_d - 1 (goes forward);
   // recv[d][0] = from the backward neighbour, recv[d][1] = from the forward neighbour (alias of send in self-exchange mode)
@@ -93,6 +95,7 @@ struct CoarseApplyArgs {
   int parity;                // -1: all sites
   bool use_y, use_x, use_xinv;
   float a, b;
+  bool force_fp32 = false;   // ignore the fp16 link copies (residual operator of the K-cycle, verify)
 };
 void coarse_apply(const CoarseApplyArgs &args);
 

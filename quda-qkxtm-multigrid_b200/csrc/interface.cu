@@ -997,6 +997,8 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   mp.generate_all_levels = mgp->generate_all_levels == QUDA_BOOLEAN_YES;
   mp.verbosity = r.verbosity;
   mp.keep_null_vectors = mgp->run_verify == QUDA_BOOLEAN_YES;  // needed by mgVerifyQudaB200 / mgNullVectorQudaB200 only
+  mp.half_storage = ip->cuda_prec_precondition == QUDA_HALF_PRECISION;
+  if (getenv("QB_MG_HALF_STORAGE")) mp.half_storage = atoi(getenv("QB_MG_HALF_STORAGE")) != 0;
   mp.vec_infile = std::string(mgp->vec_infile, strnlen(mgp->vec_infile, sizeof(mgp->vec_infile)));
   mp.vec_outfile = std::string(mgp->vec_outfile, strnlen(mgp->vec_outfile, sizeof(mgp->vec_outfile)));
   if (!mp.compute_null_vector && mp.vec_infile.empty()) QB_ERROR("compute_null_vector = NO needs vec_infile (written by an earlier newMultigridQuda with vec_outfile set)");

@@ -129,6 +129,7 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
     const double tc0 = now_s();
     matResidual->create_coarse_op(*coarse_op, *transfer);
     if (cp.smoother_pc) coarse_op->compute_xinv();
+    if (mp.half_storage) { transfer->enable_half_v(); coarse_op->enable_half_links(); }
     QB_CUDA(cudaStreamSynchronize(rt().compute));
     log_msg(1, "MG level %d: coarse operator %d x %d x %d x %d, N = %d built in %.3f s\n", level + 1, coarse_op->geom.X[0], coarse_op->geom.X[1],
             coarse_op->geom.X[2], coarse_op->geom.X[3], coarse_op->N, now_s() - tc0);

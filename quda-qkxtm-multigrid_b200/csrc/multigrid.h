@@ -33,6 +33,9 @@ struct MGParam {
   bool generate_all_levels = true;
   int verbosity = 1;
   std::string vec_infile, vec_outfile;   // near-null vector files (QudaMultigridParam::vec_infile / vec_outfile), "" = none
+  // 16-bit storage of the preconditioner's data (V for P / R, coarse links for the single-RHS coarse kernel), fp32 arithmetic:
+  // on when cuda_prec_precondition = half (or QB_MG_HALF_STORAGE=1); the outer solver's accuracy is unaffected
+  bool half_storage = false;
   bool keep_null_vectors = true;  // false: free the near-null vectors of a level once V and the coarse vectors exist (24 x 96 B/site)
 };
 

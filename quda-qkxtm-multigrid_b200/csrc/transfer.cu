@@ -3,6 +3,7 @@
 #include <vector>
 #include "layout.cuh"
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "transfer.h"
 #include "comm.h"
 
@@ -106,8 +107,27 @@ __global__ void __launch_bounds__(256) block_ortho_kernel(float *V, const int *c
   }
 }
 
+// V element loaders: fp32 planes (float4 = 2 complex) or the fp16 copy (uint2 = 2 complex, scaled by V16_SCALE so that the small
+// entries of the block-orthonormal vectors stay normal numbers); arithmetic is fp32 either way
+constexpr float V16_SCALE = 64.0f;
+__device__ __forceinline__ float4 ldv(const float4 *p) { return ld_stream(p); }
+__device__ __forceinline__ float4 ldv(const uint2 *p) {
+  const int2 h = ld_stream((const int2 *)p);
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2 *>(&h.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <typename VT> __device__ __forceinline__ float v_unscale() { return sizeof(VT) == sizeof(uint2) ? 1.0f / V16_SCALE : 1.0f; }
+__global__ void v_to_half_kernel(uint2 *dst, const float4 *src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = src[i];
+  const __half2 lo = __floats2half2_rn(v.x * V16_SCALE, v.y * V16_SCALE), hi = __floats2half2_rn(v.z * V16_SCALE, v.w * V16_SCALE);
+  dst[i] = make_uint2(*reinterpret_cast<const unsigned *>(&lo), *reinterpret_cast<const unsigned *>(&hi));
+}
+
 // thread = (fine site, component pair): out(x, k) = sum_j V(x,k,j) c(X, chi(k), j)
-__global__ void __launch_bounds__(128) prolong_kernel(float4 *out, const float4 *cin, const float4 *V, const int *f2c, long Vh_f, long Vh_c,
+template <typename VT>
+__global__ void __launch_bounds__(128) prolong_kernel(float4 *out, const float4 *cin, const VT *V, const int *f2c, long Vh_f, long Vh_c,
                                                       int Nf, int nvec, int cpc) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nkp = Nf / 2;
@@ -120,19 +140,20 @@ __global__ void __launch_bounds__(128) prolong_kernel(float4 *out, const float4 
   const long ccb = cs - (long)cpar * Vh_c;
   // coarse field [parity][plane = (S*nvec + j)/2][cb]
   const float4 *c = cin + ((size_t)cpar * nvec + (size_t)S * nvh) * Vh_c + ccb;
-  const float4 *v0 = V + v_plane(parity, k0, 0, Nf, nvh) * Vh_f + cb;
-  const float4 *v1 = V + v_plane(parity, k0 + 1, 0, Nf, nvh) * Vh_f + cb;
+  const VT *v0 = V + v_plane(parity, k0, 0, Nf, nvh) * Vh_f + cb;
+  const VT *v1 = V + v_plane(parity, k0 + 1, 0, Nf, nvh) * Vh_f + cb;
   cplx<float> a0(0.f, 0.f), a1(0.f, 0.f);
 #pragma unroll 4
   for (int jp = 0; jp < nvh; jp++) {
     const float4 cc = __ldg(c + (size_t)jp * Vh_c);
-    const float4 w0 = ld_stream(v0 + (size_t)jp * Vh_f), w1 = ld_stream(v1 + (size_t)jp * Vh_f);
+    const float4 w0 = ldv(v0 + (size_t)jp * Vh_f), w1 = ldv(v1 + (size_t)jp * Vh_f);
     cmac(a0, cplx<float>(w0.x, w0.y), cplx<float>(cc.x, cc.y));
     cmac(a0, cplx<float>(w0.z, w0.w), cplx<float>(cc.z, cc.w));
     cmac(a1, cplx<float>(w1.x, w1.y), cplx<float>(cc.x, cc.y));
     cmac(a1, cplx<float>(w1.z, w1.w), cplx<float>(cc.z, cc.w));
   }
-  out[((size_t)parity * nkp + kp) * Vh_f + cb] = make_float4(a0.re, a0.im, a1.re, a1.im);
+  const float us = v_unscale<VT>();
+  out[((size_t)parity * nkp + kp) * Vh_f + cb] = make_float4(us * a0.re, us * a0.im, us * a1.re, us * a1.im);
 }
 
 // CTA = one aggregate; threads = (32 site lanes) x (nvec/2 vector pairs).  Deterministic: fixed site order
@@ -209,8 +230,8 @@ __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V,
 // the access pattern of the prolongator.  lane <-> x position <-> aggregate, so each lane accumulates for one aggregate
 // over all rows of the block; the final reduction is a fixed shuffle tree over the row lanes and the bs_x / 2 lanes of
 // the aggregate (deterministic).
-template <int NKP>
-__global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const float4 *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
+template <int NKP, typename VT>
+__global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const VT *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
                                      long Vh_c, int nvec, int cpc, int XL) {
   const int lane = threadIdx.x, jp = threadIdx.y, nvh = nvec / 2;
   const int RS = 32 / XL;
@@ -239,8 +260,8 @@ __global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const float
 #pragma unroll
     for (int kp = 0; kp < NKP; kp++) {
       f[kp] = __ldg(fin + ((size_t)parity * NKP + kp) * Vh_f + cb);
-      w0[kp] = ld_stream(V + v_plane(parity, 2 * kp, jp, 2 * NKP, nvh) * Vh_f + cb);
-      w1[kp] = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, 2 * NKP, nvh) * Vh_f + cb);
+      w0[kp] = ldv(V + v_plane(parity, 2 * kp, jp, 2 * NKP, nvh) * Vh_f + cb);
+      w1[kp] = ldv(V + v_plane(parity, 2 * kp + 1, jp, 2 * NKP, nvh) * Vh_f + cb);
     }
 #pragma unroll
     for (int kp = 0; kp < NKP; kp++) {
@@ -249,6 +270,13 @@ __global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const float
       cmac_conj(acc[S][0], cplx<float>(w0[kp].x, w0[kp].y), f0); cmac_conj(acc[S][1], cplx<float>(w0[kp].z, w0[kp].w), f0);
       cmac_conj(acc[S][0], cplx<float>(w1[kp].x, w1[kp].y), f1); cmac_conj(acc[S][1], cplx<float>(w1[kp].z, w1[kp].w), f1);
     }
+  }
+  {
+    const float us = v_unscale<VT>();
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+      for (int qq = 0; qq < 2; qq++) { acc[s][qq].re *= us; acc[s][qq].im *= us; }
   }
   const int spa = b0 / 2;  // lanes (cb x positions) per aggregate
 #pragma unroll
@@ -275,8 +303,8 @@ constexpr int TRANSFER_MAX_NR = 6;
 struct MultiPtrs { const float4 *in[TRANSFER_MAX_NR]; float4 *out[TRANSFER_MAX_NR]; };
 
 // prolong_kernel for NR coarse vectors at once; ACC: out += P c (the coarse-grid correction is added in place)
-template <int NR, bool ACC>
-__global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const float4 *V, const int *f2c, long Vh_f, long Vh_c, int Nf, int nvec, int cpc) {
+template <int NR, bool ACC, typename VT>
+__global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const VT *V, const int *f2c, long Vh_f, long Vh_c, int Nf, int nvec, int cpc) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nkp = Nf / 2;
   if (t >= 2 * Vh_f * nkp) return;
@@ -287,14 +315,14 @@ __global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const f
   const int cpar = cs >= Vh_c ? 1 : 0;
   const long ccb = cs - (long)cpar * Vh_c;
   const size_t coff = ((size_t)cpar * nvec + (size_t)S * nvh) * Vh_c + ccb;
-  const float4 *v0 = V + v_plane(parity, k0, 0, Nf, nvh) * Vh_f + cb;
-  const float4 *v1 = V + v_plane(parity, k0 + 1, 0, Nf, nvh) * Vh_f + cb;
+  const VT *v0 = V + v_plane(parity, k0, 0, Nf, nvh) * Vh_f + cb;
+  const VT *v1 = V + v_plane(parity, k0 + 1, 0, Nf, nvh) * Vh_f + cb;
   cplx<float> a0[NR], a1[NR];
 #pragma unroll
   for (int r = 0; r < NR; r++) { a0[r] = cplx<float>(0.f, 0.f); a1[r] = cplx<float>(0.f, 0.f); }
 #pragma unroll 4
   for (int jp = 0; jp < nvh; jp++) {
-    const float4 w0 = ld_stream(v0 + (size_t)jp * Vh_f), w1 = ld_stream(v1 + (size_t)jp * Vh_f);
+    const float4 w0 = ldv(v0 + (size_t)jp * Vh_f), w1 = ldv(v1 + (size_t)jp * Vh_f);
 #pragma unroll
     for (int r = 0; r < NR; r++) {
       const float4 cc = __ldg(p.in[r] + coff + (size_t)jp * Vh_c);
@@ -307,15 +335,16 @@ __global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const f
   const size_t o = ((size_t)parity * nkp + kp) * Vh_f + cb;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
-    float4 v = make_float4(a0[r].re, a0[r].im, a1[r].re, a1[r].im);
+    const float us = v_unscale<VT>();
+    float4 v = make_float4(us * a0[r].re, us * a0[r].im, us * a1[r].re, us * a1[r].im);
     if (ACC) { const float4 old = p.out[r][o]; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
     p.out[r][o] = v;
   }
 }
 
 // restrict_rows_kernel for NR fine vectors at once (same thread mapping and reduction tree: deterministic)
-template <int NKP, int NR>
-__global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p, const float4 *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
+template <int NKP, int NR, typename VT>
+__global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p, const VT *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
                                            long Vh_c, int nvec, int cpc, int XL) {
   const int lane = threadIdx.x, jp = threadIdx.y, nvh = nvec / 2;
   const int RS = 32 / XL;
@@ -345,8 +374,8 @@ __global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p
     float4 w0[NKP], w1[NKP];
 #pragma unroll
     for (int kp = 0; kp < NKP; kp++) {
-      w0[kp] = ld_stream(V + v_plane(parity, 2 * kp, jp, 2 * NKP, nvh) * Vh_f + cb);
-      w1[kp] = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, 2 * NKP, nvh) * Vh_f + cb);
+      w0[kp] = ldv(V + v_plane(parity, 2 * kp, jp, 2 * NKP, nvh) * Vh_f + cb);
+      w1[kp] = ldv(V + v_plane(parity, 2 * kp + 1, jp, 2 * NKP, nvh) * Vh_f + cb);
     }
 #pragma unroll
     for (int r = 0; r < NR; r++) {
@@ -371,7 +400,8 @@ __global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p
   for (int r = 0; r < NR; r++)
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-      float v[4] = {acc[r][s][0].re, acc[r][s][0].im, acc[r][s][1].re, acc[r][s][1].im};
+      const float us = v_unscale<VT>();
+      float v[4] = {us * acc[r][s][0].re, us * acc[r][s][0].im, us * acc[r][s][1].re, us * acc[r][s][1].im};
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         for (int o = 16; o >= XL; o >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
@@ -511,6 +541,7 @@ Transfer::Transfer(const std::vector<SpinorField *> &B, int nvec_, int *bs, int 
 
 Transfer::~Transfer() {
   if (V) cudaFree(V);
+  if (V16) cudaFree(V16);
   if (f2c) cudaFree(f2c);
   if (c2f) cudaFree(c2f);
   for (int d = 0; d < 4; d++)
@@ -523,7 +554,8 @@ void Transfer::P(SpinorField &fo, const SpinorField &ci) const {
   if (fo.nparity != 2 || ci.nparity != 2 || fo.Vh != fine.Vh || ci.Vh != coarse.Vh || fo.ncomplex != Nf || ci.ncomplex != 2 * nvec)
     QB_ERROR("Transfer::P: field geometry mismatch");
   const long nt = 2 * fine.Vh * (Nf / 2);
-  prolong_kernel<<<div_up(nt, 128), 128, 0, rt().compute>>>((float4 *)fo.v, (const float4 *)ci.v, (const float4 *)V, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2);
+  if (V16) prolong_kernel<uint2><<<div_up(nt, 128), 128, 0, rt().compute>>>((float4 *)fo.v, (const float4 *)ci.v, (const uint2 *)V16, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2);
+  else prolong_kernel<float4><<<div_up(nt, 128), 128, 0, rt().compute>>>((float4 *)fo.v, (const float4 *)ci.v, (const float4 *)V, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2);
   QB_CHECK_LAUNCH();
   flops += 8ll * Nf * nvec * fine.V();
 }
@@ -541,8 +573,10 @@ void Transfer::R(SpinorField &co, const SpinorField &fi) const {
   else if (fine.Xh % 8 == 0) XL = 8;
   if (Nf == 12 && XL && (b0 == 2 || b0 == 4 || b0 == 8) && geo_bs[1] % (32 / XL) == 0 && !getenv("QB_RESTRICT_OLD")) {
     const unsigned nblk = (unsigned)((fine.Xh / XL) * (fine.X[1] / geo_bs[1]) * (fine.X[2] / geo_bs[2]) * (fine.X[3] / geo_bs[3]));
-    restrict_rows_kernel<6><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, f2c, fine, b0, geo_bs[1],
-                                                                            geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL);
+    if (V16) restrict_rows_kernel<6, uint2><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const uint2 *)V16, f2c, fine, b0,
+                                                                                          geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL);
+    else restrict_rows_kernel<6, float4><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, f2c, fine, b0,
+                                                                                       geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL);
   } else if (Nf == 12) RK(6);
   else RK(0);
 #undef RK
@@ -563,9 +597,10 @@ void Transfer::P_multi(SpinorField *const *fo, const SpinorField *const *ci, int
         QB_ERROR("Transfer::P_multi: field geometry mismatch");
       p.out[r] = (float4 *)f.v; p.in[r] = (const float4 *)c.v;
     }
+#define PMV(NR_, ACC_, VT_, VP_) prolong_multi_kernel<NR_, ACC_, VT_><<<div_up(nt, 128), 128, 0, rt().compute>>>(p, (const VT_ *)VP_, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2)
 #define PM(NR_) \
-    if (accumulate) prolong_multi_kernel<NR_, true><<<div_up(nt, 128), 128, 0, rt().compute>>>(p, (const float4 *)V, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2); \
-    else prolong_multi_kernel<NR_, false><<<div_up(nt, 128), 128, 0, rt().compute>>>(p, (const float4 *)V, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2)
+    if (V16) { if (accumulate) PMV(NR_, true, uint2, V16); else PMV(NR_, false, uint2, V16); } \
+    else { if (accumulate) PMV(NR_, true, float4, V); else PMV(NR_, false, float4, V); }
     switch (nr) {
       case 1: PM(1); break;
       case 2: PM(2); break;
@@ -575,6 +610,7 @@ void Transfer::P_multi(SpinorField *const *fo, const SpinorField *const *ci, int
       default: PM(6); break;
     }
 #undef PM
+#undef PMV
     QB_CHECK_LAUNCH();
     flops += 8ll * Nf * nvec * fine.V() * nr;
   }
@@ -602,7 +638,9 @@ void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int
         QB_ERROR("Transfer::R_multi: field geometry mismatch");
       p.out[r] = (float4 *)c.v; p.in[r] = (const float4 *)f.v;
     }
-#define RM(NR_) restrict_rows_multi_kernel<6, NR_><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const float4 *)V, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL)
+#define RM(NR_) \
+    if (V16) restrict_rows_multi_kernel<6, NR_, uint2><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const uint2 *)V16, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL); \
+    else restrict_rows_multi_kernel<6, NR_, float4><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const float4 *)V, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL)
     switch (nr) {
       case 1: RM(1); break;
       case 2: RM(2); break;
@@ -615,6 +653,15 @@ void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int
     QB_CHECK_LAUNCH();
     flops += 8ll * Nf * nvec * fine.V() * nr;
   }
+}
+
+// fp16 copy of V for the prolongator / restrictor (both are bound by streaming V); the coarse-link build, the block orthogonalisation
+// and the fallback aggregate-major restrictor keep the fp32 V
+void Transfer::enable_half_v() {
+  const size_t n = v_bytes() / 16;
+  if (!V16) QB_CUDA(cudaMalloc((void **)&V16, n * sizeof(uint2)));
+  v_to_half_kernel<<<(unsigned)div_up((long)n, 256), 256, 0, rt().compute>>>((uint2 *)V16, (const float4 *)V, n);
+  QB_CHECK_LAUNCH();
 }
 
 }  // namespace qb

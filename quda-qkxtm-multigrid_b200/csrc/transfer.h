@@ -43,6 +43,8 @@ class Transfer {
   int block_sites = 1;
   LevelGeom fine, coarse;
   float *V = nullptr;   // [parity][k][nvec/2][Vh_f] float4
+  void *V16 = nullptr;  // optional fp16 copy (same indexing, 4 halves per element pair) used by P / R when set
+  void enable_half_v();
   int *f2c = nullptr;   // [parity*Vh_f + cb]      -> coarse full index (parity_c*Vh_c + cb_c)
   int *c2f = nullptr;   // [coarse full index][block_sites] -> fine full index
   // ghost copies of V on the neighbours' boundary slices, [d][0]: backward neighbour's x_d = X_d-1 slice, [d][1]: forward

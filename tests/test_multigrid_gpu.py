@@ -335,6 +335,45 @@ def test_null_vector_files_round_trip(quda, oracle, tmp_path):
     assert it1 == it2 and res2 < 5e-8
 
 
+def test_mg_fp16_preconditioner_storage(quda, oracle, monkeypatch):
+    """QB_MG_HALF_STORAGE=1: V (prolongator / restrictor) and the coarse links of the single-RHS kernel stored as fp16, fp32 arithmetic.
+    Only the preconditioner changes: the outer solve reaches the same true residual in (almost) the same number of iterations, and the
+    transfer operators agree with their fp32 versions to fp16 rounding."""
+    q, L = quda, quda.lib()
+    X, kappa, mu, tol = (16, 16, 16, 16), 0.1248, 0.004, 1e-8
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711)
+    load_gauge(q, g, X, prec=8, sloppy=4, precond=4, recon=12)
+    rng = np.random.default_rng(3)
+    out = {}
+    for half in (0, 1):
+        monkeypatch.setenv("QB_MG_HALF_STORAGE", str(half))
+        ip = mg_inv_param(q, kappa, mu)
+        mgp = q.multigrid_param(ip, n_level=3, geo_block=((4, 4, 4, 4), (2, 2, 2, 2)), n_vec=(8, 8), setup_maxiter=200, setup_tol=5e-6)
+        mg = L.newMultigridQuda(C.byref(mgp))
+        info = (C.c_int * 8)()
+        L.mgLevelInfoQudaB200(mg, 0, info)
+        nc = int(np.prod(info[0:4])) * info[7] * 2
+        rng = np.random.default_rng(3)
+        fine = rng.standard_normal(oracle.V * 24).astype(np.float32)
+        coarse = rng.standard_normal(nc).astype(np.float32)
+        pf = np.zeros(oracle.V * 24, dtype=np.float32); rc = np.zeros(nc, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        L.mgProlongQudaB200(mg, 0, pf.ctypes.data_as(fp), coarse.ctypes.data_as(fp))
+        L.mgRestrictQudaB200(mg, 0, rc.ctypes.data_as(fp), fine.ctypes.data_as(fp))
+        b = point_source(oracle.V); x = np.zeros_like(b)
+        p = mg_inv_param(q, kappa, mu); p.inv_type_precondition = q.QUDA_MG_INVERTER; p.preconditioner = mg
+        p.gcrNkrylov = 20; p.tol = tol; p.maxiter = 200; p.reliable_delta = 1e-4
+        L.invertQuda(vp(x), vp(b), C.byref(p))
+        out[half] = (pf, rc, p.iter, host_residual(oracle, g, x, b, kappa, mu))
+        L.destroyMultigridQuda(mg)
+    dp = np.linalg.norm(out[1][0] - out[0][0]) / np.linalg.norm(out[0][0])
+    dr = np.linalg.norm(out[1][1] - out[0][1]) / np.linalg.norm(out[0][1])
+    print(f"fp16 storage: P deviates by {dp:.2e}, R by {dr:.2e}; MG-GCR iterations {out[0][2]} (fp32) / {out[1][2]} (fp16), residuals {out[0][3]:.2e} / {out[1][3]:.2e}")
+    assert 1e-6 < dp < 2e-3 and 1e-6 < dr < 2e-3            # fp16 rounding of V, and really a different storage
+    assert out[1][3] < 5e-8 and abs(out[1][2] - out[0][2]) <= 2
+
+
 def test_mg_half_precision_smoother(quda, oracle):
     """cuda_prec_precondition = half on the fine level (int16 links and smoother mat-vec), as the reference allows."""
     res, true_res, it_mg, it_plain, *_ = run_mg_solve(
