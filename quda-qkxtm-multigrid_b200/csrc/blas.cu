@@ -259,6 +259,40 @@ _Pragma("unroll")
   flops += 8 * x.reals(); bytes += 5 * x.bytes();
 }
 
+// first step of a fixed-iteration MR smoother started from the source itself (no copy of b into r, no normalisation pass):
+//   x (+)= a b,   r = b - a Ab          [reads b, Ab (and x), writes x, r]
+void mrFirstStep(Complex a, const SpinorField &b, const SpinorField &Ab, SpinorField &x, SpinorField &r, bool accumulate) {
+  check_same(b, Ab); check_same(b, x); check_same(b, r);
+  BY_PREC(b, const Pack<real> *B = (const Pack<real> *)b.v; const Pack<real> *AB = (const Pack<real> *)Ab.v; Pack<real> *X = (Pack<real> *)x.v;
+          Pack<real> *R = (Pack<real> *)r.v;
+          const cplx<real> A((real)a.real(), (real)a.imag()), mA(-(real)a.real(), -(real)a.imag());
+          elementwise(npacks<real>(b), [=] __device__(long i) {
+            Pack<real> u = B[i], w = AB[i], v;
+            if (accumulate) v = X[i];
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) {
+              if (!accumulate) v.c[k] = cplx<real>((real)0, (real)0);
+              cmac(v.c[k], A, u.c[k]);
+              cmac(u.c[k], mA, w.c[k]);
+            }
+            X[i] = v; R[i] = u;
+          }););
+  flops += 8 * b.reals(); bytes += (accumulate ? 5 : 4) * b.bytes();
+}
+
+// y = a x
+void cax(Complex a, const SpinorField &x, SpinorField &y) {
+  check_same(x, y);
+  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const cplx<real> A((real)a.real(), (real)a.imag());
+          elementwise(npacks<real>(x), [=] __device__(long i) {
+            Pack<real> u = X[i], v;
+_Pragma("unroll")
+            for (int k = 0; k < Pack<real>::N; k++) v.c[k] = A * u.c[k];
+            Y[i] = v;
+          }););
+  flops += 6 * x.reals(); bytes += 2 * x.bytes();
+}
+
 // ---- reductions -------------------------------------------------------------------------------
 double norm2(const SpinorField &x) {
   double out[1];

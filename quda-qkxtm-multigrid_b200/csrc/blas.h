@@ -38,6 +38,8 @@ void caxpbypz(Complex a, const SpinorField &x, Complex b, const SpinorField &y, 
 void caxpbypzYmbw(Complex a, const SpinorField &x, Complex b, SpinorField &y, SpinorField &z, const SpinorField &w);  // z += a x + b y; y -= b w
 void cabxpyAx(double a, Complex b, SpinorField &x, SpinorField &y);        // y += a b x; x *= a
 void caxpyXmaz(Complex a, SpinorField &x, SpinorField &y, const SpinorField &z);  // y += a x; x -= a z
+void mrFirstStep(Complex a, const SpinorField &b, const SpinorField &Ab, SpinorField &x, SpinorField &r, bool accumulate);  // x (+)= a b; r = b - a Ab
+void cax(Complex a, const SpinorField &x, SpinorField &y);                  // y = a x
 
 double norm2(const SpinorField &x);
 double reDotProduct(const SpinorField &x, const SpinorField &y);
