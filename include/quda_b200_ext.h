@@ -39,6 +39,9 @@ double timeDslashQudaB200(void *out, void *in, QudaInvertParam *param, QudaParit
 
 /* launch geometry of the fine Dslash kernels (the reference autotunes this, lib/tune.cpp:480-655;
  * here a fixed default is used and this knob exists for tuning runs).  Call after loadGaugeQuda. */
+/* mean ms of one batched hop over `nbatch` fp32 parity fields (multi-RHS fine Dslash: links fetched once for all members);
+   max_dev_vs_single: largest relative L2 deviation of a member from the single-field kernel on the same input (expected: 0) */
+double timeDslashBatchQudaB200(QudaInvertParam *param, QudaParity parity, int nbatch, int niter, double *max_dev_vs_single /* may be NULL */);
 void setDslashBlockSizeQudaB200(int threads_per_block);
 /* number of kernels this library has launched since initQuda (monotonic counter) */
 long long kernelLaunchCountQudaB200(void);

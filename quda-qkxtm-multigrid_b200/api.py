@@ -133,7 +133,7 @@ EXPORTS = [
     "destroyMultigridQuda", "dslashQuda", "MatQuda", "MatDagMatQuda",
     "loadCloverQuda", "freeCloverQuda", "invertMultiSrcQuda", "invertMultiShiftQuda", "cloverQuda",
     "newSpinorQudaB200", "freeSpinorQudaB200", "loadSpinorQudaB200", "saveSpinorQudaB200",
-    "dslashResidentQudaB200", "matResidentQudaB200", "matDagMatResidentQudaB200", "timeDslashQudaB200",
+    "dslashResidentQudaB200", "matResidentQudaB200", "matDagMatResidentQudaB200", "timeDslashQudaB200", "timeDslashBatchQudaB200",
     "setDslashBlockSizeQudaB200", "kernelLaunchCountQudaB200", "computeStreamQudaB200", "syncQudaB200",
     "ncclUniqueIdQudaB200", "commsBootstrapQudaB200", "commDimPartitionedSetQudaB200",
     "commRankInfoQudaB200", "faceIndexMapQudaB200",
@@ -186,6 +186,8 @@ def lib():
     L.matDagMatResidentQudaB200.argtypes = [_p, _p, IP]
     L.timeDslashQudaB200.argtypes = [_p, _p, IP, _i, _i, C.POINTER(C.c_float)]
     L.timeDslashQudaB200.restype = _d
+    L.timeDslashBatchQudaB200.argtypes = [IP, _i, _i, _i, C.POINTER(_d)]
+    L.timeDslashBatchQudaB200.restype = _d
     L.setDslashBlockSizeQudaB200.argtypes = [_i]
     L.kernelLaunchCountQudaB200.restype = C.c_longlong
     L.computeStreamQudaB200.restype = _p

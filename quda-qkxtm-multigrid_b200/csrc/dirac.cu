@@ -29,8 +29,8 @@ DiracTM::DiracTM(Lattice *lat_, const GaugeField *gauge_, double kappa_, double 
 }
 
 SpinorField &DiracTM::tmp(std::unique_ptr<SpinorField> &t, const SpinorField &like) const {
-  if (!t || t->prec != like.prec || t->Vh != like.Vh || t->nparity != like.nparity)
-    t.reset(new SpinorField(like.Vh, like.nparity, like.prec));
+  if (!t || t->prec != like.prec || t->Vh != like.Vh || t->nparity != like.nparity || t->nbatch != like.nbatch)
+    t.reset(new SpinorField(like.Vh, like.nparity, like.prec, 4, 3, like.nbatch));
   return *t;
 }
 

@@ -38,6 +38,8 @@ struct DslashParam {
   long stride;                            // plane stride of spinors and links (= Vh)
   double cin[2], co[2], cx[2];            // (p, q) pairs
   double sgn_fwd;                         // -1: (1 - gamma) on forward hops (no dagger), +1: dagger
+  int nbatch;                             // batched fields: member = threadIdx.y, byte strides below (0 = not batched)
+  long batch_in, batch_out, batch_x;
   int site_begin, site_count;             // contiguous range ...
   const int *site_list;                   // ... or explicit list of cb sites (interior / boundary split)
 };
@@ -225,8 +227,8 @@ template <typename Store> __host__ __device__ constexpr bool use_packed() {
 
 // one hop: MU direction, BACK = 0 forward (x+mu), 1 backward (x-mu); GHOST = false compiles the ghost-zone branches away
 // (unpartitioned lattices and the interior launch of partitioned ones: straight-line code, loads hoisted across hops)
-template <typename Store, int RECON, bool TWIST_IN, bool GHOST, int MU, int BACK>
-__device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const DslashParam &p, const int *x, int full, int cb) {
+template <typename Store, int RECON, bool TWIST_IN, bool GHOST, bool BATCH, int MU, int BACK>
+__device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const DslashParam &p, const void *in, const int *x, int full, int cb) {
   typedef typename Store::real real;
   const Geom &g = p.g;
   const int L = g.X[MU];
@@ -246,7 +248,7 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
     const int nfull = BACK ? (edge ? full + (L - 1) * step : full - step) : (edge ? full - (L - 1) * step : full + step);
     nbr = nfull >> 1;
     cplx<real> psi[12];
-    sc = Store::template load<12>(psi, p.in, p.in_norm, p.stride, nbr);
+    sc = Store::template load<12>(psi, in, p.in_norm, p.stride, nbr);
     if (TWIST_IN) { if constexpr (PK) apply_twist_pk(psi, (real)p.cin[0], (real)p.cin[1]); else apply_twist(psi, (real)p.cin[0], (real)p.cin[1]); }
     if constexpr (PK) project_pk<MU>(h, psi, sigma); else project<MU>(h, psi, sigma);
   }
@@ -254,11 +256,11 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
   // link: forward hop uses U_mu(x) (own parity, own site); backward uses U_mu(x-mu)^dag (other parity)
   real raw[RECON];
   if (!BACK) {
-    LinkRaw<Store, RECON>::load(raw, (const char *)p.gauge_fwd + MU * link_block_bytes<Store, RECON>(p.stride), p.stride, cb);
+    LinkRaw<Store, RECON>::template load<!BATCH>(raw, (const char *)p.gauge_fwd + MU * link_block_bytes<Store, RECON>(p.stride), p.stride, cb);
   } else if (use_ghost) {
-    LinkRaw<Store, RECON>::load(raw, p.gauge_ghost[MU], g.faceVh[MU], fidx);
+    LinkRaw<Store, RECON>::template load<!BATCH>(raw, p.gauge_ghost[MU], g.faceVh[MU], fidx);
   } else {
-    LinkRaw<Store, RECON>::load(raw, (const char *)p.gauge_bwd + MU * link_block_bytes<Store, RECON>(p.stride), p.stride, nbr);
+    LinkRaw<Store, RECON>::template load<!BATCH>(raw, (const char *)p.gauge_bwd + MU * link_block_bytes<Store, RECON>(p.stride), p.stride, nbr);
   }
   real u0;
   if (MU < 3) u0 = RECON == 8 ? (real)1 / (real)g.aniso : (real)g.aniso;
@@ -288,12 +290,32 @@ template <> struct DslashBounds<StoreD> { static constexpr int max_threads = 128
 #else
 #define QB_DSLASH_BOUNDS __launch_bounds__(DslashBounds<Store>::max_threads, DslashBounds<Store>::min_blocks)
 #endif
-template <typename Store, int RECON, bool TWIST_IN, bool HAS_X, bool GHOST>
-__global__ void QB_DSLASH_BOUNDS dslash_kernel(const DslashParam p) {
+// BATCH: blockDim = (32 sites, nbatch members <= 12), every warp works on one member of a batched field for the same 32 sites, so the
+// links of those sites come from HBM once and from L1 for the other members (they are loaded with L1 allocation here, not streamed)
+constexpr int DSLASH_BATCH_MAX = 12;
+template <typename Store, int RECON, bool TWIST_IN, bool HAS_X, bool GHOST, bool BATCH> struct DslashLaunchBounds {
+  static constexpr int max_threads = BATCH ? 32 * DSLASH_BATCH_MAX : DslashBounds<Store>::max_threads;
+  static constexpr int min_blocks = BATCH ? (sizeof(typename Store::real) == 8 ? 1 : 2) : DslashBounds<Store>::min_blocks;
+};
+template <typename Store, int RECON, bool TWIST_IN, bool HAS_X, bool GHOST, bool BATCH = false>
+__global__ void
+#ifdef QB_DSLASH_MINB
+QB_DSLASH_BOUNDS
+#else
+__launch_bounds__(DslashLaunchBounds<Store, RECON, TWIST_IN, HAS_X, GHOST, BATCH>::max_threads, DslashLaunchBounds<Store, RECON, TWIST_IN, HAS_X, GHOST, BATCH>::min_blocks)
+#endif
+dslash_kernel(const DslashParam p) {
   typedef typename Store::real real;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.site_count) return;
   const int cb = p.site_list ? p.site_list[tid] : p.site_begin + tid;
+  const void *in = p.in, *xin = p.x;
+  void *out = p.out;
+  if (BATCH) {
+    in = (const char *)p.in + (size_t)threadIdx.y * p.batch_in;
+    out = (char *)p.out + (size_t)threadIdx.y * p.batch_out;
+    xin = (const char *)p.x + (size_t)threadIdx.y * p.batch_x;
+  }
 
   int x[4], full;
   cb_coords(x, full, cb, p.parity, p.g);
@@ -314,28 +336,28 @@ __global__ void QB_DSLASH_BOUNDS dslash_kernel(const DslashParam p) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
       }
   }
-  hop<Store, RECON, TWIST_IN, GHOST, 0, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, GHOST, 0, 1>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, GHOST, 1, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, GHOST, 1, 1>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, GHOST, 2, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, GHOST, 2, 1>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, GHOST, 3, 0>(acc, p, x, full, cb);
-  hop<Store, RECON, TWIST_IN, GHOST, 3, 1>(acc, p, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 0, 0>(acc, p, in, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 0, 1>(acc, p, in, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 1, 0>(acc, p, in, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 1, 1>(acc, p, in, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 2, 0>(acc, p, in, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 2, 1>(acc, p, in, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 3, 0>(acc, p, in, x, full, cb);
+  hop<Store, RECON, TWIST_IN, GHOST, BATCH, 3, 1>(acc, p, in, x, full, cb);
 
   // epilogue: out = Cx x + Co acc
   constexpr bool PK = use_packed<Store>();
   if constexpr (PK) apply_twist_pk(acc, (real)p.co[0], (real)p.co[1]); else apply_twist(acc, (real)p.co[0], (real)p.co[1]);
   if (HAS_X) {
     cplx<real> xs[12];
-    const real xsc = Store::template load<12, false>(xs, p.x, p.x_norm, p.stride, cb);
+    const real xsc = Store::template load<12, false>(xs, xin, p.x_norm, p.stride, cb);
     const cplx<real> cu((real)p.cx[0] * xsc, (real)p.cx[1] * xsc), cl((real)p.cx[0] * xsc, -(real)p.cx[1] * xsc);
 #pragma unroll
     for (int k = 0; k < 6; k++) { if constexpr (PK) cmac_pk(acc[k], cu, xs[k]); else cmac(acc[k], cu, xs[k]); }
 #pragma unroll
     for (int k = 6; k < 12; k++) { if constexpr (PK) cmac_pk(acc[k], cl, xs[k]); else cmac(acc[k], cl, xs[k]); }
   }
-  Store::template store<12>(p.out, p.out_norm, p.stride, cb, acc);
+  Store::template store<12>(out, p.out_norm, p.stride, cb, acc);
 }
 
 // ---- face packing (replaces lib/dslash_pack.cu:271-339, :609-674) -------------------------------

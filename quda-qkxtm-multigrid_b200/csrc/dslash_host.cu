@@ -141,9 +141,26 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   // default launch geometry: 128 threads (fp32 / int16), 64 threads (fp64); lat.block_size > 0 overrides
   const int block = lat.block_size > 0 ? lat.block_size : (Store::prec == PREC_DOUBLE ? 64 : 128);
   const bool partitioned = g.part[0] || g.part[1] || g.part[2] || g.part[3];
+  if (out.nbatch != in.nbatch || (x && x->nbatch != out.nbatch)) QB_ERROR("apply_hop: batch sizes differ (out %d, in %d)", out.nbatch, in.nbatch);
+  if (out.nbatch > 1 && partitioned) QB_ERROR("apply_hop: batched fields are supported on unpartitioned lattices only");
   if (!partitioned) {
     p.site_begin = range_begin; p.site_count = range_count < 0 ? g.Vh : range_count; p.site_list = nullptr;
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, range_stream ? range_stream : r.compute);
+    cudaStream_t st = range_stream ? range_stream : r.compute;
+    if (out.nbatch > 1) {
+      // members in groups of DSLASH_BATCH_MAX: one launch per group, links read from HBM once per group
+      for (int first = 0; first < out.nbatch; first += 12) {
+        DslashParam pb = p;
+        pb.nbatch = std::min(12, out.nbatch - first);
+        pb.batch_in = (long)in.batch_bytes; pb.batch_out = (long)out.batch_bytes; pb.batch_x = x ? (long)x->batch_bytes : 0;
+        pb.in = (const char *)in.v + (size_t)first * in.batch_bytes;
+        pb.out = (char *)out.v + (size_t)first * out.batch_bytes;
+        pb.x = x ? (const char *)x->v + (size_t)first * x->batch_bytes : nullptr;
+        if (pb.nbatch == 1) { pb.nbatch = 0; launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, false, block, st); }
+        else launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, false, block, st);
+      }
+      return;
+    }
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, st);
     return;
   }
   if (range_count >= 0) QB_ERROR("apply_hop_range is only available on unpartitioned lattices");

@@ -8,6 +8,24 @@ namespace qb {
 
 template <typename Store, int RECON, bool GHOST>
 static void launch_dslash_recon(const DslashParam &p, bool twist_in, bool has_x, int block, cudaStream_t s) {
+  if (p.nbatch > 1) {  // batched fields: 32 sites x nbatch members per CTA
+    if (GHOST || Store::scaled) QB_ERROR("batched hop: unpartitioned lattices and fp32 / fp64 fields only");
+    if (p.nbatch > DSLASH_BATCH_MAX) QB_ERROR("batched hop: at most %d members per launch", DSLASH_BATCH_MAX);
+    const int nbb = div_up(p.site_count, 32);
+    const dim3 bd(32, p.nbatch);
+    if (nbb == 0) return;
+    if constexpr (!GHOST && !Store::scaled) {
+      if (twist_in) {
+        if (has_x) dslash_kernel<Store, RECON, true, true, false, true><<<nbb, bd, 0, s>>>(p);
+        else dslash_kernel<Store, RECON, true, false, false, true><<<nbb, bd, 0, s>>>(p);
+      } else {
+        if (has_x) dslash_kernel<Store, RECON, false, true, false, true><<<nbb, bd, 0, s>>>(p);
+        else dslash_kernel<Store, RECON, false, false, false, true><<<nbb, bd, 0, s>>>(p);
+      }
+    }
+    QB_CHECK_LAUNCH();
+    return;
+  }
   const int nb = div_up(p.site_count, block);
   if (nb == 0) return;
   if (twist_in) {

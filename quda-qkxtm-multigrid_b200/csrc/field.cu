@@ -4,12 +4,14 @@
 namespace qb {
 
 // ---------------------------------------------------------------------------------------------
-SpinorField::SpinorField(long Vh_, int nparity_, Prec prec_, int nspin_, int ncolor_)
-    : prec(prec_), nparity(nparity_), ncomplex(nspin_ * ncolor_), nspin(nspin_), ncolor(ncolor_), Vh(Vh_) {
+SpinorField::SpinorField(long Vh_, int nparity_, Prec prec_, int nspin_, int ncolor_, int nbatch_)
+    : prec(prec_), nparity(nparity_), ncomplex(nspin_ * ncolor_), nspin(nspin_), ncolor(ncolor_), Vh(Vh_), nbatch(nbatch_) {
   const int sb = prec == PREC_HALF ? 2 : (int)prec;
   if ((ncomplex * 2 * sb) % 16) QB_ERROR("site size %d B is not a multiple of the 16-B plane", ncomplex * 2 * sb);
+  if (nbatch < 1 || (nbatch > 1 && prec == PREC_HALF)) QB_ERROR("batched fields are fp32 / fp64 only");
   parity_bytes = (size_t)Vh * ncomplex * 2 * sb;
-  v = pool_malloc(parity_bytes * nparity);
+  batch_bytes = parity_bytes * nparity;
+  v = pool_malloc(batch_bytes * nbatch);
   if (prec == PREC_HALF) norm = (float *)pool_malloc(sizeof(float) * Vh * nparity);
   owner = true;
 }
@@ -24,6 +26,14 @@ SpinorField::~SpinorField() {
 void SpinorField::view_parity(SpinorField &dst, int p) const {
   dst.prec = prec; dst.nparity = 1; dst.ncomplex = ncomplex; dst.nspin = nspin; dst.ncolor = ncolor; dst.Vh = Vh;
   dst.v = parity_ptr(p); dst.norm = parity_norm(p); dst.parity_bytes = parity_bytes; dst.owner = false;
+  dst.nbatch = nbatch; dst.batch_bytes = batch_bytes;   // a parity view of a batch is a batch of parity views
+}
+
+void SpinorField::member(SpinorField &dst, int c) const {
+  if (c < 0 || c >= nbatch) QB_ERROR("batch member %d out of range (%d members)", c, nbatch);
+  dst.prec = prec; dst.nparity = nparity; dst.ncomplex = ncomplex; dst.nspin = nspin; dst.ncolor = ncolor; dst.Vh = Vh;
+  dst.v = (char *)v + (size_t)c * batch_bytes; dst.norm = nullptr; dst.parity_bytes = parity_bytes; dst.owner = false;
+  dst.nbatch = 1; dst.batch_bytes = batch_bytes;
 }
 
 void SpinorField::zero(cudaStream_t s) {

@@ -38,9 +38,14 @@ struct SpinorField {
   float *norm = nullptr; // half precision only
   size_t parity_bytes = 0;
   bool owner = true;
+  // batch of nbatch fields of identical shape in ONE allocation, batch_bytes apart ([rhs][parity][plane][site]); the members above
+  // describe member 0.  Only the fine-grid operators (apply_hop and everything built on it) understand batches: one launch covers all
+  // members and the links are fetched from HBM once.  BLAS works on member views (member()).
+  int nbatch = 1;
+  size_t batch_bytes = 0;
 
   SpinorField() {}
-  SpinorField(long Vh, int nparity, Prec prec, int nspin = 4, int ncolor = 3);
+  SpinorField(long Vh, int nparity, Prec prec, int nspin = 4, int ncolor = 3, int nbatch = 1);
   ~SpinorField();
   SpinorField(const SpinorField &) = delete;
   SpinorField &operator=(const SpinorField &) = delete;
@@ -52,6 +57,8 @@ struct SpinorField {
   float *parity_norm(int p) const { return norm ? norm + Vh * (nparity == 2 ? p : 0) : nullptr; }
   // non-owning view of one parity of a full field (or the field itself if single parity)
   void view_parity(SpinorField &dst, int p) const;
+  // non-owning view of member c of a batch (nbatch = 1)
+  void member(SpinorField &dst, int c) const;
   void zero(cudaStream_t s);
 };
 

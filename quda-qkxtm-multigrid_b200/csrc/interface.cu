@@ -649,6 +649,38 @@ double timeDslashQudaB200(void *out, void *in, QudaInvertParam *p, QudaParity pa
   return (double)total / niter;
 }
 
+// mean device time (ms) of one batched hop on `nbatch` resident random fp32 parity fields (one launch: links read once for all members)
+double timeDslashBatchQudaB200(QudaInvertParam *p, QudaParity parity, int nbatch, int niter, double *max_dev) {
+  require_gauge();
+  Runtime &r = rt();
+  SpinorField in(G.lat.geom.Vh, 1, PREC_SINGLE, 4, 3, nbatch), out(G.lat.geom.Vh, 1, PREC_SINGLE, 4, 3, nbatch);
+  for (int c = 0; c < nbatch; c++) { SpinorField m; in.member(m, c); random_fill(m, 1234 + c); }
+  std::unique_ptr<DiracTM> d(make_dirac(p, true, pick_gauge(PREC_SINGLE)));
+  for (int k = 0; k < 3; k++) d->Dslash(out, in, (int)parity);
+  cudaEvent_t e0, e1;
+  QB_CUDA(cudaEventCreate(&e0)); QB_CUDA(cudaEventCreate(&e1));
+  QB_CUDA(cudaEventRecord(e0, r.compute));
+  for (int k = 0; k < niter; k++) d->Dslash(out, in, (int)parity);
+  QB_CUDA(cudaEventRecord(e1, r.compute));
+  QB_CUDA(cudaStreamSynchronize(r.compute));
+  float ms = 0;
+  QB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (max_dev) {  // every member against the single-field kernel on the same input: same arithmetic, so the deviation must be exactly zero
+    *max_dev = 0.0;
+    SpinorField ref(G.lat.geom.Vh, 1, PREC_SINGLE);
+    for (int c = 0; c < nbatch; c++) {
+      SpinorField mi, mo;
+      in.member(mi, c); out.member(mo, c);
+      d->Dslash(ref, mi, (int)parity);
+      const double n2 = blas::norm2(ref);
+      const double dev = sqrt(blas::xmyNorm(mo, ref) / n2);
+      if (!(dev <= *max_dev)) *max_dev = dev;
+    }
+  }
+  return (double)ms / niter;
+}
+
 void setDslashBlockSizeQudaB200(int block) {
   if (block != 0 && (block < 32 || block > 128 || (block & 31))) QB_ERROR("dslash block size %d must be 0 (default) or a multiple of 32 in [32, 128]", block);
   G.lat.block_size = block;

@@ -227,29 +227,31 @@ __host__ __device__ inline int gauge_reals_per_plane(int prec, int recon) { retu
 template <typename Store, int RECON> struct LinkRaw;
 
 template <int RECON> struct LinkRaw<StoreD, RECON> {
+  template <bool STREAM = true>
   __device__ __forceinline__ static void load(double *r, const void *base, long stride, long i) {
     const double2 *p = (const double2 *)base + i;
 #pragma unroll
     for (int k = 0; k < RECON / 2; k++) {
-      double2 t = ld_stream(p + (long)k * stride);
+      double2 t = STREAM ? ld_stream(p + (long)k * stride) : ld_nc(p + (long)k * stride);
       r[2 * k] = t.x; r[2 * k + 1] = t.y;
     }
   }
 };
 template <int RECON> struct LinkRaw<StoreS, RECON> {
+  template <bool STREAM = true>
   __device__ __forceinline__ static void load(float *r, const void *base, long stride, long i) {
     if (RECON == 18) {
       const float2 *p = (const float2 *)base + i;
 #pragma unroll
       for (int k = 0; k < 9; k++) {
-        float2 t = ld_stream(p + (long)k * stride);
+        float2 t = STREAM ? ld_stream(p + (long)k * stride) : ld_nc(p + (long)k * stride);
         r[2 * k] = t.x; r[2 * k + 1] = t.y;
       }
     } else {
       const float4 *p = (const float4 *)base + i;
 #pragma unroll
       for (int k = 0; k < RECON / 4; k++) {
-        float4 t = ld_stream(p + (long)k * stride);
+        float4 t = STREAM ? ld_stream(p + (long)k * stride) : ld_nc(p + (long)k * stride);
         r[4 * k] = t.x; r[4 * k + 1] = t.y; r[4 * k + 2] = t.z; r[4 * k + 3] = t.w;
       }
     }
@@ -258,6 +260,7 @@ template <int RECON> struct LinkRaw<StoreS, RECON> {
 // half precision: returns integer-valued floats (the 1/32767 is folded into the hop's accumulation scale,
 // see link_scale()); recon 8 is non-linear in the stored numbers and is converted to real units here
 template <int RECON> struct LinkRaw<StoreH, RECON> {
+  template <bool STREAM = true>
   __device__ __forceinline__ static void load(float *r, const void *base, long stride, long i) {
     if (RECON == 18) {
       const int *p = (const int *)base + i;

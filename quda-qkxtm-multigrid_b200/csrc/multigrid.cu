@@ -335,7 +335,12 @@ void MG::cycle(SpinorField &x, SpinorField &b) {
     if (coarse_solver_gcr) (*coarse_solver_gcr)(*x_coarse, *r_coarse);
     else (*coarse)(*x_coarse, *r_coarse);
   }
-  { Section s(&t_prof[4]); transfer->P(*r, *x_coarse); blas::xpy(*r, x); }
+  {  // x += P x_coarse in one pass (the prolongator adds into x: no temporary, no separate xpy)
+    Section s(&t_prof[4]);
+    SpinorField *fo = &x;
+    const SpinorField *ci = x_coarse.get();
+    transfer->P_multi(&fo, &ci, 1, true);
+  }
   // post-smoothing with x as the initial guess
   if (lp.nu_post > 0) { Section s(&t_prof[5]); smooth(*postsmoother, x, b); }
 }

@@ -316,3 +316,22 @@ def test_resident_api_and_large_lattice_properties(quda, oracle):
         assert rel_l2(out, ref) <= tol, (prec, rel_l2(out, ref))
         L.freeSpinorQudaB200(fin)
         L.freeSpinorQudaB200(fout)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nbatch", [2, 5, 12, 14])
+def test_batched_hop_equals_single_field_hop(quda, oracle, nbatch):
+    """Multi-RHS fine Dslash (batched fields, one launch, links fetched once per 32 sites for all members): every member must
+    equal the single-field kernel on the same input bit for bit (identical arithmetic, only the link loads differ in cache policy).
+    14 members exercise the split into two launches."""
+    q, L = quda, quda.lib()
+    X = (8, 8, 8, 16)
+    oracle.set_dims(X)
+    g = oracle.gauge(1, True, 1.0, 137)
+    gp = q.gauge_param(X, cuda_prec=4, reconstruct=12)
+    L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+    for dagger in (q.QUDA_DAG_NO, q.QUDA_DAG_YES):
+        p = q.invert_param(cuda_prec=4, dagger=dagger, matpc=q.QUDA_MATPC_EVEN_EVEN)
+        dev = C.c_double(-1.0)
+        L.timeDslashBatchQudaB200(C.byref(p), 1, nbatch, 1, C.byref(dev))
+        assert dev.value == 0.0, dev.value
