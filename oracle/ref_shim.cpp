@@ -81,6 +81,24 @@ void tmref_tm_mat(void *out, void **gauge, void *in, double kappa, double mu, in
                   int dagger, int prec_bytes)
 { tm_mat(out, gauge, in, kappa, mu, (QudaTwistFlavorType)flavor, dagger, (QudaPrecision)prec_bytes, gparam_); }
 
+// non-degenerate doublet (wilson_dslash_reference.cpp:461-587).  Doublet parity field = [flavour 1 | flavour 2]; the reference
+// twists its inputs in place for some variants, so callers hand in scratch copies.
+void tmref_tm_ndeg_dslash(void *out, void **gauge, void *in, double kappa, double mu, double eps, int parity, int matpc, int dagger, int prec_bytes)
+{
+  const size_t F = (size_t)Vh * 24 * prec_bytes;
+  tm_ndeg_dslash(out, (char *)out + F, gauge, in, (char *)in + F, kappa, mu, eps, parity, dagger, (QudaMatPCType)matpc, (QudaPrecision)prec_bytes, gparam_);
+}
+void tmref_tm_ndeg_matpc(void *out, void **gauge, void *in, double kappa, double mu, double eps, int matpc, int dagger, int prec_bytes)
+{
+  const size_t F = (size_t)Vh * 24 * prec_bytes;
+  tm_ndeg_matpc(out, (char *)out + F, gauge, in, (char *)in + F, kappa, mu, eps, (QudaMatPCType)matpc, dagger, (QudaPrecision)prec_bytes, gparam_);
+}
+void tmref_tm_ndeg_mat(void *out, void **gauge, void *in, double kappa, double mu, double eps, int dagger, int prec_bytes)
+{
+  const size_t D = (size_t)Vh * 48 * prec_bytes;   // one parity of a doublet field
+  tm_ndeg_mat(out, (char *)out + D, gauge, in, (char *)in + D, kappa, mu, eps, dagger, (QudaPrecision)prec_bytes, gparam_);
+}
+
 void tmref_wil_mat(void *out, void **gauge, void *in, double kappa, int dagger, int prec_bytes)
 { wil_mat(out, gauge, in, kappa, dagger, (QudaPrecision)prec_bytes, gparam_); }
 

@@ -204,6 +204,106 @@ void FN(orc_tm_matpc)(REAL *out, REAL *const *gauge, const REAL *in, double kapp
 
 
 /* ---------------------------------------------------------------------------------------------
+ * Non-degenerate twisted-mass doublet: /root/reference/tests/wilson_dslash_reference.cpp
+ *   ndegTwistGamma5 :412-445  (1 + i a gamma5 tau3 + b tau1) on the flavour pair, a = +-2 kappa mu, b = -+2 kappa epsilon,
+ *                             inverse: times d = 1 / (1 + a^2 - b^2); dagger flips a
+ *   tm_ndeg_dslash :461-473, tm_ndeg_matpc :476-541, tm_ndeg_mat :544-587
+ * A doublet parity field is [flavour 1 | flavour 2], each Vh x 24 reals; a full doublet field is [even doublet | odd doublet].
+ * Same operation order as the reference (fp64 agrees to the bit); unlike the reference the inputs are never modified.
+ * ------------------------------------------------------------------------------------------- */
+void FN(orc_ndeg_twist)(REAL *out1, REAL *out2, const REAL *in1, const REAL *in2, int dagger, double kappa_, double mu_, double eps_, long n, int inverse)
+{
+  const REAL kappa = (REAL)kappa_, mu = (REAL)mu_, epsilon = (REAL)eps_;
+  REAL a, b, d;
+  if (!inverse) { a = (REAL)2.0 * kappa * mu; b = (REAL)-2.0 * kappa * epsilon; d = (REAL)1.0; }
+  else { a = (REAL)-2.0 * kappa * mu; b = (REAL)2.0 * kappa * epsilon; d = (REAL)1.0 / ((REAL)1.0 + a * a - b * b); }
+  if (dagger) a *= (REAL)-1.0;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; i++) {
+    REAL t1[24], t2[24];
+    for (int s = 0; s < 4; s++)
+      for (int c = 0; c < 3; c++) {
+        const REAL a5 = ((s / 2) ? (REAL)-1.0 : (REAL)1.0) * a;
+        const long k = i * 24 + s * 6 + c * 2;
+        t1[s * 6 + c * 2 + 0] = d * (in1[k + 0] - a5 * in1[k + 1] + b * in2[k + 0]);
+        t1[s * 6 + c * 2 + 1] = d * (in1[k + 1] + a5 * in1[k + 0] + b * in2[k + 1]);
+        t2[s * 6 + c * 2 + 0] = d * (in2[k + 0] + a5 * in2[k + 1] + b * in1[k + 0]);
+        t2[s * 6 + c * 2 + 1] = d * (in2[k + 1] - a5 * in2[k + 0] + b * in1[k + 1]);
+      }
+    for (int j = 0; j < 24; j++) { out1[i * 24 + j] = t1[j]; out2[i * 24 + j] = t2[j]; }
+  }
+}
+
+/* out, in: doublet parity fields */
+void FN(orc_tm_ndeg_dslash)(REAL *out, REAL *const *gauge, const REAL *in, double kappa, double mu, double eps, int parity, int matpc, int dagger)
+{
+  const long Vh = orc_lat.Vh, F = Vh * 24;
+  if (dagger && FN(symmetric_)(matpc)) {
+    REAL *tmp = (REAL *)malloc(sizeof(REAL) * 2 * F);
+    FN(orc_ndeg_twist)(tmp, tmp + F, in, in + F, dagger, kappa, mu, eps, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, parity, dagger);
+    FN(orc_wil_dslash)(out + F, gauge, tmp + F, parity, dagger);
+    free(tmp);
+  } else {
+    FN(orc_wil_dslash)(out, gauge, in, parity, dagger);
+    FN(orc_wil_dslash)(out + F, gauge, in + F, parity, dagger);
+    FN(orc_ndeg_twist)(out, out + F, out, out + F, dagger, kappa, mu, eps, Vh, 1);
+  }
+}
+
+void FN(orc_tm_ndeg_matpc)(REAL *out, REAL *const *gauge, const REAL *in, double kappa, double mu, double eps, int matpc, int dagger)
+{
+  const long Vh = orc_lat.Vh, F = Vh * 24;
+  const int p_out = (matpc == ORC_MATPC_EVEN_EVEN || matpc == ORC_MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p_out;
+  REAL *tmp = (REAL *)malloc(sizeof(REAL) * 2 * F);
+  REAL *xin = (REAL *)malloc(sizeof(REAL) * 2 * F);   /* the vector the final xpay adds: in, or the twisted in for the asymmetric types */
+  memcpy(xin, in, sizeof(REAL) * 2 * F);
+  if (!FN(symmetric_)(matpc)) {
+    /* A - kappa^2 D A^-1 D  (both daggers take this branch in the reference) */
+    FN(orc_wil_dslash)(tmp, gauge, in, q, dagger);
+    FN(orc_wil_dslash)(tmp + F, gauge, in + F, q, dagger);
+    FN(orc_ndeg_twist)(tmp, tmp + F, tmp, tmp + F, dagger, kappa, mu, eps, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, p_out, dagger);
+    FN(orc_wil_dslash)(out + F, gauge, tmp + F, p_out, dagger);
+    FN(orc_ndeg_twist)(xin, xin + F, in, in + F, dagger, kappa, mu, eps, Vh, 0);
+  } else if (!dagger) {
+    FN(orc_wil_dslash)(tmp, gauge, in, q, dagger);
+    FN(orc_wil_dslash)(tmp + F, gauge, in + F, q, dagger);
+    FN(orc_ndeg_twist)(tmp, tmp + F, tmp, tmp + F, dagger, kappa, mu, eps, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, p_out, dagger);
+    FN(orc_wil_dslash)(out + F, gauge, tmp + F, p_out, dagger);
+    FN(orc_ndeg_twist)(out, out + F, out, out + F, dagger, kappa, mu, eps, Vh, 1);
+  } else {
+    FN(orc_ndeg_twist)(tmp, tmp + F, in, in + F, dagger, kappa, mu, eps, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, q, dagger);
+    FN(orc_wil_dslash)(out + F, gauge, tmp + F, q, dagger);
+    FN(orc_ndeg_twist)(tmp, tmp + F, out, out + F, dagger, kappa, mu, eps, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, p_out, dagger);
+    FN(orc_wil_dslash)(out + F, gauge, tmp + F, p_out, dagger);
+  }
+  FN(xpay_)(xin, (REAL)(-kappa * kappa), out, 2 * F);
+  free(tmp); free(xin);
+}
+
+/* out, in: full doublet fields [even doublet | odd doublet] */
+void FN(orc_tm_ndeg_mat)(REAL *out, REAL *const *gauge, const REAL *in, double kappa, double mu, double eps, int dagger)
+{
+  const long Vh = orc_lat.Vh, F = Vh * 24;
+  const REAL *ie = in, *io = in + 2 * F;
+  REAL *oe = out, *oo = out + 2 * F;
+  REAL *tmp = (REAL *)malloc(sizeof(REAL) * 4 * F);
+  FN(orc_wil_dslash)(oo, gauge, ie, 1, dagger);
+  FN(orc_wil_dslash)(oo + F, gauge, ie + F, 1, dagger);
+  FN(orc_wil_dslash)(oe, gauge, io, 0, dagger);
+  FN(orc_wil_dslash)(oe + F, gauge, io + F, 0, dagger);
+  FN(orc_ndeg_twist)(tmp, tmp + F, ie, ie + F, dagger, kappa, mu, eps, Vh, 0);
+  FN(orc_ndeg_twist)(tmp + 2 * F, tmp + 3 * F, io, io + F, dagger, kappa, mu, eps, Vh, 0);
+  FN(xpay_)(tmp + 2 * F, (REAL)(-kappa), oo, 2 * F);
+  FN(xpay_)(tmp, (REAL)(-kappa), oe, 2 * F);
+  free(tmp);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * Twisted-clover (and Wilson-clover) host path: /root/reference/tests/clover_reference.cpp
  *   apply_clover / cloverReference   :19-79   packed clover: per site and chirality 6 real diagonal
  *                                             entries, then the 15 complex strictly-lower-triangular

@@ -37,6 +37,9 @@ class Oracle:
             getattr(L, "orc_tm_dslash" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 4
             getattr(L, "orc_tm_matpc" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 3
             getattr(L, "orc_tm_mat" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 2
+            getattr(L, "orc_tm_ndeg_dslash" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_int] * 3
+            getattr(L, "orc_tm_ndeg_matpc" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_int] * 2
+            getattr(L, "orc_tm_ndeg_mat" + s).argtypes = [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_int]
             getattr(L, "orc_wil_mat" + s).argtypes = [C.c_void_p] * 3 + [C.c_double, C.c_int]
             getattr(L, "orc_wil_matpc" + s).argtypes = [C.c_void_p] * 3 + [C.c_double, C.c_int, C.c_int]
         L.orc_construct_clover.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint]
@@ -99,6 +102,25 @@ class Oracle:
         g = self._cast_gauge(g, inp.dtype)
         out = np.zeros(self.V * 24, dtype=inp.dtype)
         getattr(self.L, "orc_tm_mat" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, mu, flavor, dagger)
+        return out
+
+    # non-degenerate doublet: parity field = [flavour 1 | flavour 2] (2 * Vh * 24 reals), full field = [even doublet | odd doublet]
+    def tm_ndeg_dslash(self, g, inp, kappa, mu, eps, parity, matpc, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(2 * self.Vh * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_tm_ndeg_dslash" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, mu, eps, parity, matpc, dagger)
+        return out
+
+    def tm_ndeg_matpc(self, g, inp, kappa, mu, eps, matpc, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(2 * self.Vh * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_tm_ndeg_matpc" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, mu, eps, matpc, dagger)
+        return out
+
+    def tm_ndeg_mat(self, g, inp, kappa, mu, eps, dagger):
+        g = self._cast_gauge(g, inp.dtype)
+        out = np.zeros(2 * self.V * 24, dtype=inp.dtype)
+        getattr(self.L, "orc_tm_ndeg_mat" + self._suffix(inp))(_ptr(out), _ptrs(g), _ptr(inp), kappa, mu, eps, dagger)
         return out
 
     def wil_mat(self, g, inp, kappa, dagger):
@@ -214,6 +236,10 @@ class Ref:
         L.tmref_tm_dslash.argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 5
         L.tmref_tm_matpc.argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 4
         L.tmref_tm_mat.argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_int] * 3
+        if hasattr(L, "tmref_tm_ndeg_dslash"):
+            L.tmref_tm_ndeg_dslash.argtypes = [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_int] * 4
+            L.tmref_tm_ndeg_matpc.argtypes = [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_int] * 3
+            L.tmref_tm_ndeg_mat.argtypes = [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_int] * 2
         if hasattr(L, "tmref_tmc_dslash"):
             L.tmref_construct_clover.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_uint]
             L.tmref_apply_clover.argtypes = [C.c_void_p] * 3 + [C.c_int] * 2
@@ -247,6 +273,21 @@ class Ref:
     def tm_mat(self, g, inp, kappa, mu, flavor, dagger):
         out = np.zeros(self.V * 24, dtype=inp.dtype)
         self.L.tmref_tm_mat(_ptr(out), _ptrs(g), _ptr(inp.copy()), kappa, mu, flavor, dagger, inp.itemsize)
+        return out
+
+    def tm_ndeg_dslash(self, g, inp, kappa, mu, eps, parity, matpc, dagger):
+        out = np.zeros(2 * self.Vh * 24, dtype=inp.dtype)
+        self.L.tmref_tm_ndeg_dslash(_ptr(out), _ptrs(g), _ptr(inp.copy()), kappa, mu, eps, parity, matpc, dagger, inp.itemsize)
+        return out
+
+    def tm_ndeg_matpc(self, g, inp, kappa, mu, eps, matpc, dagger):
+        out = np.zeros(2 * self.Vh * 24, dtype=inp.dtype)
+        self.L.tmref_tm_ndeg_matpc(_ptr(out), _ptrs(g), _ptr(inp.copy()), kappa, mu, eps, matpc, dagger, inp.itemsize)
+        return out
+
+    def tm_ndeg_mat(self, g, inp, kappa, mu, eps, dagger):
+        out = np.zeros(2 * self.V * 24, dtype=inp.dtype)
+        self.L.tmref_tm_ndeg_mat(_ptr(out), _ptrs(g), _ptr(inp.copy()), kappa, mu, eps, dagger, inp.itemsize)
         return out
 
     def clover(self, norm=0.1, diag=1.0, seed=4242):
