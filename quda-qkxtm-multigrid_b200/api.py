@@ -51,6 +51,7 @@ QUDA_EVEN_PARITY, QUDA_ODD_PARITY = 0, 1
 QUDA_PARITY_SITE_SUBSET, QUDA_FULL_SITE_SUBSET = 1, 2
 QUDA_DEGRAND_ROSSI_GAMMA_BASIS, QUDA_UKQCD_GAMMA_BASIS, QUDA_CHIRAL_GAMMA_BASIS = 0, 1, 2
 QUDA_TWIST_MINUS, QUDA_TWIST_PLUS, QUDA_TWIST_NO = -1, 1, 0
+QUDA_TWIST_NONDEG_DOUBLET, QUDA_TWIST_DEG_DOUBLET = 2, -2
 QUDA_USE_INIT_GUESS_NO, QUDA_USE_INIT_GUESS_YES = 0, 1
 QUDA_COMPUTE_NULL_VECTOR_NO, QUDA_COMPUTE_NULL_VECTOR_YES = 0, 1
 QUDA_BOOLEAN_NO, QUDA_BOOLEAN_YES = 0, 1

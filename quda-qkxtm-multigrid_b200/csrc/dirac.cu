@@ -15,7 +15,7 @@ void Dirac::Mdag(SpinorField &out, const SpinorField &in) const {
 }
 
 void Dirac::MdagM(SpinorField &out, const SpinorField &in) const {
-  std::unique_ptr<SpinorField> t(new SpinorField(in.Vh, in.nparity, in.prec, in.nspin, in.ncolor));
+  std::unique_ptr<SpinorField> t(new SpinorField(in.Vh, in.nparity, in.prec, in.nspin, in.ncolor, 1, in.nflavor));
   M(*t, in);
   Mdag(out, *t);
 }
@@ -25,12 +25,12 @@ void Dirac::create_coarse_op(CoarseOperator &, const Transfer &) const { QB_ERRO
 DiracTM::DiracTM(Lattice *lat_, const GaugeField *gauge_, double kappa_, double mu_, int flavor_, bool pc_, int matpc_, bool dagger_)
     : lat(lat_), gauge(gauge_), gauge_vec(nullptr), kappa(kappa_), mu(mu_), flavor(flavor_), pc(pc_), matpc_type(matpc_) {
   dagger = dagger_;
-  if (flavor != 0 && flavor != 1 && flavor != -1) QB_ERROR("only degenerate twisted mass (flavor +-1) is supported, got %d", flavor);
+  if (flavor != 0 && flavor != 1 && flavor != -1 && flavor != 2) QB_ERROR("twist flavor must be +-1 (degenerate) or 2 (non-degenerate doublet), got %d", flavor);
 }
 
 SpinorField &DiracTM::tmp(std::unique_ptr<SpinorField> &t, const SpinorField &like) const {
-  if (!t || t->prec != like.prec || t->Vh != like.Vh || t->nparity != like.nparity || t->nbatch != like.nbatch)
-    t.reset(new SpinorField(like.Vh, like.nparity, like.prec, 4, 3, like.nbatch));
+  if (!t || t->prec != like.prec || t->Vh != like.Vh || t->nparity != like.nparity || t->nbatch != like.nbatch || t->nflavor != like.nflavor)
+    t.reset(new SpinorField(like.Vh, like.nparity, like.prec, 4, 3, like.nbatch, like.nflavor));
   return *t;
 }
 
@@ -63,6 +63,7 @@ void DiracTM::TwistInv(SpinorField &out, const SpinorField &in) const { apply_tw
 
 // PC hop:  A^-1 D  (no dagger, or asymmetric)   |   D A^-1  (dagger & symmetric: twist on the input)
 void DiracTM::Dslash(SpinorField &out, const SpinorField &in, int parity) const {
+  if (flavor == 2) return NdegDslash(out, in, parity);
   if (clover) {
     // A^-1 D  |  D A^-1 (dagger & symmetric)   with A = C + i a gamma5   (dirac_twisted_clover.cpp:191-227, clover_reference.cpp:234-255)
     SpinorField &t = tmp(tmp2, in);
@@ -85,6 +86,12 @@ void DiracTM::DslashRange(SpinorField &out, const SpinorField &in, int parity, i
 
 // out = x + k (A^-1 D | D A^-1) in     (dirac_twisted_mass.cpp:297-344: dagger alone selects the input twist)
 void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, const SpinorField &x, double k) const {
+  if (flavor == 2) {  // out = x + k (T^-1 D | D T^-1) in
+    SpinorField &t = tmp(tmp2, in);
+    if (!dagger) { WilsonDslash(t, in, parity); NdegTwist(out, t, true, k, &x, 1.0); }
+    else { NdegTwist(t, in, true); WilsonDslashXpay(out, t, parity, x, k); }
+    return;
+  }
   if (clover) {
     SpinorField &t = tmp(tmp2, in);
     if (!dagger) { WilsonDslash(t, in, parity); CloverTwist(out, t, parity, true, &x, k); }
@@ -98,12 +105,13 @@ void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, co
 }
 
 void DiracTM::M(SpinorField &out, const SpinorField &in) const {
+  if (flavor == 2 && in.prec == gauge->prec) return NdegM(out, in);
   if (in.prec != gauge->prec) {
     // vectors live in another precision than the operator (e.g. fp32 smoother vectors, int16 operator):
     // convert, apply in the operator's precision, convert back
-    if (!conv_in || conv_in->prec != gauge->prec || conv_in->Vh != in.Vh || conv_in->nparity != in.nparity) {
-      conv_in.reset(new SpinorField(in.Vh, in.nparity, gauge->prec));
-      conv_out.reset(new SpinorField(in.Vh, in.nparity, gauge->prec));
+    if (!conv_in || conv_in->prec != gauge->prec || conv_in->Vh != in.Vh || conv_in->nparity != in.nparity || conv_in->nflavor != in.nflavor) {
+      conv_in.reset(new SpinorField(in.Vh, in.nparity, gauge->prec, 4, 3, 1, in.nflavor));
+      conv_out.reset(new SpinorField(in.Vh, in.nparity, gauge->prec, 4, 3, 1, in.nflavor));
     }
     copy_spinor(*conv_in, in, rt().compute);
     M(*conv_out, *conv_in);
@@ -169,6 +177,7 @@ void DiracTM::M(SpinorField &out, const SpinorField &in) const {
 //   symmetric :  src = A^-1 (b_p + kappa D A^-1 b_q),  asymmetric:  src = b_p + kappa D A^-1 b_q
 // with p the preconditioned parity and q the other one.  `src` aliases the q-half of x as in the reference.
 void DiracTM::prepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b, SolutionType sol_type) const {
+  if (flavor == 2 && pc && sol_type != SOL_MATPC && sol_type != SOL_MATPCDAG_MATPC) return NdegPrepare(src, sol, x, b);
   if (!pc) {
     if (sol_type == SOL_MATPC || sol_type == SOL_MATPCDAG_MATPC) QB_ERROR("Preconditioned solution requires a preconditioned solve_type");
     b.view_parity(src, 0); src.nparity = b.nparity; src.parity_bytes = b.parity_bytes;
@@ -215,6 +224,7 @@ void DiracTM::prepare(SpinorField &src, SpinorField &sol, SpinorField &x, Spinor
 void DiracTM::reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const {
   if (!pc) return;
   if (sol_type == SOL_MATPC || sol_type == SOL_MATPCDAG_MATPC) return;
+  if (flavor == 2) return NdegReconstruct(x, b);
   const int p = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p;
   SpinorField xp, xq, bq;
   x.view_parity(xp, p); x.view_parity(xq, q);
@@ -233,6 +243,104 @@ void DiracTM::reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol
     apply_hop(*lat, links_for(xp), xq, xp, q, dagger, TwistCoef(), TwistCoef(kappa * ai.p, kappa * ai.q), &bq, ai);
   }
   flops += 1416ll * b.Vh;
+}
+
+// ---- non-degenerate twisted-mass doublet ---------------------------------------------------------------------------------------
+// T = 1 + i a gamma5 tau3 + b tau1 with a = 2 kappa mu, b = -2 kappa epsilon; T^-1 = (1 - i a gamma5 tau3 - b tau1) / (1 + a^2 - b^2);
+// the dagger flips a (wilson_dslash_reference.cpp:412-445).  The two flavours of a field go through ONE batched Wilson hop (links read
+// once for both), the flavour mixing is the site-local apply_ndeg_twist.
+void DiracTM::NdegTwist(SpinorField &out, const SpinorField &in, bool inverse, double c1, const SpinorField *x, double c2) const {
+  double a = 2.0 * kappa * mu, b = -2.0 * kappa * epsilon, d = 1.0;
+  if (inverse) { a = -a; b = -b; d = 1.0 / (1.0 + a * a - b * b); }
+  if (dagger) a = -a;
+  apply_ndeg_twist(out, in, a, b, d, c1, x, c2);
+  flops += 96ll * in.Vh * in.nparity;
+}
+
+// T^-1 D  (no dagger, or asymmetric)   |   D T^-1  (dagger & symmetric)        [tm_ndeg_dslash :461-473]
+void DiracTM::NdegDslash(SpinorField &out, const SpinorField &in, int parity) const {
+  if (in.nflavor != 2 || out.nflavor != 2) QB_ERROR("the non-degenerate doublet operator needs flavour-doublet fields");
+  if (!dagger || !symmetric()) {
+    WilsonDslash(out, in, parity);
+    NdegTwist(out, out, true);
+  } else {
+    SpinorField &t = tmp(tmp2, in);
+    NdegTwist(t, in, true);
+    WilsonDslash(out, t, parity);
+  }
+}
+
+void DiracTM::NdegM(SpinorField &out, const SpinorField &in) const {
+  if (in.nflavor != 2 || out.nflavor != 2) QB_ERROR("the non-degenerate doublet operator needs flavour-doublet fields");
+  if (!pc) {
+    // out_p = T in_p - kappa D in_q        [tm_ndeg_mat :544-587]
+    if (in.nparity != 2 || out.nparity != 2) QB_ERROR("full operator needs full fields");
+    SpinorField oe, oo, ie, io;
+    out.view_parity(oe, 0); out.view_parity(oo, 1);
+    in.view_parity(ie, 0); in.view_parity(io, 1);
+    WilsonDslash(oo, ie, 1);
+    WilsonDslash(oe, io, 0);
+    NdegTwist(oo, io, false, 1.0, &oo, -kappa);
+    NdegTwist(oe, ie, false, 1.0, &oe, -kappa);
+    return;
+  }
+  if (in.nparity != 1 || out.nparity != 1) QB_ERROR("preconditioned operator needs single-parity fields");
+  const double kappa2 = -kappa * kappa;
+  const int p = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p;
+  SpinorField &t = tmp(tmp1, in);
+  if (!symmetric()) {
+    // T in - kappa^2 D T^-1 D in        [tm_ndeg_matpc, asymmetric branch, both daggers]
+    SpinorField &u = tmp(tmp3, in);
+    WilsonDslash(t, in, q);
+    NdegTwist(t, t, true);
+    WilsonDslash(u, t, p);
+    NdegTwist(out, in, false, 1.0, &u, kappa2);
+  } else if (!dagger) {
+    // in - kappa^2 T^-1 D T^-1 D in
+    SpinorField &u = tmp(tmp3, in);
+    WilsonDslash(t, in, q);
+    NdegTwist(t, t, true);
+    WilsonDslash(u, t, p);
+    NdegTwist(out, u, true, kappa2, &in, 1.0);
+  } else {
+    // in - kappa^2 D T^-1 D T^-1 in   (T daggered)
+    SpinorField &u = tmp(tmp3, in);
+    NdegTwist(t, in, true);
+    WilsonDslash(u, t, q);
+    NdegTwist(t, u, true);
+    WilsonDslashXpay(out, t, p, in, kappa2);
+  }
+}
+
+// symmetric: src = T^-1 (b_p + kappa D T^-1 b_q);  asymmetric: src = b_p + kappa D T^-1 b_q     (as the degenerate prepare above)
+void DiracTM::NdegPrepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b) const {
+  if (x.nparity != 2 || b.nparity != 2 || x.nflavor != 2 || b.nflavor != 2) QB_ERROR("prepare: full-lattice doublet source and solution required");
+  if (b.prec != gauge->prec) QB_ERROR("the doublet operator needs the solver vectors in the operator's precision");
+  const int p = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p;
+  SpinorField bp, bq;
+  b.view_parity(bp, p); b.view_parity(bq, q);
+  x.view_parity(src, q);
+  x.view_parity(sol, p);
+  SpinorField &t = tmp(tmp1, bq);
+  NdegTwist(t, bq, true);
+  if (symmetric()) {
+    SpinorField &u = tmp(tmp3, bq);
+    WilsonDslashXpay(u, t, p, bp, kappa);
+    NdegTwist(src, u, true);
+  } else {
+    WilsonDslashXpay(src, t, p, bp, kappa);
+  }
+}
+
+// x_q = T^-1 (b_q + kappa D x_p)
+void DiracTM::NdegReconstruct(SpinorField &x, const SpinorField &b) const {
+  const int p = (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1, q = 1 - p;
+  SpinorField xp, xq, bq;
+  x.view_parity(xp, p); x.view_parity(xq, q);
+  b.view_parity(bq, q);
+  SpinorField &t = tmp(tmp1, xp);
+  WilsonDslashXpay(t, xp, q, bq, kappa);
+  NdegTwist(xq, t, true);
 }
 
 }  // namespace qb

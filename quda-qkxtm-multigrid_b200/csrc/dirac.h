@@ -51,7 +51,8 @@ class DiracTM : public Dirac {
   const GaugeField *gauge;      // links in the operator's working precision
   const GaugeField *gauge_vec;  // links in the precision of the solver vectors (prepare / reconstruct when they differ), may be null
   double kappa, mu;
-  int flavor;   // +-1 twisted mass, 0 = plain Wilson
+  double epsilon = 0.0;   // flavour splitting of the non-degenerate doublet
+  int flavor;   // +-1 twisted mass, 0 = plain Wilson, 2 = non-degenerate doublet (fields with nflavor = 2)
   CloverSet *clover = nullptr;  // set: Wilson-clover / twisted-clover, the site-local term is C + i a gamma5 (clover.h)
   bool pc;
   int matpc_type;
@@ -62,8 +63,9 @@ class DiracTM : public Dirac {
   bool is_pc() const override { return pc; }
   int matpc() const override { return matpc_type; }
   Prec precision() const override { return gauge->prec; }
-  SpinorField *new_field(Prec prec) const override { return new SpinorField(lat->geom.Vh, pc ? 1 : 2, prec); }
-  SpinorField *new_parity_field(Prec prec) const override { return new SpinorField(lat->geom.Vh, 1, prec); }
+  int nflavor() const { return flavor == 2 ? 2 : 1; }
+  SpinorField *new_field(Prec prec) const override { return new SpinorField(lat->geom.Vh, pc ? 1 : 2, prec, 4, 3, 1, nflavor()); }
+  SpinorField *new_parity_field(Prec prec) const override { return new SpinorField(lat->geom.Vh, 1, prec, 4, 3, 1, nflavor()); }
 
   bool symmetric() const { return matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_ODD_ODD; }
   double twist_a() const { return 2.0 * kappa * mu * flavor; }   // A = 1 + i a gamma5
@@ -92,6 +94,12 @@ class DiracTM : public Dirac {
   void create_coarse_op(CoarseOperator &coarse, const Transfer &T) const override;
 
  private:
+  // non-degenerate doublet (wilson_dslash_reference.cpp:412-587; dirac_twisted_mass.cpp handles it through the same class)
+  void NdegTwist(SpinorField &out, const SpinorField &in, bool inverse, double c1 = 1.0, const SpinorField *x = nullptr, double c2 = 0.0) const;
+  void NdegDslash(SpinorField &out, const SpinorField &in, int parity) const;
+  void NdegM(SpinorField &out, const SpinorField &in) const;
+  void NdegPrepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b) const;
+  void NdegReconstruct(SpinorField &x, const SpinorField &b) const;
   SpinorField &tmp(std::unique_ptr<SpinorField> &t, const SpinorField &like) const;
   const GaugeField &links_for(const SpinorField &f) const;
 };

@@ -56,6 +56,9 @@ void apply_hop_range(Lattice &lat, const GaugeField &gauge, SpinorField &out, co
 
 void face_index_map(const Lattice &lat, int mu, int face_num, int parity, int *h_out);
 
+// non-degenerate doublet: out = c1 * d (1 + i a gamma5 tau3 + b tau1) in + c2 * x   (x may be null or alias out)
+void apply_ndeg_twist(SpinorField &out, const SpinorField &in, double a, double b, double d, double c1, const SpinorField *x, double c2);
+
 // out = (p + i q gamma5) in on every site of the field
 void apply_twist_field(SpinorField &out, const SpinorField &in, TwistCoef c);
 

@@ -142,19 +142,24 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   const int block = lat.block_size > 0 ? lat.block_size : (Store::prec == PREC_DOUBLE ? 64 : 128);
   const bool partitioned = g.part[0] || g.part[1] || g.part[2] || g.part[3];
   if (out.nbatch != in.nbatch || (x && x->nbatch != out.nbatch)) QB_ERROR("apply_hop: batch sizes differ (out %d, in %d)", out.nbatch, in.nbatch);
-  if (out.nbatch > 1 && partitioned) QB_ERROR("apply_hop: batched fields are supported on unpartitioned lattices only");
+  if (out.nflavor != in.nflavor || (x && x->nflavor != out.nflavor)) QB_ERROR("apply_hop: flavour counts differ");
+  // members handled by one launch: the fields of a batch, or the two flavours of a doublet (which sit inside the parity block)
+  const int nmember = out.nflavor == 2 ? 2 : out.nbatch;
+  const size_t st_in = out.nflavor == 2 ? in.flavor_bytes() : in.batch_bytes, st_out = out.nflavor == 2 ? out.flavor_bytes() : out.batch_bytes;
+  const size_t st_x = x ? (out.nflavor == 2 ? x->flavor_bytes() : x->batch_bytes) : 0;
+  if (nmember > 1 && partitioned) QB_ERROR("apply_hop: batched / flavour-doublet fields are supported on unpartitioned lattices only");
   if (!partitioned) {
     p.site_begin = range_begin; p.site_count = range_count < 0 ? g.Vh : range_count; p.site_list = nullptr;
     cudaStream_t st = range_stream ? range_stream : r.compute;
-    if (out.nbatch > 1) {
+    if (nmember > 1) {
       // members in groups of DSLASH_BATCH_MAX: one launch per group, links read from HBM once per group
-      for (int first = 0; first < out.nbatch; first += 12) {
+      for (int first = 0; first < nmember; first += 12) {
         DslashParam pb = p;
-        pb.nbatch = std::min(12, out.nbatch - first);
-        pb.batch_in = (long)in.batch_bytes; pb.batch_out = (long)out.batch_bytes; pb.batch_x = x ? (long)x->batch_bytes : 0;
-        pb.in = (const char *)in.v + (size_t)first * in.batch_bytes;
-        pb.out = (char *)out.v + (size_t)first * out.batch_bytes;
-        pb.x = x ? (const char *)x->v + (size_t)first * x->batch_bytes : nullptr;
+        pb.nbatch = std::min(12, nmember - first);
+        pb.batch_in = (long)st_in; pb.batch_out = (long)st_out; pb.batch_x = (long)st_x;
+        pb.in = (const char *)in.v + (size_t)first * st_in;
+        pb.out = (char *)out.v + (size_t)first * st_out;
+        pb.x = x ? (const char *)x->v + (size_t)first * st_x : nullptr;
         if (pb.nbatch == 1) { pb.nbatch = 0; launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, false, block, st); }
         else launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, false, block, st);
       }
@@ -267,6 +272,49 @@ void face_index_map(const Lattice &lat, int mu, int face_num, int parity, int *h
   QB_CUDA(cudaMemcpyAsync(h_out, d, sizeof(int) * n, cudaMemcpyDeviceToHost, rt().compute));
   QB_CUDA(cudaStreamSynchronize(rt().compute));
   QB_CUDA(cudaFree(d));
+}
+
+// out = c1 * d (1 + i a gamma5 tau3 + b tau1) in + c2 * x on a flavour-doublet field (x may be null, may alias out)
+template <typename Store>
+__global__ void __launch_bounds__(128) ndeg_twist_kernel(void *out, const void *in, const void *x, long Vh, long nsites, size_t parity_bytes, size_t flavor_bytes,
+                                                         double a_, double b_, double d_, double c1_, double c2_) {
+  typedef typename Store::real real;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsites) return;
+  const int parity = (int)(t / Vh);
+  const long cb = t - (long)parity * Vh;
+  const size_t off = parity_bytes * parity;
+  cplx<real> f1[12], f2[12], o1[12], o2[12];
+  Store::template load<12, false>(f1, (const char *)in + off, nullptr, Vh, cb);
+  Store::template load<12, false>(f2, (const char *)in + off + flavor_bytes, nullptr, Vh, cb);
+  const real a = (real)a_, b = (real)b_, s1 = (real)(c1_ * d_);
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    const real a5 = k < 6 ? a : -a;   // gamma5 = diag(1, 1, -1, -1) in the internal chiral basis
+    o1[k] = cplx<real>(s1 * (f1[k].re - a5 * f1[k].im + b * f2[k].re), s1 * (f1[k].im + a5 * f1[k].re + b * f2[k].im));
+    o2[k] = cplx<real>(s1 * (f2[k].re + a5 * f2[k].im + b * f1[k].re), s1 * (f2[k].im - a5 * f2[k].re + b * f1[k].im));
+  }
+  if (x) {
+    const real c2 = (real)c2_;
+    cplx<real> x1[12], x2[12];
+    Store::template load<12, false>(x1, (const char *)x + off, nullptr, Vh, cb);
+    Store::template load<12, false>(x2, (const char *)x + off + flavor_bytes, nullptr, Vh, cb);
+#pragma unroll
+    for (int k = 0; k < 12; k++) { o1[k].re += c2 * x1[k].re; o1[k].im += c2 * x1[k].im; o2[k].re += c2 * x2[k].re; o2[k].im += c2 * x2[k].im; }
+  }
+  Store::template store<12>((char *)out + off, nullptr, Vh, cb, o1);
+  Store::template store<12>((char *)out + off + flavor_bytes, nullptr, Vh, cb, o2);
+}
+
+void apply_ndeg_twist(SpinorField &out, const SpinorField &in, double a, double b, double d, double c1, const SpinorField *x, double c2) {
+  if (in.nflavor != 2 || out.nflavor != 2 || (x && x->nflavor != 2)) QB_ERROR("apply_ndeg_twist needs flavour-doublet fields");
+  if (out.prec != in.prec || out.Vh != in.Vh || out.nparity != in.nparity || (x && (x->prec != in.prec || x->nparity != in.nparity))) QB_ERROR("apply_ndeg_twist: field mismatch");
+  const long n = in.Vh * in.nparity;
+  cudaStream_t s = rt().compute;
+  if (in.prec == PREC_DOUBLE) ndeg_twist_kernel<StoreD><<<div_up(n, 128), 128, 0, s>>>(out.v, in.v, x ? x->v : nullptr, in.Vh, n, in.parity_bytes, in.flavor_bytes(), a, b, d, c1, c2);
+  else if (in.prec == PREC_SINGLE) ndeg_twist_kernel<StoreS><<<div_up(n, 128), 128, 0, s>>>(out.v, in.v, x ? x->v : nullptr, in.Vh, n, in.parity_bytes, in.flavor_bytes(), a, b, d, c1, c2);
+  else QB_ERROR("apply_ndeg_twist: fp32 / fp64 fields only");
+  QB_CHECK_LAUNCH();
 }
 
 void apply_twist_field(SpinorField &out, const SpinorField &in, TwistCoef c) {

@@ -4,12 +4,14 @@
 namespace qb {
 
 // ---------------------------------------------------------------------------------------------
-SpinorField::SpinorField(long Vh_, int nparity_, Prec prec_, int nspin_, int ncolor_, int nbatch_)
-    : prec(prec_), nparity(nparity_), ncomplex(nspin_ * ncolor_), nspin(nspin_), ncolor(ncolor_), Vh(Vh_), nbatch(nbatch_) {
+SpinorField::SpinorField(long Vh_, int nparity_, Prec prec_, int nspin_, int ncolor_, int nbatch_, int nflavor_)
+    : prec(prec_), nparity(nparity_), ncomplex(nspin_ * ncolor_), nspin(nspin_), ncolor(ncolor_), Vh(Vh_), nbatch(nbatch_), nflavor(nflavor_) {
   const int sb = prec == PREC_HALF ? 2 : (int)prec;
   if ((ncomplex * 2 * sb) % 16) QB_ERROR("site size %d B is not a multiple of the 16-B plane", ncomplex * 2 * sb);
   if (nbatch < 1 || (nbatch > 1 && prec == PREC_HALF)) QB_ERROR("batched fields are fp32 / fp64 only");
-  parity_bytes = (size_t)Vh * ncomplex * 2 * sb;
+  if (nflavor != 1 && nflavor != 2) QB_ERROR("nflavor must be 1 or 2");
+  if (nflavor == 2 && (prec == PREC_HALF || nbatch > 1)) QB_ERROR("flavour-doublet fields are fp32 / fp64 and not batched");
+  parity_bytes = (size_t)Vh * ncomplex * 2 * sb * nflavor;
   batch_bytes = parity_bytes * nparity;
   v = pool_malloc(batch_bytes * nbatch);
   if (prec == PREC_HALF) norm = (float *)pool_malloc(sizeof(float) * Vh * nparity);
@@ -27,6 +29,7 @@ void SpinorField::view_parity(SpinorField &dst, int p) const {
   dst.prec = prec; dst.nparity = 1; dst.ncomplex = ncomplex; dst.nspin = nspin; dst.ncolor = ncolor; dst.Vh = Vh;
   dst.v = parity_ptr(p); dst.norm = parity_norm(p); dst.parity_bytes = parity_bytes; dst.owner = false;
   dst.nbatch = nbatch; dst.batch_bytes = batch_bytes;   // a parity view of a batch is a batch of parity views
+  dst.nflavor = nflavor;
 }
 
 void SpinorField::member(SpinorField &dst, int c) const {
@@ -333,14 +336,14 @@ void free_staging() {
 template <typename Host>
 static void import_spinor_host(SpinorField &f, const void *h, HostBasis basis, HostSpinorOrder order, cudaStream_t s) {
   if (f.ncomplex != 12) QB_ERROR("host import only for nSpin=4, nColor=3 fields");
-  const long nsites = f.Vh * f.nparity;
+  const long nsites = f.Vh * f.nparity * f.nflavor;   // doublet: 2 * nparity blocks of Vh sites, see export_spinor_host
   const size_t hb = sizeof(Host) * nsites * 24;
   Host *stage = (Host *)staging(hb);
   QB_CUDA(cudaMemcpyAsync(stage, h, hb, cudaMemcpyHostToDevice, s));
   const int bs = 128, nb = div_up(nsites, bs);
-  if (f.prec == PREC_DOUBLE) import_spinor_kernel<StoreD, Host><<<nb, bs, 0, s>>>(f.v, f.norm, stage, f.Vh, nsites, f.parity_bytes, basis, order);
-  else if (f.prec == PREC_SINGLE) import_spinor_kernel<StoreS, Host><<<nb, bs, 0, s>>>(f.v, f.norm, stage, f.Vh, nsites, f.parity_bytes, basis, order);
-  else import_spinor_kernel<StoreH, Host><<<nb, bs, 0, s>>>(f.v, f.norm, stage, f.Vh, nsites, f.parity_bytes, basis, order);
+  if (f.prec == PREC_DOUBLE) import_spinor_kernel<StoreD, Host><<<nb, bs, 0, s>>>(f.v, f.norm, stage, f.Vh, nsites, f.flavor_bytes(), basis, order);
+  else if (f.prec == PREC_SINGLE) import_spinor_kernel<StoreS, Host><<<nb, bs, 0, s>>>(f.v, f.norm, stage, f.Vh, nsites, f.flavor_bytes(), basis, order);
+  else import_spinor_kernel<StoreH, Host><<<nb, bs, 0, s>>>(f.v, f.norm, stage, f.Vh, nsites, f.flavor_bytes(), basis, order);
   QB_CHECK_LAUNCH();
 }
 
@@ -353,13 +356,14 @@ void import_spinor(SpinorField &f, const void *h, Prec host_prec, HostBasis basi
 template <typename Host>
 static void export_spinor_host(void *h, const SpinorField &f, HostBasis basis, HostSpinorOrder order, cudaStream_t s) {
   if (f.ncomplex != 12) QB_ERROR("host export only for nSpin=4, nColor=3 fields");
-  const long nsites = f.Vh * f.nparity;
+  // a flavour doublet is 2 * nparity consecutive blocks of Vh sites: [parity][flavour][site] on the host and on the device
+  const long nsites = f.Vh * f.nparity * f.nflavor;
   const size_t hb = sizeof(Host) * nsites * 24;
   Host *stage = (Host *)staging(hb);
   const int bs = 128, nb = div_up(nsites, bs);
-  if (f.prec == PREC_DOUBLE) export_spinor_kernel<StoreD, Host><<<nb, bs, 0, s>>>(stage, f.v, f.norm, f.Vh, nsites, f.parity_bytes, basis, order);
-  else if (f.prec == PREC_SINGLE) export_spinor_kernel<StoreS, Host><<<nb, bs, 0, s>>>(stage, f.v, f.norm, f.Vh, nsites, f.parity_bytes, basis, order);
-  else export_spinor_kernel<StoreH, Host><<<nb, bs, 0, s>>>(stage, f.v, f.norm, f.Vh, nsites, f.parity_bytes, basis, order);
+  if (f.prec == PREC_DOUBLE) export_spinor_kernel<StoreD, Host><<<nb, bs, 0, s>>>(stage, f.v, f.norm, f.Vh, nsites, f.flavor_bytes(), basis, order);
+  else if (f.prec == PREC_SINGLE) export_spinor_kernel<StoreS, Host><<<nb, bs, 0, s>>>(stage, f.v, f.norm, f.Vh, nsites, f.flavor_bytes(), basis, order);
+  else export_spinor_kernel<StoreH, Host><<<nb, bs, 0, s>>>(stage, f.v, f.norm, f.Vh, nsites, f.flavor_bytes(), basis, order);
   QB_CHECK_LAUNCH();
   QB_CUDA(cudaMemcpyAsync(h, stage, hb, cudaMemcpyDeviceToHost, s));
   QB_CUDA(cudaStreamSynchronize(s));
@@ -457,7 +461,7 @@ __global__ void convert_spinor_kernel(void *dst, float *dnorm, const void *src, 
 }
 
 void copy_spinor(SpinorField &dst, const SpinorField &src, cudaStream_t s) {
-  if (dst.Vh != src.Vh || dst.nparity != src.nparity || dst.ncomplex != src.ncomplex) QB_ERROR("copy_spinor: geometry mismatch");
+  if (dst.Vh != src.Vh || dst.nparity != src.nparity || dst.ncomplex != src.ncomplex || dst.nflavor != src.nflavor) QB_ERROR("copy_spinor: geometry mismatch");
   if (dst.v == src.v) return;
   if (dst.prec == src.prec) {
     QB_CUDA(cudaMemcpyAsync(dst.v, src.v, src.bytes(), cudaMemcpyDeviceToDevice, s));
@@ -465,9 +469,9 @@ void copy_spinor(SpinorField &dst, const SpinorField &src, cudaStream_t s) {
     return;
   }
   if (src.ncomplex != 12) QB_ERROR("precision-changing copy only for fine fields");
-  const long nsites = src.Vh * src.nparity;
+  const long nsites = src.Vh * src.nparity * src.nflavor;
   const int bs = 128, nb = div_up(nsites, bs);
-#define CV(D, S) convert_spinor_kernel<D, S><<<nb, bs, 0, s>>>(dst.v, dst.norm, src.v, src.norm, src.Vh, nsites, dst.parity_bytes, src.parity_bytes)
+#define CV(D, S) convert_spinor_kernel<D, S><<<nb, bs, 0, s>>>(dst.v, dst.norm, src.v, src.norm, src.Vh, nsites, dst.flavor_bytes(), src.flavor_bytes())
   if (dst.prec == PREC_DOUBLE && src.prec == PREC_SINGLE) CV(StoreD, StoreS);
   else if (dst.prec == PREC_DOUBLE && src.prec == PREC_HALF) CV(StoreD, StoreH);
   else if (dst.prec == PREC_SINGLE && src.prec == PREC_DOUBLE) CV(StoreS, StoreD);

@@ -43,16 +43,21 @@ struct SpinorField {
   // members and the links are fetched from HBM once.  BLAS works on member views (member()).
   int nbatch = 1;
   size_t batch_bytes = 0;
+  // flavour doublet (non-degenerate twisted mass): nflavor = 2 flavours side by side INSIDE every parity block,
+  // [parity][flavour][plane][site] (the host layout of the reference's doublet fields); parity_bytes covers both flavours, so BLAS
+  // sees one flat vector and parity views stay contiguous; the hop kernel treats the flavours as a batch of two.
+  int nflavor = 1;
+  size_t flavor_bytes() const { return parity_bytes / nflavor; }
 
   SpinorField() {}
-  SpinorField(long Vh, int nparity, Prec prec, int nspin = 4, int ncolor = 3, int nbatch = 1);
+  SpinorField(long Vh, int nparity, Prec prec, int nspin = 4, int ncolor = 3, int nbatch = 1, int nflavor = 1);
   ~SpinorField();
   SpinorField(const SpinorField &) = delete;
   SpinorField &operator=(const SpinorField &) = delete;
 
   int planes() const { return ncomplex * 2 * (int)(prec == PREC_HALF ? 2 : prec) / 16; }
   size_t bytes() const { return parity_bytes * nparity; }
-  long reals() const { return (long)Vh * ncomplex * 2 * nparity; }
+  long reals() const { return (long)Vh * ncomplex * 2 * nparity * nflavor; }
   void *parity_ptr(int p) const { return (char *)v + parity_bytes * (nparity == 2 ? p : 0); }
   float *parity_norm(int p) const { return norm ? norm + Vh * (nparity == 2 ? p : 0) : nullptr; }
   // non-owning view of one parity of a full field (or the field itself if single parity)

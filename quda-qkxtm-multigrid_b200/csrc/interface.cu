@@ -65,8 +65,12 @@ void check_invert_param_operator(const QudaInvertParam *p) {
     QB_ERROR("Clover field not allocated (call loadCloverQuda)");
   if (p->dslash_type == QUDA_TWISTED_MASS_DSLASH || p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH) {
     if (p->mu == INVALID_DOUBLE) QB_ERROR("Parameter mu undefined");
-    if (p->twist_flavor != QUDA_TWIST_PLUS && p->twist_flavor != QUDA_TWIST_MINUS)
-      QB_ERROR("Twist flavor not set %d (only the degenerate +-1 flavours are supported)", (int)p->twist_flavor);
+    if (p->twist_flavor != QUDA_TWIST_PLUS && p->twist_flavor != QUDA_TWIST_MINUS && p->twist_flavor != QUDA_TWIST_NONDEG_DOUBLET)
+      QB_ERROR("Twist flavor not set %d (QUDA_TWIST_PLUS / MINUS or QUDA_TWIST_NONDEG_DOUBLET)", (int)p->twist_flavor);
+    if (p->twist_flavor == QUDA_TWIST_NONDEG_DOUBLET) {
+      if (p->dslash_type != QUDA_TWISTED_MASS_DSLASH) QB_ERROR("The non-degenerate doublet is implemented for QUDA_TWISTED_MASS_DSLASH only");
+      if (p->epsilon == INVALID_DOUBLE) QB_ERROR("Parameter epsilon undefined");
+    }
   }
   if (p->matpc_type == QUDA_MATPC_INVALID) QB_ERROR("Parameter matpc_type undefined");
   if (p->dagger == QUDA_DAG_INVALID) QB_ERROR("Parameter dagger undefined");
@@ -86,22 +90,27 @@ DiracTM *make_dirac(const QudaInvertParam *p, bool pc, const GaugeField *gauge, 
   const int flavor = twisted ? (int)p->twist_flavor : 0;
   const double mu = twisted ? p->mu * mu_scale : 0.0;
   DiracTM *d = new DiracTM(&G.lat, gauge, p->kappa * kappa_scale, mu, flavor, pc, (int)p->matpc_type, p->dagger == QUDA_DAG_YES);
+  if (flavor == 2) d->epsilon = p->epsilon;
   if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH) d->clover = &G.clover;
   return d;
 }
 
 // small pool of resident work fields so that dslashQuda / MatQuda do not cudaMalloc per call
 std::map<std::pair<int, int>, std::vector<SpinorField *>> pool;
-SpinorField *pool_get(int nparity, Prec prec) {
-  auto &v = pool[{nparity, (int)prec}];
+SpinorField *pool_get(int nparity, Prec prec, int nflavor = 1) {
+  auto &v = pool[{nparity + 16 * nflavor, (int)prec}];
   if (!v.empty() && v.back()->Vh == G.lat.geom.Vh) {
     SpinorField *f = v.back();
     v.pop_back();
     return f;
   }
-  return new SpinorField(G.lat.geom.Vh, nparity, prec);
+  return new SpinorField(G.lat.geom.Vh, nparity, prec, 4, 3, 1, nflavor);
 }
-void pool_put(SpinorField *f) { pool[{f->nparity, (int)f->prec}].push_back(f); }
+void pool_put(SpinorField *f) { pool[{f->nparity + 16 * f->nflavor, (int)f->prec}].push_back(f); }
+// flavours per field of the operator selected by the parameters (2: non-degenerate twisted-mass doublet, host fields [parity][flavour][site])
+int nflavor_of(const QudaInvertParam *p) {
+  return (p->dslash_type == QUDA_TWISTED_MASS_DSLASH && p->twist_flavor == QUDA_TWIST_NONDEG_DOUBLET) ? 2 : 1;
+}
 void pool_clear() {
   for (auto &kv : pool)
     for (auto *f : kv.second) delete f;
@@ -503,7 +512,7 @@ void pipe_cleanup_c() {
 static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaParity parity, SpinorField &in, SpinorField &out) {
   const Geom &g = G.lat.geom;
   if (g.part[0] || g.part[1] || g.part[2] || g.part[3]) return false;
-  if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH) return false;  // two kernels per hop: plain path
+  if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH || in.nflavor != 1) return false;  // two kernels per hop: plain path
   if (p->input_location != QUDA_CPU_FIELD_LOCATION || p->output_location != QUDA_CPU_FIELD_LOCATION) return false;
   const int T = g.X[3];
   int nchunk = 0;
@@ -561,7 +570,7 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
 void dslashQuda(void *h_out, void *h_in, QudaInvertParam *p, QudaParity parity) {
   require_gauge();
   const Prec prec = to_prec(p->cuda_prec, "cuda_prec");
-  SpinorField *in = pool_get(1, prec), *out = pool_get(1, prec);
+  SpinorField *in = pool_get(1, prec, nflavor_of(p)), *out = pool_get(1, prec, nflavor_of(p));
   if (parity != QUDA_EVEN_PARITY && parity != QUDA_ODD_PARITY) QB_ERROR("invalid parity %d", (int)parity);
   if (dslash_pipelined(h_out, h_in, p, parity, *in, *out)) {
     pool_put(in); pool_put(out);
@@ -578,7 +587,7 @@ void MatQuda(void *h_out, void *h_in, QudaInvertParam *p) {
   require_gauge();
   const bool pc = (p->solution_type == QUDA_MATPC_SOLUTION || p->solution_type == QUDA_MATPCDAG_MATPC_SOLUTION);
   const Prec prec = to_prec(p->cuda_prec, "cuda_prec");
-  SpinorField *in = pool_get(pc ? 1 : 2, prec), *out = pool_get(pc ? 1 : 2, prec);
+  SpinorField *in = pool_get(pc ? 1 : 2, prec, nflavor_of(p)), *out = pool_get(pc ? 1 : 2, prec, nflavor_of(p));
   load_host_spinor(*in, h_in, p);
   mat_fields(*out, *in, p, false);
   save_host_spinor(h_out, *out, p);
@@ -590,7 +599,7 @@ void MatDagMatQuda(void *h_out, void *h_in, QudaInvertParam *p) {
   require_gauge();
   const bool pc = (p->solution_type == QUDA_MATPC_SOLUTION || p->solution_type == QUDA_MATPCDAG_MATPC_SOLUTION);
   const Prec prec = to_prec(p->cuda_prec, "cuda_prec");
-  SpinorField *in = pool_get(pc ? 1 : 2, prec), *out = pool_get(pc ? 1 : 2, prec);
+  SpinorField *in = pool_get(pc ? 1 : 2, prec, nflavor_of(p)), *out = pool_get(pc ? 1 : 2, prec, nflavor_of(p));
   load_host_spinor(*in, h_in, p);
   mat_fields(*out, *in, p, true);
   save_host_spinor(h_out, *out, p);
@@ -809,7 +818,7 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
   const Prec prec = sp.precision;
   const Prec prec_vec_sloppy = blas_prec(sp.precision_sloppy);
   if (prec == PREC_HALF) QB_ERROR("cuda_prec must be single or double for a solve");
-  param->spinorGiB = (double)G.lat.geom.Vh * 24 * (pc_solve ? 1 : 2) * (int)prec * (param->preserve_source == QUDA_PRESERVE_SOURCE_NO ? 7 : 9) / (double)(1 << 30);
+  param->spinorGiB = (double)G.lat.geom.Vh * nflavor_of(param) * 24 * (pc_solve ? 1 : 2) * (int)prec * (param->preserve_source == QUDA_PRESERVE_SOURCE_NO ? 7 : 9) / (double)(1 << 30);
 
   // createDirac (interface_quda.cpp:1386-1410): precise, sloppy and preconditioner operators
   std::unique_ptr<DiracTM> d(make_dirac(param, pc_solve, pick_gauge(prec)));
@@ -818,8 +827,10 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
   if (dS->gauge->prec != prec_vec_sloppy) dS->gauge_vec = pick_gauge(prec_vec_sloppy);
   if (dP->gauge->prec != prec_vec_sloppy) dP->gauge_vec = pick_gauge(prec_vec_sloppy);
 
-  std::unique_ptr<SpinorField> b(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec));
-  std::unique_ptr<SpinorField> x(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec));
+  const int nfl = nflavor_of(param);
+  if (nfl == 2 && param->inv_type_precondition == QUDA_MG_INVERTER) QB_ERROR("Multigrid for the non-degenerate doublet is not implemented");
+  std::unique_ptr<SpinorField> b(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec, 4, 3, 1, nfl));
+  std::unique_ptr<SpinorField> x(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec, 4, 3, 1, nfl));
   load_host_spinor(*b, hp_b, param);
   if (param->use_init_guess == QUDA_USE_INIT_GUESS_YES) load_host_spinor(*x, hp_x, param);
   else blas::zero(*x);
@@ -861,7 +872,7 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
   }
   std::unique_ptr<SpinorField> tmp_in;
   if (mat_solution && !direct_solve) {  // normal equations: b' = A^dag b
-    tmp_in.reset(new SpinorField(in.Vh, in.nparity, in.prec));
+    tmp_in.reset(new SpinorField(in.Vh, in.nparity, in.prec, 4, 3, 1, in.nflavor));
     blas::copy(*tmp_in, in);
     d->Mdag(in, *tmp_in);
   }
@@ -987,6 +998,7 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   if (!mgp || !mgp->invert_param) QB_ERROR("newMultigridQuda: null parameter struct");
   QudaInvertParam *ip = mgp->invert_param;
   check_invert_param_operator(ip);
+  if (nflavor_of(ip) == 2) QB_ERROR("Multigrid for the non-degenerate doublet is not implemented");
   if (mgp->n_level == INVALID_INT) QB_ERROR("Parameter n_level undefined");
   if (mgp->n_level < 2 || mgp->n_level > QUDA_MAX_MG_LEVEL) QB_ERROR("Maximum number of multigrid levels is %d (and at least 2), requested %d", QUDA_MAX_MG_LEVEL, mgp->n_level);
   if (ip->solve_type != QUDA_DIRECT_SOLVE) QB_ERROR("Outer MG solver can only use QUDA_DIRECT_SOLVE at present");

@@ -8,10 +8,10 @@ namespace qb {
 
 using blas::Complex;
 
-SpinorField *new_like(const SpinorField &a, Prec prec) { return new SpinorField(a.Vh, a.nparity, prec, a.nspin, a.ncolor); }
+SpinorField *new_like(const SpinorField &a, Prec prec) { return new SpinorField(a.Vh, a.nparity, prec, a.nspin, a.ncolor, 1, a.nflavor); }
 
 static void ensure(std::unique_ptr<SpinorField> &f, const SpinorField &like, Prec prec) {
-  if (!f || f->Vh != like.Vh || f->nparity != like.nparity || f->ncomplex != like.ncomplex || f->prec != prec) f.reset(new_like(like, prec));
+  if (!f || f->Vh != like.Vh || f->nparity != like.nparity || f->ncomplex != like.ncomplex || f->nflavor != like.nflavor || f->prec != prec) f.reset(new_like(like, prec));
 }
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
