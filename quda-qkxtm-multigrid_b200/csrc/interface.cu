@@ -746,12 +746,13 @@ namespace {
 
 InverterType to_inverter(QudaInverterType t) {
   switch (t) {
+    case QUDA_CG_INVERTER: return INV_CG;
     case QUDA_GCR_INVERTER: return INV_GCR;
     case QUDA_MR_INVERTER: return INV_MR;
     case QUDA_BICGSTAB_INVERTER: return INV_BICGSTAB;
     case QUDA_MG_INVERTER: return INV_MG;
     case QUDA_INVALID_INVERTER: return INV_NONE;
-    default: QB_ERROR("Invalid solver type %d (this build provides GCR, MR, BiCGStab and the MG preconditioner)", (int)t);
+    default: QB_ERROR("Invalid solver type %d (this build provides CG, GCR, MR, BiCGStab and the MG preconditioner)", (int)t);
   }
 }
 

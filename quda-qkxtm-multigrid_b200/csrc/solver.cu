@@ -21,8 +21,82 @@ Solver *Solver::create(SolverParam &param, const DiracMatrix &mat, const DiracMa
     case INV_GCR: return new GCR(mat, matSloppy, matPrecon, param, K);
     case INV_MR: return new MR(mat, matSloppy, param);
     case INV_BICGSTAB: return new BiCGStab(mat, matSloppy, param);
-    default: QB_ERROR("Invalid solver type %d (this build provides GCR, MR and BiCGStab)", (int)param.inv_type);
+    case INV_CG: return new CG(mat, matSloppy, param);
+    default: QB_ERROR("Invalid solver type %d (this build provides CG, GCR, MR and BiCGStab)", (int)param.inv_type);
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// CG (lib/inv_cg_quda.cpp:37-330): iteration in the sloppy precision, solution accumulated in the outer
+// precision; a reliable update (true residual from the outer-precision operator, sloppy accumulator folded
+// into y) whenever the iterated residual has dropped by `delta` relative to its maximum since the last
+// update (:178-240).
+// -------------------------------------------------------------------------------------------------
+void CG::operator()(SpinorField &x, SpinorField &b) {
+  const Prec px = x.prec, ps = blas_prec(param.precision_sloppy);
+  const double t0 = now_s();
+  ensure(r, x, px); ensure(y, x, px); ensure(p, x, ps); ensure(Ap, x, ps);
+  SpinorField *rs = r.get(), *xs = &x;
+  const bool mixed = px != ps;
+  if (mixed) { ensure(rS, x, ps); ensure(xS, x, ps); ensure(tmp, x, px); rs = rS.get(); xs = xS.get(); }
+  const double b2 = blas::norm2(b);
+  if (b2 == 0.0) { blas::zero(x); param.true_res = 0.0; return; }
+  double r2;
+  if (param.use_init_guess) {
+    mat(*r, x);
+    r2 = blas::xmyNorm(b, *r);
+    blas::copy(*y, x);
+  } else {
+    blas::copy(*r, b);
+    r2 = b2;
+    blas::zero(*y);
+  }
+  blas::zero(*xs);   // xs == &x when not mixed: x accumulates the correction, y holds the initial guess
+  if (mixed) blas::copy(*rS, *r);
+  blas::copy(*p, *rs);
+  const double stop = param.tol * param.tol * b2;
+  const double delta = param.delta > 0.0 && param.delta < 1.0 ? param.delta : 1e-1;
+  double rNorm = sqrt(r2), r0Norm = rNorm, maxrx = rNorm, maxrr = rNorm;
+  int k = 0, updates = 0;
+  while (r2 > stop && k < param.maxiter) {
+    matSloppy(*Ap, *p);
+    const double pAp = blas::reDotProduct(*p, *Ap);
+    if (!(pAp > 0.0)) { log_msg(1, "CG: <p, A p> = %e is not positive: the operator is not Hermitian positive definite (use a NORMOP solve type)\n", pAp); break; }
+    const double alpha = r2 / pAp;
+    const double r2_old = r2;
+    r2 = blas::axpyNorm(-alpha, *Ap, *rs);
+    blas::axpy(alpha, *p, *xs);
+    rNorm = sqrt(r2);
+    if (rNorm > maxrx) maxrx = rNorm;
+    if (rNorm > maxrr) maxrr = rNorm;
+    const bool updateX = rNorm < delta * r0Norm && r0Norm <= maxrx;
+    const bool updateR = (rNorm < delta * maxrr && r0Norm <= maxrr) || updateX;
+    k++;
+    if (mixed && (updateR || !(r2 > stop))) {
+      // reliable update: y += xS, r = b - A y in the outer precision, restart the sloppy accumulator
+      blas::copy(*tmp, *xS);
+      blas::xpy(*tmp, *y);
+      mat(*r, *y);
+      r2 = blas::xmyNorm(b, *r);
+      blas::copy(*rS, *r);
+      blas::zero(*xS);
+      rNorm = sqrt(r2); maxrr = rNorm; maxrx = rNorm; r0Norm = rNorm;
+      updates++;
+    }
+    blas::xpay(*rs, r2 / r2_old, *p);   // p = r + beta p
+    if (param.verbosity >= 2) log_msg(2, "CG: %d iterations, <r,r> = %e, |r|/|b| = %e\n", k, r2, sqrt(r2 / b2));
+  }
+  // x = y + accumulated correction
+  if (mixed) { blas::copy(*tmp, *xS); blas::xpy(*tmp, *y); blas::copy(x, *y); }
+  else blas::xpy(*y, x);
+  param.iter += k;
+  param.secs += now_s() - t0;
+  if (param.compute_true_res) {
+    mat(*r, x);
+    param.true_res = sqrt(blas::xmyNorm(b, *r) / b2);
+  } else param.true_res = sqrt(r2 / b2);
+  if (k == param.maxiter && r2 > stop) log_msg(1, "CG: exceeded maximum iterations %d\n", param.maxiter);
+  log_msg(1, "CG: Convergence at %d iterations (%d reliable updates), L2 relative residual: iterated = %e, true = %e\n", k, updates, sqrt(r2 / b2), param.true_res);
 }
 
 // -------------------------------------------------------------------------------------------------

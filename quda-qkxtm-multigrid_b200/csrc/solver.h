@@ -74,6 +74,16 @@ class GCR : public Solver {
   void set_inner(int maxiter, double tol) { if (own_K) { Kparam.maxiter = maxiter; Kparam.tol = tol; } }
 };
 
+// Conjugate gradient on a Hermitian positive definite operator (the normal operator M^dag M of the NORMOP solve types),
+// mixed precision with reliable updates (lib/inv_cg_quda.cpp)
+class CG : public Solver {
+  DiracMatrix mat, matSloppy;
+  std::unique_ptr<SpinorField> r, y, p, Ap, rS, xS, tmp;
+ public:
+  CG(const DiracMatrix &mat_, const DiracMatrix &matSloppy_, SolverParam &p_) : Solver(p_), mat(mat_), matSloppy(matSloppy_) {}
+  void operator()(SpinorField &x, SpinorField &b) override;
+};
+
 class BiCGStab : public Solver {
   DiracMatrix mat, matSloppy;
   std::unique_ptr<SpinorField> r, r0, p, v, t, y, xs, rs;

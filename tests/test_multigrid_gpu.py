@@ -191,6 +191,28 @@ def test_krylov_solvers_without_multigrid(quda, oracle, inv, precond):
         assert p.iter > 0 and p.secs > 0
 
 
+@pytest.mark.parametrize("solve", ["normop_pc", "normop"])
+def test_cg_on_the_normal_equations(quda, oracle, solve):
+    """invert_test's default solver (QUDA_CG_INVERTER, lib/inv_cg_quda.cpp) on M^dag M, fp64 outer / fp32 sloppy with reliable updates:
+    x solves M x = b (MAT solution through the normal equations); residual of M checked on the host."""
+    q, L = quda, quda.lib()
+    X = (8, 8, 8, 8)
+    kappa, mu = 0.12, 0.1
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.3, antiperiodic=True, seed=7)
+    load_gauge(q, g, X, antiperiodic=True)
+    b = oracle.drand(oracle.V * 24, seed=5)
+    p = mg_inv_param(q, kappa, mu)
+    p.solve_type = q.QUDA_NORMOP_PC_SOLVE if solve == "normop_pc" else q.QUDA_NORMOP_SOLVE
+    p.inv_type = q.QUDA_CG_INVERTER
+    p.tol = 1e-10; p.maxiter = 4000; p.reliable_delta = 0.1
+    x = np.zeros_like(b)
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    res = host_residual(oracle, g, x, b, kappa, mu)
+    print(f"CG {solve}: {p.iter} iterations, host residual of M x = b: {res:.2e}, reported (normal system) {p.true_res:.2e}")
+    assert res < 5e-8 and p.true_res < 2e-10 and p.iter > 0
+
+
 def run_mg_solve(q, oracle, X, blocks, nvecs, n_level, kappa, mu, eps, tol, precond_prec=4, nu=2, setup_maxiter=200):
     L = q.lib()
     oracle.set_dims(X)
