@@ -147,7 +147,21 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   const int nmember = out.nflavor == 2 ? 2 : out.nbatch;
   const size_t st_in = out.nflavor == 2 ? in.flavor_bytes() : in.batch_bytes, st_out = out.nflavor == 2 ? out.flavor_bytes() : out.batch_bytes;
   const size_t st_x = x ? (out.nflavor == 2 ? x->flavor_bytes() : x->batch_bytes) : 0;
-  if (nmember > 1 && partitioned) QB_ERROR("apply_hop: batched / flavour-doublet fields are supported on unpartitioned lattices only");
+  if (nmember > 1 && partitioned) {
+    // partitioned lattice: the halo arena and the pack kernel hold one field, so the members go through the overlapped
+    // pack / exchange / interior / boundary path one after the other (no link sharing between members here)
+    auto member_view = [](SpinorField &w, const SpinorField &f, int c, size_t stride) {
+      w.prec = f.prec; w.nparity = 1; w.ncomplex = f.ncomplex; w.nspin = f.nspin; w.ncolor = f.ncolor; w.Vh = f.Vh;
+      w.v = (char *)f.v + (size_t)c * stride; w.norm = nullptr; w.parity_bytes = f.flavor_bytes(); w.owner = false; w.nbatch = 1; w.nflavor = 1;
+    };
+    for (int c = 0; c < nmember; c++) {
+      SpinorField oc, ic, xc;
+      member_view(oc, out, c, st_out); member_view(ic, in, c, st_in);
+      if (x) member_view(xc, *x, c, st_x);
+      hop_T<Store>(lat, gauge, oc, ic, parity, dagger, cin, co, x ? &xc : nullptr, cx, range_begin, range_count, range_stream);
+    }
+    return;
+  }
   if (!partitioned) {
     p.site_begin = range_begin; p.site_count = range_count < 0 ? g.Vh : range_count; p.site_list = nullptr;
     cudaStream_t st = range_stream ? range_stream : r.compute;

@@ -99,3 +99,42 @@ def test_ndeg_invert(quda, oracle, solve, matpc):
     res = np.linalg.norm(b - oracle.tm_ndeg_mat(g, x, kappa, mu, eps, 0)) / np.linalg.norm(b)
     print(f"ndeg invert {solve} matpc={matpc}: {p.iter} iterations, host residual {res:.2e}, reported {p.true_res:.2e}")
     assert res < 5e-9 and p.iter > 0
+
+
+@pytest.mark.parametrize("mask", [8, 12, 15])
+def test_ndeg_doublet_on_partitioned_lattice_self_exchange(mask):
+    """The doublet on a partitioned lattice (halo path on one GPU, the reference's --partition trick): the flavours go through the
+    pack / exchange / interior / boundary path one after the other.  Runs in a subprocess (partitioning is fixed at communicator set-up)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, {root!r})
+import quda_b200 as q
+from tests import oracle_util as ou
+o = ou.load_oracle(); X=(8,4,6,8); o.set_dims(X)
+g = o.gauge(1, True, 1.0, 137); sp = o.drand(4*o.Vh*24, 4711); even = sp[:2*o.Vh*24].copy()
+L = q.lib(); L.initQuda(0); L.commDimPartitionedSetQudaB200({mask})
+gp = q.gauge_param(X, cuda_prec=8, reconstruct=12)
+L.loadGaugeQuda((C.c_void_p*4)(*[a.ctypes.data for a in g]), C.byref(gp))
+worst = 0.0
+def par(**kw):
+    p = q.invert_param(cuda_prec=8, flavor=q.QUDA_TWIST_NONDEG_DOUBLET, **kw); p.epsilon = 0.03; p.Ls = 2
+    return p
+for parity, matpc, dag in [(0,0,0),(1,0,1),(0,2,1),(1,3,0)]:
+    p = par(matpc=matpc, dagger=dag)
+    out = np.zeros(2*o.Vh*24)
+    L.dslashQuda(out.ctypes.data_as(C.c_void_p), even.ctypes.data_as(C.c_void_p), C.byref(p), parity)
+    worst = max(worst, ou.rel_l2(out, o.tm_ndeg_dslash(g, even, 0.1, 0.01, 0.03, parity, matpc, dag)))
+p = par(solution_type=q.QUDA_MAT_SOLUTION)
+out = np.zeros(2*o.V*24)
+L.MatQuda(out.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p), C.byref(p))
+worst = max(worst, ou.rel_l2(out, o.tm_ndeg_mat(g, sp, 0.1, 0.01, 0.03, 0)))
+L.endQuda()
+print("WORST", worst)
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert float(r.stdout.strip().split("WORST")[-1]) <= 1e-13
