@@ -371,6 +371,8 @@ static void fill_transfer_args(GalerkinArgs &a, const Transfer &T) {
   a.N = 2 * T.nvec;
 }
 
+float *decompress_ghost_links(const GaugeField &gf, const Geom &g, int mu) { return decompress_ghost(gf, g, mu); }
+
 void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
                             const float *clover_site) {
   if (T.Nf != 12) QB_ERROR("build_coarse_from_fine: transfer is not defined on a Wilson-type fine field");

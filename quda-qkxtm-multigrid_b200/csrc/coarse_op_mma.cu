@@ -34,6 +34,7 @@ namespace qb {
 using namespace tc;
 
 float *decompress_gauge(const GaugeField &gf, const Geom &g);  // coarse_op.cu
+float *decompress_ghost_links(const GaugeField &gf, const Geom &g, int mu);  // coarse_op.cu: [parity][faceVh][18], cudaMalloc'ed
 
 // ---- site-major copies of the operands: everything a site needs is one contiguous block -> one bulk copy ------------------
 // Vs[fs][k][j] complex  (12 * nvec * 8 bytes per fine site, fs = parity * Vh + cb)
@@ -53,8 +54,15 @@ __global__ void pack_v_site_major_kernel(float2 *Vs, const float4 *V, int Nf, in
   *dst = v;
 }
 
+// index of a site inside the checkerboarded face orthogonal to mu (3-d lexicographic of the remaining coordinates >> 1)
+__device__ __forceinline__ int face_index_rt(int mu, const int *x, const Geom &g) {
+  const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
+  return (int)((x[d0] + g.X[d0] * (x[d1] + (long)g.X[d1] * x[d2])) >> 1);
+}
+
 // Us[fs][d][10] complex (9 entries + pad: 80-byte records), d = 2 mu: -kappa U_mu(x);  d = 2 mu + 1: -kappa U_mu(x - mu)^dag  (periodic wrap, boundary sign in U)
-__global__ void pack_u_site_kernel(float2 *Us, const float *U, Geom g, float kappa) {
+struct GhostLinks { const float *u[4]; };   // decompressed U_mu at x_mu = X_mu - 1 of the backward neighbour, [parity][faceVh][18] (partitioned dims)
+__global__ void pack_u_site_kernel(float2 *Us, const float *U, Geom g, float kappa, GhostLinks gl) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long Vh = g.Vh;
   if (t >= 2 * Vh * 8) return;
@@ -71,16 +79,23 @@ __global__ void pack_u_site_kernel(float2 *Us, const float *U, Geom g, float kap
   } else {
     int x[4], full;
     cb_coords(x, full, cb, parity, g);
-    x[mu] = (x[mu] + g.X[mu] - 1) % g.X[mu];
-    const long ncb = ((((long)x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.X[0] + x[0]) >> 1;
-    const float *u = U + (((size_t)(1 - parity) * 4 + mu) * Vh + ncb) * 18;
+    const float *u;
+    if (x[mu] == 0 && g.part[mu]) {   // the link lives on the backward neighbour: ghost copy, indexed by the face site
+      u = gl.u[mu] + ((size_t)(1 - parity) * g.faceVh[mu] + face_index_rt(mu, x, g)) * 18;
+    } else {
+      x[mu] = (x[mu] + g.X[mu] - 1) % g.X[mu];
+      const long ncb = ((((long)x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.X[0] + x[0]) >> 1;
+      u = U + (((size_t)(1 - parity) * 4 + mu) * Vh + ncb) * 18;
+    }
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) dst[r * 3 + c] = make_float2(-kappa * u[(c * 3 + r) * 2], kappa * u[(c * 3 + r) * 2 + 1]);
   }
 }
 
-// nbr[fs][d] = full index of x + e_d
-__global__ void fine_nbr_kernel(int *nbr, Geom g) {
+// nbr[fs][d] = full index of x + e_d; across a partitioned boundary: index of the ghost record appended to Vs,
+// Vf + ghost_off[mu][from forward (d even) : 1, from backward : 0] + neighbour parity * faceVh + face index
+struct GhostOffsets { long off[4][2]; };
+__global__ void fine_nbr_kernel(int *nbr, Geom g, GhostOffsets go) {
   const long fs = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long Vh = g.Vh;
   if (fs >= 2 * Vh) return;
@@ -91,6 +106,11 @@ __global__ void fine_nbr_kernel(int *nbr, Geom g) {
   for (int d = 0; d < 8; d++) {
     const int mu = d >> 1;
     int y[4] = {x[0], x[1], x[2], x[3]};
+    const bool edge = (d & 1) ? (x[mu] == 0) : (x[mu] == g.X[mu] - 1);
+    if (edge && g.part[mu]) {
+      nbr[fs * 8 + d] = (int)(2 * Vh + go.off[mu][(d & 1) ? 0 : 1] + (long)(1 - parity) * g.faceVh[mu] + face_index_rt(mu, x, g));
+      continue;
+    }
     y[mu] = (y[mu] + ((d & 1) ? g.X[mu] - 1 : 1)) % g.X[mu];
     const long ncb = ((((long)y[3] * g.X[2] + y[2]) * g.X[1] + y[1]) * g.X[0] + y[0]) >> 1;
     nbr[fs * 8 + d] = (int)((long)(1 - parity) * Vh + ncb);
@@ -100,7 +120,7 @@ __global__ void fine_nbr_kernel(int *nbr, Geom g) {
 // per (aggregate, site-in-aggregate) record, in the order the CTAs walk: everything index-like the pipeline needs, so that
 // no role chases pointers: {fs, nbr[8], mask (bit d: x + e_d leaves the aggregate), pad}
 struct __align__(16) GmMeta { int fs; int nb[8]; int mask; int pad[2]; };
-__global__ void galerkin_meta_kernel(GmMeta *meta, const int *c2f, const int *f2c, const int *nbr, long n, int bs) {
+__global__ void galerkin_meta_kernel(GmMeta *meta, const int *c2f, const int *f2c, const int *nbr, long n, int bs, long Vf) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int X = (int)(t / bs);
@@ -109,7 +129,7 @@ __global__ void galerkin_meta_kernel(GmMeta *meta, const int *c2f, const int *f2
   m.mask = 0;
   for (int d = 0; d < 8; d++) {
     m.nb[d] = nbr[(size_t)m.fs * 8 + d];
-    if (f2c[m.nb[d]] != X) m.mask |= 1 << d;
+    if (m.nb[d] >= Vf || f2c[m.nb[d]] != X) m.mask |= 1 << d;   // ghost records (other rank) are never in this aggregate
   }
   m.pad[0] = m.pad[1] = 0;
   meta[t] = m;
@@ -509,7 +529,8 @@ template <int NV> static void launch_gm(const GalerkinMmaArgs &a) {
 
 bool galerkin_mma_supported(const Transfer &T) {
   if (getenv("QB_GALERKIN_MMA") && atoi(getenv("QB_GALERKIN_MMA")) == 0) return false;
-  if (T.Nf != 12 || T.fine.partitioned()) return false;
+  if (T.Nf != 12) return false;
+  if (T.fine.partitioned() && getenv("QB_GALERKIN_MMA_PARTITIONED") && atoi(getenv("QB_GALERKIN_MMA_PARTITIONED")) == 0) return false;
   return T.nvec == 8 || T.nvec == 16 || T.nvec == 24;
 }
 
@@ -521,22 +542,45 @@ void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const Ga
   float *U = decompress_gauge(gauge, fine_geom);
   float2 *Vs, *Us;
   int *nbr;
-  Vs = (float2 *)pool_malloc((size_t)Vf * 12 * T.nvec * sizeof(float2));
+  // partitioned dimensions: the neighbours' boundary slices of V (Transfer::Vghost) become extra site-major records behind the Vf local
+  // ones and the neighbour table points at them; backward links across the boundary come from the gauge field's ghost links.
+  // The tensor-core kernel itself only follows the tables.
+  GhostOffsets go{};
+  GhostLinks gl{};
+  float *ug[4] = {nullptr, nullptr, nullptr, nullptr};
+  long nghost = 0;
+  for (int d = 0; d < 4; d++) {
+    gl.u[d] = nullptr;
+    for (int k = 0; k < 2; k++) go.off[d][k] = 0;
+    if (!fine_geom.part[d]) continue;
+    if (!T.Vghost[d][0] || !T.Vghost[d][1]) QB_ERROR("transfer operator has no ghost V for partitioned dimension %d", d);
+    if (!gauge.ghost[d]) QB_ERROR("gauge field has no ghost links for partitioned dimension %d", d);
+    for (int k = 0; k < 2; k++) { go.off[d][k] = nghost; nghost += 2L * fine_geom.faceVh[d]; }
+    ug[d] = decompress_ghost_links(gauge, fine_geom, d);
+    gl.u[d] = ug[d];
+  }
+  Vs = (float2 *)pool_malloc((size_t)(Vf + nghost) * 12 * T.nvec * sizeof(float2));
   Us = (float2 *)pool_malloc((size_t)Vf * 80 * sizeof(float2));
   nbr = (int *)pool_malloc((size_t)Vf * 8 * sizeof(int));
   {
     const long n = Vf * 12 * (T.nvec / 2);
     pack_v_site_major_kernel<<<div_up(n, 256), 256, 0, s>>>(Vs, (const float4 *)T.V, 12, T.nvec, Vh);
     QB_CHECK_LAUNCH();
-    pack_u_site_kernel<<<div_up(Vf * 8, 256), 256, 0, s>>>(Us, U, fine_geom, (float)kappa);
+    for (int d = 0; d < 4; d++)
+      for (int k = 0; k < 2 && fine_geom.part[d]; k++) {
+        const long fv = fine_geom.faceVh[d], ng = 2 * fv * 12 * (T.nvec / 2);
+        pack_v_site_major_kernel<<<div_up(ng, 256), 256, 0, s>>>(Vs + (size_t)(Vf + go.off[d][k]) * 12 * T.nvec, (const float4 *)T.Vghost[d][k], 12, T.nvec, fv);
+        QB_CHECK_LAUNCH();
+      }
+    pack_u_site_kernel<<<div_up(Vf * 8, 256), 256, 0, s>>>(Us, U, fine_geom, (float)kappa, gl);
     QB_CHECK_LAUNCH();
-    fine_nbr_kernel<<<div_up(Vf, 256), 256, 0, s>>>(nbr, fine_geom);
+    fine_nbr_kernel<<<div_up(Vf, 256), 256, 0, s>>>(nbr, fine_geom, go);
     QB_CHECK_LAUNCH();
   }
   GmMeta *meta;
   const long nmeta = T.coarse.V() * T.block_sites;
   meta = (GmMeta *)pool_malloc((size_t)nmeta * sizeof(GmMeta));
-  galerkin_meta_kernel<<<div_up(nmeta, 256), 256, 0, s>>>(meta, T.c2f, T.f2c, nbr, nmeta, T.block_sites);
+  galerkin_meta_kernel<<<div_up(nmeta, 256), 256, 0, s>>>(meta, T.c2f, T.f2c, nbr, nmeta, T.block_sites, Vf);
   QB_CHECK_LAUNCH();
   GalerkinMmaArgs a{};
   a.Vs = Vs; a.Us = Us; a.meta = meta; a.clover = clover_site; a.Y = out.Y; a.Vc = T.coarse.V(); a.block_sites = T.block_sites;
@@ -579,6 +623,8 @@ void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const Ga
     cudaFree(a.dbg);
   }
   pool_free(U); pool_free(Vs); pool_free(Us); pool_free(nbr); pool_free(meta);
+  for (int d = 0; d < 4; d++)
+    if (ug[d]) QB_CUDA(cudaFree(ug[d]));
 }
 
 }  // namespace qb
