@@ -118,6 +118,7 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True):
                             setup_maxiter=500, setup_tol=5e-6, run_verify=False)
     # storage precision of the preconditioner's data (V of the transfer operators, coarse links of the single-RHS kernel): fp32, or
     # fp16 with fp32 arithmetic (what cuda_prec_precondition = half selects; here chosen independently of the level-0 smoother)
+    half_storage = half_storage or os.environ.get("QB_BENCH_HALF_STORAGE") == "1"
     os.environ["QB_MG_HALF_STORAGE"] = "1" if half_storage else "0"
     t0 = time.perf_counter()
     mg = L.newMultigridQuda(C.byref(mgp))
