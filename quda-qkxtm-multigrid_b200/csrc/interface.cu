@@ -516,7 +516,8 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   if (p->input_location != QUDA_CPU_FIELD_LOCATION || p->output_location != QUDA_CPU_FIELD_LOCATION) return false;
   const int T = g.X[3];
   int nchunk = 0;
-  for (int c : {16, 8, 4}) if (T % c == 0 && T / c >= 2) { nchunk = c; break; }
+  const int want = getenv("QB_PIPE_CHUNKS") ? atoi(getenv("QB_PIPE_CHUNKS")) : 16;   // measured on B200 (32^3x64 fp32): 16 slabs 2.88 ms, 32 slabs 3.28 ms
+  for (int c : {32, 16, 8, 4}) if (c <= want && T % c == 0 && T / c >= 2) { nchunk = c; break; }
   if (!nchunk || (long)g.Vh * 24 * 4 < (4l << 20)) return false;  // small fields: latency dominates, keep it simple
   Runtime &r = rt();
   if (!pipe_state.h2d) {
