@@ -22,6 +22,7 @@ QUDA_INVALID_ENUM = -(2 ** 31)
 QUDA_CPU_FIELD_LOCATION, QUDA_CUDA_FIELD_LOCATION = 1, 2
 QUDA_SU3_LINKS = QUDA_WILSON_LINKS = 0
 QUDA_QDP_GAUGE_ORDER = 5
+QUDA_QDPJIT_GAUGE_ORDER, QUDA_CPS_WILSON_GAUGE_ORDER, QUDA_MILC_GAUGE_ORDER = 6, 7, 8
 QUDA_ANTI_PERIODIC_T, QUDA_PERIODIC_T = -1, 1
 QUDA_HALF_PRECISION, QUDA_SINGLE_PRECISION, QUDA_DOUBLE_PRECISION = 2, 4, 8
 QUDA_RECONSTRUCT_NO, QUDA_RECONSTRUCT_12, QUDA_RECONSTRUCT_8 = 18, 12, 8

@@ -263,7 +263,8 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
     LinkRaw<Store, RECON>::template load<!BATCH>(raw, (const char *)p.gauge_bwd + MU * link_block_bytes<Store, RECON>(p.stride), p.stride, nbr);
   }
   real u0;
-  if (MU < 3) u0 = RECON == 8 ? (real)1 / (real)g.aniso : (real)g.aniso;
+  const real an = sizeof(real) == 8 ? (real)g.aniso : (real)g.aniso_f;
+  if (MU < 3) u0 = RECON == 8 ? (real)1 / an : an;
   else u0 = BACK ? (x[3] == 0 ? (real)g.tb_bwd : (real)1) : (x[3] == L - 1 ? (real)g.tb_fwd : (real)1);
   cplx<real> U[9];
   reconstruct_link<real, RECON, PK>(U, raw, link_u0<Store, RECON>(u0));

@@ -37,7 +37,8 @@ void Lattice::init(const int *X, int t_boundary_sign, double anisotropy) {
   const bool last_t = r.coord[3] == r.grid[3] - 1, first_t = r.coord[3] == 0;
   geom.tb_fwd = (t_boundary_sign < 0 && last_t) ? -1 : 1;
   geom.tb_bwd = (t_boundary_sign < 0 && first_t) ? -1 : 1;
-  geom.aniso = (float)anisotropy;
+  geom.aniso = anisotropy;
+  geom.aniso_f = (float)anisotropy;
   for (int i = 0; i < 3; i++) arena_bytes[i] = 0;
   if (r.part_mask) setup_partition();
 }

@@ -76,16 +76,23 @@ __device__ __forceinline__ void store_link_real(void *block, long stride, int rp
 }
 
 template <typename Host, int STORE_BYTES, int RECON>
-__global__ void import_gauge_kernel(void *dst, const Host *stage, Geom g, long Vh) {
+__global__ void import_gauge_kernel(void *dst, const Host *stage, Geom g, long Vh, int order) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 8 * Vh) return;
   const int pm = (int)(t / Vh);  // parity*4 + mu  (matches the destination block order)
   const long cb = t - (long)pm * Vh;
   const int parity = pm >> 2, mu = pm & 3;
-  const Host *src = stage + ((long)mu * 2 * Vh + (long)parity * Vh + cb) * 18;
+  const Host *src = order == GAUGE_ORDER_QDP ? stage + ((long)mu * 2 * Vh + (long)parity * Vh + cb) * 18 : stage + (((long)parity * Vh + cb) * 4 + mu) * 18;
   double m[18];
+  if (order == GAUGE_ORDER_CPS) {   // column-row colour order, links divided by the anisotropy on load (gauge_field_order.h:1094-1112)
 #pragma unroll
-  for (int k = 0; k < 18; k++) m[k] = (double)src[k];
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) { m[(i * 3 + j) * 2] = (double)src[(j * 3 + i) * 2] / (double)g.aniso; m[(i * 3 + j) * 2 + 1] = (double)src[(j * 3 + i) * 2 + 1] / (double)g.aniso; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 18; k++) m[k] = (double)src[k];
+  }
   const int rpp = gauge_reals_per_plane(STORE_BYTES == 2 ? 2 : STORE_BYTES, RECON);
   void *block = (char *)dst + (size_t)pm * RECON * STORE_BYTES * Vh;
   if (RECON == 18 || RECON == 12) {
@@ -111,17 +118,21 @@ __global__ void import_gauge_kernel(void *dst, const Host *stage, Geom g, long V
 }
 
 template <typename Host>
-static void import_gauge_host(GaugeField &gf, void *const *h_gauge, const Geom &geom, cudaStream_t s) {
+static void import_gauge_host(GaugeField &gf, void *const *h_gauge, const Geom &geom, cudaStream_t s, HostGaugeOrder order) {
   const long Vh = gf.Vh;
   Host *stage;
   const size_t per_dir = sizeof(Host) * 2 * Vh * 18;
   QB_CUDA(cudaMalloc((void **)&stage, 4 * per_dir));
-  for (int mu = 0; mu < 4; mu++)
-    QB_CUDA(cudaMemcpyAsync((char *)stage + mu * per_dir, h_gauge[mu], per_dir, cudaMemcpyHostToDevice, s));
+  if (order == GAUGE_ORDER_QDP) {
+    for (int mu = 0; mu < 4; mu++)
+      QB_CUDA(cudaMemcpyAsync((char *)stage + mu * per_dir, h_gauge[mu], per_dir, cudaMemcpyHostToDevice, s));
+  } else {  // one contiguous host array
+    QB_CUDA(cudaMemcpyAsync(stage, (const void *)h_gauge, 4 * per_dir, cudaMemcpyHostToDevice, s));
+  }
   const int bs = 256;
   const int nb = div_up(8 * Vh, bs);
   const int sb = gf.store_bytes();
-#define LAUNCH(SB, RC) import_gauge_kernel<Host, SB, RC><<<nb, bs, 0, s>>>(gf.data, stage, geom, Vh)
+#define LAUNCH(SB, RC) import_gauge_kernel<Host, SB, RC><<<nb, bs, 0, s>>>(gf.data, stage, geom, Vh, (int)order)
 #define BY_RECON(SB)                         \
   if (gf.recon == 18) LAUNCH(SB, 18);        \
   else if (gf.recon == 12) LAUNCH(SB, 12);   \
@@ -136,15 +147,15 @@ static void import_gauge_host(GaugeField &gf, void *const *h_gauge, const Geom &
   QB_CUDA(cudaFree(stage));
 }
 
-void import_gauge(GaugeField &g, void *const *h_gauge, Prec host_prec, const Geom &geom, cudaStream_t s) {
-  if (host_prec == PREC_DOUBLE) import_gauge_host<double>(g, h_gauge, geom, s);
-  else if (host_prec == PREC_SINGLE) import_gauge_host<float>(g, h_gauge, geom, s);
+void import_gauge(GaugeField &g, void *const *h_gauge, Prec host_prec, const Geom &geom, cudaStream_t s, HostGaugeOrder order) {
+  if (host_prec == PREC_DOUBLE) import_gauge_host<double>(g, h_gauge, geom, s, order);
+  else if (host_prec == PREC_SINGLE) import_gauge_host<float>(g, h_gauge, geom, s, order);
   else QB_ERROR("host gauge precision %d not supported", (int)host_prec);
 }
 
 // export (saveGaugeQuda): reconstruct every link and write the QDP host order
 template <typename Store, int RECON, typename Host>
-__global__ void export_gauge_kernel(Host *stage, const void *src, Geom g, long Vh) {
+__global__ void export_gauge_kernel(Host *stage, const void *src, Geom g, long Vh, int order) {
   typedef typename Store::real real;
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 8 * Vh) return;
@@ -163,19 +174,26 @@ __global__ void export_gauge_kernel(Host *stage, const void *src, Geom g, long V
   cplx<real> U[9];
   reconstruct_link<real, RECON>(U, raw, link_u0<Store, RECON>(u0));
   const real ls = link_scale<Store, RECON>();
-  Host *dst = stage + ((long)mu * 2 * Vh + (long)parity * Vh + cb) * 18;
+  Host *dst = order == GAUGE_ORDER_QDP ? stage + ((long)mu * 2 * Vh + (long)parity * Vh + cb) * 18 : stage + (((long)parity * Vh + cb) * 4 + mu) * 18;
+  if (order == GAUGE_ORDER_CPS) {
 #pragma unroll
-  for (int k = 0; k < 9; k++) { dst[2 * k] = (Host)(U[k].re * ls); dst[2 * k + 1] = (Host)(U[k].im * ls); }
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) { dst[(j * 3 + i) * 2] = (Host)(U[i * 3 + j].re * ls * (real)g.aniso); dst[(j * 3 + i) * 2 + 1] = (Host)(U[i * 3 + j].im * ls * (real)g.aniso); }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; k++) { dst[2 * k] = (Host)(U[k].re * ls); dst[2 * k + 1] = (Host)(U[k].im * ls); }
+  }
 }
 
 template <typename Host>
-static void export_gauge_host(void *const *h_gauge, const GaugeField &gf, const Geom &geom, cudaStream_t s) {
+static void export_gauge_host(void *const *h_gauge, const GaugeField &gf, const Geom &geom, cudaStream_t s, HostGaugeOrder order) {
   const long Vh = gf.Vh;
   Host *stage;
   const size_t per_dir = sizeof(Host) * 2 * Vh * 18;
   QB_CUDA(cudaMalloc((void **)&stage, 4 * per_dir));
   const int bs = 256, nb = div_up(8 * Vh, bs);
-#define LAUNCH(ST, RC) export_gauge_kernel<ST, RC, Host><<<nb, bs, 0, s>>>(stage, gf.data, geom, Vh)
+#define LAUNCH(ST, RC) export_gauge_kernel<ST, RC, Host><<<nb, bs, 0, s>>>(stage, gf.data, geom, Vh, (int)order)
 #define BY_RECON(ST)                       \
   if (gf.recon == 18) LAUNCH(ST, 18);      \
   else if (gf.recon == 12) LAUNCH(ST, 12); \
@@ -186,15 +204,19 @@ static void export_gauge_host(void *const *h_gauge, const GaugeField &gf, const 
 #undef BY_RECON
 #undef LAUNCH
   QB_CHECK_LAUNCH();
-  for (int mu = 0; mu < 4; mu++)
-    QB_CUDA(cudaMemcpyAsync(h_gauge[mu], (char *)stage + mu * per_dir, per_dir, cudaMemcpyDeviceToHost, s));
+  if (order == GAUGE_ORDER_QDP) {
+    for (int mu = 0; mu < 4; mu++)
+      QB_CUDA(cudaMemcpyAsync(h_gauge[mu], (char *)stage + mu * per_dir, per_dir, cudaMemcpyDeviceToHost, s));
+  } else {
+    QB_CUDA(cudaMemcpyAsync((void *)h_gauge, stage, 4 * per_dir, cudaMemcpyDeviceToHost, s));
+  }
   QB_CUDA(cudaStreamSynchronize(s));
   QB_CUDA(cudaFree(stage));
 }
 
-void export_gauge(void *const *h_gauge, const GaugeField &g, Prec host_prec, const Geom &geom, cudaStream_t s) {
-  if (host_prec == PREC_DOUBLE) export_gauge_host<double>(h_gauge, g, geom, s);
-  else if (host_prec == PREC_SINGLE) export_gauge_host<float>(h_gauge, g, geom, s);
+void export_gauge(void *const *h_gauge, const GaugeField &g, Prec host_prec, const Geom &geom, cudaStream_t s, HostGaugeOrder order) {
+  if (host_prec == PREC_DOUBLE) export_gauge_host<double>(h_gauge, g, geom, s, order);
+  else if (host_prec == PREC_SINGLE) export_gauge_host<float>(h_gauge, g, geom, s, order);
   else QB_ERROR("host gauge precision %d not supported", (int)host_prec);
 }
 

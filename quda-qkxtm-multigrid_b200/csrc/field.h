@@ -25,7 +25,8 @@ struct Geom {
   int faceVh[4];  // checkerboard face volume per dimension
   int tb_fwd;     // -1 if forward T links on the local slice t=T-1 carry the antiperiodic sign
   int tb_bwd;     // -1 if backward T links used by sites at t=0 carry it
-  float aniso;    // anisotropy (recon 12/8: scale of the reconstructed row for spatial links)
+  double aniso;   // anisotropy (recon 12/8: scale of the reconstructed row for spatial links); double: fp64 fields must see the exact value
+  float aniso_f;  // the same rounded once on the host, for the fp32 / int16 kernels (no fp64 conversion in their inner code)
 };
 
 struct SpinorField {
@@ -91,8 +92,11 @@ enum HostBasis { BASIS_DEGRAND_ROSSI = 0, BASIS_UKQCD = 1 };
 enum HostSpinorOrder { ORDER_SPIN_COLOR = 0, ORDER_COLOR_SPIN = 1 };
 
 // h_gauge: QDP order void*[4], each [parity][cb][row][col][re,im] in host_prec
-void import_gauge(GaugeField &g, void *const *h_gauge, Prec host_prec, const Geom &geom, cudaStream_t s);
-void export_gauge(void *const *h_gauge, const GaugeField &g, Prec host_prec, const Geom &geom, cudaStream_t s);
+// host link orders (include/gauge_field_order.h of the reference): QDP = void*[4], [mu][parity][x_cb][row][col]; MILC = one array
+// [parity][x_cb][mu][row][col] (:1028-1070); CPS = MILC indexing with the colour matrix transposed and multiplied by the anisotropy (:1076-1135)
+enum HostGaugeOrder { GAUGE_ORDER_QDP = 0, GAUGE_ORDER_MILC = 1, GAUGE_ORDER_CPS = 2 };
+void import_gauge(GaugeField &g, void *const *h_gauge, Prec host_prec, const Geom &geom, cudaStream_t s, HostGaugeOrder order = GAUGE_ORDER_QDP);
+void export_gauge(void *const *h_gauge, const GaugeField &g, Prec host_prec, const Geom &geom, cudaStream_t s, HostGaugeOrder order = GAUGE_ORDER_QDP);
 // fills g.ghost[d] for the partitioned dimensions from the local field (self-exchange) or the neighbour (NCCL)
 void exchange_gauge_ghost(GaugeField &g, const Geom &geom, cudaStream_t s);
 

@@ -50,6 +50,12 @@ HostBasis to_basis(QudaGammaBasis b) {
   if (b == QUDA_UKQCD_GAMMA_BASIS) return BASIS_UKQCD;
   QB_ERROR("Parameter gamma_basis undefined");
 }
+HostGaugeOrder host_gauge_order(QudaGaugeFieldOrder o) {
+  if (o == QUDA_QDP_GAUGE_ORDER) return GAUGE_ORDER_QDP;
+  if (o == QUDA_MILC_GAUGE_ORDER) return GAUGE_ORDER_MILC;
+  if (o == QUDA_CPS_WILSON_GAUGE_ORDER) return GAUGE_ORDER_CPS;
+  QB_ERROR("Gauge order %d not supported (QUDA_QDP_GAUGE_ORDER, QUDA_MILC_GAUGE_ORDER, QUDA_CPS_WILSON_GAUGE_ORDER)", (int)o);
+}
 HostSpinorOrder to_order(QudaDiracFieldOrder o) {
   if (o == QUDA_DIRAC_ORDER) return ORDER_SPIN_COLOR;
   if (o == QUDA_QDP_DIRAC_ORDER) return ORDER_COLOR_SPIN;
@@ -408,7 +414,8 @@ void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
     if (param->X[i] == INVALID_INT) QB_ERROR("Parameter X[%d] undefined", i);
   if (param->type != QUDA_WILSON_LINKS) QB_ERROR("Only QUDA_WILSON_LINKS gauge fields are supported");
   if (param->anisotropy == INVALID_DOUBLE) QB_ERROR("Parameter anisotropy undefined");
-  if (param->gauge_order != QUDA_QDP_GAUGE_ORDER) QB_ERROR("Gauge order %d not supported (QUDA_QDP_GAUGE_ORDER only)", (int)param->gauge_order);
+  if (param->gauge_order != QUDA_QDP_GAUGE_ORDER && param->gauge_order != QUDA_MILC_GAUGE_ORDER && param->gauge_order != QUDA_CPS_WILSON_GAUGE_ORDER)
+    QB_ERROR("Gauge order %d not supported (QUDA_QDP_GAUGE_ORDER, QUDA_MILC_GAUGE_ORDER, QUDA_CPS_WILSON_GAUGE_ORDER)", (int)param->gauge_order);
   if (param->t_boundary == QUDA_INVALID_T_BOUNDARY) QB_ERROR("Parameter t_boundary undefined");
   if (param->location != QUDA_CPU_FIELD_LOCATION) QB_ERROR("loadGaugeQuda expects a host gauge field");
   const Prec cpu_prec = to_prec(param->cpu_prec, "cpu_prec");
@@ -426,15 +433,16 @@ void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
   G.param = *param;
   const long Vh = G.lat.geom.Vh;
   void *const *hg = (void *const *)h_gauge;
+  const HostGaugeOrder gorder = host_gauge_order(param->gauge_order);
 
   G.precise.reset(new GaugeField(Vh, prec, (int)param->reconstruct));
-  import_gauge(*G.precise, hg, cpu_prec, G.lat.geom, r.compute);
+  import_gauge(*G.precise, hg, cpu_prec, G.lat.geom, r.compute, gorder);
   build_gauge_ghost(*G.precise);
   double gib = (double)G.precise->bytes() / (1 << 30);
   if (prec_s == prec && rec_s == (int)param->reconstruct) G.sloppy = G.precise;
   else {
     G.sloppy.reset(new GaugeField(Vh, prec_s, rec_s));
-    import_gauge(*G.sloppy, hg, cpu_prec, G.lat.geom, r.compute);
+    import_gauge(*G.sloppy, hg, cpu_prec, G.lat.geom, r.compute, gorder);
     build_gauge_ghost(*G.sloppy);
     gib += (double)G.sloppy->bytes() / (1 << 30);
   }
@@ -442,7 +450,7 @@ void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
   else if (prec_p == prec && rec_p == (int)param->reconstruct) G.precondition = G.precise;
   else {
     G.precondition.reset(new GaugeField(Vh, prec_p, rec_p));
-    import_gauge(*G.precondition, hg, cpu_prec, G.lat.geom, r.compute);
+    import_gauge(*G.precondition, hg, cpu_prec, G.lat.geom, r.compute, gorder);
     build_gauge_ghost(*G.precondition);
     gib += (double)G.precondition->bytes() / (1 << 30);
   }
@@ -463,8 +471,7 @@ void freeGaugeQuda(void) {
 
 void saveGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
   require_gauge();
-  if (param->gauge_order != QUDA_QDP_GAUGE_ORDER) QB_ERROR("Gauge order %d not supported", (int)param->gauge_order);
-  export_gauge((void *const *)h_gauge, *G.precise, to_prec(param->cpu_prec, "cpu_prec"), G.lat.geom, rt().compute);
+  export_gauge((void *const *)h_gauge, *G.precise, to_prec(param->cpu_prec, "cpu_prec"), G.lat.geom, rt().compute, host_gauge_order(param->gauge_order));
 }
 
 // ---- operator application -----------------------------------------------------------------------

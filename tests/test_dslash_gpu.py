@@ -335,3 +335,29 @@ def test_batched_hop_equals_single_field_hop(quda, oracle, nbatch):
         dev = C.c_double(-1.0)
         L.timeDslashBatchQudaB200(C.byref(p), 1, nbatch, 1, C.byref(dev))
         assert dev.value == 0.0, dev.value
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order,aniso", [("milc", 1.0), ("milc", 1.7), ("cps", 1.0), ("cps", 1.7)])
+def test_host_gauge_orders(quda, oracle, order, aniso):
+    """loadGaugeQuda / saveGaugeQuda with the MILC and CPS host link orders (include/gauge_field_order.h:1028-1135 of the reference):
+    one array [parity][x_cb][mu][..], CPS with transposed colour matrices scaled by the anisotropy.  The Dslash on links loaded in that
+    order must equal the oracle's on the QDP links, and saveGaugeQuda must hand the same array back."""
+    q, L = quda, quda.lib()
+    X = (8, 4, 6, 8)
+    oracle.set_dims(X)
+    g = oracle.gauge(kind=1, antiperiodic=True, anisotropy=aniso, seed=321)   # QDP: 4 arrays [parity][cb][3][3][2]
+    V, Vh = oracle.V, oracle.Vh
+    qdp = np.stack([a.reshape(V, 3, 3, 2) for a in g], axis=1)              # [site (parity-major)][mu][row][col][2]
+    host = (np.transpose(qdp, (0, 1, 3, 2, 4)) * aniso if order == "cps" else qdp).copy().ravel()
+    gp = q.gauge_param(X, cuda_prec=8, reconstruct=18, anisotropy=aniso)
+    gp.gauge_order = q.QUDA_CPS_WILSON_GAUGE_ORDER if order == "cps" else q.QUDA_MILC_GAUGE_ORDER
+    L.loadGaugeQuda(vp(host), C.byref(gp))
+    sp = oracle.drand(oracle.Vh * 24, seed=9)
+    p = q.invert_param(kappa=KAPPA, mu=MU, cuda_prec=8)
+    out = np.zeros(Vh * 24)
+    L.dslashQuda(vp(out), vp(sp), C.byref(p), 0)
+    assert rel_l2(out, oracle.tm_dslash(g, sp, KAPPA, MU, 1, 0, 0, 0)) < 1e-13
+    back = np.zeros_like(host)
+    L.saveGaugeQuda(vp(back), C.byref(gp))
+    assert np.allclose(back, host, rtol=0, atol=1e-14)
