@@ -278,6 +278,13 @@ struct BlockOps {
     for (int r = 0; r < R; r++) c[r] = Cx(a[r], 0.0);
     blas_.axpy<3>(c, none, x, nullptr, x);
   }
+  // x *= sc; y += coef x (the scaled x); r2 = |y|^2 per column
+  void scale_axpy_norm(const std::vector<double> &sc, const std::vector<Cx> &coef, Vec x, Vec y, std::vector<double> &r2, const Mask &m) {
+    std::vector<Cx> dot;
+    scale(sc, x, m);
+    axpy(coef, x, y, m);
+    cdot(y, y, dot, r2, m);
+  }
   // beta[i][c] = <v_i, y>_c for i < k, then y -= sum_i beta_i v_i   (one vector at a time: modified Gram-Schmidt)
   void ortho(const std::vector<Vec> &v, int k, Vec y, std::vector<std::vector<Cx>> &beta, const Mask &live) {
     std::vector<Cx> dot, coef(R);
@@ -316,6 +323,11 @@ struct FieldOps {
   }
   void axpy(const std::vector<Cx> &a, Vec x, Vec y, const Mask &m) { for (int r = 0; r < R; r++) if (m[r] && a[r] != Cx(0, 0)) blas::caxpy(a[r], *(*x)[r], *(*y)[r]); }
   void scale(const std::vector<double> &a, Vec x, const Mask &m) { for (int r = 0; r < R; r++) if (m[r] && a[r] != 1.0) blas::ax(a[r], *(*x)[r]); }
+  // x *= sc; y += coef x; r2 = |y|^2: the fused kernel of the single-source GCR (cabxpyAxNorm: 4 field streams instead of 7)
+  void scale_axpy_norm(const std::vector<double> &sc, const std::vector<Cx> &coef, Vec x, Vec y, std::vector<double> &r2, const Mask &m) {
+    r2.assign(R, 0.0);
+    for (int r = 0; r < R; r++) if (m[r]) r2[r] = blas::cabxpyAxNorm(sc[r], coef[r], *(*x)[r], *(*y)[r]);
+  }
   // per column the fused multi-vector kernels of blas.cu (y is read once for all k dot products / updated once for all k terms)
   void ortho(const std::vector<Vec> &v, int k, Vec y, std::vector<std::vector<Cx>> &beta, const Mask &live) {
     beta.assign(k, std::vector<Cx>(R, Cx(0, 0)));
@@ -430,9 +442,7 @@ template <class Ops> struct BlockKrylov {
           else { gamma[k][c] = 1.0; alpha[k][c] = Cx(0, 0); sc[c] = 1.0; }
           coef[c] = -alpha[k][c];
         }
-        ops.scale(sc, Ap[k], live);
-        ops.axpy(coef, Ap[k], r, live);
-        ops.cdot(r, r, dot, nx, live);
+        ops.scale_axpy_norm(sc, coef, Ap[k], r, nx, live);   // Ap_k /= gamma_k; r -= alpha_k Ap_k; |r|^2
         k++; total++;
         for (int c = 0; c < R; c++) if (live[c]) {
           r2[c] = nx[c];
