@@ -303,6 +303,14 @@ def test_block_mg_multi_src_solve(quda, oracle, n_level, X, blocks, nvecs, mode,
 
     xb, it_b, tr_b, t_b = solve(True)
     xs, it_s, tr_s, t_s = solve(False)
+    if mode == 3 and n_level == 2:
+        # blocks of 2 sources: 5 sources = 2 + 2 + a left-over single one (ordinary path), counters accumulate
+        monkeypatch.setenv("QB_BLOCK_MG_R", "2")
+        xc, it_c, tr_c, _ = solve(True)
+        monkeypatch.delenv("QB_BLOCK_MG_R")
+        assert tr_c < 5e-8 and it_c >= it_b
+        for a, b_ in zip(xc, xs):
+            assert np.linalg.norm(a - b_) / np.linalg.norm(b_) < 1e-6
     L.destroyMultigridQuda(mg)
     worst = max(host_residual(oracle, g, x, b, kappa, mu) for x, b in zip(xb, bs))
     print(f"block MG ({n_level} levels, mode {mode}): {it_b} lock-step iterations in {t_b:.3f} s, sequential {it_s} iterations (sum over {nsrc}) in {t_s:.3f} s; "
