@@ -549,26 +549,26 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   // everything previously queued on the compute stream must be done before the staging buffers are reused
   QB_CUDA(cudaEventRecord(pipe_state.ev_done, r.compute));
   QB_CUDA(cudaStreamWaitEvent(pipe_state.h2d, pipe_state.ev_done, 0));
+  // H2D stream: nothing but back-to-back copies (the reorder kernels run on the compute stream, so no copy waits for a kernel)
   for (int c = 0; c < nchunk; c++) {
     QB_CUDA(cudaMemcpyAsync(stage_in + c * csites * site_bytes, (const char *)h_in + c * csites * site_bytes, csites * site_bytes, cudaMemcpyHostToDevice, pipe_state.h2d));
-    import_spinor_range(in, stage_in, hp, basis, order, c * csites, csites, pipe_state.h2d);
     QB_CUDA(cudaEventRecord(pipe_state.ev_in[c], pipe_state.h2d));
   }
-  // slab c needs its t-neighbours c-1 and c+1 (periodic): process 1 .. nchunk-2 as they arrive, then nchunk-1 and 0
-  std::vector<int> order_c;
-  for (int c = 1; c < nchunk - 1; c++) order_c.push_back(c);
-  order_c.push_back(nchunk - 1);
-  order_c.push_back(0);
-  for (int c : order_c) {
-    QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[(c + 1) % nchunk], 0));
+  // slab k needs its t-neighbours k-1 and k+1 (periodic): convert slab c as it lands, then multiply slab c-1; slabs nchunk-1 and 0 last
+  auto process = [&](int k) {
+    d->DslashRange(out, in, (int)parity, (int)(k * csites), (int)csites, r.compute);
+    export_spinor_range(stage_out, out, hp, basis, order, k * csites, csites, r.compute);
+    QB_CUDA(cudaEventRecord(pipe_state.ev_out[k], r.compute));
+    QB_CUDA(cudaStreamWaitEvent(pipe_state.d2h, pipe_state.ev_out[k], 0));
+    QB_CUDA(cudaMemcpyAsync((char *)h_out + k * csites * site_bytes, stage_out + k * csites * site_bytes, csites * site_bytes, cudaMemcpyDeviceToHost, pipe_state.d2h));
+  };
+  for (int c = 0; c < nchunk; c++) {
     QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[c], 0));
-    QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[(c + nchunk - 1) % nchunk], 0));
-    d->DslashRange(out, in, (int)parity, (int)(c * csites), (int)csites, r.compute);
-    export_spinor_range(stage_out, out, hp, basis, order, c * csites, csites, r.compute);
-    QB_CUDA(cudaEventRecord(pipe_state.ev_out[c], r.compute));
-    QB_CUDA(cudaStreamWaitEvent(pipe_state.d2h, pipe_state.ev_out[c], 0));
-    QB_CUDA(cudaMemcpyAsync((char *)h_out + c * csites * site_bytes, stage_out + c * csites * site_bytes, csites * site_bytes, cudaMemcpyDeviceToHost, pipe_state.d2h));
+    import_spinor_range(in, stage_in, hp, basis, order, c * csites, csites, r.compute);
+    if (c >= 2) process(c - 1);
   }
+  process(nchunk - 1);
+  process(0);
   QB_CUDA(cudaStreamSynchronize(pipe_state.d2h));
   QB_CUDA(cudaStreamSynchronize(r.compute));
   return true;
