@@ -384,6 +384,25 @@ def main():
             barrier()
             res["e2e_ms"] = (time.perf_counter() - t0) * 1e3 / n
             res["e2e_bytes"] = hin.numel() * hin.element_size()
+            # what the PCIe link alone allows for these two buffers: H2D and D2H of the same sizes on two streams at once (no compute, no
+            # dependency between them); dslashQuda cannot beat it and has to add the three slabs whose result can only leave after the
+            # last input slab has arrived
+            dbuf_in = torch.empty(hin.numel(), dtype=hin.dtype, device="cuda")
+            dbuf_out = torch.empty(hin.numel(), dtype=hin.dtype, device="cuda")
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            torch.cuda.synchronize()
+            best = None
+            for _ in range(6):
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s1):
+                    dbuf_in.copy_(hin, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    hout.copy_(dbuf_out, non_blocking=True)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) * 1e3
+                best = dt if best is None else min(best, dt)
+            res["pcie_ms"] = best
+            del dbuf_in, dbuf_out
         L.freeSpinorQudaB200(fin)
         L.freeSpinorQudaB200(fout)
         return res
@@ -443,7 +462,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": traffic, "peak_source": peak_kind, "kernel": "dslash_kernel<StoreS,12,TWIST_IN=false,HAS_X=false,GHOST=false>" if args.prec == 4 else "dslash_kernel"},
             "e2e": {"value": FLOPS_PER_SITE * sites / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": main_res["e2e_bytes"], "d2h_bytes_per_step": main_res["e2e_bytes"]},
+                    "h2d_bytes_per_step": main_res["e2e_bytes"], "d2h_bytes_per_step": main_res["e2e_bytes"],
+                    "pcie_floor_ms": main_res.get("pcie_ms"),
+                    "pcie_floor_note": "H2D + D2H of the same two pinned buffers on two streams at once, no compute: the link-bound lower limit of this call"},
             "gpu_launches": main_res["launches"],
             "clocks": sampler.summary(),
             "cpu_baseline": cpu,

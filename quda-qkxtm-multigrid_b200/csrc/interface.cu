@@ -522,10 +522,30 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH || in.nflavor != 1) return false;  // two kernels per hop: plain path
   if (p->input_location != QUDA_CPU_FIELD_LOCATION || p->output_location != QUDA_CPU_FIELD_LOCATION) return false;
   const int T = g.X[3];
-  int nchunk = 0;
-  const int want = getenv("QB_PIPE_CHUNKS") ? atoi(getenv("QB_PIPE_CHUNKS")) : 16;   // measured on B200 (32^3x64 fp32): 16 slabs 2.88 ms, 32 slabs 3.28 ms
-  for (int c : {32, 16, 8, 4}) if (c <= want && T % c == 0 && T / c >= 2) { nchunk = c; break; }
-  if (!nchunk || (long)g.Vh * 24 * 4 < (4l << 20)) return false;  // small fields: latency dominates, keep it simple
+  // Slabs of whole time slices.  A slab can be multiplied once it and its two t-neighbours have landed, so whatever depends on the LAST
+  // slab to arrive (that slab and its two neighbours) leaves only after the H2D stream has finished: the exposed tail.  The very last slab
+  // is sent FIRST (slab 0 needs it across the periodic boundary).  Uniform slabs on B200 (32^3x64, fp32): 16 slabs 2.88 ms, 32 slabs 3.28 ms.
+  // Measured with CUDA events on B200 (QB_PIPE_TRACE=1, 32^3x64 fp32, link floor 2.04 ms): every extra copy costs the H2D stream ~30 us,
+  // the first D2H cannot start before the first three slabs are in, and the D2H stream runs one slab behind the H2D stream.  So: few
+  // slabs, thin ones at the head (the first results leave early) and tapering ones at the end (little is left when the last input lands).
+  const int want = getenv("QB_PIPE_CHUNKS") ? atoi(getenv("QB_PIPE_CHUNKS")) : 13;   // 9 / 11 / 13 slabs: 3.06 / 2.82 / 2.73 ms (uniform 16: 2.88 ms)
+  const bool tapered = !(getenv("QB_PIPE_UNIFORM") && atoi(getenv("QB_PIPE_UNIFORM"))) && T >= 32 && want >= 8;
+  std::vector<int> tslices;   // time slices per slab
+  if (tapered) {
+    const int head = std::max(1, T / 32);
+    const int tail[4] = {std::max(1, T / 16), std::max(1, T / 32), 1, 1};
+    const int rest = T - 2 * head - (tail[0] + tail[1] + tail[2] + tail[3]);
+    const int nbig = std::max(1, std::min(want - 6, rest));
+    tslices.push_back(head); tslices.push_back(head);
+    for (int c = 0; c < nbig; c++) tslices.push_back(rest / nbig + (c < rest % nbig ? 1 : 0));
+    for (int c = 0; c < 4; c++) tslices.push_back(tail[c]);
+  } else {
+    int n = 0;
+    for (int c : {32, 16, 8, 4}) if (c <= want && T % c == 0 && T / c >= 2) { n = c; break; }
+    for (int c = 0; c < n; c++) tslices.push_back(T / n);
+  }
+  const int nchunk = (int)tslices.size();
+  if (nchunk < 4 || (long)g.Vh * 24 * 4 < (4l << 20)) return false;  // small fields: latency dominates, keep it simple
   Runtime &r = rt();
   if (!pipe_state.h2d) {
     QB_CUDA(cudaStreamCreateWithFlags(&pipe_state.h2d, cudaStreamNonBlocking));
@@ -544,31 +564,53 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   const size_t site_bytes = 24 * (size_t)hp;
   const size_t hb = site_bytes * g.Vh;
   char *stage_in = (char *)staging(2 * hb), *stage_out = stage_in + hb;
-  const long csites = g.Vh / nchunk;
+  const long slice_sites = g.Vh / T;   // checkerboard sites per time slice (cb index is t-slowest)
+  std::vector<long> begin(nchunk), count(nchunk);
+  for (int c = 0, t0 = 0; c < nchunk; t0 += tslices[c], c++) { begin[c] = t0 * slice_sites; count[c] = tslices[c] * slice_sites; }
   std::unique_ptr<DiracTM> d(make_dirac(p, true, pick_gauge(in.prec)));
   // everything previously queued on the compute stream must be done before the staging buffers are reused
   QB_CUDA(cudaEventRecord(pipe_state.ev_done, r.compute));
   QB_CUDA(cudaStreamWaitEvent(pipe_state.h2d, pipe_state.ev_done, 0));
-  // H2D stream: nothing but back-to-back copies (the reorder kernels run on the compute stream, so no copy waits for a kernel)
-  for (int c = 0; c < nchunk; c++) {
-    QB_CUDA(cudaMemcpyAsync(stage_in + c * csites * site_bytes, (const char *)h_in + c * csites * site_bytes, csites * site_bytes, cudaMemcpyHostToDevice, pipe_state.h2d));
+  // H2D stream: nothing but back-to-back copies (the reorder kernels run on the compute stream), last slab first
+  static const bool trace = getenv("QB_PIPE_TRACE") && atoi(getenv("QB_PIPE_TRACE"));
+  cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};   // h2d begin / end, d2h first copy begin / last copy end
+  if (trace) for (auto &e : tr) QB_CUDA(cudaEventCreate(&e));
+  if (trace) QB_CUDA(cudaEventRecord(tr[0], pipe_state.h2d));
+  std::vector<int> arrival;
+  arrival.push_back(nchunk - 1);
+  for (int c = 0; c < nchunk - 1; c++) arrival.push_back(c);
+  for (int c : arrival) {
+    QB_CUDA(cudaMemcpyAsync(stage_in + begin[c] * site_bytes, (const char *)h_in + begin[c] * site_bytes, count[c] * site_bytes, cudaMemcpyHostToDevice, pipe_state.h2d));
     QB_CUDA(cudaEventRecord(pipe_state.ev_in[c], pipe_state.h2d));
   }
-  // slab k needs its t-neighbours k-1 and k+1 (periodic): convert slab c as it lands, then multiply slab c-1; slabs nchunk-1 and 0 last
+  if (trace) QB_CUDA(cudaEventRecord(tr[1], pipe_state.h2d));
+  bool first_out = true;
   auto process = [&](int k) {
-    d->DslashRange(out, in, (int)parity, (int)(k * csites), (int)csites, r.compute);
-    export_spinor_range(stage_out, out, hp, basis, order, k * csites, csites, r.compute);
+    d->DslashRange(out, in, (int)parity, (int)begin[k], (int)count[k], r.compute);
+    export_spinor_range(stage_out, out, hp, basis, order, begin[k], count[k], r.compute);
     QB_CUDA(cudaEventRecord(pipe_state.ev_out[k], r.compute));
     QB_CUDA(cudaStreamWaitEvent(pipe_state.d2h, pipe_state.ev_out[k], 0));
-    QB_CUDA(cudaMemcpyAsync((char *)h_out + k * csites * site_bytes, stage_out + k * csites * site_bytes, csites * site_bytes, cudaMemcpyDeviceToHost, pipe_state.d2h));
+    if (trace && first_out) { QB_CUDA(cudaEventRecord(tr[2], pipe_state.d2h)); first_out = false; }
+    QB_CUDA(cudaMemcpyAsync((char *)h_out + begin[k] * site_bytes, stage_out + begin[k] * site_bytes, count[k] * site_bytes, cudaMemcpyDeviceToHost, pipe_state.d2h));
   };
-  for (int c = 0; c < nchunk; c++) {
+  // convert every slab as it lands; slab k is multiplied once k-1, k, k+1 (periodic) are there: arrival order n-1, 0, 1, ... => after
+  // slab c >= 1 has landed, slab c-1 is complete; the tail is n-2 and n-1
+  for (size_t a = 0; a < arrival.size(); a++) {
+    const int c = arrival[a];
     QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[c], 0));
-    import_spinor_range(in, stage_in, hp, basis, order, c * csites, csites, r.compute);
-    if (c >= 2) process(c - 1);
+    import_spinor_range(in, stage_in, hp, basis, order, begin[c], count[c], r.compute);
+    if (a >= 2) process(c - 1);
   }
+  process(nchunk - 2);
   process(nchunk - 1);
-  process(0);
+  if (trace) {
+    QB_CUDA(cudaEventRecord(tr[3], pipe_state.d2h));
+    QB_CUDA(cudaEventSynchronize(tr[3]));
+    float h2d = 0, first = 0, total = 0, tail = 0;
+    cudaEventElapsedTime(&h2d, tr[0], tr[1]); cudaEventElapsedTime(&first, tr[0], tr[2]); cudaEventElapsedTime(&total, tr[0], tr[3]); cudaEventElapsedTime(&tail, tr[1], tr[3]);
+    fprintf(stderr, "dslashQuda pipeline: %d slabs, H2D %.3f ms, first D2H starts at %.3f ms, last D2H ends at %.3f ms (%.3f ms after the last H2D)\n", nchunk, h2d, first, total, tail);
+    for (auto &e : tr) cudaEventDestroy(e);
+  }
   QB_CUDA(cudaStreamSynchronize(pipe_state.d2h));
   QB_CUDA(cudaStreamSynchronize(r.compute));
   return true;
