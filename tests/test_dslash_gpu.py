@@ -361,3 +361,19 @@ def test_host_gauge_orders(quda, oracle, order, aniso):
     back = np.zeros_like(host)
     L.saveGaugeQuda(vp(back), C.byref(gp))
     assert np.allclose(back, host, rtol=0, atol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("X,uniform", [((16, 16, 16, 32), 0), ((16, 16, 16, 32), 1), ((12, 12, 24, 48), 0), ((16, 16, 32, 16), 0)])
+def test_pipelined_host_path_matches_oracle(quda, oracle, X, uniform, monkeypatch):
+    """dslashQuda on lattices large enough for the slab-pipelined host path (H2D, reorder, hop, reorder, D2H overlapped per T-slab;
+    tapered slab schedule with the last slab sent first, or equal slabs): every site against the oracle, both parities and daggers."""
+    monkeypatch.setenv("QB_PIPE_UNIFORM", str(uniform))
+    c = Ctx(quda, oracle, X, 4, 12)
+    for parity, dagger in ((0, 0), (1, 1)):
+        p = c.param(flavor=1, matpc=0, dagger=dagger)
+        src = c.even if parity == 0 else c.sp[c.Vh * 24:].copy()
+        out = np.zeros(c.Vh * 24)
+        quda.lib().dslashQuda(vp(out), vp(src), C.byref(p), parity)
+        oracle.set_dims(X)
+        assert rel_l2(out, oracle.tm_dslash(c.g, src, KAPPA, MU, 1, parity, 0, dagger)) <= TOL[4]
