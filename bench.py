@@ -14,6 +14,11 @@ owns a 32^3 x 64 block of a lattice partitioned along T (one process per GPU, NC
 `roofline`: compulsory bytes (576 B/site fp32 r12: 8 links x 48 B + in + out spinor) / kernel time vs
             the measured HBM peak (MEASURED_PEAKS.json).
 `cpu_baseline`: the CPU oracle (OpenMP port of the reference's verify path) on the host cores.
+
+N>1 additionally: `parity` = dslashQuda / MatQuda on a small partitioned lattice on all ranks against the
+global CPU oracle before anything is timed (non-zero exit on mismatch); `extra.c3` = BASELINE configs[2], global 64^3x128
+split T-only and T x Z (strong scaling, halo bytes and the NVLink rate of the halo path alone); `extra.c5_mg_gcr` (N=8) =
+BASELINE configs[4], 3-level MG-GCR on global 64^3x128.  N=1 additionally: `extra.c4_48x96` = BASELINE configs[3].
 """
 import argparse
 import ctypes as C
@@ -88,6 +93,195 @@ def make_inputs(oracle, X, seed):
     g = oracle.gauge(kind=1, antiperiodic=True, seed=seed)
     sp = oracle.drand(oracle.Vh * 24, seed=seed)
     return g, sp
+
+
+def tiled_gauge(oracle, Xl, seed, tb=4, weak=False):
+    """Random SU(3) links of a (X, Y, Z, tb) block from the oracle's generator, repeated along T to the local lattice, fp32, QDP
+    even-odd order.  T is the slowest index of the checkerboard order and tb is even, so the repetition is a plain tile of each
+    parity block; links are site-local, so any such field is a valid gauge field (used for the large timing-only lattices)."""
+    Xb = (Xl[0], Xl[1], Xl[2], min(tb, Xl[3]))
+    assert Xl[3] % Xb[3] == 0
+    oracle.set_dims(Xb)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=seed) if weak else oracle.gauge(kind=1, antiperiodic=False, seed=seed)
+    reps = Xl[3] // Xb[3]
+    return [np.ascontiguousarray(np.tile(a.astype(np.float32).reshape(2, -1), (1, reps))).ravel() for a in g]
+
+
+def parity_check(q, L, oracle, du, rank, world, grid, Xl=(8, 4, 6, 8)):
+    """Multi-rank parity before timing: every rank loads its block of ONE global lattice (generated identically on every rank by the
+    oracle), applies dslashQuda / MatQuda through the C ABI with the NCCL halo exchange, and compares with its slice of the global
+    CPU result.  Returns {name: worst relative L2 over ranks}; raises on a tolerance violation (north_star: 1e-13 / 1e-6 / 1e-3)."""
+    import torch
+    import torch.distributed as dist
+    L.initCommsGridQuda(4, (C.c_int * 4)(*grid), None, None)
+    coords = du.rank_coords(rank, grid)
+    idx, Xg = du.local_to_global_index(Xl, grid, coords)
+    oracle.set_dims(Xg)
+    g = oracle.gauge(kind=1, antiperiodic=True, seed=137)
+    sp = oracle.drand(2 * oracle.Vh * 24, seed=137)
+    Vhl, Vhg = int(np.prod(Xl)) // 2, oracle.Vh
+    gl = [du.slice_field(a, idx, 18) for a in g]
+    spl = du.slice_field(sp, idx, 24)
+    out = {}
+    for prec, name, tol in ((8, "fp64", 1e-13), (4, "fp32", 1e-6), (2, "half", 1e-3)):
+        gp = q.gauge_param(Xl, cuda_prec=prec, reconstruct=12)
+        L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in gl]), C.byref(gp))
+        worst = 0.0
+        for flavor, parity, matpc, dag in ((1, 0, 0, 0), (-1, 1, 0, 1)):
+            p = q.invert_param(cuda_prec=prec, flavor=flavor, matpc=matpc, dagger=dag)
+            inp = spl[(1 - parity) * Vhl * 24:(2 - parity) * Vhl * 24].copy()
+            res = np.zeros(Vhl * 24)
+            L.dslashQuda(vp(res), vp(inp), C.byref(p), parity)
+            gin = sp[(1 - parity) * Vhg * 24:(2 - parity) * Vhg * 24].copy()
+            full = np.zeros(2 * Vhg * 24)
+            full[parity * Vhg * 24:(parity + 1) * Vhg * 24] = oracle.tm_dslash(g, gin, KAPPA, MU, flavor, parity, matpc, dag)
+            ref_l = du.slice_field(full, idx, 24)[parity * Vhl * 24:(parity + 1) * Vhl * 24]
+            worst = max(worst, ou_rel_l2(res, ref_l))
+        p = q.invert_param(cuda_prec=prec, solution_type=q.QUDA_MAT_SOLUTION)
+        res = np.zeros(2 * Vhl * 24)
+        L.MatQuda(vp(res), vp(spl), C.byref(p))
+        worst = max(worst, ou_rel_l2(res, du.slice_field(oracle.tm_mat(g, sp, KAPPA, MU, 1, 0), idx, 24)))
+        t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = float(t.item())
+        if not out[name] <= tol:
+            raise SystemExit(f"bench.py: multi-GPU parity FAILED on grid {grid}: {name} rel-L2 {out[name]:.3e} > {tol:g}")
+    return {"grid": list(grid), "local": list(Xl), "global": list(Xg), "rel_l2": out,
+            "checked": "dslashQuda (2 flavour/parity/dagger variants) + MatQuda per precision vs the global CPU oracle, max over ranks"}
+
+
+def ou_rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def run_c3(q, L, oracle, rank, world, grid, steps, warmup, max_over_ranks, barrier, global_X=(64, 64, 64, 128)):
+    """BASELINE configs[2]: global 64^3x128 over the ranks of `grid` (strong scaling), fp32 recon-12, resident fields."""
+    Xl = tuple(global_X[d] // grid[d] for d in range(4))
+    L.initCommsGridQuda(4, (C.c_int * 4)(*grid), None, None)
+    g = tiled_gauge(oracle, Xl, seed=1000 + rank)
+    gp = q.gauge_param(Xl, cpu_prec=4, cuda_prec=4, reconstruct=12, t_boundary=q.QUDA_PERIODIC_T)
+    L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+    del g
+    Vh = int(np.prod(Xl)) // 2
+    sp = np.random.default_rng(7 + rank).standard_normal(Vh * 24, dtype=np.float32)
+    p = q.invert_param(cuda_prec=4, cpu_prec=4)
+    fin = L.newSpinorQudaB200(q.QUDA_PARITY_SITE_SUBSET, 4)
+    fout = L.newSpinorQudaB200(q.QUDA_PARITY_SITE_SUBSET, 4)
+    L.loadSpinorQudaB200(fin, vp(sp), C.byref(p))
+    L.timeDslashQudaB200(fout, fin, C.byref(p), 0, warmup, None)
+    barrier()
+    ms = max_over_ranks(L.timeDslashQudaB200(fout, fin, C.byref(p), 0, steps, None))
+    barrier()
+    sent = C.c_double(0.0)
+    L.timeHaloQudaB200(fout, fin, C.byref(p), 0, 3, C.byref(sent))
+    barrier()
+    halo_ms = max_over_ranks(L.timeHaloQudaB200(fout, fin, C.byref(p), 0, steps, C.byref(sent)))
+    barrier()
+    L.freeSpinorQudaB200(fin)
+    L.freeSpinorQudaB200(fout)
+    peaks, _ = measured_peaks()
+    sites = Vh * world
+    res = {"grid": list(grid), "local": list(Xl), "global": list(global_X), "ms_per_hop": ms,
+           "gflops": FLOPS_PER_SITE * sites / (ms * 1e-3) / 1e9,
+           "hbm_gbs_compulsory_per_gpu": 576 * Vh / (ms * 1e-3) / 1e9,
+           "roofline_frac": 576 * Vh / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+           "effective_gbs_reference_model": 1152 * sites / (ms * 1e-3) / 1e9,
+           "halo_bytes_sent_per_gpu_per_hop": sent.value,
+           "halo_alone_ms": halo_ms,
+           "nvlink_gbs_per_gpu_each_way_halo_alone": sent.value / (halo_ms * 1e-3) / 1e9 if halo_ms > 0 else None,
+           "halo_note": "halo_alone = face pack kernel + ncclSend/Recv group of every partitioned face on the halo stream with no compute to hide "
+                        "behind; inside a hop it overlaps the interior kernel"}
+    return res
+
+
+def run_c5(q, L, oracle, du, rank, world, grid, global_X=(64, 64, 64, 128)):
+    """BASELINE configs[4]: 3-level MG-GCR twisted-mass solve on global 64^3x128, physical-point-like mu, 4^4 then 2^4 aggregates,
+    24 vectors per level; every rank draws its own weak-field links (site-local: any set of local fields is a valid global field once
+    ghost links are exchanged), point source on rank 0."""
+    Xl = tuple(global_X[d] // grid[d] for d in range(4))
+    L.initCommsGridQuda(4, (C.c_int * 4)(*grid), None, None)
+    kappa, mu = 0.1248, 0.001
+    oracle.set_dims(Xl)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711 + 31 * rank)
+    gp = q.gauge_param(Xl, cuda_prec=8, reconstruct=12, cuda_prec_sloppy=4, cuda_prec_precondition=4, t_boundary=q.QUDA_PERIODIC_T)
+    L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+    del g
+
+    def inv_param():
+        p = q.invert_param(kappa=kappa, mu=mu, cuda_prec=8, solution_type=q.QUDA_MAT_SOLUTION)
+        p.cuda_prec_sloppy = 4; p.cuda_prec_precondition = 4
+        p.solve_type = q.QUDA_DIRECT_SOLVE; p.inv_type = q.QUDA_GCR_INVERTER
+        p.gcrNkrylov = 20; p.tol = 1e-9; p.maxiter = 10000; p.reliable_delta = 1e-4
+        return p
+
+    ip = inv_param()
+    mgp = q.multigrid_param(ip, n_level=3, geo_block=((4, 4, 4, 4), (2, 2, 2, 2)), n_vec=(24, 24), nu_pre=2, nu_post=2,
+                            setup_maxiter=500, setup_tol=5e-6, run_verify=False)
+    t0 = time.perf_counter()
+    mg = L.newMultigridQuda(C.byref(mgp))
+    setup = time.perf_counter() - t0
+    V = int(np.prod(Xl))
+    b = np.zeros(V * 24)
+    if rank == 0:
+        b[0:24:2] = 1.0
+    x = np.zeros_like(b)
+    p = inv_param()
+    p.inv_type_precondition = q.QUDA_MG_INVERTER
+    p.preconditioner = mg
+    L.invertQuda(vp(x), vp(b), C.byref(p))  # warm-up (allocations)
+    p.iter = 0
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    L.destroyMultigridQuda(mg)
+    return {"grid": list(grid), "local": list(Xl), "global": list(global_X), "levels": 3, "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24],
+            "kappa": kappa, "mu": mu, "tol": 1e-9, "setup_seconds": setup, "solve_seconds": p.secs, "iterations": p.iter, "true_res": p.true_res,
+            "true_res_note": "relative L2 residual recomputed by the library with the fp64 operator whose multi-GPU parity is checked above"}
+
+
+def run_c4(q, L, oracle, X=(48, 48, 48, 96)):
+    """BASELINE configs[3]: 2-level MG on 48^3x96, 4^4 aggregates, 24 vectors -> 12^3x24 coarse lattice (41 472 sites, N = 48):
+    coarse Dslash, prolongator and restrictor against the HBM roofline, and one MG-GCR solve.  Links: weak-field block tiled along T."""
+    kappa, mu = 0.1248, 0.004
+    g = tiled_gauge(oracle, X, seed=4711, weak=True)
+    gp = q.gauge_param(X, cpu_prec=4, cuda_prec=8, reconstruct=12, cuda_prec_sloppy=4, cuda_prec_precondition=4, t_boundary=q.QUDA_PERIODIC_T)
+    L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
+    del g
+
+    def inv_param():
+        p = q.invert_param(kappa=kappa, mu=mu, cuda_prec=8, solution_type=q.QUDA_MAT_SOLUTION)
+        p.cuda_prec_sloppy = 4; p.cuda_prec_precondition = 4
+        p.solve_type = q.QUDA_DIRECT_SOLVE; p.inv_type = q.QUDA_GCR_INVERTER
+        p.gcrNkrylov = 20; p.tol = 1e-9; p.maxiter = 5000; p.reliable_delta = 1e-4
+        return p
+
+    ip = inv_param()
+    mgp = q.multigrid_param(ip, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(24,), nu_pre=2, nu_post=2, setup_maxiter=100, setup_tol=5e-6, run_verify=False)
+    t0 = time.perf_counter()
+    mg = L.newMultigridQuda(C.byref(mgp))
+    setup = time.perf_counter() - t0
+    V = int(np.prod(X))
+    b = np.zeros(V * 24); b[0:24:2] = 1.0
+    x = np.zeros_like(b)
+    p = inv_param()
+    p.inv_type_precondition = q.QUDA_MG_INVERTER
+    p.preconditioner = mg
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    peaks, _ = measured_peaks()
+    info = (C.c_int * 8)()
+    L.mgLevelInfoQudaB200(mg, 0, info)
+    sites, N = int(np.prod(info[0:4])), info[7]
+    res = {"lattice": list(X), "coarse_lattice": list(info[0:4]), "n_vec": 24, "N": N, "kappa": kappa, "mu": mu, "setup_seconds": setup, "setup_maxiter": 100,
+           "mg_gcr_2level": {"solve_seconds": p.secs, "iterations": p.iter, "true_res": p.true_res, "tol": 1e-9}}
+    ms = L.mgTimeQudaB200(mg, 1, 0, 50)
+    byts = sites * (9 * N * N * 8 + 10 * N * 8)
+    res["coarse_dslash"] = {"sites": sites, "ms": ms, "gflops": sites * ((8 + 1) * 8 * N * N - 2 * N) / ms / 1e6, "hbm_gbs": byts / ms / 1e6,
+                            "roofline_frac": byts / ms / 1e6 / peaks["hbm_gbs"], "bytes": byts}
+    for what, name in ((2, "prolong"), (3, "restrict")):
+        ms = L.mgTimeQudaB200(mg, 0, what, 20)
+        byts = V * (8 * 12 * 24 + 96)
+        res[name] = {"ms": ms, "hbm_gbs": byts / ms / 1e6, "roofline_frac": byts / ms / 1e6 / peaks["hbm_gbs"], "bytes": byts}
+    L.destroyMultigridQuda(mg)
+    return res
 
 
 def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True):
@@ -236,51 +430,71 @@ def cpu_baseline_port(oracle, g, sp, budget_s=12.0):
             "ms_per_step": best * 1e3}
 
 
-def _ref_worker(args):
-    """One process = one copy of the reference's own single-threaded tm_dslash on a 16^3x32 lattice."""
-    reps, seed = args
+_REF = {}
+
+
+def _ref_init(seed_base):
+    """Pool initializer: one process = one copy of the reference's own single-threaded CPU code with its own 32^3x64 fp32 fields
+    (the same lattice, precision and parameters as the GPU arm's step)."""
+    import multiprocessing as mp
     from tests import oracle_util as ou
+    ident = mp.current_process()._identity
+    seed = seed_base + (ident[0] if ident else 0)
     ref = ou.load_ref()
     orc = ou.load_oracle()
-    X = (16, 16, 16, 32)
-    ref.setup(X, antiperiodic=True)
-    orc.set_dims(X)
-    g = [a.astype(np.float32) for a in orc.gauge(kind=1, antiperiodic=True, seed=seed)]
-    sp = orc.drand(ref.Vh * 24, seed=seed).astype(np.float32)
-    ref.tm_dslash(g, sp, KAPPA, MU, 1, 0, 0, 0)
+    ref.setup(LOCAL_X, antiperiodic=True)
+    orc.set_dims(LOCAL_X)
+    _REF["ref"] = ref
+    _REF["g"] = [a.astype(np.float32) for a in orc.gauge(kind=1, antiperiodic=True, seed=seed)]
+    _REF["sp"] = orc.drand(ref.Vh * 24, seed=seed).astype(np.float32)
+
+
+def _ref_worker(reps):
+    ref = _REF["ref"]
     t0 = time.perf_counter()
     for _ in range(reps):
-        ref.tm_dslash(g, sp, KAPPA, MU, 1, 0, 0, 0)
+        ref.tm_dslash(_REF["g"], _REF["sp"], KAPPA, MU, 1, 0, 0, 0)
     return (time.perf_counter() - t0) / reps, ref.Vh
 
 
+def workload_config(prec=4, recon=12, world=1):
+    """`config` of the bench line: the same dict for both arms."""
+    dtype = {8: "f64", 4: "f32", 2: "i16-storage/f32-math"}[prec]
+    X = LOCAL_X
+    return {"workload": f"twisted-mass even-odd Dslash {X[0]}^3x{X[3]} per GPU, {dtype}, reconstruct-{recon} (BASELINE configs[1])",
+            "global_lattice": [X[0], X[1], X[2], X[3] * world], "partition": [1, 1, 1, world], "kappa": KAPPA, "mu": MU,
+            "l2_policy": "inputs larger than L2: gauge 403 MB + spinors 201 MB per hop vs 126 MB L2",
+            "flops_per_site": FLOPS_PER_SITE, "bytes_per_site_compulsory": BYTES_COMPULSORY[(prec, recon)]}
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU Dslash (oracle/_ref, unmodified sources) on all host cores.
-    The code is single-threaded as shipped, so one independent copy runs per core (site-parallel work
-    has no cross-core dependency) and the aggregate rate is reported."""
+    """--impl reference: the reference's own CPU Dslash (oracle/_ref, unmodified sources, tests/wilson_dslash_reference.cpp) on all
+    host cores, on the GPU arm's config: 32^3x64, fp32, kappa 0.1, mu 0.01, parity 0.  The code is single-threaded as shipped, so one
+    independent copy with its own fields runs per core (a site-parallel stencil has no cross-core dependency) and one step = every
+    copy applying tm_dslash once; the aggregate rate is reported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     from tests import oracle_util as ou
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     have_ref = ou.load_ref() is not None
     steps, warmup = args.steps, args.warmup
-    times = []
+    rates = []
+    vh = LOCAL_X[0] * LOCAL_X[1] * LOCAL_X[2] * LOCAL_X[3] // 2
     if have_ref:
-        reps = 2
-        with mp.get_context("spawn").Pool(cores) as pool:
+        with mp.get_context("spawn").Pool(cores, initializer=_ref_init, initargs=(137,)) as pool:
+            t_start = time.perf_counter()
             for s in range(warmup + steps):
-                t0 = time.perf_counter()
-                res = pool.map(_ref_worker, [(reps, 137 + i) for i in range(cores)])
+                res = pool.map(_ref_worker, [1] * cores, chunksize=1)
                 if s >= warmup:
-                    # aggregate rate of this step: all copies run concurrently
-                    times.append(sum(FLOPS_PER_SITE * vh / t for t, vh in res) / 1e9)
-                if time.perf_counter() - t0 > 60 and len(times) >= 1:
-                    break
-        gflops = float(np.mean(times))
-        kind, sample = "reference", f"{cores} concurrent copies of the reference's tm_dslash (tests/wilson_dslash_reference.cpp, -O3, fp32) on 16^3x32, {reps} reps per step"
-        vh = 16 * 16 * 16 * 32 // 2
+                    rates.append(sum(FLOPS_PER_SITE * v / t for t, v in res) / 1e9)  # all copies run concurrently
+                if time.perf_counter() - t_start > 150 and len(rates) >= 3:
+                    break   # bounded sample: keep the arm within a few minutes on slow hosts
+        gflops = float(np.mean(rates))
+        kind = "reference"
+        sample = (f"{cores} concurrent copies of the reference's tm_dslash (tests/wilson_dslash_reference.cpp, -O3, fp32), each on its own "
+                  f"32^3x64 lattice, {len(rates)} timed steps of one hop per copy")
         ms = FLOPS_PER_SITE * vh * cores / gflops / 1e6
     else:
         orc = ou.load_oracle()
@@ -288,9 +502,9 @@ def run_reference(args):
         b = cpu_baseline_port(orc, g, sp, budget_s=20.0)
         gflops, kind, sample, ms = b["value"], "port", b["sample"], b["ms_per_step"]
     line = {"impl": "reference", "metric": "tm_dslash_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
-            "steps": len(times) if times else steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": len(rates) if rates else steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "twisted-mass even-odd Dslash, fp32 (CPU verify path of the reference), lattice sample 16^3x32 per core"},
+            "config": workload_config(4, 12, args.gpus),
             "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -309,6 +523,10 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the half-precision extra measurement")
     ap.add_argument("--no-mg", action="store_true", help="skip the 3-level MG-GCR solve leg (N=1 only)")
     ap.add_argument("--mg-precond", type=int, default=4, choices=[2, 4], help="precision of the level-0 smoother operator (2 = int16, 4 = fp32)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity check (N>1)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the 64^3x128 strong-scaling legs (N>1)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 48^3x96 coarse-operator legs (N=1)")
+    ap.add_argument("--c5", choices=["auto", "on", "off"], default="auto", help="3-level MG-GCR on global 64^3x128 (auto: N=8 only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -321,10 +539,12 @@ def main():
     if world != args.gpus:
         if args.gpus != 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    import importlib
     import torch
     import torch.distributed as dist
     import quda_b200 as q
     from tests import oracle_util as ou
+    du = importlib.import_module("quda-qkxtm-multigrid_b200.dist")
 
     torch.cuda.set_device(local_rank)
     L = q.lib()
@@ -343,14 +563,26 @@ def main():
     L.initQudaMemory()
 
     oracle = ou.load_oracle()
-    X = LOCAL_X
-    g, sp = make_inputs(oracle, X, 137 + 17 * rank)
-    Vh = oracle.Vh
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- multi-GPU parity gate: nothing is timed unless the partitioned operator reproduces the global CPU oracle ----
+    parity_res = None
+    if world > 1 and not args.no_parity:
+        grids = [(1, 1, 1, world)]
+        if world >= 4:
+            grids.append(du.default_grid(world) if world == 8 else (1, 1, 2, world // 2))
+        else:
+            grids.append((1, 1, world, 1))
+        parity_res = [parity_check(q, L, oracle, du, rank, world, gr) for gr in grids]
+        L.initCommsGridQuda(4, (C.c_int * 4)(1, 1, 1, world), None, None)
+
+    X = LOCAL_X
+    g, sp = make_inputs(oracle, X, 137 + 17 * rank)
+    Vh = oracle.Vh
 
     def run_config(prec, recon, steps, warmup, with_e2e):
         gp = q.gauge_param(X, cuda_prec=prec, reconstruct=recon)
@@ -429,6 +661,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if world > 1:
+        del g
+    c3_res, c5_res, c4_res = None, None, None
+    if world > 1 and not args.no_c3 and not args.no_extra:
+        # BASELINE configs[2]: 64^3x128 over T, and over T x Z (Z alone on 2 GPUs)
+        c3_res = {"t_only": run_c3(q, L, oracle, rank, world, (1, 1, 1, world), args.steps, args.warmup, max_over_ranks, barrier)}
+        g2 = (1, 1, 2, world // 2)
+        c3_res["z_only" if world == 2 else "t_and_z"] = run_c3(q, L, oracle, rank, world, g2, args.steps, args.warmup, max_over_ranks, barrier)
+    if world > 1 and (args.c5 == "on" or (args.c5 == "auto" and world == 8)) and not args.no_extra:
+        c5_res = run_c5(q, L, oracle, du, rank, world, du.default_grid(world))
+    if world == 1 and not args.no_c4 and not args.no_mg and not args.no_extra:
+        c4_res = run_c4(q, L, oracle)
+
     ms = max_over_ranks(main_res["ms"])
     e2e_ms = max_over_ranks(main_res["e2e_ms"])
     half_ms = max_over_ranks(extra["half_r12"]["ms"]) if extra else None
@@ -454,13 +699,11 @@ def main():
         line = {
             "metric": "tm_dslash_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": {"workload": f"twisted-mass even-odd Dslash {X[0]}^3x{X[3]} per GPU, {dtype}, reconstruct-{args.recon} (BASELINE configs[1])",
-                       "global_lattice": [X[0], X[1], X[2], X[3] * world], "partition": [1, 1, 1, world], "kappa": KAPPA, "mu": MU,
-                       "l2_policy": "inputs larger than L2: gauge 403 MB + spinors 201 MB per hop vs 126 MB L2",
-                       "flops_per_site": FLOPS_PER_SITE, "bytes_per_site_compulsory": bpsite},
+            "config": workload_config(args.prec, args.recon, world),
             "effective_gbs_reference_model": BYTES_REFMODEL.get((args.prec, args.recon), 0) * sites / (ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": traffic, "peak_source": peak_kind, "kernel": "dslash_kernel<StoreS,12,TWIST_IN=false,HAS_X=false,GHOST=false>" if args.prec == 4 else "dslash_kernel"},
+                         "traffic": traffic, "traffic_source": "profiles/dslash_traffic.json (dram__bytes of one ncu --set full capture of this kernel; a constant, not measured in this run)",
+                         "peak_source": peak_kind, "kernel": "dslash_kernel<StoreS,12,TWIST_IN=false,HAS_X=false,GHOST=false>" if args.prec == 4 else "dslash_kernel"},
             "e2e": {"value": FLOPS_PER_SITE * sites / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": main_res["e2e_bytes"], "d2h_bytes_per_step": main_res["e2e_bytes"],
                     "pcie_floor_ms": main_res.get("pcie_ms"),
@@ -470,6 +713,15 @@ def main():
             "cpu_baseline": cpu,
             "extra": {},
         }
+        if parity_res:
+            line["parity"] = {"status": "green", "parity_rel_l2": {k: max(r["rel_l2"][k] for r in parity_res) for k in ("fp64", "fp32", "half")},
+                              "tolerance": {"fp64": 1e-13, "fp32": 1e-6, "half": 1e-3}, "cases": parity_res}
+        if c3_res:
+            line["extra"]["c3_64x128"] = c3_res
+        if c5_res:
+            line["extra"]["c5_mg_gcr"] = c5_res
+        if c4_res:
+            line["extra"]["c4_48x96"] = c4_res
         if mg_res:
             line["extra"]["mg_gcr_3level"] = mg_res
             line["extra"]["mg_gcr_3level_fp16_preconditioner_storage"] = mg_res_h16

@@ -37,6 +37,10 @@ void matDagMatResidentQudaB200(void *out, void *in, QudaInvertParam *param);
 double timeDslashQudaB200(void *out, void *in, QudaInvertParam *param, QudaParity parity, int niter,
                           float *per_iter_ms);
 
+/* mean device time in ms of the halo part of one hop alone on a partitioned lattice (face pack kernel + exchange of every
+ * partitioned face; no interior / boundary kernel); bytes_sent (may be NULL) receives the bytes this rank sends per hop */
+double timeHaloQudaB200(void *out, void *in, QudaInvertParam *param, QudaParity parity, int niter, double *bytes_sent);
+
 /* launch geometry of the fine Dslash kernels (the reference autotunes this, lib/tune.cpp:480-655;
  * here a fixed default is used and this knob exists for tuning runs).  Call after loadGaugeQuda. */
 /* mean ms of one batched hop over `nbatch` fp32 parity fields (multi-RHS fine Dslash: links fetched once for all members);

@@ -135,7 +135,7 @@ EXPORTS = [
     "destroyMultigridQuda", "dslashQuda", "MatQuda", "MatDagMatQuda",
     "loadCloverQuda", "freeCloverQuda", "invertMultiSrcQuda", "invertMultiShiftQuda", "cloverQuda",
     "newSpinorQudaB200", "freeSpinorQudaB200", "loadSpinorQudaB200", "saveSpinorQudaB200",
-    "dslashResidentQudaB200", "matResidentQudaB200", "matDagMatResidentQudaB200", "timeDslashQudaB200", "timeDslashBatchQudaB200",
+    "dslashResidentQudaB200", "matResidentQudaB200", "matDagMatResidentQudaB200", "timeDslashQudaB200", "timeDslashBatchQudaB200", "timeHaloQudaB200",
     "setDslashBlockSizeQudaB200", "kernelLaunchCountQudaB200", "computeStreamQudaB200", "syncQudaB200",
     "ncclUniqueIdQudaB200", "commsBootstrapQudaB200", "commDimPartitionedSetQudaB200",
     "commRankInfoQudaB200", "faceIndexMapQudaB200",
@@ -190,6 +190,8 @@ def lib():
     L.timeDslashQudaB200.restype = _d
     L.timeDslashBatchQudaB200.argtypes = [IP, _i, _i, _i, C.POINTER(_d)]
     L.timeDslashBatchQudaB200.restype = _d
+    L.timeHaloQudaB200.argtypes = [_p, _p, IP, _i, _i, C.POINTER(_d)]
+    L.timeHaloQudaB200.restype = _d
     L.setDslashBlockSizeQudaB200.argtypes = [_i]
     L.kernelLaunchCountQudaB200.restype = C.c_longlong
     L.computeStreamQudaB200.restype = _p

@@ -30,6 +30,8 @@ CoarseOperator::~CoarseOperator() {
   if (Xinv) cudaFree(Xinv);
   if (Y16) cudaFree(Y16);
   if (Xinv16) cudaFree(Xinv16);
+  if (Yhat) cudaFree(Yhat);
+  if (Yhat16) cudaFree(Yhat16);
   if (Ymma) cudaFree(Ymma);
   if (Xinv_mma) cudaFree(Xinv_mma);
   if (nbr) cudaFree(nbr);
@@ -262,15 +264,21 @@ void CoarseOperator::enable_half_links() {
     if (!Xinv16) QB_CUDA(cudaMalloc((void **)&Xinv16, nx * sizeof(uint2)));
     links_to_half_kernel<<<(unsigned)div_up((long)nx, 256), 256, 0, rt().compute>>>((uint2 *)Xinv16, (const float4 *)Xinv, nx);
   }
+  if (Yhat) {
+    if (!Yhat16) QB_CUDA(cudaMalloc((void **)&Yhat16, ny * sizeof(uint2)));
+    links_to_half_kernel<<<(unsigned)div_up((long)ny, 256), 256, 0, rt().compute>>>((uint2 *)Yhat16, (const float4 *)Yhat, ny);
+  }
   QB_CHECK_LAUNCH();
 }
 
 void coarse_apply(const CoarseApplyArgs &a) {
   const CoarseOperator &op = *a.op;
   CoarseKernelArgs k;
-  k.Y = (const float4 *)op.Y; k.Xinv = (const float4 *)op.Xinv;
-  const bool h16 = op.Y16 && (!a.use_xinv || op.Xinv16) && !a.force_fp32;
-  k.Y16 = h16 ? (const uint2 *)op.Y16 : nullptr; k.Xinv16 = h16 ? (const uint2 *)op.Xinv16 : nullptr;
+  if (a.use_yhat && !op.Yhat) QB_ERROR("coarse_apply: Yhat has not been computed");
+  k.Y = (const float4 *)(a.use_yhat ? op.Yhat : op.Y); k.Xinv = (const float4 *)op.Xinv;
+  const void *y16 = a.use_yhat ? op.Yhat16 : op.Y16;
+  const bool h16 = y16 && (!a.use_xinv || op.Xinv16) && !a.force_fp32;
+  k.Y16 = h16 ? (const uint2 *)y16 : nullptr; k.Xinv16 = h16 ? (const uint2 *)op.Xinv16 : nullptr;
   k.out = (float4 *)a.out; k.in_hop = (const float4 *)a.in_hop; k.in_diag = (const float4 *)a.in_diag; k.xpay = (const float4 *)a.xpay;
   for (int p = 0; p < 2; p++) { k.out_poff[p] = a.out_poff[p]; k.hop_poff[p] = a.hop_poff[p]; k.diag_poff[p] = a.diag_poff[p]; k.xpay_poff[p] = a.xpay_poff[p]; }
   for (int d = 0; d < 4; d++) k.X[d] = op.geom.X[d];
@@ -407,6 +415,69 @@ void CoarseOperator::compute_xinv() {
 }
 
 // -----------------------------------------------------------------------------------------------------
+// Yhat_d(x) = Xinv(x) L_d(x), d < 8; slot 8 = identity.  One CTA per (site, d): both N x N matrices staged in shared memory
+// as [row][col], thread = output element.  8 N^3 flops per (site, d): milliseconds once per setup.
+// -----------------------------------------------------------------------------------------------------
+template <int N> __global__ void __launch_bounds__(256) yhat_kernel(float4 *Yhat, const float4 *Y, const float4 *Xinv) {
+  constexpr int NRP = N / 2;
+  extern __shared__ float2 smem[];
+  float2 *A = smem;          // Xinv [row][col]
+  float2 *B = smem + N * N;  // Y_d  [row][col]
+  const long site = blockIdx.x;
+  const int d = blockIdx.y;
+  float2 *dst = (float2 *)(Yhat + ((size_t)site * 9 + d) * N * NRP);
+  if (d == 8) {
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+      const int r = e / N, c = e - r * N;
+      dst[((size_t)c * NRP + (r >> 1)) * 2 + (r & 1)] = make_float2(r == c ? 1.f : 0.f, 0.f);
+    }
+    return;
+  }
+  const float4 *xs = Xinv + (size_t)site * N * NRP, *ys = Y + ((size_t)site * 9 + d) * N * NRP;
+  for (int e = threadIdx.x; e < N * NRP; e += blockDim.x) {
+    const int c = e / NRP, rp = e - c * NRP;
+    const float4 a = xs[e], b = ys[e];
+    A[(2 * rp) * N + c] = make_float2(a.x, a.y); A[(2 * rp + 1) * N + c] = make_float2(a.z, a.w);
+    B[(2 * rp) * N + c] = make_float2(b.x, b.y); B[(2 * rp + 1) * N + c] = make_float2(b.z, b.w);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int c = e / N, r = e - c * N;   // consecutive threads: consecutive rows of one column (contiguous stores)
+    cplx<float> acc(0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < N; k++) {
+      const float2 a = A[r * N + k], b = B[k * N + c];
+      cmac(acc, cplx<float>(a.x, a.y), cplx<float>(b.x, b.y));
+    }
+    dst[((size_t)c * NRP + (r >> 1)) * 2 + (r & 1)] = make_float2(acc.re, acc.im);
+  }
+}
+
+template <int N> static void launch_yhat(float *Yhat, const float *Y, const float *Xinv, long nsites) {
+  const size_t sm = (size_t)2 * N * N * sizeof(float2);
+  QB_CUDA(cudaFuncSetAttribute(yhat_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  yhat_kernel<N><<<dim3((unsigned)nsites, 9), 256, sm, rt().compute>>>((float4 *)Yhat, (const float4 *)Y, (const float4 *)Xinv);
+  QB_CHECK_LAUNCH();
+}
+
+void CoarseOperator::compute_yhat() {
+  if (!Xinv) compute_xinv();
+  if (!Yhat) QB_CUDA(cudaMalloc((void **)&Yhat, link_bytes()));
+  switch (N) {
+    case 4: launch_yhat<4>(Yhat, Y, Xinv, geom.V()); break;
+    case 8: launch_yhat<8>(Yhat, Y, Xinv, geom.V()); break;
+    case 12: launch_yhat<12>(Yhat, Y, Xinv, geom.V()); break;
+    case 16: launch_yhat<16>(Yhat, Y, Xinv, geom.V()); break;
+    case 24: launch_yhat<24>(Yhat, Y, Xinv, geom.V()); break;
+    case 32: launch_yhat<32>(Yhat, Y, Xinv, geom.V()); break;
+    case 40: launch_yhat<40>(Yhat, Y, Xinv, geom.V()); break;
+    case 48: launch_yhat<48>(Yhat, Y, Xinv, geom.V()); break;
+    case 64: launch_yhat<64>(Yhat, Y, Xinv, geom.V()); break;
+    default: QB_ERROR("Yhat for n_vec = %d is not instantiated", nvec);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------
 // DiracCoarse
 // -----------------------------------------------------------------------------------------------------
 static void field_offsets(long *poff, const SpinorField &f, int parity_of_single) {
@@ -479,6 +550,22 @@ void DiracCoarse::M(SpinorField &out, const SpinorField &in) const {
   // symmetric even-odd Schur complement: out = in - Xinv_p Y_pq Xinv_q Y_qp in
   if (in.nparity != 1 || out.nparity != 1) QB_ERROR("DiracCoarsePC::M needs single-parity fields");
   const int p = p_parity(), q = 1 - p;
+  if (op->Yhat) {
+    // out = in - Yhat_pq Yhat_qp in: two launches, no separate Xinv pass (DiracCoarsePC::M, lib/dirac_coarse.cpp:245-283)
+    SpinorField &t = ensure_tmp(tmp1, in);
+    CoarseApplyArgs a{};
+    a.op = op.get(); a.out = (float *)t.v; a.in_hop = (const float *)in.v;
+    field_offsets(a.out_poff, t, q); field_offsets(a.hop_poff, in, p);
+    a.parity = q; a.use_y = true; a.use_yhat = true; a.a = 1.f; a.b = 0.f;
+    coarse_apply(a);
+    CoarseApplyArgs b{};
+    b.op = op.get(); b.out = (float *)out.v; b.in_hop = (const float *)t.v; b.xpay = (const float *)in.v;
+    field_offsets(b.out_poff, out, p); field_offsets(b.hop_poff, t, q); field_offsets(b.xpay_poff, in, p);
+    b.parity = p; b.use_y = true; b.use_yhat = true; b.a = -1.f; b.b = 1.f;
+    coarse_apply(b);
+    flops += 2ll * 8 * 8 * op->N * op->N * op->geom.Vh;
+    return;
+  }
   SpinorField &t1 = ensure_tmp(tmp1, in), &t2 = ensure_tmp(tmp2, in);
   Dslash(t1, in, q);
   CloverInv(t2, t1, q);
@@ -523,6 +610,19 @@ void DiracCoarse::reconstruct(SpinorField &x, const SpinorField &b, SolutionType
   CloverInv(xq, t1, q);
 }
 
-void DiracCoarse::create_coarse_op(CoarseOperator &coarse, const Transfer &T) const { build_coarse_from_coarse(coarse, T, *op); }
+void DiracCoarse::create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned) const {
+  if (preconditioned && !op->Yhat) op->compute_yhat();
+  build_coarse_from_coarse(coarse, T, *op, preconditioned);
+}
+
+// X^-1 on every site of a full field
+void DiracCoarse::DiagInv(SpinorField &out, const SpinorField &in) const {
+  if (in.nparity != 2 || out.nparity != 2) QB_ERROR("DiracCoarse::DiagInv needs full fields");
+  CoarseApplyArgs a{};
+  a.op = op.get(); a.out = (float *)out.v; a.in_diag = (const float *)in.v;
+  field_offsets(a.out_poff, out, 0); field_offsets(a.diag_poff, in, 0);
+  a.parity = -1; a.use_xinv = true; a.a = 1.f;
+  coarse_apply(a);
+}
 
 }  // namespace qb

@@ -11,6 +11,7 @@
 //     M_c = R M P   holds exactly (up to rounding) -- checked by tests (the identity of MG::verify,
 // lib/multigrid.cpp:372-486).  The -kappa of the reference's  X - kappa * sum Y  is folded into the links.
 #pragma once
+#include <complex>
 #include <memory>
 #include "dirac.h"
 #include "transfer.h"
@@ -25,6 +26,14 @@ struct CoarseOperator {
   float *Xinv = nullptr;  // [V][N][N/2] float4, inverse of the site-diagonal block L_8 (for even-odd preconditioning)
   void *Y16 = nullptr, *Xinv16 = nullptr;   // optional fp16 copies used by the single-RHS kernel (enable_half_links)
   void enable_half_links();
+  // Preconditioned links Yhat_d(x) = Xinv(x) L_d(x), d < 8, same record layout as Y with the identity in slot 8
+  // (createYpreconditioned, lib/coarse_op.cuh:1217-1283; here every link sits on its OUTPUT site, so the backward links need no
+  // Xinv of a neighbour and no ghost exchange).  Two uses: the even-odd operator 1 - Yhat_pq Yhat_qp in two launches instead of four,
+  // and the preconditioned coarsening of this level: the Galerkin product of Xinv M = 1 + sum_d Yhat_d (DiracCoarsePC::createCoarseOp,
+  // lib/dirac_coarse.cpp:377-380).
+  float *Yhat = nullptr;
+  void *Yhat16 = nullptr;
+  void compute_yhat();
   // halo buffers of coarse spinors for partitioned dimensions: [d][dir] -> [parity][plane N/2][faceVh] float4
   // send[d][0] = my slice x_d = 0 (goes backward), send[d][1] = my slice x_d = X_d - 1 (goes forward);
   // recv[d][0] = from the backward neighbour, recv[d][1] = from the forward neighbour (alias of send in self-exchange mode)
@@ -48,7 +57,10 @@ struct CoarseOperator {
 // clover_site: site-major fp32 packed clover term [V][72] (nullptr: the site-local term is 1 + i a gamma5)
 void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
                             const float *clover_site = nullptr);
-void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine);
+// preconditioned = true: coarsen Xinv M (the links Yhat of `fine`) instead of M
+void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine, bool preconditioned = false);
+// rows of chirality 0 / 1 of every link matrix (slots 0..8) times c0 / c1: turns R M P into R A^-1 M P when A is a constant per chirality
+void scale_coarse_rows(CoarseOperator &op, std::complex<double> c0, std::complex<double> c1);
 // tensor-core variant of build_coarse_from_fine (coarse_op_mma.cu); out.Y allocated and zeroed
 bool galerkin_mma_supported(const Transfer &T);
 void build_coarse_from_fine_mma(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
@@ -78,7 +90,8 @@ class DiracCoarse : public Dirac {
   void M(SpinorField &out, const SpinorField &in) const override;
   void prepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b, SolutionType sol_type) const override;
   void reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const override;
-  void create_coarse_op(CoarseOperator &coarse, const Transfer &T) const override;
+  void create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned = false) const override;
+  void DiagInv(SpinorField &out, const SpinorField &in) const override;
   int p_parity() const { return (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1; }
 };
 
@@ -96,6 +109,7 @@ struct CoarseApplyArgs {
   bool use_y, use_x, use_xinv;
   float a, b;
   bool force_fp32 = false;   // ignore the fp16 link copies (residual operator of the K-cycle, verify)
+  bool use_yhat = false;     // hopping term from Yhat = Xinv Y instead of Y
 };
 void coarse_apply(const CoarseApplyArgs &args);
 

@@ -399,22 +399,50 @@ void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeF
     if (ug[d]) QB_CUDA(cudaFree(ug[d]));
 }
 
-void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine) {
+void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine, bool preconditioned) {
   if (T.Nf != fine.N || T.fine.Vh != fine.geom.Vh) QB_ERROR("build_coarse_from_coarse: transfer does not match the fine coarse-operator");
+  if (preconditioned && !fine.Yhat) QB_ERROR("build_coarse_from_coarse: preconditioned coarsening needs the Yhat links of the fine level");
   out.allocate(T.coarse, T.nvec);
   GalerkinArgs a{};
   fill_transfer_args(a, T);
-  a.Yc = (float4 *)out.Y; a.U = nullptr; a.Yf = (const float4 *)fine.Y;
+  // preconditioned: the stencil 1 + sum_d Yhat_d of Xinv M (slot 8 of Yhat holds the identity), same kernel
+  a.Yc = (float4 *)out.Y; a.U = nullptr; a.Yf = (const float4 *)(preconditioned ? fine.Yhat : fine.Y);
   launch_galerkin<1>(a, T.coarse.V());
   QB_CUDA(cudaStreamSynchronize(rt().compute));
 }
 
-void DiracTM::create_coarse_op(CoarseOperator &coarse, const Transfer &T) const {
-  if (pc) QB_ERROR("coarsening of the even-odd preconditioned operator is not implemented: coarsen the full operator (coarse_grid_solution_type = QUDA_MAT_SOLUTION)");
+// rows of chirality S (r / nvec) of all nine matrices of a site times c[S]
+__global__ void scale_rows_kernel(float2 *Y, size_t n, int N, int nvec, float2 c0, float2 c1) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = (int)(((i >> 1) % (N / 2)) * 2 + (i & 1));   // element index = ((.. * N + col) * N/2 + rp) * 2 + (r & 1)
+  const float2 c = r < nvec ? c0 : c1, v = Y[i];
+  Y[i] = make_float2(c.x * v.x - c.y * v.y, c.x * v.y + c.y * v.x);
+}
+
+void scale_coarse_rows(CoarseOperator &op, std::complex<double> c0, std::complex<double> c1) {
+  const size_t n = (size_t)op.geom.V() * 9 * op.N * op.N;
+  scale_rows_kernel<<<(unsigned)div_up((long)n, 256), 256, 0, rt().compute>>>((float2 *)op.Y, n, op.N, op.nvec, make_float2((float)c0.real(), (float)c0.imag()),
+                                                                            make_float2((float)c1.real(), (float)c1.imag()));
+  QB_CHECK_LAUNCH();
+}
+
+// `this` is the full operator of the level.  preconditioned: the coarse links of A^-1 M = 1 - kappa A^-1 D, the operator whose even-odd
+// Schur complement is the symmetric preconditioned one (the reference gets there through AV = A^-1 V and bidirectional links,
+// lib/coarse_op.cuh:202-224, :1349-1440, called from DiracTwistedMassPC::createCoarseOp, lib/dirac_twisted_mass.cpp:580).  For twisted
+// mass A = 1 + i a gamma5 is a constant per chirality and V is chirality-blocked, so  V^dag A^-1 M V = A_c^-1 (V^dag M V):  the rows of
+// chirality +- of the ordinary Galerkin links get the factor 1 / (1 +- i a) -- exact, and the tensor-core build is reused as it is.
+void DiracTM::create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned) const {
+  if (pc) QB_ERROR("create_coarse_op is called on the full operator of the level (preconditioned = true selects the coarsening of A^-1 M)");
   if (dagger) QB_ERROR("create_coarse_op: operator must not be daggered");
+  if (preconditioned && clover) QB_ERROR("preconditioned coarsening (coarse_grid_solution_type = QUDA_MATPC_SOLUTION) with a clover term is not implemented: use QUDA_MAT_SOLUTION");
   float *cs = clover ? clover->site_major_f32() : nullptr;
   build_coarse_from_fine(coarse, T, *gauge, lat->geom, kappa, flavor ? twist_a() : 0.0, cs);
   if (cs) pool_free(cs);
+  if (preconditioned && flavor) {
+    const std::complex<double> one(1.0, 0.0), ia(0.0, twist_a());
+    scale_coarse_rows(coarse, one / (one + ia), one / (one - ia));
+  }
 }
 
 }  // namespace qb

@@ -116,6 +116,9 @@ void comm_set_grid(const int *dims, int (*func)(const int *, void *), void *fdat
             found = true;
           }
   if (!found) QB_ERROR("rank %d not found in the rank map", r.rank);
+  // the grid may be set again (another decomposition of the same ranks, before the next loadGaugeQuda): with real ranks the
+  // partitioned dimensions are exactly those of the grid
+  if (r.size > 1) r.part_mask = 0;
   for (int d = 0; d < 4; d++)
     if (dims[d] > 1) r.part_mask |= 1 << d;
   r.grid_set = true;

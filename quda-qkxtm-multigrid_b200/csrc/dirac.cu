@@ -4,6 +4,7 @@
 // composite below is issued as ONE fused hop kernel where the reference needs a hop plus separate
 // twist / xpay kernels.
 #include "dirac.h"
+#include "blas.h"
 
 namespace qb {
 
@@ -20,7 +21,24 @@ void Dirac::MdagM(SpinorField &out, const SpinorField &in) const {
   Mdag(out, *t);
 }
 
-void Dirac::create_coarse_op(CoarseOperator &, const Transfer &) const { QB_ERROR("create_coarse_op not implemented for this operator"); }
+void Dirac::create_coarse_op(CoarseOperator &, const Transfer &, bool) const { QB_ERROR("create_coarse_op not implemented for this operator"); }
+void Dirac::DiagInv(SpinorField &, const SpinorField &) const { QB_ERROR("DiagInv not implemented for this operator"); }
+
+// A^-1 on every site of the field (full or single parity); with a clover term (C + i a gamma5)^-1 parity by parity
+void DiracTM::DiagInv(SpinorField &out, const SpinorField &in) const {
+  if (flavor == 2) QB_ERROR("DiagInv: the non-degenerate doublet is not supported");
+  if (clover) {
+    if (in.nparity != 2) QB_ERROR("DiagInv with a clover term needs a full field");
+    for (int p = 0; p < 2; p++) {
+      SpinorField o, i;
+      out.view_parity(o, p); in.view_parity(i, p);
+      CloverTwist(o, i, p, true);
+    }
+    return;
+  }
+  if (flavor == 0) { if (out.v != in.v) blas::copy(out, in); return; }
+  TwistInv(out, in);
+}
 
 DiracTM::DiracTM(Lattice *lat_, const GaugeField *gauge_, double kappa_, double mu_, int flavor_, bool pc_, int matpc_, bool dagger_)
     : lat(lat_), gauge(gauge_), gauge_vec(nullptr), kappa(kappa_), mu(mu_), flavor(flavor_), pc(pc_), matpc_type(matpc_) {

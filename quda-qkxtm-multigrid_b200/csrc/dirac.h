@@ -40,8 +40,13 @@ class Dirac {
   // x, b: full fields.  On return src/sol are (views of) the fields the solver works on.
   virtual void prepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b, SolutionType sol_type) const = 0;
   virtual void reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const = 0;
-  // build the coarse operator of this operator through the transfer T (multigrid setup)
-  virtual void create_coarse_op(CoarseOperator &coarse, const Transfer &T) const;
+  // build the coarse operator of this operator through the transfer T (multigrid setup).  preconditioned = true: the Galerkin product
+  // of S^-1 M (S = site-diagonal term: A on the fine grid, X on a coarse grid) whose even-odd Schur complement is the symmetric
+  // preconditioned operator -- what Dirac*PC::createCoarseOp builds in the reference (lib/dirac_twisted_mass.cpp:580,
+  // lib/dirac_coarse.cpp:377, lib/coarse_op.cuh:1349-1440)
+  virtual void create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned = false) const;
+  // out = S^-1 in on every site of a full or parity field (S as above)
+  virtual void DiagInv(SpinorField &out, const SpinorField &in) const;
 };
 
 // Wilson and degenerate twisted-mass operator (lib/dirac_wilson.cpp, lib/dirac_twisted_mass.cpp)
@@ -91,7 +96,8 @@ class DiracTM : public Dirac {
   void M(SpinorField &out, const SpinorField &in) const override;
   void prepare(SpinorField &src, SpinorField &sol, SpinorField &x, SpinorField &b, SolutionType sol_type) const override;
   void reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const override;
-  void create_coarse_op(CoarseOperator &coarse, const Transfer &T) const override;
+  void create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned = false) const override;
+  void DiagInv(SpinorField &out, const SpinorField &in) const override;
 
  private:
   // non-degenerate doublet (wilson_dslash_reference.cpp:412-587; dirac_twisted_mass.cpp handles it through the same class)

@@ -16,6 +16,9 @@
 namespace qb {
 
 static int prec_index(Prec p) { return p == PREC_DOUBLE ? 0 : (p == PREC_SINGLE ? 1 : 2); }
+// measurement hook (timeHaloQudaB200): on partitioned lattices run only pack + exchange of a hop, no interior / boundary kernel
+static bool g_halo_only = false;
+void set_halo_only(bool on) { g_halo_only = on; }
 static int prec_store_bytes(Prec p) { return p == PREC_HALF ? 2 : (int)p; }
 
 void Lattice::init(const int *X, int t_boundary_sign, double anisotropy) {
@@ -230,6 +233,11 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
 
   const int np = parity;
   DslashParam pb = p;
+  if (g_halo_only) {
+    QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
+    QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
+    return;
+  }
   if (lat.n_boundary[np]) {
     pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
     launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, r.halo);

@@ -140,6 +140,7 @@ void mass_rescale_out(SpinorField &out, const QudaInvertParam *p, bool pc, bool 
 
 // accessors used by solver / multigrid glue
 namespace qb {
+void set_halo_only(bool on);  // dslash_host.cu
 Lattice &global_lattice() { return G.lat; }
 const GaugeField *global_gauge(Prec prec) { return pick_gauge(prec); }
 }
@@ -754,6 +755,35 @@ double timeDslashQudaB200(void *out, void *in, QudaInvertParam *p, QudaParity pa
   if (per_iter_ms)
     for (int k = 0; k < niter; k++) QB_CUDA(cudaEventElapsedTime(&per_iter_ms[k], ev[k], ev[k + 1]));
   for (auto &e : ev) cudaEventDestroy(e);
+  return (double)total / niter;
+}
+
+// mean device time (ms) of the halo part of one hop alone (face pack kernel + NCCL exchange of every partitioned face, no interior /
+// boundary kernel): what the NVLink path delivers when nothing hides it.  bytes_out (may be NULL) = bytes this rank sends per hop.
+double timeHaloQudaB200(void *out, void *in, QudaInvertParam *p, QudaParity parity, int niter, double *bytes_out) {
+  require_gauge();
+  Runtime &r = rt();
+  SpinorField &o = *(SpinorField *)out, &i = *(SpinorField *)in;
+  const Geom &g = G.lat.geom;
+  double bytes = 0;
+  for (int d = 0; d < 4; d++)
+    if (g.part[d]) bytes += 2.0 * g.faceVh[d] * (12.0 * (i.prec == PREC_HALF ? 2 : (int)i.prec) + (i.prec == PREC_HALF ? 4 : 0));
+  if (bytes_out) *bytes_out = bytes;
+  if (bytes == 0) return 0.0;
+  std::unique_ptr<DiracTM> d(make_dirac(p, true, pick_gauge(i.prec)));
+  set_halo_only(true);
+  d->Dslash(o, i, (int)parity);
+  cudaEvent_t e0, e1;
+  QB_CUDA(cudaEventCreate(&e0)); QB_CUDA(cudaEventCreate(&e1));
+  QB_CUDA(cudaStreamSynchronize(r.compute));
+  QB_CUDA(cudaEventRecord(e0, r.compute));
+  for (int k = 0; k < niter; k++) d->Dslash(o, i, (int)parity);
+  QB_CUDA(cudaEventRecord(e1, r.compute));
+  QB_CUDA(cudaStreamSynchronize(r.compute));
+  set_halo_only(false);
+  float total = 0;
+  QB_CUDA(cudaEventElapsedTime(&total, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return (double)total / niter;
 }
 
