@@ -21,6 +21,10 @@ extern "C" {
  * The lattice is the one of the gauge field loaded with loadGaugeQuda. */
 void *newSpinorQudaB200(QudaSiteSubset site_subset, QudaPrecision precision);
 void freeSpinorQudaB200(void *field);
+/* QudaInvertParam::make_resident_solution = 1 (reference include/quda.h:293-297, lib/interface_quda.cpp:2493-2508): invertQuda leaves the
+ * solution on the device and does not write h_x.  This returns that field (owned by the library; replaced by the next such solve, released by
+ * freeGaugeQuda / endQuda), NULL if there is none; use it with saveSpinorQudaB200 or the *Resident* operators below. */
+void *residentSolutionQudaB200(void);
 /* host (param->cpu_prec, dirac_order, gamma_basis) <-> resident field; mirrors the
  * cudaColorSpinorField <- cpuColorSpinorField assignment (lib/cuda_color_spinor_field.cu:513-552) */
 void loadSpinorQudaB200(void *field, const void *h_in, QudaInvertParam *param);

@@ -180,6 +180,8 @@ def lib():
     L.invertMultiSrcQuda.argtypes = [_p, _p, IP]
     L.newSpinorQudaB200.argtypes = [_i, _i]
     L.newSpinorQudaB200.restype = _p
+    L.residentSolutionQudaB200.restype = _p
+    L.residentSolutionQudaB200.argtypes = []
     L.freeSpinorQudaB200.argtypes = [_p]
     L.loadSpinorQudaB200.argtypes = [_p, _p, IP]
     L.saveSpinorQudaB200.argtypes = [_p, _p, IP]
@@ -282,9 +284,13 @@ def invert_param(kappa=0.1, mu=0.01, flavor=QUDA_TWIST_PLUS, dslash_type=QUDA_TW
 
 def multigrid_param(inv_param, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(24,), nu_pre=2, nu_post=2,
                     smoother_tol=0.25, omega=0.85, setup_maxiter=500, setup_tol=5e-6,
-                    cycle=QUDA_MG_CYCLE_RECURSIVE, generate_all_levels=True, run_verify=True):
+                    cycle=QUDA_MG_CYCLE_RECURSIVE, generate_all_levels=True, run_verify=True, solve_type=None):
     """What tests/multigrid_invert_test.cpp:161-286 (setMultigridParam) fills in.
-    `inv_param` must stay alive as long as the returned struct is used."""
+    `inv_param` must stay alive as long as the returned struct is used.
+    solve_type = the OUTER solve type the hierarchy is meant for (the test's global `solve_type`, tests/test_util.cpp:1600 defaults to
+    QUDA_DIRECT_PC_SOLVE): an even-odd outer solve injects single-parity fields into the coarse grids (multigrid_invert_test.cpp:252),
+    i.e. the preconditioned coarsening.  None = QUDA_DIRECT_SOLVE (full-field injection)."""
+    pc_inject = solve_type == QUDA_DIRECT_PC_SOLVE
     m = lib().newQudaMultigridParam()
     m.invert_param = C.pointer(inv_param)
     m.n_level = n_level
@@ -301,7 +307,7 @@ def multigrid_param(inv_param, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(24,)
         m.smoother_tol[l] = smoother_tol
         m.global_reduction[l] = QUDA_BOOLEAN_YES
         m.smoother_solve_type[l] = QUDA_DIRECT_PC_SOLVE
-        m.coarse_grid_solution_type[l] = QUDA_MAT_SOLUTION
+        m.coarse_grid_solution_type[l] = QUDA_MATPC_SOLUTION if pc_inject else QUDA_MAT_SOLUTION
         m.omega[l] = omega
         m.location[l] = QUDA_CUDA_FIELD_LOCATION
     m.smoother[n_level - 1] = QUDA_GCR_INVERTER

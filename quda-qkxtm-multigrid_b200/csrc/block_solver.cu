@@ -673,6 +673,8 @@ class BlockMG {
 bool block_mg_supported(const MG &mg, int R, int mode) {
   if (getenv("QB_BLOCK_MG") && atoi(getenv("QB_BLOCK_MG")) == 0) return false;
   if (R < 2 || R > MAXR || !mg.coarse) return false;
+  for (const MG *m = &mg; m; m = m->coarse.get())
+    if (m->pc_coarsen) return false;   // hierarchies coarsened on the even-odd system take the one-at-a-time path
   for (const MG *m = mg.coarse.get(); m; m = m->coarse.get()) {
     const DiracCoarse *dr = dynamic_cast<const DiracCoarse *>(m->matResidual), *ds = dynamic_cast<const DiracCoarse *>(m->matSmooth);
     if (!dr || !ds || !ds->pc || dr->op->geom.partitioned()) return false;

@@ -5,6 +5,7 @@
 #include <climits>
 #include <cstring>
 #include <chrono>
+#include <limits>
 #include <map>
 #include <string>
 #include <vector>
@@ -28,6 +29,7 @@ struct GaugeSet {
   std::shared_ptr<GaugeField> precise, sloppy, precondition;
   bool loaded = false;
   CloverSet clover;  // loadCloverQuda (process-global like the gauge field, interface_quda.cpp:723-900)
+  std::unique_ptr<SpinorField> solution_resident;  // make_resident_solution (solutionResident, interface_quda.cpp:2500-2508)
 } G;
 
 void require_init() {
@@ -419,6 +421,10 @@ void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
     QB_ERROR("Gauge order %d not supported (QUDA_QDP_GAUGE_ORDER, QUDA_MILC_GAUGE_ORDER, QUDA_CPS_WILSON_GAUGE_ORDER)", (int)param->gauge_order);
   if (param->t_boundary == QUDA_INVALID_T_BOUNDARY) QB_ERROR("Parameter t_boundary undefined");
   if (param->location != QUDA_CPU_FIELD_LOCATION) QB_ERROR("loadGaugeQuda expects a host gauge field");
+  // interface_quda.cpp:582-589: use_resident_gauge takes the device field a gauge-update routine left behind (make_resident_gauge of
+  // the force / update entry points, outside this build's scope), so there is never one to use
+  if (param->use_resident_gauge != 0 && param->use_resident_gauge != INVALID_INT)
+    QB_ERROR("No resident gauge field (use_resident_gauge = %d: this build has no gauge-update routine that could have left one; pass the host field)", param->use_resident_gauge);
   const Prec cpu_prec = to_prec(param->cpu_prec, "cpu_prec");
   const Prec prec = to_prec(param->cuda_prec, "cuda_prec");
   if (param->reconstruct == QUDA_RECONSTRUCT_INVALID) QB_ERROR("Parameter reconstruct undefined");
@@ -464,6 +470,7 @@ void freeGaugeQuda(void) {
   QB_CUDA(cudaDeviceSynchronize());
   pool_clear();
   G.clover.release();
+  G.solution_resident.reset();
   G.precise.reset(); G.sloppy.reset(); G.precondition.reset();
   G.lat.release();
   pool_release_all();
@@ -517,17 +524,6 @@ void pipe_cleanup_c() {
   pipe_state.h2d = pipe_state.d2h = nullptr; pipe_state.ev_done = nullptr; pipe_state.ev_in.clear(); pipe_state.ev_out.clear();
 }
 
-// grid-stride 128-bit copy with four independent loads in flight per thread (host-mapped <-> device)
-__global__ void __launch_bounds__(256) pcie_copy_kernel(float4 *dst, const float4 *src, size_t n) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n; i += 4 * stride) {
-    const float4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], e = src[i + 3 * stride];
-    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = e;
-  }
-  for (; i < n; i += stride) dst[i] = src[i];
-}
-
 static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaParity parity, SpinorField &in, SpinorField &out) {
   const Geom &g = G.lat.geom;
   if (g.part[0] || g.part[1] || g.part[2] || g.part[3]) return false;
@@ -540,8 +536,9 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   // Measured with CUDA events on B200 (QB_PIPE_TRACE=1, 32^3x64 fp32, link floor 2.04 ms): every extra copy costs the H2D stream ~30 us,
   // the first D2H cannot start before the first three slabs are in, and the D2H stream runs one slab behind the H2D stream.  So: few
   // slabs, thin ones at the head (the first results leave early) and tapering ones at the end (little is left when the last input lands).
-  const int want = getenv("QB_PIPE_CHUNKS") ? atoi(getenv("QB_PIPE_CHUNKS")) : 13;   // 9 / 11 / 13 slabs: 3.06 / 2.82 / 2.73 ms (uniform 16: 2.88 ms)
-  const bool tapered = !(getenv("QB_PIPE_UNIFORM") && atoi(getenv("QB_PIPE_UNIFORM"))) && T >= 32 && want >= 8;
+  static const int want = getenv("QB_PIPE_CHUNKS") ? atoi(getenv("QB_PIPE_CHUNKS")) : 13;   // 9 / 11 / 13 slabs: 3.06 / 2.82 / 2.73 ms (uniform 16: 2.88 ms)
+  static const bool uniform = getenv("QB_PIPE_UNIFORM") && atoi(getenv("QB_PIPE_UNIFORM"));
+  const bool tapered = !uniform && T >= 32 && want >= 8;
   std::vector<int> tslices;   // time slices per slab
   if (tapered) {
     const int head = std::max(1, T / 32);
@@ -584,44 +581,6 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   QB_CUDA(cudaEventRecord(pipe_state.ev_done, r.compute));
   QB_CUDA(cudaStreamWaitEvent(pipe_state.h2d, pipe_state.ev_done, 0));
   // H2D stream: nothing but back-to-back copies (the reorder kernels run on the compute stream), last slab first
-  // Zero-copy variant (QB_PIPE_ZEROCOPY=1, pinned + mapped caller buffers only): the reorder kernels read the input from and write the
-  // result to host memory directly over PCIe (no copy engine, no staging, no per-copy cost); import kernels on the H2D stream, export
-  // kernels on the D2H stream so that the two directions overlap
-  if (getenv("QB_PIPE_ZEROCOPY") && atoi(getenv("QB_PIPE_ZEROCOPY"))) {
-    cudaPointerAttributes ai{}, ao{};
-    if (cudaPointerGetAttributes(&ai, h_in) == cudaSuccess && cudaPointerGetAttributes(&ao, h_out) == cudaSuccess && ai.type == cudaMemoryTypeHost &&
-        ao.type == cudaMemoryTypeHost && ai.devicePointer && ao.devicePointer) {
-      std::vector<int> arr;
-      arr.push_back(nchunk - 1);
-      for (int c = 0; c < nchunk - 1; c++) arr.push_back(c);
-      // coalesced 128-bit copy kernels instead of the copy engines: a launch costs ~5 us where a cudaMemcpyAsync costs the stream ~30 us
-      // (reading the host array with the reorder kernel's 96-byte-per-thread pattern directly is 13x slower: 36.6 ms)
-      for (int c : arr) {
-        const size_t n16 = (size_t)count[c] * site_bytes / 16;
-        pcie_copy_kernel<<<64, 256, 0, pipe_state.h2d>>>((float4 *)(stage_in + begin[c] * site_bytes), (const float4 *)((const char *)ai.devicePointer + begin[c] * site_bytes), n16);
-        QB_CUDA(cudaEventRecord(pipe_state.ev_in[c], pipe_state.h2d));
-      }
-      auto proc = [&](int k) {
-        d->DslashRange(out, in, (int)parity, (int)begin[k], (int)count[k], r.compute);
-        export_spinor_range(stage_out, out, hp, basis, order, begin[k], count[k], r.compute);
-        QB_CUDA(cudaEventRecord(pipe_state.ev_out[k], r.compute));
-        QB_CUDA(cudaStreamWaitEvent(pipe_state.d2h, pipe_state.ev_out[k], 0));
-        const size_t n16 = (size_t)count[k] * site_bytes / 16;
-        pcie_copy_kernel<<<64, 256, 0, pipe_state.d2h>>>((float4 *)((char *)ao.devicePointer + begin[k] * site_bytes), (const float4 *)(stage_out + begin[k] * site_bytes), n16);
-      };
-      for (size_t a = 0; a < arr.size(); a++) {
-        QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[arr[a]], 0));
-        import_spinor_range(in, stage_in, hp, basis, order, begin[arr[a]], count[arr[a]], r.compute);
-        if (a >= 2) proc(arr[a] - 1);
-      }
-      proc(nchunk - 2);
-      proc(nchunk - 1);
-      QB_CUDA(cudaStreamSynchronize(pipe_state.d2h));
-      QB_CUDA(cudaStreamSynchronize(r.compute));
-      return true;
-    }
-    cudaGetLastError();   // not mapped host memory: staged copies below
-  }
   static const bool trace = getenv("QB_PIPE_TRACE") && atoi(getenv("QB_PIPE_TRACE"));
   cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};   // h2d begin / end, d2h first copy begin / last copy end
   if (trace) for (auto &e : tr) QB_CUDA(cudaEventCreate(&e));
@@ -713,6 +672,9 @@ void *newSpinorQudaB200(QudaSiteSubset site_subset, QudaPrecision precision) {
   return new SpinorField(G.lat.geom.Vh, (int)site_subset, to_prec(precision, "precision"));
 }
 void freeSpinorQudaB200(void *f) { delete (SpinorField *)f; }
+// solution left on the device by the last invertQuda with make_resident_solution = 1 (owned by the library until the next such solve,
+// freeGaugeQuda or endQuda); NULL if there is none.  Usable with saveSpinorQudaB200 / the *Resident* operators.
+void *residentSolutionQudaB200(void) { return G.solution_resident.get(); }
 void loadSpinorQudaB200(void *f, const void *h_in, QudaInvertParam *p) {
   require_gauge();
   load_host_spinor(*(SpinorField *)f, h_in, p);
@@ -940,8 +902,21 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
   if (pc_solution && !pc_solve) QB_ERROR("Preconditioned (PC) solution_type requires a PC solve_type");
   if (!mat_solution && !pc_solution && pc_solve) QB_ERROR("Unpreconditioned MATDAG_MAT solution_type requires an unpreconditioned solve_type");
   if (param->inv_type_precondition == QUDA_MG_INVERTER && (!direct_solve || !mat_solution)) QB_ERROR("Multigrid preconditioning only supported for direct solves");
+  if (param->inv_type_precondition == QUDA_MG_INVERTER && pc_solve) {
+    // the cycle then runs on single-parity fields of the even-odd system: the hierarchy must have been built for it
+    // (coarse_grid_solution_type = QUDA_MATPC_SOLUTION, same symmetric matpc_type; multigrid.cpp:494-505)
+    if (!param->preconditioner) QB_ERROR("inv_type_precondition is QUDA_MG_INVERTER but `preconditioner` is not set (call newMultigridQuda first)");
+    const MultigridSolver *ms = (const MultigridSolver *)param->preconditioner;
+    if (!ms->mp.level[0].coarse_pc) QB_ERROR("Unsupported solution type combination: an even-odd preconditioned outer solve needs a multigrid built with coarse_grid_solution_type = QUDA_MATPC_SOLUTION");
+    if ((int)param->matpc_type != (int)QUDA_MATPC_EVEN_EVEN && (int)param->matpc_type != (int)QUDA_MATPC_ODD_ODD) QB_ERROR("Multigrid on the even-odd system needs a symmetric matpc_type");
+    if (ms->diracSmooth->matpc() != (int)param->matpc_type) QB_ERROR("matpc_type of the solve (%d) differs from the one the multigrid was built with", (int)param->matpc_type);
+  }
   if (!mat_solution && direct_solve) QB_ERROR("Two-pass MATDAG_MAT solves with a direct solver are not implemented; use a NORMOP solve_type");
 
+  // stopping criterion: the L2 relative residual only (invert_quda.h:201-240 maps residual_type onto the solvers' convergence test);
+  // anything else would silently change the stopping semantics, so it is refused
+  if ((int)param->residual_type != (int)QUDA_L2_RELATIVE_RESIDUAL && (int)param->residual_type != INVALID_INT)
+    QB_ERROR("residual_type %d is not supported: this build stops on QUDA_L2_RELATIVE_RESIDUAL only (no heavy-quark or absolute residual)", (int)param->residual_type);
   SolverParam sp;
   fill_solver_param(sp, param);
   param->secs = 0; param->gflops = 0; param->iter = 0;
@@ -1020,10 +995,19 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
   if (K) ((MultigridSolver *)param->preconditioner)->mg->print_profile();
   d->reconstruct(*x, *b, st);
   if (param->solver_normalization == QUDA_SOURCE_NORMALIZATION) blas::ax(sqrt(nb), *x);
-  save_host_spinor(hp_x, *x, param);
+  // interface_quda.cpp:2493-2508: make_resident_solution keeps the solution on the device instead of copying it to h_x; it replaces the
+  // previous resident solution and is handed out by residentSolutionQudaB200 (the reference's consumers of use_resident_solution are the
+  // force routines, interface_quda.cpp:4107-4146, 4930-4985, outside this build; invertQuda itself never reads use_resident_solution)
+  if (param->make_resident_solution == 1) {
+    QB_CUDA(cudaStreamSynchronize(r.compute));
+    G.solution_resident = std::move(x);
+  } else {
+    save_host_spinor(hp_x, *x, param);
+  }
 
   param->true_res = sp.true_res;
-  param->true_res_hq = 0.0;
+  // the heavy-quark residual is not computed (residual_type other than L2 is refused above): NaN, not a value that reads as converged
+  param->true_res_hq = std::numeric_limits<double>::quiet_NaN();
   param->iter += sp.iter;
   param->secs += sp.secs;
   const double gflops = (double)(d->flops + dS->flops + dP->flops + (double)blas::flops) * 1e-9;
@@ -1144,8 +1128,12 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
     MGLevelParam &lp = mp.level[l];
     if (mgp->smoother_solve_type[l] != QUDA_DIRECT_SOLVE && mgp->smoother_solve_type[l] != QUDA_DIRECT_PC_SOLVE)
       QB_ERROR("Unsupported smoother solve type %d on level %d", (int)mgp->smoother_solve_type[l], l);
-    if (mgp->coarse_grid_solution_type[l] == QUDA_MATPC_SOLUTION)
-      QB_ERROR("coarse_grid_solution_type = QUDA_MATPC_SOLUTION (preconditioned coarsening) is not implemented; use QUDA_MAT_SOLUTION");
+    if (mgp->coarse_grid_solution_type[l] != QUDA_MATPC_SOLUTION && mgp->coarse_grid_solution_type[l] != QUDA_MAT_SOLUTION && l < mgp->n_level - 1)
+      QB_ERROR("coarse_grid_solution_type[%d] must be QUDA_MAT_SOLUTION or QUDA_MATPC_SOLUTION", l);
+    // single-parity injection into the coarse grid = coarsening of the even-odd preconditioned operator (multigrid.cpp:145-155)
+    lp.coarse_pc = mgp->coarse_grid_solution_type[l] == QUDA_MATPC_SOLUTION;
+    if (lp.coarse_pc && mgp->smoother_solve_type[l] != QUDA_DIRECT_PC_SOLVE)
+      QB_ERROR("For this coarse grid solution type, a preconditioned smoother is required (level %d)", l);
     for (int d = 0; d < 4; d++) {
       lp.geo_bs[d] = mgp->geo_block_size[l][d];
       if (l < mp.n_level - 1 && (lp.geo_bs[d] == INVALID_INT || lp.geo_bs[d] < 1)) QB_ERROR("Parameter geo_block_size[%d][%d] undefined", l, d);

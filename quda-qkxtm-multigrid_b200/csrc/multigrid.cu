@@ -80,6 +80,7 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
     postsmoother.reset(Solver::create(param_postsmooth, ms, ms, ms));
   }
   r.reset(new_full(*matResidual));
+  pc_parity = (matSmooth->matpc() == MATPC_EVEN_EVEN || matSmooth->matpc() == MATPC_EVEN_EVEN_ASYM) ? 0 : 1;
 
   if (!last) {
     // ---- near-null vectors ----
@@ -125,16 +126,23 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
     // V holds everything the cycle needs; the near-null vectors (n_vec x 96 B/site on the fine grid) are only kept for verify()
     if (!mp.keep_null_vectors) B.clear();
 
+    // coarsening of the even-odd preconditioned system (multigrid.cpp:145-155): coarse_grid_solution_type = MATPC with an even-odd smoother
+    pc_coarsen = lp.coarse_pc && lp.smoother_pc;
+    if (lp.coarse_pc && !lp.smoother_pc) QB_ERROR("MG level %d: coarse_grid_solution_type = QUDA_MATPC_SOLUTION needs smoother_solve_type = QUDA_DIRECT_PC_SOLVE", level + 1);
+    if (pc_coarsen && (matSmooth->matpc() == MATPC_EVEN_EVEN_ASYM || matSmooth->matpc() == MATPC_ODD_ODD_ASYM))
+      QB_ERROR("Unsupported coarsening of matpc = %d (the preconditioned coarsening needs the symmetric even-odd operator, lib/coarse_op.cuh:1317)", matSmooth->matpc());
     coarse_op.reset(new CoarseOperator());
     const double tc0 = now_s();
-    matResidual->create_coarse_op(*coarse_op, *transfer);
+    if (pc_coarsen) log_msg(1, "MG level %d: coarsening the even-odd preconditioned operator (bi-directional links of S^-1 M)\n", level + 1);
+    matResidual->create_coarse_op(*coarse_op, *transfer, pc_coarsen);
     if (cp.smoother_pc) coarse_op->compute_xinv();
     if (mp.half_storage) { transfer->enable_half_v(); coarse_op->enable_half_links(); }
     QB_CUDA(cudaStreamSynchronize(rt().compute));
     log_msg(1, "MG level %d: coarse operator %d x %d x %d x %d, N = %d built in %.3f s\n", level + 1, coarse_op->geom.X[0], coarse_op->geom.X[1],
             coarse_op->geom.X[2], coarse_op->geom.X[3], coarse_op->N, now_s() - tc0);
     coarseResidual.reset(new DiracCoarse(coarse_op, false, MATPC_EVEN_EVEN));
-    coarseSmooth.reset(new DiracCoarse(coarse_op, cp.smoother_pc, MATPC_EVEN_EVEN));
+    // the even-odd systems of all levels live on the parity of the outer matpc_type (multigrid.cpp:300-309 sets the transfer's parity from it)
+    coarseSmooth.reset(new DiracCoarse(coarse_op, cp.smoother_pc, pc_parity == 0 ? MATPC_EVEN_EVEN : MATPC_ODD_ODD));
     r_coarse.reset(transfer->new_coarse_field());
     x_coarse.reset(transfer->new_coarse_field());
     coarse.reset(new MG(mp, level + 1, coarseResidual.get(), coarseSmooth.get(), Bc.empty() ? nullptr : &Bc));
@@ -154,8 +162,15 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
       param_coarse_solver.delta = 1e-8;
       param_coarse_solver.precision = param_coarse_solver.precision_sloppy = param_coarse_solver.precision_precondition = PREC_SINGLE;
       param_coarse_solver.verbosity = 0;
-      DiracMatrix mc(coarseResidual.get());
-      coarse_solver_gcr.reset(new GCR(mc, mc, mc, param_coarse_solver, coarse.get()));
+      if (cp.coarse_pc && cp.smoother_pc) {
+        // the next level injects single-parity fields into its coarse grid: its K-cycle GCR runs on the even-odd operator and the
+        // cycle below it sees single-parity fields (multigrid.cpp:250-261)
+        DiracMatrix mc(coarseSmooth.get());
+        coarse_solver_pc.reset(new PreconditionedSolver(new GCR(mc, mc, mc, param_coarse_solver, coarse.get()), coarseSmooth.get(), param_coarse_solver));
+      } else {
+        DiracMatrix mc(coarseResidual.get());
+        coarse_solver_gcr.reset(new GCR(mc, mc, mc, param_coarse_solver, coarse.get()));
+      }
     }
   }
   setup_secs = now_s() - t0;
@@ -310,8 +325,58 @@ struct Section {
   ~Section() { if (on) { cudaStreamSynchronize(rt().compute); *acc += now_s() - t0; } }
 };
 
+// The cycle on the even-odd system M_pc x = b of this level (single-parity fields; multigrid.cpp:494-560 with outer = inner =
+// QUDA_MATPC_SOLUTION).  M_pc is the Schur complement of S^-1 M, whose Galerkin product is the next level's operator: the residual
+// is restricted from this parity only, the coarse level solves its FULL system, and the correction is prolongated back to this parity.
+void MG::cycle_pc(SpinorField &x, SpinorField &b) {
+  const MGLevelParam &lp = mp.level[level];
+  ncycle++;
+  if (!matSmooth->is_pc()) QB_ERROR("MG level %d: single-parity fields need an even-odd preconditioned smoother operator", level + 1);
+  if (level == mp.n_level - 1) {  // coarsest grid: solve the even-odd system directly
+    Section s(&t_prof[0]);
+    (*presmoother)(x, b);
+    return;
+  }
+  if (!pc_coarsen) QB_ERROR("Unsupported solution type combination: single-parity fields on MG level %d need coarse_grid_solution_type = QUDA_MATPC_SOLUTION", level + 1);
+  SpinorField rp;
+  r->view_parity(rp, pc_parity);
+  if (lp.nu_pre > 0) {
+    { Section s(&t_prof[0]); (*presmoother)(x, b); }
+    Section s(&t_prof[1]);
+    matSmooth->M(rp, x);
+    blas::axpby(1.0, b, -1.0, rp);
+  } else {
+    blas::zero(x);
+    blas::copy(rp, b);
+  }
+  { Section s(&t_prof[2]); transfer->R(*r_coarse, rp, pc_parity); }
+  {
+    Section s(&t_prof[3]);
+    if (coarse_solver_pc) (*coarse_solver_pc)(*x_coarse, *r_coarse);
+    else if (coarse_solver_gcr) (*coarse_solver_gcr)(*x_coarse, *r_coarse);
+    else (*coarse)(*x_coarse, *r_coarse);
+  }
+  {
+    Section s(&t_prof[4]);
+    SpinorField *fo = &x;
+    const SpinorField *ci = x_coarse.get();
+    transfer->P_multi(&fo, &ci, 1, true, pc_parity);
+  }
+  if (lp.nu_post > 0) { Section s(&t_prof[5]); (*postsmoother)(x, b); }
+}
+
 void MG::cycle(SpinorField &x, SpinorField &b) {
   const MGLevelParam &lp = mp.level[level];
+  if (x.nparity == 1) { cycle_pc(x, b); return; }
+  if (level < mp.n_level - 1 && pc_coarsen) {
+    // full fields on a level that coarsens its even-odd system (outer MAT, inner MATPC): reduce to the even-odd system exactly,
+    // run the single-parity cycle on it, reconstruct the other parity
+    SpinorField src, sol;
+    matSmooth->prepare(src, sol, x, b, SOL_MAT);
+    cycle_pc(sol, src);
+    matSmooth->reconstruct(x, b, SOL_MAT);
+    return;
+  }
   ncycle++;
   if (level == mp.n_level - 1) {  // coarsest grid solve
     Section s(&t_prof[0]);
@@ -332,7 +397,8 @@ void MG::cycle(SpinorField &x, SpinorField &b) {
   { Section s(&t_prof[2]); transfer->R(*r_coarse, *r); }
   {
     Section s(&t_prof[3]);
-    if (coarse_solver_gcr) (*coarse_solver_gcr)(*x_coarse, *r_coarse);
+    if (coarse_solver_pc) (*coarse_solver_pc)(*x_coarse, *r_coarse);
+    else if (coarse_solver_gcr) (*coarse_solver_gcr)(*x_coarse, *r_coarse);
     else (*coarse)(*x_coarse, *r_coarse);
   }
   {  // x += P x_coarse in one pass (the prolongator adds into x: no temporary, no separate xpy)
@@ -355,7 +421,8 @@ void MG::print_profile() {
 }
 
 void MG::operator()(SpinorField &x, SpinorField &b) {
-  if (x.nparity != 2 || b.nparity != 2) QB_ERROR("MG: the multigrid cycle acts on full fields (use solve_type = QUDA_DIRECT_SOLVE for the outer solver)");
+  if (x.nparity != b.nparity) QB_ERROR("MG: solution and source must both be full or both single-parity fields");
+  if (x32 && x32->nparity != x.nparity) { x32.reset(); b32.reset(); }
   if (x.prec == PREC_SINGLE && b.prec == PREC_SINGLE) {
     cycle(x, b);  // b is only read (smoothers preserve their source)
     return;
@@ -391,7 +458,12 @@ void MG::verify(double *dev) {
   // (3) R M P eta = M_c eta
   transfer->P(*t_f, *eta);
   matResidual->M(*t_f2, *t_f);
-  transfer->R(*t_c, *t_f2);
+  if (pc_coarsen) {  // the coarse operator is the Galerkin product of S^-1 M
+    matResidual->DiagInv(*t_f, *t_f2);
+    transfer->R(*t_c, *t_f);
+  } else {
+    transfer->R(*t_c, *t_f2);
+  }
   coarseResidual->M(*t_c2, *eta);
   dev[2] = sqrt(blas::xmyNorm(*t_c2, *t_c) / blas::norm2(*t_c2));
 }

@@ -17,6 +17,9 @@ struct MGLevelParam {
   int nvec = 24;
   InverterType smoother = INV_MR;
   bool smoother_pc = true;          // smoother_solve_type == QUDA_DIRECT_PC_SOLVE
+  // coarse_grid_solution_type == QUDA_MATPC_SOLUTION: this level hands a single-parity residual of the even-odd system to the next level,
+  // whose operator is then built by preconditioned coarsening (multigrid.cpp:145-155); needs smoother_pc
+  bool coarse_pc = false;
   int nu_pre = 2, nu_post = 2;
   double smoother_tol = 0.25;
   double omega = 0.85;
@@ -52,6 +55,9 @@ class MG : public Solver {
   std::unique_ptr<DiracCoarse> coarseResidual, coarseSmooth;
   std::unique_ptr<MG> coarse;
   std::unique_ptr<Solver> coarse_solver_gcr;  // K-cycle wrapper
+  std::unique_ptr<Solver> coarse_solver_pc;   // K-cycle on the next level's even-odd system: prepare -> coarse_solver_gcr -> reconstruct
+  bool pc_coarsen = false;    // the next level's operator is the Galerkin product of S^-1 M (preconditioned coarsening)
+  int pc_parity = 0;          // parity the even-odd system of this level lives on (matpc_type of the smoother operator)
   SolverParam param_coarse_solver, param_presmooth, param_postsmooth;
   std::unique_ptr<Solver> presmoother, postsmoother;
   std::vector<std::unique_ptr<SpinorField>> B;   // near-null vectors of this level
@@ -74,6 +80,21 @@ class MG : public Solver {
   void load_vectors();
   void save_vectors();
   void cycle(SpinorField &x, SpinorField &b);
+  void cycle_pc(SpinorField &x, SpinorField &b);   // single-parity fields of the even-odd system (multigrid.cpp:494-560 with MATPC types)
+};
+
+// Solver on the even-odd system wrapped in prepare / reconstruct so that it takes full fields (PreconditionedSolver, include/invert_quda.h:598)
+class PreconditionedSolver : public Solver {
+  std::unique_ptr<Solver> solver;
+  const Dirac *dirac;
+ public:
+  PreconditionedSolver(Solver *s, const Dirac *d, SolverParam &p) : Solver(p), solver(s), dirac(d) {}
+  void operator()(SpinorField &x, SpinorField &b) override {
+    SpinorField src, sol;
+    dirac->prepare(src, sol, x, b, SOL_MAT);
+    (*solver)(sol, src);
+    dirac->reconstruct(x, b, SOL_MAT);
+  }
 };
 
 // handle returned by newMultigridQuda (multigrid_solver of interface_quda.cpp:2161-2255)

@@ -340,7 +340,9 @@ void GCR::operator()(SpinorField &x, SpinorField &b) {
       r2_old = r2;
     }
   }
-  if (total_iter > 0) blas::copy(x, *y);
+  // y carries the accumulated solution (the initial guess was moved there and x zeroed): restore it also when the guess already
+  // satisfied the tolerance and no iteration ran
+  if (total_iter > 0 || param.use_init_guess) blas::copy(x, *y);
   param.iter += total_iter;
   if (!param.is_preconditioner) {
     param.secs += now_s() - t0;

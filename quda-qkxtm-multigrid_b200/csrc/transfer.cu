@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) prolong_kernel(float4 *out, const float4 
 // per lane, shuffle tree across lanes (the reference uses cub::BlockReduce, restrictor.cu:159-237).
 template <int NKP>  // NKP = Nf/2 known at compile time (full unrolling => all V loads of a site in flight), 0 = generic
 __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V, const int *c2f, long Vh_f, long Vh_c, int Nf, int nvec,
-                                int cpc, int block_sites) {
+                                int cpc, int block_sites, int par, long in_pstride) {
   const int X = blockIdx.x;  // coarse full index
   const int lane = threadIdx.x, jp = threadIdx.y;
   const int nkp = NKP ? NKP : Nf / 2, nvh = nvec / 2;
@@ -170,13 +170,14 @@ __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V,
   for (int i = lane; i < block_sites; i += 32) {
     const int fs = c2f[(size_t)X * block_sites + i];
     const int parity = fs >= Vh_f ? 1 : 0;
+    if (par >= 0 && parity != par) continue;   // single-parity input: the other parity counts as zero
     const long cb = fs - (long)parity * Vh_f;
     if (NKP > 0) {
       // issue every load of this site before the first use: 3 * NKP independent 128-bit requests in flight per thread
       float4 f[NKP ? NKP : 1], w0[NKP ? NKP : 1], w1[NKP ? NKP : 1];
 #pragma unroll
       for (int kp = 0; kp < NKP; kp++) {
-        f[kp] = __ldg(fin + ((size_t)parity * NKP + kp) * Vh_f + cb);
+        f[kp] = __ldg(fin + (size_t)parity * in_pstride + (size_t)kp * Vh_f + cb);
         w0[kp] = ld_stream(V + v_plane(parity, 2 * kp, jp, Nf, nvh) * Vh_f + cb);
         w1[kp] = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, Nf, nvh) * Vh_f + cb);
       }
@@ -190,7 +191,7 @@ __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V,
       continue;
     }
     for (int kp = 0; kp < nkp; kp++) {
-      const float4 f = __ldg(fin + ((size_t)parity * nkp + kp) * Vh_f + cb);
+      const float4 f = __ldg(fin + (size_t)parity * in_pstride + (size_t)kp * Vh_f + cb);
       const float4 w0 = ld_stream(V + v_plane(parity, 2 * kp, jp, Nf, nvh) * Vh_f + cb);
       const float4 w1 = ld_stream(V + v_plane(parity, 2 * kp + 1, jp, Nf, nvh) * Vh_f + cb);
       const int S = (2 * kp) / cpc;
@@ -232,7 +233,7 @@ __global__ void restrict_kernel(float4 *out, const float4 *fin, const float4 *V,
 // the aggregate (deterministic).
 template <int NKP, typename VT>
 __global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const VT *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
-                                     long Vh_c, int nvec, int cpc, int XL) {
+                                     long Vh_c, int nvec, int cpc, int XL, int par, long in_pstride) {
   const int lane = threadIdx.x, jp = threadIdx.y, nvh = nvec / 2;
   const int RS = 32 / XL;
   const int xl = lane % XL, rs = lane / XL;
@@ -244,14 +245,15 @@ __global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const VT *V
   const int bz = bid % nbz;
   const int bt = bid / nbz;
   const int nyg = b1 / RS;                 // groups of RS consecutive y rows inside the block
-  const int niter = 2 * nyg * b2 * b3;     // (parity, y group, z, t)
+  const int npar = par < 0 ? 2 : 1;        // par >= 0: single-parity input, the other parity counts as zero and is never read
+  const int niter = npar * nyg * b2 * b3;  // (parity, y group, z, t)
   cplx<float> acc[2][2];  // [chirality][j within pair]
 #pragma unroll
   for (int s = 0; s < 2; s++) { acc[s][0] = cplx<float>(0.f, 0.f); acc[s][1] = cplx<float>(0.f, 0.f); }
   long first_fs = -1;
   for (int it = 0; it < niter; it++) {
-    const int parity = it & 1;
-    int r = it >> 1;
+    const int parity = par < 0 ? (it & 1) : par;
+    int r = par < 0 ? (it >> 1) : it;
     const int yg = r % nyg; r /= nyg;
     const int y = by * b1 + yg * RS + rs, z = bz * b2 + r % b2, t = bt * b3 + r / b2;
     const long cb = (((long)t * fg.X[2] + z) * fg.X[1] + y) * fg.Xh + XL * g + xl;
@@ -259,7 +261,7 @@ __global__ void restrict_rows_kernel(float4 *out, const float4 *fin, const VT *V
     float4 f[NKP], w0[NKP], w1[NKP];
 #pragma unroll
     for (int kp = 0; kp < NKP; kp++) {
-      f[kp] = __ldg(fin + ((size_t)parity * NKP + kp) * Vh_f + cb);
+      f[kp] = __ldg(fin + (size_t)parity * in_pstride + (size_t)kp * Vh_f + cb);
       w0[kp] = ldv(V + v_plane(parity, 2 * kp, jp, 2 * NKP, nvh) * Vh_f + cb);
       w1[kp] = ldv(V + v_plane(parity, 2 * kp + 1, jp, 2 * NKP, nvh) * Vh_f + cb);
     }
@@ -304,12 +306,15 @@ struct MultiPtrs { const float4 *in[TRANSFER_MAX_NR]; float4 *out[TRANSFER_MAX_N
 
 // prolong_kernel for NR coarse vectors at once; ACC: out += P c (the coarse-grid correction is added in place)
 template <int NR, bool ACC, typename VT>
-__global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const VT *V, const int *f2c, long Vh_f, long Vh_c, int Nf, int nvec, int cpc) {
+__global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const VT *V, const int *f2c, long Vh_f, long Vh_c, int Nf, int nvec, int cpc,
+                                                            int par, long out_pstride) {
+  // par < 0: both parities of full fine fields; par = 0 / 1: only that parity (preconditioned coarsening: the coarse-grid correction
+  // of the even-odd system lives on one parity, half of V is never touched), out_pstride = float4 distance of the parity blocks of out
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nkp = Nf / 2;
-  if (t >= 2 * Vh_f * nkp) return;
+  if (t >= (par < 0 ? 2 : 1) * Vh_f * nkp) return;
   const long cb = t % Vh_f;
-  const int kp = (int)((t / Vh_f) % nkp), parity = (int)(t / (Vh_f * nkp));
+  const int kp = (int)((t / Vh_f) % nkp), parity = par < 0 ? (int)(t / (Vh_f * nkp)) : par;
   const int k0 = 2 * kp, S = k0 / cpc, nvh = nvec / 2;
   const int cs = f2c[(size_t)parity * Vh_f + cb];
   const int cpar = cs >= Vh_c ? 1 : 0;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const V
       cmac(a1[r], cplx<float>(w1.z, w1.w), cplx<float>(cc.z, cc.w));
     }
   }
-  const size_t o = ((size_t)parity * nkp + kp) * Vh_f + cb;
+  const size_t o = (size_t)parity * out_pstride + (size_t)kp * Vh_f + cb;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
     const float us = v_unscale<VT>();
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(128) prolong_multi_kernel(MultiPtrs p, const V
 // restrict_rows_kernel for NR fine vectors at once (same thread mapping and reduction tree: deterministic)
 template <int NKP, int NR, typename VT>
 __global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p, const VT *V, const int *f2c, LevelGeom fg, int b0, int b1, int b2, int b3,
-                                           long Vh_c, int nvec, int cpc, int XL) {
+                                           long Vh_c, int nvec, int cpc, int XL, int par, long in_pstride) {
   const int lane = threadIdx.x, jp = threadIdx.y, nvh = nvec / 2;
   const int RS = 32 / XL;
   const int xl = lane % XL, rs = lane / XL;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p
   const int bz = bid % nbz;
   const int bt = bid / nbz;
   const int nyg = b1 / RS;
-  const int niter = 2 * nyg * b2 * b3;
+  const int niter = (par < 0 ? 2 : 1) * nyg * b2 * b3;
   cplx<float> acc[NR][2][2];
 #pragma unroll
   for (int r = 0; r < NR; r++)
@@ -365,8 +370,8 @@ __global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p
     for (int s = 0; s < 2; s++) { acc[r][s][0] = cplx<float>(0.f, 0.f); acc[r][s][1] = cplx<float>(0.f, 0.f); }
   long first_fs = -1;
   for (int it = 0; it < niter; it++) {
-    const int parity = it & 1;
-    int rr = it >> 1;
+    const int parity = par < 0 ? (it & 1) : par;
+    int rr = par < 0 ? (it >> 1) : it;
     const int yg = rr % nyg; rr /= nyg;
     const int y = by * b1 + yg * RS + rs, z = bz * b2 + rr % b2, t = bt * b3 + rr / b2;
     const long cb = (((long)t * fg.X[2] + z) * fg.X[1] + y) * fg.Xh + XL * g + xl;
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(384, 1) restrict_rows_multi_kernel(MultiPtrs p
     for (int r = 0; r < NR; r++) {
 #pragma unroll
       for (int kp = 0; kp < NKP; kp++) {
-        const float4 f = __ldg(p.in[r] + ((size_t)parity * NKP + kp) * Vh_f + cb);
+        const float4 f = __ldg(p.in[r] + (size_t)parity * in_pstride + (size_t)kp * Vh_f + cb);
         constexpr int CPC = NKP;            // components per chirality = Nf / 2 (two coarse spins): compile-time, keeps acc in registers
         const int S = (2 * kp) / CPC;
         const cplx<float> f0(f.x, f.y), f1(f.z, f.w);
@@ -560,12 +565,16 @@ void Transfer::P(SpinorField &fo, const SpinorField &ci) const {
   flops += 8ll * Nf * nvec * fine.V();
 }
 
-void Transfer::R(SpinorField &co, const SpinorField &fi) const {
+// fine fields of the parity-restricted variants: a single-parity field, or a full field of which only block `parity` is used
+static long fine_pstride(const SpinorField &f, int Nf) { return f.nparity == 2 ? (long)(Nf / 2) * f.Vh : 0; }
+
+void Transfer::R(SpinorField &co, const SpinorField &fi, int parity) const {
   if (co.prec != PREC_SINGLE || fi.prec != PREC_SINGLE) QB_ERROR("Transfer::R works in single precision");
-  if (fi.nparity != 2 || co.nparity != 2 || fi.Vh != fine.Vh || co.Vh != coarse.Vh || fi.ncomplex != Nf || co.ncomplex != 2 * nvec)
+  if ((parity < 0 && fi.nparity != 2) || co.nparity != 2 || fi.Vh != fine.Vh || co.Vh != coarse.Vh || fi.ncomplex != Nf || co.ncomplex != 2 * nvec)
     QB_ERROR("Transfer::R: field geometry mismatch");
+  const long ips = fine_pstride(fi, Nf);
 #define RK(NKP) restrict_kernel<NKP><<<(unsigned)coarse.V(), dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, c2f, \
-                                                                                      fine.Vh, coarse.Vh, Nf, nvec, Nf / 2, block_sites)
+                                                                                      fine.Vh, coarse.Vh, Nf, nvec, Nf / 2, block_sites, parity, ips)
   const int b0 = geo_bs[0];
   // lanes per row: the whole row if it fits a warp (contiguous runs over consecutive y rows), else pieces of 8
   int XL = 0;
@@ -574,30 +583,32 @@ void Transfer::R(SpinorField &co, const SpinorField &fi) const {
   if (Nf == 12 && XL && (b0 == 2 || b0 == 4 || b0 == 8) && geo_bs[1] % (32 / XL) == 0 && !getenv("QB_RESTRICT_OLD")) {
     const unsigned nblk = (unsigned)((fine.Xh / XL) * (fine.X[1] / geo_bs[1]) * (fine.X[2] / geo_bs[2]) * (fine.X[3] / geo_bs[3]));
     if (V16) restrict_rows_kernel<6, uint2><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const uint2 *)V16, f2c, fine, b0,
-                                                                                          geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL);
+                                                                                          geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL, parity, ips);
     else restrict_rows_kernel<6, float4><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>((float4 *)co.v, (const float4 *)fi.v, (const float4 *)V, f2c, fine, b0,
-                                                                                       geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL);
+                                                                                       geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL, parity, ips);
   } else if (Nf == 12) RK(6);
   else RK(0);
 #undef RK
   QB_CHECK_LAUNCH();
-  flops += 8ll * Nf * nvec * fine.V();
+  flops += 8ll * Nf * nvec * fine.Vh * (parity < 0 ? 2 : 1);
 }
 
 // n fine fields fo[i] (+)= P ci[i]: V is streamed once per group of up to TRANSFER_MAX_NR vectors
-void Transfer::P_multi(SpinorField *const *fo, const SpinorField *const *ci, int n, bool accumulate) const {
-  const long nt = 2 * fine.Vh * (Nf / 2);
+void Transfer::P_multi(SpinorField *const *fo, const SpinorField *const *ci, int n, bool accumulate, int parity) const {
+  const long nt = (parity < 0 ? 2 : 1) * fine.Vh * (Nf / 2);
+  const long ops = fine_pstride(*fo[0], Nf);
   for (int first = 0; first < n; first += TRANSFER_MAX_NR) {
     const int nr = std::min(TRANSFER_MAX_NR, n - first);
     MultiPtrs p{};
     for (int r = 0; r < nr; r++) {
       SpinorField &f = *fo[first + r];
       const SpinorField &c = *ci[first + r];
-      if (f.prec != PREC_SINGLE || c.prec != PREC_SINGLE || f.nparity != 2 || c.nparity != 2 || f.Vh != fine.Vh || c.Vh != coarse.Vh || f.ncomplex != Nf || c.ncomplex != 2 * nvec)
+      if (f.prec != PREC_SINGLE || c.prec != PREC_SINGLE || (parity < 0 && f.nparity != 2) || f.nparity != fo[0]->nparity || c.nparity != 2 || f.Vh != fine.Vh ||
+          c.Vh != coarse.Vh || f.ncomplex != Nf || c.ncomplex != 2 * nvec)
         QB_ERROR("Transfer::P_multi: field geometry mismatch");
       p.out[r] = (float4 *)f.v; p.in[r] = (const float4 *)c.v;
     }
-#define PMV(NR_, ACC_, VT_, VP_) prolong_multi_kernel<NR_, ACC_, VT_><<<div_up(nt, 128), 128, 0, rt().compute>>>(p, (const VT_ *)VP_, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2)
+#define PMV(NR_, ACC_, VT_, VP_) prolong_multi_kernel<NR_, ACC_, VT_><<<div_up(nt, 128), 128, 0, rt().compute>>>(p, (const VT_ *)VP_, f2c, fine.Vh, coarse.Vh, Nf, nvec, Nf / 2, parity, ops)
 #define PM(NR_) \
     if (V16) { if (accumulate) PMV(NR_, true, uint2, V16); else PMV(NR_, false, uint2, V16); } \
     else { if (accumulate) PMV(NR_, true, float4, V); else PMV(NR_, false, float4, V); }
@@ -612,21 +623,22 @@ void Transfer::P_multi(SpinorField *const *fo, const SpinorField *const *ci, int
 #undef PM
 #undef PMV
     QB_CHECK_LAUNCH();
-    flops += 8ll * Nf * nvec * fine.V() * nr;
+    flops += 8ll * Nf * nvec * fine.Vh * (parity < 0 ? 2 : 1) * nr;
   }
 }
 
 // n coarse fields co[i] = R fi[i]
-void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int n) const {
+void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int n, int parity) const {
   const int b0 = geo_bs[0];
   int XL = 0;
   if (fine.Xh == 8 || fine.Xh == 16 || fine.Xh % 32 == 0) XL = fine.Xh < 32 ? fine.Xh : 32;
   else if (fine.Xh % 8 == 0) XL = 8;
   const bool rows = Nf == 12 && XL && (b0 == 2 || b0 == 4 || b0 == 8) && geo_bs[1] % (32 / XL) == 0 && 32 * (nvec / 2) <= 384;
   if (!rows) {  // geometries the row-major kernel does not take: one vector at a time
-    for (int i = 0; i < n; i++) R(*co[i], *fi[i]);
+    for (int i = 0; i < n; i++) R(*co[i], *fi[i], parity);
     return;
   }
+  const long ips = fine_pstride(*fi[0], Nf);
   const unsigned nblk = (unsigned)((fine.Xh / XL) * (fine.X[1] / geo_bs[1]) * (fine.X[2] / geo_bs[2]) * (fine.X[3] / geo_bs[3]));
   for (int first = 0; first < n; first += TRANSFER_MAX_NR) {
     const int nr = std::min(TRANSFER_MAX_NR, n - first);
@@ -634,13 +646,14 @@ void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int
     for (int r = 0; r < nr; r++) {
       SpinorField &c = *co[first + r];
       const SpinorField &f = *fi[first + r];
-      if (f.prec != PREC_SINGLE || c.prec != PREC_SINGLE || f.nparity != 2 || c.nparity != 2 || f.Vh != fine.Vh || c.Vh != coarse.Vh || f.ncomplex != Nf || c.ncomplex != 2 * nvec)
+      if (f.prec != PREC_SINGLE || c.prec != PREC_SINGLE || (parity < 0 && f.nparity != 2) || f.nparity != fi[0]->nparity || c.nparity != 2 || f.Vh != fine.Vh ||
+          c.Vh != coarse.Vh || f.ncomplex != Nf || c.ncomplex != 2 * nvec)
         QB_ERROR("Transfer::R_multi: field geometry mismatch");
       p.out[r] = (float4 *)c.v; p.in[r] = (const float4 *)f.v;
     }
 #define RM(NR_) \
-    if (V16) restrict_rows_multi_kernel<6, NR_, uint2><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const uint2 *)V16, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL); \
-    else restrict_rows_multi_kernel<6, NR_, float4><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const float4 *)V, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL)
+    if (V16) restrict_rows_multi_kernel<6, NR_, uint2><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const uint2 *)V16, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL, parity, ips); \
+    else restrict_rows_multi_kernel<6, NR_, float4><<<nblk, dim3(32, nvec / 2), 0, rt().compute>>>(p, (const float4 *)V, f2c, fine, b0, geo_bs[1], geo_bs[2], geo_bs[3], coarse.Vh, nvec, Nf / 2, XL, parity, ips)
     switch (nr) {
       case 1: RM(1); break;
       case 2: RM(2); break;
@@ -651,7 +664,7 @@ void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int
     }
 #undef RM
     QB_CHECK_LAUNCH();
-    flops += 8ll * Nf * nvec * fine.V() * nr;
+    flops += 8ll * Nf * nvec * fine.Vh * (parity < 0 ? 2 : 1) * nr;
   }
 }
 

@@ -60,10 +60,12 @@ class Transfer {
 
   SpinorField *new_coarse_field() const { return new SpinorField(coarse.Vh, 2, PREC_SINGLE, 2, nvec); }
   void P(SpinorField &fine_out, const SpinorField &coarse_in) const;
-  void R(SpinorField &coarse_out, const SpinorField &fine_in) const;
+  // parity >= 0 (preconditioned coarsening, lib/transfer.cpp:270-348 with a parity site subset): the fine field lives on that parity only
+  // (a single-parity field, or that block of a full field); the other parity counts as zero and its half of V is never read
+  void R(SpinorField &coarse_out, const SpinorField &fine_in, int parity = -1) const;
   // several vectors per pass over V (block multigrid); accumulate: fine_out += P coarse_in
-  void P_multi(SpinorField *const *fine_out, const SpinorField *const *coarse_in, int n, bool accumulate) const;
-  void R_multi(SpinorField *const *coarse_out, const SpinorField *const *fine_in, int n) const;
+  void P_multi(SpinorField *const *fine_out, const SpinorField *const *coarse_in, int n, bool accumulate, int parity = -1) const;
+  void R_multi(SpinorField *const *coarse_out, const SpinorField *const *fine_in, int n, int parity = -1) const;
   size_t v_bytes() const { return (size_t)2 * fine.Vh * Nf * nvec * 8; }
  private:
   void exchange_v_ghost();
