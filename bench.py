@@ -284,7 +284,7 @@ def run_c4(q, L, oracle, X=(48, 48, 48, 96)):
     return res
 
 
-def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True):
+def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=False):
     """Second half of the BASELINE metric: 3-level MG-GCR twisted-mass solve (seconds), plus the coarse-operator
     kernels against their HBM roofline.  32^3x64, 4^4 then 2^4 aggregates, 24 vectors per level, MR(2,2) smoother,
     K-cycle, fp64 outer GCR(20) / fp32 MG / int16 level-0 smoother, weak-field SU(3) gauge (periodic)."""
@@ -307,9 +307,12 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True):
         p.verbosity = int(os.environ.get("QB_VERBOSITY", q.QUDA_SILENT))
         return p
 
+    # pc: the reference test's default (tests/test_util.cpp:1600, multigrid_invert_test.cpp:252): outer GCR on the even-odd system,
+    # every level injects single-parity fields into its coarse grid (preconditioned coarsening); the MG's own invert_param stays
+    # QUDA_DIRECT_SOLVE as interface_quda.cpp:2179 demands
     ip = inv_param()
     mgp = q.multigrid_param(ip, n_level=3, geo_block=((4, 4, 4, 4), (2, 2, 2, 2)), n_vec=(24, 24), nu_pre=2, nu_post=2,
-                            setup_maxiter=500, setup_tol=5e-6, run_verify=False)
+                            setup_maxiter=500, setup_tol=5e-6, run_verify=False, solve_type=q.QUDA_DIRECT_PC_SOLVE if pc else q.QUDA_DIRECT_SOLVE)
     # storage precision of the preconditioner's data (V of the transfer operators, coarse links of the single-RHS kernel): fp32, or
     # fp16 with fp32 arithmetic (what cuda_prec_precondition = half selects; here chosen independently of the level-0 smoother)
     half_storage = half_storage or os.environ.get("QB_BENCH_HALF_STORAGE") == "1"
@@ -330,12 +333,16 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True):
     p = inv_param()
     p.inv_type_precondition = q.QUDA_MG_INVERTER
     p.preconditioner = mg
+    if pc:
+        p.solve_type = q.QUDA_DIRECT_PC_SOLVE
     L.invertQuda(vp(x), vp(b), C.byref(p))  # warm-up (allocations)
     p.iter = 0
     t0 = time.perf_counter()
     L.invertQuda(vp(x), vp(b), C.byref(p))
     wall_s = time.perf_counter() - t0
     p0 = inv_param()
+    if pc:
+        p0.solve_type = q.QUDA_DIRECT_PC_SOLVE
     x0 = np.zeros_like(b)
     L.invertQuda(vp(x0), vp(b), C.byref(p0))
     # 12 spin-colour point sources of one propagator: invertMultiSrcQuda on the block path (all sources through the K-cycle in
@@ -365,7 +372,8 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True):
         os.environ.pop("QB_BLOCK_MG", None)
         multi["speedup_per_source"] = multi["sequential"]["solve_seconds"] / multi["block"]["solve_seconds"]
         del bs, xs
-    res = {"lattice": list(X), "levels": 3, "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond],
+    res = {"lattice": list(X), "levels": 3, "outer_solve": "QUDA_DIRECT_PC_SOLVE, coarse_grid_solution_type MATPC on every level" if pc else "QUDA_DIRECT_SOLVE, coarse_grid_solution_type MAT",
+           "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond],
            "preconditioner_storage": "fp16 V and coarse links, fp32 arithmetic" if half_storage else "fp32", "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
            "setup_seconds": setup_s, "setup_seconds_first_call": setup_first_s, "solve_seconds": p.secs, "solve_wall_seconds_incl_h2d_d2h": wall_s, "iterations": p.iter,
            "true_res": p.true_res, "tol": 1e-9, "plain_gcr_seconds": p0.secs, "plain_gcr_iterations": p0.iter, "plain_gcr_true_res": p0.true_res}
@@ -651,6 +659,8 @@ def main():
     if world == 1 and not args.no_mg and not args.no_extra:
         mg_res = run_mg_leg(q, L, oracle, X, args.mg_precond)
         mg_res_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False)
+        mg_res_pc = run_mg_leg(q, L, oracle, X, args.mg_precond, full=False, pc=True)
+        mg_res_pc_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False, pc=True)
     sampler.stop_flag = True
 
     # max over ranks of the device time
@@ -725,6 +735,8 @@ def main():
         if mg_res:
             line["extra"]["mg_gcr_3level"] = mg_res
             line["extra"]["mg_gcr_3level_fp16_preconditioner_storage"] = mg_res_h16
+            line["extra"]["mg_gcr_3level_even_odd"] = mg_res_pc
+            line["extra"]["mg_gcr_3level_even_odd_fp16_preconditioner_storage"] = mg_res_pc_h16
         if half_ms:
             line["extra"]["half_r12"] = {"ms_per_step": half_ms, "gflops": FLOPS_PER_SITE * sites / (half_ms * 1e-3) / 1e9,
                                          "hbm_gbs_compulsory": 296 * Vh / (half_ms * 1e-3) / 1e9,
