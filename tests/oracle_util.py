@@ -334,3 +334,124 @@ def rel_l2(a, b):
         a = a.astype(np.float64)
         b = b.astype(np.float64)
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+# QudaDiracType values of the reference's include/enum_quda.h (the `dirac` argument of CoarseOp / calculateY)
+def _ref_enum(name):
+    """value of an enumerator of the reference's include/enum_quda.h, read from the table written when libmgref.so was built"""
+    return MGREF_ENUMS[name]
+
+
+MGREF_ENUMS = {}
+
+
+class MgRef:
+    """numpy face of oracle/_ref/libmgref.so = the reference's own multigrid HOST code (lib/transfer.cpp, transfer_util.cu,
+    prolongator.cu, restrictor.cu, coarse_op.cu(h), coarsecoarse_op.cu, dslash_coarse.cu), driven by oracle/mg_ref_shim.cpp.
+    Host field order everywhere: [parity][x_cb][spin][colour][re, im] fp32, DeGrand-Rossi basis (the `generic` order of the
+    mg*QudaB200 test hooks)."""
+
+    def __init__(self, lib):
+        self.L = L = lib
+        vp, ip = C.c_void_p, C.POINTER(C.c_int)
+        L.mgref_transfer_new.argtypes = [vp, C.c_int, ip, C.c_int, C.c_int, ip, C.c_int]
+        L.mgref_transfer_new.restype = vp
+        L.mgref_transfer_free.argtypes = [vp]
+        L.mgref_transfer_V.argtypes = [vp, vp]
+        L.mgref_P.argtypes = [vp, vp, vp, C.c_int]
+        L.mgref_R.argtypes = [vp, vp, vp, C.c_int]
+        L.mgref_coarse_op.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.mgref_coarse_op.restype = vp
+        L.mgref_coarse_coarse_op.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int]
+        L.mgref_coarse_coarse_op.restype = vp
+        L.mgref_coarse_free.argtypes = [vp]
+        L.mgref_coarse_dims.argtypes = [vp, ip]
+        L.mgref_coarse_links.argtypes = [vp, C.c_int, vp]
+        L.mgref_apply_coarse.argtypes = [vp, vp, vp, vp, C.c_double] + [C.c_int] * 5
+        L.mgref_enum.argtypes = [C.c_char_p]
+        L.mgref_enum.restype = C.c_int
+        for n in ("QUDA_WILSON_DIRAC", "QUDA_TWISTED_MASS_DIRAC", "QUDA_TWISTED_MASSPC_DIRAC", "QUDA_COARSE_DIRAC", "QUDA_COARSEPC_DIRAC",
+                  "QUDA_MATPC_EVEN_EVEN", "QUDA_MATPC_ODD_ODD", "QUDA_MATPC_INVALID"):
+            MGREF_ENUMS[n] = L.mgref_enum(n.encode())
+
+    class Transfer:
+        def __init__(self, ref, B, X, nspin, ncolor, geo_bs, spin_bs):
+            """B: list of null vectors (full host fields, fp32)"""
+            self.ref, self.X, self.nspin, self.ncolor, self.nvec, self.spin_bs = ref, tuple(X), nspin, ncolor, len(B), spin_bs
+            Bs = np.ascontiguousarray(np.stack([np.asarray(b, dtype=np.float32) for b in B]))
+            bs = (C.c_int * 4)(*geo_bs)
+            self.h = ref.L.mgref_transfer_new(_ptr(Bs), self.nvec, (C.c_int * 4)(*X), nspin, ncolor, bs, spin_bs)
+            self.geo_bs = tuple(bs)
+            self.Xc = tuple(X[d] // self.geo_bs[d] for d in range(4))
+            self.nf = int(np.prod(X)) * nspin * ncolor          # complex components of a fine field
+            self.nc = int(np.prod(self.Xc)) * (nspin // spin_bs) * self.nvec
+
+        def V(self):
+            out = np.zeros(2 * self.nf * self.nvec, dtype=np.float32)
+            self.ref.L.mgref_transfer_V(self.h, _ptr(out))
+            return out
+
+        def P(self, coarse, parity=-1):
+            out = np.zeros(2 * self.nf // (2 if parity >= 0 else 1), dtype=np.float32)
+            coarse = np.ascontiguousarray(coarse, dtype=np.float32)
+            self.ref.L.mgref_P(self.h, _ptr(out), _ptr(coarse), parity)
+            return out
+
+        def R(self, fine, parity=-1):
+            out = np.zeros(2 * self.nc, dtype=np.float32)
+            fine = np.ascontiguousarray(fine, dtype=np.float32)
+            self.ref.L.mgref_R(self.h, _ptr(out), _ptr(fine), parity)
+            return out
+
+        def free(self):
+            self.ref.L.mgref_transfer_free(self.h)
+
+    class Coarse:
+        def __init__(self, ref, h):
+            self.ref, self.h = ref, h
+            info = (C.c_int * 5)()
+            ref.L.mgref_coarse_dims(h, info)
+            self.Xc, self.N = tuple(info[0:4]), info[4]
+            self.V = int(np.prod(self.Xc))
+
+        def links(self, which):
+            """which: 'Y' | 'X' | 'Xinv' | 'Yhat' -> complex array [dir][parity*Vh + x_cb][row][col] (dir axis only for Y / Yhat)"""
+            w = {"Y": 0, "X": 1, "Xinv": 2, "Yhat": 3}[which]
+            geo = 8 if w in (0, 3) else 1
+            out = np.zeros(geo * self.V * self.N * self.N * 2, dtype=np.float32)
+            self.ref.L.mgref_coarse_links(self.h, w, _ptr(out))
+            z = (out[0::2] + 1j * out[1::2]).reshape(geo, self.V, self.N, self.N)
+            return z if geo == 8 else z[0]
+
+        def apply(self, inA, kappa, inB=None, parity=-1, dslash=True, clover=True, yhat=False, xinv=False):
+            """ApplyCoarse (lib/dslash_coarse.cu:806-814) on host fields"""
+            inA = np.ascontiguousarray(inA, dtype=np.float32)
+            inB = inA if inB is None else np.ascontiguousarray(inB, dtype=np.float32)
+            out = np.zeros(self.V * self.N * 2 // (2 if parity >= 0 else 1), dtype=np.float32)
+            self.ref.L.mgref_apply_coarse(self.h, _ptr(out), _ptr(inA), _ptr(inB), kappa, parity, int(dslash), int(clover), int(yhat), int(xinv))
+            return out
+
+        def free(self):
+            self.ref.L.mgref_coarse_free(self.h)
+
+    def transfer(self, B, X, nspin, ncolor, geo_bs, spin_bs):
+        return MgRef.Transfer(self, B, X, nspin, ncolor, geo_bs, spin_bs)
+
+    def coarse_op(self, T, gauge32, kappa, mu_arg, dirac, matpc="QUDA_MATPC_INVALID"):
+        """CoarseOp's host worker calculateY (lib/coarse_op.cu:152-213, coarse_op.cuh:1309-1497); gauge32: 4 fp32 QDP arrays"""
+        g = [np.ascontiguousarray(a, dtype=np.float32) for a in gauge32]
+        self._keep = g
+        return MgRef.Coarse(self, self.L.mgref_coarse_op(T.h, _ptrs(g), kappa, mu_arg, _ref_enum(dirac), _ref_enum(matpc)))
+
+    def coarse_coarse_op(self, T, fine, kappa, pc=False, matpc="QUDA_MATPC_EVEN_EVEN"):
+        return MgRef.Coarse(self, self.L.mgref_coarse_coarse_op(T.h, fine.h, kappa, int(pc), _ref_enum(matpc)))
+
+
+def load_mgref():
+    path = os.path.join(ORACLE_DIR, "_ref", "libmgref.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference/lib"):
+            subprocess.check_call(["make", "-s", "-j", "8", "-C", ORACLE_DIR, "_ref/libmgref.so"])
+        else:
+            return None
+    return MgRef(C.CDLL(path))
