@@ -92,6 +92,11 @@ void mgRestrictQudaB200(void *mg, int level, float *h_coarse_out, const float *h
 /* operator of a level: pc = 0 the full operator (level 0: fine M, level >= 1: coarse M_c), pc = 1 the smoother's operator */
 void mgMatQudaB200(void *mg, int level, int pc, float *h_out, const float *h_in);
 void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out);
+/* link matrices of the coarse operator on level `level` >= 1, row-major h_out[site][d][row][col][re,im] (site = parity * Vh + x_cb;
+ * d = 0..7: hop to x + e_d with e_d = +mu (d = 2 mu) / -mu (d = 2 mu + 1), d = 8: site-diagonal block).  which = 0: the links L (the -kappa
+ * of the reference's X - kappa sum Y folded in: Y_{mu+4}(x) = -L_{2mu}(x)/kappa, Y_mu(x) = -L_{2mu+1}(x+mu)^dag/kappa, X = L_8,
+ * lib/dslash_coarse.cu:49-203), 1: Xinv ([site][row][col]), 2: Yhat = Xinv L.  Test hook for the element-wise comparison with the reference's calculateY. */
+void mgCoarseLinksQudaB200(void *mg, int level, int which, float *h_out);
 /* mean device time in ms (CUDA events on the compute stream) of `niter` applications on level `level` of
  * what = 0: full operator, 1: smoother operator, 2: prolongator, 3: restrictor */
 double mgTimeQudaB200(void *mg, int level, int what, int niter);

@@ -141,6 +141,7 @@ EXPORTS = [
     "commRankInfoQudaB200", "faceIndexMapQudaB200",
     "blasQudaB200", "mgVerifyQudaB200", "mgLevelInfoQudaB200", "mgProlongQudaB200", "mgRestrictQudaB200", "mgMatQudaB200",
     "mgNullVectorQudaB200", "mgCycleQudaB200", "mgTimeQudaB200", "mgMatMrhsQudaB200", "mgTimeMrhsQudaB200", "mgMrhsMaxRhsQudaB200",
+    "mgCoarseLinksQudaB200", "residentSolutionQudaB200",
 ]
 
 _lib = None
@@ -209,6 +210,7 @@ def lib():
     L.mgRestrictQudaB200.argtypes = [_p, _i, _p, _p]
     L.mgMatQudaB200.argtypes = [_p, _i, _i, _p, _p]
     L.mgNullVectorQudaB200.argtypes = [_p, _i, _i, _p]
+    L.mgCoarseLinksQudaB200.argtypes = [_p, _i, _i, _p]
     L.mgCycleQudaB200.argtypes = [_p, _i, _p, _p]
     L.mgTimeQudaB200.argtypes = [_p, _i, _i, _i]
     L.mgTimeQudaB200.restype = _d

@@ -1247,6 +1247,31 @@ void mgMatQudaB200(void *mg, int level, int pc, float *h_out, const float *h_in)
   d->M(*out, *in);
   export_generic(h_out, *out, rt().compute);
 }
+// Link matrices of the coarse operator ON level `level` >= 1 (built by level - 1), row-major: out[site][d][row][col][re, im], site = full
+// index (parity * Vh + x_cb), d = 0..7 the hop to x + e_d (e_d = +mu for d = 2 mu, -mu for d = 2 mu + 1), d = 8 the site-diagonal block;
+// which = 0: L (the -kappa of the reference's  X - kappa sum Y  folded in), 1: Xinv ([site][row][col]), 2: Yhat = Xinv L (slot 8 = 1).
+// In the reference's terms (dslash_coarse.cu:49-203): Y_{mu+4}(x) = -L_{2mu}(x) / kappa, Y_mu(x) = -L_{2mu+1}(x + mu)^dag / kappa, X = L_8.
+void mgCoarseLinksQudaB200(void *mg, int level, int which, float *h_out) {
+  if (level < 1) QB_ERROR("mgCoarseLinksQudaB200: level must be >= 1");
+  MG *m = mg_level(mg, level - 1);
+  if (!m->coarse_op) QB_ERROR("multigrid has no level %d", level);
+  const CoarseOperator &op = *m->coarse_op;
+  const float *src = which == 0 ? op.Y : (which == 1 ? op.Xinv : op.Yhat);
+  if (!src) QB_ERROR("mgCoarseLinksQudaB200: link field %d has not been computed on level %d", which, level);
+  const int N = op.N, nd = which == 1 ? 1 : 9;
+  const size_t nmat = (size_t)op.geom.V() * nd, per = (size_t)N * N * 2;
+  std::vector<float> raw(nmat * per);
+  QB_CUDA(cudaStreamSynchronize(rt().compute));
+  QB_CUDA(cudaMemcpy(raw.data(), src, raw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  // device layout of one matrix: [col][row pair] float4 = (M[2rp][col], M[2rp+1][col])
+  for (size_t k = 0; k < nmat; k++)
+    for (int c = 0; c < N; c++)
+      for (int r = 0; r < N; r++) {
+        const float *e = raw.data() + k * per + ((size_t)c * (N / 2) + (r >> 1)) * 4 + (r & 1) * 2;
+        float *o = h_out + k * per + ((size_t)r * N + c) * 2;
+        o[0] = e[0]; o[1] = e[1];
+      }
+}
 // null vector k of level `level` in host order
 void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out) {
   MG *m = mg_level(mg, level);
