@@ -281,7 +281,42 @@ def run_c4(q, L, oracle, X=(48, 48, 48, 96)):
         byts = V * (8 * 12 * 24 + 96)
         res[name] = {"ms": ms, "hbm_gbs": byts / ms / 1e6, "roofline_frac": byts / ms / 1e6 / peaks["hbm_gbs"], "bytes": byts}
     L.destroyMultigridQuda(mg)
+    res["cpu_reference_coarse_dslash"] = cpu_baseline_coarse(oracle)
     return res
+
+
+def cpu_baseline_coarse(oracle):
+    """CPU baseline of the coarse Dslash: the reference's OWN host path -- ApplyCoarse -> CPU coarseDslash,
+    lib/dslash_coarse.cu:263-290, single-threaded as shipped (its OpenMP pragma is commented out, :279) -- from oracle/_ref/libmgref.so,
+    on a bounded sample: N = 48 (n_vec 24) links built by the reference's calculateY from random vectors on 8^3x16 with 2^4 aggregates
+    -> 4^3x8 = 512 coarse sites (the per-site cost does not depend on the lattice size).  Checker / baseline only, never the product."""
+    from tests import oracle_util as ou
+    ref = ou.load_mgref()
+    if ref is None:
+        return None
+    Xs, kappa = (8, 8, 8, 16), 0.1248
+    oracle.set_dims(Xs)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=11)
+    rng = np.random.default_rng(7)
+    B = [rng.standard_normal(oracle.V * 24).astype(np.float32) for _ in range(24)]
+    t0 = time.perf_counter()
+    T = ref.transfer(B, Xs, 4, 3, (2, 2, 2, 2), 2)
+    co = ref.coarse_op(T, g, kappa, 2 * kappa * 0.004, "QUDA_TWISTED_MASS_DIRAC")
+    build_s = time.perf_counter() - t0
+    v = rng.standard_normal(co.V * co.N * 2).astype(np.float32)
+    co.apply(v, kappa)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or time.perf_counter() - t0 < 3.0:
+        co.apply(v, kappa)
+        reps += 1
+    sec = (time.perf_counter() - t0) / reps
+    N, sites = co.N, co.V
+    out = {"kind": "reference", "cores": 1, "sites": sites, "N": N, "seconds_per_application": sec,
+           "gflops": sites * ((8 + 1) * 8 * N * N - 2 * N) / sec / 1e9, "us_per_site": sec / sites * 1e6,
+           "links_build_seconds_reference_calculateY": build_s, "fine_sites_of_the_build": int(np.prod(Xs)),
+           "sample": "lib/dslash_coarse.cu CPU coarseDslash from oracle/_ref/libmgref.so, 512 coarse sites, N = 48, 1 thread"}
+    co.free(); T.free()
+    return out
 
 
 def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=False):

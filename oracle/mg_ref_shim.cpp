@@ -94,6 +94,8 @@ struct DevicePropInit {
     // single-process communicator (what initCommsGridQuda / initQuda set up, lib/interface_quda.cpp:340-420), lib/comm_single.cpp
     const int dims[4] = {1, 1, 1, 1};
     comm_init(4, dims, rank_of, 0);
+    // the reference logs every setup stage with printfQuda on stdout; bench.py owns stdout (one JSON line): keep the log only on request
+    setOutputFile(getenv("MGREF_VERBOSE") ? stderr : fopen("/dev/null", "w"));
   }
   static int rank_of(const int *, void *) { return 0; }
 } device_prop_init;

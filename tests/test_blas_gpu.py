@@ -98,3 +98,52 @@ def test_reductions_are_deterministic(quda):
     first = run(L, "cDotProductNormA", 4, *vecs)[1]
     for _ in range(5):
         assert run(L, "cDotProductNormA", 4, *vecs)[1] == first
+
+
+@pytest.mark.parametrize("prec", [8, 4])
+def test_blas_against_the_reference_host_blas(quda, prec):
+    """the five operations the reference's own host BLAS provides (tests/blas_reference.cpp: ax, axpy, xpay, mxpy, norm_2, compiled
+    unmodified into oracle/_ref/libtmref.so -- what its solvers' host verification uses), same inputs, element-wise"""
+    import os
+    from tests import oracle_util as ou
+    path = os.path.join(ou.ORACLE_DIR, "_ref", "libtmref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libtmref.so is absent")
+    R = C.CDLL(path)
+    vp_, dbl, it = C.c_void_p, C.c_double, C.c_int
+    R.norm_2.restype = dbl
+    R.norm_2.argtypes = [vp_, it, it]
+    R.ax.argtypes = [dbl, vp_, it, it]
+    R.axpy.argtypes = [dbl, vp_, vp_, it, it]
+    R.xpay.argtypes = [vp_, dbl, vp_, it, it]
+    R.mxpy.argtypes = [vp_, vp_, it, it]
+    L = quda.lib()
+    n = 12 * 4099
+    dt = np.float64 if prec == 8 else np.float32
+    rng = np.random.default_rng(prec)
+    vecs = [(rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex128 if prec == 8 else np.complex64).astype(np.complex128) for _ in range(4)]
+
+    def reals(v):
+        f = np.empty(2 * v.size, dtype=dt)
+        f[0::2] = v.real; f[1::2] = v.imag
+        return f
+
+    def ptr(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    tol = 1e-14 if prec == 8 else 1e-6
+    a = A.real
+    for name in ("ax", "axpy", "xpay", "mxpy", "norm2"):
+        got, res = run(L, name, prec, *vecs)
+        x, y = reals(vecs[0]), reals(vecs[1])
+        if name == "ax": R.ax(a, ptr(x), x.size, prec)
+        elif name == "axpy": R.axpy(a, ptr(x), ptr(y), x.size, prec)
+        elif name == "xpay": R.xpay(ptr(x), a, ptr(y), x.size, prec)
+        elif name == "mxpy": R.mxpy(ptr(x), ptr(y), x.size, prec)
+        else:
+            ref = R.norm_2(ptr(x), x.size, prec)
+            assert abs(res[0] - ref) <= (1e-13 if prec == 8 else 1e-6) * ref, (res[0], ref)
+            continue
+        for g, h in zip(got[:2], (x, y)):
+            hc = h[0::2].astype(np.float64) + 1j * h[1::2].astype(np.float64)
+            assert np.abs(g - hc).max() <= tol * np.abs(hc).max(), name
