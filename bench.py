@@ -215,27 +215,52 @@ def run_c5(q, L, oracle, du, rank, world, grid, global_X=(64, 64, 64, 128)):
         p.gcrNkrylov = 20; p.tol = 1e-9; p.maxiter = 10000; p.reliable_delta = 1e-4
         return p
 
-    ip = inv_param()
-    mgp = q.multigrid_param(ip, n_level=3, geo_block=((4, 4, 4, 4), (2, 2, 2, 2)), n_vec=(24, 24), nu_pre=2, nu_post=2,
-                            setup_maxiter=500, setup_tol=5e-6, run_verify=False)
-    t0 = time.perf_counter()
-    mg = L.newMultigridQuda(C.byref(mgp))
-    setup = time.perf_counter() - t0
     V = int(np.prod(Xl))
     b = np.zeros(V * 24)
     if rank == 0:
         b[0:24:2] = 1.0
     x = np.zeros_like(b)
-    p = inv_param()
-    p.inv_type_precondition = q.QUDA_MG_INVERTER
-    p.preconditioner = mg
-    L.invertQuda(vp(x), vp(b), C.byref(p))  # warm-up (allocations)
-    p.iter = 0
-    L.invertQuda(vp(x), vp(b), C.byref(p))
-    L.destroyMultigridQuda(mg)
-    return {"grid": list(grid), "local": list(Xl), "global": list(global_X), "levels": 3, "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24],
-            "kappa": kappa, "mu": mu, "tol": 1e-9, "setup_seconds": setup, "solve_seconds": p.secs, "iterations": p.iter, "true_res": p.true_res,
-            "true_res_note": "relative L2 residual recomputed by the library with the fp64 operator whose multi-GPU parity is checked above"}
+
+    def one(pc):
+        ip = inv_param()
+        mgp = q.multigrid_param(ip, n_level=3, geo_block=((4, 4, 4, 4), (2, 2, 2, 2)), n_vec=(24, 24), nu_pre=2, nu_post=2, setup_maxiter=500,
+                                setup_tol=5e-6, run_verify=False, solve_type=q.QUDA_DIRECT_PC_SOLVE if pc else q.QUDA_DIRECT_SOLVE)
+        t0 = time.perf_counter()
+        mg = L.newMultigridQuda(C.byref(mgp))
+        setup = time.perf_counter() - t0
+
+        def solve_param():
+            p = inv_param()
+            p.inv_type_precondition = q.QUDA_MG_INVERTER
+            p.preconditioner = mg
+            if pc:
+                p.solve_type = q.QUDA_DIRECT_PC_SOLVE
+            return p
+
+        p = solve_param()
+        L.invertQuda(vp(x), vp(b), C.byref(p))  # warm-up (allocations)
+        p.iter = 0
+        L.invertQuda(vp(x), vp(b), C.byref(p))
+        # where the time goes: a third solve with the (stream-synchronising, hence slower) section timers of the cycle
+        L.mgProfileEnableQudaB200(1)
+        pp = solve_param()
+        L.invertQuda(vp(x), vp(b), C.byref(pp))
+        L.mgProfileEnableQudaB200(0)
+        prof = {"solve_seconds_with_timers": pp.secs}
+        for lvl in range(3):
+            t6 = (C.c_double * 6)(); nc = C.c_long(0)
+            L.mgProfileGetQudaB200(mg, lvl, t6, C.byref(nc))
+            prof[f"level{lvl}"] = {"cycles": nc.value, "pre_smooth_or_coarsest_solve": t6[0], "residual": t6[1], "restrict": t6[2],
+                                   "coarse_solve_incl_lower_levels": t6[3], "prolong": t6[4], "post_smooth": t6[5]}
+        L.destroyMultigridQuda(mg)
+        return {"setup_seconds": setup, "solve_seconds": p.secs, "iterations": p.iter, "true_res": p.true_res, "profile": prof}
+
+    res = {"peer_mailbox_allreduce_active": bool(L.commPeerReduceActiveQudaB200()), "grid": list(grid), "local": list(Xl), "global": list(global_X), "levels": 3,
+           "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu, "tol": 1e-9,
+           "true_res_note": "relative L2 residual recomputed by the library with the fp64 operator whose multi-GPU parity is checked above"}
+    res.update(one(False))
+    res["even_odd"] = one(True)   # QUDA_DIRECT_PC_SOLVE outer solve, hierarchy coarsened on the even-odd system (the reference's default)
+    return res
 
 
 def run_c4(q, L, oracle, X=(48, 48, 48, 96)):
@@ -691,6 +716,7 @@ def main():
         half = run_config(2, 12, args.steps, args.warmup, False)
         extra["half_r12"] = half
     mg_res = None
+    reduce_res = None
     if world == 1 and not args.no_mg and not args.no_extra:
         mg_res = run_mg_leg(q, L, oracle, X, args.mg_precond)
         mg_res_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False)
@@ -714,6 +740,18 @@ def main():
         c3_res = {"t_only": run_c3(q, L, oracle, rank, world, (1, 1, 1, world), args.steps, args.warmup, max_over_ranks, barrier)}
         g2 = (1, 1, 2, world // 2)
         c3_res["z_only" if world == 2 else "t_and_z"] = run_c3(q, L, oracle, rank, world, g2, args.steps, args.warmup, max_over_ranks, barrier)
+    if world > 1 and not args.no_extra:
+        # global reductions: host-visible latency of one norm2 of a coarse-level sized vector (98 304 reals) with the all-reduce
+        # fused into the reduction kernel over the NVLink peer mailboxes, and with ncclAllReduce on the compute stream
+        barrier()
+        active = L.commPeerReduceActiveQudaB200()
+        us_peer = max_over_ranks(L.timeReduceQudaB200(98304, 200, 1))
+        barrier()
+        us_nccl = max_over_ranks(L.timeReduceQudaB200(98304, 200, 0))
+        barrier()
+        reduce_res = {"peer_mailbox_allreduce_active": bool(active), "norm2_us_fused_peer_allreduce": us_peer if active else None,
+                      "norm2_us_nccl_allreduce": us_nccl, "vector_reals": 98304,
+                      "note": "kernel launch + all-reduce over the ranks + the stream synchronisation that hands the sum to the host, mean of 200, max over ranks"}
     if world > 1 and (args.c5 == "on" or (args.c5 == "auto" and world == 8)) and not args.no_extra:
         c5_res = run_c5(q, L, oracle, du, rank, world, du.default_grid(world))
     if world == 1 and not args.no_c4 and not args.no_mg and not args.no_extra:
@@ -763,6 +801,8 @@ def main():
                               "tolerance": {"fp64": 1e-13, "fp32": 1e-6, "half": 1e-3}, "cases": parity_res}
         if c3_res:
             line["extra"]["c3_64x128"] = c3_res
+        if reduce_res:
+            line["extra"]["global_reduction"] = reduce_res
         if c5_res:
             line["extra"]["c5_mg_gcr"] = c5_res
         if c4_res:

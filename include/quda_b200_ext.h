@@ -45,6 +45,14 @@ double timeDslashQudaB200(void *out, void *in, QudaInvertParam *param, QudaParit
  * partitioned face; no interior / boundary kernel); bytes_sent (may be NULL) receives the bytes this rank sends per hop */
 double timeHaloQudaB200(void *out, void *in, QudaInvertParam *param, QudaParity parity, int niter, double *bytes_sent);
 
+/* Global reductions: 1 when the all-reduce over the ranks runs INSIDE the reduction kernel (the last CTA stores the rank's
+ * sums into every peer's HBM mailbox over NVLink, waits for the peers' flags and adds in rank order), 0 when it is an ncclAllReduce on the
+ * compute stream (mailboxes not mappable, QB_PEER_REDUCE=0) or a single rank.  Reference: lib/reduce_core.cuh:72-93 + MPI_Allreduce. */
+int commPeerReduceActiveQudaB200(void);
+/* mean host-visible latency (microseconds) of one global norm2 of an fp32 field of n_reals reals: kernel + all-reduce + the stream
+ * synchronisation that hands the sum to the host; use_peer = 0 forces the ncclAllReduce path for comparison (collective call) */
+double timeReduceQudaB200(long n_reals, int niter, int use_peer);
+
 /* launch geometry of the fine Dslash kernels (the reference autotunes this, lib/tune.cpp:480-655;
  * here a fixed default is used and this knob exists for tuning runs).  Call after loadGaugeQuda. */
 /* mean ms of one batched hop over `nbatch` fp32 parity fields (multi-RHS fine Dslash: links fetched once for all members);
@@ -92,6 +100,10 @@ void mgRestrictQudaB200(void *mg, int level, float *h_coarse_out, const float *h
 /* operator of a level: pc = 0 the full operator (level 0: fine M, level >= 1: coarse M_c), pc = 1 the smoother's operator */
 void mgMatQudaB200(void *mg, int level, int pc, float *h_out, const float *h_in);
 void mgNullVectorQudaB200(void *mg, int level, int k, float *h_out);
+/* wall-clock profile of the multigrid cycle: enable the stream-synchronising section timers, then read (and reset) a level's accumulated
+ * seconds t6 = {pre-smooth or coarsest solve, residual, restrict, coarse solve (all levels below), prolong, post-smooth} and its cycle count */
+void mgProfileEnableQudaB200(int on);
+void mgProfileGetQudaB200(void *mg, int level, double *t6, long *ncycle);
 /* link matrices of the coarse operator on level `level` >= 1, row-major h_out[site][d][row][col][re,im] (site = parity * Vh + x_cb;
  * d = 0..7: hop to x + e_d with e_d = +mu (d = 2 mu) / -mu (d = 2 mu + 1), d = 8: site-diagonal block).  which = 0: the links L (the -kappa
  * of the reference's X - kappa sum Y folded in: Y_{mu+4}(x) = -L_{2mu}(x)/kappa, Y_mu(x) = -L_{2mu+1}(x+mu)^dag/kappa, X = L_8,

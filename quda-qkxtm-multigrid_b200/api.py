@@ -141,7 +141,8 @@ EXPORTS = [
     "commRankInfoQudaB200", "faceIndexMapQudaB200",
     "blasQudaB200", "mgVerifyQudaB200", "mgLevelInfoQudaB200", "mgProlongQudaB200", "mgRestrictQudaB200", "mgMatQudaB200",
     "mgNullVectorQudaB200", "mgCycleQudaB200", "mgTimeQudaB200", "mgMatMrhsQudaB200", "mgTimeMrhsQudaB200", "mgMrhsMaxRhsQudaB200",
-    "mgCoarseLinksQudaB200", "residentSolutionQudaB200",
+    "mgCoarseLinksQudaB200", "residentSolutionQudaB200", "commPeerReduceActiveQudaB200", "timeReduceQudaB200",
+    "mgProfileEnableQudaB200", "mgProfileGetQudaB200",
 ]
 
 _lib = None
@@ -195,6 +196,8 @@ def lib():
     L.timeDslashBatchQudaB200.restype = _d
     L.timeHaloQudaB200.argtypes = [_p, _p, IP, _i, _i, C.POINTER(_d)]
     L.timeHaloQudaB200.restype = _d
+    L.timeReduceQudaB200.restype = _d
+    L.timeReduceQudaB200.argtypes = [C.c_long, _i, _i]
     L.setDslashBlockSizeQudaB200.argtypes = [_i]
     L.kernelLaunchCountQudaB200.restype = C.c_longlong
     L.computeStreamQudaB200.restype = _p
@@ -211,6 +214,8 @@ def lib():
     L.mgMatQudaB200.argtypes = [_p, _i, _i, _p, _p]
     L.mgNullVectorQudaB200.argtypes = [_p, _i, _i, _p]
     L.mgCoarseLinksQudaB200.argtypes = [_p, _i, _i, _p]
+    L.mgProfileEnableQudaB200.argtypes = [_i]
+    L.mgProfileGetQudaB200.argtypes = [_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_long)]
     L.mgCycleQudaB200.argtypes = [_p, _i, _p, _p]
     L.mgTimeQudaB200.argtypes = [_p, _i, _i, _i]
     L.mgTimeQudaB200.restype = _d

@@ -32,6 +32,7 @@ static double *d_partial = nullptr;      // [grid][MAX_RED]
 static unsigned *d_counter = nullptr;
 static double *h_result = nullptr;       // mapped pinned host memory, written by the last block
 static double *d_result = nullptr;       // device alias of h_result
+static double *d_sum = nullptr;          // device-memory result for the ncclAllReduce fallback
 static int max_grid = 0;
 
 void init() {
@@ -42,17 +43,27 @@ void init() {
   QB_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned)));
   QB_CUDA(cudaHostAlloc((void **)&h_result, sizeof(double) * MAX_RED, cudaHostAllocMapped));
   QB_CUDA(cudaHostGetDevicePointer((void **)&d_result, h_result, 0));
+  QB_CUDA(cudaMalloc((void **)&d_sum, sizeof(double) * MAX_RED));
 }
 
 void end() {
   if (d_partial) cudaFree(d_partial);
   if (d_counter) cudaFree(d_counter);
   if (h_result) cudaFreeHost(h_result);
+  if (d_sum) cudaFree(d_sum);
+  d_sum = nullptr;
   d_partial = nullptr; d_counter = nullptr; h_result = nullptr; d_result = nullptr;
 }
 
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int NR, typename F>
-__global__ void __launch_bounds__(BLOCK) red_kernel(long n, F f, double *partial, unsigned *counter, double *result) {
+__global__ void __launch_bounds__(BLOCK) red_kernel(long n, F f, double *partial, unsigned *counter, double *result, const PeerReduce pr) {
   double acc[NR];
 _Pragma("unroll")
   for (int k = 0; k < NR; k++) acc[k] = 0.0;
@@ -81,12 +92,37 @@ _Pragma("unroll")
   __syncthreads();
   if (last) {
     // deterministic final pass: fixed order over CTAs
+    __shared__ double fin[NR];
     for (int k = warp; k < NR; k += BLOCK / 32) {
       double v = 0.0;
       for (int b = lane; b < (int)gridDim.x; b += 32) v += partial[(long)b * NR + k];
 _Pragma("unroll")
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) result[k] = v;
+      if (lane == 0) { if (pr.size > 1) fin[k] = v; else result[k] = v; }
+    }
+    if (pr.size > 1) {
+      // all-reduce over the ranks inside the kernel (comm.h): my sums into every rank's mailbox over NVLink, then the flags, then wait
+      // for everybody's flag in my own mailbox and add in rank order
+      __syncthreads();
+      const int slot = (int)(pr.seq & 1);
+      for (int i = threadIdx.x; i < pr.size * NR; i += BLOCK) {
+        const int p = i / NR, k = i - p * NR;
+        pr.box[p][((size_t)slot * pr.size + pr.rank) * PEER_MAX_RED + k] = fin[k];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if ((int)threadIdx.x < pr.size) {
+        st_release_sys(pr.flag[threadIdx.x] + slot * pr.size + pr.rank, pr.seq);
+        const unsigned long long *mine = pr.flag[pr.rank] + slot * pr.size + threadIdx.x;
+        while (ld_acquire_sys(mine) < pr.seq) {}
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < NR) {
+        const volatile double *box = pr.box[pr.rank] + (size_t)slot * pr.size * PEER_MAX_RED;
+        double v = 0.0;
+        for (int p = 0; p < pr.size; p++) v += box[(size_t)p * PEER_MAX_RED + threadIdx.x];
+        result[threadIdx.x] = v;
+      }
     }
   }
 }
@@ -95,11 +131,31 @@ template <int NR, typename F> static void reduce(double *out, long n, F f) {
   Runtime &r = rt();
   init();
   const int grid = grid_for(n);
-  red_kernel<NR, F><<<grid, BLOCK, 0, r.compute>>>(n, f, d_partial, d_counter, d_result);
+  const bool global = global_reduction && r.size > 1;
+  PeerReduce pr;   // size 1: the kernel writes this rank's sums into the mapped host result
+  if (global && comm_peer_reduce_ready()) {
+    // the all-reduce happens inside the kernel over the peers' mailboxes: when the stream is idle the global sums are on the host
+    pr = comm_peer_reduce_next();
+    red_kernel<NR, F><<<grid, BLOCK, 0, r.compute>>>(n, f, d_partial, d_counter, d_result, pr);
+    QB_CHECK_LAUNCH();
+    QB_CUDA(cudaStreamSynchronize(r.compute));
+    for (int k = 0; k < NR; k++) out[k] = h_result[k];
+    return;
+  }
+  if (global) {
+    // no peer mapping: sums stay on the device, ncclAllReduce on the compute stream, one copy to the host, one synchronisation
+    red_kernel<NR, F><<<grid, BLOCK, 0, r.compute>>>(n, f, d_partial, d_counter, d_sum, pr);
+    QB_CHECK_LAUNCH();
+    comm_allreduce_sum_device(d_sum, NR, r.compute);
+    QB_CUDA(cudaMemcpyAsync(h_result, d_sum, sizeof(double) * NR, cudaMemcpyDeviceToHost, r.compute));
+    QB_CUDA(cudaStreamSynchronize(r.compute));
+    for (int k = 0; k < NR; k++) out[k] = h_result[k];
+    return;
+  }
+  red_kernel<NR, F><<<grid, BLOCK, 0, r.compute>>>(n, f, d_partial, d_counter, d_result, pr);
   QB_CHECK_LAUNCH();
   QB_CUDA(cudaStreamSynchronize(r.compute));
   for (int k = 0; k < NR; k++) out[k] = h_result[k];
-  if (global_reduction) comm_allreduce_sum(out, NR);
 }
 
 template <typename F> static void elementwise(long n, F f) {

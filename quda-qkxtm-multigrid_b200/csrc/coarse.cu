@@ -101,13 +101,18 @@ void CoarseOperator::exchange_ghost(const float *field, const long *poff, int pa
   coarse_pack_kernel<<<div_up(off, 256), 256, 0, r.compute>>>(a);
   QB_CHECK_LAUNCH();
   if (comm_self_exchange()) return;
+  // all faces of all partitioned dimensions in one NCCL group (one launch; the reference posts them all before waiting too,
+  // lib/dslash_coarse.cu:707).  my back face -> backward neighbour's "from forward" ghost; my forward face -> forward neighbour's
+  // "from backward" ghost
+  const void *sb[8]; void *rb[8]; int to[8], from[8]; size_t nb[8];
+  int n = 0;
   for (int d = 0; d < 4; d++) {
     if (!geom.part[d]) continue;
     const size_t bytes = (size_t)2 * a.nplanes * geom.faceVh[d] * sizeof(float4);
-    // my back face -> backward neighbour's "from forward" ghost; my forward face -> forward neighbour's "from backward" ghost
-    comm_sendrecv(send[d][0], comm_neighbor_rank(d, 0), recv[d][1], comm_neighbor_rank(d, 1), bytes, r.compute);
-    comm_sendrecv(send[d][1], comm_neighbor_rank(d, 1), recv[d][0], comm_neighbor_rank(d, 0), bytes, r.compute);
+    sb[n] = send[d][0]; to[n] = comm_neighbor_rank(d, 0); rb[n] = recv[d][1]; from[n] = comm_neighbor_rank(d, 1); nb[n++] = bytes;
+    sb[n] = send[d][1]; to[n] = comm_neighbor_rank(d, 1); rb[n] = recv[d][0]; from[n] = comm_neighbor_rank(d, 0); nb[n++] = bytes;
   }
+  comm_sendrecv_group(n, sb, to, rb, from, nb, r.compute);
 }
 
 // -----------------------------------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 // NCCL-backed communication layer (dlopen'ed: no link-time dependency, so the single-GPU path
 // works on a box without NCCL, and inside a PyTorch process the already-loaded libnccl is reused).
 #include <dlfcn.h>
+#include <vector>
 #include "comm.h"
 #include "dslash_api.h"
 
@@ -21,6 +22,7 @@ struct NcclApi {
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -54,11 +56,14 @@ static void load_nccl() {
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
 }
+
+static void peer_reduce_setup();
 
 void comm_unique_id(void *out128) {
   load_nccl();
@@ -79,6 +84,74 @@ void comm_bootstrap(int rank, int size, const void *unique_id128) {
   ncclUniqueId id;
   memcpy(&id, unique_id128, sizeof(id));
   QB_NCCL(nccl.CommInitRank(&comm, size, id, rank));
+  peer_reduce_setup();
+}
+
+// ---- peer mailboxes for the fused all-reduce (comm.h) ----------------------------------------------------------------------------
+static PeerReduce peer;
+static bool peer_ready = false;
+static void *peer_local = nullptr;           // my mailbox: boxes then flags
+static void *peer_mapped[PEER_MAX_RANKS];    // IPC mappings of the peers' mailboxes
+static size_t peer_box_bytes(int size) { return sizeof(double) * 2 * size * PEER_MAX_RED; }
+
+static void peer_reduce_setup() {
+  Runtime &r = rt();
+  peer_ready = false;
+  const char *env = getenv("QB_PEER_REDUCE");
+  if (env && atoi(env) == 0) return;
+  if (r.size > PEER_MAX_RANKS) return;
+  const size_t bytes = peer_box_bytes(r.size) + sizeof(unsigned long long) * 2 * r.size;
+  QB_CUDA(cudaMalloc(&peer_local, bytes));
+  QB_CUDA(cudaMemset(peer_local, 0, bytes));
+  cudaIpcMemHandle_t mine;
+  bool ok = cudaIpcGetMemHandle(&mine, peer_local) == cudaSuccess;
+  // exchange the handles (and whether every rank got one) through NCCL
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  Msg m{}; m.h = mine; m.ok = ok ? 1 : 0;
+  Msg *d_all = nullptr;
+  QB_CUDA(cudaMalloc((void **)&d_all, sizeof(Msg) * r.size));
+  QB_CUDA(cudaMemcpy(d_all + r.rank, &m, sizeof(Msg), cudaMemcpyHostToDevice));
+  QB_NCCL(nccl.AllGather(d_all + r.rank, d_all, sizeof(Msg), ncclInt8, comm, r.compute));
+  QB_CUDA(cudaStreamSynchronize(r.compute));
+  std::vector<Msg> all(r.size);
+  QB_CUDA(cudaMemcpy(all.data(), d_all, sizeof(Msg) * r.size, cudaMemcpyDeviceToHost));
+  QB_CUDA(cudaFree(d_all));
+  for (int p = 0; p < r.size; p++) ok = ok && all[p].ok;
+  int mapped_ok = ok ? 1 : 0;
+  if (ok) {
+    for (int p = 0; p < r.size; p++) {
+      if (p == r.rank) { peer_mapped[p] = peer_local; continue; }
+      if (cudaIpcOpenMemHandle(&peer_mapped[p], all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mapped_ok = 0; peer_mapped[p] = nullptr; }
+    }
+  }
+  cudaGetLastError();
+  // all ranks must take the same path
+  double v = mapped_ok ? 0.0 : 1.0;
+  comm_allreduce_sum(&v, 1);
+  if (v != 0.0) {
+    log_msg(1, "peer mailboxes for the fused all-reduce could not be mapped on every rank: reductions use ncclAllReduce\n");
+    return;
+  }
+  peer.rank = r.rank; peer.size = r.size; peer.seq = 0;
+  for (int p = 0; p < r.size; p++) {
+    peer.box[p] = (double *)peer_mapped[p];
+    peer.flag[p] = (unsigned long long *)((char *)peer_mapped[p] + peer_box_bytes(r.size));
+  }
+  peer_ready = true;
+  log_msg(2, "fused all-reduce: mailboxes of %d ranks mapped over CUDA IPC\n", r.size);
+}
+
+static bool peer_enabled = true;
+bool comm_peer_reduce_ready() { return peer_ready && peer_enabled; }
+void comm_peer_reduce_enable(bool on) { peer_enabled = on; }
+PeerReduce comm_peer_reduce_next() {
+  peer.seq++;
+  return peer;
+}
+
+void comm_allreduce_sum_device(double *d_data, int n, cudaStream_t s) {
+  if (rt().size == 1) return;
+  QB_NCCL(nccl.AllReduce(d_data, d_data, n, ncclFloat64, ncclSum, comm, s));
 }
 
 static int default_rank_from_coords(const int *c, void *fdata) {
@@ -154,6 +227,22 @@ void comm_sendrecv(const void *sendbuf, int to_rank, void *recvbuf, int from_ran
   QB_NCCL(nccl.GroupEnd());
 }
 
+// n send / receive pairs in ONE NCCL group (one launch on the stream instead of n)
+void comm_sendrecv_group(int n, const void *const *sendbuf, const int *to_rank, void *const *recvbuf, const int *from_rank, const size_t *bytes, cudaStream_t s) {
+  Runtime &r = rt();
+  if (r.size == 1) {
+    for (int i = 0; i < n; i++) QB_CUDA(cudaMemcpyAsync(recvbuf[i], sendbuf[i], bytes[i], cudaMemcpyDeviceToDevice, s));
+    return;
+  }
+  if (!comm) QB_ERROR("exchange requested but the NCCL communicator was not created");
+  QB_NCCL(nccl.GroupStart());
+  for (int i = 0; i < n; i++) {
+    QB_NCCL(nccl.Send(sendbuf[i], bytes[i], ncclInt8, to_rank[i], comm, s));
+    QB_NCCL(nccl.Recv(recvbuf[i], bytes[i], ncclInt8, from_rank[i], comm, s));
+  }
+  QB_NCCL(nccl.GroupEnd());
+}
+
 void comm_exchange_halo(Lattice &lat, int pi, cudaStream_t s) {
   Runtime &r = rt();
   if (r.size == 1) return;
@@ -205,6 +294,13 @@ void comm_barrier() {
 }
 
 void comm_finalize() {
+  if (peer_local) {
+    cudaDeviceSynchronize();
+    for (int p = 0; p < rt().size && p < PEER_MAX_RANKS; p++)
+      if (p != rt().rank && peer_mapped[p]) cudaIpcCloseMemHandle(peer_mapped[p]);
+    cudaFree(peer_local);
+    peer_local = nullptr; peer_ready = false;
+  }
   if (comm) nccl.CommDestroy(comm);
   comm = nullptr;
   if (d_red) cudaFree(d_red);

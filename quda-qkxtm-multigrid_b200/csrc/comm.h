@@ -25,6 +25,29 @@ void comm_free_halo(void *p);
 void comm_exchange_halo(Lattice &lat, int prec_idx, cudaStream_t s);
 // generic point-to-point pair on a stream (gauge ghost links, coarse halos)
 void comm_sendrecv(const void *sendbuf, int to_rank, void *recvbuf, int from_rank, size_t bytes, cudaStream_t s);
+void comm_sendrecv_group(int n, const void *const *sendbuf, const int *to_rank, void *const *recvbuf, const int *from_rank, const size_t *bytes, cudaStream_t s);
+
+// ---- all-reduce fused into the reduction kernels (blas.cu) ----------------------------------------------------------------------
+// Every rank exposes a small mailbox in its HBM to all peers (CUDA IPC over NVLink / NVSwitch, opened once at bootstrap).  The last CTA
+// of a reduction kernel stores its rank's partial sums straight into every peer's mailbox, raises a sequence flag there, waits for the
+// flags of all peers in its own mailbox and adds the contributions in rank order (deterministic, identical on all ranks): the global sum
+// is complete when the kernel ends -- no NCCL launch, no host staging, one stream synchronisation where the host needs the scalar.
+// (Reference: kernel -> mapped host memory spin -> MPI_Allreduce, lib/reduce_core.cuh:72-93, lib/face_buffer.cpp:407-428.)
+constexpr int PEER_MAX_RANKS = 16;
+constexpr int PEER_MAX_RED = 64;       // doubles per reduction
+struct PeerReduce {
+  int rank = 0, size = 1;
+  unsigned long long seq = 0;          // sequence number of this reduction (identical on all ranks: reductions are collective)
+  double *box[PEER_MAX_RANKS];         // box[p]: mailbox of rank p as seen from this device, [2 slots][size][PEER_MAX_RED]
+  unsigned long long *flag[PEER_MAX_RANKS];  // flag[p]: [2 slots][size] sequence flags of rank p's mailbox
+};
+// false: single rank, or the mailboxes could not be mapped (then reductions fall back to ncclAllReduce on the compute stream)
+bool comm_peer_reduce_ready();
+void comm_peer_reduce_enable(bool on);   // measurement switch (all ranks alike)
+// arguments for the next collective reduction (advances the sequence number)
+PeerReduce comm_peer_reduce_next();
+// fallback: in-place sum of n doubles in device memory, enqueued on stream s
+void comm_allreduce_sum_device(double *d_data, int n, cudaStream_t s);
 
 // sum / max all-reduce of n doubles held on the host (blocking; used by reductions in solvers)
 void comm_allreduce_sum(double *data, int n);

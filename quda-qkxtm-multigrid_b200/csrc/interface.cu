@@ -799,6 +799,27 @@ void commRankInfoQudaB200(int *info10) {
   info10[0] = r.rank; info10[1] = r.size;
   for (int d = 0; d < 4; d++) { info10[2 + d] = r.coord[d]; info10[6 + d] = r.grid[d]; }
 }
+// 1 when global reductions run their all-reduce inside the reduction kernel over the NVLink peer mailboxes (comm.h), 0 when they use
+// ncclAllReduce (single rank: 0)
+int commPeerReduceActiveQudaB200(void) { return comm_peer_reduce_ready() ? 1 : 0; }
+// mean host-visible latency in microseconds of one global norm2 of an fp32 vector of n_reals reals (kernel + all-reduce over the ranks +
+// the stream synchronisation after which the host holds the sum), over niter calls.  use_peer = 0 forces the ncclAllReduce path.
+double timeReduceQudaB200(long n_reals, int niter, int use_peer) {
+  require_init();
+  if (n_reals < 24) n_reals = 24;
+  SpinorField f(n_reals / 24, 1, PREC_SINGLE);
+  random_fill(f, 12345ull + rt().rank);
+  const bool had = comm_peer_reduce_ready();
+  if (!use_peer) comm_peer_reduce_enable(false);
+  double sink = 0;
+  for (int i = 0; i < 5; i++) sink += blas::norm2(f);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < niter; i++) sink += blas::norm2(f);
+  const double us = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6 / niter;
+  comm_peer_reduce_enable(had);
+  if (sink == -1.0) log_msg(0, "");
+  return us;
+}
 void ncclUniqueIdQudaB200(void *out) { comm_unique_id(out); }
 void commsBootstrapQudaB200(int rank, int size, const void *id) { comm_bootstrap(rank, size, id); }
 void commDimPartitionedSetQudaB200(int mask) {
@@ -992,7 +1013,7 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
                                                                param->tol_precondition == INVALID_DOUBLE ? 0.1 : param->tol_precondition);
     (*solve)(out, in);
   }
-  if (K) ((MultigridSolver *)param->preconditioner)->mg->print_profile();
+  if (K && getenv("QUDA_B200_MG_PROFILE")) ((MultigridSolver *)param->preconditioner)->mg->print_profile();
   d->reconstruct(*x, *b, st);
   if (param->solver_normalization == QUDA_SOURCE_NORMALIZATION) blas::ax(sqrt(nb), *x);
   // interface_quda.cpp:2493-2508: make_resident_solution keeps the solution on the device instead of copying it to h_x; it replaces the
@@ -1203,6 +1224,17 @@ static MG *mg_level(void *mg, int level) {
 }
 
 void mgVerifyQudaB200(void *mg, int level, double *dev3) { mg_level(mg, level)->verify(dev3); }
+
+// Wall-clock profile of the cycle per level: on != 0 switches the (stream-synchronising) section timers on.  mgProfileGetQudaB200 returns
+// and resets the accumulated seconds of level `level`: t6 = {pre-smooth (or the coarsest-grid solve), residual, restrict, coarse solve
+// (everything below), prolong, post-smooth}, *ncycle = cycles counted.
+void mgProfileEnableQudaB200(int on) { mg_profile_enable(on != 0); }
+void mgProfileGetQudaB200(void *mg, int level, double *t6, long *ncycle) {
+  MG *m = mg_level(mg, level);
+  for (int i = 0; i < 6; i++) { t6[i] = m->t_prof[i]; m->t_prof[i] = 0; }
+  if (ncycle) *ncycle = m->ncycle;
+  m->ncycle = 0;
+}
 
 void mgLevelInfoQudaB200(void *mg, int level, int *info8) {
   MG *m = mg_level(mg, level);

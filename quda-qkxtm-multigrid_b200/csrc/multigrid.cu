@@ -314,10 +314,11 @@ void MG::smooth(Solver &s, SpinorField &x, SpinorField &b) {
 }
 
 // optional wall-clock profile of the cycle (QUDA_B200_MG_PROFILE=1): sections are bracketed by stream syncs
+static int g_mg_profile = -1;
+void mg_profile_enable(bool on) { g_mg_profile = on ? 1 : 0; }
 static bool mg_profile_on() {
-  static int on = -1;
-  if (on < 0) { const char *e = getenv("QUDA_B200_MG_PROFILE"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on == 1;
+  if (g_mg_profile < 0) { const char *e = getenv("QUDA_B200_MG_PROFILE"); g_mg_profile = (e && e[0] == '1') ? 1 : 0; }
+  return g_mg_profile == 1;
 }
 struct Section {
   double *acc; double t0; bool on;

@@ -105,6 +105,7 @@ struct MultigridSolver {
 };
 
 void random_fill(SpinorField &f, unsigned long long seed);
+void mg_profile_enable(bool on);   // section timers of the cycle (stream-synchronised, so they slow the solve down)
 // batched null-vector generation on coarse levels through the multi-RHS tensor-core operator (block_solver.cu)
 bool block_null_vectors_supported(const Dirac *matSmooth, int nvec);
 int block_null_vectors(const Dirac *matSmooth, std::vector<SpinorField *> &x, int maxiter, double tol);

@@ -40,8 +40,10 @@ def main():
         p.gcrNkrylov = 20; p.tol = 1e-8; p.maxiter = 2000; p.reliable_delta = 1e-4
         return p
 
+    pc = os.environ.get("QB_MG_PC") == "1"   # hierarchy coarsened on the even-odd system + even-odd outer solve (the reference's default)
     ip = inv_param()
-    mgp = q.multigrid_param(ip, n_level=3, geo_block=((2, 2, 2, 2), (2, 2, 2, 2)), n_vec=(8, 8), setup_maxiter=100, setup_tol=5e-6)
+    mgp = q.multigrid_param(ip, n_level=3, geo_block=((2, 2, 2, 2), (2, 2, 2, 2)), n_vec=(8, 8), setup_maxiter=100, setup_tol=5e-6,
+                            solve_type=q.QUDA_DIRECT_PC_SOLVE if pc else q.QUDA_DIRECT_SOLVE)
     mg = L.newMultigridQuda(C.byref(mgp))
     for lvl in (0, 1):
         dev = (C.c_double * 3)()
@@ -53,8 +55,12 @@ def main():
     p = inv_param()
     p.inv_type_precondition = q.QUDA_MG_INVERTER
     p.preconditioner = mg
+    if pc:
+        p.solve_type = q.QUDA_DIRECT_PC_SOLVE
     L.invertQuda(x.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p), C.byref(p))
     p0 = inv_param()
+    if pc:
+        p0.solve_type = q.QUDA_DIRECT_PC_SOLVE
     x0 = np.zeros_like(bl)
     L.invertQuda(x0.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p), C.byref(p0))
     import torch
@@ -70,9 +76,14 @@ def main():
         xg = np.zeros(2 * o.Vh * 24).reshape(-1, 24); xg[idx] = x.reshape(-1, 24); xg = xg.ravel()
     res = np.linalg.norm(bg - o.tm_mat(g, xg, kappa, mu, 1, 0)) / np.linalg.norm(bg)
     assert res < 5e-8, res
+    if world > 1:
+        # every rank must have seen bit-identical global sums (the all-reduce adds the ranks' contributions in a fixed order)
+        tr = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(tr, torch.tensor([p.true_res, float(p.iter)], dtype=torch.float64, device="cuda"))
+        assert all(bool((t == tr[0]).all()) for t in tr), [t.tolist() for t in tr]
     assert p.iter < p0.iter / 2, (p.iter, p0.iter)
     if rank == 0:
-        print(f"MULTIGPU_MG_OK ranks={world} grid={grid} local={Xl} mg_iters={p.iter} plain_iters={p0.iter} host_res={res:.2e} true_res={p.true_res:.2e}", flush=True)
+        print(f"MULTIGPU_MG_OK ranks={world} grid={grid} local={Xl} pc={int(pc)} peer_reduce={os.environ.get('QB_PEER_REDUCE', '1')} mg_iters={p.iter} plain_iters={p0.iter} host_res={res:.2e} true_res={p.true_res:.2e}", flush=True)
     L.destroyMultigridQuda(mg)
     L.endQuda()
     if world > 1:

@@ -151,12 +151,15 @@ def test_nccl_halo_exchange_vs_global_oracle(nranks, grid, local):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks,grid", [(2, "1,1,1,2"), (2, "1,1,2,1"), (4, "1,1,2,2")])
-def test_distributed_multigrid_solve(nranks, grid):
+@pytest.mark.parametrize("nranks,grid,pc,peer", [(2, "1,1,1,2", 0, 1), (2, "1,1,2,1", 0, 1), (4, "1,1,2,2", 0, 1),
+                                                 (2, "1,1,1,2", 1, 1), (2, "1,1,2,1", 1, 0), (2, "1,1,1,2", 0, 0)])
+def test_distributed_multigrid_solve(nranks, grid, pc, peer):
+    """pc = 1: hierarchy on the even-odd system + QUDA_DIRECT_PC_SOLVE; peer = 1: all-reduces fused into the reduction kernels over the
+    NVLink peer mailboxes (comm.h), 0: ncclAllReduce on the compute stream"""
     import torch
     if torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8")
+    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8", QB_MG_PC=str(pc), QB_PEER_REDUCE=str(peer))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
            "--master-port", "29633", os.path.join(ROOT, "tests", "multi_gpu_mg.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
