@@ -790,6 +790,8 @@ def main():
             "e2e": {"value": FLOPS_PER_SITE * sites / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": main_res["e2e_bytes"], "d2h_bytes_per_step": main_res["e2e_bytes"],
                     "pcie_floor_ms": main_res.get("pcie_ms"),
+                    "rank0_cpu_affinity": len(os.sched_getaffinity(0)),
+                    "affinity_note": "N > 1: each rank is bound to the cpus of its GPU's NUMA node (initQudaDevice / commsBootstrap, as the reference's setNumaAffinity) before the pinned host buffers are allocated",
                     "pcie_floor_note": "H2D + D2H of the same two pinned buffers on two streams at once, no compute: the link-bound lower limit of this call"},
             "gpu_launches": main_res["launches"],
             "clocks": sampler.summary(),

@@ -1,6 +1,8 @@
 // C-ABI entry points: the quda.h subset of SURVEY.md section 8(b) plus the resident-field extensions.
 // Behavioural model: /root/reference/lib/interface_quda.cpp (line refs at each function).
 #include <algorithm>
+#include <cctype>
+#include <sched.h>
 #include <cfloat>
 #include <climits>
 #include <cstring>
@@ -162,6 +164,43 @@ void initCommsGridQuda(int nDim, const int *dims, QudaCommsMap func, void *fdata
   comm_set_grid(dims, func, fdata);
 }
 
+// CPU / memory affinity of the process to the NUMA node its GPU hangs off (the reference: setNumaAffinityNVML from initQudaDevice,
+// lib/interface_quda.cpp:429-434, lib/numa_affinity.cpp, switched off by QUDA_ENABLE_NUMA=0).  Here without NVML: PCI bus id -> sysfs numa_node
+// -> cpulist -> sched_setaffinity; pinned host buffers allocated afterwards land on that node (first touch), which is what keeps the
+// H2D / D2H copies of 8 ranks on one host from all crossing the socket interconnect.  Only when several ranks share the host.
+static void set_numa_affinity(int dev) {
+  const char *env = getenv("QUDA_ENABLE_NUMA");
+  if (env && strcmp(env, "0") == 0) return;
+  if (rt().size <= 1 && !(env && strcmp(env, "1") == 0)) return;
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) { cudaGetLastError(); return; }
+  for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE *f = fopen(path, "r");
+  if (!f) return;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  if (node < 0) return;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return;
+  char list[4096] = "";
+  if (!fgets(list, sizeof(list), f)) list[0] = 0;
+  fclose(f);
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n = 0;
+  for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; c++) { CPU_SET(c, &set); n++; } }
+    else if (sscanf(tok, "%d", &a) == 1) { CPU_SET(a, &set); n++; }
+  }
+  if (n == 0) return;
+  if (sched_setaffinity(0, sizeof(set), &set) == 0) log_msg(2, "Set NUMA affinity for device %d: node %d, %d cpus\n", dev, node, n);
+}
+
 void initQudaDevice(int dev) {
   Runtime &r = rt();
   if (r.device_ready) return;
@@ -178,6 +217,7 @@ void initQudaDevice(int dev) {
   r.num_sms = prop.multiProcessorCount;
   r.device_ready = true;
   log_msg(2, "Using device %d: %s (%d SMs)\n", dev, prop.name, r.num_sms);
+  set_numa_affinity(dev);
 }
 
 void initQudaMemory(void) {
@@ -821,7 +861,10 @@ double timeReduceQudaB200(long n_reals, int niter, int use_peer) {
   return us;
 }
 void ncclUniqueIdQudaB200(void *out) { comm_unique_id(out); }
-void commsBootstrapQudaB200(int rank, int size, const void *id) { comm_bootstrap(rank, size, id); }
+void commsBootstrapQudaB200(int rank, int size, const void *id) {
+  comm_bootstrap(rank, size, id);
+  if (size > 1 && rt().device_ready) set_numa_affinity(rt().device);   // the device was chosen before the ranks were known
+}
 void commDimPartitionedSetQudaB200(int mask) {
   if (G.loaded) QB_ERROR("commDimPartitionedSetQudaB200 must be called before loadGaugeQuda");
   rt().part_mask |= (mask & 15);
