@@ -252,8 +252,36 @@ def run_c5(q, L, oracle, du, rank, world, grid, global_X=(64, 64, 64, 128)):
             L.mgProfileGetQudaB200(mg, lvl, t6, C.byref(nc))
             prof[f"level{lvl}"] = {"cycles": nc.value, "pre_smooth_or_coarsest_solve": t6[0], "residual": t6[1], "restrict": t6[2],
                                    "coarse_solve_incl_lower_levels": t6[3], "prolong": t6[4], "post_smooth": t6[5]}
+        multi = None
+        if not pc and os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
+            # the "multi-RHS coarse grid" of config 5: 12 spin-colour point sources through invertMultiSrcQuda; block path = lock-step
+            # GCR, coarse levels on the multi-RHS tensor-core operator with ghost zones of block fields, against one source at a time
+            nsrc = 12
+            bs = []
+            for k in range(nsrc):
+                bk = np.zeros(V * 24)
+                if rank == 0:
+                    bk[2 * k] = 1.0
+                bs.append(bk)
+            xs = [np.zeros(V * 24) for _ in range(nsrc)]
+            multi = {"sources": nsrc}
+            for name, env in (("block", "1"), ("sequential", "0")):
+                os.environ["QB_BLOCK_MG"] = env
+                pm = solve_param()
+                pm.num_src = nsrc
+                ptr_x, ptr_b = (C.c_void_p * nsrc)(*[a.ctypes.data for a in xs]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bs])
+                if name == "block":
+                    L.invertMultiSrcQuda(ptr_x, ptr_b, C.byref(pm))  # warm-up (allocations)
+                L.invertMultiSrcQuda(ptr_x, ptr_b, C.byref(pm))
+                multi[name] = {"solve_seconds": pm.secs, "seconds_per_source": pm.secs / nsrc, "iterations": pm.iter, "worst_true_res": pm.true_res}
+            os.environ.pop("QB_BLOCK_MG", None)
+            multi["speedup_per_source"] = multi["sequential"]["solve_seconds"] / multi["block"]["solve_seconds"]
+            del bs, xs
         L.destroyMultigridQuda(mg)
-        return {"setup_seconds": setup, "solve_seconds": p.secs, "iterations": p.iter, "true_res": p.true_res, "profile": prof}
+        out = {"setup_seconds": setup, "solve_seconds": p.secs, "iterations": p.iter, "true_res": p.true_res, "profile": prof}
+        if multi:
+            out["multi_src_12_point_sources"] = multi
+        return out
 
     res = {"peer_mailbox_allreduce_active": bool(L.commPeerReduceActiveQudaB200()), "grid": list(grid), "local": list(Xl), "global": list(global_X), "levels": 3,
            "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu, "tol": 1e-9,

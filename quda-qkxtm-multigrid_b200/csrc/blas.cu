@@ -2,6 +2,7 @@
 #include "blas.h"
 #include "comm.h"
 #include "layout.cuh"
+#include "peer_reduce.cuh"
 
 namespace qb {
 namespace blas {
@@ -55,13 +56,6 @@ void end() {
   d_partial = nullptr; d_counter = nullptr; h_result = nullptr; d_result = nullptr;
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
 template <int NR, typename F>
 __global__ void __launch_bounds__(BLOCK) red_kernel(long n, F f, double *partial, unsigned *counter, double *result, const PeerReduce pr) {
   double acc[NR];
@@ -101,28 +95,10 @@ _Pragma("unroll")
       if (lane == 0) { if (pr.size > 1) fin[k] = v; else result[k] = v; }
     }
     if (pr.size > 1) {
-      // all-reduce over the ranks inside the kernel (comm.h): my sums into every rank's mailbox over NVLink, then the flags, then wait
-      // for everybody's flag in my own mailbox and add in rank order
-      __syncthreads();
-      const int slot = (int)(pr.seq & 1);
-      for (int i = threadIdx.x; i < pr.size * NR; i += BLOCK) {
-        const int p = i / NR, k = i - p * NR;
-        pr.box[p][((size_t)slot * pr.size + pr.rank) * PEER_MAX_RED + k] = fin[k];
-      }
-      __threadfence_system();
-      __syncthreads();
-      if ((int)threadIdx.x < pr.size) {
-        st_release_sys(pr.flag[threadIdx.x] + slot * pr.size + pr.rank, pr.seq);
-        const unsigned long long *mine = pr.flag[pr.rank] + slot * pr.size + threadIdx.x;
-        while (ld_acquire_sys(mine) < pr.seq) {}
-      }
-      __syncthreads();
-      if ((int)threadIdx.x < NR) {
-        const volatile double *box = pr.box[pr.rank] + (size_t)slot * pr.size * PEER_MAX_RED;
-        double v = 0.0;
-        for (int p = 0; p < pr.size; p++) v += box[(size_t)p * PEER_MAX_RED + threadIdx.x];
-        result[threadIdx.x] = v;
-      }
+      // all-reduce over the ranks inside the kernel (peer_reduce.cuh): my sums into every rank's mailbox over NVLink, then the flags,
+      // then wait for everybody's flag in my own mailbox and add in rank order
+      peer_allreduce_cta(pr, fin, NR);
+      if ((int)threadIdx.x < NR) result[threadIdx.x] = fin[threadIdx.x];
     }
   }
 }

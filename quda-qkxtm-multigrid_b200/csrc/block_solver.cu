@@ -14,7 +14,9 @@
 #include <cstdlib>
 #include <vector>
 #include "coarse.h"
+#include "comm.h"
 #include "multigrid.h"
+#include "peer_reduce.cuh"
 
 namespace qb {
 
@@ -44,12 +46,17 @@ __global__ void block_cdot_kernel(const float4 *x, const float4 *y, long n4, int
     o[0] = s0; o[1] = s1; o[2] = s2;
   }
 }
-__global__ void block_cdot_final_kernel(const double *partial, int nblk, int R, double *out) {
+// one CTA of 3 * MAXR threads; pr.size > 1: the sums are all-reduced over the ranks inside the kernel (peer_reduce.cuh)
+__global__ void block_cdot_final_kernel(const double *partial, int nblk, int R, double *out, const PeerReduce pr) {
+  __shared__ double fin[3 * MAXR];
   const int t = threadIdx.x;
-  if (t >= 3 * R) return;
-  double s = 0;
-  for (int b = 0; b < nblk; b++) s += partial[(size_t)b * R * 3 + t];
-  out[t] = s;
+  if (t < 3 * R) {
+    double s = 0;
+    for (int b = 0; b < nblk; b++) s += partial[(size_t)b * R * 3 + t];
+    fin[t] = s;
+  }
+  if (pr.size > 1) peer_allreduce_cta(pr, fin, 3 * R);
+  if (t < 3 * R) out[t] = fin[t];
 }
 
 // op 0: y += a x            op 1: z = x + a y + b z (p = r + a v + b p)        op 2: z += a x + b y         op 3: y = a x
@@ -95,8 +102,13 @@ struct BlockBlas {
   void cdot(const float *x, const float *y, std::vector<std::complex<double>> &dot, std::vector<double> &nx) {
     cudaStream_t s = rt().compute;
     block_cdot_kernel<<<nblk, threads, sizeof(double) * 3 * threads, s>>>((const float4 *)x, (const float4 *)y, n4, R, partial);
-    block_cdot_final_kernel<<<1, 3 * MAXR, 0, s>>>(partial, nblk, R, result_d);
+    // global sums on partitioned lattices: inside the kernel over the peer mailboxes, else ncclAllReduce on the stream
+    PeerReduce pr;
+    const bool global = rt().size > 1;
+    if (global && comm_peer_reduce_ready()) pr = comm_peer_reduce_next();
+    block_cdot_final_kernel<<<1, 3 * MAXR, 0, s>>>(partial, nblk, R, result_d, pr);
     QB_CHECK_LAUNCH();
+    if (global && pr.size == 1) comm_allreduce_sum_device(result_d, 3 * R, s);
     QB_CUDA(cudaMemcpyAsync(result.data(), result_d, sizeof(double) * 3 * R, cudaMemcpyDeviceToHost, s));
     QB_CUDA(cudaStreamSynchronize(s));
     dot.resize(R); nx.resize(R);
@@ -145,7 +157,7 @@ struct BlockMhat {
 bool block_null_vectors_supported(const Dirac *matSmooth, int nvec) {
   if (getenv("QB_BLOCK_SETUP") && atoi(getenv("QB_BLOCK_SETUP")) == 0) return false;
   const DiracCoarse *d = dynamic_cast<const DiracCoarse *>(matSmooth);
-  if (!d || !d->pc || d->op->geom.partitioned()) return false;
+  if (!d || !d->pc) return false;
   const int mode = getenv("QB_BLOCK_SETUP_MODE") ? atoi(getenv("QB_BLOCK_SETUP_MODE")) : 3;
   return coarse_mrhs_max_rhs(d->op->N, mode) >= 1 && nvec >= 2;
 }
@@ -677,7 +689,7 @@ bool block_mg_supported(const MG &mg, int R, int mode) {
     if (m->pc_coarsen) return false;   // hierarchies coarsened on the even-odd system take the one-at-a-time path
   for (const MG *m = mg.coarse.get(); m; m = m->coarse.get()) {
     const DiracCoarse *dr = dynamic_cast<const DiracCoarse *>(m->matResidual), *ds = dynamic_cast<const DiracCoarse *>(m->matSmooth);
-    if (!dr || !ds || !ds->pc || dr->op->geom.partitioned()) return false;
+    if (!dr || !ds || !ds->pc) return false;
     const InverterType sm = m->mp.level[m->level].smoother;
     if (m->coarse ? sm != INV_MR : (sm != INV_MR && sm != INV_GCR)) return false;   // the coarsest level solves with GCR(20) either way
     const int N = dr->op->N;

@@ -35,6 +35,8 @@ CoarseOperator::~CoarseOperator() {
   if (Ymma) cudaFree(Ymma);
   if (Xinv_mma) cudaFree(Xinv_mma);
   if (nbr) cudaFree(nbr);
+  if (mrhs_send) cudaFree(mrhs_send);
+  if (mrhs_recv) cudaFree(mrhs_recv);
   for (int d = 0; d < 4; d++)
     for (int k = 0; k < 2; k++) {
       if (recv[d][k] && !comm_self_exchange()) cudaFree(recv[d][k]);

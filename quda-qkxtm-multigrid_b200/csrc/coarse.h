@@ -50,6 +50,16 @@ struct CoarseOperator {
   int *nbr = nullptr;         // [V][8] full-site index of x + e_d
   bool mrhs_ready = false;
   void prepare_mrhs();        // (re)build the three arrays above from Y / Xinv
+  // Partitioned lattices: ghost zone of BLOCK fields.  The neighbour table points boundary hops at "ghost sites" numbered from 2 Vh:
+  // ghost site = mrhs_goff[d][dir] + parity * faceVh[d] + face index, dir 0 = slice X_d - 1 of the backward neighbour, dir 1 = slice 0
+  // of the forward neighbour; the send / receive arenas hold one contiguous [kc][r] block of R vectors per ghost site, exactly what the
+  // kernel's producer bulk-copies for a local neighbour (reference: ghost zones of composite fields, lib/color_spinor_pack.cu,
+  // lib/dslash_coarse.cu:707)
+  long mrhs_goff[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  long mrhs_ghost_sites = 0;
+  mutable float *mrhs_send = nullptr, *mrhs_recv = nullptr;
+  mutable size_t mrhs_arena_bytes = 0;
+  void exchange_block_ghost(const float *field, const long *poff, int parity_mask, int R) const;
   ~CoarseOperator();
 };
 

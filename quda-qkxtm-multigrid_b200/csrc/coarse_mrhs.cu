@@ -26,6 +26,7 @@
 //   warps 6-9 : epilogue  - tcgen05.ld -> shared staging -> a * out + b * xpay -> coalesced 128-bit stores
 #include <cstdlib>
 #include "coarse.h"
+#include "comm.h"
 #include "tc05.cuh"
 
 namespace qb {
@@ -49,8 +50,11 @@ __global__ void ymma_from_y_kernel(float4 *dst, const float4 *src, int N, long n
   dst[t] = (i & 1) ? make_float4(c0.z, c0.w, c1.z, c1.w) : make_float4(c0.x, c0.y, c1.x, c1.y);
 }
 
-// neighbour table: full-site index (parity * Vh + cb) of x + e_d for d < 8
-__global__ void coarse_nbr_kernel(int *nbr, LevelGeom g) {
+struct GhostOff { long off[4][2]; };
+
+// neighbour table: full-site index (parity * Vh + cb) of x + e_d for d < 8; hops across a partitioned boundary point at ghost sites,
+// numbered from 2 Vh (CoarseOperator::mrhs_goff)
+__global__ void coarse_nbr_kernel(int *nbr, LevelGeom g, GhostOff go) {
   const long fs = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (fs >= 2L * g.Vh) return;
   const int parity = fs >= g.Vh ? 1 : 0;
@@ -64,6 +68,14 @@ __global__ void coarse_nbr_kernel(int *nbr, LevelGeom g) {
   for (int d = 0; d < 8; d++) {
     const int mu = d >> 1;
     int y[4] = {x[0], x[1], x[2], x[3]};
+    const bool wrap = (d & 1) ? x[mu] == 0 : x[mu] == g.X[mu] - 1;
+    if (wrap && g.part[mu]) {
+      // face index of the neighbour on its slice: 3-d lexicographic index of the other coordinates >> 1 (coarse_face_to_cb)
+      const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
+      const long fidx = (((long)x[d2] * g.X[d1] + x[d1]) * g.X[d0] + x[d0]) >> 1;
+      nbr[fs * 8 + d] = (int)(2L * g.Vh + go.off[mu][(d & 1) ? 0 : 1] + (long)(1 - parity) * g.faceVh[mu] + fidx);
+      continue;
+    }
     y[mu] = (y[mu] + ((d & 1) ? g.X[mu] - 1 : 1)) % g.X[mu];
     const long ncb = ((((long)y[3] * g.X[2] + y[2]) * g.X[1] + y[1]) * g.X[0] + y[0]) >> 1;
     nbr[fs * 8 + d] = (int)((long)(1 - parity) * g.Vh + ncb);
@@ -71,7 +83,6 @@ __global__ void coarse_nbr_kernel(int *nbr, LevelGeom g) {
 }
 
 void CoarseOperator::prepare_mrhs() {
-  if (geom.partitioned()) QB_ERROR("multi-RHS coarse operator: partitioned coarse lattices are not supported yet");
   cudaStream_t s = rt().compute;
   const long V = geom.V();
   if (mrhs_ready && Ymma && nbr && (!Xinv || Xinv_mma)) return;   // links are immutable once the level is set up
@@ -89,10 +100,97 @@ void CoarseOperator::prepare_mrhs() {
     QB_CHECK_LAUNCH();
   }
   if (!nbr) {
+    GhostOff go;
+    long off = 0;
+    for (int d = 0; d < 4; d++)
+      for (int dir = 0; dir < 2; dir++) {
+        go.off[d][dir] = mrhs_goff[d][dir] = off;
+        if (geom.part[d]) off += 2L * geom.faceVh[d];
+      }
+    mrhs_ghost_sites = off;
     QB_CUDA(cudaMalloc((void **)&nbr, sizeof(int) * 8 * V));
-    coarse_nbr_kernel<<<div_up(V, 256), 256, 0, s>>>(nbr, geom);
+    coarse_nbr_kernel<<<div_up(V, 256), 256, 0, s>>>(nbr, geom, go);
     QB_CHECK_LAUNCH();
   }
+}
+
+// ---- ghost zone of block fields ------------------------------------------------------------------------------------------------
+struct BlockPackArgs {
+  float4 *send;
+  const float4 *field;
+  long poff[2];
+  int X[4], faceVh[4], part[4];
+  long goff[4][2];
+  long off[5];   // prefix sums of the float4 counts per partitioned dimension
+  int nelem, parity_mask;
+};
+__device__ __forceinline__ long block_face_to_cb(int mu, int fidx, int slice, int parity, const int *X) {
+  const int d0 = mu == 0 ? 1 : 0, d1 = mu <= 1 ? 2 : 1, d2 = mu <= 2 ? 3 : 2;
+  const int L0 = X[d0], L1 = X[d1];
+  const int f2 = 2 * fidx;
+  const int row = f2 / L0;
+  const int c = row / L1, b = row - c * L1;
+  int a = f2 - row * L0;
+  a += (slice + b + c + parity + a) & 1;
+  int x[4];
+  x[mu] = slice; x[d0] = a; x[d1] = b; x[d2] = c;
+  return ((((long)x[3] * X[2] + x[2]) * X[1] + x[1]) * X[0] + x[0]) >> 1;
+}
+// send arena, same site numbering as the receiver's ghost zone seen from the other side: block [d][0] = my slice x_d = 0 (travels
+// backward, becomes the neighbour's [d][1]), block [d][1] = my slice x_d = X_d - 1
+__global__ void block_ghost_pack_kernel(const BlockPackArgs a) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.off[4]) return;
+  int d = 0;
+  while (d < 3 && t >= a.off[d + 1]) d++;
+  long r = t - a.off[d];
+  const int e = (int)(r % a.nelem); r /= a.nelem;
+  const int fv = a.faceVh[d];
+  const int fidx = (int)(r % fv); r /= fv;
+  const int parity = (int)(r & 1), dir = (int)(r >> 1);
+  if (!((a.parity_mask >> parity) & 1)) return;
+  const long cb = block_face_to_cb(d, fidx, dir ? a.X[d] - 1 : 0, parity, a.X);
+  a.send[(size_t)(a.goff[d][dir] + (long)parity * fv + fidx) * a.nelem + e] = a.field[a.poff[parity] + (size_t)cb * a.nelem + e];
+}
+
+void CoarseOperator::exchange_block_ghost(const float *field, const long *poff, int parity_mask, int R) const {
+  if (!geom.partitioned()) return;
+  Runtime &r = rt();
+  const int nelem = (N / 2) * R;
+  const size_t need = (size_t)mrhs_ghost_sites * nelem * sizeof(float4);
+  if (need > mrhs_arena_bytes) {
+    QB_CUDA(cudaStreamSynchronize(r.compute));
+    if (mrhs_send) { cudaFree(mrhs_send); cudaFree(mrhs_recv); }
+    QB_CUDA(cudaMalloc((void **)&mrhs_send, need));
+    QB_CUDA(cudaMalloc((void **)&mrhs_recv, need));
+    mrhs_arena_bytes = need;
+  }
+  BlockPackArgs a;
+  a.send = (float4 *)mrhs_send; a.field = (const float4 *)field;
+  a.poff[0] = poff[0]; a.poff[1] = poff[1];
+  a.nelem = nelem; a.parity_mask = parity_mask;
+  long off = 0;
+  for (int d = 0; d < 4; d++) {
+    a.X[d] = geom.X[d]; a.faceVh[d] = geom.faceVh[d]; a.part[d] = geom.part[d];
+    a.goff[d][0] = mrhs_goff[d][0]; a.goff[d][1] = mrhs_goff[d][1];
+    a.off[d] = off;
+    if (geom.part[d]) off += 4L * geom.faceVh[d] * nelem;
+  }
+  a.off[4] = off;
+  block_ghost_pack_kernel<<<div_up(off, 256), 256, 0, r.compute>>>(a);
+  QB_CHECK_LAUNCH();
+  const void *sb[8]; void *rb[8]; int to[8], from[8]; size_t nb[8];
+  int n = 0;
+  for (int d = 0; d < 4; d++) {
+    if (!geom.part[d]) continue;
+    const size_t blk = (size_t)2 * geom.faceVh[d] * nelem * sizeof(float4);
+    char *s0 = (char *)mrhs_send + (size_t)mrhs_goff[d][0] * nelem * sizeof(float4), *s1 = (char *)mrhs_send + (size_t)mrhs_goff[d][1] * nelem * sizeof(float4);
+    char *r0 = (char *)mrhs_recv + (size_t)mrhs_goff[d][0] * nelem * sizeof(float4), *r1 = (char *)mrhs_recv + (size_t)mrhs_goff[d][1] * nelem * sizeof(float4);
+    // my slice 0 -> the backward neighbour's "from forward" block [d][1]; my last slice -> the forward neighbour's "from backward" block [d][0]
+    sb[n] = s0; to[n] = comm_neighbor_rank(d, 0); rb[n] = r1; from[n] = comm_neighbor_rank(d, 1); nb[n++] = blk;
+    sb[n] = s1; to[n] = comm_neighbor_rank(d, 1); rb[n] = r0; from[n] = comm_neighbor_rank(d, 0); nb[n++] = blk;
+  }
+  comm_sendrecv_group(n, sb, to, rb, from, nb, r.compute);
 }
 
 // ---- block fields: [parity][cb][kc][r] float4 <-> R single fields [parity][plane kc][cb] float4 ----------------------
@@ -148,6 +246,7 @@ void CoarseBlockField::unpack(SpinorField *const *f) const { block_copy(const_ca
 // ---- the kernel -------------------------------------------------------------------------------------------------
 struct MrhsKernelArgs {
   const float4 *Ymma, *Xinv_mma;
+  const float4 *ghost;   // ghost zone of in_hop (partitioned lattices): one block per ghost site, numbered from 2 Vh in nbr
   const int *nbr;
   float4 *out;
   const float4 *in_hop, *in_diag, *xpay;
@@ -267,8 +366,12 @@ __global__ void __launch_bounds__(MRHS_THREADS, 1) coarse_mrhs_kernel(const Mrhs
           if (d == 8) vsrc = p.in_diag + p.diag_poff[parity] + (size_t)cb * nelem;
           else {
             const int nfs = nb[d];
-            const int np = nfs >= p.Vh ? 1 : 0;
-            vsrc = p.in_hop + p.hop_poff[np] + (size_t)(nfs - (long)np * p.Vh) * nelem;
+            if (nfs >= 2 * p.Vh) {
+              vsrc = p.ghost + (size_t)(nfs - 2 * p.Vh) * nelem;
+            } else {
+              const int np = nfs >= p.Vh ? 1 : 0;
+              vsrc = p.in_hop + p.hop_poff[np] + (size_t)(nfs - (long)np * p.Vh) * nelem;
+            }
           }
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char *st = link0 + (size_t)stage * LINK;
@@ -527,6 +630,11 @@ void coarse_apply_mrhs(const CoarseMrhsArgs &a) {
   k.R = a.R; k.a = a.a; k.b = a.b; k.has_xpay = a.xpay ? 1 : 0;
   k.variant = getenv("QB_MRHS_VARIANT") ? atoi(getenv("QB_MRHS_VARIANT")) : 0;
   if (!k.use_y && !k.diag_kind) QB_ERROR("coarse_apply_mrhs: nothing to apply");
+  if (k.use_y && op.geom.partitioned()) {
+    // halo of the hop input: the parities the output sites read from (both for a full-lattice apply)
+    op.exchange_block_ghost(a.in_hop, a.hop_poff, a.parity < 0 ? 3 : (1 << (1 - a.parity)), a.R);
+    k.ghost = (const float4 *)op.mrhs_recv;
+  }
   const int rows = a.R * (a.mode == 3 ? 4 : 2);
   if (a.R < 1 || a.R > coarse_mrhs_max_rhs(op.N, a.mode))
     QB_ERROR("coarse_apply_mrhs: %d right-hand sides do not fit one launch in mode %d (N = %d: at most %d)", a.R, a.mode, op.N, coarse_mrhs_max_rhs(op.N, a.mode));

@@ -34,7 +34,7 @@ void comm_sendrecv_group(int n, const void *const *sendbuf, const int *to_rank, 
 // is complete when the kernel ends -- no NCCL launch, no host staging, one stream synchronisation where the host needs the scalar.
 // (Reference: kernel -> mapped host memory spin -> MPI_Allreduce, lib/reduce_core.cuh:72-93, lib/face_buffer.cpp:407-428.)
 constexpr int PEER_MAX_RANKS = 16;
-constexpr int PEER_MAX_RED = 64;       // doubles per reduction
+constexpr int PEER_MAX_RED = 192;      // doubles per reduction (block dot products of 64 right-hand sides: 3 x 64)
 struct PeerReduce {
   int rank = 0, size = 1;
   unsigned long long seq = 0;          // sequence number of this reduction (identical on all ranks: reductions are collective)

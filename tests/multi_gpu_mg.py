@@ -42,6 +42,8 @@ def main():
 
     pc = os.environ.get("QB_MG_PC") == "1"   # hierarchy coarsened on the even-odd system + even-odd outer solve (the reference's default)
     ip = inv_param()
+    if os.environ.get("QB_MG_MULTISRC") == "1":
+        ip.verbosity = q.QUDA_SUMMARIZE
     mgp = q.multigrid_param(ip, n_level=3, geo_block=((2, 2, 2, 2), (2, 2, 2, 2)), n_vec=(8, 8), setup_maxiter=100, setup_tol=5e-6,
                             solve_type=q.QUDA_DIRECT_PC_SOLVE if pc else q.QUDA_DIRECT_SOLVE)
     mg = L.newMultigridQuda(C.byref(mgp))
@@ -82,6 +84,35 @@ def main():
         dist.all_gather(tr, torch.tensor([p.true_res, float(p.iter)], dtype=torch.float64, device="cuda"))
         assert all(bool((t == tr[0]).all()) for t in tr), [t.tolist() for t in tr]
     assert p.iter < p0.iter / 2, (p.iter, p0.iter)
+    if os.environ.get("QB_MG_MULTISRC") == "1" and not pc:
+        # block multigrid on the partitioned lattice (BASELINE config 5: multi-RHS coarse grid): ghost zones of block fields in the
+        # tensor-core coarse operator, global block reductions; every solution checked with the global host operator
+        nsrc = 3
+        rngs = np.random.default_rng(5)
+        bgs = [o.drand(2 * o.Vh * 24, seed=21 + k) for k in range(nsrc)]
+        bls = [dist_util.slice_field(bgk, idx, 24) for bgk in bgs]
+        xls = [np.zeros_like(bl) for _ in range(nsrc)]
+        pm = inv_param()
+        pm.inv_type_precondition = q.QUDA_MG_INVERTER
+        pm.preconditioner = mg
+        pm.num_src = nsrc
+        pm.verbosity = q.QUDA_SUMMARIZE
+        L.invertMultiSrcQuda((C.c_void_p * nsrc)(*[a.ctypes.data for a in xls]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bls]), C.byref(pm))
+        for k in range(nsrc):
+            if world > 1:
+                xs = [torch.zeros(xls[k].size, dtype=torch.float64, device="cuda") for _ in range(world)]
+                dist.all_gather(xs, torch.from_numpy(xls[k]).cuda())
+                xg = np.zeros(2 * o.Vh * 24).reshape(-1, 24)
+                for r in range(world):
+                    ridx, _ = dist_util.local_to_global_index(Xl, grid, dist_util.rank_coords(r, grid))
+                    xg[ridx] = xs[r].cpu().numpy().reshape(-1, 24)
+                xg = xg.ravel()
+            else:
+                xg = np.zeros(2 * o.Vh * 24).reshape(-1, 24); xg[idx] = xls[k].reshape(-1, 24); xg = xg.ravel()
+            resk = np.linalg.norm(bgs[k] - o.tm_mat(g, xg, kappa, mu, 1, 0)) / np.linalg.norm(bgs[k])
+            assert resk < 5e-8, (k, resk)
+        if rank == 0:
+            print(f"MULTIGPU_MG_MULTISRC_OK sources={nsrc} lockstep_iters={pm.iter} worst_true_res={pm.true_res:.2e}", flush=True)
     if rank == 0:
         print(f"MULTIGPU_MG_OK ranks={world} grid={grid} local={Xl} pc={int(pc)} peer_reduce={os.environ.get('QB_PEER_REDUCE', '1')} mg_iters={p.iter} plain_iters={p0.iter} host_res={res:.2e} true_res={p.true_res:.2e}", flush=True)
     L.destroyMultigridQuda(mg)
