@@ -39,7 +39,7 @@ def main():
     spl = dist_util.slice_field(sp, idx, 24)
     worst = 0.0
     kappa, mu = 0.1, 0.01
-    for prec, tol in ((8, 1e-13), (4, 1e-6), (2, 2e-3)):
+    for prec, tol in ((8, 1e-13), (4, 1e-6), (2, 1e-3)):   # the north_star tolerances (bench parity gate measures 2.8e-16 / 8.5e-8 / 3.0e-5)
         gp = q.gauge_param(Xl, cuda_prec=prec, reconstruct=12)
         L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in gl]), C.byref(gp))
         for flavor, parity, matpc, dag in ((1, 0, 0, 0), (1, 1, 0, 1), (-1, 0, 2, 1)):

@@ -57,11 +57,10 @@ def run_dslash(c, flavor, parity, matpc, dagger):
 def test_tm_dslash_all_variants_8x8x8x8(quda, oracle, prec, recon):
     """BASELINE config 1 (8^4, random SU(3)) -- dslash_test --test 0, every flavor/parity/matpc/dagger."""
     c = Ctx(quda, oracle, (8, 8, 8, 8), prec, recon)
+    # north_star tolerances for every reconstruction type (fp64 1e-13, fp32 1e-6, half 1e-3; the reference itself asserts 1e-3 for
+    # reconstruct-8, dslash_test.cpp:942-947).  Measured on B200: fp32 recon 18 / 12 / 8 = 8.2e-8 / 8.4e-8 / 2.3e-7, half 2.9e-5 / 3.0e-5 /
+    # 6.4e-5, fp64 1.7e-16 / 2.8e-16 / 6.5e-16
     tol = TOL[prec]
-    if recon == 8 and prec == 4:
-        tol = 5e-6   # fp32 reconstruct-8: trig + rsqrt reconstruction (reference asserts 1e-3 here, dslash_test.cpp:942-947)
-    if recon == 8 and prec == 2:
-        tol = 2e-3
     worst = 0.0
     for flavor in (1, -1):
         for parity in (0, 1):
@@ -69,6 +68,7 @@ def test_tm_dslash_all_variants_8x8x8x8(quda, oracle, prec, recon):
                 for dagger in (0, 1):
                     out, ref = run_dslash(c, flavor, parity, matpc, dagger)
                     worst = max(worst, rel_l2(out, ref))
+    print(f"MEASURED dslash prec {prec} recon {recon}: worst rel L2 over 16 variants = {worst:.3e} (asserted <= {tol})")
     assert worst <= tol, f"prec {prec} recon {recon}: rel L2 {worst:.3e} > {tol}"
 
 
@@ -78,7 +78,8 @@ def test_matpc_and_mat(quda, oracle, prec):
     q = quda
     c = Ctx(quda, oracle, (8, 8, 8, 8), prec, 12)
     L = q.lib()
-    tol = TOL[prec] * (1 if prec != 2 else 2)
+    tol = TOL[prec]   # measured: fp64 2.2e-16, fp32 5.2e-8, half 2.4e-5
+    worst = 0.0
     for flavor in (1, -1):
         for matpc in range(4):
             for dagger in (0, 1):
@@ -86,7 +87,9 @@ def test_matpc_and_mat(quda, oracle, prec):
                 out = np.zeros(c.Vh * 24)
                 L.MatQuda(vp(out), vp(c.even), C.byref(p))
                 ref = c.o.tm_matpc(c.g, c.even, KAPPA, MU, flavor, matpc, dagger)
+                worst = max(worst, rel_l2(out, ref))
                 assert rel_l2(out, ref) <= tol, (flavor, matpc, dagger)
+    print(f"MEASURED matpc prec {prec} recon 12: worst rel L2 = {worst:.3e} (asserted <= {tol})")
     for dagger in (0, 1):
         p = c.param(dagger=dagger, solution_type=q.QUDA_MAT_SOLUTION)
         out = np.zeros(c.o.V * 24)
@@ -262,7 +265,7 @@ print("WORST", worst)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     worst = float(r.stdout.strip().split("WORST")[-1])
-    assert worst <= TOL[prec] * (2 if prec == 2 else 1), worst
+    assert worst <= TOL[prec], worst
 
 
 def test_resident_api_and_large_lattice_properties(quda, oracle):
