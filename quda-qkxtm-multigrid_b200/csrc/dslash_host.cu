@@ -17,8 +17,13 @@ namespace qb {
 
 static int prec_index(Prec p) { return p == PREC_DOUBLE ? 0 : (p == PREC_SINGLE ? 1 : 2); }
 // measurement hook (timeHaloQudaB200): on partitioned lattices run only pack + exchange of a hop, no interior / boundary kernel
-static bool g_halo_only = false;
-void set_halo_only(bool on) { g_halo_only = on; }
+// Phases of a hop on a partitioned lattice.  Normal operation runs all three; the timing hook runs the exchange alone; the pipelined
+// host path of dslashQuda (interface.cu) starts the exchange as soon as the boundary slices of the input have landed, runs the interior
+// in slabs (apply_hop_range) while later slabs are still arriving, and the boundary sites at the end.
+enum { PH_EXCHANGE = 1, PH_BOUNDARY = 2, PH_INTERIOR = 4, PH_SYNC = 8, PH_ALL = 7 };
+static int g_phase_mask = PH_ALL;
+void set_hop_phase(int mask) { g_phase_mask = mask; }
+void set_halo_only(bool on) { g_phase_mask = on ? (PH_EXCHANGE | PH_SYNC) : PH_ALL; }
 static int prec_store_bytes(Prec p) { return p == PREC_HALF ? 2 : (int)p; }
 
 void Lattice::init(const int *X, int t_boundary_sign, double anisotropy) {
@@ -186,7 +191,18 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, st);
     return;
   }
-  if (range_count >= 0) QB_ERROR("apply_hop_range is only available on unpartitioned lattices");
+  if (range_count >= 0) {
+    // slab of the interior (pipelined host path): only for a T-only partition, where the interior is the contiguous block of the
+    // time slices 1 .. T-2 and a slab needs nothing but its own and the two adjacent slabs of `in`
+    if (g.part[0] || g.part[1] || g.part[2] || !lat.interior_contiguous[parity]) QB_ERROR("apply_hop_range on a partitioned lattice needs a T-only partition");
+    const int lo = std::max(range_begin, lat.interior_begin[parity]);
+    const int hi = std::min(range_begin + range_count, lat.interior_begin[parity] + lat.n_interior[parity]);
+    if (hi > lo) {
+      p.site_begin = lo; p.site_count = hi - lo; p.site_list = nullptr;
+      launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, range_stream ? range_stream : r.compute);
+    }
+    return;
+  }
 
   const int pi = prec_index(Store::prec);
   ensure_arena(lat, Store::prec);
@@ -226,32 +242,40 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   // compute the boundary sites right there -- they are few (2 faces of X*Y*Z/2 sites for a T split), so
   // the launch is latency-bound and hides completely under the interior kernel running on the compute stream.
   // Interior and boundary launches write disjoint sites of `out`.
-  QB_CUDA(cudaEventRecord(r.ev_in_ready, r.compute));
-  QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_in_ready, 0));
-  launch_pack_T<Store>(pk, twist_in, r.halo);
-  if (!self) comm_exchange_halo(lat, pi, r.halo);
+  const int mask = g_phase_mask;
+  if (mask & PH_EXCHANGE) {
+    QB_CUDA(cudaEventRecord(r.ev_in_ready, r.compute));
+    QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_in_ready, 0));
+    launch_pack_T<Store>(pk, twist_in, r.halo);
+    if (!self) comm_exchange_halo(lat, pi, r.halo);
+    if (!(mask & PH_BOUNDARY)) {
+      QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
+      if (mask & PH_SYNC) QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
+    }
+  }
 
   const int np = parity;
-  DslashParam pb = p;
-  if (g_halo_only) {
-    QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
-    QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
-    return;
+  if (mask & PH_BOUNDARY) {
+    DslashParam pb = p;
+    // with the exchange in this call: on the halo stream right behind it; alone (pipelined host path): on the compute stream, after
+    // the exchange started earlier has finished
+    cudaStream_t bs = (mask & PH_EXCHANGE) ? r.halo : r.compute;
+    if (!(mask & PH_EXCHANGE)) QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
+    if (lat.n_boundary[np]) {
+      pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
+      launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, bs);
+    }
+    if (mask & PH_EXCHANGE) QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
   }
-  if (lat.n_boundary[np]) {
-    pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
-    launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, r.halo);
-  }
-  QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
 
   // interior sites: everything that needs no remote data, overlapping with pack + exchange + boundary
-  if (lat.n_interior[np]) {
+  if ((mask & PH_INTERIOR) && lat.n_interior[np]) {
     p.site_count = lat.n_interior[np];
     if (lat.interior_contiguous[np]) { p.site_begin = lat.interior_begin[np]; p.site_list = nullptr; }
     else { p.site_begin = 0; p.site_list = lat.interior_list[np]; }
     launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, r.compute);
   }
-  QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
+  if ((mask & PH_EXCHANGE) && (mask & PH_BOUNDARY)) QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
 }
 
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,

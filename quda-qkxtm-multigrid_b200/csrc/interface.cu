@@ -145,6 +145,7 @@ void mass_rescale_out(SpinorField &out, const QudaInvertParam *p, bool pc, bool 
 // accessors used by solver / multigrid glue
 namespace qb {
 void set_halo_only(bool on);  // dslash_host.cu
+void set_hop_phase(int mask); // dslash_host.cu: 1 pack + exchange, 2 boundary sites, 4 interior (7 = a whole hop)
 Lattice &global_lattice() { return G.lat; }
 const GaugeField *global_gauge(Prec prec) { return pick_gauge(prec); }
 }
@@ -566,7 +567,11 @@ void pipe_cleanup_c() {
 
 static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaParity parity, SpinorField &in, SpinorField &out) {
   const Geom &g = G.lat.geom;
-  if (g.part[0] || g.part[1] || g.part[2] || g.part[3]) return false;
+  // partitioned lattices: T-only splits (the default decomposition up to 4 ranks, and the weak-scaling layout of bench.py).  The faces are
+  // the time slices 0 and T-1: they travel first, the halo exchange starts as soon as they have landed and overlaps the remaining copies;
+  // the interior is multiplied slab by slab as on one GPU, the two boundary slices at the end.
+  if (g.part[0] || g.part[1] || g.part[2]) return false;
+  const bool part_t = g.part[3] != 0;
   if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH || p->dslash_type == QUDA_CLOVER_WILSON_DSLASH || in.nflavor != 1) return false;  // two kernels per hop: plain path
   if (p->input_location != QUDA_CPU_FIELD_LOCATION || p->output_location != QUDA_CPU_FIELD_LOCATION) return false;
   const int T = g.X[3];
@@ -576,13 +581,14 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   // Measured with CUDA events on B200 (QB_PIPE_TRACE=1, 32^3x64 fp32, link floor 2.04 ms): every extra copy costs the H2D stream ~30 us,
   // the first D2H cannot start before the first three slabs are in, and the D2H stream runs one slab behind the H2D stream.  So: few
   // slabs, thin ones at the head (the first results leave early) and tapering ones at the end (little is left when the last input lands).
-  static const int want = getenv("QB_PIPE_CHUNKS") ? atoi(getenv("QB_PIPE_CHUNKS")) : 13;   // 9 / 11 / 13 slabs: 3.06 / 2.82 / 2.73 ms (uniform 16: 2.88 ms)
-  static const bool uniform = getenv("QB_PIPE_UNIFORM") && atoi(getenv("QB_PIPE_UNIFORM"));
+  const int want = getenv("QB_PIPE_CHUNKS") ? atoi(getenv("QB_PIPE_CHUNKS")) : 13;   // 9 / 11 / 13 slabs: 3.06 / 2.82 / 2.73 ms (uniform 16: 2.88 ms)
+  const bool uniform = getenv("QB_PIPE_UNIFORM") && atoi(getenv("QB_PIPE_UNIFORM"));   // two getenv per call (microseconds against a millisecond call): the tests switch them per case
   const bool tapered = !uniform && T >= 32 && want >= 8;
   std::vector<int> tslices;   // time slices per slab
   if (tapered) {
     const int head = std::max(1, T / 32);
-    const int tail[4] = {std::max(1, T / 16), std::max(1, T / 32), 1, 1};
+    // T partition: the last slab is exactly the face slice T-1 plus its neighbour (the boundary kernel reads T-2 as well)
+    const int tail[4] = {std::max(1, T / 16), std::max(1, T / 32), 1, part_t ? 2 : 1};
     const int rest = T - 2 * head - (tail[0] + tail[1] + tail[2] + tail[3]);
     const int nbig = std::max(1, std::min(want - 6, rest));
     tslices.push_back(head); tslices.push_back(head);
@@ -634,13 +640,20 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
   }
   if (trace) QB_CUDA(cudaEventRecord(tr[1], pipe_state.h2d));
   bool first_out = true;
-  auto process = [&](int k) {
-    d->DslashRange(out, in, (int)parity, (int)begin[k], (int)count[k], r.compute);
-    export_spinor_range(stage_out, out, hp, basis, order, begin[k], count[k], r.compute);
-    QB_CUDA(cudaEventRecord(pipe_state.ev_out[k], r.compute));
-    QB_CUDA(cudaStreamWaitEvent(pipe_state.d2h, pipe_state.ev_out[k], 0));
+  auto ship = [&](long b0, long n, cudaEvent_t ev) {   // reorder [b0, b0 + n) of `out` for the host and start its way back
+    if (n <= 0) return;
+    export_spinor_range(stage_out, out, hp, basis, order, b0, n, r.compute);
+    QB_CUDA(cudaEventRecord(ev, r.compute));
+    QB_CUDA(cudaStreamWaitEvent(pipe_state.d2h, ev, 0));
     if (trace && first_out) { QB_CUDA(cudaEventRecord(tr[2], pipe_state.d2h)); first_out = false; }
-    QB_CUDA(cudaMemcpyAsync((char *)h_out + begin[k] * site_bytes, stage_out + begin[k] * site_bytes, count[k] * site_bytes, cudaMemcpyDeviceToHost, pipe_state.d2h));
+    QB_CUDA(cudaMemcpyAsync((char *)h_out + b0 * site_bytes, stage_out + b0 * site_bytes, n * site_bytes, cudaMemcpyDeviceToHost, pipe_state.d2h));
+  };
+  auto process = [&](int k) {
+    d->DslashRange(out, in, (int)parity, (int)begin[k], (int)count[k], r.compute);   // partitioned: clipped to the interior slices
+    long b0 = begin[k], n = count[k];
+    if (part_t && k == 0) { b0 += slice_sites; n -= slice_sites; }   // the face slices leave after the boundary launch
+    if (part_t && k == nchunk - 1) n -= slice_sites;
+    ship(b0, n, pipe_state.ev_out[k]);
   };
   // convert every slab as it lands; slab k is multiplied once k-1, k, k+1 (periodic) are there: arrival order n-1, 0, 1, ... => after
   // slab c >= 1 has landed, slab c-1 is complete; the tail is n-2 and n-1
@@ -648,10 +661,29 @@ static bool dslash_pipelined(void *h_out, void *h_in, QudaInvertParam *p, QudaPa
     const int c = arrival[a];
     QB_CUDA(cudaStreamWaitEvent(r.compute, pipe_state.ev_in[c], 0));
     import_spinor_range(in, stage_in, hp, basis, order, begin[c], count[c], r.compute);
+    if (part_t && a == 1) {
+      // both face slices are on the device: pack and exchange them now (halo stream), under the copies still to come
+      set_hop_phase(1);
+      d->Dslash(out, in, (int)parity);
+      set_hop_phase(7);
+    }
     if (a >= 2) process(c - 1);
   }
   process(nchunk - 2);
   process(nchunk - 1);
+  if (part_t) {
+    // boundary sites (time slices 0 and T-1) from the ghost zone, then their way back
+    set_hop_phase(2);
+    d->Dslash(out, in, (int)parity);
+    set_hop_phase(7);
+    while ((int)pipe_state.ev_out.size() < nchunk + 2) {
+      cudaEvent_t e;
+      QB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      pipe_state.ev_out.push_back(e);
+    }
+    ship(0, slice_sites, pipe_state.ev_out[nchunk]);
+    ship((long)(T - 1) * slice_sites, slice_sites, pipe_state.ev_out[nchunk + 1]);
+  }
   if (trace) {
     QB_CUDA(cudaEventRecord(tr[3], pipe_state.d2h));
     QB_CUDA(cudaEventSynchronize(tr[3]));

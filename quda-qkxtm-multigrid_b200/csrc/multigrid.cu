@@ -3,6 +3,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
+#include "comm.h"
 #include "multigrid.h"
 
 namespace qb {
@@ -240,69 +243,137 @@ void MG::generate_null_vectors() {
   }
 }
 
-// Near-null vector files (multigrid.cpp:607-691 uses QIO's read/write_spinor_field; QIO / LIME are not available here, so the
-// container is a plain binary one): <name>_level_<l>[_rank_<r>] =  header, then n_vec vectors of this rank's sub-lattice in the
-// order [parity][x_cb][spin][colour][re, im], fp32.
+// Near-null vector files (multigrid.cpp:607-691 uses QIO's read / write_spinor_field; QIO / LIME are not in this image, so files
+// written by the reference cannot be read here and vice versa -- stated in INTEGRATION.md and in the error message below).  The
+// container is ONE file per level, <name>_level_<l>, independent of the rank layout: a setup saved on N ranks loads on M ranks.
+//   bytes 0..127  header, little-endian: char magic[8] = "QB200VEC"; int32 version = 2, level, nvec, nspin, ncolor, global X[4], prec (4)
+//   then nvec vectors, each the GLOBAL field in lexicographic site order (x fastest, then y, z, t; NOT even-odd),
+//   per site [spin][colour][re, im] float32, DeGrand-Rossi basis on the fine level (coarse levels: spin = chirality, colour = vector index)
+// Every rank writes / reads the runs of sites it owns at their global offsets (pwrite / pread).
 namespace {
+constexpr int VEC_HEADER_BYTES = 128;
 struct VecFileHeader {
   char magic[8];          // "QB200VEC"
-  int version, level, nvec, nspin, ncolor, X[4], rank, nranks, prec;
+  int version, level, nvec, nspin, ncolor, X[4], prec;
 };
-std::string vec_file_name(const std::string &base, int level) {
-  std::string n = base + "_level_" + std::to_string(level);
-  if (rt().size > 1) n += "_rank_" + std::to_string(rt().rank);
-  return n;
-}
+static_assert(sizeof(VecFileHeader) <= VEC_HEADER_BYTES, "header layout");
+std::string vec_file_name(const std::string &base, int level) { return base + "_level_" + std::to_string(level); }
 void level_dims(const Dirac *m, int *X) {
   if (const DiracTM *d = dynamic_cast<const DiracTM *>(m)) for (int k = 0; k < 4; k++) X[k] = d->lat->geom.X[k];
   else if (const DiracCoarse *c = dynamic_cast<const DiracCoarse *>(m)) for (int k = 0; k < 4; k++) X[k] = c->op->geom.X[k];
   else QB_ERROR("MG: unknown operator type");
+}
+// local host order [parity][x_cb][component] <-> local lexicographic order (x fastest)
+void to_lex(std::vector<float> &lex, std::vector<float> &eo, const int *X, int ncomp2, bool back) {
+  const long V = (long)X[0] * X[1] * X[2] * X[3], Vh = V / 2;
+  for (long i = 0; i < V; i++) {
+    const int x = (int)(i % X[0]), y = (int)((i / X[0]) % X[1]), z = (int)((i / ((long)X[0] * X[1])) % X[2]), t = (int)(i / ((long)X[0] * X[1] * X[2]));
+    const long e = (long)((x + y + z + t) & 1) * Vh + (i >> 1);
+    if (back) memcpy(eo.data() + e * ncomp2, lex.data() + i * ncomp2, sizeof(float) * ncomp2);
+    else memcpy(lex.data() + i * ncomp2, eo.data() + e * ncomp2, sizeof(float) * ncomp2);
+  }
+}
+// calls f(local lexicographic start site, run length in sites, global lexicographic start site) for every run of this rank's sites that
+// is contiguous in the global file
+template <typename F> void for_each_run(const int *X, F f) {
+  const Runtime &r = rt();
+  int G[4], off[4];
+  for (int d = 0; d < 4; d++) { G[d] = X[d] * r.grid[d]; off[d] = r.coord[d] * X[d]; }
+  // a run covers the dimensions 0..m-1 entirely, where all of grid[0..m-2] are 1 (the x extent of a rank is always contiguous)
+  int m = 1;
+  while (m < 4 && r.grid[m - 1] == 1) m++;
+  long run = 1;
+  for (int d = 0; d < m; d++) run *= X[d];
+  long outer = 1;
+  for (int d = m; d < 4; d++) outer *= X[d];
+  for (long o = 0; o < outer; o++) {
+    int c[4] = {0, 0, 0, 0};
+    long rem = o;
+    for (int d = m; d < 4; d++) { c[d] = (int)(rem % X[d]); rem /= X[d]; }
+    const long lstart = (((long)c[3] * X[2] + c[2]) * X[1] + c[1]) * X[0] + c[0];
+    const long gstart = ((((long)(c[3] + off[3]) * G[2] + (c[2] + off[2])) * G[1] + (c[1] + off[1])) * G[0]) + (c[0] + off[0]);
+    f(lstart, run, gstart);
+  }
 }
 }  // namespace
 
 void MG::save_vectors() {
   const std::string name = vec_file_name(mp.vec_outfile, level);
   log_msg(1, "MG level %d: saving %d vectors to %s\n", level + 1, (int)B.size(), name.c_str());
-  FILE *f = fopen(name.c_str(), "wb");
-  if (!f) QB_ERROR("cannot open %s for writing", name.c_str());
+  Runtime &r = rt();
   VecFileHeader h{};
   memcpy(h.magic, "QB200VEC", 8);
-  h.version = 1; h.level = level; h.nvec = (int)B.size(); h.nspin = B[0]->nspin; h.ncolor = B[0]->ncolor;
-  level_dims(matResidual, h.X);
-  h.rank = rt().rank; h.nranks = rt().size; h.prec = 4;
-  if (fwrite(&h, sizeof(h), 1, f) != 1) QB_ERROR("write error on %s", name.c_str());
-  std::vector<float> host(B[0]->bytes() / sizeof(float));
-  for (auto &v : B) {
-    export_generic(host.data(), *v, rt().compute);
-    if (fwrite(host.data(), sizeof(float), host.size(), f) != host.size()) QB_ERROR("write error on %s", name.c_str());
+  h.version = 2; h.level = level; h.nvec = (int)B.size(); h.nspin = B[0]->nspin; h.ncolor = B[0]->ncolor; h.prec = 4;
+  int X[4];
+  level_dims(matResidual, X);
+  long Vg = 1;
+  for (int d = 0; d < 4; d++) { h.X[d] = X[d] * r.grid[d]; Vg *= h.X[d]; }
+  const int nc2 = B[0]->ncomplex * 2;
+  if (r.rank == 0) {
+    FILE *f = fopen(name.c_str(), "wb");
+    if (!f) QB_ERROR("cannot open %s for writing", name.c_str());
+    char head[VEC_HEADER_BYTES] = {0};
+    memcpy(head, &h, sizeof(h));
+    if (fwrite(head, 1, VEC_HEADER_BYTES, f) != VEC_HEADER_BYTES) QB_ERROR("write error on %s", name.c_str());
+    fclose(f);
   }
-  fclose(f);
+  comm_barrier();
+  const int fd = open(name.c_str(), O_WRONLY);
+  if (fd < 0) QB_ERROR("cannot open %s for writing", name.c_str());
+  const long V = (long)X[0] * X[1] * X[2] * X[3];
+  std::vector<float> host((size_t)V * nc2), lex((size_t)V * nc2);
+  for (size_t k = 0; k < B.size(); k++) {
+    export_generic(host.data(), *B[k], r.compute);
+    to_lex(lex, host, X, nc2, false);
+    for_each_run(X, [&](long ls, long n, long gs) {
+      const off_t at = VEC_HEADER_BYTES + ((off_t)k * Vg + gs) * nc2 * (off_t)sizeof(float);
+      const size_t bytes = (size_t)n * nc2 * sizeof(float);
+      if (pwrite(fd, lex.data() + ls * nc2, bytes, at) != (ssize_t)bytes) QB_ERROR("write error on %s", name.c_str());
+    });
+  }
+  close(fd);
+  comm_barrier();
 }
 
 void MG::load_vectors() {
   const MGLevelParam &lp = mp.level[level];
   const std::string name = vec_file_name(mp.vec_infile, level);
   log_msg(1, "MG level %d: loading %d vectors from %s\n", level + 1, lp.nvec, name.c_str());
-  FILE *f = fopen(name.c_str(), "rb");
-  if (!f) QB_ERROR("cannot open %s for reading", name.c_str());
+  Runtime &r = rt();
+  const int fd = open(name.c_str(), O_RDONLY);
+  if (fd < 0) QB_ERROR("cannot open %s for reading", name.c_str());
+  char head[VEC_HEADER_BYTES];
   VecFileHeader h{};
-  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "QB200VEC", 8) != 0 || h.version != 1) QB_ERROR("%s is not a null-vector file of this library", name.c_str());
+  if (pread(fd, head, VEC_HEADER_BYTES, 0) != VEC_HEADER_BYTES) QB_ERROR("%s is truncated", name.c_str());
+  memcpy(&h, head, sizeof(h));
+  if (memcmp(h.magic, "QB200VEC", 8) != 0 || h.version != 2)
+    QB_ERROR("%s is not a near-null vector file of this library (version 2 container, see INTEGRATION.md; the reference's QIO / LIME files are not readable here)", name.c_str());
   std::unique_ptr<SpinorField> like(new_full(*matResidual));
   int X[4];
   level_dims(matResidual, X);
-  if (h.level != level || h.nvec < lp.nvec || h.nspin != like->nspin || h.ncolor != like->ncolor || h.nranks != rt().size || h.rank != rt().rank ||
-      h.X[0] != X[0] || h.X[1] != X[1] || h.X[2] != X[2] || h.X[3] != X[3])
-    QB_ERROR("%s does not match this level (file: level %d, %d vectors, %d x %d components, %d x %d x %d x %d, rank %d of %d)", name.c_str(), h.level, h.nvec,
-             h.nspin, h.ncolor, h.X[0], h.X[1], h.X[2], h.X[3], h.rank, h.nranks);
-  std::vector<float> host(like->bytes() / sizeof(float));
+  long Vg = 1;
+  bool dims_ok = true;
+  for (int d = 0; d < 4; d++) { dims_ok = dims_ok && h.X[d] == X[d] * r.grid[d]; Vg *= h.X[d]; }
+  if (h.level != level || h.nvec < lp.nvec || h.nspin != like->nspin || h.ncolor != like->ncolor || !dims_ok)
+    QB_ERROR("%s does not match this level (file: level %d, %d vectors, %d x %d components, global lattice %d x %d x %d x %d)", name.c_str(), h.level, h.nvec,
+             h.nspin, h.ncolor, h.X[0], h.X[1], h.X[2], h.X[3]);
+  const int nc2 = like->ncomplex * 2;
+  const long V = (long)X[0] * X[1] * X[2] * X[3];
+  std::vector<float> host((size_t)V * nc2), lex((size_t)V * nc2);
   B.clear();
-  for (int i = 0; i < lp.nvec; i++) {
-    if (fread(host.data(), sizeof(float), host.size(), f) != host.size()) QB_ERROR("%s is truncated", name.c_str());
+  for (int k = 0; k < lp.nvec; k++) {
+    for_each_run(X, [&](long ls, long n, long gs) {
+      const off_t at = VEC_HEADER_BYTES + ((off_t)k * Vg + gs) * nc2 * (off_t)sizeof(float);
+      const size_t bytes = (size_t)n * nc2 * sizeof(float);
+      if (pread(fd, lex.data() + ls * nc2, bytes, at) != (ssize_t)bytes) QB_ERROR("%s is truncated", name.c_str());
+    });
+    to_lex(lex, host, X, nc2, true);
     std::unique_ptr<SpinorField> v(new_full(*matResidual));
-    import_generic(*v, host.data(), rt().compute);
+    import_generic(*v, host.data(), r.compute);
+    QB_CUDA(cudaStreamSynchronize(r.compute));
     B.push_back(std::move(v));
   }
-  fclose(f);
+  close(fd);
 }
 
 // x <- smoother applied to M x = b through the (possibly even-odd preconditioned) smoother operator

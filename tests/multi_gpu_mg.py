@@ -46,6 +46,8 @@ def main():
         ip.verbosity = q.QUDA_SUMMARIZE
     mgp = q.multigrid_param(ip, n_level=3, geo_block=((2, 2, 2, 2), (2, 2, 2, 2)), n_vec=(8, 8), setup_maxiter=100, setup_tol=5e-6,
                             solve_type=q.QUDA_DIRECT_PC_SOLVE if pc else q.QUDA_DIRECT_SOLVE)
+    if os.environ.get("QB_MG_VECFILE"):
+        mgp.vec_outfile = os.environ["QB_MG_VECFILE"].encode()
     mg = L.newMultigridQuda(C.byref(mgp))
     for lvl in (0, 1):
         dev = (C.c_double * 3)()

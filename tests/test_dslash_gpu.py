@@ -380,3 +380,39 @@ def test_pipelined_host_path_matches_oracle(quda, oracle, X, uniform, monkeypatc
         quda.lib().dslashQuda(vp(out), vp(src), C.byref(p), parity)
         oracle.set_dims(X)
         assert rel_l2(out, oracle.tm_dslash(c.g, src, KAPPA, MU, 1, parity, 0, dagger)) <= TOL[4]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("X,uniform", [((16, 16, 16, 32), 0), ((16, 16, 16, 32), 1), ((12, 12, 24, 48), 0)])
+def test_pipelined_host_path_on_t_partitioned_lattice(oracle, X, uniform):
+    """the slab pipeline of dslashQuda on a lattice partitioned in T (self-exchange on one GPU): the face slices travel first and
+    their halo exchange overlaps the remaining copies, the interior is multiplied slab by slab, the boundary slices last"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, {root!r})
+import quda_b200 as q
+from tests import oracle_util as ou
+o = ou.load_oracle(); X={X!r}; o.set_dims(X)
+g = o.gauge(1, True, 1.0, 137); sp = o.drand(2*o.Vh*24, 137)
+L = q.lib(); L.initQuda(0); L.commDimPartitionedSetQudaB200(8)
+gp = q.gauge_param(X, cuda_prec=4, reconstruct=12)
+L.loadGaugeQuda((C.c_void_p*4)(*[a.ctypes.data for a in g]), C.byref(gp))
+worst = 0.0
+for flavor, parity, matpc, dag in [(1,0,0,0),(1,1,0,1),(-1,0,2,1)]:
+    p = q.invert_param(cuda_prec=4, flavor=flavor, matpc=matpc, dagger=dag)
+    src = sp[(1-parity)*o.Vh*24:(2-parity)*o.Vh*24].copy() if False else (sp[:o.Vh*24].copy() if parity == 0 else sp[o.Vh*24:].copy())
+    out = np.zeros(o.Vh*24)
+    L.dslashQuda(out.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), C.byref(p), parity)
+    worst = max(worst, ou.rel_l2(out, o.tm_dslash(g, src, 0.1, 0.01, flavor, parity, matpc, dag)))
+L.endQuda()
+print("WORST", worst)
+"""
+    env = dict(os.environ, QB_PIPE_UNIFORM=str(uniform), QB_PIPE_TRACE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "dslashQuda pipeline:" in r.stderr, r.stderr[-2000:]    # the pipelined path was taken
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst <= TOL[4], worst

@@ -138,7 +138,8 @@ def test_face_index_map_bit_exact(quda, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks,grid,local", [(2, "1,1,1,2", "8,4,6,8"), (2, "1,1,2,1", "4,4,4,8"), (4, "1,1,2,2", "4,4,4,4")])
+@pytest.mark.parametrize("nranks,grid,local", [(2, "1,1,1,2", "8,4,6,8"), (2, "1,1,2,1", "4,4,4,8"), (4, "1,1,2,2", "4,4,4,4"),
+                                               (2, "1,1,1,2", "16,16,16,32")])   # the last one is large enough for the slab-pipelined host path
 def test_nccl_halo_exchange_vs_global_oracle(nranks, grid, local):
     import torch
     if torch.cuda.device_count() < nranks:
@@ -181,3 +182,44 @@ def test_distributed_block_multigrid(nranks, grid):
     assert r.returncode == 0 and "MULTIGPU_MG_MULTISRC_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     assert "null vectors from one batched BiCGStab on the multi-RHS tensor-core operator" in r.stdout, r.stdout[-3000:]
     assert "invertMultiSrcQuda: block of 3 sources" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.gpu
+def test_null_vectors_saved_on_two_ranks_load_on_one(quda, oracle, tmp_path):
+    """the near-null vector container is independent of the rank layout: a 3-level setup saved by 2 ranks (T split) is loaded by this
+    single-rank process (compute_null_vector = NO) and preconditions the same solve in the same number of iterations"""
+    import ctypes as C
+    import re
+    import numpy as np
+    import torch
+    from tests.test_multigrid_gpu import host_residual, load_gauge, mg_inv_param, vp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    base = str(tmp_path / "nv2")
+    env = dict(os.environ, QB_GRID="1,1,1,2", QB_LOCAL="8,8,8,8", QB_MG_VECFILE=base)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29677", os.path.join(ROOT, "tests", "multi_gpu_mg.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTIGPU_MG_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    it2 = int(re.search(r"mg_iters=(\d+)", r.stdout).group(1))
+    assert os.path.exists(base + "_level_0") and os.path.exists(base + "_level_1")
+    q, L = quda, quda.lib()
+    X, kappa, mu = (8, 8, 8, 16), 0.1245, 0.005
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=True, seed=4711)
+    load_gauge(q, g, X, prec=8, sloppy=4, precond=4, recon=12, antiperiodic=True)
+    ip = mg_inv_param(q, kappa, mu)
+    mgp = q.multigrid_param(ip, n_level=3, geo_block=((2, 2, 2, 2), (2, 2, 2, 2)), n_vec=(8, 8), setup_maxiter=100, setup_tol=5e-6)
+    mgp.compute_null_vector = q.QUDA_COMPUTE_NULL_VECTOR_NO
+    mgp.vec_infile = base.encode()
+    mg = L.newMultigridQuda(C.byref(mgp))
+    b = oracle.drand(2 * oracle.Vh * 24, seed=11)
+    x = np.zeros_like(b)
+    p = mg_inv_param(q, kappa, mu)
+    p.inv_type_precondition = q.QUDA_MG_INVERTER
+    p.preconditioner = mg
+    p.gcrNkrylov = 20; p.tol = 1e-8; p.maxiter = 2000; p.reliable_delta = 1e-4
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    res = host_residual(oracle, g, x, b, kappa, mu)
+    L.destroyMultigridQuda(mg)
+    assert res < 5e-8 and abs(p.iter - it2) <= 2, (res, p.iter, it2)

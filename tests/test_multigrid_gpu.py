@@ -358,6 +358,15 @@ def test_null_vector_files_round_trip(quda, oracle, tmp_path):
     v1, it1, res1, t1 = build(True)
     import os
     assert os.path.exists(base.decode() + "_level_0") and os.path.exists(base.decode() + "_level_1")
+    # documented layout: 128-byte header, then global lexicographic sites, [spin][colour][re,im] fp32
+    raw = open(base.decode() + "_level_0", "rb").read()
+    hdr = np.frombuffer(raw[8:8 + 10 * 4], dtype="<i4")
+    assert raw[:8] == b"QB200VEC" and list(hdr) == [2, 0, 8, 4, 3, 8, 8, 8, 16, 4]
+    vec3 = np.frombuffer(raw, dtype="<f4", offset=128 + 3 * oracle.V * 24 * 4, count=oracle.V * 24).reshape(oracle.V, 24)
+    lex = np.arange(oracle.V)
+    xs, ys, zs, ts = lex % 8, (lex // 8) % 8, (lex // 64) % 8, lex // 512
+    eo = ((xs + ys + zs + ts) & 1) * oracle.Vh + (lex >> 1)
+    assert np.array_equal(vec3, v1[0].reshape(oracle.V, 24)[eo])
     v2, it2, res2, t2 = build(False)
     print(f"null-vector files: setup {t1:.2f} s computing, {t2:.2f} s loading; MG-GCR {it1} / {it2} iterations, residuals {res1:.2e} / {res2:.2e}")
     for a, b_ in zip(v1, v2):
