@@ -372,7 +372,7 @@ def cpu_baseline_coarse(oracle):
     return out
 
 
-def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=False):
+def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=False, multi_src=None):
     """Second half of the BASELINE metric: 3-level MG-GCR twisted-mass solve (seconds), plus the coarse-operator
     kernels against their HBM roofline.  32^3x64, 4^4 then 2^4 aggregates, 24 vectors per level, MR(2,2) smoother,
     K-cycle, fp64 outer GCR(20) / fp32 MG / int16 level-0 smoother, weak-field SU(3) gauge (periodic)."""
@@ -436,7 +436,9 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=Fal
     # 12 spin-colour point sources of one propagator: invertMultiSrcQuda on the block path (all sources through the K-cycle in
     # lock-step, coarse levels on the multi-RHS tensor-core operator) against the same call with the block path switched off
     multi = None
-    if full and os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
+    if multi_src is None:
+        multi_src = full
+    if multi_src and os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
         nsrc = int(os.environ.get("QB_BENCH_NSRC", "12"))
         bs = []
         for k in range(nsrc):
@@ -450,6 +452,8 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=Fal
             pm.inv_type_precondition = q.QUDA_MG_INVERTER
             pm.preconditioner = mg
             pm.num_src = nsrc
+            if pc:
+                pm.solve_type = q.QUDA_DIRECT_PC_SOLVE
             ptr_x, ptr_b = (C.c_void_p * nsrc)(*[a.ctypes.data for a in xs]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bs])
             if name == "block":
                 L.invertMultiSrcQuda(ptr_x, ptr_b, C.byref(pm))  # warm-up (allocations), as for the single solve above
@@ -748,7 +752,7 @@ def main():
     if world == 1 and not args.no_mg and not args.no_extra:
         mg_res = run_mg_leg(q, L, oracle, X, args.mg_precond)
         mg_res_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False)
-        mg_res_pc = run_mg_leg(q, L, oracle, X, args.mg_precond, full=False, pc=True)
+        mg_res_pc = run_mg_leg(q, L, oracle, X, args.mg_precond, full=False, pc=True, multi_src=True)
         mg_res_pc_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False, pc=True)
     sampler.stop_flag = True
 

@@ -495,11 +495,11 @@ struct BlockMGLevel {
   CoarseOperator *op;
   int R, mode, p, q;
   long Vh; int N; size_t pf4;    // float4 per parity block
-  std::unique_ptr<CoarseBlockField> x, b, r, t;
+  std::unique_ptr<CoarseBlockField> x, b, r, t, pview;   // pview: non-owning single-parity view used for pack / unpack of scratch buffers
   std::unique_ptr<BlockOps> ops_full, ops_par;
-  std::unique_ptr<BlockKrylov<BlockOps>> smoother, kcycle_gcr;
+  std::unique_ptr<BlockKrylov<BlockOps>> smoother, kcycle_gcr, kcycle_gcr_par;
   std::unique_ptr<BlockMhat> mhat;
-  float *s1 = nullptr, *s2 = nullptr, *src = nullptr;   // parity scratch
+  float *s1 = nullptr, *s2 = nullptr, *src = nullptr, *rp = nullptr, *s_k = nullptr;   // parity scratch (rp: residual, s_k: source of the K-cycle's even-odd system)
   std::vector<std::unique_ptr<SpinorField>> fx, fb;     // R single fields of this level (transfers to / from the neighbours)
   double t_prof[6] = {0, 0, 0, 0, 0, 0};                // smooth-pre, residual, restrict, coarse solve, prolong, smooth-post
 
@@ -518,15 +518,29 @@ struct BlockMGLevel {
     ops_par.reset(new BlockOps((long)pf4, R));
     smoother.reset(new BlockKrylov<BlockOps>(*ops_par));
     kcycle_gcr.reset(new BlockKrylov<BlockOps>(*ops_full));
+    kcycle_gcr_par.reset(new BlockKrylov<BlockOps>(*ops_par));
     mhat.reset(new BlockMhat(*op, p, R, mode));
-    s1 = ops_par->make(); s2 = ops_par->make(); src = ops_par->make();
+    s1 = ops_par->make(); s2 = ops_par->make(); src = ops_par->make(); rp = ops_par->make(); s_k = ops_par->make();
+    pview.reset(new CoarseBlockField(Vh, 1, N, R, rp));
     for (int c = 0; c < R; c++) {
       fx.emplace_back(new SpinorField(Vh, 2, PREC_SINGLE, 2, op->nvec));
       fb.emplace_back(new SpinorField(Vh, 2, PREC_SINGLE, 2, op->nvec));
       blas::zero(*fx.back()); blas::zero(*fb.back());
     }
   }
-  ~BlockMGLevel() { pool_free(s1); pool_free(s2); pool_free(src); }
+  ~BlockMGLevel() { pool_free(s1); pool_free(s2); pool_free(src); pool_free(rp); pool_free(s_k); }
+  // source of the even-odd system from a full-lattice right-hand side: out = Xinv_p (b_p - Y_pq Xinv_q b_q)   (DiracCoarsePC::prepare)
+  void prepare(float *out, CoarseBlockField &bb) {
+    float *bp = par(bb, p), *bq = par(bb, q);
+    mhat->launch(s1, nullptr, bq, nullptr, q, false, true, 1.f, 0.f);
+    mhat->launch(s2, s1, nullptr, bp, p, true, false, -1.f, 1.f);
+    mhat->launch(out, nullptr, s2, nullptr, p, false, true, 1.f, 0.f);
+  }
+  // x_q = Xinv_q (b_q - Y_qp x_p)   (DiracCoarsePC::reconstruct)
+  void reconstruct(CoarseBlockField &xx, CoarseBlockField &bb) {
+    mhat->launch(s1, par(xx, p), nullptr, par(bb, q), q, true, false, -1.f, 1.f);
+    mhat->launch(par(xx, q), nullptr, s1, nullptr, q, false, true, 1.f, 0.f);
+  }
   float *par(CoarseBlockField &f, int parity) const { return f.v + (size_t)parity * pf4 * 4; }
 
   // out = M in on full block fields
@@ -574,6 +588,13 @@ class BlockMG {
     MG &m = *L.mg;
     const MGLevelParam &lp = m.mp.level[m.level];
     if (!m.coarse) { BSection s_(&L.t_prof[0]); L.smooth(x, b, true, 0, false, active); return; }
+    if (m.pc_coarsen) {
+      // this level coarsens its even-odd system: reduce the full system to it exactly, run the single-parity cycle, reconstruct
+      L.prepare(L.src, b);
+      cycle_pc(l, L.par(x, L.p), L.src, active);
+      L.reconstruct(x, b);
+      return;
+    }
     BlockMGLevel &C = *lv[l];
     if (lp.nu_pre > 0) {
       { BSection s_(&L.t_prof[0]); L.smooth(x, b, false, lp.nu_pre, false, active); }
@@ -592,10 +613,47 @@ class BlockMG {
     if (lp.nu_post > 0) { BSection s_(&L.t_prof[5]); L.smooth(x, b, false, lp.nu_post, true, active); }
   }
 
+  // MG::cycle_pc on level l >= 1: the cycle on the even-odd system Mhat x_p = src of a level that coarsens it (single-parity block
+  // buffers); the next level receives the residual of this parity only and solves its full system
+  void cycle_pc(int l, float *xp, float *srcp, const Mask &active) {
+    BlockMGLevel &L = *lv[l - 1], &C = *lv[l];
+    MG &m = *L.mg;
+    const MGLevelParam &lp = m.mp.level[m.level];
+    BlockKrylov<BlockOps>::Op A = [&L](float *o, float *i, const Mask &) { (*L.mhat)(o, i); };
+    if (lp.nu_pre > 0) {
+      { BSection s_(&L.t_prof[0]); L.smoother->mr(A, xp, srcp, lp.nu_pre, lp.omega, false, active); }
+      BSection s_(&L.t_prof[1]);
+      (*L.mhat)(L.rp, xp);
+      std::vector<Cx> a(R, Cx(-1, 0)), one(R, Cx(1, 0)), none;
+      L.ops_par->blas_.axpy<3>(a, none, L.rp, nullptr, L.rp);     // rp = -Mhat x
+      L.ops_par->axpy(one, srcp, L.rp, active);                   // rp += src
+    } else {
+      L.ops_par->zero(xp, active);
+      L.ops_par->copy(L.rp, srcp, active);
+    }
+    { BSection s_(&L.t_prof[2]); restrict_to(l, L.rp, *C.b, active, L.p); }
+    { BSection s_(&L.t_prof[3]); coarse_solve(l + 1, *C.x, *C.b, active); }
+    { BSection s_(&L.t_prof[4]); prolong_add(l, *C.x, xp, active, L.p); }
+    if (lp.nu_post > 0) { BSection s_(&L.t_prof[5]); L.smoother->mr(A, xp, srcp, lp.nu_post, lp.omega, true, active); }
+  }
+
   // solve on level l as seen from level l - 1: the level's cycle, wrapped in GCR(10) when the parent runs a K-cycle
   void coarse_solve(int l, CoarseBlockField &x, CoarseBlockField &b, const Mask &active) {
     BlockMGLevel &L = *lv[l - 1];
     MG *parent = l == 1 ? &top : lv[l - 2]->mg;
+    if (parent->coarse_solver_pc) {
+      // K-cycle on the even-odd system of this level (MG::MG: GCR on the even-odd operator inside prepare / reconstruct)
+      const SolverParam &sp = parent->param_coarse_solver;
+      BlockKrylov<BlockOps>::Op A = [&L](float *o, float *i, const Mask &) { (*L.mhat)(o, i); };
+      BlockKrylov<BlockOps>::Op K = [this, l](float *o, float *i, const Mask &m) { cycle_pc(l, o, i, m); };
+      L.prepare(L.s_k, b);
+      std::vector<Cx> dot; std::vector<double> n2, stop(R), r2;
+      L.ops_par->cdot(L.s_k, L.s_k, dot, n2, active);
+      for (int c = 0; c < R; c++) stop[c] = sp.tol * sp.tol * n2[c];
+      L.kcycle_gcr_par->gcr(A, &K, L.par(x, L.p), L.s_k, stop, sp.Nkrylov, sp.maxiter, active, r2);
+      L.reconstruct(x, b);
+      return;
+    }
     if (!parent->coarse_solver_gcr) { cycle(l, x, b, active); return; }
     const SolverParam &sp = parent->param_coarse_solver;
     BlockKrylov<BlockOps>::Op A = [&L](float *o, float *i, const Mask &) { L.full_M(o, i); };
@@ -625,6 +683,33 @@ class BlockMG {
     for (int c = 0; c < R; c++) if (active[c]) L.mg->transfer->R(*pc[c], *pf[c]);
     coarse.pack(pc.data());
   }
+  // single-parity variants (levels that coarsen their even-odd system): fine_par = block buffer of parity `parity`
+  void restrict_to(int l, float *fine_par, CoarseBlockField &coarse, const Mask &active, int parity) {
+    BlockMGLevel &L = *lv[l - 1], &C = *lv[l];
+    std::vector<SpinorField *> pc(R);
+    std::vector<const void *> ptr(R);
+    for (int c = 0; c < R; c++) { pc[c] = C.fb[c].get(); ptr[c] = L.fb[c]->parity_ptr(parity); }
+    L.pview->v = fine_par;
+    L.pview->unpack_ptrs(ptr.data());
+    for (int c = 0; c < R; c++) if (active[c]) L.mg->transfer->R(*pc[c], *L.fb[c], parity);
+    coarse.pack(pc.data());
+  }
+  void prolong_add(int l, CoarseBlockField &coarse, float *fine_par, const Mask &active, int parity) {
+    BlockMGLevel &L = *lv[l - 1], &C = *lv[l];
+    std::vector<SpinorField *> pc(R);
+    std::vector<const void *> ptr(R);
+    for (int c = 0; c < R; c++) { pc[c] = C.fx[c].get(); ptr[c] = L.fx[c]->parity_ptr(parity); }
+    coarse.unpack(pc.data());
+    for (int c = 0; c < R; c++) if (active[c]) {
+      SpinorField *fo = L.fx[c].get();
+      const SpinorField *ci = pc[c];
+      L.mg->transfer->P_multi(&fo, &ci, 1, false, parity);
+    }
+    L.pview->v = L.rp;   // rp is free again at this point of the cycle
+    L.pview->pack_ptrs(ptr.data());
+    std::vector<Cx> one(R, Cx(1, 0));
+    L.ops_par->axpy(one, L.rp, fine_par, active);
+  }
   void prolong_add(int l, CoarseBlockField &coarse, CoarseBlockField &fine, const Mask &active) {
     BlockMGLevel &L = *lv[l - 1], &C = *lv[l];
     std::vector<SpinorField *> pf(R), pc(R);
@@ -643,13 +728,18 @@ class BlockMG {
     std::vector<SpinorField *> pb(R), px(R);
     for (int c = 0; c < R; c++) { pb[c] = L1.fb[c].get(); px[c] = L1.fx[c].get(); }
     std::vector<SpinorField *> act_res, act_pb, act_px, act_x;
-    while ((int)rres.size() < R) rres.emplace_back(new SpinorField(top.r->Vh, 2, PREC_SINGLE));
+    // single-parity fields: the cycle on the even-odd system (MG::cycle_pc): smoother and residual on M_pc directly, transfers restricted
+    // to that parity
+    const bool pc = x[0]->nparity == 1;
+    const int tpar = pc ? top.pc_parity : -1;
+    if (pc && !top.pc_coarsen) QB_ERROR("block multigrid: single-parity fields need a hierarchy coarsened on the even-odd system");
+    while ((int)rres.size() < R) rres.emplace_back(new SpinorField(top.r->Vh, pc ? 1 : 2, PREC_SINGLE));
     for (int c = 0; c < R; c++) {
       if (!active[c]) continue;
       if (lp.nu_pre > 0) {
-        { BSection s_(&t_prof[0]); top.smooth(*top.presmoother, *x[c], *b[c]); }
+        { BSection s_(&t_prof[0]); if (pc) (*top.presmoother)(*x[c], *b[c]); else top.smooth(*top.presmoother, *x[c], *b[c]); }
         BSection s_(&t_prof[1]);
-        top.matResidual->M(*rres[c], *x[c]);
+        (pc ? top.matSmooth : top.matResidual)->M(*rres[c], *x[c]);
         blas::axpby(1.0, *b[c], -1.0, *rres[c]);
       } else {
         blas::zero(*x[c]);
@@ -657,16 +747,16 @@ class BlockMG {
       }
       act_res.push_back(rres[c].get()); act_pb.push_back(pb[c]); act_px.push_back(px[c]); act_x.push_back(x[c]);
     }
-    { BSection s_(&t_prof[2]); top.transfer->R_multi(act_pb.data(), act_res.data(), (int)act_res.size()); }
+    { BSection s_(&t_prof[2]); top.transfer->R_multi(act_pb.data(), act_res.data(), (int)act_res.size(), tpar); }
     {
       BSection s_(&t_prof[3]);
       L1.b->pack(pb.data());
       coarse_solve(1, *L1.x, *L1.b, active);
       L1.x->unpack(px.data());
     }
-    { BSection s_(&t_prof[4]); top.transfer->P_multi(act_x.data(), act_px.data(), (int)act_x.size(), true); }
+    { BSection s_(&t_prof[4]); top.transfer->P_multi(act_x.data(), act_px.data(), (int)act_x.size(), true, tpar); }
     if (lp.nu_post > 0)
-      for (int c = 0; c < R; c++) if (active[c]) { BSection s_(&t_prof[5]); top.smooth(*top.postsmoother, *x[c], *b[c]); }
+      for (int c = 0; c < R; c++) if (active[c]) { BSection s_(&t_prof[5]); if (pc) (*top.postsmoother)(*x[c], *b[c]); else top.smooth(*top.postsmoother, *x[c], *b[c]); }
     ncycle++;
   }
   double t_prof[6] = {0, 0, 0, 0, 0, 0};
@@ -685,8 +775,6 @@ class BlockMG {
 bool block_mg_supported(const MG &mg, int R, int mode) {
   if (getenv("QB_BLOCK_MG") && atoi(getenv("QB_BLOCK_MG")) == 0) return false;
   if (R < 2 || R > MAXR || !mg.coarse) return false;
-  for (const MG *m = &mg; m; m = m->coarse.get())
-    if (m->pc_coarsen) return false;   // hierarchies coarsened on the even-odd system take the one-at-a-time path
   for (const MG *m = mg.coarse.get(); m; m = m->coarse.get()) {
     const DiracCoarse *dr = dynamic_cast<const DiracCoarse *>(m->matResidual), *ds = dynamic_cast<const DiracCoarse *>(m->matSmooth);
     if (!dr || !ds || !ds->pc) return false;

@@ -130,7 +130,9 @@ struct CoarseBlockField {
   int nparity, N, R;
   float *v = nullptr;
   void **ptrs = nullptr;  // device scratch: member field pointers for pack / unpack
+  bool owner = true;
   CoarseBlockField(long Vh, int nparity, int N, int R);
+  CoarseBlockField(long Vh, int nparity, int N, int R, float *storage);   // non-owning view of an existing block buffer
   ~CoarseBlockField();
   CoarseBlockField(const CoarseBlockField &) = delete;
   size_t parity_float4() const { return (size_t)Vh * (N / 2) * R; }

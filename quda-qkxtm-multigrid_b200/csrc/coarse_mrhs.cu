@@ -213,8 +213,11 @@ CoarseBlockField::CoarseBlockField(long Vh_, int nparity_, int N_, int R_) : Vh(
   v = (float *)pool_malloc(bytes());
   QB_CUDA(cudaMalloc((void **)&ptrs, sizeof(void *) * R));
 }
+CoarseBlockField::CoarseBlockField(long Vh_, int nparity_, int N_, int R_, float *storage) : Vh(Vh_), nparity(nparity_), N(N_), R(R_), v(storage), owner(false) {
+  QB_CUDA(cudaMalloc((void **)&ptrs, sizeof(void *) * R));
+}
 CoarseBlockField::~CoarseBlockField() {
-  if (v) pool_free(v);
+  if (v && owner) pool_free(v);
   if (ptrs) cudaFree(ptrs);
 }
 static void block_copy(CoarseBlockField &b, SpinorField *const *f, int to_block) {

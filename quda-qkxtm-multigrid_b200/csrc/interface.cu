@@ -1117,18 +1117,27 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
 // the coarse links are read once per operator application for all sources.  Returns false when the request does not qualify.
 static bool invert_multi_src_block(void **hp_x, void **hp_b, QudaInvertParam *param) {
   if (param->num_src < 2 || param->inv_type != QUDA_GCR_INVERTER || param->inv_type_precondition != QUDA_MG_INVERTER || !param->preconditioner) return false;
-  if (param->solve_type != QUDA_DIRECT_SOLVE || param->solution_type != QUDA_MAT_SOLUTION || param->use_init_guess == QUDA_USE_INIT_GUESS_YES) return false;
+  if ((param->solve_type != QUDA_DIRECT_SOLVE && param->solve_type != QUDA_DIRECT_PC_SOLVE) || param->solution_type != QUDA_MAT_SOLUTION ||
+      param->use_init_guess == QUDA_USE_INIT_GUESS_YES)
+    return false;
   const int mode = getenv("QB_BLOCK_MG_MODE") ? atoi(getenv("QB_BLOCK_MG_MODE")) : 3;
-  MG &mg = *((MultigridSolver *)param->preconditioner)->mg;
+  MultigridSolver *ms = (MultigridSolver *)param->preconditioner;
+  MG &mg = *ms->mg;
+  // even-odd outer solve (the reference's default): the hierarchy must be coarsened on the even-odd system of the same symmetric matpc_type
+  const bool pc = param->solve_type == QUDA_DIRECT_PC_SOLVE;
+  if (pc && (!mg.pc_coarsen || ((int)param->matpc_type != (int)QUDA_MATPC_EVEN_EVEN && (int)param->matpc_type != (int)QUDA_MATPC_ODD_ODD) ||
+             ms->diracSmooth->matpc() != (int)param->matpc_type))
+    return false;   // invertQuda reports what is wrong
   SolverParam sp;
   fill_solver_param(sp, param);
   const Prec prec = sp.precision;
   if (prec == PREC_HALF) QB_ERROR("cuda_prec must be single or double for a solve");
-  // sources per block: as many as the multi-RHS kernel takes, and as the Krylov space (2 x min(Nkrylov, 16) + 6 single-precision full fields
+  // sources per block: as many as the multi-RHS kernel takes, and as the Krylov space (2 x min(Nkrylov, 16) + 6 single-precision fields
   // per source, allocated as the iteration proceeds) leaves room for
   size_t free_b = 0, total_b = 0;
   QB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const size_t per_src = (size_t)G.lat.geom.Vh * 2 * 96 * (2 * std::min(sp.Nkrylov, 16) + 6) + (size_t)G.lat.geom.Vh * 2 * 24 * (int)prec * 4;
+  const int npar = pc ? 1 : 2;
+  const size_t per_src = (size_t)G.lat.geom.Vh * npar * 96 * (2 * std::min(sp.Nkrylov, 16) + 6) + (size_t)G.lat.geom.Vh * 2 * 24 * (int)prec * 4;
   int Rblk = std::min<int>(param->num_src, (int)std::max<size_t>(1, (size_t)(0.7 * (double)(free_b + pool_cached_bytes())) / per_src));
   if (getenv("QB_BLOCK_MG_R")) Rblk = std::min(Rblk, atoi(getenv("QB_BLOCK_MG_R")));
   while (Rblk >= 2 && !block_mg_supported(mg, Rblk, mode)) Rblk--;
@@ -1139,38 +1148,46 @@ static bool invert_multi_src_block(void **hp_x, void **hp_b, QudaInvertParam *pa
   const int saved_verbosity = r.verbosity;
   if ((int)param->verbosity != INVALID_INT) r.verbosity = (int)param->verbosity;
   const Prec prec_vec_sloppy = blas_prec(sp.precision_sloppy);
-  std::unique_ptr<DiracTM> d(make_dirac(param, false, pick_gauge(prec)));
-  std::unique_ptr<DiracTM> dS(make_dirac(param, false, pick_gauge(sp.precision_sloppy)));
+  std::unique_ptr<DiracTM> d(make_dirac(param, pc, pick_gauge(prec)));
+  std::unique_ptr<DiracTM> dS(make_dirac(param, pc, pick_gauge(sp.precision_sloppy)));
   if (dS->gauge->prec != prec_vec_sloppy) dS->gauge_vec = pick_gauge(prec_vec_sloppy);
   DiracMatrix m(d.get(), false), mS(dS.get(), false);
-  param->secs = 0; param->gflops = 0; param->iter = 0; param->true_res = 0; param->true_res_hq = 0;
+  param->secs = 0; param->gflops = 0; param->iter = 0; param->true_res = 0; param->true_res_hq = std::numeric_limits<double>::quiet_NaN();
+  double gflops_single = 0.0;   // left-over single sources go through invertQuda, which resets the flop counters
   auto now = [&]() { QB_CUDA(cudaStreamSynchronize(r.compute)); return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int first = 0; first < param->num_src; first += Rblk) {
     const int R = std::min(Rblk, param->num_src - first);
     if (R == 1) {  // a single left-over source: the ordinary path, its counters added to the block's
       const double secs = param->secs, tr0 = param->true_res; const int it0 = param->iter;
+      const unsigned long long bf = blas::flops;
       invertQuda(hp_x[first], hp_b[first], param);
+      gflops_single += param->gflops;
+      blas::flops = bf;
       param->secs += secs; param->iter += it0; param->true_res = std::max(param->true_res, tr0);
       continue;
     }
     std::vector<std::unique_ptr<SpinorField>> bs(R), xs(R);
+    std::vector<SpinorField> vin(R), vout(R);   // what the solver works on: the fields themselves, or the even-odd source / solution views
     std::vector<SpinorField *> pb(R), px(R);
     std::vector<double> nb(R);
     for (int c = 0; c < R; c++) {
       bs[c].reset(new SpinorField(G.lat.geom.Vh, 2, prec)); xs[c].reset(new SpinorField(G.lat.geom.Vh, 2, prec));
-      pb[c] = bs[c].get(); px[c] = xs[c].get();
       load_host_spinor(*bs[c], hp_b[first + c], param);
+      blas::zero(*xs[c]);
       nb[c] = blas::norm2(*bs[c]);
       if (nb[c] == 0.0) QB_ERROR("Source %d has zero norm", first + c);
       if (param->solver_normalization == QUDA_SOURCE_NORMALIZATION) blas::ax(1.0 / sqrt(nb[c]), *bs[c]);
       if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION)
         blas::ax(2.0 * param->kappa, *bs[c]);   // massRescale, MAT solution (interface_quda.cpp:1412-1494)
+      d->prepare(vin[c], vout[c], *xs[c], *bs[c], SOL_MAT);   // full solve: the fields themselves
+      pb[c] = &vin[c]; px[c] = &vout[c];
     }
     std::vector<double> tr;
     const double t0 = now();   // secs counts the solve only, like invertQuda (sources already on the device)
     const int it = block_mg_gcr_solve(mg, m, mS, px, pb, sp, mode, tr);
     param->secs += now() - t0;
     for (int c = 0; c < R; c++) {
+      d->reconstruct(*xs[c], *bs[c], SOL_MAT);
       if (param->solver_normalization == QUDA_SOURCE_NORMALIZATION) blas::ax(sqrt(nb[c]), *xs[c]);
       save_host_spinor(hp_x[first + c], *xs[c], param);
       param->true_res = std::max(param->true_res, tr[c]);
@@ -1179,7 +1196,7 @@ static bool invert_multi_src_block(void **hp_x, void **hp_b, QudaInvertParam *pa
     log_msg(1, "invertMultiSrcQuda: block of %d sources, %d lock-step GCR iterations, worst true residual %e\n", R, it, param->true_res);
   }
   QB_CUDA(cudaStreamSynchronize(r.compute));
-  param->gflops = (double)(d->flops + dS->flops + (double)blas::flops) * 1e-9;
+  param->gflops = gflops_single + (double)(d->flops + dS->flops + (double)blas::flops) * 1e-9;
   blas::flops = 0;
   r.verbosity = saved_verbosity;
   return true;

@@ -159,3 +159,41 @@ def test_mg_on_the_odd_odd_system(quda, oracle):
     print(f"odd-odd: {p.iter} MG iterations vs {p0.iter} plain, host residual {res:.2e}")
     assert res < 5e-8 and p.iter < p0.iter / 3
     L.destroyMultigridQuda(mg)
+
+
+@pytest.mark.parametrize("n_level,X,blocks,nvecs", [(2, (8, 8, 8, 16), ((4, 4, 4, 4),), (8,)),
+                                                    (3, (16, 16, 16, 16), ((4, 4, 4, 4), (2, 2, 2, 2)), (8, 8))])
+def test_block_mg_multi_src_on_the_even_odd_system(quda, oracle, n_level, X, blocks, nvecs, monkeypatch):
+    """invertMultiSrcQuda with the reference's default solve type (QUDA_DIRECT_PC_SOLVE) on a hierarchy coarsened on the even-odd
+    system: all sources in lock-step through the single-parity block K-cycle (coarse levels on the multi-RHS tensor-core operator);
+    every solution checked with the host operator and against the one-source-at-a-time path"""
+    q, L = quda, quda.lib()
+    kappa, mu, tol = 0.1248, 0.004, 1e-8
+    g, mg, mgp, ip = build(q, oracle, X, blocks, nvecs, n_level, kappa, mu, 0.25)
+    nsrc = 5
+    rng = np.random.default_rng(11)
+    bs = [point_source(oracle.V)] + [rng.standard_normal(oracle.V * 24) for _ in range(nsrc - 1)]
+
+    def solve(block):
+        monkeypatch.setenv("QB_BLOCK_MG", "1" if block else "0")
+        p = mg_inv_param(q, kappa, mu)
+        p.solve_type = q.QUDA_DIRECT_PC_SOLVE
+        p.inv_type_precondition = q.QUDA_MG_INVERTER
+        p.preconditioner = mg
+        p.gcrNkrylov = 20; p.tol = tol; p.maxiter = 200; p.reliable_delta = 1e-4
+        p.num_src = nsrc
+        xs = [np.zeros(oracle.V * 24) for _ in range(nsrc)]
+        L.invertMultiSrcQuda((C.c_void_p * nsrc)(*[a.ctypes.data for a in xs]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bs]), C.byref(p))
+        return xs, p.iter, p.true_res, p.secs
+
+    xb, it_b, tr_b, t_b = solve(True)
+    xs, it_s, tr_s, t_s = solve(False)
+    L.destroyMultigridQuda(mg)
+    worst = max(host_residual(oracle, g, x, b, kappa, mu) for x, b in zip(xb, bs))
+    print(f"even-odd block MG ({n_level} levels): {it_b} lock-step iterations in {t_b:.3f} s, sequential {it_s} iterations (sum over {nsrc}) in {t_s:.3f} s; "
+          f"worst host residual {worst:.2e}")
+    assert worst < 5e-8 and tr_b < 5e-8 and tr_s < 5e-8
+    assert it_b < it_s, (it_b, it_s)                       # lock-step count, not the sum: the block path was taken
+    assert it_b <= 1.5 * it_s / nsrc + 3, (it_b, it_s)
+    for a, b_ in zip(xb, xs):
+        assert np.linalg.norm(a - b_) / np.linalg.norm(b_) < 1e-6
