@@ -11,8 +11,8 @@ void CoarseOperator::allocate(const LevelGeom &g, int nvec_) {
   geom = g;
   nvec = nvec_;
   N = 2 * nvec;
-  if (Y) cudaFree(Y);
-  QB_CUDA(cudaMalloc((void **)&Y, link_bytes()));
+  if (Y) pool_free(Y);
+  Y = (float *)pool_malloc(link_bytes());   // GB-sized link arrays go through the caching allocator
   QB_CUDA(cudaMemsetAsync(Y, 0, link_bytes(), rt().compute));
   for (int d = 0; d < 4; d++) {
     if (!geom.part[d]) continue;
@@ -26,14 +26,14 @@ void CoarseOperator::allocate(const LevelGeom &g, int nvec_) {
 }
 
 CoarseOperator::~CoarseOperator() {
-  if (Y) cudaFree(Y);
-  if (Xinv) cudaFree(Xinv);
-  if (Y16) cudaFree(Y16);
-  if (Xinv16) cudaFree(Xinv16);
-  if (Yhat) cudaFree(Yhat);
-  if (Yhat16) cudaFree(Yhat16);
-  if (Ymma) cudaFree(Ymma);
-  if (Xinv_mma) cudaFree(Xinv_mma);
+  if (Y) pool_free(Y);
+  if (Xinv) pool_free(Xinv);
+  if (Y16) pool_free(Y16);
+  if (Xinv16) pool_free(Xinv16);
+  if (Yhat) pool_free(Yhat);
+  if (Yhat16) pool_free(Yhat16);
+  if (Ymma) pool_free(Ymma);
+  if (Xinv_mma) pool_free(Xinv_mma);
   if (nbr) cudaFree(nbr);
   if (mrhs_send) cudaFree(mrhs_send);
   if (mrhs_recv) cudaFree(mrhs_recv);
@@ -265,14 +265,14 @@ __global__ void links_to_half_kernel(uint2 *dst, const float4 *src, size_t n) {
 }
 void CoarseOperator::enable_half_links() {
   const size_t ny = (size_t)geom.V() * 9 * N * (N / 2), nx = (size_t)geom.V() * N * (N / 2);
-  if (!Y16) QB_CUDA(cudaMalloc((void **)&Y16, ny * sizeof(uint2)));
+  if (!Y16) Y16 = pool_malloc(ny * sizeof(uint2));
   links_to_half_kernel<<<(unsigned)div_up((long)ny, 256), 256, 0, rt().compute>>>((uint2 *)Y16, (const float4 *)Y, ny);
   if (Xinv) {
-    if (!Xinv16) QB_CUDA(cudaMalloc((void **)&Xinv16, nx * sizeof(uint2)));
+    if (!Xinv16) Xinv16 = pool_malloc(nx * sizeof(uint2));
     links_to_half_kernel<<<(unsigned)div_up((long)nx, 256), 256, 0, rt().compute>>>((uint2 *)Xinv16, (const float4 *)Xinv, nx);
   }
   if (Yhat) {
-    if (!Yhat16) QB_CUDA(cudaMalloc((void **)&Yhat16, ny * sizeof(uint2)));
+    if (!Yhat16) Yhat16 = pool_malloc(ny * sizeof(uint2));
     links_to_half_kernel<<<(unsigned)div_up((long)ny, 256), 256, 0, rt().compute>>>((uint2 *)Yhat16, (const float4 *)Yhat, ny);
   }
   QB_CHECK_LAUNCH();
@@ -406,7 +406,7 @@ template <int N> static void launch_xinv(float *Xinv, const float *Y, long nsite
 }
 
 void CoarseOperator::compute_xinv() {
-  if (!Xinv) QB_CUDA(cudaMalloc((void **)&Xinv, (size_t)geom.V() * N * N * 8));
+  if (!Xinv) Xinv = (float *)pool_malloc((size_t)geom.V() * N * N * 8);
   switch (N) {
     case 4: launch_xinv<4>(Xinv, Y, geom.V()); break;
     case 8: launch_xinv<8>(Xinv, Y, geom.V()); break;
@@ -469,7 +469,7 @@ template <int N> static void launch_yhat(float *Yhat, const float *Y, const floa
 
 void CoarseOperator::compute_yhat() {
   if (!Xinv) compute_xinv();
-  if (!Yhat) QB_CUDA(cudaMalloc((void **)&Yhat, link_bytes()));
+  if (!Yhat) Yhat = (float *)pool_malloc(link_bytes());
   switch (N) {
     case 4: launch_yhat<4>(Yhat, Y, Xinv, geom.V()); break;
     case 8: launch_yhat<8>(Yhat, Y, Xinv, geom.V()); break;

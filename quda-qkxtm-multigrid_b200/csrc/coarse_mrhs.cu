@@ -87,14 +87,14 @@ void CoarseOperator::prepare_mrhs() {
   const long V = geom.V();
   if (mrhs_ready && Ymma && nbr && (!Xinv || Xinv_mma)) return;   // links are immutable once the level is set up
   mrhs_ready = true;
-  if (!Ymma) QB_CUDA(cudaMalloc((void **)&Ymma, link_bytes()));
+  if (!Ymma) Ymma = (float *)pool_malloc(link_bytes());
   {
     const long n = V * 9 * N * (N / 2);
     ymma_from_y_kernel<<<div_up(n, 256), 256, 0, s>>>((float4 *)Ymma, (const float4 *)Y, N, V * 9);
     QB_CHECK_LAUNCH();
   }
   if (Xinv) {
-    if (!Xinv_mma) QB_CUDA(cudaMalloc((void **)&Xinv_mma, (size_t)V * N * N * 8));
+    if (!Xinv_mma) Xinv_mma = (float *)pool_malloc((size_t)V * N * N * 8);
     const long n = V * N * (N / 2);
     ymma_from_y_kernel<<<div_up(n, 256), 256, 0, s>>>((float4 *)Xinv_mma, (const float4 *)Xinv, N, V);
     QB_CHECK_LAUNCH();

@@ -1291,7 +1291,13 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   for (int l = 0; l < mp.n_level - 1; l++)
     for (int d = 0; d < 4; d++) mgp->geo_block_size[l][d] = mp.level[l].geo_bs[d];
   QB_CUDA(cudaDeviceSynchronize());
-  pool_release_all();  // the setup's multi-GB scratch (site-major V, decompressed links) goes back to the driver
+  // the setup's multi-GB scratch (site-major V, decompressed links) sits in the allocator's cache: hand it back to the driver only when it
+  // is a sizeable part of the device (cudaFree / cudaMalloc of such blocks cost up to 0.5 s per setup, and the QKXTM drivers set up twice)
+  {
+    size_t free_b = 0, total_b = 0;
+    QB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (pool_cached_bytes() > total_b / 8 || free_b < total_b / 4) pool_release_all();
+  }
   mgp->secs = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
   mgp->gflops = 0;
   r.verbosity = saved_verbosity;

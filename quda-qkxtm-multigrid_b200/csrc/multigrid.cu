@@ -138,7 +138,12 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
     const double tc0 = now_s();
     if (pc_coarsen) log_msg(1, "MG level %d: coarsening the even-odd preconditioned operator (bi-directional links of S^-1 M)\n", level + 1);
     matResidual->create_coarse_op(*coarse_op, *transfer, pc_coarsen);
-    if (cp.smoother_pc) coarse_op->compute_xinv();
+    if (cp.smoother_pc) {
+      coarse_op->compute_xinv();
+      // Yhat = Xinv Y (createYpreconditioned, lib/coarse_op.cuh:1217-1283): the even-odd coarse operator 1 - Yhat_pq Yhat_qp in two launches
+      // instead of four (QB_MG_YHAT=0: keep the Xinv launches, saves one copy of the links)
+      if (!(getenv("QB_MG_YHAT") && atoi(getenv("QB_MG_YHAT")) == 0)) coarse_op->compute_yhat();
+    }
     if (mp.half_storage) { transfer->enable_half_v(); coarse_op->enable_half_links(); }
     QB_CUDA(cudaStreamSynchronize(rt().compute));
     log_msg(1, "MG level %d: coarse operator %d x %d x %d x %d, N = %d built in %.3f s\n", level + 1, coarse_op->geom.X[0], coarse_op->geom.X[1],

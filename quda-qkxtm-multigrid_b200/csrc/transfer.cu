@@ -532,7 +532,7 @@ Transfer::Transfer(const std::vector<SpinorField *> &B, int nvec_, int *bs, int 
 
   // V <- null vectors, then block orthonormalisation
   cudaStream_t s = rt().compute;
-  QB_CUDA(cudaMalloc((void **)&V, v_bytes()));
+  V = (float *)pool_malloc(v_bytes());   // multi-GB: through the caching allocator (a second setup of the same shape, e.g. the DN flavour, reuses the block)
   const long nt = 2 * fine.Vh * (Nf / 2);
   for (int j = 0; j < nvec; j++) {
     fill_v_kernel<<<div_up(nt, 256), 256, 0, s>>>((float4 *)V, (const float4 *)B[j]->v, fine.Vh, Nf, nvec, j);
@@ -545,8 +545,8 @@ Transfer::Transfer(const std::vector<SpinorField *> &B, int nvec_, int *bs, int 
 }
 
 Transfer::~Transfer() {
-  if (V) cudaFree(V);
-  if (V16) cudaFree(V16);
+  if (V) pool_free(V);
+  if (V16) pool_free(V16);
   if (f2c) cudaFree(f2c);
   if (c2f) cudaFree(c2f);
   for (int d = 0; d < 4; d++)
@@ -672,7 +672,7 @@ void Transfer::R_multi(SpinorField *const *co, const SpinorField *const *fi, int
 // and the fallback aggregate-major restrictor keep the fp32 V
 void Transfer::enable_half_v() {
   const size_t n = v_bytes() / 16;
-  if (!V16) QB_CUDA(cudaMalloc((void **)&V16, n * sizeof(uint2)));
+  if (!V16) V16 = pool_malloc(n * sizeof(uint2));
   v_to_half_kernel<<<(unsigned)div_up((long)n, 256), 256, 0, rt().compute>>>((uint2 *)V16, (const float4 *)V, n);
   QB_CHECK_LAUNCH();
 }
