@@ -16,6 +16,46 @@ template <typename real> struct alignas(16) Pack {
   cplx<real> c[N];
 };
 
+// Field accessors: the BLAS functors below are written once, on "packs" of complex numbers, and run on
+//   Acc<double> / Acc<float> : flat arrays of 16-byte packs (1 / 2 complex numbers), any field shape;
+//   AccH                     : int16 + norm fields (lib/blas_core.h:12-52 handles them as short4 + norm, M = 6): one pack = one SITE of 12
+//                              complex numbers, decoded to fp32 on load, re-normalised and re-quantised on store (fp32 arithmetic, as the
+//                              reference does for half precision).
+template <typename real_> struct Acc {
+  typedef real_ real;
+  typedef Pack<real_> pack;
+  Pack<real_> *p;
+  Acc() : p(nullptr) {}
+  explicit Acc(const SpinorField &f) : p((Pack<real_> *)f.v) {}
+  static long count(const SpinorField &f) { return f.reals() * (long)sizeof(real_) / 16; }
+  __device__ __forceinline__ pack load(long i) const { return p[i]; }
+  __device__ __forceinline__ void store(long i, const pack &v) const { p[i] = v; }
+};
+struct PackH {
+  static constexpr int N = 12;
+  cplx<float> c[N];
+};
+struct AccH {
+  typedef float real;
+  typedef PackH pack;
+  char *v; float *norm; long Vh; size_t parity_bytes;
+  AccH() : v(nullptr), norm(nullptr), Vh(0), parity_bytes(0) {}
+  explicit AccH(const SpinorField &f) : v((char *)f.v), norm(f.norm), Vh(f.Vh), parity_bytes(f.parity_bytes) {
+    if (f.ncomplex != 12 || f.nflavor != 1 || f.nbatch != 1) QB_ERROR("blas: half-precision vectors are supported for single fine-grid fields (4 spins x 3 colours) only");
+  }
+  static long count(const SpinorField &f) { return (long)f.nparity * f.Vh; }
+  __device__ __forceinline__ pack load(long i) const {
+    const long par = i / Vh, cb = i - par * Vh;
+    pack u;
+    load_scaled<StoreH, 12, false>(u.c, v + par * parity_bytes, norm + par * Vh, Vh, cb);
+    return u;
+  }
+  __device__ __forceinline__ void store(long i, const pack &u) const {
+    const long par = i / Vh, cb = i - par * Vh;
+    StoreH::store<12>(v + par * parity_bytes, norm + par * Vh, Vh, cb, u.c);
+  }
+};
+
 static const int BLOCK = 256;
 static int grid_for(long n) {
   const long want = (n + BLOCK - 1) / BLOCK;
@@ -143,18 +183,13 @@ static void check_same(const SpinorField &a, const SpinorField &b) {
   if (a.prec != b.prec) QB_ERROR("blas: precision mismatch (%d vs %d)", (int)a.prec, (int)b.prec);
   if (a.reals() != b.reals()) QB_ERROR("blas: field length mismatch (%ld vs %ld)", a.reals(), b.reals());
 }
-static void check_prec(const SpinorField &a) {
-  if (a.prec == PREC_HALF) QB_ERROR("blas: half-precision fields are only supported by the Dslash kernels; use single precision for solver vectors");
-}
-
 #define BY_PREC(field, ...)                                \
   do {                                                     \
-    check_prec(field);                                     \
-    if ((field).prec == PREC_DOUBLE) { typedef double real; __VA_ARGS__ } \
-    else { typedef float real; __VA_ARGS__ }               \
+    if ((field).prec == PREC_DOUBLE) { typedef double real; typedef Acc<double> FA; __VA_ARGS__ } \
+    else if ((field).prec == PREC_SINGLE) { typedef float real; typedef Acc<float> FA; __VA_ARGS__ } \
+    else { typedef float real; typedef AccH FA; __VA_ARGS__ }               \
   } while (0)
 
-template <typename real> static long npacks(const SpinorField &x) { return x.reals() * (long)sizeof(real) / 16; }
 template <typename real> __host__ __device__ inline cplx<real> cmul(cplx<real> a, cplx<real> b) { return a * b; }
 
 void zero(SpinorField &a) { a.zero(rt().compute); }
@@ -162,36 +197,36 @@ void copy(SpinorField &dst, const SpinorField &src) { copy_spinor(dst, src, rt()
 
 // ---- elementwise ------------------------------------------------------------------------------
 void ax(double a, SpinorField &x) {
-  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; const real A = (real)a;
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> v = X[i];
+  BY_PREC(x, const FA X(x); const real A = (real)a;
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack v = X.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re *= A; v.c[k].im *= A; }
-            X[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { v.c[k].re *= A; v.c[k].im *= A; }
+            X.store(i, v);
           }););
   flops += x.reals(); bytes += 2 * x.bytes();
 }
 
 void axpby(double a, const SpinorField &x, double b, SpinorField &y) {
   check_same(x, y);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const real A = (real)a, B = (real)b;
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y); const real A = (real)a, B = (real)b;
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re = A * u.c[k].re + B * v.c[k].re; v.c[k].im = A * u.c[k].im + B * v.c[k].im; }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { v.c[k].re = A * u.c[k].re + B * v.c[k].re; v.c[k].im = A * u.c[k].im + B * v.c[k].im; }
+            Y.store(i, v);
           }););
   flops += 3 * x.reals(); bytes += 3 * x.bytes();
 }
 
 void axpy(double a, const SpinorField &x, SpinorField &y) {
   check_same(x, y);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const real A = (real)a;
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y); const real A = (real)a;
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re += A * u.c[k].re; v.c[k].im += A * u.c[k].im; }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { v.c[k].re += A * u.c[k].re; v.c[k].im += A * u.c[k].im; }
+            Y.store(i, v);
           }););
   flops += 2 * x.reals(); bytes += 3 * x.bytes();
 }
@@ -202,91 +237,91 @@ void xpay(const SpinorField &x, double a, SpinorField &y) { axpby(1.0, x, a, y);
 
 void caxpy(Complex a, const SpinorField &x, SpinorField &y) {
   check_same(x, y);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const cplx<real> A((real)a.real(), (real)a.imag());
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y); const cplx<real> A((real)a.real(), (real)a.imag());
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) cmac(v.c[k], A, u.c[k]);
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) cmac(v.c[k], A, u.c[k]);
+            Y.store(i, v);
           }););
   flops += 4 * x.reals(); bytes += 3 * x.bytes();
 }
 
 void caxpby(Complex a, const SpinorField &x, Complex b, SpinorField &y) {
   check_same(x, y);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
+  BY_PREC(x, const FA X(x); const FA Y(y);
           const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag());
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i];
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cplx<real> t = B * v.c[k]; cmac(t, A, u.c[k]); v.c[k] = t; }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cplx<real> t = B * v.c[k]; cmac(t, A, u.c[k]); v.c[k] = t; }
+            Y.store(i, v);
           }););
   flops += 7 * x.reals(); bytes += 3 * x.bytes();
 }
 
 void cxpaypbz(const SpinorField &x, Complex a, const SpinorField &y, Complex b, SpinorField &z) {
   check_same(x, y); check_same(x, z);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v; Pack<real> *Z = (Pack<real> *)z.v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const FA Z(z);
           const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag());
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i], w = Z[i];
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i), w = Z.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cplx<real> t = u.c[k]; cmac(t, A, v.c[k]); cmac(t, B, w.c[k]); w.c[k] = t; }
-            Z[i] = w;
+            for (int k = 0; k < FA::pack::N; k++) { cplx<real> t = u.c[k]; cmac(t, A, v.c[k]); cmac(t, B, w.c[k]); w.c[k] = t; }
+            Z.store(i, w);
           }););
   flops += 8 * x.reals(); bytes += 4 * x.bytes();
 }
 
 void caxpbypz(Complex a, const SpinorField &x, Complex b, const SpinorField &y, SpinorField &z) {
   check_same(x, y); check_same(x, z);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v; Pack<real> *Z = (Pack<real> *)z.v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const FA Z(z);
           const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag());
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i], w = Z[i];
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i), w = Z.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(w.c[k], A, u.c[k]); cmac(w.c[k], B, v.c[k]); }
-            Z[i] = w;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(w.c[k], A, u.c[k]); cmac(w.c[k], B, v.c[k]); }
+            Z.store(i, w);
           }););
   flops += 8 * x.reals(); bytes += 4 * x.bytes();
 }
 
 void caxpbypzYmbw(Complex a, const SpinorField &x, Complex b, SpinorField &y, SpinorField &z, const SpinorField &w) {
   check_same(x, y); check_same(x, z); check_same(x, w);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; Pack<real> *Z = (Pack<real> *)z.v;
-          const Pack<real> *W = (const Pack<real> *)w.v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const FA Z(z);
+          const FA W(w);
           const cplx<real> A((real)a.real(), (real)a.imag()), B((real)b.real(), (real)b.imag()), mB(-(real)b.real(), -(real)b.imag());
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i], zz = Z[i], ww = W[i];
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i), zz = Z.load(i), ww = W.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(zz.c[k], A, u.c[k]); cmac(zz.c[k], B, v.c[k]); cmac(v.c[k], mB, ww.c[k]); }
-            Z[i] = zz; Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(zz.c[k], A, u.c[k]); cmac(zz.c[k], B, v.c[k]); cmac(v.c[k], mB, ww.c[k]); }
+            Z.store(i, zz); Y.store(i, v);
           }););
   flops += 12 * x.reals(); bytes += 6 * x.bytes();
 }
 
 void cabxpyAx(double a, Complex b, SpinorField &x, SpinorField &y) {
   check_same(x, y);
-  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
+  BY_PREC(x, const FA X(x); const FA Y(y);
           const real A = (real)a; const cplx<real> AB((real)(a * b.real()), (real)(a * b.imag()));
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i];
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; }
-            X[i] = u; Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; }
+            X.store(i, u); Y.store(i, v);
           }););
   flops += 5 * x.reals(); bytes += 4 * x.bytes();
 }
 
 void caxpyXmaz(Complex a, SpinorField &x, SpinorField &y, const SpinorField &z) {
   check_same(x, y); check_same(x, z);
-  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const FA Z(z);
           const cplx<real> A((real)a.real(), (real)a.imag()), mA(-(real)a.real(), -(real)a.imag());
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v = Y[i], w = Z[i];
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v = Y.load(i), w = Z.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); cmac(u.c[k], mA, w.c[k]); }
-            X[i] = u; Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(v.c[k], A, u.c[k]); cmac(u.c[k], mA, w.c[k]); }
+            X.store(i, u); Y.store(i, v);
           }););
   flops += 8 * x.reals(); bytes += 5 * x.bytes();
 }
@@ -295,19 +330,19 @@ _Pragma("unroll")
 //   x (+)= a b,   r = b - a Ab          [reads b, Ab (and x), writes x, r]
 void mrFirstStep(Complex a, const SpinorField &b, const SpinorField &Ab, SpinorField &x, SpinorField &r, bool accumulate) {
   check_same(b, Ab); check_same(b, x); check_same(b, r);
-  BY_PREC(b, const Pack<real> *B = (const Pack<real> *)b.v; const Pack<real> *AB = (const Pack<real> *)Ab.v; Pack<real> *X = (Pack<real> *)x.v;
-          Pack<real> *R = (Pack<real> *)r.v;
+  BY_PREC(b, const FA B(b); const FA AB(Ab); const FA X(x);
+          const FA R(r);
           const cplx<real> A((real)a.real(), (real)a.imag()), mA(-(real)a.real(), -(real)a.imag());
-          elementwise(npacks<real>(b), [=] __device__(long i) {
-            Pack<real> u = B[i], w = AB[i], v;
-            if (accumulate) v = X[i];
+          elementwise(FA::count(b), [=] __device__(long i) {
+            FA::pack u = B.load(i), w = AB.load(i), v;
+            if (accumulate) v = X.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) {
+            for (int k = 0; k < FA::pack::N; k++) {
               if (!accumulate) v.c[k] = cplx<real>((real)0, (real)0);
               cmac(v.c[k], A, u.c[k]);
               cmac(u.c[k], mA, w.c[k]);
             }
-            X[i] = v; R[i] = u;
+            X.store(i, v); R.store(i, u);
           }););
   flops += 8 * b.reals(); bytes += (accumulate ? 5 : 4) * b.bytes();
 }
@@ -315,12 +350,12 @@ _Pragma("unroll")
 // y = a x
 void cax(Complex a, const SpinorField &x, SpinorField &y) {
   check_same(x, y);
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const cplx<real> A((real)a.real(), (real)a.imag());
-          elementwise(npacks<real>(x), [=] __device__(long i) {
-            Pack<real> u = X[i], v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const cplx<real> A((real)a.real(), (real)a.imag());
+          elementwise(FA::count(x), [=] __device__(long i) {
+            FA::pack u = X.load(i), v;
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) v.c[k] = A * u.c[k];
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) v.c[k] = A * u.c[k];
+            Y.store(i, v);
           }););
   flops += 6 * x.reals(); bytes += 2 * x.bytes();
 }
@@ -328,11 +363,11 @@ _Pragma("unroll")
 // ---- reductions -------------------------------------------------------------------------------
 double norm2(const SpinorField &x) {
   double out[1];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v;
-          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i];
+  BY_PREC(x, const FA X(x);
+          reduce<1>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) acc[0] += (double)u.c[k].re * u.c[k].re + (double)u.c[k].im * u.c[k].im;
+            for (int k = 0; k < FA::pack::N; k++) acc[0] += (double)u.c[k].re * u.c[k].re + (double)u.c[k].im * u.c[k].im;
           }););
   flops += 2 * x.reals(); bytes += x.bytes();
   return out[0];
@@ -341,11 +376,11 @@ _Pragma("unroll")
 double reDotProduct(const SpinorField &x, const SpinorField &y) {
   check_same(x, y);
   double out[1];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
-          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y);
+          reduce<1>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) acc[0] += (double)u.c[k].re * v.c[k].re + (double)u.c[k].im * v.c[k].im;
+            for (int k = 0; k < FA::pack::N; k++) acc[0] += (double)u.c[k].re * v.c[k].re + (double)u.c[k].im * v.c[k].im;
           }););
   flops += 2 * x.reals(); bytes += 2 * x.bytes();
   return out[0];
@@ -361,11 +396,11 @@ template <typename real> __device__ __forceinline__ double norm_c(cplx<real> u) 
 Complex cDotProduct(const SpinorField &x, const SpinorField &y) {
   check_same(x, y);
   double out[2];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
-          reduce<2>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y);
+          reduce<2>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) cdot_acc(acc, u.c[k], v.c[k]);
+            for (int k = 0; k < FA::pack::N; k++) cdot_acc(acc, u.c[k], v.c[k]);
           }););
   flops += 4 * x.reals(); bytes += 2 * x.bytes();
   return Complex(out[0], out[1]);
@@ -374,11 +409,11 @@ _Pragma("unroll")
 double3_ cDotProductNormA(const SpinorField &x, const SpinorField &y) {
   check_same(x, y);
   double out[3];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
-          reduce<3>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y);
+          reduce<3>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cdot_acc(acc, u.c[k], v.c[k]); acc[2] += norm_c(u.c[k]); }
+            for (int k = 0; k < FA::pack::N; k++) { cdot_acc(acc, u.c[k], v.c[k]); acc[2] += norm_c(u.c[k]); }
           }););
   flops += 6 * x.reals(); bytes += 2 * x.bytes();
   return double3_{out[0], out[1], out[2]};
@@ -387,11 +422,11 @@ _Pragma("unroll")
 double3_ cDotProductNormB(const SpinorField &x, const SpinorField &y) {
   check_same(x, y);
   double out[3];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; const Pack<real> *Y = (const Pack<real> *)y.v;
-          reduce<3>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y);
+          reduce<3>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cdot_acc(acc, u.c[k], v.c[k]); acc[2] += norm_c(v.c[k]); }
+            for (int k = 0; k < FA::pack::N; k++) { cdot_acc(acc, u.c[k], v.c[k]); acc[2] += norm_c(v.c[k]); }
           }););
   flops += 6 * x.reals(); bytes += 2 * x.bytes();
   return double3_{out[0], out[1], out[2]};
@@ -400,12 +435,12 @@ _Pragma("unroll")
 double axpyNorm(double a, const SpinorField &x, SpinorField &y) {
   check_same(x, y);
   double out[1];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const real A = (real)a;
-          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y); const real A = (real)a;
+          reduce<1>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re += A * u.c[k].re; v.c[k].im += A * u.c[k].im; acc[0] += norm_c(v.c[k]); }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { v.c[k].re += A * u.c[k].re; v.c[k].im += A * u.c[k].im; acc[0] += norm_c(v.c[k]); }
+            Y.store(i, v);
           }););
   flops += 4 * x.reals(); bytes += 3 * x.bytes();
   return out[0];
@@ -414,12 +449,12 @@ _Pragma("unroll")
 double xmyNorm(const SpinorField &x, SpinorField &y) {
   check_same(x, y);
   double out[1];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
-          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y);
+          reduce<1>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re = u.c[k].re - v.c[k].re; v.c[k].im = u.c[k].im - v.c[k].im; acc[0] += norm_c(v.c[k]); }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { v.c[k].re = u.c[k].re - v.c[k].re; v.c[k].im = u.c[k].im - v.c[k].im; acc[0] += norm_c(v.c[k]); }
+            Y.store(i, v);
           }););
   flops += 3 * x.reals(); bytes += 3 * x.bytes();
   return out[0];
@@ -428,12 +463,12 @@ _Pragma("unroll")
 double caxpyNorm(Complex a, const SpinorField &x, SpinorField &y) {
   check_same(x, y);
   double out[1];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const cplx<real> A((real)a.real(), (real)a.imag());
-          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+  BY_PREC(x, const FA X(x); const FA Y(y); const cplx<real> A((real)a.real(), (real)a.imag());
+          reduce<1>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); acc[0] += norm_c(v.c[k]); }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(v.c[k], A, u.c[k]); acc[0] += norm_c(v.c[k]); }
+            Y.store(i, v);
           }););
   flops += 6 * x.reals(); bytes += 3 * x.bytes();
   return out[0];
@@ -442,13 +477,13 @@ _Pragma("unroll")
 double cabxpyAxNorm(double a, Complex b, SpinorField &x, SpinorField &y) {
   check_same(x, y);
   double out[1];
-  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v;
+  BY_PREC(x, const FA X(x); const FA Y(y);
           const real A = (real)a; const cplx<real> AB((real)(a * b.real()), (real)(a * b.imag()));
-          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i];
+          reduce<1>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; acc[0] += norm_c(v.c[k]); }
-            X[i] = u; Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(v.c[k], AB, u.c[k]); u.c[k].re *= A; u.c[k].im *= A; acc[0] += norm_c(v.c[k]); }
+            X.store(i, u); Y.store(i, v);
           }););
   flops += 7 * x.reals(); bytes += 4 * x.bytes();
   return out[0];
@@ -457,13 +492,13 @@ _Pragma("unroll")
 Complex caxpyDotzy(Complex a, const SpinorField &x, SpinorField &y, const SpinorField &z) {
   check_same(x, y); check_same(x, z);
   double out[2];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const FA Z(z);
           const cplx<real> A((real)a.real(), (real)a.imag());
-          reduce<2>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i], w = Z[i];
+          reduce<2>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i), w = Z.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); cdot_acc(acc, w.c[k], v.c[k]); }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(v.c[k], A, u.c[k]); cdot_acc(acc, w.c[k], v.c[k]); }
+            Y.store(i, v);
           }););
   flops += 8 * x.reals(); bytes += 4 * x.bytes();
   return Complex(out[0], out[1]);
@@ -472,13 +507,13 @@ _Pragma("unroll")
 double caxpyXmazNormX(Complex a, SpinorField &x, SpinorField &y, const SpinorField &z) {
   check_same(x, y); check_same(x, z);
   double out[1];
-  BY_PREC(x, Pack<real> *X = (Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const FA Z(z);
           const cplx<real> A((real)a.real(), (real)a.imag()), mA(-(real)a.real(), -(real)a.imag());
-          reduce<1>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i], w = Z[i];
+          reduce<1>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i), w = Z.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { cmac(v.c[k], A, u.c[k]); cmac(u.c[k], mA, w.c[k]); acc[0] += norm_c(u.c[k]); }
-            X[i] = u; Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { cmac(v.c[k], A, u.c[k]); cmac(u.c[k], mA, w.c[k]); acc[0] += norm_c(u.c[k]); }
+            X.store(i, u); Y.store(i, v);
           }););
   flops += 10 * x.reals(); bytes += 5 * x.bytes();
   return out[0];
@@ -487,13 +522,13 @@ _Pragma("unroll")
 Complex xpaycDotzy(const SpinorField &x, double a, SpinorField &y, const SpinorField &z) {
   check_same(x, y); check_same(x, z);
   double out[2];
-  BY_PREC(x, const Pack<real> *X = (const Pack<real> *)x.v; Pack<real> *Y = (Pack<real> *)y.v; const Pack<real> *Z = (const Pack<real> *)z.v;
+  BY_PREC(x, const FA X(x); const FA Y(y); const FA Z(z);
           const real A = (real)a;
-          reduce<2>(out, npacks<real>(x), [=] __device__(long i, double *acc) {
-            Pack<real> u = X[i], v = Y[i], w = Z[i];
+          reduce<2>(out, FA::count(x), [=] __device__(long i, double *acc) {
+            FA::pack u = X.load(i), v = Y.load(i), w = Z.load(i);
 _Pragma("unroll")
-            for (int k = 0; k < Pack<real>::N; k++) { v.c[k].re = u.c[k].re + A * v.c[k].re; v.c[k].im = u.c[k].im + A * v.c[k].im; cdot_acc(acc, w.c[k], v.c[k]); }
-            Y[i] = v;
+            for (int k = 0; k < FA::pack::N; k++) { v.c[k].re = u.c[k].re + A * v.c[k].re; v.c[k].im = u.c[k].im + A * v.c[k].im; cdot_acc(acc, w.c[k], v.c[k]); }
+            Y.store(i, v);
           }););
   flops += 6 * x.reals(); bytes += 4 * x.bytes();
   return Complex(out[0], out[1]);
@@ -501,18 +536,18 @@ _Pragma("unroll")
 
 // ---- block variants -----------------------------------------------------------------------------
 static const int MAX_BLOCK_VEC = 32;
-template <typename real> struct PtrList { const Pack<real> *p[MAX_BLOCK_VEC]; cplx<real> a[MAX_BLOCK_VEC]; int n; };
+template <typename A> struct PtrList { A p[MAX_BLOCK_VEC]; cplx<typename A::real> a[MAX_BLOCK_VEC]; int n; };
 
-template <int NV, typename real> static void block_cdot(double *out, const PtrList<real> &L, const Pack<real> *Y, long n) {
-  const PtrList<real> l = L;
+template <int NV, typename A> static void block_cdot(double *out, const PtrList<A> &L, const A &Y, long n) {
+  const PtrList<A> l = L;
   reduce<2 * NV>(out, n, [=] __device__(long i, double *acc) {
-    Pack<real> v = Y[i];
+    typename A::pack v = Y.load(i);
 _Pragma("unroll")
     for (int j = 0; j < NV; j++) {
       if (j < l.n) {
-        Pack<real> u = l.p[j][i];
+        typename A::pack u = l.p[j].load(i);
 _Pragma("unroll")
-        for (int k = 0; k < Pack<real>::N; k++) cdot_acc(acc + 2 * j, u.c[k], v.c[k]);
+        for (int k = 0; k < A::pack::N; k++) cdot_acc(acc + 2 * j, u.c[k], v.c[k]);
       }
     }
   });
@@ -524,9 +559,8 @@ void cDotProduct(Complex *result, const std::vector<SpinorField *> &x, const Spi
   if (n > MAX_BLOCK_VEC) QB_ERROR("block cDotProduct supports at most %d vectors", MAX_BLOCK_VEC);
   for (auto *f : x) check_same(*f, y);
   double out[2 * MAX_BLOCK_VEC];
-  BY_PREC(y, PtrList<real> L; L.n = n; for (int j = 0; j < n; j++) L.p[j] = (const Pack<real> *)x[j]->v;
-          for (int j = n; j < MAX_BLOCK_VEC; j++) L.p[j] = nullptr;
-          const Pack<real> *Y = (const Pack<real> *)y.v; const long np = npacks<real>(y);
+  BY_PREC(y, PtrList<FA> L; L.n = n; for (int j = 0; j < n; j++) L.p[j] = FA(*x[j]);
+          const FA Y(y); const long np = FA::count(y);
           if (n <= 4) block_cdot<4>(out, L, Y, np);
           else if (n <= 8) block_cdot<8>(out, L, Y, np);
           else if (n <= 16) block_cdot<16>(out, L, Y, np);
@@ -540,17 +574,17 @@ void caxpy(const Complex *a, const std::vector<SpinorField *> &x, SpinorField &y
   if (n == 0) return;
   if (n > MAX_BLOCK_VEC) QB_ERROR("block caxpy supports at most %d vectors", MAX_BLOCK_VEC);
   for (auto *f : x) check_same(*f, y);
-  BY_PREC(y, PtrList<real> L; L.n = n;
-          for (int j = 0; j < n; j++) { L.p[j] = (const Pack<real> *)x[j]->v; L.a[j] = cplx<real>((real)a[j].real(), (real)a[j].imag()); }
-          Pack<real> *Y = (Pack<real> *)y.v;
-          elementwise(npacks<real>(y), [=] __device__(long i) {
-            Pack<real> v = Y[i];
+  BY_PREC(y, PtrList<FA> L; L.n = n;
+          for (int j = 0; j < n; j++) { L.p[j] = FA(*x[j]); L.a[j] = cplx<real>((real)a[j].real(), (real)a[j].imag()); }
+          const FA Y(y);
+          elementwise(FA::count(y), [=] __device__(long i) {
+            FA::pack v = Y.load(i);
             for (int j = 0; j < L.n; j++) {
-              Pack<real> u = L.p[j][i];
+              FA::pack u = L.p[j].load(i);
 _Pragma("unroll")
-              for (int k = 0; k < Pack<real>::N; k++) cmac(v.c[k], L.a[j], u.c[k]);
+              for (int k = 0; k < FA::pack::N; k++) cmac(v.c[k], L.a[j], u.c[k]);
             }
-            Y[i] = v;
+            Y.store(i, v);
           }););
   flops += 4ull * n * y.reals(); bytes += (unsigned long long)(n + 2) * y.bytes();
 }

@@ -1017,6 +1017,8 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
   fill_solver_param(sp, param);
   param->secs = 0; param->gflops = 0; param->iter = 0;
   const Prec prec = sp.precision;
+  // int16 solver vectors exist for single fields; a doublet solve keeps fp32 vectors in front of a half-precision operator
+  struct HalfVecGuard { bool saved; HalfVecGuard(bool off) : saved(half_vectors_enabled()) { if (off) set_half_vectors(false); } ~HalfVecGuard() { set_half_vectors(saved); } } hv_guard(nflavor_of(param) == 2);
   const Prec prec_vec_sloppy = blas_prec(sp.precision_sloppy);
   if (prec == PREC_HALF) QB_ERROR("cuda_prec must be single or double for a solve");
   param->spinorGiB = (double)G.lat.geom.Vh * nflavor_of(param) * 24 * (pc_solve ? 1 : 2) * (int)prec * (param->preserve_source == QUDA_PRESERVE_SOURCE_NO ? 7 : 9) / (double)(1 << 30);
@@ -1030,6 +1032,7 @@ void invertQuda(void *hp_x, void *hp_b, QudaInvertParam *param) {
 
   const int nfl = nflavor_of(param);
   if (nfl == 2 && param->inv_type_precondition == QUDA_MG_INVERTER) QB_ERROR("Multigrid for the non-degenerate doublet is not implemented");
+
   std::unique_ptr<SpinorField> b(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec, 4, 3, 1, nfl));
   std::unique_ptr<SpinorField> x(new SpinorField(G.lat.geom.Vh, pc_solution ? 1 : 2, prec, 4, 3, 1, nfl));
   load_host_spinor(*b, hp_b, param);
@@ -1147,7 +1150,7 @@ static bool invert_multi_src_block(void **hp_x, void **hp_b, QudaInvertParam *pa
   Runtime &r = rt();
   const int saved_verbosity = r.verbosity;
   if ((int)param->verbosity != INVALID_INT) r.verbosity = (int)param->verbosity;
-  const Prec prec_vec_sloppy = blas_prec(sp.precision_sloppy);
+  const Prec prec_vec_sloppy = sp.precision_sloppy == PREC_HALF ? PREC_SINGLE : sp.precision_sloppy;   // the lock-step Krylov space is fp32
   std::unique_ptr<DiracTM> d(make_dirac(param, pc, pick_gauge(prec)));
   std::unique_ptr<DiracTM> dS(make_dirac(param, pc, pick_gauge(sp.precision_sloppy)));
   if (dS->gauge->prec != prec_vec_sloppy) dS->gauge_vec = pick_gauge(prec_vec_sloppy);
@@ -1532,15 +1535,21 @@ extern "C" int blasQudaB200(const char *name, long n, int prec, const double *co
   using namespace qb::blas;
   if (n <= 0 || n % 12) QB_ERROR("blasQudaB200: n must be a positive multiple of 12");
   const Prec pr = to_prec((QudaPrecision)prec, "prec");
-  if (pr == PREC_HALF) QB_ERROR("blasQudaB200: single or double precision only");
+  // half precision (int16 + norm fields): the host arrays are fp32; they go through an fp32 device field and the library's own
+  // fp32 <-> int16 conversion (blas::copy), in the internal plane order [plane][site] of a parity field of n / 12 sites
+  const bool half = pr == PREC_HALF;
   const long Vh = n / 12;
-  const size_t bytes = (size_t)n * 2 * (int)pr;
+  const size_t bytes = (size_t)n * 2 * (half ? 4 : (int)pr);
   SpinorField fx(Vh, 1, pr), fy(Vh, 1, pr), fz(Vh, 1, pr), fw(Vh, 1, pr);
+  SpinorField stage(Vh, 1, half ? PREC_SINGLE : pr);
   cudaStream_t s = rt().compute;
   void *hp[4] = {x, y, z, w};
   SpinorField *fp[4] = {&fx, &fy, &fz, &fw};
   for (int i = 0; i < 4; i++)
-    if (hp[i]) QB_CUDA(cudaMemcpyAsync(fp[i]->v, hp[i], bytes, cudaMemcpyHostToDevice, s));
+    if (hp[i]) {
+      if (half) { QB_CUDA(cudaMemcpyAsync(stage.v, hp[i], bytes, cudaMemcpyHostToDevice, s)); copy(*fp[i], stage); }
+      else QB_CUDA(cudaMemcpyAsync(fp[i]->v, hp[i], bytes, cudaMemcpyHostToDevice, s));
+    }
   const double a = coef[0];
   const Complex ca(coef[0], coef[1]), cb(coef[2], coef[3]);
   const std::string nm(name);
@@ -1582,7 +1591,10 @@ extern "C" int blasQudaB200(const char *name, long n, int prec, const double *co
     caxpy(c3, v, fw);
   } else QB_ERROR("blasQudaB200: unknown operation %s", name);
   for (int i = 0; i < 4; i++)
-    if (hp[i]) QB_CUDA(cudaMemcpyAsync(hp[i], fp[i]->v, bytes, cudaMemcpyDeviceToHost, s));
+    if (hp[i]) {
+      if (half) { copy(stage, *fp[i]); QB_CUDA(cudaMemcpyAsync(hp[i], stage.v, bytes, cudaMemcpyDeviceToHost, s)); QB_CUDA(cudaStreamSynchronize(s)); }
+      else QB_CUDA(cudaMemcpyAsync(hp[i], fp[i]->v, bytes, cudaMemcpyDeviceToHost, s));
+    }
   QB_CUDA(cudaStreamSynchronize(s));
   return nres;
 }

@@ -6,6 +6,13 @@
 
 namespace qb {
 
+static int g_half_vectors = -1;
+bool half_vectors_enabled() {
+  if (g_half_vectors < 0) { const char *e = getenv("QB_HALF_VECTORS"); g_half_vectors = (e && atoi(e) == 0) ? 0 : 1; }
+  return g_half_vectors == 1;
+}
+void set_half_vectors(bool on) { g_half_vectors = on ? 1 : 0; }
+
 using blas::Complex;
 
 SpinorField *new_like(const SpinorField &a, Prec prec) { return new SpinorField(a.Vh, a.nparity, prec, a.nspin, a.ncolor, 1, a.nflavor); }

@@ -93,6 +93,10 @@ class BiCGStab : public Solver {
 };
 
 SpinorField *new_like(const SpinorField &a, Prec prec);
-inline Prec blas_prec(Prec p) { return p == PREC_HALF ? PREC_SINGLE : p; }  // solver vectors: fp32 at least
+// Precision of the solver's vectors for an operator precision p.  int16 + norm vectors (the reference's half precision, lib/blas_core.h:12-52)
+// are used for single fine-grid fields; doublet fields and QB_HALF_VECTORS=0 keep fp32 vectors in front of a half-precision operator.
+bool half_vectors_enabled();
+void set_half_vectors(bool on);
+inline Prec blas_prec(Prec p) { return (p == PREC_HALF && !half_vectors_enabled()) ? PREC_SINGLE : p; }
 
 }  // namespace qb

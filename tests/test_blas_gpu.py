@@ -147,3 +147,43 @@ def test_blas_against_the_reference_host_blas(quda, prec):
         for g, h in zip(got[:2], (x, y)):
             hc = h[0::2].astype(np.float64) + 1j * h[1::2].astype(np.float64)
             assert np.abs(g - hc).max() <= tol * np.abs(hc).max(), name
+
+
+def run_half(L, name, x, y, z, w):
+    """prec = 2: fp32 host arrays in the internal plane order of a parity field ([plane of 2 complex][site]); the library converts to
+    int16 + norm and back"""
+    arrs = []
+    for v in (x, y, z, w):
+        f = np.empty(2 * v.size, dtype=np.float32)
+        f[0::2] = v.real; f[1::2] = v.imag
+        arrs.append(f)
+    coef = (C.c_double * 4)(A.real, A.imag, B.real, B.imag)
+    res = (C.c_double * 8)()
+    n = L.blasQudaB200(name.encode(), x.size, 2, coef, *[a.ctypes.data_as(C.c_void_p) for a in arrs], res)
+    back = [a[0::2].astype(np.float64) + 1j * a[1::2].astype(np.float64) for a in arrs]
+    return back, list(res)[:n]
+
+
+@pytest.mark.parametrize("n", [12 * 64, 12 * 40000])
+def test_half_precision_blas(quda, n):
+    """int16 + norm solver vectors (the reference's half precision: short4 + norm, fp32 arithmetic, lib/blas_core.h:12-52,
+    lib/io_spinor.h:282-320): every BLAS / reduction operation against the host on the same fp32 inputs.  Each site is quantised to
+    16 bits relative to its largest component on the way in and on the way out: tolerance 1e-3 of the vector norm (north_star's half bar);
+    measured 2e-5 .. 6e-5."""
+    L = quda.lib()
+    rng = np.random.default_rng(n)
+    vecs = [(rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64).astype(np.complex128) for _ in range(4)]
+    worst = 0.0
+    for name in OPS:
+        got, res = run_half(L, name, *vecs)
+        want, wres = host(name, *vecs)
+        for g, h in zip(got, want):
+            err = np.linalg.norm(g - h) / np.linalg.norm(h)
+            worst = max(worst, err)
+            assert err <= 1e-3, (name, err)
+        if wres is not None:
+            scale = np.linalg.norm(vecs[0]) * np.linalg.norm(vecs[1])
+            assert len(res) == len(wres), name
+            for a, b in zip(res, wres):
+                assert abs(a - b) <= 1e-3 * max(abs(b), scale), (name, a, b)
+    print(f"half-precision BLAS, n = {n}: worst relative L2 error of an output vector {worst:.2e}")

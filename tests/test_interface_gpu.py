@@ -69,3 +69,54 @@ def test_make_resident_solution_keeps_the_solution_on_the_device(quda, oracle):
     x3 = np.zeros_like(b)
     L.invertQuda(vp(x3), vp(b), C.byref(p))
     assert host_residual(oracle, g, x3, b, kappa, mu) < 5e-9 and L.residentSolutionQudaB200() == f
+
+
+@pytest.mark.parametrize("inv", ["gcr", "bicgstab", "cg"])
+def test_half_precision_sloppy_solver_vectors(quda, oracle, inv):
+    """cuda_prec_sloppy = half: int16 + norm Krylov vectors and an int16 sloppy operator inside reliable updates / defect correction in the
+    outer precision (the reference's mixed-precision mode, lib/inv_gcr_quda.cpp, lib/blas_core.h:12-52).  The solution must still reach
+    the requested residual of the fp64 operator."""
+    q, L = quda, quda.lib()
+    kappa, mu = 0.12, 0.1
+    g, b = setup(q, oracle, sloppy=2)
+    p = mg_inv_param(q, kappa, mu, sloppy=2, precond=2)
+    if inv == "cg":
+        p.solve_type = q.QUDA_NORMOP_PC_SOLVE
+        p.inv_type = q.QUDA_CG_INVERTER
+        p.tol = 1e-9; p.maxiter = 8000; p.reliable_delta = 0.1
+    else:
+        p.solve_type = q.QUDA_DIRECT_PC_SOLVE
+        p.inv_type = q.QUDA_GCR_INVERTER if inv == "gcr" else q.QUDA_BICGSTAB_INVERTER
+        p.tol = 1e-8; p.maxiter = 4000; p.gcrNkrylov = 16; p.reliable_delta = 1e-2
+    x = np.zeros_like(b)
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    res = host_residual(oracle, g, x, b, kappa, mu)
+    print(f"{inv} with half-precision sloppy vectors: {p.iter} iterations, host residual {res:.2e}")
+    assert res < (5e-8 if inv != "cg" else 5e-7) and p.iter > 0
+
+
+def test_mg_gcr_with_half_precision_krylov_space(quda, oracle):
+    """outer GCR in int16 vectors around the multigrid preconditioner (fp32 inside): converges to the same residual in about the same
+    number of iterations as with fp32 Krylov vectors"""
+    from tests.test_multigrid_gpu import point_source
+    q, L = quda, quda.lib()
+    X, kappa, mu = (8, 8, 8, 16), 0.1245, 0.005
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711)
+    iters = {}
+    for sloppy in (4, 2):
+        load_gauge(q, g, X, prec=8, sloppy=sloppy, precond=4, recon=12)
+        ip = mg_inv_param(q, kappa, mu, sloppy=4)
+        mgp = q.multigrid_param(ip, n_level=2, geo_block=((4, 4, 4, 4),), n_vec=(8,), setup_maxiter=200, setup_tol=5e-6)
+        mg = L.newMultigridQuda(C.byref(mgp))
+        b = point_source(oracle.V); x = np.zeros_like(b)
+        p = mg_inv_param(q, kappa, mu, sloppy=sloppy)
+        p.inv_type_precondition = q.QUDA_MG_INVERTER; p.preconditioner = mg
+        p.gcrNkrylov = 20; p.tol = 1e-8; p.maxiter = 300; p.reliable_delta = 1e-2
+        L.invertQuda(vp(x), vp(b), C.byref(p))
+        res = host_residual(oracle, g, x, b, kappa, mu)
+        L.destroyMultigridQuda(mg)
+        iters[sloppy] = p.iter
+        assert res < 5e-8, (sloppy, res)
+    print(f"MG-GCR iterations with fp32 / int16 Krylov vectors: {iters[4]} / {iters[2]}")
+    assert iters[2] <= 2 * iters[4] + 4
