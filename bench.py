@@ -372,14 +372,18 @@ def cpu_baseline_coarse(oracle):
     return out
 
 
-def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=False, multi_src=None):
+def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=False, multi_src=None, sloppy=4):
     """Second half of the BASELINE metric: 3-level MG-GCR twisted-mass solve (seconds), plus the coarse-operator
     kernels against their HBM roofline.  32^3x64, 4^4 then 2^4 aggregates, 24 vectors per level, MR(2,2) smoother,
     K-cycle, fp64 outer GCR(20) / fp32 MG / int16 level-0 smoother, weak-field SU(3) gauge (periodic)."""
     kappa, mu = 0.1248, 0.004
     oracle.set_dims(X)
     g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=4711)
+    # sloppy = 2: int16 + norm Krylov vectors and int16 links in the outer GCR (the multigrid keeps fp32 vectors: its invert_param says so)
     gp = q.gauge_param(X, cuda_prec=8, reconstruct=12, cuda_prec_sloppy=4, cuda_prec_precondition=precond, t_boundary=q.QUDA_PERIODIC_T)
+    if sloppy == 2:
+        gp.cuda_prec_sloppy = 2
+        gp.cuda_prec_precondition = 4 if precond == 4 else 2
     L.loadGaugeQuda((C.c_void_p * 4)(*[a.ctypes.data for a in g]), C.byref(gp))
 
     def inv_param():
@@ -421,6 +425,9 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=Fal
     p = inv_param()
     p.inv_type_precondition = q.QUDA_MG_INVERTER
     p.preconditioner = mg
+    p.cuda_prec_sloppy = sloppy
+    if sloppy == 2:
+        p.reliable_delta = 1e-2
     if pc:
         p.solve_type = q.QUDA_DIRECT_PC_SOLVE
     L.invertQuda(vp(x), vp(b), C.byref(p))  # warm-up (allocations)
@@ -464,7 +471,7 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=Fal
         os.environ.pop("QB_BLOCK_MG", None)
         multi["speedup_per_source"] = multi["sequential"]["solve_seconds"] / multi["block"]["solve_seconds"]
         del bs, xs
-    res = {"lattice": list(X), "levels": 3, "outer_solve": "QUDA_DIRECT_PC_SOLVE, coarse_grid_solution_type MATPC on every level" if pc else "QUDA_DIRECT_SOLVE, coarse_grid_solution_type MAT",
+    res = {"lattice": list(X), "levels": 3, "outer_krylov_vectors": {4: "fp32", 2: "int16 + norm (cuda_prec_sloppy = half), reliable_delta 1e-2"}[sloppy], "outer_solve": "QUDA_DIRECT_PC_SOLVE, coarse_grid_solution_type MATPC on every level" if pc else "QUDA_DIRECT_SOLVE, coarse_grid_solution_type MAT",
            "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond],
            "preconditioner_storage": "fp16 V and coarse links, fp32 arithmetic" if half_storage else "fp32", "blocks": [[4, 4, 4, 4], [2, 2, 2, 2]], "n_vec": [24, 24], "kappa": kappa, "mu": mu,
            "setup_seconds": setup_s, "setup_seconds_first_call": setup_first_s, "solve_seconds": p.secs, "solve_wall_seconds_incl_h2d_d2h": wall_s, "iterations": p.iter,
@@ -754,6 +761,8 @@ def main():
         mg_res_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False)
         mg_res_pc = run_mg_leg(q, L, oracle, X, args.mg_precond, full=False, pc=True, multi_src=True)
         mg_res_pc_h16 = run_mg_leg(q, L, oracle, X, args.mg_precond, half_storage=True, full=False, pc=True)
+        # int16 outer Krylov space: needs the fp32 links resident for the multigrid, i.e. an fp32 level-0 smoother
+        mg_res_pc_h16_hs = run_mg_leg(q, L, oracle, X, 4, half_storage=True, full=False, pc=True, sloppy=2) if args.mg_precond == 4 else None
     sampler.stop_flag = True
 
     # max over ranks of the device time
@@ -846,6 +855,8 @@ def main():
             line["extra"]["mg_gcr_3level_fp16_preconditioner_storage"] = mg_res_h16
             line["extra"]["mg_gcr_3level_even_odd"] = mg_res_pc
             line["extra"]["mg_gcr_3level_even_odd_fp16_preconditioner_storage"] = mg_res_pc_h16
+            if mg_res_pc_h16_hs:
+                line["extra"]["mg_gcr_3level_even_odd_fp16_storage_half_sloppy"] = mg_res_pc_h16_hs
         if half_ms:
             line["extra"]["half_r12"] = {"ms_per_step": half_ms, "gflops": FLOPS_PER_SITE * sites / (half_ms * 1e-3) / 1e9,
                                          "hbm_gbs_compulsory": 296 * Vh / (half_ms * 1e-3) / 1e9,

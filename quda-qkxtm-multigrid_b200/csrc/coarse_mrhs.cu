@@ -22,8 +22,8 @@
 // One persistent CTA per SM walks sites; warp roles:
 //   warp 0    : producer  - one 1-D bulk copy (cp.async.bulk, mbarrier complete_tx) per (site, direction) link matrix
 //   warp 1    : MMA issue - one thread, tcgen05.mma.kind::tf32, tcgen05.commit releases stages / publishes accumulators
-//   warps 2-5 : builders  - A tile (and in MODE 3 the hi / lo split of the B tile)
-//   warps 6-9 : epilogue  - tcgen05.ld -> shared staging -> a * out + b * xpay -> coalesced 128-bit stores
+//   warps 2-9  : builders  - A tile (and in MODE 3 the hi / lo split of the B tile): two groups of 128 threads on alternate stages
+//   warps 10-13: epilogue - tcgen05.ld -> shared staging -> a * out + b * xpay -> coalesced 128-bit stores
 #include <cstdlib>
 #include "coarse.h"
 #include "comm.h"
@@ -263,7 +263,8 @@ struct MrhsKernelArgs {
   int variant;  // tuning experiments (QB_MRHS_VARIANT): 0 = production
 };
 
-constexpr int MRHS_THREADS = 320;
+constexpr int MRHS_BUILD_GROUPS = 2;     // builder groups of 128 threads on alternate stages (a third group gained nothing: 0.417 vs 0.411 ms at 12 rhs)
+constexpr int MRHS_THREADS = 64 + 128 * MRHS_BUILD_GROUPS + 128;
 constexpr int MRHS_MAX_STAGES = 10;  // depth limit of the link ring
 constexpr int MRHS_MAX_WORK = 4;     // depth limit of the work ring (A tile, lo part of the link tile)
 
@@ -279,7 +280,10 @@ template <int N, int M, int MODE> struct MrhsCfg {
   static constexpr int NKC = N / 2;          // 16-byte chunks (2 complex numbers) along K per direction
   static constexpr int KSTEPS = NKC / 2;     // tf32 MMAs (K = 8) per direction
   static constexpr int Y_BYTES = N * NKC * 16;
-  static constexpr int BGROUP = 64;                      // threads per builder group; the two groups take alternate stages
+  // threads per builder group; the two groups take alternate stages.  Round-2 measurement (tools/mrhs_bench.py): the kernel time grows
+  // linearly with the number of right-hand sides although the MMA count per site does not -- the builders' shared-memory work (and not the
+  // tcgen05 issue rate: a second issuing warp for disjoint accumulator groups changed nothing) is what binds MODE 3, so they get 8 warps
+  static constexpr int BGROUP = 128;
   static constexpr int YPT = (N * NKC + BGROUP - 1) / BGROUP;  // B-tile float4 per builder thread (MODE 3 split)
   // Accumulator groups.  The tensor core rounds every accumulation toward zero, so the error of a long chain grows
   // linearly with its length; MODE 3 therefore keeps one TMEM accumulator per pair of directions and adds them in
@@ -430,12 +434,12 @@ __global__ void __launch_bounds__(MRHS_THREADS, 1) coarse_mrhs_kernel(const Mrhs
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + 4 * MRHS_BUILD_GROUPS) {
     // ================= builders: raw vectors -> A tile rows, (MODE 3) hi / lo split of the link tile =================
     // Two groups of 64 threads take alternate stages, so that two stages are always under construction.  A thread owns
     // fixed 16-byte slots of the A tile: slot = (chunk kc, row m), m = 2r + h (+ 2R for the lo rows), read from
     // raw[kc][r]; consecutive threads write consecutive slots (no bank conflicts) and the index math is done once.
-    const int grp = (warp - 2) >> 1, bt = tid - 64 - grp * C::BGROUP;
+    const int grp = (warp - 2) >> 2, bt = tid - 64 - grp * C::BGROUP;
     const int live = (MODE == 3 ? 4 : 2) * R;  // live rows
     const int nslot = NKC * live;
     // slot e = bt + u * BGROUP <-> (kc, m) advanced incrementally: no division in the loop
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(MRHS_THREADS, 1) coarse_mrhs_kernel(const Mrhs
     const long nstage_total = ((p.nsites - blockIdx.x + gridDim.x - 1) / gridDim.x) * ndir;
     const uint32_t link_s = smem_u32(link0), work_s = smem_u32(work0);
     constexpr int BATCH = 4;
-    for (long c = grp; c < nstage_total; c += 2) {
+    for (long c = grp; c < nstage_total; c += MRHS_BUILD_GROUPS) {
       mbar_wait(&full[stage], phase);
       mbar_wait(&work_free[w], wphase ^ 1);
       const uint32_t ls = link_s + (uint32_t)stage * LINK, ws = work_s + (uint32_t)w * WORK;
@@ -492,6 +496,8 @@ __global__ void __launch_bounds__(MRHS_THREADS, 1) coarse_mrhs_kernel(const Mrhs
             const int e = e0 + u * C::BGROUP;
             if (e < N * NKC) {
               const float4 x = v[u];
+              // (measured, round 2: leaving the raw tile as the hi operand -- the tensor core truncates the low 13 bits, the parity tests pass
+              // with lo = x - trunc(x) -- saves this store but not time: 0.437 vs 0.411 ms at 12 rhs)
               const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
               sts128(ls + (uint32_t)e * 16, h);
               sts128(yl + (uint32_t)e * 16, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
@@ -501,12 +507,12 @@ __global__ void __launch_bounds__(MRHS_THREADS, 1) coarse_mrhs_kernel(const Mrhs
       }
       fence_proxy_async_smem();
       mbar_arrive(&ab_ready[w]);
-      stage += 2; if (stage >= S) { stage -= S; phase ^= 1; }
-      w += 2; if (w >= NW) { w -= NW; wphase ^= 1; }
+      stage += MRHS_BUILD_GROUPS; if (stage >= S) { stage -= S; phase ^= 1; }
+      w += MRHS_BUILD_GROUPS; while (w >= NW) { w -= NW; wphase ^= 1; }
     }
   } else {
     // ================= epilogue =================
-    const int et = tid - 192;
+    const int et = tid - (64 + 128 * MRHS_BUILD_GROUPS);
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
     // accumulator row held by this thread: M = 128: lane i <-> row i; M = 64: rows 16 q' .. 16 q' + 15 sit in lanes 32 q' .. 32 q' + 15
