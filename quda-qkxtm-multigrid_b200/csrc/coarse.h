@@ -65,8 +65,9 @@ struct CoarseOperator {
 
 // Builders of the Galerkin coarse links (coarse_op.cu)
 // clover_site: site-major fp32 packed clover term [V][72] (nullptr: the site-local term is 1 + i a gamma5)
+// VL: left vectors of the product in the layout of T.V (nullptr: V itself), see DiracTM::create_coarse_op
 void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
-                            const float *clover_site = nullptr);
+                            const float *clover_site = nullptr, const float *VL = nullptr);
 // preconditioned = true: coarsen Xinv M (the links Yhat of `fine`) instead of M
 void build_coarse_from_coarse(CoarseOperator &out, const Transfer &T, const CoarseOperator &fine, bool preconditioned = false);
 // rows of chirality 0 / 1 of every link matrix (slots 0..8) times c0 / c1: turns R M P into R A^-1 M P when A is a constant per chirality

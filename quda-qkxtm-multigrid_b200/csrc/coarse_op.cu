@@ -106,6 +106,8 @@ static float *decompress_ghost(const GaugeField &gf, const Geom &g, int mu) {
 struct GalerkinArgs {
   // transfer
   const float4 *V;
+  const float4 *VL;   // left vectors of the Galerkin product (same layout as V); nullptr: V itself.  Preconditioned coarsening with a clover
+                      // term: VL = A^-dag V, so that VL^dag L V = V^dag A^-1 L V (the reference's AV, lib/coarse_op.cuh:384-456, on the other side)
   const int *f2c, *c2f;
   int Nf, nvec, block_sites;
   long Vh_f;
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const GalerkinArgs a) {
   float2 *Vn = Vx + Nf * nvec;        // [Nf][nvec]
   float2 *W = Vn + Nf * nvec;         // [Nf][N]
   float2 *Ld = W + Nf * N;            // LEVEL 0: 9 complex (the link); LEVEL 1: [Nf][Nf]
+  float2 *VxL = a.VL ? Ld + (LEVEL == 0 ? 16 : Nf * Nf) : Vx;   // [Nf][nvec] left vectors at x
   __shared__ int s_info[4];           // neighbour parity, leaves-block flag, ghost flag
   __shared__ long s_cb[2];
 
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const GalerkinArgs a) {
       const long ncb = s_cb[0];
       const bool ghost = s_info[2] != 0;
       stage_V(Vx, a, a.V, a.Vh_f, parity, cb);
+      if (a.VL) stage_V(VxL, a, a.VL, a.Vh_f, parity, cb);
       if (d < 8) {
         if (ghost) stage_V(Vn, a, a.Vghost[d >> 1][(d & 1) ? 0 : 1], a.faceVh[d >> 1], npar, ncb);
         else stage_V(Vn, a, a.V, a.Vh_f, npar, ncb);
@@ -324,8 +328,8 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const GalerkinArgs a) {
       }
       __syncthreads();
       if (owner) {
-        if (s_info[1]) accumulate_tile<T>(hop, Vx, W, nvec, N, cpc, r0, c0);
-        else accumulate_tile<T>(diag, Vx, W, nvec, N, cpc, r0, c0);
+        if (s_info[1]) accumulate_tile<T>(hop, VxL, W, nvec, N, cpc, r0, c0);
+        else accumulate_tile<T>(diag, VxL, W, nvec, N, cpc, r0, c0);
       }
     }
     if (owner && d < 8) store_tile<T>(a.Yc, X, d, N, r0, c0, hop);
@@ -342,7 +346,7 @@ static int tile_for(int N, int nvec) {
 
 template <int LEVEL> static void launch_galerkin(const GalerkinArgs &a, long Vc) {
   const int T = tile_for(a.N, a.nvec);
-  const size_t sm = sizeof(float2) * ((size_t)2 * a.Nf * a.nvec + (size_t)a.Nf * a.N + (LEVEL == 0 ? 16 : (size_t)a.Nf * a.Nf));
+  const size_t sm = sizeof(float2) * ((size_t)(a.VL ? 3 : 2) * a.Nf * a.nvec + (size_t)a.Nf * a.N + (LEVEL == 0 ? 16 : (size_t)a.Nf * a.Nf));
   cudaStream_t s = rt().compute;
   const int threads = std::max(32, (((a.N / T) * (a.N / T) + 31) / 32) * 32);
 #define GO(TT)                                                                                               \
@@ -374,10 +378,10 @@ static void fill_transfer_args(GalerkinArgs &a, const Transfer &T) {
 float *decompress_ghost_links(const GaugeField &gf, const Geom &g, int mu) { return decompress_ghost(gf, g, mu); }
 
 void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeField &gauge, const Geom &fine_geom, double kappa, double twist_a,
-                            const float *clover_site) {
+                            const float *clover_site, const float *VL) {
   if (T.Nf != 12) QB_ERROR("build_coarse_from_fine: transfer is not defined on a Wilson-type fine field");
   out.allocate(T.coarse, T.nvec);
-  if (galerkin_mma_supported(T)) {  // tensor-core build (coarse_op_mma.cu)
+  if (!VL && galerkin_mma_supported(T)) {  // tensor-core build (coarse_op_mma.cu); separate left vectors take the CUDA-core kernel
     build_coarse_from_fine_mma(out, T, gauge, fine_geom, kappa, twist_a, clover_site);
     return;
   }
@@ -385,6 +389,7 @@ void build_coarse_from_fine(CoarseOperator &out, const Transfer &T, const GaugeF
   GalerkinArgs a{};
   fill_transfer_args(a, T);
   a.Yc = (float4 *)out.Y; a.U = U; a.kappa = (float)kappa; a.twist_a = (float)twist_a; a.Yf = nullptr; a.clover = clover_site;
+  a.VL = (const float4 *)VL;
   float *ug[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int d = 0; d < 4; d++)
     if (fine_geom.part[d]) {
@@ -432,14 +437,59 @@ void scale_coarse_rows(CoarseOperator &op, std::complex<double> c0, std::complex
 // lib/coarse_op.cuh:202-224, :1349-1440, called from DiracTwistedMassPC::createCoarseOp, lib/dirac_twisted_mass.cpp:580).  For twisted
 // mass A = 1 + i a gamma5 is a constant per chirality and V is chirality-blocked, so  V^dag A^-1 M V = A_c^-1 (V^dag M V):  the rows of
 // chirality +- of the ordinary Galerkin links get the factor 1 / (1 +- i a) -- exact, and the tensor-core build is reused as it is.
+// column j of V as a fine field and back: f(x, k) = V(x, k, j)   (fill_v_kernel of transfer.cu is the other direction)
+__global__ void v_column_kernel(float4 *field, const float4 *V, long Vh, int Nf, int nvec, int j, int to_v, float4 *Vout) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nkp = Nf / 2, nvh = nvec / 2;
+  if (t >= 2 * Vh * nkp) return;
+  const long cb = t % Vh;
+  const int kp = (int)((t / Vh) % nkp), parity = (int)(t / (Vh * nkp));
+  const size_t i0 = (((size_t)parity * Nf + 2 * kp) * nvh + j / 2) * Vh + cb, i1 = (((size_t)parity * Nf + 2 * kp + 1) * nvh + j / 2) * Vh + cb;
+  float4 *f = field + ((size_t)parity * nkp + kp) * Vh + cb;
+  if (!to_v) {
+    const float2 a = ((const float2 *)(V + i0))[j & 1], b = ((const float2 *)(V + i1))[j & 1];
+    *f = make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    const float4 v = *f;
+    ((float2 *)(Vout + i0))[j & 1] = make_float2(v.x, v.y);
+    ((float2 *)(Vout + i1))[j & 1] = make_float2(v.z, v.w);
+  }
+}
+
+// `this` is the full operator of the level.  preconditioned: the coarse links of A^-1 M = 1 - kappa A^-1 D, the operator whose even-odd
+// Schur complement is the symmetric preconditioned one (the reference gets there through AV = A^-1 V and bidirectional links,
+// lib/coarse_op.cuh:202-224, :1349-1440, called from DiracTwistedMassPC::createCoarseOp, lib/dirac_twisted_mass.cpp:580).  For twisted
+// mass A = 1 + i a gamma5 is a constant per chirality and V is chirality-blocked, so  V^dag A^-1 M V = A_c^-1 (V^dag M V):  the rows of
+// chirality +- of the ordinary Galerkin links get the factor 1 / (1 +- i a) -- exact, and the tensor-core build is reused as it is.
+// With a clover term (DiracTwistedCloverPC::createCoarseOp, computeTMCAV lib/coarse_op.cuh:384-456) A = C + i a gamma5 varies from site
+// to site: the product is taken with the left vectors  VL = A^-dag V  (column by column through the clover kernel), VL^dag L V = V^dag A^-1 L V.
 void DiracTM::create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned) const {
   if (pc) QB_ERROR("create_coarse_op is called on the full operator of the level (preconditioned = true selects the coarsening of A^-1 M)");
   if (dagger) QB_ERROR("create_coarse_op: operator must not be daggered");
-  if (preconditioned && clover) QB_ERROR("preconditioned coarsening (coarse_grid_solution_type = QUDA_MATPC_SOLUTION) with a clover term is not implemented: use QUDA_MAT_SOLUTION");
   float *cs = clover ? clover->site_major_f32() : nullptr;
-  build_coarse_from_fine(coarse, T, *gauge, lat->geom, kappa, flavor ? twist_a() : 0.0, cs);
+  float *VL = nullptr;
+  if (preconditioned && clover) {
+    if (gauge->prec != PREC_SINGLE) QB_ERROR("preconditioned coarsening with a clover term needs the fp32 operator");
+    VL = (float *)pool_malloc(T.v_bytes());
+    SpinorField f(lat->geom.Vh, 2, PREC_SINGLE), gfield(lat->geom.Vh, 2, PREC_SINGLE);
+    const long nt = 2 * (long)lat->geom.Vh * 6;
+    const CloverField &cl = clover->get(PREC_SINGLE, twist_a());
+    for (int j = 0; j < T.nvec; j++) {
+      v_column_kernel<<<div_up(nt, 256), 256, 0, rt().compute>>>((float4 *)f.v, (const float4 *)T.V, lat->geom.Vh, 12, T.nvec, j, 0, nullptr);
+      QB_CHECK_LAUNCH();
+      for (int p = 0; p < 2; p++) {
+        SpinorField o, i;
+        gfield.view_parity(o, p); f.view_parity(i, p);
+        clover_apply(o, i, cl, p, CLOVER_INVERSE_ADJ, twist_a(), nullptr, 1.0);
+      }
+      v_column_kernel<<<div_up(nt, 256), 256, 0, rt().compute>>>((float4 *)gfield.v, nullptr, lat->geom.Vh, 12, T.nvec, j, 1, (float4 *)VL);
+      QB_CHECK_LAUNCH();
+    }
+  }
+  build_coarse_from_fine(coarse, T, *gauge, lat->geom, kappa, flavor ? twist_a() : 0.0, cs, VL);
   if (cs) pool_free(cs);
-  if (preconditioned && flavor) {
+  if (VL) pool_free(VL);
+  if (preconditioned && flavor && !clover) {
     const std::complex<double> one(1.0, 0.0), ia(0.0, twist_a());
     scale_coarse_rows(coarse, one / (one + ia), one / (one - ia));
   }

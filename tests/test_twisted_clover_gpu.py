@@ -209,3 +209,87 @@ def test_invert_multi_src(quda, oracle):
         res = np.linalg.norm(b - oracle.tmc_mat(c.g, x, c.c, KAPPA, MU, 1, 0)) / np.linalg.norm(b)
         assert res < 5e-9
     assert p.iter > 0 and p.true_res < 5e-9
+
+
+@pytest.mark.parametrize("nvec", [4, 8])
+def test_tmc_multigrid_on_the_even_odd_system(quda, oracle, nvec):
+    """The reference's default solve type with twisted clover (DiracTwistedCloverPC::createCoarseOp, computeTMCAV lib/coarse_op.cuh:384-456):
+    coarse_grid_solution_type = MATPC coarsens A^-1 M with the site-dependent A = C + i a gamma5.  Dense check of the coarse operator against
+    P^dag A^-1 (tmc_mat) P with the oracle (A^-1 from the oracle's clover blocks in numpy), the library's own identity, and an
+    even-odd MG-GCR solve checked with the host operator."""
+    from tests.test_multigrid_gpu import as_c
+    q, L = quda, quda.lib()
+    X = (4, 4, 4, 8)
+    bs = (2, 2, 2, 2)
+    oracle.set_dims(X)
+    g = oracle.weak_gauge(eps=0.25, antiperiodic=False, seed=21)
+    cl = oracle.clover(norm=0.05, diag=1.0, seed=99)
+    kappa, mu = 0.122, 0.03
+    a = 2 * kappa * mu
+    gp = q.gauge_param(X, cuda_prec=8, reconstruct=18, cuda_prec_sloppy=4, cuda_prec_precondition=4, t_boundary=q.QUDA_PERIODIC_T)
+    L.loadGaugeQuda((C.c_void_p * 4)(*[x_.ctypes.data for x_ in g]), C.byref(gp))
+
+    def param():
+        p = q.invert_param(kappa=kappa, mu=mu, cuda_prec=8, dslash_type=q.QUDA_TWISTED_CLOVER_DSLASH, solution_type=q.QUDA_MAT_SOLUTION)
+        p.cuda_prec_sloppy = 4; p.cuda_prec_precondition = 4
+        p.clover_cpu_prec = 8
+        p.clover_cuda_prec = 8; p.clover_cuda_prec_sloppy = 4; p.clover_cuda_prec_precondition = 4
+        p.clover_order = q.QUDA_PACKED_CLOVER_ORDER
+        p.clover_coeff = 1.0
+        p.compute_clover = p.compute_clover_inverse = p.return_clover = p.return_clover_inverse = 0
+        p.solve_type = q.QUDA_DIRECT_SOLVE
+        p.inv_type = q.QUDA_GCR_INVERTER
+        p.gcrNkrylov = 20; p.tol = 1e-9; p.maxiter = 2000; p.reliable_delta = 1e-4
+        return p
+
+    ip = param()
+    L.loadCloverQuda(vp(cl), None, C.byref(ip))
+    mgp = q.multigrid_param(ip, n_level=2, geo_block=(bs,), n_vec=(nvec,), setup_maxiter=100, setup_tol=1e-4, solve_type=q.QUDA_DIRECT_PC_SOLVE)
+    mg = L.newMultigridQuda(C.byref(mgp))
+    dev = (C.c_double * 3)()
+    L.mgVerifyQudaB200(mg, 0, dev)
+    assert dev[0] < 5e-6 and dev[2] < 5e-5, list(dev)
+    info = (C.c_int * 8)()
+    L.mgLevelInfoQudaB200(mg, 0, info)
+    N = info[7]
+    Vf, Vc = int(np.prod(X)), int(np.prod(info[0:4]))
+    nf, nc = Vf * 12, Vc * N
+    P = np.zeros((nf, nc), dtype=np.complex128); Mc = np.zeros((nc, nc), dtype=np.complex128)
+    e = np.zeros(2 * nc, dtype=np.float32); out = np.zeros(2 * nf, dtype=np.float32); oc = np.zeros(2 * nc, dtype=np.float32)
+    for i in range(nc):
+        e[:] = 0; e[2 * i] = 1
+        L.mgProlongQudaB200(mg, 0, vp(out), vp(e)); P[:, i] = as_c(out.astype(np.float64))
+        L.mgMatQudaB200(mg, 1, 0, vp(oc), vp(e)); Mc[:, i] = as_c(oc.astype(np.float64))
+    # A^-1 site by site from the packed Hermitian blocks (two 6 x 6 blocks per site: chirality +, -)
+    blocks = oracle.clover_unpack(cl).reshape(Vf, 2, 6, 6)
+    Ainv = np.zeros_like(blocks)
+    for chi, sgn in ((0, 1.0), (1, -1.0)):
+        Ainv[:, chi] = np.linalg.inv(blocks[:, chi] + 1j * sgn * a * np.eye(6))
+
+    def apply_ainv(z):
+        v = z.reshape(Vf, 2, 6)
+        return np.einsum("xcij,xcj->xci", Ainv, v).reshape(-1)
+
+    def to_reals(z):
+        r = np.zeros(2 * z.size); r[0::2] = z.real; r[1::2] = z.imag
+        return r
+
+    AMP = np.stack([apply_ainv(as_c(oracle.tmc_mat(g, to_reals(P[:, i]), cl, kappa, mu, 1, 0))) for i in range(nc)], axis=1)
+    ref = P.conj().T @ AMP
+    err = np.abs(Mc - ref).max() / np.abs(ref).max()
+    print(f"twisted clover, preconditioned coarsening, n_vec {nvec}: |M_c - P^dag A^-1 M P| = {err:.2e}")
+    assert err < 1e-5
+    b = np.zeros(oracle.V * 24); b[0] = 1.0; b[2] = 1.0
+    x = np.zeros_like(b)
+    p = param()
+    p.solve_type = q.QUDA_DIRECT_PC_SOLVE
+    p.inv_type_precondition = q.QUDA_MG_INVERTER
+    p.preconditioner = mg
+    L.invertQuda(vp(x), vp(b), C.byref(p))
+    res = np.linalg.norm(b - oracle.tmc_mat(g, x, cl, kappa, mu, 1, 0)) / np.linalg.norm(b)
+    p0 = param(); p0.solve_type = q.QUDA_DIRECT_PC_SOLVE
+    x0 = np.zeros_like(b)
+    L.invertQuda(vp(x0), vp(b), C.byref(p0))
+    print(f"twisted-clover even-odd MG-GCR: {p.iter} iterations (plain even-odd GCR {p0.iter}), host residual {res:.2e}")
+    assert res < 5e-9 and p.iter < p0.iter
+    L.destroyMultigridQuda(mg)
