@@ -253,7 +253,7 @@ def run_c5(q, L, oracle, du, rank, world, grid, global_X=(64, 64, 64, 128)):
             prof[f"level{lvl}"] = {"cycles": nc.value, "pre_smooth_or_coarsest_solve": t6[0], "residual": t6[1], "restrict": t6[2],
                                    "coarse_solve_incl_lower_levels": t6[3], "prolong": t6[4], "post_smooth": t6[5]}
         multi = None
-        if not pc and os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
+        if os.environ.get("QB_BENCH_MULTI_SRC", "1") != "0":
             # the "multi-RHS coarse grid" of config 5: 12 spin-colour point sources through invertMultiSrcQuda; block path = lock-step
             # GCR, coarse levels on the multi-RHS tensor-core operator with ghost zones of block fields, against one source at a time
             nsrc = 12
