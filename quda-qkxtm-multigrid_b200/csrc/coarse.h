@@ -103,6 +103,7 @@ class DiracCoarse : public Dirac {
   void reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const override;
   void create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned = false) const override;
   void DiagInv(SpinorField &out, const SpinorField &in) const override;
+  void Diag(SpinorField &out, const SpinorField &in, int parity) const override { Clover(out, in, parity); }
   int p_parity() const { return (matpc_type == MATPC_EVEN_EVEN || matpc_type == MATPC_EVEN_EVEN_ASYM) ? 0 : 1; }
 };
 

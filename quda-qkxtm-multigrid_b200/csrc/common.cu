@@ -1,4 +1,5 @@
 // Runtime singleton, logging and the error path.
+#include <chrono>
 #include "common.h"
 #include <map>
 #include <unordered_map>
@@ -39,6 +40,10 @@ void log_msg(int level, const char *fmt, ...) {
 
 static std::multimap<size_t, void *> pool_cache;          // free blocks by size
 static std::unordered_map<void *, size_t> pool_live;       // blocks handed out
+static double pool_driver_seconds = 0.0;                   // wall time spent inside cudaMalloc / cudaFree on behalf of the pool
+static long pool_driver_calls = 0;
+static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+double pool_driver_time(long *calls) { if (calls) *calls = pool_driver_calls; return pool_driver_seconds; }
 
 void *pool_malloc(size_t bytes) {
   if (bytes == 0) bytes = 16;
@@ -48,7 +53,9 @@ void *pool_malloc(size_t bytes) {
     p = it->second;
     pool_cache.erase(it);
   } else {
+    const double t0 = wall_s();
     cudaError_t e = cudaMalloc(&p, bytes);
+    pool_driver_seconds += wall_s() - t0; pool_driver_calls++;
     if (e != cudaSuccess) {
       // out of memory: drop the cache and retry once
       cudaGetLastError();
@@ -79,7 +86,9 @@ size_t pool_cached_bytes() {
 }
 
 void pool_release_all() {
-  for (auto &kv : pool_cache) cudaFree(kv.second);
+  const double t0 = wall_s();
+  for (auto &kv : pool_cache) { cudaFree(kv.second); pool_driver_calls++; }
+  pool_driver_seconds += wall_s() - t0;
   pool_cache.clear();
 }
 

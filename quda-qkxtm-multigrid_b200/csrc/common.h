@@ -58,6 +58,7 @@ void *pool_malloc(size_t bytes);
 void pool_free(void *ptr);
 size_t pool_cached_bytes();  // bytes sitting in the cache (reusable without a driver call)
 void pool_release_all();   // return everything cached to the driver (freeGaugeQuda / endQuda)
+double pool_driver_time(long *calls);  // seconds (and calls) spent in cudaMalloc / cudaFree on behalf of the pool so far
 
 inline int div_up(long a, long b) { return (int)((a + b - 1) / b); }
 

@@ -23,6 +23,14 @@ void Dirac::MdagM(SpinorField &out, const SpinorField &in) const {
 
 void Dirac::create_coarse_op(CoarseOperator &, const Transfer &, bool) const { QB_ERROR("create_coarse_op not implemented for this operator"); }
 void Dirac::DiagInv(SpinorField &, const SpinorField &) const { QB_ERROR("DiagInv not implemented for this operator"); }
+void Dirac::Diag(SpinorField &, const SpinorField &, int) const { QB_ERROR("Diag not implemented for this operator"); }
+
+void DiracTM::Diag(SpinorField &out, const SpinorField &in, int parity) const {
+  if (flavor == 2) QB_ERROR("Diag: the non-degenerate doublet is not supported");
+  if (clover) { CloverTwist(out, in, parity, false); return; }
+  if (flavor == 0) { if (out.v != in.v) blas::copy(out, in); return; }
+  Twist(out, in);
+}
 
 // A^-1 on every site of the field (full or single parity); with a clover term (C + i a gamma5)^-1 parity by parity
 void DiracTM::DiagInv(SpinorField &out, const SpinorField &in) const {

@@ -47,6 +47,8 @@ class Dirac {
   virtual void create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned = false) const;
   // out = S^-1 in on every site of a full or parity field (S as above)
   virtual void DiagInv(SpinorField &out, const SpinorField &in) const;
+  // out = S in on the single-parity field `in` of parity `parity` (S = A on the fine grid, X on a coarse grid)
+  virtual void Diag(SpinorField &out, const SpinorField &in, int parity) const;
 };
 
 // Wilson and degenerate twisted-mass operator (lib/dirac_wilson.cpp, lib/dirac_twisted_mass.cpp)
@@ -98,6 +100,7 @@ class DiracTM : public Dirac {
   void reconstruct(SpinorField &x, const SpinorField &b, SolutionType sol_type) const override;
   void create_coarse_op(CoarseOperator &coarse, const Transfer &T, bool preconditioned = false) const override;
   void DiagInv(SpinorField &out, const SpinorField &in) const override;
+  void Diag(SpinorField &out, const SpinorField &in, int parity) const override;
 
  private:
   // non-degenerate doublet (wilson_dslash_reference.cpp:412-587; dirac_twisted_mass.cpp handles it through the same class)

@@ -1237,6 +1237,8 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   if ((int)ip->verbosity != INVALID_INT) r.verbosity = (int)ip->verbosity;
   const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 
+  long alloc_calls0 = 0;
+  const double alloc_t0 = pool_driver_time(&alloc_calls0);
   MultigridSolver *ms = new MultigridSolver();
   MGParam &mp = ms->mp;
   mp.n_level = mgp->n_level;
@@ -1299,7 +1301,12 @@ void *newMultigridQuda(QudaMultigridParam *mgp) {
   {
     size_t free_b = 0, total_b = 0;
     QB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if (pool_cached_bytes() > total_b / 8 || free_b < total_b / 4) pool_release_all();
+    if (free_b < total_b / 4) pool_release_all();
+  }
+  {
+    long calls = 0;
+    const double t = pool_driver_time(&calls);
+    log_msg(1, "newMultigridQuda: %.3f s of the setup inside cudaMalloc / cudaFree (%ld calls of the caching allocator)\n", t - alloc_t0, calls - alloc_calls0);
   }
   mgp->secs = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
   mgp->gflops = 0;

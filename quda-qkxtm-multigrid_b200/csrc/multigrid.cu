@@ -76,6 +76,9 @@ MG::MG(MGParam &mp_, int level_, const Dirac *matResidual_, const Dirac *matSmoo
   }
   DiracMatrix ms(matSmooth);
   presmoother.reset(Solver::create(param_presmooth, ms, ms, ms));
+  // the residual after pre-smoothing comes out of the smoother itself where that is possible (use_solver_residual, lib/multigrid.cpp:536-546)
+  if (!last && !(getenv("QB_MG_SOLVER_RESIDUAL") && atoi(getenv("QB_MG_SOLVER_RESIDUAL")) == 0))
+    if (MR *mr = dynamic_cast<MR *>(presmoother.get())) mr->keep_residual = true;
   if (!last) {
     param_postsmooth = param_presmooth;
     param_postsmooth.use_init_guess = true;
@@ -417,16 +420,21 @@ void MG::cycle_pc(SpinorField &x, SpinorField &b) {
   if (!pc_coarsen) QB_ERROR("Unsupported solution type combination: single-parity fields on MG level %d need coarse_grid_solution_type = QUDA_MATPC_SOLUTION", level + 1);
   SpinorField rp;
   r->view_parity(rp, pc_parity);
+  const SpinorField *rsrc = &rp;
   if (lp.nu_pre > 0) {
     { Section s(&t_prof[0]); (*presmoother)(x, b); }
     Section s(&t_prof[1]);
-    matSmooth->M(rp, x);
-    blas::axpby(1.0, b, -1.0, rp);
+    const MR *mr = dynamic_cast<const MR *>(presmoother.get());
+    if (mr && mr->residual()) rsrc = mr->residual();   // b - M_pc x left behind by the smoother's last step
+    else {
+      matSmooth->M(rp, x);
+      blas::axpby(1.0, b, -1.0, rp);
+    }
   } else {
     blas::zero(x);
     blas::copy(rp, b);
   }
-  { Section s(&t_prof[2]); transfer->R(*r_coarse, rp, pc_parity); }
+  { Section s(&t_prof[2]); transfer->R(*r_coarse, *rsrc, pc_parity); }
   {
     Section s(&t_prof[3]);
     if (coarse_solver_pc) (*coarse_solver_pc)(*x_coarse, *r_coarse);
@@ -461,17 +469,31 @@ void MG::cycle(SpinorField &x, SpinorField &b) {
     return;
   }
   // pre-smoothing (zero initial guess) and residual
+  int rpar = -1;   // >= 0: the residual lives on that parity only
   if (lp.nu_pre > 0) {
     { Section s(&t_prof[0]); smooth(*presmoother, x, b); }
     Section s(&t_prof[1]);
-    matResidual->M(*r, x);
-    blas::axpby(1.0, b, -1.0, *r);
+    const MR *mr = dynamic_cast<const MR *>(presmoother.get());
+    if (mr && mr->residual() && matSmooth->is_pc()) {
+      // x came out of the even-odd system with x_q reconstructed exactly, so b - M x vanishes on parity q and equals S (src - M_pc x_p) on
+      // parity p (S = the site-diagonal term; for the asymmetric fine operator no S): one site-local kernel on the smoother's own residual
+      // instead of a full operator application, and the restrictor reads one parity of V only
+      rpar = pc_parity;
+      SpinorField rp;
+      r->view_parity(rp, rpar);
+      const bool symmetric = matSmooth->matpc() == MATPC_EVEN_EVEN || matSmooth->matpc() == MATPC_ODD_ODD;
+      if (symmetric) matSmooth->Diag(rp, *mr->residual(), rpar);
+      else blas::copy(rp, *mr->residual());
+    } else {
+      matResidual->M(*r, x);
+      blas::axpby(1.0, b, -1.0, *r);
+    }
   } else {
     blas::zero(x);
     blas::copy(*r, b);
   }
   // coarse-grid correction
-  { Section s(&t_prof[2]); transfer->R(*r_coarse, *r); }
+  { Section s(&t_prof[2]); transfer->R(*r_coarse, *r, rpar); }
   {
     Section s(&t_prof[3]);
     if (coarse_solver_pc) (*coarse_solver_pc)(*x_coarse, *r_coarse);

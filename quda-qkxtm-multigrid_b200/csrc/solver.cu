@@ -130,13 +130,14 @@ void MR::operator()(SpinorField &x, SpinorField &b) {
       rc = r.get();
     }
     int k = 0;
+    residual_valid = false;
     while (k < param.maxiter) {
       matSloppy(*Ar, *rc);
       const blas::double3_ d = blas::cDotProductNormA(*Ar, *rc);
       if (d.z == 0.0) break;
       const Complex alpha = param.omega * Complex(d.x, d.y) / d.z;
       const bool last = k == param.maxiter - 1;
-      if (last) {
+      if (last && !keep_residual) {
         if (x_valid) blas::caxpy(alpha, *rc, x);
         else blas::cax(alpha, *rc, x);
       } else if (rc == &b) {
@@ -147,6 +148,7 @@ void MR::operator()(SpinorField &x, SpinorField &b) {
       }
       x_valid = true;
       k++;
+      if (last && keep_residual) residual_valid = true;
     }
     if (!x_valid) blas::zero(x);
     param.iter += k;

@@ -54,6 +54,13 @@ class MR : public Solver {
  public:
   MR(const DiracMatrix &mat_, const DiracMatrix &matSloppy_, SolverParam &p) : Solver(p), mat(mat_), matSloppy(matSloppy_) {}
   void operator()(SpinorField &x, SpinorField &b) override;
+  // Smoother use (the multigrid's use_solver_residual, lib/multigrid.cpp:536-546): with keep_residual set the fixed-iteration fast path
+  // also carries out the residual update of its last step (one BLAS pass instead of the operator application the caller would need to
+  // recompute b - A x) and residual() returns b - A x of the solution just produced; nullptr when the path taken did not keep it.
+  bool keep_residual = false;
+  const SpinorField *residual() const { return residual_valid ? r.get() : nullptr; }
+ private:
+  bool residual_valid = false;
 };
 
 class GCR : public Solver {
