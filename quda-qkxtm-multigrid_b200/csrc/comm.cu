@@ -94,17 +94,12 @@ static void *peer_local = nullptr;           // my mailbox: boxes then flags
 static void *peer_mapped[PEER_MAX_RANKS];    // IPC mappings of the peers' mailboxes
 static size_t peer_box_bytes(int size) { return sizeof(double) * 2 * size * PEER_MAX_RED; }
 
-static void peer_reduce_setup() {
+bool comm_ipc_map(void *local, void **mapped) {
   Runtime &r = rt();
-  peer_ready = false;
-  const char *env = getenv("QB_PEER_REDUCE");
-  if (env && atoi(env) == 0) return;
-  if (r.size > PEER_MAX_RANKS) return;
-  const size_t bytes = peer_box_bytes(r.size) + sizeof(unsigned long long) * 2 * r.size;
-  QB_CUDA(cudaMalloc(&peer_local, bytes));
-  QB_CUDA(cudaMemset(peer_local, 0, bytes));
+  for (int p = 0; p < r.size; p++) mapped[p] = nullptr;
+  if (r.size == 1) { mapped[0] = local; return true; }
   cudaIpcMemHandle_t mine;
-  bool ok = cudaIpcGetMemHandle(&mine, peer_local) == cudaSuccess;
+  bool ok = cudaIpcGetMemHandle(&mine, local) == cudaSuccess;
   // exchange the handles (and whether every rank got one) through NCCL
   struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
   Msg m{}; m.h = mine; m.ok = ok ? 1 : 0;
@@ -120,8 +115,8 @@ static void peer_reduce_setup() {
   int mapped_ok = ok ? 1 : 0;
   if (ok) {
     for (int p = 0; p < r.size; p++) {
-      if (p == r.rank) { peer_mapped[p] = peer_local; continue; }
-      if (cudaIpcOpenMemHandle(&peer_mapped[p], all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mapped_ok = 0; peer_mapped[p] = nullptr; }
+      if (p == r.rank) { mapped[p] = local; continue; }
+      if (cudaIpcOpenMemHandle(&mapped[p], all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mapped_ok = 0; mapped[p] = nullptr; }
     }
   }
   cudaGetLastError();
@@ -129,6 +124,31 @@ static void peer_reduce_setup() {
   double v = mapped_ok ? 0.0 : 1.0;
   comm_allreduce_sum(&v, 1);
   if (v != 0.0) {
+    for (int p = 0; p < r.size; p++)
+      if (p != r.rank && mapped[p]) { cudaIpcCloseMemHandle(mapped[p]); mapped[p] = nullptr; }
+    return false;
+  }
+  return true;
+}
+
+void comm_ipc_unmap(void **mapped) {
+  Runtime &r = rt();
+  for (int p = 0; p < r.size; p++) {
+    if (p != r.rank && mapped[p]) cudaIpcCloseMemHandle(mapped[p]);
+    mapped[p] = nullptr;
+  }
+}
+
+static void peer_reduce_setup() {
+  Runtime &r = rt();
+  peer_ready = false;
+  const char *env = getenv("QB_PEER_REDUCE");
+  if (env && atoi(env) == 0) return;
+  if (r.size > PEER_MAX_RANKS) return;
+  const size_t bytes = peer_box_bytes(r.size) + sizeof(unsigned long long) * 2 * r.size;
+  QB_CUDA(cudaMalloc(&peer_local, bytes));
+  QB_CUDA(cudaMemset(peer_local, 0, bytes));
+  if (!comm_ipc_map(peer_local, peer_mapped)) {
     log_msg(1, "peer mailboxes for the fused all-reduce could not be mapped on every rank: reductions use ncclAllReduce\n");
     return;
   }
@@ -296,8 +316,7 @@ void comm_barrier() {
 void comm_finalize() {
   if (peer_local) {
     cudaDeviceSynchronize();
-    for (int p = 0; p < rt().size && p < PEER_MAX_RANKS; p++)
-      if (p != rt().rank && peer_mapped[p]) cudaIpcCloseMemHandle(peer_mapped[p]);
+    if (rt().size <= PEER_MAX_RANKS) comm_ipc_unmap(peer_mapped);
     cudaFree(peer_local);
     peer_local = nullptr; peer_ready = false;
   }

@@ -49,6 +49,12 @@ PeerReduce comm_peer_reduce_next();
 // fallback: in-place sum of n doubles in device memory, enqueued on stream s
 void comm_allreduce_sum_device(double *d_data, int n, cudaStream_t s);
 
+// Maps one device allocation of EVERY rank into this process (CUDA IPC over NVLink / NVSwitch).  Collective: all ranks call it with their
+// own allocation.  mapped[r] (r < size) = pointer valid on this device for rank r's allocation (own rank: `local` itself).  Returns false,
+// on all ranks alike, if any rank could not export or open a handle (then nothing stays mapped).
+bool comm_ipc_map(void *local, void **mapped);
+void comm_ipc_unmap(void **mapped);
+
 // sum / max all-reduce of n doubles held on the host (blocking; used by reductions in solvers)
 void comm_allreduce_sum(double *data, int n);
 void comm_allreduce_max(double *data, int n);

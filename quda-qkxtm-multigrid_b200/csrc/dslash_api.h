@@ -36,6 +36,15 @@ struct Lattice {
   size_t arena_bytes[3] = {0, 0, 0};
   size_t face_off[3][4][2];   // byte offset of the (d, dir) half-spinor block inside an arena
   size_t norm_off[3][4][2];   // byte offset of the norm block (half precision only)
+  // Direct halo delivery (several ranks, receive arenas mapped into each other with CUDA IPC): the pack kernel stores the projected
+  // faces straight into the NEIGHBOUR's ghost zone over NVLink, a one-warp kernel raises a sequence flag there, and the receiver's
+  // boundary launch is preceded by a one-warp kernel that waits for the flags of its two neighbours -- no NCCL kernel, no copy of the
+  // faces.  The receive arena is double buffered by sequence parity (a neighbour can be one hop ahead, never two: it needs my flag of
+  // hop n + 1, raised after my boundary launch of hop n, before it may overwrite the buffer of hop n with hop n + 2).
+  bool peer_halo[3] = {false, false, false};
+  void *peer_recv[3][16];                    // receive arena of every rank as seen from this device
+  unsigned long long *halo_flags[3] = {nullptr, nullptr, nullptr};   // my [4][2] arrival flags (inside my receive arena, behind the two buffers)
+  unsigned long long halo_seq[3] = {0, 0, 0};
   int block_size = 0;         // 0: per-precision default
 
   void init(const int *X, int t_boundary_sign, double anisotropy);

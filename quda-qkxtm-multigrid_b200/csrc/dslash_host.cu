@@ -59,9 +59,18 @@ void Lattice::release() {
     n_interior[p] = n_boundary[p] = 0;
   }
   for (int i = 0; i < 3; i++) {
+    if (peer_halo[i]) {
+      // nobody may still be storing into (or reading flags from) an arena that is about to go away
+      cudaDeviceSynchronize();
+      comm_barrier();
+      comm_ipc_unmap(peer_recv[i]);
+      comm_barrier();
+      peer_halo[i] = false;
+    }
     if (send_arena[i]) comm_free_halo(send_arena[i]);
     if (recv_arena[i]) comm_free_halo(recv_arena[i]);
     send_arena[i] = recv_arena[i] = nullptr;
+    halo_flags[i] = nullptr;
     arena_bytes[i] = 0;
   }
 }
@@ -121,7 +130,33 @@ static void ensure_arena(Lattice &lat, Prec prec) {
     }
   lat.arena_bytes[pi] = off;
   lat.send_arena[pi] = comm_alloc_halo(off);
-  lat.recv_arena[pi] = comm_alloc_halo(off);
+  // receive side: two buffers (sequence parity) + the arrival flags; mapped into the neighbours when there are real ranks
+  const size_t recv_total = 2 * off + 256;
+  lat.recv_arena[pi] = comm_alloc_halo(recv_total);
+  QB_CUDA(cudaMemset(lat.recv_arena[pi], 0, recv_total));
+  lat.halo_flags[pi] = (unsigned long long *)((char *)lat.recv_arena[pi] + 2 * off);
+  lat.halo_seq[pi] = 0;
+  lat.peer_halo[pi] = false;
+  const char *env = getenv("QB_PEER_HALO");
+  if (rt().size > 1 && rt().size <= 16 && !(env && atoi(env) == 0)) {
+    lat.peer_halo[pi] = comm_ipc_map(lat.recv_arena[pi], lat.peer_recv[pi]);
+    if (!lat.peer_halo[pi]) log_msg(1, "halo exchange: receive arenas could not be mapped between the ranks, faces travel through NCCL send / recv\n");
+  }
+}
+
+// arrival flags of the direct halo delivery
+struct HaloFlags { unsigned long long *p[8]; unsigned long long seq; int n; };
+__global__ void halo_signal_kernel(const HaloFlags f) {
+  if ((int)threadIdx.x < f.n) {
+    __threadfence_system();   // the faces were stored by the pack kernel before this one in stream order
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[threadIdx.x]), "l"(f.seq) : "memory");
+  }
+}
+__global__ void halo_wait_kernel(const HaloFlags f) {
+  if ((int)threadIdx.x < f.n) {
+    unsigned long long v;
+    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.p[threadIdx.x]) : "memory"); } while (v < f.seq);
+  }
 }
 
 template <typename Store>
@@ -208,6 +243,13 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   ensure_arena(lat, Store::prec);
   char *send = (char *)lat.send_arena[pi], *recv = (char *)lat.recv_arena[pi];
   const bool self = comm_self_exchange();
+  const bool peer = lat.peer_halo[pi];
+  const int mask = g_phase_mask;
+  if (peer && (mask & PH_EXCHANGE)) lat.halo_seq[pi]++;   // identical on all ranks: hops are collective
+  const unsigned long long seq = lat.halo_seq[pi];
+  const size_t buf = peer ? (size_t)(seq & 1) * lat.arena_bytes[pi] : 0;
+  HaloFlags sig{}, wt{};
+  sig.seq = wt.seq = seq;
   // self-exchange (single rank, forced partitioning): our back face *is* our forward ghost -> alias, no copy
   PackParam pk;
   memset(&pk, 0, sizeof(pk));
@@ -229,8 +271,17 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
       p.ghost[d][dir] = src + lat.face_off[pi][d][1 - dir];
       p.ghost_norm[d][dir] = (const float *)(src + lat.norm_off[pi][d][1 - dir]);
       if (!self) {  // received blocks are laid out by *receiving* slot: recv[d][0] <- from back, recv[d][1] <- from fwd
-        p.ghost[d][dir] = recv + lat.face_off[pi][d][dir];
-        p.ghost_norm[d][dir] = (const float *)(recv + lat.norm_off[pi][d][dir]);
+        p.ghost[d][dir] = recv + buf + lat.face_off[pi][d][dir];
+        p.ghost_norm[d][dir] = (const float *)(recv + buf + lat.norm_off[pi][d][dir]);
+      }
+      if (peer && g.part[d]) {
+        // my face `dir` (0: slice x_d = 0, travels backward; 1: slice X_d - 1, travels forward) goes straight into the neighbour's
+        // receive slot (d, 1 - dir) of this hop's buffer; its arrival flag (d, 1 - dir) sits behind the neighbour's two buffers
+        char *nb = (char *)lat.peer_recv[pi][comm_neighbor_rank(d, dir)];
+        pk.send[d][dir] = nb + buf + lat.face_off[pi][d][1 - dir];
+        pk.send_norm[d][dir] = (float *)(nb + buf + lat.norm_off[pi][d][1 - dir]);
+        sig.p[sig.n++] = (unsigned long long *)(nb + 2 * lat.arena_bytes[pi]) + (d * 2 + (1 - dir));
+        wt.p[wt.n++] = lat.halo_flags[pi] + (d * 2 + dir);
       }
     }
     p.gauge_ghost[d] = gauge.ghost[d] ? (const char *)gauge.ghost[d] + (size_t)(1 - parity) * gauge.recon * gauge.store_bytes() * g.faceVh[d] : nullptr;
@@ -242,12 +293,15 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   // compute the boundary sites right there -- they are few (2 faces of X*Y*Z/2 sites for a T split), so
   // the launch is latency-bound and hides completely under the interior kernel running on the compute stream.
   // Interior and boundary launches write disjoint sites of `out`.
-  const int mask = g_phase_mask;
   if (mask & PH_EXCHANGE) {
     QB_CUDA(cudaEventRecord(r.ev_in_ready, r.compute));
     QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_in_ready, 0));
     launch_pack_T<Store>(pk, twist_in, r.halo);
-    if (!self) comm_exchange_halo(lat, pi, r.halo);
+    if (peer) {
+      halo_signal_kernel<<<1, 32, 0, r.halo>>>(sig);
+      QB_CHECK_LAUNCH();
+      if (mask & PH_SYNC) { halo_wait_kernel<<<1, 32, 0, r.halo>>>(wt); QB_CHECK_LAUNCH(); }   // timing hook: until the neighbours' faces are here
+    } else if (!self) comm_exchange_halo(lat, pi, r.halo);
     if (!(mask & PH_BOUNDARY)) {
       QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
       if (mask & PH_SYNC) QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
@@ -261,6 +315,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     // the exchange started earlier has finished
     cudaStream_t bs = (mask & PH_EXCHANGE) ? r.halo : r.compute;
     if (!(mask & PH_EXCHANGE)) QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
+    if (peer) { halo_wait_kernel<<<1, 32, 0, bs>>>(wt); QB_CHECK_LAUNCH(); }   // the neighbours' faces of this hop have landed
     if (lat.n_boundary[np]) {
       pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
       launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, bs);

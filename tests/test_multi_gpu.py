@@ -138,13 +138,16 @@ def test_face_index_map_bit_exact(quda, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks,grid,local", [(2, "1,1,1,2", "8,4,6,8"), (2, "1,1,2,1", "4,4,4,8"), (4, "1,1,2,2", "4,4,4,4"),
-                                               (2, "1,1,1,2", "16,16,16,32")])   # the last one is large enough for the slab-pipelined host path
-def test_nccl_halo_exchange_vs_global_oracle(nranks, grid, local):
+@pytest.mark.parametrize("nranks,grid,local,peer", [(2, "1,1,1,2", "8,4,6,8", 1), (2, "1,1,2,1", "4,4,4,8", 1), (4, "1,1,2,2", "4,4,4,4", 1),
+                                                    (2, "1,1,1,2", "16,16,16,32", 1),   # large enough for the slab-pipelined host path
+                                                    (2, "1,1,1,2", "8,4,6,8", 0), (2, "1,1,2,1", "16,16,16,32", 0), (4, "1,1,2,2", "4,4,4,4", 0)])
+def test_nccl_halo_exchange_vs_global_oracle(nranks, grid, local, peer):
+    """peer = 1: faces stored by the pack kernel straight into the neighbour's ghost zone (CUDA IPC over NVLink, arrival flags);
+    peer = 0: NCCL send / recv groups"""
     import torch
     if torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    env = dict(os.environ, QB_GRID=grid, QB_LOCAL=local)
+    env = dict(os.environ, QB_GRID=grid, QB_LOCAL=local, QB_PEER_HALO=str(peer))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_dslash.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
