@@ -14,14 +14,22 @@ void CoarseOperator::allocate(const LevelGeom &g, int nvec_) {
   if (Y) pool_free(Y);
   Y = (float *)pool_malloc(link_bytes());   // GB-sized link arrays go through the caching allocator
   QB_CUDA(cudaMemsetAsync(Y, 0, link_bytes(), rt().compute));
+  size_t off = 0;
   for (int d = 0; d < 4; d++) {
     if (!geom.part[d]) continue;
     const size_t bytes = (size_t)2 * (N / 2) * geom.faceVh[d] * sizeof(float4);
     for (int k = 0; k < 2; k++) {
       QB_CUDA(cudaMalloc((void **)&send[d][k], bytes));
       if (comm_self_exchange()) recv[d][1 - k] = send[d][k];  // my back face is my own forward ghost and vice versa
-      else QB_CUDA(cudaMalloc((void **)&recv[d][k], bytes));
+      recv_off[d][k] = off;
+      off += (bytes + 255) & ~(size_t)255;
     }
+  }
+  if (off && !comm_self_exchange()) {
+    ghost_arena.create(off);   // collective: every rank builds its coarse operators in the same order
+    for (int d = 0; d < 4; d++)
+      for (int k = 0; k < 2; k++)
+        if (geom.part[d]) recv[d][k] = (float *)(ghost_arena.local + recv_off[d][k]);
   }
 }
 
@@ -36,12 +44,11 @@ CoarseOperator::~CoarseOperator() {
   if (Xinv_mma) pool_free(Xinv_mma);
   if (nbr) cudaFree(nbr);
   if (mrhs_send) cudaFree(mrhs_send);
-  if (mrhs_recv) cudaFree(mrhs_recv);
+  mrhs_arena.destroy();
+  ghost_arena.destroy();
   for (int d = 0; d < 4; d++)
-    for (int k = 0; k < 2; k++) {
-      if (recv[d][k] && !comm_self_exchange()) cudaFree(recv[d][k]);
+    for (int k = 0; k < 2; k++)
       if (send[d][k]) cudaFree(send[d][k]);
-    }
 }
 
 // ---- coarse halo: plain copies of the boundary slices (no spin projection on coarse levels,
@@ -88,6 +95,10 @@ __global__ void coarse_pack_kernel(const CoarsePackArgs a) {
 void CoarseOperator::exchange_ghost(const float *field, const long *poff, int parity_mask) const {
   if (!geom.partitioned()) return;
   Runtime &r = rt();
+  const bool peer = ghost_arena.peer;
+  if (peer) ghost_arena.seq++;
+  HaloFlags sig{}, wt{};
+  sig.seq = wt.seq = ghost_arena.seq;
   CoarsePackArgs a;
   a.field = (const float4 *)field;
   a.poff[0] = poff[0]; a.poff[1] = poff[1];
@@ -96,6 +107,14 @@ void CoarseOperator::exchange_ghost(const float *field, const long *poff, int pa
   for (int d = 0; d < 4; d++) {
     a.X[d] = geom.X[d]; a.faceVh[d] = geom.faceVh[d]; a.part[d] = geom.part[d];
     a.send[d][0] = (float4 *)send[d][0]; a.send[d][1] = (float4 *)send[d][1];
+    if (peer && geom.part[d])
+      for (int dir = 0; dir < 2; dir++) {
+        // my face `dir` (0: slice 0, travels backward) lands in the receive block (d, 1 - dir) of that neighbour's current buffer
+        const int nb = comm_neighbor_rank(d, dir);
+        a.send[d][dir] = (float4 *)(ghost_arena.send_base(nb) + recv_off[d][1 - dir]);
+        sig.p[sig.n++] = ghost_arena.flag_of(nb, d * 2 + (1 - dir));
+        wt.p[wt.n++] = ghost_arena.flag_mine(d * 2 + dir);
+      }
     a.off[d] = off;
     if (geom.part[d]) off += 2L * 2 * a.nplanes * geom.faceVh[d];
   }
@@ -103,6 +122,11 @@ void CoarseOperator::exchange_ghost(const float *field, const long *poff, int pa
   coarse_pack_kernel<<<div_up(off, 256), 256, 0, r.compute>>>(a);
   QB_CHECK_LAUNCH();
   if (comm_self_exchange()) return;
+  if (peer) {
+    comm_halo_signal(sig, r.compute);
+    comm_halo_wait(wt, r.compute);
+    return;
+  }
   // all faces of all partitioned dimensions in one NCCL group (one launch; the reference posts them all before waiting too,
   // lib/dslash_coarse.cu:707).  my back face -> backward neighbour's "from forward" ghost; my forward face -> forward neighbour's
   // "from backward" ghost
@@ -293,12 +317,15 @@ void coarse_apply(const CoarseApplyArgs &a) {
   k.parity = a.parity; k.use_y = a.use_y; k.use_x = a.use_x; k.use_xinv = a.use_xinv; k.a = a.a; k.b = a.b;
   for (int d = 0; d < 4; d++) {
     k.part[d] = op.geom.part[d]; k.faceVh[d] = op.geom.faceVh[d];
-    k.ghost[d][0] = (const float4 *)op.recv[d][0]; k.ghost[d][1] = (const float4 *)op.recv[d][1];
   }
   if (a.use_y && op.geom.partitioned()) {
     // halo of the hop input: the parities the output sites read from (both for a full-lattice apply)
     op.exchange_ghost(a.in_hop, a.hop_poff, a.parity < 0 ? 3 : (1 << (1 - a.parity)));
   }
+  // (after the exchange: with direct peer delivery the receive buffer alternates with the exchange sequence number)
+  const size_t gbuf = op.ghost_arena.buf();
+  for (int d = 0; d < 4; d++)
+    for (int kdir = 0; kdir < 2; kdir++) k.ghost[d][kdir] = op.recv[d][kdir] ? (const float4 *)((const char *)op.recv[d][kdir] + gbuf) : nullptr;
   if (a.use_xinv && !op.Xinv) QB_ERROR("coarse_apply: Xinv has not been computed");
   const long nsites = a.parity < 0 ? op.geom.V() : op.geom.Vh;
   switch (op.N) {

@@ -11,6 +11,7 @@
 //     M_c = R M P   holds exactly (up to rounding) -- checked by tests (the identity of MG::verify,
 // lib/multigrid.cpp:372-486).  The -kappa of the reference's  X - kappa * sum Y  is folded into the links.
 #pragma once
+#include "comm.h"
 #include <complex>
 #include <memory>
 #include "dirac.h"
@@ -39,6 +40,10 @@ struct CoarseOperator {
   // recv[d][0] = from the backward neighbour, recv[d][1] = from the forward neighbour (alias of send in self-exchange mode)
   float *send[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   float *recv[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  // with real ranks the receive blocks live in one arena that the neighbours' pack kernels store into directly over NVLink
+  // (PeerArena, comm.h); recv_off[d][k] = byte offset of block (d, k) inside one buffer of it.  NCCL send / recv when it is not mapped.
+  mutable PeerArena ghost_arena;
+  size_t recv_off[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   size_t link_bytes() const { return (size_t)geom.V() * 9 * N * N * 8; }
   void allocate(const LevelGeom &g, int nvec_);
   // pack the boundary slices of the parities in `parity_mask` of a coarse field and exchange them with the neighbours
@@ -57,8 +62,9 @@ struct CoarseOperator {
   // lib/dslash_coarse.cu:707)
   long mrhs_goff[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   long mrhs_ghost_sites = 0;
-  mutable float *mrhs_send = nullptr, *mrhs_recv = nullptr;
+  mutable float *mrhs_send = nullptr, *mrhs_recv = nullptr;   // mrhs_recv: current buffer of mrhs_arena
   mutable size_t mrhs_arena_bytes = 0;
+  mutable PeerArena mrhs_arena;
   void exchange_block_ghost(const float *field, const long *poff, int parity_mask, int R) const;
   ~CoarseOperator();
 };

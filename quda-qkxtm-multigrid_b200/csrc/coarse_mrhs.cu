@@ -116,11 +116,10 @@ void CoarseOperator::prepare_mrhs() {
 
 // ---- ghost zone of block fields ------------------------------------------------------------------------------------------------
 struct BlockPackArgs {
-  float4 *send;
+  float4 *dst[4][2];   // where face (d, dir) goes: a block of the send arena, or of the neighbour's ghost zone itself (peer delivery)
   const float4 *field;
   long poff[2];
   int X[4], faceVh[4], part[4];
-  long goff[4][2];
   long off[5];   // prefix sums of the float4 counts per partitioned dimension
   int nelem, parity_mask;
 };
@@ -150,7 +149,7 @@ __global__ void block_ghost_pack_kernel(const BlockPackArgs a) {
   const int parity = (int)(r & 1), dir = (int)(r >> 1);
   if (!((a.parity_mask >> parity) & 1)) return;
   const long cb = block_face_to_cb(d, fidx, dir ? a.X[d] - 1 : 0, parity, a.X);
-  a.send[(size_t)(a.goff[d][dir] + (long)parity * fv + fidx) * a.nelem + e] = a.field[a.poff[parity] + (size_t)cb * a.nelem + e];
+  a.dst[d][dir][(size_t)((long)parity * fv + fidx) * a.nelem + e] = a.field[a.poff[parity] + (size_t)cb * a.nelem + e];
 }
 
 void CoarseOperator::exchange_block_ghost(const float *field, const long *poff, int parity_mask, int R) const {
@@ -159,26 +158,47 @@ void CoarseOperator::exchange_block_ghost(const float *field, const long *poff, 
   const int nelem = (N / 2) * R;
   const size_t need = (size_t)mrhs_ghost_sites * nelem * sizeof(float4);
   if (need > mrhs_arena_bytes) {
+    // (collective: `need` depends on the operator and R only, alike on all ranks)
     QB_CUDA(cudaStreamSynchronize(r.compute));
-    if (mrhs_send) { cudaFree(mrhs_send); cudaFree(mrhs_recv); }
+    if (mrhs_send) cudaFree(mrhs_send);
     QB_CUDA(cudaMalloc((void **)&mrhs_send, need));
-    QB_CUDA(cudaMalloc((void **)&mrhs_recv, need));
+    mrhs_arena.create(need);
     mrhs_arena_bytes = need;
   }
+  const bool peer = mrhs_arena.peer;
+  if (peer) mrhs_arena.seq++;
+  mrhs_recv = (float *)mrhs_arena.recv_base();
+  HaloFlags sig{}, wt{};
+  sig.seq = wt.seq = mrhs_arena.seq;
+  const size_t site_bytes = (size_t)nelem * sizeof(float4);
   BlockPackArgs a;
-  a.send = (float4 *)mrhs_send; a.field = (const float4 *)field;
+  a.field = (const float4 *)field;
   a.poff[0] = poff[0]; a.poff[1] = poff[1];
   a.nelem = nelem; a.parity_mask = parity_mask;
   long off = 0;
   for (int d = 0; d < 4; d++) {
     a.X[d] = geom.X[d]; a.faceVh[d] = geom.faceVh[d]; a.part[d] = geom.part[d];
-    a.goff[d][0] = mrhs_goff[d][0]; a.goff[d][1] = mrhs_goff[d][1];
+    for (int dir = 0; dir < 2; dir++) {
+      a.dst[d][dir] = (float4 *)((char *)mrhs_send + (size_t)mrhs_goff[d][dir] * site_bytes);
+      if (peer && geom.part[d]) {
+        // my slice 0 (dir 0) -> the backward neighbour's "from forward" block [d][1]; my last slice -> the forward neighbour's [d][0]
+        const int nb = comm_neighbor_rank(d, dir);
+        a.dst[d][dir] = (float4 *)(mrhs_arena.send_base(nb) + (size_t)mrhs_goff[d][1 - dir] * site_bytes);
+        sig.p[sig.n++] = mrhs_arena.flag_of(nb, d * 2 + (1 - dir));
+        wt.p[wt.n++] = mrhs_arena.flag_mine(d * 2 + dir);
+      }
+    }
     a.off[d] = off;
     if (geom.part[d]) off += 4L * geom.faceVh[d] * nelem;
   }
   a.off[4] = off;
   block_ghost_pack_kernel<<<div_up(off, 256), 256, 0, r.compute>>>(a);
   QB_CHECK_LAUNCH();
+  if (peer) {
+    comm_halo_signal(sig, r.compute);
+    comm_halo_wait(wt, r.compute);
+    return;
+  }
   const void *sb[8]; void *rb[8]; int to[8], from[8]; size_t nb[8];
   int n = 0;
   for (int d = 0; d < 4; d++) {

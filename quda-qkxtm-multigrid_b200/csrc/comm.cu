@@ -139,6 +139,55 @@ void comm_ipc_unmap(void **mapped) {
   }
 }
 
+// ---- direct halo delivery (comm.h) -------------------------------------------------------------------------------------------------
+bool comm_peer_halo_wanted() {
+  const char *env = getenv("QB_PEER_HALO");
+  return rt().size > 1 && rt().size <= PEER_MAX_RANKS && !(env && atoi(env) == 0);
+}
+
+__global__ void halo_signal_kernel(const HaloFlags f) {
+  if ((int)threadIdx.x < f.n) {
+    __threadfence_system();   // the faces were stored by the pack kernel before this one in stream order
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[threadIdx.x]), "l"(f.seq) : "memory");
+  }
+}
+__global__ void halo_wait_kernel(const HaloFlags f) {
+  if ((int)threadIdx.x < f.n) {
+    unsigned long long v;
+    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.p[threadIdx.x]) : "memory"); } while (v < f.seq);
+  }
+}
+void comm_halo_signal(const HaloFlags &f, cudaStream_t s) {
+  halo_signal_kernel<<<1, 32, 0, s>>>(f);
+  QB_CHECK_LAUNCH();
+}
+void comm_halo_wait(const HaloFlags &f, cudaStream_t s) {
+  halo_wait_kernel<<<1, 32, 0, s>>>(f);
+  QB_CHECK_LAUNCH();
+}
+
+void PeerArena::create(size_t buffer_bytes) {
+  destroy();
+  bytes = (buffer_bytes + 255) & ~(size_t)255;
+  const size_t total = 2 * bytes + 256;
+  QB_CUDA(cudaMalloc((void **)&local, total));
+  QB_CUDA(cudaMemset(local, 0, total));
+  seq = 0;
+  peer = comm_peer_halo_wanted() && comm_ipc_map(local, mapped);
+}
+void PeerArena::destroy() {
+  if (!local) return;
+  if (peer) {
+    // nobody may still be storing into (or have mapped) an arena that goes away
+    cudaDeviceSynchronize();
+    comm_barrier();
+    comm_ipc_unmap(mapped);
+    comm_barrier();
+  }
+  cudaFree(local);
+  local = nullptr; bytes = 0; peer = false; seq = 0;
+}
+
 static void peer_reduce_setup() {
   Runtime &r = rt();
   peer_ready = false;

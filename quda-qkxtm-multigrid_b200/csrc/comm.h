@@ -55,6 +55,30 @@ void comm_allreduce_sum_device(double *d_data, int n, cudaStream_t s);
 bool comm_ipc_map(void *local, void **mapped);
 void comm_ipc_unmap(void **mapped);
 
+// Ghost-zone arena the neighbours store their faces into directly (coarse-level halos; the fine Dslash keeps the same scheme in
+// Lattice, dslash_host.cu).  Two buffers selected by the parity of the exchange sequence number (a rank may start packing exchange s + 1
+// while a neighbour still reads exchange s) followed by 8 arrival flags, slot = dim * 2 + dir.  create / destroy are collective.
+struct PeerArena {
+  char *local = nullptr;
+  size_t bytes = 0;                    // one buffer
+  void *mapped[PEER_MAX_RANKS] = {};
+  bool peer = false;                   // neighbours' arenas mapped here (else: plain local receive buffer for NCCL send / recv)
+  unsigned long long seq = 0;          // exchanges so far (identical on all ranks: exchanges are collective)
+  void create(size_t buffer_bytes);
+  void destroy();
+  size_t buf() const { return peer ? (size_t)(seq & 1) * bytes : 0; }
+  char *recv_base() const { return local + buf(); }
+  char *send_base(int rank) const { return (char *)mapped[rank] + buf(); }
+  unsigned long long *flag_mine(int slot) const { return (unsigned long long *)(local + 2 * bytes) + slot; }
+  unsigned long long *flag_of(int rank, int slot) const { return (unsigned long long *)((char *)mapped[rank] + 2 * bytes) + slot; }
+};
+// arrival flags: signal = release-store seq into up to 8 remote flags (after the stores of the pack kernel before it in stream order);
+// wait = spin until up to 8 local flags have reached seq
+struct HaloFlags { unsigned long long *p[8]; unsigned long long seq; int n; };
+void comm_halo_signal(const HaloFlags &f, cudaStream_t s);
+void comm_halo_wait(const HaloFlags &f, cudaStream_t s);
+bool comm_peer_halo_wanted();          // more than one rank, <= PEER_MAX_RANKS, not switched off (QB_PEER_HALO=0)
+
 // sum / max all-reduce of n doubles held on the host (blocking; used by reductions in solvers)
 void comm_allreduce_sum(double *data, int n);
 void comm_allreduce_max(double *data, int n);

@@ -137,25 +137,9 @@ static void ensure_arena(Lattice &lat, Prec prec) {
   lat.halo_flags[pi] = (unsigned long long *)((char *)lat.recv_arena[pi] + 2 * off);
   lat.halo_seq[pi] = 0;
   lat.peer_halo[pi] = false;
-  const char *env = getenv("QB_PEER_HALO");
-  if (rt().size > 1 && rt().size <= 16 && !(env && atoi(env) == 0)) {
+  if (comm_peer_halo_wanted()) {
     lat.peer_halo[pi] = comm_ipc_map(lat.recv_arena[pi], lat.peer_recv[pi]);
     if (!lat.peer_halo[pi]) log_msg(1, "halo exchange: receive arenas could not be mapped between the ranks, faces travel through NCCL send / recv\n");
-  }
-}
-
-// arrival flags of the direct halo delivery
-struct HaloFlags { unsigned long long *p[8]; unsigned long long seq; int n; };
-__global__ void halo_signal_kernel(const HaloFlags f) {
-  if ((int)threadIdx.x < f.n) {
-    __threadfence_system();   // the faces were stored by the pack kernel before this one in stream order
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[threadIdx.x]), "l"(f.seq) : "memory");
-  }
-}
-__global__ void halo_wait_kernel(const HaloFlags f) {
-  if ((int)threadIdx.x < f.n) {
-    unsigned long long v;
-    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.p[threadIdx.x]) : "memory"); } while (v < f.seq);
   }
 }
 
@@ -298,9 +282,8 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     QB_CUDA(cudaStreamWaitEvent(r.halo, r.ev_in_ready, 0));
     launch_pack_T<Store>(pk, twist_in, r.halo);
     if (peer) {
-      halo_signal_kernel<<<1, 32, 0, r.halo>>>(sig);
-      QB_CHECK_LAUNCH();
-      if (mask & PH_SYNC) { halo_wait_kernel<<<1, 32, 0, r.halo>>>(wt); QB_CHECK_LAUNCH(); }   // timing hook: until the neighbours' faces are here
+      comm_halo_signal(sig, r.halo);
+      if (mask & PH_SYNC) comm_halo_wait(wt, r.halo);   // timing hook: until the neighbours' faces are here
     } else if (!self) comm_exchange_halo(lat, pi, r.halo);
     if (!(mask & PH_BOUNDARY)) {
       QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
@@ -315,7 +298,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     // the exchange started earlier has finished
     cudaStream_t bs = (mask & PH_EXCHANGE) ? r.halo : r.compute;
     if (!(mask & PH_EXCHANGE)) QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
-    if (peer) { halo_wait_kernel<<<1, 32, 0, bs>>>(wt); QB_CHECK_LAUNCH(); }   // the neighbours' faces of this hop have landed
+    if (peer) comm_halo_wait(wt, bs);   // the neighbours' faces of this hop have landed
     if (lat.n_boundary[np]) {
       pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
       launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, bs);

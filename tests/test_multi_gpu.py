@@ -159,11 +159,12 @@ def test_nccl_halo_exchange_vs_global_oracle(nranks, grid, local, peer):
                                                  (2, "1,1,1,2", 1, 1), (2, "1,1,2,1", 1, 0), (2, "1,1,1,2", 0, 0)])
 def test_distributed_multigrid_solve(nranks, grid, pc, peer):
     """pc = 1: hierarchy on the even-odd system + QUDA_DIRECT_PC_SOLVE; peer = 1: all-reduces fused into the reduction kernels over the
-    NVLink peer mailboxes (comm.h), 0: ncclAllReduce on the compute stream"""
+    NVLink peer mailboxes and fine + coarse halo faces stored straight into the neighbours' ghost zones (comm.h), 0: ncclAllReduce and
+    NCCL send / recv groups on the compute stream"""
     import torch
     if torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8", QB_MG_PC=str(pc), QB_PEER_REDUCE=str(peer))
+    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8", QB_MG_PC=str(pc), QB_PEER_REDUCE=str(peer), QB_PEER_HALO=str(peer))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
            "--master-port", "29633", os.path.join(ROOT, "tests", "multi_gpu_mg.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
@@ -171,14 +172,15 @@ def test_distributed_multigrid_solve(nranks, grid, pc, peer):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks,grid", [(2, "1,1,1,2"), (2, "1,1,2,1"), (4, "1,1,2,2")])
-def test_distributed_block_multigrid(nranks, grid):
+@pytest.mark.parametrize("nranks,grid,peer", [(2, "1,1,1,2", 1), (2, "1,1,2,1", 1), (4, "1,1,2,2", 1), (2, "1,1,2,1", 0)])
+def test_distributed_block_multigrid(nranks, grid, peer):
     """BASELINE config 5's "multi-RHS coarse grid" on a lattice partitioned over real ranks: batched coarse null-vector setup and the
-    block multigrid behind invertMultiSrcQuda with ghost zones of block fields exchanged over NCCL; no fallback to one-at-a-time"""
+    block multigrid behind invertMultiSrcQuda with the ghost zones of block fields filled by the neighbours' pack kernels over NVLink peer
+    memory (peer = 1) or exchanged over NCCL (peer = 0); no fallback to one-at-a-time"""
     import torch
     if torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8", QB_MG_MULTISRC="1")
+    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8", QB_MG_MULTISRC="1", QB_PEER_HALO=str(peer))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
            "--master-port", "29655", os.path.join(ROOT, "tests", "multi_gpu_mg.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
