@@ -84,6 +84,25 @@ void DiracTM::CloverTwist(SpinorField &out, const SpinorField &in, int parity, b
   flops += (inverse ? 576ll : 552ll) * in.Vh;
 }
 
+// out = [x +] k A^-1 D in (A^-dagger with dagger) in one launch: the inverse clover block is the hop kernel's epilogue.
+// QB_FUSE_CLOVER=0: hop and clover_apply as two launches (measurement switch)
+static bool fuse_clover() {
+  static int f = -1;
+  if (f < 0) { const char *e = getenv("QB_FUSE_CLOVER"); f = (e && atoi(e) == 0) ? 0 : 1; }
+  return f == 1;
+}
+void DiracTM::WilsonDslashCloverInv(SpinorField &out, const SpinorField &in, int parity, const SpinorField *x, double k) const {
+  if (!fuse_clover() || out.v == in.v || (x && x->v == in.v)) {
+    SpinorField &t = tmp(tmp2, in);
+    WilsonDslash(t, in, parity);
+    CloverTwist(out, t, parity, true, x, k);
+    return;
+  }
+  const CloverField &cl = clover->get(in.prec, twist_a());
+  apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), TwistCoef(k, 0.0), x, TwistCoef(), cl.Ainv, dagger ? 2 : 1);
+  flops += (1320ll + 576ll + (x ? 48ll : 0ll)) * in.Vh;
+}
+
 void DiracTM::Twist(SpinorField &out, const SpinorField &in) const { apply_twist_field(out, in, A()); }
 void DiracTM::TwistInv(SpinorField &out, const SpinorField &in) const { apply_twist_field(out, in, Ainv()); }
 
@@ -92,9 +111,8 @@ void DiracTM::Dslash(SpinorField &out, const SpinorField &in, int parity) const 
   if (flavor == 2) return NdegDslash(out, in, parity);
   if (clover) {
     // A^-1 D  |  D A^-1 (dagger & symmetric)   with A = C + i a gamma5   (dirac_twisted_clover.cpp:191-227, clover_reference.cpp:234-255)
-    SpinorField &t = tmp(tmp2, in);
-    if (!dagger || !symmetric()) { WilsonDslash(t, in, parity); CloverTwist(out, t, parity, true); }
-    else { CloverTwist(t, in, 1 - parity, true); WilsonDslash(out, t, parity); }
+    if (!dagger || !symmetric()) WilsonDslashCloverInv(out, in, parity, nullptr, 1.0);
+    else { SpinorField &t = tmp(tmp2, in); CloverTwist(t, in, 1 - parity, true); WilsonDslash(out, t, parity); }
     return;
   }
   if (flavor == 0) return WilsonDslash(out, in, parity);
@@ -119,9 +137,8 @@ void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, co
     return;
   }
   if (clover) {
-    SpinorField &t = tmp(tmp2, in);
-    if (!dagger) { WilsonDslash(t, in, parity); CloverTwist(out, t, parity, true, &x, k); }
-    else { CloverTwist(t, in, 1 - parity, true); WilsonDslashXpay(out, t, parity, x, k); }
+    if (!dagger) WilsonDslashCloverInv(out, in, parity, &x, k);
+    else { SpinorField &t = tmp(tmp2, in); CloverTwist(t, in, 1 - parity, true); WilsonDslashXpay(out, t, parity, x, k); }
     return;
   }
   if (flavor == 0) return WilsonDslashXpay(out, in, parity, x, k);
@@ -182,8 +199,7 @@ void DiracTM::M(SpinorField &out, const SpinorField &in) const {
     } else {
       // (C + i a g5) in - kappa^2 D A^-1 D in, both daggers
       SpinorField &u = tmp(tmp3, in);
-      WilsonDslash(u, in, 1 - p_out);
-      CloverTwist(t, u, 1 - p_out, true);
+      WilsonDslashCloverInv(t, in, 1 - p_out, nullptr, 1.0);
       CloverTwist(u, in, p_out, false);
       WilsonDslashXpay(out, t, p_out, u, kappa2);
     }

@@ -90,6 +90,8 @@ class DiracTM : public Dirac {
   void TwistInv(SpinorField &out, const SpinorField &in) const;   // A^-1 in
   // clover operators: out(parity) = [x +] k (C + i a g5) in  /  [x +] k (C + i a g5)^-1 in, daggered as the operator is
   void CloverTwist(SpinorField &out, const SpinorField &in, int parity, bool inverse, const SpinorField *x = nullptr, double k = 1.0) const;
+  // out = [x +] k A^-1 D in   (A^-dagger D^dagger when daggered), one launch
+  void WilsonDslashCloverInv(SpinorField &out, const SpinorField &in, int parity, const SpinorField *x, double k) const;
 
   void Dslash(SpinorField &out, const SpinorField &in, int parity) const override;
   // Dslash restricted to the checkerboard range [begin, begin+count) of the output, on stream s (unpartitioned lattice)

@@ -42,6 +42,9 @@ struct DslashParam {
   long batch_in, batch_out, batch_x;
   int site_begin, site_count;             // contiguous range ...
   const int *site_list;                   // ... or explicit list of cb sites (interior / boundary split)
+  // twisted clover: (C + i a gamma5)^-1 of the output parity as two full complex 6 x 6 blocks per site, [parity][36 planes][Vh] in the
+  // arithmetic type (clover.h); applied to Co * (hop sum) before the x term.  nullptr: no clover term.
+  const void *clover_inv;
 };
 
 // ---- gamma matrices, DeGrand-Rossi: gamma_mu[s][gcol(mu,s)] = gre + i gim -----------------------
@@ -279,6 +282,40 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
   }
 }
 
+// acc <- S acc with S = (C + i a gamma5)^-1 (ADJ = false) or its conjugate transpose (ADJ = true): the site-local factor of the
+// twisted-clover even-odd operator fused into the hop's epilogue (the reference fuses it the same way, lib/tmc_dslash_def.h; as a second
+// launch it costs one more write and read of the spinor, 192 of 1344 B per site in fp32).  One 6 x 6 block per chirality, streamed row
+// by row (12 reals) so that only one row is live.
+template <typename real, bool ADJ, bool PK>
+__device__ __forceinline__ void clover_inv_mul(cplx<real> *acc, const void *Av, int parity, long Vh, long cb) {
+  constexpr int RP = sizeof(real) == 8 ? 2 : 4;
+#pragma unroll
+  for (int chi = 0; chi < 2; chi++) {
+    cplx<real> *v = acc + 6 * chi;
+    cplx<real> o[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) o[i] = cplx<real>((real)0, (real)0);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      real m[12];
+#pragma unroll
+      for (int q = 0; q < 12 / RP; q++) {
+        const real *src = (const real *)Av + (((size_t)parity * (144 / RP) + (chi * 72 + i * 12) / RP + q) * Vh + cb) * RP;
+        if constexpr (RP == 2) { const double2 t = ld_stream((const double2 *)src); m[2 * q] = t.x; m[2 * q + 1] = t.y; }
+        else { const float4 t = ld_stream((const float4 *)src); m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+      }
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        const cplx<real> b(m[2 * j], m[2 * j + 1]);
+        if (!ADJ) { if constexpr (PK) cmac_pk(o[i], b, v[j]); else cmac(o[i], b, v[j]); }
+        else cmac_conj(o[j], b, v[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) v[i] = o[i];
+  }
+}
+
 // Launch bounds from the B200 sweeps of profiles/README_r01.md: the kernel is HBM-latency bound; with the ghost-zone
 // branches compiled away fp32 / int16 run best at 72 registers (7 CTAs of 128 threads per SM: the extra registers let
 // the compiler keep the next hop's loads in flight), fp64 needs 128 registers to avoid spills.
@@ -298,7 +335,8 @@ template <typename Store, int RECON, bool TWIST_IN, bool HAS_X, bool GHOST, bool
   static constexpr int max_threads = BATCH ? 32 * DSLASH_BATCH_MAX : DslashBounds<Store>::max_threads;
   static constexpr int min_blocks = BATCH ? (sizeof(typename Store::real) == 8 ? 1 : 2) : DslashBounds<Store>::min_blocks;
 };
-template <typename Store, int RECON, bool TWIST_IN, bool HAS_X, bool GHOST, bool BATCH = false>
+// CLOVER: 0 none, 1 inverse twisted-clover block on the output, 2 its conjugate transpose
+template <typename Store, int RECON, bool TWIST_IN, bool HAS_X, bool GHOST, bool BATCH = false, int CLOVER = 0>
 __global__ void
 #ifdef QB_DSLASH_MINB
 QB_DSLASH_BOUNDS
@@ -349,6 +387,7 @@ dslash_kernel(const DslashParam p) {
   // epilogue: out = Cx x + Co acc
   constexpr bool PK = use_packed<Store>();
   if constexpr (PK) apply_twist_pk(acc, (real)p.co[0], (real)p.co[1]); else apply_twist(acc, (real)p.co[0], (real)p.co[1]);
+  if constexpr (CLOVER != 0) clover_inv_mul<real, CLOVER == 2, PK>(acc, p.clover_inv, p.parity, p.stride, cb);
   if (HAS_X) {
     cplx<real> xs[12];
     const real xsc = Store::template load<12, false>(xs, xin, p.x_norm, p.stride, cb);

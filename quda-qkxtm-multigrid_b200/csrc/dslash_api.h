@@ -8,7 +8,7 @@ struct DslashParam;
 struct PackParam;
 struct StoreD; struct StoreS; struct StoreH;
 
-template <typename Store> void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, bool ghost, int block, cudaStream_t s);
+template <typename Store> void launch_dslash_T(const DslashParam &p, int recon, bool twist_in, bool has_x, bool ghost, int block, cudaStream_t s, int clover = 0);
 template <typename Store> void launch_pack_T(const PackParam &p, bool twist_in, cudaStream_t s);
 template <typename Store> void launch_twist_T(void *out, float *out_norm, const void *in, const float *in_norm, long stride, int n, double pr, double qr, cudaStream_t s);
 
@@ -55,8 +55,10 @@ struct Lattice {
 // out(parity) = Cx x + Co D(parity <- 1-parity) Cin in     (see dslash.cuh)
 // x may be nullptr.  Runs on rt().compute; when dimensions are partitioned the face pack + exchange
 // run on rt().halo concurrently with the interior kernel, then the boundary sites are completed.
+// clover_inv != nullptr: out = Cx x + S Co D in with S = (C + i a gamma5)^-1 of the output parity (clover_mode 1) or its conjugate
+// transpose (2), CloverField::Ainv in the arithmetic type of the fields -- the twisted-clover even-odd hop in one launch
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
-               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx);
+               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, const void *clover_inv = nullptr, int clover_mode = 0);
 
 // same on the contiguous checkerboard range [site_begin, site_begin + site_count) only, on stream s (unpartitioned lattices;
 // used by the pipelined host path of dslashQuda)

@@ -146,7 +146,7 @@ static void ensure_arena(Lattice &lat, Prec prec) {
 template <typename Store>
 static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
                   TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, int range_begin = 0, int range_count = -1,
-                  cudaStream_t range_stream = nullptr) {
+                  cudaStream_t range_stream = nullptr, const void *clover_inv = nullptr, int clover_mode = 0) {
   Runtime &r = rt();
   const Geom &g = lat.geom;
   DslashParam p;
@@ -163,6 +163,8 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   p.co[0] = co.p; p.co[1] = co.q;
   p.cx[0] = cx.p; p.cx[1] = cx.q;
   p.sgn_fwd = dagger ? 1.0 : -1.0;
+  p.clover_inv = clover_inv;
+  const int clover = clover_inv ? clover_mode : 0;
   const bool twist_in = !cin.trivial();
   const bool has_x = x != nullptr;
 
@@ -173,6 +175,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   if (out.nflavor != in.nflavor || (x && x->nflavor != out.nflavor)) QB_ERROR("apply_hop: flavour counts differ");
   // members handled by one launch: the fields of a batch, or the two flavours of a doublet (which sit inside the parity block)
   const int nmember = out.nflavor == 2 ? 2 : out.nbatch;
+  if (clover && (nmember > 1 || twist_in)) QB_ERROR("apply_hop: the fused clover epilogue takes single fields without input twist");
   const size_t st_in = out.nflavor == 2 ? in.flavor_bytes() : in.batch_bytes, st_out = out.nflavor == 2 ? out.flavor_bytes() : out.batch_bytes;
   const size_t st_x = x ? (out.nflavor == 2 ? x->flavor_bytes() : x->batch_bytes) : 0;
   if (nmember > 1 && partitioned) {
@@ -207,7 +210,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
       }
       return;
     }
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, st);
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, st, clover);
     return;
   }
   if (range_count >= 0) {
@@ -218,7 +221,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     const int hi = std::min(range_begin + range_count, lat.interior_begin[parity] + lat.n_interior[parity]);
     if (hi > lo) {
       p.site_begin = lo; p.site_count = hi - lo; p.site_list = nullptr;
-      launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, range_stream ? range_stream : r.compute);
+      launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, range_stream ? range_stream : r.compute, clover);
     }
     return;
   }
@@ -301,7 +304,7 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     if (peer) comm_halo_wait(wt, bs);   // the neighbours' faces of this hop have landed
     if (lat.n_boundary[np]) {
       pb.site_begin = 0; pb.site_count = lat.n_boundary[np]; pb.site_list = lat.boundary_list[np];
-      launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, bs);
+      launch_dslash_T<Store>(pb, gauge.recon, twist_in, has_x, true, block, bs, clover);
     }
     if (mask & PH_EXCHANGE) QB_CUDA(cudaEventRecord(r.ev_halo_done, r.halo));
   }
@@ -311,20 +314,20 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
     p.site_count = lat.n_interior[np];
     if (lat.interior_contiguous[np]) { p.site_begin = lat.interior_begin[np]; p.site_list = nullptr; }
     else { p.site_begin = 0; p.site_list = lat.interior_list[np]; }
-    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, r.compute);
+    launch_dslash_T<Store>(p, gauge.recon, twist_in, has_x, false, block, r.compute, clover);
   }
   if ((mask & PH_EXCHANGE) && (mask & PH_BOUNDARY)) QB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_halo_done, 0));
 }
 
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
-               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx) {
+               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, const void *clover_inv, int clover_mode) {
   if (out.prec != in.prec || out.prec != gauge.prec || (x && x->prec != out.prec))
     QB_ERROR("apply_hop: precision mismatch (out %d, in %d, gauge %d)", (int)out.prec, (int)in.prec, (int)gauge.prec);
   if (out.Vh != lat.geom.Vh || in.Vh != lat.geom.Vh) QB_ERROR("apply_hop: field volume does not match the lattice");
   if (out.v == in.v) QB_ERROR("apply_hop: out and in must not alias");
-  if (out.prec == PREC_DOUBLE) hop_T<StoreD>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
-  else if (out.prec == PREC_SINGLE) hop_T<StoreS>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
-  else hop_T<StoreH>(lat, gauge, out, in, parity, dagger, cin, co, x, cx);
+  if (out.prec == PREC_DOUBLE) hop_T<StoreD>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode);
+  else if (out.prec == PREC_SINGLE) hop_T<StoreS>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode);
+  else hop_T<StoreH>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode);
 }
 
 // face index -> checkerboard index table of the pack kernel (for the index-parity tests)
