@@ -17,6 +17,37 @@ CloverField::CloverField(long Vh_, Prec prec_) : prec(prec_), Vh(Vh_) {
 CloverField::~CloverField() {
   if (C) cudaFree(C);
   if (Ainv) cudaFree(Ainv);
+  if (Ainv16) cudaFree(Ainv16);
+  if (Ainv16_norm) cudaFree(Ainv16_norm);
+}
+
+// fp32 inverse blocks [parity][36 float4 planes][cb] -> int16 [parity][36 int2 planes][cb] + norm (largest |element| of the site)
+__global__ void clover_inv_to_int16_kernel(int2 *out, float *norm, const float4 *in, long Vh) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * Vh) return;
+  const long parity = t / Vh, cb = t - parity * Vh;
+  float m = 0.0f;
+  for (int pl = 0; pl < 36; pl++) {
+    const float4 v = in[(parity * 36 + pl) * Vh + cb];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  norm[t] = m;
+  const float s = m > 0.0f ? HALF_MAX / m : 0.0f;
+  for (int pl = 0; pl < 36; pl++) {
+    const float4 v = in[(parity * 36 + pl) * Vh + cb];
+    out[(parity * 36 + pl) * Vh + cb] = make_int2(pack_s16x2(v.x, v.y, s), pack_s16x2(v.z, v.w, s));
+  }
+}
+void CloverField::ainv16() {
+  if (prec != PREC_SINGLE) QB_ERROR("int16 inverse clover blocks are derived from the fp32 copy");
+  if (have16 && a16 == a) return;
+  if (!Ainv16) {
+    QB_CUDA(cudaMalloc(&Ainv16, (size_t)2 * Vh * 144 * sizeof(short)));
+    QB_CUDA(cudaMalloc((void **)&Ainv16_norm, (size_t)2 * Vh * sizeof(float)));
+  }
+  clover_inv_to_int16_kernel<<<div_up(2 * Vh, 128), 128, 0, rt().compute>>>((int2 *)Ainv16, Ainv16_norm, (const float4 *)Ainv, Vh);
+  QB_CHECK_LAUNCH();
+  have16 = true; a16 = a;
 }
 
 // index of L(row, col), row > col, in the column-by-column packed lower triangle (clover_reference.cpp:45-52)

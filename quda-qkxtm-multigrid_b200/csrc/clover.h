@@ -21,6 +21,14 @@ struct CloverField {
   long Vh = 0;
   void *C = nullptr;
   void *Ainv = nullptr;
+  // fp32 copies only: the inverse blocks once more as int16 fixed point + one float norm per site ([parity][36 planes of 4 x int16][cb],
+  // norm [parity][cb]; the reference keeps its half-precision clover as short4 + norm too, lib/clover_field.cpp) for the int16 hop's
+  // fused epilogue: 292 instead of 576 B per site.  Built by ainv16() on first use.
+  void *Ainv16 = nullptr;
+  float *Ainv16_norm = nullptr;
+  double a16 = 0.0;
+  bool have16 = false;
+  void ainv16();
   double a = 0.0;           // twist the inverse was built for
   CloverField(long Vh, Prec prec);
   ~CloverField();

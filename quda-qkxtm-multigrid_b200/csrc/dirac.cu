@@ -99,7 +99,10 @@ void DiracTM::WilsonDslashCloverInv(SpinorField &out, const SpinorField &in, int
     return;
   }
   const CloverField &cl = clover->get(in.prec, twist_a());
-  apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), TwistCoef(k, 0.0), x, TwistCoef(), cl.Ainv, dagger ? 2 : 1);
+  if (in.prec == PREC_HALF) {
+    const_cast<CloverField &>(cl).ainv16();
+    apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), TwistCoef(k, 0.0), x, TwistCoef(), cl.Ainv16, dagger ? 2 : 1, cl.Ainv16_norm);
+  } else apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), TwistCoef(k, 0.0), x, TwistCoef(), cl.Ainv, dagger ? 2 : 1);
   flops += (1320ll + 576ll + (x ? 48ll : 0ll)) * in.Vh;
 }
 

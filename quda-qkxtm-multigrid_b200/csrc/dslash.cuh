@@ -45,6 +45,7 @@ struct DslashParam {
   // twisted clover: (C + i a gamma5)^-1 of the output parity as two full complex 6 x 6 blocks per site, [parity][36 planes][Vh] in the
   // arithmetic type (clover.h); applied to Co * (hop sum) before the x term.  nullptr: no clover term.
   const void *clover_inv;
+  const float *clover_norm;               // int16 storage: one float per site, [parity][Vh]; clover_inv then holds 36 planes of 4 x int16
 };
 
 // ---- gamma matrices, DeGrand-Rossi: gamma_mu[s][gcol(mu,s)] = gre + i gim -----------------------
@@ -286,9 +287,11 @@ __device__ __forceinline__ void hop(cplx<typename Store::real> *acc, const Dslas
 // twisted-clover even-odd operator fused into the hop's epilogue (the reference fuses it the same way, lib/tmc_dslash_def.h; as a second
 // launch it costs one more write and read of the spinor, 192 of 1344 B per site in fp32).  One 6 x 6 block per chirality, streamed row
 // by row (12 reals) so that only one row is live.
-template <typename real, bool ADJ, bool PK>
-__device__ __forceinline__ void clover_inv_mul(cplx<real> *acc, const void *Av, int parity, long Vh, long cb) {
+template <typename real, bool ADJ, bool PK, bool I16>
+__device__ __forceinline__ void clover_inv_mul(cplx<real> *acc, const void *Av, const float *Anorm, int parity, long Vh, long cb) {
   constexpr int RP = sizeof(real) == 8 ? 2 : 4;
+  real scale = (real)1;
+  if constexpr (I16) scale = (real)(ld_nc(Anorm + (size_t)parity * Vh + cb) * (1.0f / HALF_MAX));
 #pragma unroll
   for (int chi = 0; chi < 2; chi++) {
     cplx<real> *v = acc + 6 * chi;
@@ -300,9 +303,18 @@ __device__ __forceinline__ void clover_inv_mul(cplx<real> *acc, const void *Av, 
       real m[12];
 #pragma unroll
       for (int q = 0; q < 12 / RP; q++) {
-        const real *src = (const real *)Av + (((size_t)parity * (144 / RP) + (chi * 72 + i * 12) / RP + q) * Vh + cb) * RP;
-        if constexpr (RP == 2) { const double2 t = ld_stream((const double2 *)src); m[2 * q] = t.x; m[2 * q + 1] = t.y; }
-        else { const float4 t = ld_stream((const float4 *)src); m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+        const size_t plane = (size_t)parity * (144 / RP) + (chi * 72 + i * 12) / RP + q;
+        if constexpr (I16) {
+          const int2 t = ld_stream((const int2 *)Av + plane * Vh + cb);
+          float a0, a1, a2, a3;
+          unpack_s16x2_raw(t.x, a0, a1);
+          unpack_s16x2_raw(t.y, a2, a3);
+          m[4 * q] = (real)a0; m[4 * q + 1] = (real)a1; m[4 * q + 2] = (real)a2; m[4 * q + 3] = (real)a3;
+        } else {
+          const real *src = (const real *)Av + (plane * Vh + cb) * RP;
+          if constexpr (RP == 2) { const double2 t = ld_stream((const double2 *)src); m[2 * q] = t.x; m[2 * q + 1] = t.y; }
+          else { const float4 t = ld_stream((const float4 *)src); m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+        }
       }
 #pragma unroll
       for (int j = 0; j < 6; j++) {
@@ -312,7 +324,7 @@ __device__ __forceinline__ void clover_inv_mul(cplx<real> *acc, const void *Av, 
       }
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) v[i] = o[i];
+    for (int i = 0; i < 6; i++) v[i] = I16 ? cplx<real>(o[i].re * scale, o[i].im * scale) : o[i];
   }
 }
 
@@ -387,7 +399,7 @@ dslash_kernel(const DslashParam p) {
   // epilogue: out = Cx x + Co acc
   constexpr bool PK = use_packed<Store>();
   if constexpr (PK) apply_twist_pk(acc, (real)p.co[0], (real)p.co[1]); else apply_twist(acc, (real)p.co[0], (real)p.co[1]);
-  if constexpr (CLOVER != 0) clover_inv_mul<real, CLOVER == 2, PK>(acc, p.clover_inv, p.parity, p.stride, cb);
+  if constexpr (CLOVER != 0) clover_inv_mul<real, CLOVER == 2, PK, Store::scaled>(acc, p.clover_inv, p.clover_norm, p.parity, p.stride, cb);
   if (HAS_X) {
     cplx<real> xs[12];
     const real xsc = Store::template load<12, false>(xs, xin, p.x_norm, p.stride, cb);

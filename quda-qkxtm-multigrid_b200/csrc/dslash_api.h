@@ -56,9 +56,11 @@ struct Lattice {
 // x may be nullptr.  Runs on rt().compute; when dimensions are partitioned the face pack + exchange
 // run on rt().halo concurrently with the interior kernel, then the boundary sites are completed.
 // clover_inv != nullptr: out = Cx x + S Co D in with S = (C + i a gamma5)^-1 of the output parity (clover_mode 1) or its conjugate
-// transpose (2), CloverField::Ainv in the arithmetic type of the fields -- the twisted-clover even-odd hop in one launch
+// transpose (2), CloverField::Ainv in the arithmetic type of the fields (int16 fields: Ainv16 + clover_norm) -- the twisted-clover even-odd
+// hop in one launch
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
-               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, const void *clover_inv = nullptr, int clover_mode = 0);
+               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, const void *clover_inv = nullptr, int clover_mode = 0,
+               const float *clover_norm = nullptr);
 
 // same on the contiguous checkerboard range [site_begin, site_begin + site_count) only, on stream s (unpartitioned lattices;
 // used by the pipelined host path of dslashQuda)

@@ -146,7 +146,7 @@ static void ensure_arena(Lattice &lat, Prec prec) {
 template <typename Store>
 static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
                   TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, int range_begin = 0, int range_count = -1,
-                  cudaStream_t range_stream = nullptr, const void *clover_inv = nullptr, int clover_mode = 0) {
+                  cudaStream_t range_stream = nullptr, const void *clover_inv = nullptr, int clover_mode = 0, const float *clover_norm = nullptr) {
   Runtime &r = rt();
   const Geom &g = lat.geom;
   DslashParam p;
@@ -164,6 +164,8 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
   p.cx[0] = cx.p; p.cx[1] = cx.q;
   p.sgn_fwd = dagger ? 1.0 : -1.0;
   p.clover_inv = clover_inv;
+  p.clover_norm = clover_norm;
+  if (clover_inv && Store::prec == PREC_HALF && !clover_norm) QB_ERROR("apply_hop: int16 fields take the int16 + norm copy of the inverse clover blocks");
   const int clover = clover_inv ? clover_mode : 0;
   const bool twist_in = !cin.trivial();
   const bool has_x = x != nullptr;
@@ -320,14 +322,14 @@ static void hop_T(Lattice &lat, const GaugeField &gauge, SpinorField &out, const
 }
 
 void apply_hop(Lattice &lat, const GaugeField &gauge, SpinorField &out, const SpinorField &in, int parity, bool dagger,
-               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, const void *clover_inv, int clover_mode) {
+               TwistCoef cin, TwistCoef co, const SpinorField *x, TwistCoef cx, const void *clover_inv, int clover_mode, const float *clover_norm) {
   if (out.prec != in.prec || out.prec != gauge.prec || (x && x->prec != out.prec))
     QB_ERROR("apply_hop: precision mismatch (out %d, in %d, gauge %d)", (int)out.prec, (int)in.prec, (int)gauge.prec);
   if (out.Vh != lat.geom.Vh || in.Vh != lat.geom.Vh) QB_ERROR("apply_hop: field volume does not match the lattice");
   if (out.v == in.v) QB_ERROR("apply_hop: out and in must not alias");
-  if (out.prec == PREC_DOUBLE) hop_T<StoreD>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode);
-  else if (out.prec == PREC_SINGLE) hop_T<StoreS>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode);
-  else hop_T<StoreH>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode);
+  if (out.prec == PREC_DOUBLE) hop_T<StoreD>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode, clover_norm);
+  else if (out.prec == PREC_SINGLE) hop_T<StoreS>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode, clover_norm);
+  else hop_T<StoreH>(lat, gauge, out, in, parity, dagger, cin, co, x, cx, 0, -1, nullptr, clover_inv, clover_mode, clover_norm);
 }
 
 // face index -> checkerboard index table of the pack kernel (for the index-parity tests)
