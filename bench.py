@@ -458,6 +458,8 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=Fal
         xs = [np.zeros(V * 24) for _ in range(nsrc)]
         multi = {"sources": nsrc}
         for name, env in (("block", "1"), ("sequential", "0")):
+            if name == "sequential" and os.environ.get("QB_BENCH_BLOCK_ONLY") == "1":
+                continue
             os.environ["QB_BLOCK_MG"] = env
             pm = inv_param()
             pm.inv_type_precondition = q.QUDA_MG_INVERTER
@@ -473,7 +475,8 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=Fal
             wall = time.perf_counter() - t0
             multi[name] = {"solve_seconds": pm.secs, "seconds_per_source": pm.secs / nsrc, "wall_seconds_incl_h2d_d2h": wall, "iterations": pm.iter, "worst_true_res": pm.true_res}
         os.environ.pop("QB_BLOCK_MG", None)
-        multi["speedup_per_source"] = multi["sequential"]["solve_seconds"] / multi["block"]["solve_seconds"]
+        if "sequential" in multi:
+            multi["speedup_per_source"] = multi["sequential"]["solve_seconds"] / multi["block"]["solve_seconds"]
         del bs, xs
     res = {"lattice": list(X), "levels": 3, "outer_krylov_vectors": {4: "fp32", 2: "int16 + norm (cuda_prec_sloppy = half), reliable_delta 1e-2"}[sloppy], "outer_solve": "QUDA_DIRECT_PC_SOLVE, coarse_grid_solution_type MATPC on every level" if pc else "QUDA_DIRECT_SOLVE, coarse_grid_solution_type MAT",
            "smoother_precision_level0": {2: "int16", 4: "fp32"}[precond],

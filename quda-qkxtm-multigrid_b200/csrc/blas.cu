@@ -474,6 +474,28 @@ _Pragma("unroll")
   return out[0];
 }
 
+// BiCGStab tail in one pass: x += a p + w r; r -= w t; returns (<r0, r>, |r|^2) of the new r  (5 reads + 2 writes instead of the 7 + 2
+// of caxpbypz, caxpyNorm and the next iteration's cDotProduct; the reference fuses the same three, caxpbypzYmbwcDotProductUYNormY,
+// lib/inv_bicgstab_quda.cpp)
+double3_ bicgstabUpdate(Complex a, const SpinorField &p, Complex w, SpinorField &r, const SpinorField &t, SpinorField &x, const SpinorField &r0) {
+  check_same(p, r); check_same(p, t); check_same(p, x); check_same(p, r0);
+  double out[3];
+  BY_PREC(p, const FA P(p); const FA R(r); const FA T(t); const FA X(x); const FA R0(r0);
+          const cplx<real> A((real)a.real(), (real)a.imag()), W((real)w.real(), (real)w.imag()), mW(-(real)w.real(), -(real)w.imag());
+          reduce<3>(out, FA::count(p), [=] __device__(long i, double *acc) {
+            FA::pack pp = P.load(i), rr = R.load(i), tt = T.load(i), xx = X.load(i), zz = R0.load(i);
+_Pragma("unroll")
+            for (int k = 0; k < FA::pack::N; k++) {
+              cmac(xx.c[k], A, pp.c[k]); cmac(xx.c[k], W, rr.c[k]);
+              cmac(rr.c[k], mW, tt.c[k]);
+              cdot_acc(acc, zz.c[k], rr.c[k]); acc[2] += norm_c(rr.c[k]);
+            }
+            X.store(i, xx); R.store(i, rr);
+          }););
+  flops += 18 * p.reals(); bytes += 7 * p.bytes();
+  return double3_{out[0], out[1], out[2]};
+}
+
 double cabxpyAxNorm(double a, Complex b, SpinorField &x, SpinorField &y) {
   check_same(x, y);
   double out[1];

@@ -49,6 +49,8 @@ double3_ cDotProductNormB(const SpinorField &x, const SpinorField &y);     // (R
 double axpyNorm(double a, const SpinorField &x, SpinorField &y);           // y += a x; |y|^2
 double xmyNorm(const SpinorField &x, SpinorField &y);                      // y = x - y; |y|^2
 double caxpyNorm(Complex a, const SpinorField &x, SpinorField &y);         // y += a x; |y|^2
+// x += a p + w r; r -= w t; (Re <r0, r>, Im <r0, r>, |r|^2) of the new r
+double3_ bicgstabUpdate(Complex a, const SpinorField &p, Complex w, SpinorField &r, const SpinorField &t, SpinorField &x, const SpinorField &r0);
 double cabxpyAxNorm(double a, Complex b, SpinorField &x, SpinorField &y);  // y += a b x; x *= a; |y|^2 (what lib/reduce_quda.cu:490-497 computes; its comment says x)
 Complex caxpyDotzy(Complex a, const SpinorField &x, SpinorField &y, const SpinorField &z);  // y += a x; (z, y)
 double caxpyXmazNormX(Complex a, SpinorField &x, SpinorField &y, const SpinorField &z);     // y += a x; x -= a z; |x|^2

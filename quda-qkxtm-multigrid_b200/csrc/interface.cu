@@ -1586,7 +1586,9 @@ extern "C" int blasQudaB200(const char *name, long n, int prec, const double *co
   else if (nm == "caxpyDotzy") { Complex c = caxpyDotzy(ca, fx, fy, fz); result[0] = c.real(); result[1] = c.imag(); nres = 2; }
   else if (nm == "caxpyXmazNormX") { result[0] = caxpyXmazNormX(ca, fx, fy, fz); nres = 1; }
   else if (nm == "xpaycDotzy") { Complex c = xpaycDotzy(fx, a, fy, fz); result[0] = c.real(); result[1] = c.imag(); nres = 2; }
-  else if (nm == "block_cDotProduct") {  // (x,w), (y,w), (z,w)
+  else if (nm == "bicgstabUpdate") {  // w += a x + b y; y -= b z; (<x, y>, |y|^2)
+    double3_ d = bicgstabUpdate(ca, fx, cb, fy, fz, fw, fx); result[0] = d.x; result[1] = d.y; result[2] = d.z; nres = 3;
+  } else if (nm == "block_cDotProduct") {  // (x,w), (y,w), (z,w)
     std::vector<SpinorField *> v{&fx, &fy, &fz};
     Complex r3[3];
     cDotProduct(r3, v, fw);

@@ -430,9 +430,10 @@ void BiCGStab::operator()(SpinorField &x, SpinorField &b) {
   blas::zero(*p); blas::zero(*v);
   Complex rho(1.0, 0.0), rho0(1.0, 0.0), alpha(1.0, 0.0), omega(1.0, 0.0);
   int k = 0;
+  Complex rho_next = blas::cDotProduct(*r0, *r);
   while (r2 > stop && k < param.maxiter) {
     rho0 = rho;
-    rho = blas::cDotProduct(*r0, *r);
+    rho = rho_next;
     if (std::abs(rho0) == 0.0 || std::abs(omega) == 0.0) break;
     const Complex beta = (rho / rho0) * (alpha / omega);
     // p = r + beta (p - omega v)
@@ -446,9 +447,10 @@ void BiCGStab::operator()(SpinorField &x, SpinorField &b) {
     const blas::double3_ ts = blas::cDotProductNormA(*t, *r);
     if (ts.z == 0.0) { blas::caxpy(alpha, *p, *xs); r2 = blas::norm2(*r); k++; break; }
     omega = Complex(ts.x, ts.y) / ts.z;
-    // x += alpha p + omega s ; r = s - omega t
-    blas::caxpbypz(alpha, *p, omega, *r, *xs);
-    r2 = blas::caxpyNorm(-omega, *t, *r);
+    // x += alpha p + omega s ; r = s - omega t ; <r0, r> of the next iteration and |r|^2 in the same pass
+    const blas::double3_ up = blas::bicgstabUpdate(alpha, *p, omega, *r, *t, *xs, *r0);
+    rho_next = Complex(up.x, up.y);
+    r2 = up.z;
     k++;
     if (param.verbosity >= 3) log_msg(3, "BiCGstab: %d iterations, <r,r> = %e, |r|/|b| = %e\n", k, r2, sqrt(r2 / b2));
   }

@@ -54,6 +54,7 @@ def host(name, x, y, z, w):
     elif name == "caxpyDotzy": y = y + a * x; d = np.vdot(z, y); r = [d.real, d.imag]
     elif name == "caxpyXmazNormX": y = y + a * x; x = x - a * z; r = [np.vdot(x, x).real]
     elif name == "xpaycDotzy": y = x + ar * y; d = np.vdot(z, y); r = [d.real, d.imag]
+    elif name == "bicgstabUpdate": w = w + a * x + b * y; y = y - b * z; d = np.vdot(x, y); r = [d.real, d.imag, np.vdot(y, y).real]
     elif name == "block_cDotProduct":
         r = []
         for v in (x, y, z):
@@ -65,7 +66,7 @@ def host(name, x, y, z, w):
 
 OPS = ["ax", "axpy", "xpy", "xpay", "mxpy", "axpby", "caxpy", "caxpby", "cxpaypbz", "caxpbypz", "caxpbypzYmbw", "cabxpyAx",
        "caxpyXmaz", "norm2", "reDotProduct", "cDotProduct", "cDotProductNormA", "cDotProductNormB", "axpyNorm", "xmyNorm",
-       "caxpyNorm", "cabxpyAxNorm", "caxpyDotzy", "caxpyXmazNormX", "xpaycDotzy", "block_cDotProduct", "block_caxpy"]
+       "caxpyNorm", "cabxpyAxNorm", "caxpyDotzy", "caxpyXmazNormX", "xpaycDotzy", "bicgstabUpdate", "block_cDotProduct", "block_caxpy"]
 
 
 @pytest.mark.parametrize("prec", [8, 4])
