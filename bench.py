@@ -470,9 +470,15 @@ def run_mg_leg(q, L, oracle, X, precond=2, half_storage=False, full=True, pc=Fal
             ptr_x, ptr_b = (C.c_void_p * nsrc)(*[a.ctypes.data for a in xs]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bs])
             if name == "block":
                 L.invertMultiSrcQuda(ptr_x, ptr_b, C.byref(pm))  # warm-up (allocations), as for the single solve above
+            prof = name == "block" and os.environ.get("QB_BENCH_CUDA_PROFILER") == "1"   # ncu --profile-from-start off: this solve only
+            if prof:
+                import torch
+                torch.cuda.cudart().cudaProfilerStart()
             t0 = time.perf_counter()
             L.invertMultiSrcQuda(ptr_x, ptr_b, C.byref(pm))
             wall = time.perf_counter() - t0
+            if prof:
+                torch.cuda.cudart().cudaProfilerStop()
             multi[name] = {"solve_seconds": pm.secs, "seconds_per_source": pm.secs / nsrc, "wall_seconds_incl_h2d_d2h": wall, "iterations": pm.iter, "worst_true_res": pm.true_res}
         os.environ.pop("QB_BLOCK_MG", None)
         if "sequential" in multi:
