@@ -178,16 +178,33 @@ float *CloverSet::site_major_f32() const {
 void CloverSet::release() {
   if (master) cudaFree(master);
   master = nullptr;
-  d64.reset(); f32.reset();
+  for (int i = 0; i < CLOVER_CACHE; i++) { d64[i].f.reset(); f32[i].f.reset(); }
   loaded = false;
 }
 
 const CloverField &CloverSet::get(Prec prec, double a) {
   if (!loaded) QB_ERROR("no clover field resident: call loadCloverQuda first");
-  std::unique_ptr<CloverField> &f = prec == PREC_DOUBLE ? d64 : f32;
+  Slot *slots = prec == PREC_DOUBLE ? d64 : f32;
+  // the copy built for this twist, else an empty slot, else the least recently used one
+  int pick = -1;
+  for (int i = 0; i < CLOVER_CACHE; i++)
+    if (slots[i].f && slots[i].f->a == a) pick = i;
+  bool rebuild = false;
+  if (pick < 0) {
+    rebuild = true;
+    for (int i = 0; i < CLOVER_CACHE && pick < 0; i++)
+      if (!slots[i].f) pick = i;
+    if (pick < 0) {
+      pick = 0;
+      for (int i = 1; i < CLOVER_CACHE; i++)
+        if (slots[i].last_use < slots[pick].last_use) pick = i;
+    }
+  }
+  std::unique_ptr<CloverField> &f = slots[pick].f;
+  slots[pick].last_use = ++use_clock;
   const bool fresh = !f;
   if (fresh) f.reset(new CloverField(Vh, prec == PREC_DOUBLE ? PREC_DOUBLE : PREC_SINGLE));
-  if (fresh || f->a != a) {
+  if (fresh || rebuild) {
     const long n = 4 * Vh;
     if (f->prec == PREC_DOUBLE) clover_prepare_kernel<double><<<div_up(n, 128), 128, 0, rt().compute>>>((double *)f->C, (double *)f->Ainv, master, Vh, a, fresh ? 1 : 0);
     else clover_prepare_kernel<float><<<div_up(n, 128), 128, 0, rt().compute>>>((float *)f->C, (float *)f->Ainv, master, Vh, a, fresh ? 1 : 0);

@@ -40,7 +40,12 @@ struct CloverField {
 struct CloverSet {
   long Vh = 0;
   double *master = nullptr;   // [V][72] packed, even sites first (QUDA_PACKED_CLOVER_ORDER)
-  std::unique_ptr<CloverField> d64, f32;
+  // per precision up to CLOVER_CACHE working copies, each with the inverse built for one twist `a`: the outer operator and the multigrid
+  // operators (kappa, mu scaled by delta_kappaPR / delta_muPR) may use different twists in turn and must not evict each other
+  static constexpr int CLOVER_CACHE = 3;
+  struct Slot { std::unique_ptr<CloverField> f; unsigned long last_use = 0; };
+  Slot d64[CLOVER_CACHE], f32[CLOVER_CACHE];
+  unsigned long use_clock = 0;
   bool loaded = false;
   // working copy in the precision the operator computes in (PREC_HALF -> fp32), with the inverse built for twist a
   const CloverField &get(Prec prec, double a);

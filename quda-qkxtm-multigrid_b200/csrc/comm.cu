@@ -170,7 +170,7 @@ void PeerArena::create(size_t buffer_bytes) {
   destroy();
   bytes = (buffer_bytes + 255) & ~(size_t)255;
   const size_t total = 2 * bytes + 256;
-  QB_CUDA(cudaMalloc((void **)&local, total));
+  local = (char *)comm_alloc_halo(total);
   QB_CUDA(cudaMemset(local, 0, total));
   seq = 0;
   peer = comm_peer_halo_wanted() && comm_ipc_map(local, mapped);
@@ -195,7 +195,7 @@ static void peer_reduce_setup() {
   if (env && atoi(env) == 0) return;
   if (r.size > PEER_MAX_RANKS) return;
   const size_t bytes = peer_box_bytes(r.size) + sizeof(unsigned long long) * 2 * r.size;
-  QB_CUDA(cudaMalloc(&peer_local, bytes));
+  peer_local = comm_alloc_halo(bytes);
   QB_CUDA(cudaMemset(peer_local, 0, bytes));
   if (!comm_ipc_map(peer_local, peer_mapped)) {
     log_msg(1, "peer mailboxes for the fused all-reduce could not be mapped on every rank: reductions use ncclAllReduce\n");
@@ -275,9 +275,12 @@ int comm_neighbor_rank(int dim, int dir) {
   return rank_map ? rank_map(c, rank_map_data) : 0;
 }
 
+// Buffers that may be exported to the peers with CUDA IPC: whole multiples of 2 MiB, so that an exported handle covers this buffer alone
+// (the driver packs smaller allocations into shared 2 MiB blocks, and an IPC handle always exports the whole block)
+static size_t ipc_round(size_t bytes) { const size_t g = (size_t)2 << 20; return ((bytes ? bytes : 1) + g - 1) / g * g; }
 void *comm_alloc_halo(size_t bytes) {
   void *p = nullptr;
-  QB_CUDA(cudaMalloc(&p, bytes ? bytes : 256));
+  QB_CUDA(cudaMalloc(&p, ipc_round(bytes)));
   return p;
 }
 void comm_free_halo(void *p) {
