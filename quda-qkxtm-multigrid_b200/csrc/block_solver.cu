@@ -315,16 +315,41 @@ struct BlockOps {
 };
 
 // R separate fine-grid fields (single precision, full); inactive columns are skipped altogether
+// QB_BLOCK_BATCH=0: the R columns of a fine-grid block vector as separate fields and every fine operator application one column at a time
+static bool block_batch_on() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("QB_BLOCK_BATCH"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on == 1;
+}
+
 struct FieldOps {
   typedef std::vector<SpinorField *> *Vec;
   int R; long Vh; int nparity;
   std::vector<std::unique_ptr<std::vector<SpinorField *>>> owned;
+  // single-parity vectors: the R columns are the members of ONE batch field, so that the fine operator can run on all of them in one
+  // launch per hop (links read once per group of 12 columns); BLAS works on the member views
+  std::vector<std::pair<Vec, SpinorField *>> batches;
   FieldOps(int R_, long Vh_, int nparity_) : R(R_), Vh(Vh_), nparity(nparity_) {}
-  ~FieldOps() { for (auto &v : owned) for (SpinorField *f : *v) delete f; }
+  ~FieldOps() {
+    for (auto &v : owned) for (SpinorField *f : *v) delete f;
+    for (auto &b : batches) delete b.second;
+  }
   Vec make() {
     owned.emplace_back(new std::vector<SpinorField *>(R));
-    for (int r = 0; r < R; r++) { (*owned.back())[r] = new SpinorField(Vh, nparity, PREC_SINGLE); blas::zero(*(*owned.back())[r]); }
+    SpinorField *bf = (nparity == 1 && R > 1 && block_batch_on()) ? new SpinorField(Vh, 1, PREC_SINGLE, 4, 3, R) : nullptr;
+    for (int r = 0; r < R; r++) {
+      SpinorField *f;
+      if (bf) { f = new SpinorField(); bf->member(*f, r); }
+      else f = new SpinorField(Vh, nparity, PREC_SINGLE);
+      (*owned.back())[r] = f;
+      blas::zero(*f);
+    }
+    if (bf) batches.emplace_back(owned.back().get(), bf);
     return owned.back().get();
+  }
+  SpinorField *batch(Vec v) const {
+    for (auto &b : batches) if (b.first == v) return b.second;
+    return nullptr;
   }
   void release(Vec) {}
   void copy(Vec d, Vec s_, const Mask &m) { for (int r = 0; r < R; r++) if (m[r]) blas::copy(*(*d)[r], *(*s_)[r]); }
@@ -721,8 +746,64 @@ class BlockMG {
     L.ops_full->axpy(one, L.t->v, fine.v, active);
   }
 
+  // ---- level-0 smoother of the even-odd cycle, all columns in lock-step ---------------------------------------------------------
+  // scratch block vectors (residual, A r) as batch fields + member views
+  std::unique_ptr<SpinorField> sB[2];
+  std::vector<std::unique_ptr<SpinorField>> sV[2];
+  void ensure_smoother_scratch(long Vh) {
+    for (int i = 0; i < 2; i++) {
+      if (sB[i] && sB[i]->Vh == Vh) continue;
+      sV[i].clear();
+      sB[i].reset(new SpinorField(Vh, 1, PREC_SINGLE, 4, 3, R));
+      for (int c = 0; c < R; c++) { sV[i].emplace_back(new SpinorField()); sB[i]->member(*sV[i].back(), c); }
+    }
+  }
+  // out = M_pc in on every active column: one batched application (one launch per hop for all columns, links read once per group of 12)
+  // when both sides are batch fields and every column is active, else column by column
+  void apply_smoother_op(SpinorField *outB, SpinorField *const *out, const SpinorField *inB, SpinorField *const *in, const Mask &active) {
+    bool all = true;
+    for (int c = 0; c < R; c++) all = all && active[c];
+    if (all && outB && inB) { top.matSmooth->M(*outB, *inB); return; }
+    for (int c = 0; c < R; c++) if (active[c]) top.matSmooth->M(*out[c], *in[c]);
+  }
+  // The smoother fast path of MR::operator() (solver.cu: fixed iteration count, source preserved, no normalisation passes, last residual
+  // update dropped unless it is wanted) on R columns at once.  keep_residual: sV[0][c] holds b - M_pc x of column c on return.
+  void mr_lockstep(std::vector<SpinorField *> &x, SpinorField *xB, std::vector<SpinorField *> &b, SpinorField *bB, int nu, double omega, bool init_guess,
+                   bool keep_residual, bool global_reduction, const Mask &active) {
+    ensure_smoother_scratch(x[0]->Vh);
+    blas::set_global_reduction(global_reduction);
+    std::vector<SpinorField *> r(R), Ar(R), rc(R);
+    for (int c = 0; c < R; c++) { r[c] = sV[0][c].get(); Ar[c] = sV[1][c].get(); rc[c] = b[c]; }
+    SpinorField *rB = sB[0].get(), *ArB = sB[1].get();
+    const SpinorField *rcB = bB;
+    bool from_b = true, x_valid = init_guess;
+    if (init_guess) {
+      apply_smoother_op(rB, r.data(), xB, x.data(), active);
+      for (int c = 0; c < R; c++) if (active[c]) blas::axpby(1.0, *b[c], -1.0, *r[c]);   // r = b - A x0
+      rc = r; rcB = rB; from_b = false;
+    }
+    for (int k = 0; k < nu; k++) {
+      apply_smoother_op(ArB, Ar.data(), rcB, rc.data(), active);
+      const bool last = k == nu - 1;
+      for (int c = 0; c < R; c++) {
+        if (!active[c]) continue;
+        const blas::double3_ d = blas::cDotProductNormA(*Ar[c], *rc[c]);
+        const Cx alpha = d.z > 0.0 ? omega * Cx(d.x, d.y) / d.z : Cx(0, 0);
+        if (last && !keep_residual) {
+          if (x_valid) blas::caxpy(alpha, *rc[c], *x[c]);
+          else blas::cax(alpha, *rc[c], *x[c]);
+        } else if (from_b) blas::mrFirstStep(alpha, *b[c], *Ar[c], *x[c], *r[c], x_valid);
+        else blas::caxpyXmaz(alpha, *r[c], *x[c], *Ar[c]);   // x += alpha r; r -= alpha A r
+      }
+      if (from_b && !(last && !keep_residual)) { rc = r; rcB = rB; from_b = false; }
+      x_valid = true;
+    }
+    if (!x_valid) for (int c = 0; c < R; c++) if (active[c]) blas::zero(*x[c]);
+    blas::set_global_reduction(true);
+  }
+
   // level-0 cycle for R fine right-hand sides (single precision, full fields)
-  void apply(std::vector<SpinorField *> &x, std::vector<SpinorField *> &b, const Mask &active) {
+  void apply(std::vector<SpinorField *> &x, std::vector<SpinorField *> &b, const Mask &active, SpinorField *xB = nullptr, SpinorField *bB = nullptr) {
     const MGLevelParam &lp = top.mp.level[0];
     BlockMGLevel &L1 = *lv[0];
     std::vector<SpinorField *> pb(R), px(R);
@@ -734,18 +815,31 @@ class BlockMG {
     const int tpar = pc ? top.pc_parity : -1;
     if (pc && !top.pc_coarsen) QB_ERROR("block multigrid: single-parity fields need a hierarchy coarsened on the even-odd system");
     while ((int)rres.size() < R) rres.emplace_back(new SpinorField(top.r->Vh, pc ? 1 : 2, PREC_SINGLE));
+    // even-odd cycle with an MR smoother: all columns in lock-step, the operator on batch fields, the residual after pre-smoothing
+    // left behind by the smoother's last step (use_solver_residual, as MG::cycle_pc)
+    const bool lockstep = pc && block_batch_on() && top.mp.level[0].smoother == INV_MR && x[0]->prec == PREC_SINGLE && b[0]->prec == PREC_SINGLE;
+    if (lockstep && lp.nu_pre > 0) {
+      BSection s_(&t_prof[0]);
+      mr_lockstep(x, xB, b, bB, lp.nu_pre, lp.omega, false, true, lp.global_reduction, active);
+    }
     for (int c = 0; c < R; c++) {
       if (!active[c]) continue;
-      if (lp.nu_pre > 0) {
+      SpinorField *res = rres[c].get();
+      if (lockstep && lp.nu_pre > 0) res = sV[0][c].get();
+      else if (lp.nu_pre > 0) {
         { BSection s_(&t_prof[0]); if (pc) (*top.presmoother)(*x[c], *b[c]); else top.smooth(*top.presmoother, *x[c], *b[c]); }
         BSection s_(&t_prof[1]);
-        (pc ? top.matSmooth : top.matResidual)->M(*rres[c], *x[c]);
-        blas::axpby(1.0, *b[c], -1.0, *rres[c]);
+        const MR *mr = pc ? dynamic_cast<const MR *>(top.presmoother.get()) : nullptr;
+        if (mr && mr->residual()) blas::copy(*rres[c], *mr->residual());   // b - M_pc x left behind by the smoother's last step
+        else {
+          (pc ? top.matSmooth : top.matResidual)->M(*rres[c], *x[c]);
+          blas::axpby(1.0, *b[c], -1.0, *rres[c]);
+        }
       } else {
         blas::zero(*x[c]);
         blas::copy(*rres[c], *b[c]);
       }
-      act_res.push_back(rres[c].get()); act_pb.push_back(pb[c]); act_px.push_back(px[c]); act_x.push_back(x[c]);
+      act_res.push_back(res); act_pb.push_back(pb[c]); act_px.push_back(px[c]); act_x.push_back(x[c]);
     }
     { BSection s_(&t_prof[2]); top.transfer->R_multi(act_pb.data(), act_res.data(), (int)act_res.size(), tpar); }
     {
@@ -755,8 +849,11 @@ class BlockMG {
       L1.x->unpack(px.data());
     }
     { BSection s_(&t_prof[4]); top.transfer->P_multi(act_x.data(), act_px.data(), (int)act_x.size(), true, tpar); }
-    if (lp.nu_post > 0)
-      for (int c = 0; c < R; c++) if (active[c]) { BSection s_(&t_prof[5]); if (pc) (*top.postsmoother)(*x[c], *b[c]); else top.smooth(*top.postsmoother, *x[c], *b[c]); }
+    if (lp.nu_post > 0) {
+      if (lockstep) { BSection s_(&t_prof[5]); mr_lockstep(x, xB, b, bB, lp.nu_post, lp.omega, true, false, lp.global_reduction, active); }
+      else
+        for (int c = 0; c < R; c++) if (active[c]) { BSection s_(&t_prof[5]); if (pc) (*top.postsmoother)(*x[c], *b[c]); else top.smooth(*top.postsmoother, *x[c], *b[c]); }
+    }
     ncycle++;
   }
   double t_prof[6] = {0, 0, 0, 0, 0, 0};
@@ -798,8 +895,14 @@ int block_mg_gcr_solve(MG &mg, const DiracMatrix &mat, const DiracMatrix &matSlo
   FieldOps ops(R, x[0]->Vh, x[0]->nparity);
   BlockKrylov<FieldOps> kry(ops);
   typedef BlockKrylov<FieldOps>::Op Op;
-  Op A = [&](FieldOps::Vec o, FieldOps::Vec i, const Mask &m) { for (int c = 0; c < R; c++) if (m[c]) matSloppy(*(*o)[c], *(*i)[c]); };
-  Op K = [&](FieldOps::Vec o, FieldOps::Vec i, const Mask &m) { bmg.apply(*o, *i, m); };
+  Op A = [&](FieldOps::Vec o, FieldOps::Vec i, const Mask &m) {
+    SpinorField *oB = ops.batch(o), *iB = ops.batch(i);
+    bool all = oB && iB;
+    for (int c = 0; c < R; c++) all = all && m[c];
+    if (all) { matSloppy(*oB, *iB); return; }   // one launch per hop for all columns
+    for (int c = 0; c < R; c++) if (m[c]) matSloppy(*(*o)[c], *(*i)[c]);
+  };
+  Op K = [&](FieldOps::Vec o, FieldOps::Vec i, const Mask &m) { bmg.apply(*o, *i, m, ops.batch(o), ops.batch(i)); };
   FieldOps::Vec rS = ops.make(), e = ops.make();
   std::vector<std::unique_ptr<SpinorField>> r(R), tmp(R);
   std::vector<double> b2(R), r2(R), stop(R), stop_inner(R), r2_inner;

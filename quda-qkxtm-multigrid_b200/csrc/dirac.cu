@@ -121,7 +121,7 @@ void DiracTM::Dslash(SpinorField &out, const SpinorField &in, int parity) const 
   if (flavor == 0) return WilsonDslash(out, in, parity);
   if (!dagger || !symmetric()) apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), Ainv(), nullptr, TwistCoef());
   else apply_hop(*lat, *gauge, out, in, parity, dagger, Ainv(), TwistCoef(), nullptr, TwistCoef());
-  flops += 1392ll * in.Vh;
+  flops += 1392ll * in.Vh * in.nbatch;
 }
 
 void DiracTM::DslashRange(SpinorField &out, const SpinorField &in, int parity, int begin, int count, cudaStream_t s) const {
@@ -147,10 +147,21 @@ void DiracTM::DslashXpay(SpinorField &out, const SpinorField &in, int parity, co
   if (flavor == 0) return WilsonDslashXpay(out, in, parity, x, k);
   if (!dagger) apply_hop(*lat, *gauge, out, in, parity, dagger, TwistCoef(), Ainv(k), &x, TwistCoef());
   else apply_hop(*lat, *gauge, out, in, parity, dagger, Ainv(), TwistCoef(k, 0.0), &x, TwistCoef());
-  flops += 1416ll * in.Vh;
+  flops += 1416ll * in.Vh * in.nbatch;
 }
 
 void DiracTM::M(SpinorField &out, const SpinorField &in) const {
+  if (in.nbatch > 1 && (clover || flavor == 2 || in.prec != gauge->prec || !pc)) {
+    // batch fields: only the plain even-odd twisted-mass / Wilson operator in the fields' own precision runs on all members at once
+    // (batched hop, links read once per group); everything else member by member
+    if (out.nbatch != in.nbatch) QB_ERROR("DiracTM::M: batch sizes differ");
+    for (int c = 0; c < in.nbatch; c++) {
+      SpinorField o, i;
+      out.member(o, c); in.member(i, c);
+      M(o, i);
+    }
+    return;
+  }
   if (flavor == 2 && in.prec == gauge->prec) return NdegM(out, in);
   if (in.prec != gauge->prec) {
     // vectors live in another precision than the operator (e.g. fp32 smoother vectors, int16 operator):
