@@ -86,7 +86,7 @@ def main():
         dist.all_gather(tr, torch.tensor([p.true_res, float(p.iter)], dtype=torch.float64, device="cuda"))
         assert all(bool((t == tr[0]).all()) for t in tr), [t.tolist() for t in tr]
     assert p.iter < p0.iter / 2, (p.iter, p0.iter)
-    if os.environ.get("QB_MG_MULTISRC") == "1" and not pc:
+    if os.environ.get("QB_MG_MULTISRC") == "1":
         # block multigrid on the partitioned lattice (BASELINE config 5: multi-RHS coarse grid): ghost zones of block fields in the
         # tensor-core coarse operator, global block reductions; every solution checked with the global host operator
         nsrc = 3
@@ -99,6 +99,8 @@ def main():
         pm.preconditioner = mg
         pm.num_src = nsrc
         pm.verbosity = q.QUDA_SUMMARIZE
+        if pc:
+            pm.solve_type = q.QUDA_DIRECT_PC_SOLVE
         L.invertMultiSrcQuda((C.c_void_p * nsrc)(*[a.ctypes.data for a in xls]), (C.c_void_p * nsrc)(*[a.ctypes.data for a in bls]), C.byref(pm))
         for k in range(nsrc):
             if world > 1:

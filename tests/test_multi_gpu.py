@@ -172,15 +172,17 @@ def test_distributed_multigrid_solve(nranks, grid, pc, peer):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks,grid,peer", [(2, "1,1,1,2", 1), (2, "1,1,2,1", 1), (4, "1,1,2,2", 1), (2, "1,1,2,1", 0)])
-def test_distributed_block_multigrid(nranks, grid, peer):
+@pytest.mark.parametrize("nranks,grid,peer,pc", [(2, "1,1,1,2", 1, 0), (2, "1,1,2,1", 1, 0), (4, "1,1,2,2", 1, 0), (2, "1,1,2,1", 0, 0), (2, "1,1,1,2", 1, 1)])
+def test_distributed_block_multigrid(nranks, grid, peer, pc):
     """BASELINE config 5's "multi-RHS coarse grid" on a lattice partitioned over real ranks: batched coarse null-vector setup and the
     block multigrid behind invertMultiSrcQuda with the ghost zones of block fields filled by the neighbours' pack kernels over NVLink peer
     memory (peer = 1) or exchanged over NCCL (peer = 0); no fallback to one-at-a-time"""
     import torch
     if torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8", QB_MG_MULTISRC="1", QB_PEER_HALO=str(peer))
+    # pc = 1: even-odd hierarchy and QUDA_DIRECT_PC_SOLVE (level-0 smoother of all sources in lock-step on batch fields, whose hops go
+    # member by member through the overlapped halo path on a partitioned lattice)
+    env = dict(os.environ, QB_GRID=grid, QB_LOCAL="8,8,8,8", QB_MG_MULTISRC="1", QB_PEER_HALO=str(peer), QB_MG_PC=str(pc))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
            "--master-port", "29655", os.path.join(ROOT, "tests", "multi_gpu_mg.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
